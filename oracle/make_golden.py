@@ -1,0 +1,170 @@
+"""Generate tests/golden/*.npz by executing the REFERENCE'S OWN SOURCES (test infrastructure only).
+
+Run in the build container (needs /root/reference, which does not exist on the GPU box):
+
+    python oracle/make_golden.py
+
+``/root/reference/model.py`` and ``utils.py`` are imported unmodified; TensorFlow / Keras / pyscipopt (absent here)
+are replaced by the torch-backed stand-ins under ``oracle/tf_shim``.  What the fixtures therefore pin is everything
+the reference's Python source decides -- model wiring (which tensor feeds which convolution, receiving side, concat
+order), variable creation order and shapes (the ``save_state`` stream), the pre-norm pretraining protocol and
+Chan-merge arithmetic, and ``load_batch``'s offset arithmetic and casts.  The arithmetic *inside* each TF op is the
+shim's restatement of TF semantics (see oracle/gcnn_oracle.py header: parity against TensorFlow itself is unpinned).
+
+Outputs (all small):
+  batch_tiny.npz       3 'tiny' samples -> reference ``load_batch`` outputs (bit-exact integer contract)
+  fwd_<case>.npz       inputs, fp64 scores / loss / flat gradient (stored as fp32), fp32-run scores
+  pretrain_tiny.npz    batches + pre-norm parameters after the reference's pretraining loop
+  state_stream.pkl     the weights every fixture uses, written by the reference's own ``save_state`` (62 arrays)
+"""
+import gzip
+import os
+import pickle
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REFERENCE = os.environ.get("GCNN_REFERENCE", "/root/reference")
+sys.path.insert(0, os.path.join(HERE, "tf_shim"))
+sys.path.insert(0, REFERENCE)
+sys.path.insert(0, ROOT)
+
+import tensorflow as tf  # noqa: E402  (the shim)
+from tensorflow import keras  # noqa: E402
+
+import gcnn_oracle as orc  # noqa: E402
+from gcnn_cut_selector_b200 import synth  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def reference_model(params: dict, dtype):
+    """Instantiate the reference GCNN over the shim and load ``params`` positionally (like restore_state)."""
+    tf.set_float_dtype(dtype)
+    keras.reset_name_counters()
+    import model as ref_model
+    m = ref_model.GCNN()
+    variables = m.variables
+    assert len(variables) == len(orc.PARAM_SPECS), (len(variables), len(orc.PARAM_SPECS))
+    for v, (name, shape, trainable) in zip(variables, orc.PARAM_SPECS):
+        assert tuple(v.shape) == tuple(shape) and v.trainable == trainable, (v.name, v.shape, name, shape)
+        v.assign(params[name].to(dtype))
+    assert [v.name for v in variables] == m.variables_topological_order
+    return m, ref_model
+
+
+def write_sample_files(samples, folder):
+    files = []
+    for i, (state, imp) in enumerate(samples):
+        path = os.path.join(folder, f"sample_{i}.pkl")
+        with gzip.open(path, "wb") as fh:
+            pickle.dump({"data": [state, imp]}, fh)
+        files.append(path)
+    return files
+
+
+def run_reference_batch(samples):
+    import utils as ref_utils
+    tf.set_float_dtype(torch.float32)
+    with tempfile.TemporaryDirectory() as tmp:
+        files = write_sample_files(samples, tmp)
+        out = ref_utils.load_batch(files)
+    return [o.numpy() for o in out]
+
+
+def fwd_case(name, samples, params):
+    batch = run_reference_batch(samples)
+    inputs = tuple(batch[:7]) + (int(batch[7].sum()), int(batch[8].sum()), int(batch[9].sum()))
+    targets = batch[10]
+    res = {}
+    for tag, dtype in (("f64", torch.float64), ("f32", torch.float32)):
+        m, _ = reference_model(params, dtype)
+        tin = tuple(tf.convert_to_tensor(x) if isinstance(x, np.ndarray) else tf.convert_to_tensor(np.int32(x))
+                    for x in inputs)
+        pred = m(tin, tf.convert_to_tensor(True))
+        y = torch.as_tensor(targets).to(dtype)
+        loss = ((y - pred) ** 2).mean()  # Keras MeanSquaredError on 1-D tensors (model_trainer.py:271)
+        tv = m.trainable_variables
+        grads = torch.autograd.grad(loss, [v._t for v in tv])
+        res[tag] = (pred.detach().numpy(), float(loss), torch.cat([g.reshape(-1) for g in grads]).numpy())
+    np.savez_compressed(
+        os.path.join(GOLDEN, f"fwd_{name}.npz"),
+        cons=batch[0], cons_ei=batch[1], cons_ef=batch[2], var=batch[3], cut=batch[4], cut_ei=batch[5],
+        cut_ef=batch[6], n_cons=batch[7], n_vars=batch[8], n_cuts=batch[9], targets=targets,
+        scores_f64=res["f64"][0], loss_f64=res["f64"][1], grad_f64_as_f32=res["f64"][2].astype(np.float32),
+        scores_f32=res["f32"][0].astype(np.float32))
+    print(f"fwd_{name}: {len(samples)} samples, N_k={batch[4].shape[0]}, loss={res['f64'][1]:.6e}, "
+          f"f32-vs-f64 score dev={np.abs(res['f32'][0] - res['f64'][0]).max():.2e}")
+
+
+def pretrain_case(params):
+    """The reference's own pretrain loop (model_trainer.py:207-234) over two tiny batches, in fp64 and fp32."""
+    batches = [run_reference_batch(synth.make_samples("tiny", 3, seed0=100 + 10 * b)) for b in range(2)]
+    out = {}
+    for tag, dtype in (("f64", torch.float64), ("f32", torch.float32)):
+        m, ref_model = reference_model(params, dtype)
+        m.pretrain_init()
+        n_layers, order = 0, []
+        torch.set_grad_enabled(False)  # TF eager tensors carry no tape here; keeps np.sqrt(tensor) legal
+        while True:
+            for batch in batches:
+                inputs = tuple(tf.convert_to_tensor(x) for x in batch[:7]) + tuple(
+                    tf.convert_to_tensor(np.int32(batch[i].sum())) for i in (7, 8, 9))
+                if not m.pretrain(inputs, tf.convert_to_tensor(True)):
+                    break
+            res = m.pretrain_next()
+            if res is None:
+                break
+            order.append(res[1])
+            n_layers += 1
+        torch.set_grad_enabled(True)
+        assert n_layers == 11, n_layers
+        non_trainable = [v for v in m.variables if not v.trainable]
+        out[tag] = np.concatenate([v.numpy().reshape(-1) for v in non_trainable])
+        pin = tuple(tf.convert_to_tensor(x) for x in batches[0][:7]) + tuple(
+            tf.convert_to_tensor(np.int32(batches[0][i].sum())) for i in (7, 8, 9))
+        out[tag + "_scores"] = m(pin, tf.convert_to_tensor(False)).detach().numpy()
+    flat = {}
+    for b, batch in enumerate(batches):
+        for i, key in enumerate(["cons", "cons_ei", "cons_ef", "var", "cut", "cut_ei", "cut_ef", "n_cons", "n_vars",
+                                 "n_cuts", "targets"]):
+            flat[f"b{b}_{key}"] = batch[i]
+    np.savez_compressed(os.path.join(GOLDEN, "pretrain_tiny.npz"), prenorm_f64=out["f64"],
+                        prenorm_f32=out["f32"].astype(np.float32), scores_f64=out["f64_scores"],
+                        layer_order=np.asarray(order), **flat)
+    print("pretrain_tiny: 11 layers; order:", order)
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    params = orc.init_params(seed=12345, dtype=torch.float32)  # weights live in fp32, like the reference's
+    # the weights fixture IS the save_state stream written by the reference's own method (model.py:47-56)
+    m, _ = reference_model(params, torch.float32)
+    m.save_state(os.path.join(GOLDEN, "state_stream.pkl"))
+
+    # batching contract: raw samples + what reference load_batch makes of them
+    samples = synth.make_samples("tiny", 3, seed0=0)
+    samples[1] = synth.shuffle_edges(samples[1], 5)
+    batch = run_reference_batch(samples)
+    with open(os.path.join(GOLDEN, "batch_tiny_samples.pkl"), "wb") as fh:
+        pickle.dump(samples, fh)
+    np.savez_compressed(os.path.join(GOLDEN, "batch_tiny.npz"), **{f"out{i}": o for i, o in enumerate(batch)})
+    print("batch_tiny dtypes:", [str(o.dtype) for o in batch])
+
+    fwd_case("tiny3", samples, params)
+    fwd_case("mini2", synth.make_samples("mini", 2, seed0=40), params)
+    iso = synth.make_samples("tiny", 2, seed0=60)
+    # a sample with an edge-less cut side and isolated nodes: scatter must leave zero rows (model.py:568-569)
+    (c, ce, v, k, ke), imp = iso[0]
+    keep = ke["indices"][0] != 1
+    iso[0] = ((c, ce, v, k, {"indices": ke["indices"][:, keep], "values": ke["values"][keep]}), imp)
+    fwd_case("isolated", iso, params)
+    pretrain_case(params)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,3 @@
+"""Import stub so the reference's utils.py (which annotates with pyscipopt types) can be imported for its
+``load_batch``; SCIP itself is absent.  Test infrastructure only."""
+from . import scip  # noqa: F401
