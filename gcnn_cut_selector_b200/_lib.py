@@ -1,0 +1,105 @@
+"""ctypes binding of libgcnn_b200.so (include/gcnn_b200.h).  No CPU fallback: a missing library is a hard error."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libgcnn_b200.so")
+
+OK, INVALID, CUDA_ERROR, OOM = 0, 1, 2, 3
+N_TRAINABLE, N_PRENORM, N_ARRAYS, N_PRENORM_LAYERS = 93121, 58, 62, 11
+
+
+class GcnnError(RuntimeError):
+    """CUDA-side failure reported by the library (status GCNN_CUDA_ERROR)."""
+
+
+class InvalidArgumentError(ValueError):
+    """Bad argument or edge index out of range -- what TF-CPU's tf.gather raises in the reference (model.py:564)."""
+
+
+class ResourceExhaustedError(MemoryError):
+    """The batch does not fit on the device.  Stands in for ``tf.errors.ResourceExhaustedError``, which the
+    reference's loops catch to skip a batch (model_trainer.py:224-227, 308-311; model_tester.py:229-232)."""
+
+
+class Batch(C.Structure):
+    """``gcnn_batch``: the model input 10-tuple as raw pointers + sizes."""
+    _fields_ = [("cons_feats", C.c_void_p), ("cons_edge_inds", C.c_void_p), ("cons_edge_feats", C.c_void_p),
+                ("var_feats", C.c_void_p), ("cut_feats", C.c_void_p), ("cut_edge_inds", C.c_void_p),
+                ("cut_edge_feats", C.c_void_p), ("n_cons", C.c_int64), ("n_vars", C.c_int64), ("n_cuts", C.c_int64),
+                ("n_cons_edges", C.c_int64), ("n_cut_edges", C.c_int64)]
+
+
+_P, _I64, _I, _F = C.c_void_p, C.c_int64, C.c_int, C.c_float
+_BP = C.POINTER(Batch)
+
+# name -> (restype, argtypes); every symbol include/gcnn_b200.h declares
+SIGNATURES = {
+    "gcnn_version": (_I, []),
+    "gcnn_last_error": (C.c_char_p, []),
+    "gcnn_kernel_launches": (_I, []),
+    "gcnn_param_info": (_I, [_I, C.c_char_p, _I, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I), C.POINTER(_I64)]),
+    "gcnn_workspace_create": (_I, [C.POINTER(_P)]),
+    "gcnn_workspace_destroy": (_I, [_P]),
+    "gcnn_workspace_reserve": (_I, [_P, _I64, _I64, _I64, _I64, _I64, _I]),
+    "gcnn_workspace_bytes": (_I64, [_P]),
+    "gcnn_check": (_I, [_P, _P]),
+    "gcnn_build_csr": (_I, [_P, _I, _P, _P, _I64, _I64, _I64, _I, _P]),
+    "gcnn_csr_export": (_I, [_P, _I, _I, _P, _P, _P, _P, _P]),
+    "gcnn_forward": (_I, [_P, _P, _P, _BP, _P, _I, _P]),
+    "gcnn_backward": (_I, [_P, _P, _P, _BP, _P, _P, _P]),
+    "gcnn_mse_seed": (_I, [_P, _P, _I64, _F, _P, _P, _P]),
+    "gcnn_adam_step": (_I, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I64, _P, _P]),
+    "gcnn_forward_backward": (_I, [_P, _P, _P, _BP, _P, _F, _P, _P, _P, _P]),
+    "gcnn_prenorm_stats": (_I, [_P, _P, _P, _BP, _I, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                C.POINTER(C.c_double), _P]),
+    "gcnn_score_host": (_I, [_P, _P, _P, _BP, _P, _P]),
+    "gcnn_train_step_host": (_I, [_P, _P, _P, _P, _P, _BP, _P, _F, _I64, C.POINTER(_F), _P]),
+    "gcnn_edge_forward": (_I, [_P, _P, _P, _I64, _P, _P, _P, _F, _F, _F, _P, _P, _P]),
+    "gcnn_edge_backward": (_I, [_P, _P, _P, _P, _I64, _P, _P, _P, _P, _F, _F, _F, _P, _P, _P]),
+    "gcnn_linear_forward": (_I, [_P, _P, _P, _I64, _I, _I, _P, _P]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the in-tree shared library and declare every prototype; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m gcnn_cut_selector_b200.build` "
+                "(there is no CPU fallback for the GCNN hot path)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the header and the library ever disagree
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(status: int):
+    if status == OK:
+        return
+    msg = load().gcnn_last_error().decode(errors="replace")
+    if status == INVALID:
+        raise InvalidArgumentError(msg)
+    if status == OOM:
+        raise ResourceExhaustedError(msg)
+    raise GcnnError(msg)
+
+
+def param_table():
+    """[(name, shape, trainable, offset)] for the 62 arrays in save_state order (model.py:47-56)."""
+    lib = load()
+    out = []
+    buf = C.create_string_buffer(64)
+    for i in range(N_ARRAYS):
+        rows, cols, off, tr = _I64(), _I64(), _I64(), _I()
+        check(lib.gcnn_param_info(i, buf, 64, C.byref(rows), C.byref(cols), C.byref(tr), C.byref(off)))
+        shape = (rows.value,) if cols.value == 0 else (rows.value, cols.value)
+        out.append((buf.value.decode(), shape, bool(tr.value), off.value))
+    return out

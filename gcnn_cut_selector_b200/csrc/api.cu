@@ -1,0 +1,750 @@
+// C ABI of libgcnn_b200.so: workspace management and whole-model orchestration (see include/gcnn_b200.h).
+//
+// Orchestration follows GCNN.call (model.py:257-300) and PartialGraphConvolution.call (model.py:533-575); the
+// backward is the hand-derived adjoint verified against autograd in the oracle tests.
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+#include <cmath>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+namespace gcnn {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+struct Caps { int64_t nc = 0, nv = 0, nk = 0, ec = 0, ek = 0; int training = 0; };
+
+struct ConvActs { float *A, *B, *H, *cnt, *C, *U1, *Y; };
+
+struct GraphLayouts { EdgeLayout by_left, by_var; };
+
+}  // namespace gcnn
+
+using namespace gcnn;
+
+struct gcnn_workspace {
+    char* arena = nullptr;
+    size_t arena_bytes = 0;
+    Caps cap;
+    // carved pointers
+    int32_t* flags = nullptr;  // [0] sort scratch flag, [1] sticky index error
+    GraphLayouts graph[2];
+    SortScratch sort;
+    float *h1c, *c0, *h1v, *v0, *h1k, *k0;
+    ConvActs conv[3];
+    float *g1, *scores, *d_scores, *loss_sum;
+    // backward
+    float *dk1, *dv1, *dc1, *dk0, *dv0, *dc0, *t_dU1, *t_dC, *t_G, *t_dR, *t_dS, *t_dh1, *t_dg;
+    float* partials[32];
+    float* dw_partials[3];
+    // stats
+    double *st_partials, *st_out, *st_center;
+    // host staging mirrors (device side)
+    float *s_cons, *s_cef, *s_var, *s_cut, *s_kef, *s_targets;
+    int32_t *s_cei, *s_kei;
+    // bookkeeping of the last forward (validated by backward)
+    gcnn_batch last{};
+    int have_activations = 0;
+};
+
+namespace gcnn {
+
+struct Carver {
+    char* base;
+    size_t off = 0;
+    template <typename T>
+    T* take(int64_t n) {
+        off = (off + 255) & ~(size_t)255;
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += sizeof(T) * (size_t)(n > 0 ? n : 0);
+        return p;
+    }
+};
+
+static int64_t max3(int64_t a, int64_t b, int64_t c) { return a > b ? (a > c ? a : c) : (b > c ? b : c); }
+
+// Lays out every buffer for capacities `c`; with base == nullptr only measures.
+static size_t carve(gcnn_workspace* ws, char* base, const Caps& c) {
+    Carver cv{base};
+    const int64_t nc = c.nc, nv = c.nv, nk = c.nk, ec = c.ec, ek = c.ek;
+    const int64_t nmax = max3(nc, nv, nk), emax = ec > ek ? ec : ek;
+    ws->flags = cv.take<int32_t>(64);
+    for (int g = 0; g < 2; ++g) {
+        const int64_t nl = g == 0 ? nc : nk, E = g == 0 ? ec : ek;
+        EdgeLayout* ls[2] = {&ws->graph[g].by_left, &ws->graph[g].by_var};
+        for (int s = 0; s < 2; ++s) {
+            ls[s]->ptr = cv.take<int32_t>((s == 0 ? nl : nv) + 1);
+            ls[s]->other = cv.take<int32_t>(E);
+            ls[s]->val = cv.take<float>(E);
+            ls[s]->perm = cv.take<int32_t>(E);
+        }
+    }
+    ws->sort.key_a = cv.take<int32_t>(emax);
+    ws->sort.val_a = cv.take<int32_t>(emax);
+    ws->sort.key_b = cv.take<int32_t>(emax);
+    ws->sort.val_b = cv.take<int32_t>(emax);
+    ws->sort.hist = cv.take<int32_t>(sort_hist_entries(emax));
+    ws->sort.flags = ws->flags;
+
+    auto rows = [&](int64_t n) { return cv.take<float>(n * D); };
+    ws->h1c = rows(nc); ws->c0 = rows(nc);
+    ws->h1v = rows(nv); ws->v0 = rows(nv);
+    ws->h1k = rows(nk); ws->k0 = rows(nk);
+    const int64_t n_left[3] = {nc, nc, nk}, n_recv[3] = {nc, nv, nk};
+    for (int i = 0; i < 3; ++i) {
+        ConvActs& a = ws->conv[i];
+        a.A = rows(n_left[i]); a.B = rows(nv);
+        a.H = rows(n_recv[i]); a.cnt = rows(n_recv[i]); a.C = rows(n_recv[i]);
+        a.U1 = rows(n_recv[i]); a.Y = rows(n_recv[i]);
+    }
+    ws->g1 = rows(nk);
+    ws->scores = cv.take<float>(nk);
+    ws->d_scores = cv.take<float>(nk);
+    ws->loss_sum = cv.take<float>(64);
+
+    ws->st_partials = cv.take<double>((int64_t)NUM_SMS * 4 * 2 * D);
+    ws->st_out = cv.take<double>(2 * D);
+    ws->st_center = cv.take<double>(D);
+
+    ws->s_cons = cv.take<float>(nc * GCNN_CONS_FEATS);
+    ws->s_cei = cv.take<int32_t>(2 * ec);
+    ws->s_cef = cv.take<float>(ec);
+    ws->s_var = cv.take<float>(nv * GCNN_VAR_FEATS);
+    ws->s_cut = cv.take<float>(nk * GCNN_CUT_FEATS);
+    ws->s_kei = cv.take<int32_t>(2 * ek);
+    ws->s_kef = cv.take<float>(ek);
+    ws->s_targets = cv.take<float>(nk);
+
+    if (c.training) {
+        ws->dk1 = rows(nk); ws->dv1 = rows(nv); ws->dc1 = rows(nc);
+        ws->dk0 = rows(nk); ws->dv0 = rows(nv); ws->dc0 = rows(nc);
+        ws->t_dU1 = rows(nmax); ws->t_dC = rows(nmax); ws->t_G = rows(nmax); ws->t_dR = rows(nmax);
+        ws->t_dS = rows(nmax); ws->t_dh1 = rows(nmax); ws->t_dg = rows(nk);
+        const int64_t parts = wgrad_max_parts();
+        for (int i = 0; i < 32; ++i) ws->partials[i] = cv.take<float>(parts * (2 * D * D + D));
+        for (int i = 0; i < 3; ++i) ws->dw_partials[i] = cv.take<float>((int64_t)edge_backward_max_partials() * D);
+    }
+    return cv.off + 256;
+}
+
+static bool fits(const Caps& cap, int64_t nc, int64_t nv, int64_t nk, int64_t ec, int64_t ek, int training) {
+    return nc <= cap.nc && nv <= cap.nv && nk <= cap.nk && ec <= cap.ec && ek <= cap.ek && training <= cap.training;
+}
+
+static int check_batch(const gcnn_workspace* ws, const gcnn_batch* b, int training) {
+    if (!ws || !b) { set_error("null workspace or batch"); return GCNN_INVALID; }
+    if (b->n_cons < 0 || b->n_vars < 0 || b->n_cuts < 0 || b->n_cons_edges < 0 || b->n_cut_edges < 0) {
+        set_error("negative size in batch"); return GCNN_INVALID;
+    }
+    if (!ws->arena || !fits(ws->cap, b->n_cons, b->n_vars, b->n_cuts, b->n_cons_edges, b->n_cut_edges, training)) {
+        set_error("workspace too small for this batch: call gcnn_workspace_reserve first"); return GCNN_INVALID;
+    }
+    return GCNN_OK;
+}
+
+// ---- forward -----------------------------------------------------------------------------------------------------
+// stop_layer: -1 runs everything; k in [5, 10] returns as soon as the input of pre-norm layer k exists.
+static int forward_impl(gcnn_workspace* ws, const float* p, const float* pn, const gcnn_batch* b, float* scores_out,
+                        int stop_layer, cudaStream_t st) {
+    const int64_t nc = b->n_cons, nv = b->n_vars, nk = b->n_cuts, ec = b->n_cons_edges, ek = b->n_cut_edges;
+
+    // F1: edge layouts.  conv 0 reduces by constraint, conv 1 by variable (both over constraint edges),
+    // conv 2 by cut; the opposite grouping of each edge set serves the backward pass.
+    GCNN_TRY(build_layout(b->cons_edge_inds, b->cons_edge_inds + ec, b->cons_edge_feats, ec, nc, nv, ws->sort,
+                          ws->flags + 1, ws->graph[0].by_left, st));
+    GCNN_TRY(build_layout(b->cons_edge_inds + ec, b->cons_edge_inds, b->cons_edge_feats, ec, nv, nc, ws->sort,
+                          ws->flags + 1, ws->graph[0].by_var, st));
+    GCNN_TRY(build_layout(b->cut_edge_inds, b->cut_edge_inds + ek, b->cut_edge_feats, ek, nk, nv, ws->sort,
+                          ws->flags + 1, ws->graph[1].by_left, st));
+    if (ws->cap.training)
+        GCNN_TRY(build_layout(b->cut_edge_inds + ek, b->cut_edge_inds, b->cut_edge_feats, ek, nv, nk, ws->sort,
+                              ws->flags + 1, ws->graph[1].by_var, st));
+
+    // embeddings (model.py:287-291)
+    struct { const float* x; int K; int shift, scale; const EmbOff* o; float *h1, *out; int64_t n; } emb[3] = {
+        {b->cons_feats, GCNN_CONS_FEATS, PN.cons_shift, PN.cons_scale, &P.cons, ws->h1c, ws->c0, nc},
+        {b->var_feats, GCNN_VAR_FEATS, PN.var_shift, PN.var_scale, &P.var, ws->h1v, ws->v0, nv},
+        {b->cut_feats, GCNN_CUT_FEATS, PN.cut_shift, PN.cut_scale, &P.cut, ws->h1k, ws->k0, nk}};
+    for (auto& e : emb) {
+        GCNN_TRY(embed1_forward(e.x, e.K, pn + e.shift, pn + e.scale, p + e.o->W1, p + e.o->b1, e.h1, e.n, st));
+        LinFwdArgs a{e.h1, nullptr, nullptr, p + e.o->W2, p + e.o->b2, nullptr, e.out, e.n, 64, 1};
+        GCNN_TRY(linear_forward(a, st));
+    }
+
+    // convolutions (model.py:294-296): {left feats, var feats, receiving side, graph, edge pre-norm}
+    const float* left_in[3] = {ws->c0, ws->conv[0].Y, ws->k0};
+    const float* var_in[3] = {ws->v0, ws->v0, ws->conv[1].Y};
+    const int64_t n_left[3] = {nc, nc, nk};
+    const int recv_is_left[3] = {1, 0, 1};
+    const int graph_of[3] = {0, 0, 1};
+    const int fshift[3] = {PN.cedge_shift, PN.cedge_shift, PN.kedge_shift};
+    const int fscale[3] = {PN.cedge_scale, PN.cedge_scale, PN.kedge_scale};
+    for (int i = 0; i < 3; ++i) {
+        const ConvOff& o = P.conv[i];
+        ConvActs& a = ws->conv[i];
+        const int64_t n_recv = recv_is_left[i] ? n_left[i] : nv;
+        const float* recv_in = recv_is_left[i] ? left_in[i] : var_in[i];
+        LinFwdArgs pa{left_in[i], nullptr, nullptr, p + o.Wl, p + o.bl, nullptr, a.A, n_left[i], 64, 0};
+        GCNN_TRY(linear_forward(pa, st));
+        LinFwdArgs pb{var_in[i], nullptr, nullptr, p + o.Wr, nullptr, nullptr, a.B, nv, 64, 0};
+        GCNN_TRY(linear_forward(pb, st));
+        const EdgeLayout& L = recv_is_left[i] ? ws->graph[graph_of[i]].by_left : ws->graph[graph_of[i]].by_var;
+        const float* R = recv_is_left[i] ? a.A : a.B;
+        const float* S = recv_is_left[i] ? a.B : a.A;
+        EdgeScalars sc{pn + fshift[i], pn + fscale[i], pn + PN.conv_sf[i]};
+        if (stop_layer == 5 + 2 * i) return GCNN_OK;
+        GCNN_TRY(edge_forward(L, n_recv, R, S, p + o.we, sc, a.H, a.cnt, st));
+        LinFwdArgs pc{a.H, nullptr, nullptr, p + o.Wf, p + o.bf, L.ptr, a.C, n_recv, 64, 0};
+        GCNN_TRY(linear_forward(pc, st));
+        if (stop_layer == 6 + 2 * i) return GCNN_OK;
+        LinFwdArgs p1{a.C, recv_in, pn + PN.conv_sp[i], p + o.Wo1, p + o.bo1, nullptr, a.U1, n_recv, 128, 1};
+        GCNN_TRY(linear_forward(p1, st));
+        LinFwdArgs p2{a.U1, nullptr, nullptr, p + o.Wo2, p + o.bo2, nullptr, a.Y, n_recv, 64, 1};
+        GCNN_TRY(linear_forward(p2, st));
+    }
+
+    // head (model.py:299-300)
+    LinFwdArgs h1{ws->conv[2].Y, nullptr, nullptr, p + P.Wh1, p + P.bh1, nullptr, ws->g1, nk, 64, 1};
+    GCNN_TRY(linear_forward(h1, st));
+    GCNN_TRY(head2_forward(ws->g1, p + P.Wh2, p + P.bh2, scores_out ? scores_out : ws->scores, nk, st));
+    return GCNN_OK;
+}
+
+// ---- backward ----------------------------------------------------------------------------------------------------
+static int backward_impl(gcnn_workspace* ws, const float* p, const float* pn, const gcnn_batch* b,
+                         const float* d_scores, float* grads, cudaStream_t st) {
+    const int64_t nc = b->n_cons, nv = b->n_vars, nk = b->n_cuts;
+    std::vector<ReduceJob> jobs;
+    int slot = 0;
+    auto add_job = [&](const float* part, int n_parts, int stride, int count, int dst) {
+        jobs.push_back(ReduceJob{part, n_parts, stride, count, dst});
+    };
+    int n_parts = 0;
+
+    // head
+    GCNN_TRY(head2_backward(ws->g1, p + P.Wh2, d_scores, ws->t_dg, ws->partials[slot], &n_parts, nk, st));
+    add_job(ws->partials[slot++], n_parts, D + 1, D + 1, P.Wh2);
+    {
+        LinWgradArgs w{ws->conv[2].Y, nullptr, nullptr, ws->t_dg, nullptr, nullptr, 64, nk, 1, ws->partials[slot],
+                       &n_parts};
+        GCNN_TRY(linear_wgrad(w, st));
+        add_job(ws->partials[slot++], n_parts, D * D + D, D * D + D, P.Wh1);
+        LinDgradArgs d{ws->t_dg, nullptr, p + P.Wh1, 64, ws->dk1, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, nk};
+        GCNN_TRY(linear_dgrad(d, st));
+    }
+
+    const float* left_in[3] = {ws->c0, ws->conv[0].Y, ws->k0};
+    const float* var_in[3] = {ws->v0, ws->v0, ws->conv[1].Y};
+    const int64_t n_left[3] = {nc, nc, nk};
+    const int recv_is_left[3] = {1, 0, 1};
+    const int graph_of[3] = {0, 0, 1};
+    const int fshift[3] = {PN.cedge_shift, PN.cedge_shift, PN.kedge_shift};
+    const int fscale[3] = {PN.cedge_scale, PN.cedge_scale, PN.kedge_scale};
+    float* dY_of[3] = {ws->dc1, ws->dv1, ws->dk1};
+    // gradient sinks of each conv's inputs and whether a previous writer exists (accumulate) -- order: conv 2, 1, 0
+    float* d_left[3] = {ws->dc0, ws->dc1, ws->dk0};
+    float* d_var[3] = {ws->dv0, ws->dv0, ws->dv1};
+    bool dv0_written = false;
+
+    for (int i = 2; i >= 0; --i) {
+        const ConvOff& o = P.conv[i];
+        ConvActs& a = ws->conv[i];
+        const int64_t n_recv = recv_is_left[i] ? n_left[i] : nv;
+        const int64_t n_send = recv_is_left[i] ? nv : n_left[i];
+        const float* recv_in = recv_is_left[i] ? left_in[i] : var_in[i];
+        float* d_recv_in = recv_is_left[i] ? d_left[i] : d_var[i];
+        const float* dY = dY_of[i];
+        const EdgeLayout& Lr = recv_is_left[i] ? ws->graph[graph_of[i]].by_left : ws->graph[graph_of[i]].by_var;
+        const EdgeLayout& Ls = recv_is_left[i] ? ws->graph[graph_of[i]].by_var : ws->graph[graph_of[i]].by_left;
+
+        // output MLP layer 2: Y = relu(U1 Wo2 + bo2)
+        {
+            LinWgradArgs w{a.U1, nullptr, nullptr, dY, a.Y, nullptr, 64, n_recv, 1, ws->partials[slot], &n_parts};
+            GCNN_TRY(linear_wgrad(w, st));
+            add_job(ws->partials[slot++], n_parts, D * D + D, D * D + D, o.Wo2);
+            LinDgradArgs d{dY, a.Y, p + o.Wo2, 64, ws->t_dU1, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, n_recv};
+            GCNN_TRY(linear_dgrad(d, st));
+        }
+        // output MLP layer 1: U1 = relu([s_p C, X_t] Wo1 + bo1)
+        {
+            LinWgradArgs w{a.C, recv_in, pn + PN.conv_sp[i], ws->t_dU1, a.U1, nullptr, 128, n_recv, 1,
+                           ws->partials[slot], &n_parts};
+            GCNN_TRY(linear_wgrad(w, st));
+            add_job(ws->partials[slot++], n_parts, 2 * D * D + D, 2 * D * D + D, o.Wo1);
+            // which earlier op already wrote the receiving input's gradient?
+            int acc2 = 0;
+            if (d_recv_in == ws->dv0) { acc2 = dv0_written ? 1 : 0; dv0_written = true; }
+            LinDgradArgs d{ws->t_dU1, a.U1, p + o.Wo1, 128, ws->t_dC, pn + PN.conv_sp[i], 0, d_recv_in, acc2, nullptr,
+                           nullptr, nullptr, n_recv};
+            GCNN_TRY(linear_dgrad(d, st));
+        }
+        // hoisted feature_module_final: C = H Wf + deg bf;  G = dC Wf^T;  dR = s_f G cnt
+        {
+            LinWgradArgs w{a.H, nullptr, nullptr, ws->t_dC, nullptr, Lr.ptr, 64, n_recv, 1, ws->partials[slot],
+                           &n_parts};
+            GCNN_TRY(linear_wgrad(w, st));
+            add_job(ws->partials[slot++], n_parts, D * D + D, D * D + D, o.Wf);
+            LinDgradArgs d{ws->t_dC, nullptr, p + o.Wf, 64, ws->t_G, nullptr, 0, nullptr, 0, a.cnt, pn + PN.conv_sf[i],
+                           ws->t_dR, n_recv};
+            GCNN_TRY(linear_dgrad(d, st));
+        }
+        // edge backward over the transposed layout
+        const float* R = recv_is_left[i] ? a.A : a.B;
+        const float* S = recv_is_left[i] ? a.B : a.A;
+        EdgeScalars sc{pn + fshift[i], pn + fscale[i], pn + PN.conv_sf[i]};
+        int n_dw = 0;
+        GCNN_TRY(edge_backward(Ls, n_send, R, S, ws->t_G, p + o.we, sc, ws->t_dS, ws->dw_partials[i], &n_dw, st));
+        add_job(ws->dw_partials[i], n_dw, D, D, o.we);
+        const float* dA = recv_is_left[i] ? ws->t_dR : ws->t_dS;
+        const float* dB = recv_is_left[i] ? ws->t_dS : ws->t_dR;
+        // left projection A = X_l Wl + bl
+        {
+            LinWgradArgs w{left_in[i], nullptr, nullptr, dA, nullptr, nullptr, 64, n_left[i], 1, ws->partials[slot],
+                           &n_parts};
+            GCNN_TRY(linear_wgrad(w, st));
+            add_job(ws->partials[slot++], n_parts, D * D + D, D * D + D, o.Wl);
+            // the left input's gradient was already written by the concat branch iff the left side receives
+            LinDgradArgs d{dA, nullptr, p + o.Wl, 64, d_left[i], nullptr, recv_is_left[i] ? 1 : 0, nullptr, 0, nullptr,
+                           nullptr, nullptr, n_left[i]};
+            GCNN_TRY(linear_dgrad(d, st));
+        }
+        // right projection B = X_v Wr
+        {
+            LinWgradArgs w{var_in[i], nullptr, nullptr, dB, nullptr, nullptr, 64, nv, 0, ws->partials[slot], &n_parts};
+            GCNN_TRY(linear_wgrad(w, st));
+            add_job(ws->partials[slot++], n_parts, D * D + D, D * D, o.Wr);
+            int acc = 0;
+            if (d_var[i] == ws->dv0) { acc = dv0_written ? 1 : 0; dv0_written = true; }
+            else acc = 0;  // dv1 has conv 2's right projection as its only writer
+            LinDgradArgs d{dB, nullptr, p + o.Wr, 64, d_var[i], nullptr, acc, nullptr, 0, nullptr, nullptr, nullptr, nv};
+            GCNN_TRY(linear_dgrad(d, st));
+        }
+    }
+
+    // embeddings: out = relu(h1 W2 + b2), h1 = relu(xn W1 + b1)
+    struct { const float* x; int K; int shift, scale; const EmbOff* o; float *h1, *out, *dout; int64_t n; } emb[3] = {
+        {b->cons_feats, GCNN_CONS_FEATS, PN.cons_shift, PN.cons_scale, &P.cons, ws->h1c, ws->c0, ws->dc0, nc},
+        {b->var_feats, GCNN_VAR_FEATS, PN.var_shift, PN.var_scale, &P.var, ws->h1v, ws->v0, ws->dv0, nv},
+        {b->cut_feats, GCNN_CUT_FEATS, PN.cut_shift, PN.cut_scale, &P.cut, ws->h1k, ws->k0, ws->dk0, nk}};
+    for (auto& e : emb) {
+        LinWgradArgs w{e.h1, nullptr, nullptr, e.dout, e.out, nullptr, 64, e.n, 1, ws->partials[slot], &n_parts};
+        GCNN_TRY(linear_wgrad(w, st));
+        add_job(ws->partials[slot++], n_parts, D * D + D, D * D + D, e.o->W2);
+        LinDgradArgs d{e.dout, e.out, p + e.o->W2, 64, ws->t_dh1, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, e.n};
+        GCNN_TRY(linear_dgrad(d, st));
+        GCNN_TRY(embed1_wgrad(e.x, e.K, pn + e.shift, pn + e.scale, ws->t_dh1, e.h1, e.n, ws->partials[slot], &n_parts,
+                              st));
+        add_job(ws->partials[slot++], n_parts, (e.K + 1) * D, (e.K + 1) * D, e.o->W1);
+    }
+    return reduce_partials(jobs.data(), (int)jobs.size(), grads, st);
+}
+
+static int h2d(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+    if (bytes == 0) return GCNN_OK;
+    GCNN_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    return GCNN_OK;
+}
+
+static int stage_batch(gcnn_workspace* ws, const gcnn_batch* hb, gcnn_batch* db, cudaStream_t st) {
+    *db = *hb;
+    GCNN_TRY(h2d(ws->s_cons, hb->cons_feats, sizeof(float) * hb->n_cons * GCNN_CONS_FEATS, st));
+    GCNN_TRY(h2d(ws->s_cei, hb->cons_edge_inds, sizeof(int32_t) * 2 * hb->n_cons_edges, st));
+    GCNN_TRY(h2d(ws->s_cef, hb->cons_edge_feats, sizeof(float) * hb->n_cons_edges, st));
+    GCNN_TRY(h2d(ws->s_var, hb->var_feats, sizeof(float) * hb->n_vars * GCNN_VAR_FEATS, st));
+    GCNN_TRY(h2d(ws->s_cut, hb->cut_feats, sizeof(float) * hb->n_cuts * GCNN_CUT_FEATS, st));
+    GCNN_TRY(h2d(ws->s_kei, hb->cut_edge_inds, sizeof(int32_t) * 2 * hb->n_cut_edges, st));
+    GCNN_TRY(h2d(ws->s_kef, hb->cut_edge_feats, sizeof(float) * hb->n_cut_edges, st));
+    db->cons_feats = ws->s_cons; db->cons_edge_inds = ws->s_cei; db->cons_edge_feats = ws->s_cef;
+    db->var_feats = ws->s_var; db->cut_feats = ws->s_cut; db->cut_edge_inds = ws->s_kei;
+    db->cut_edge_feats = ws->s_kef;
+    return GCNN_OK;
+}
+
+static int read_error_flag(gcnn_workspace* ws, cudaStream_t st) {
+    int32_t flag = 0;
+    GCNN_CUDA_TRY(cudaMemcpyAsync(&flag, ws->flags + 1, sizeof(flag), cudaMemcpyDeviceToHost, st));
+    GCNN_CUDA_TRY(cudaStreamSynchronize(st));
+    if (flag) {
+        GCNN_CUDA_TRY(cudaMemsetAsync(ws->flags + 1, 0, sizeof(int32_t), st));
+        set_error("edge index out of range (InvalidArgument, cf. tf.gather in model.py:564)");
+        return GCNN_INVALID;
+    }
+    return GCNN_OK;
+}
+
+}  // namespace gcnn
+
+// =====================================================================================================================
+extern "C" {
+
+int gcnn_version(void) { return 100; }
+const char* gcnn_last_error(void) { return g_err; }
+int gcnn_kernel_launches(void) { return g_launches.load(); }
+
+int gcnn_param_info(int index, char* name, int name_cap, int64_t* rows, int64_t* cols, int* trainable,
+                    int64_t* offset) {
+    struct Info { const char* name; int rows, cols, trainable, offset; };
+    static std::vector<Info> table = [] {
+        std::vector<Info> t;
+        static char names[GCNN_N_ARRAYS][64];
+        int n = 0;
+        auto add = [&](const char* a, const char* b, int r, int c, int tr, int off) {
+            snprintf(names[n], sizeof(names[n]), "%s%s", a, b);
+            t.push_back(Info{names[n], r, c, tr, off});
+            ++n;
+        };
+        auto emb = [&](const char* nm, int f, const EmbOff& o, int sh, int sc) {
+            add(nm, "/prenorm/shift", f, 0, 0, sh); add(nm, "/prenorm/scale", f, 0, 0, sc);
+            add(nm, "_1/kernel", f, D, 1, o.W1); add(nm, "_1/bias", D, 0, 1, o.b1);
+            add(nm, "_2/kernel", D, D, 1, o.W2); add(nm, "_2/bias", D, 0, 1, o.b2);
+        };
+        emb("cons_emb", GCNN_CONS_FEATS, P.cons, PN.cons_shift, PN.cons_scale);
+        add("cons_edge", "/prenorm/shift", 1, 0, 0, PN.cedge_shift); add("cons_edge", "/prenorm/scale", 1, 0, 0, PN.cedge_scale);
+        emb("var_emb", GCNN_VAR_FEATS, P.var, PN.var_shift, PN.var_scale);
+        emb("cut_emb", GCNN_CUT_FEATS, P.cut, PN.cut_shift, PN.cut_scale);
+        add("cut_edge", "/prenorm/shift", 1, 0, 0, PN.kedge_shift); add("cut_edge", "/prenorm/scale", 1, 0, 0, PN.kedge_scale);
+        const char* cn[3] = {"cons_conv", "var_conv", "cut_conv"};
+        for (int i = 0; i < 3; ++i) {
+            const ConvOff& o = P.conv[i];
+            add(cn[i], "_feat_left/kernel", D, D, 1, o.Wl); add(cn[i], "_feat_left/bias", D, 0, 1, o.bl);
+            add(cn[i], "_feat_edge/kernel", 1, D, 1, o.we);
+            add(cn[i], "_feat_right/kernel", D, D, 1, o.Wr);
+            add(cn[i], "_final/prenorm/scale", 1, 0, 0, PN.conv_sf[i]);
+            add(cn[i], "_feat_final/kernel", D, D, 1, o.Wf); add(cn[i], "_feat_final/bias", D, 0, 1, o.bf);
+            add(cn[i], "_post/prenorm/scale", 1, 0, 0, PN.conv_sp[i]);
+            add(cn[i], "_out_1/kernel", 2 * D, D, 1, o.Wo1); add(cn[i], "_out_1/bias", D, 0, 1, o.bo1);
+            add(cn[i], "_out_2/kernel", D, D, 1, o.Wo2); add(cn[i], "_out_2/bias", D, 0, 1, o.bo2);
+        }
+        add("out_1", "/kernel", D, D, 1, P.Wh1); add("out_1", "/bias", D, 0, 1, P.bh1);
+        add("out_2", "/kernel", D, 1, 1, P.Wh2); add("out_2", "/bias", 1, 0, 1, P.bh2);
+        return t;
+    }();
+    if (index < 0 || index >= (int)table.size()) { set_error("param index out of range"); return GCNN_INVALID; }
+    const Info& it = table[index];
+    if (name && name_cap > 0) { strncpy(name, it.name, name_cap - 1); name[name_cap - 1] = 0; }
+    if (rows) *rows = it.rows;
+    if (cols) *cols = it.cols;  // 0 = one-dimensional array
+    if (trainable) *trainable = it.trainable;
+    if (offset) *offset = it.offset;
+    return GCNN_OK;
+}
+
+int gcnn_workspace_create(gcnn_workspace** out) {
+    if (!out) { set_error("null out pointer"); return GCNN_INVALID; }
+    gcnn_workspace* ws = new (std::nothrow) gcnn_workspace();
+    if (!ws) { set_error("host allocation failed"); return GCNN_OOM; }
+    *out = ws;
+    return GCNN_OK;
+}
+
+int gcnn_workspace_destroy(gcnn_workspace* ws) {
+    if (!ws) return GCNN_OK;
+    if (ws->arena) cudaFree(ws->arena);
+    delete ws;
+    return GCNN_OK;
+}
+
+int gcnn_workspace_reserve(gcnn_workspace* ws, int64_t nc, int64_t nv, int64_t nk, int64_t ec, int64_t ek,
+                           int training) {
+    if (!ws || nc < 0 || nv < 0 || nk < 0 || ec < 0 || ek < 0) { set_error("bad reserve arguments"); return GCNN_INVALID; }
+    training = training ? 1 : 0;
+    if (ws->arena && fits(ws->cap, nc, nv, nk, ec, ek, training)) return GCNN_OK;
+    Caps c = ws->cap;
+    c.nc = nc > c.nc ? nc : c.nc; c.nv = nv > c.nv ? nv : c.nv; c.nk = nk > c.nk ? nk : c.nk;
+    c.ec = ec > c.ec ? ec : c.ec; c.ek = ek > c.ek ? ek : c.ek; c.training = training > c.training ? training : c.training;
+    gcnn_workspace probe;
+    const size_t bytes = carve(&probe, nullptr, c);
+    GCNN_CUDA_TRY(cudaDeviceSynchronize());
+    if (ws->arena) { cudaFree(ws->arena); ws->arena = nullptr; ws->arena_bytes = 0; ws->cap = Caps(); }
+    char* mem = nullptr;
+    cudaError_t err = cudaMalloc(&mem, bytes);
+    if (err != cudaSuccess) {
+        cudaGetLastError();
+        set_error("workspace of %zu bytes does not fit on the device: %s", bytes, cudaGetErrorString(err));
+        return err == cudaErrorMemoryAllocation ? GCNN_OOM : GCNN_CUDA_ERROR;
+    }
+    ws->arena = mem;
+    ws->arena_bytes = bytes;
+    ws->cap = c;
+    ws->have_activations = 0;
+    carve(ws, mem, c);
+    GCNN_CUDA_TRY(cudaMemset(ws->flags, 0, sizeof(int32_t) * 64));
+    return GCNN_OK;
+}
+
+int64_t gcnn_workspace_bytes(const gcnn_workspace* ws) { return ws ? (int64_t)ws->arena_bytes : 0; }
+
+int gcnn_check(gcnn_workspace* ws, void* stream) {
+    if (!ws || !ws->arena) { set_error("workspace not reserved"); return GCNN_INVALID; }
+    return read_error_flag(ws, (cudaStream_t)stream);
+}
+
+int gcnn_build_csr(gcnn_workspace* ws, int which, const int32_t* ei, const float* ef, int64_t E, int64_t n_left,
+                   int64_t n_vars, int need_transposed, void* stream) {
+    if (!ws || !ws->arena || which < 0 || which > 1) { set_error("bad build_csr arguments"); return GCNN_INVALID; }
+    const int64_t cap_left = which == 0 ? ws->cap.nc : ws->cap.nk, cap_e = which == 0 ? ws->cap.ec : ws->cap.ek;
+    if (n_left > cap_left || n_vars > ws->cap.nv || E > cap_e) { set_error("workspace too small"); return GCNN_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    GCNN_TRY(build_layout(ei, ei + E, ef, E, n_left, n_vars, ws->sort, ws->flags + 1, ws->graph[which].by_left, st));
+    if (need_transposed)
+        GCNN_TRY(build_layout(ei + E, ei, ef, E, n_vars, n_left, ws->sort, ws->flags + 1, ws->graph[which].by_var, st));
+    ws->last.n_vars = n_vars;
+    if (which == 0) { ws->last.n_cons = n_left; ws->last.n_cons_edges = E; }
+    else { ws->last.n_cuts = n_left; ws->last.n_cut_edges = E; }
+    return GCNN_OK;
+}
+
+int gcnn_csr_export(gcnn_workspace* ws, int which, int side, int32_t* ptr, int32_t* other, float* val, int32_t* perm,
+                    void* stream) {
+    if (!ws || !ws->arena || which < 0 || which > 1 || side < 0 || side > 1) { set_error("bad export arguments"); return GCNN_INVALID; }
+    const EdgeLayout& L = side == 0 ? ws->graph[which].by_left : ws->graph[which].by_var;
+    const int64_t E = which == 0 ? ws->last.n_cons_edges : ws->last.n_cut_edges;
+    const int64_t n = side == 1 ? ws->last.n_vars : (which == 0 ? ws->last.n_cons : ws->last.n_cuts);
+    cudaStream_t st = (cudaStream_t)stream;
+    auto d2d = [&](void* dst, const void* src, size_t bytes) -> int {
+        if (!dst || bytes == 0) return GCNN_OK;
+        GCNN_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st));
+        return GCNN_OK;
+    };
+    GCNN_TRY(d2d(ptr, L.ptr, sizeof(int32_t) * (n + 1)));
+    GCNN_TRY(d2d(other, L.other, sizeof(int32_t) * E));
+    GCNN_TRY(d2d(val, L.val, sizeof(float) * E));
+    GCNN_TRY(d2d(perm, L.perm, sizeof(int32_t) * E));
+    return GCNN_OK;
+}
+
+int gcnn_forward(gcnn_workspace* ws, const float* params, const float* prenorm, const gcnn_batch* batch,
+                 float* scores_out, int save_activations, void* stream) {
+    GCNN_TRY(check_batch(ws, batch, save_activations ? 1 : 0));
+    GCNN_TRY(forward_impl(ws, params, prenorm, batch, scores_out, -1, (cudaStream_t)stream));
+    ws->last = *batch;
+    ws->have_activations = 1;
+    return GCNN_OK;
+}
+
+int gcnn_backward(gcnn_workspace* ws, const float* params, const float* prenorm, const gcnn_batch* batch,
+                  const float* d_scores, float* grads_out, void* stream) {
+    GCNN_TRY(check_batch(ws, batch, 1));
+    if (!ws->have_activations || ws->last.n_cons != batch->n_cons || ws->last.n_vars != batch->n_vars ||
+        ws->last.n_cuts != batch->n_cuts || ws->last.n_cons_edges != batch->n_cons_edges ||
+        ws->last.n_cut_edges != batch->n_cut_edges) {
+        set_error("gcnn_backward must follow gcnn_forward(save_activations=1) on the same batch");
+        return GCNN_INVALID;
+    }
+    return backward_impl(ws, params, prenorm, batch, d_scores, grads_out, (cudaStream_t)stream);
+}
+
+int gcnn_mse_seed(const float* scores, const float* targets, int64_t n, float scale, float* d_scores,
+                  float* loss_sum_out, void* stream) {
+    return mse_seed(scores, targets, n, scale, d_scores, loss_sum_out, (cudaStream_t)stream);
+}
+
+int gcnn_adam_step(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1,
+                   float beta2, float eps, int64_t step, const float* grad_divisor, void* stream) {
+    if (step < 1) { set_error("adam step counts from 1"); return GCNN_INVALID; }
+    // Keras 2.7 Adam._prepare_local: lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t)
+    const double lr_t = (double)lr * std::sqrt(1.0 - std::pow((double)beta2, (double)step)) /
+                        (1.0 - std::pow((double)beta1, (double)step));
+    return adam_step(params, grads, m, v, n, (float)lr_t, beta1, beta2, eps, grad_divisor, (cudaStream_t)stream);
+}
+
+int gcnn_forward_backward(gcnn_workspace* ws, const float* params, const float* prenorm, const gcnn_batch* batch,
+                          const float* targets, float seed_scale, float* scores_out, float* grads_out,
+                          float* loss_sum_out, void* stream) {
+    GCNN_TRY(check_batch(ws, batch, 1));
+    cudaStream_t st = (cudaStream_t)stream;
+    float* scores = scores_out ? scores_out : ws->scores;
+    GCNN_TRY(forward_impl(ws, params, prenorm, batch, scores, -1, st));
+    ws->last = *batch;
+    ws->have_activations = 1;
+    GCNN_TRY(mse_seed(scores, targets, batch->n_cuts, seed_scale, ws->d_scores, loss_sum_out ? loss_sum_out : ws->loss_sum,
+                      st));
+    return backward_impl(ws, params, prenorm, batch, ws->d_scores, grads_out, st);
+}
+
+int gcnn_prenorm_stats(gcnn_workspace* ws, const float* params, const float* prenorm, const gcnn_batch* b, int layer,
+                       double* mean_out, double* var_out, double* count_out, void* stream) {
+    GCNN_TRY(check_batch(ws, b, 0));
+    if (layer < 0 || layer >= GCNN_N_PRENORM_LAYERS) { set_error("pre-norm layer index out of range"); return GCNN_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    double host[2 * D];
+    double center[D];
+    auto fetch = [&](int n) -> int {
+        GCNN_CUDA_TRY(cudaMemcpyAsync(host, ws->st_out, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+        GCNN_CUDA_TRY(cudaStreamSynchronize(st));
+        return GCNN_OK;
+    };
+    if (layer <= 4) {  // raw input features: per-column statistics (model.py:410-413 with n_units = K)
+        const float* x; int K; int64_t M;
+        switch (layer) {
+            case 0: x = b->cons_feats; K = GCNN_CONS_FEATS; M = b->n_cons; break;
+            case 1: x = b->cons_edge_feats; K = 1; M = b->n_cons_edges; break;
+            case 2: x = b->var_feats; K = GCNN_VAR_FEATS; M = b->n_vars; break;
+            case 3: x = b->cut_feats; K = GCNN_CUT_FEATS; M = b->n_cuts; break;
+            default: x = b->cut_edge_feats; K = 1; M = b->n_cut_edges; break;
+        }
+        *count_out = (double)M;
+        if (M == 0) { for (int k = 0; k < K; ++k) { mean_out[k] = 0; var_out[k] = 0; } return GCNN_OK; }
+        GCNN_TRY(col_stats(x, M, K, nullptr, ws->st_partials, ws->st_out, st));
+        GCNN_TRY(fetch(2 * K));
+        for (int k = 0; k < K; ++k) center[k] = host[k] / (double)M;
+        GCNN_CUDA_TRY(cudaMemcpyAsync(ws->st_center, center, sizeof(double) * K, cudaMemcpyHostToDevice, st));
+        GCNN_TRY(col_stats(x, M, K, ws->st_center, ws->st_partials, ws->st_out, st));
+        GCNN_TRY(fetch(2 * K));
+        for (int k = 0; k < K; ++k) {
+            const double d = host[k] / (double)M;
+            mean_out[k] = center[k] + d;
+            var_out[k] = host[K + k] / (double)M - d * d;
+        }
+        return GCNN_OK;
+    }
+    GCNN_TRY(forward_impl(ws, params, prenorm, b, nullptr, layer, st));
+    ws->have_activations = 0;
+    const int i = (layer - 5) / 2;
+    const bool is_z = ((layer - 5) % 2) == 0;
+    const int recv_is_left = i != 1;
+    const int64_t n_left = i == 2 ? b->n_cuts : b->n_cons;
+    const int64_t n_recv = recv_is_left ? n_left : b->n_vars;
+    ConvActs& a = ws->conv[i];
+    if (is_z) {  // all E x 64 joint pre-activations (feature_module_final pre-norm, n_units = 1)
+        const int64_t E = i == 2 ? b->n_cut_edges : b->n_cons_edges;
+        const double n = (double)E * D;
+        *count_out = n;
+        if (E == 0) { mean_out[0] = 0; var_out[0] = 0; return GCNN_OK; }
+        const EdgeLayout& L = recv_is_left ? ws->graph[i == 2 ? 1 : 0].by_left : ws->graph[0].by_var;
+        const float* R = recv_is_left ? a.A : a.B;
+        const float* S = recv_is_left ? a.B : a.A;
+        EdgeScalars sc{prenorm + (i == 2 ? PN.kedge_shift : PN.cedge_shift),
+                       prenorm + (i == 2 ? PN.kedge_scale : PN.cedge_scale), prenorm + PN.conv_sf[i]};
+        GCNN_TRY(edge_z_stats(L, n_recv, R, S, params + P.conv[i].we, sc, 0.0, ws->st_partials, ws->st_out, st));
+        GCNN_TRY(fetch(2));
+        const double c = host[0] / n;
+        GCNN_TRY(edge_z_stats(L, n_recv, R, S, params + P.conv[i].we, sc, c, ws->st_partials, ws->st_out, st));
+        GCNN_TRY(fetch(2));
+        const double d = host[0] / n;
+        mean_out[0] = c + d;
+        var_out[0] = host[1] / n - d * d;
+        return GCNN_OK;
+    }
+    // conv output C [n_recv, 64], all elements (post_conv_module pre-norm, n_units = 1)
+    const double n = (double)n_recv * D;
+    *count_out = n;
+    if (n_recv == 0) { mean_out[0] = 0; var_out[0] = 0; return GCNN_OK; }
+    GCNN_TRY(col_stats(a.C, n_recv, D, nullptr, ws->st_partials, ws->st_out, st));
+    GCNN_TRY(fetch(2 * D));
+    double s = 0;
+    for (int k = 0; k < D; ++k) s += host[k];
+    const double c = s / n;
+    for (int k = 0; k < D; ++k) center[k] = c;
+    GCNN_CUDA_TRY(cudaMemcpyAsync(ws->st_center, center, sizeof(double) * D, cudaMemcpyHostToDevice, st));
+    GCNN_TRY(col_stats(a.C, n_recv, D, ws->st_center, ws->st_partials, ws->st_out, st));
+    GCNN_TRY(fetch(2 * D));
+    double s1 = 0, s2 = 0;
+    for (int k = 0; k < D; ++k) { s1 += host[k]; s2 += host[D + k]; }
+    const double d = s1 / n;
+    mean_out[0] = c + d;
+    var_out[0] = s2 / n - d * d;
+    return GCNN_OK;
+}
+
+int gcnn_score_host(gcnn_workspace* ws, const float* params, const float* prenorm, const gcnn_batch* hb,
+                    float* scores_host, void* stream) {
+    GCNN_TRY(check_batch(ws, hb, 0));
+    cudaStream_t st = (cudaStream_t)stream;
+    gcnn_batch db;
+    GCNN_TRY(stage_batch(ws, hb, &db, st));
+    GCNN_TRY(forward_impl(ws, params, prenorm, &db, ws->scores, -1, st));
+    ws->have_activations = 0;
+    if (hb->n_cuts > 0)
+        GCNN_CUDA_TRY(cudaMemcpyAsync(scores_host, ws->scores, sizeof(float) * hb->n_cuts, cudaMemcpyDeviceToHost, st));
+    return read_error_flag(ws, st);
+}
+
+int gcnn_train_step_host(gcnn_workspace* ws, float* params, const float* prenorm, float* adam_m, float* adam_v,
+                         const gcnn_batch* hb, const float* targets_host, float lr, int64_t step, float* loss_host,
+                         void* stream) {
+    GCNN_TRY(check_batch(ws, hb, 1));
+    cudaStream_t st = (cudaStream_t)stream;
+    gcnn_batch db;
+    GCNN_TRY(stage_batch(ws, hb, &db, st));
+    GCNN_TRY(h2d(ws->s_targets, targets_host, sizeof(float) * hb->n_cuts, st));
+    // gradients land in the first trainable-sized slice of the (otherwise idle) dS scratch? No: keep them separate.
+    float* grads = ws->partials[31];
+    const float scale = hb->n_cuts > 0 ? 1.f / (float)hb->n_cuts : 0.f;
+    GCNN_TRY(gcnn_forward_backward(ws, params, prenorm, &db, ws->s_targets, scale, nullptr, grads, ws->loss_sum, st));
+    GCNN_TRY(gcnn_adam_step(params, grads, adam_m, adam_v, GCNN_N_TRAINABLE, lr, 0.9f, 0.999f, 1e-7f, step, nullptr,
+                            st));
+    float loss_sum = 0.f;
+    GCNN_CUDA_TRY(cudaMemcpyAsync(&loss_sum, ws->loss_sum, sizeof(float), cudaMemcpyDeviceToHost, st));
+    GCNN_TRY(read_error_flag(ws, st));
+    if (loss_host) *loss_host = hb->n_cuts > 0 ? loss_sum / (float)hb->n_cuts : 0.f;
+    return GCNN_OK;
+}
+
+int gcnn_edge_forward(const int32_t* ptr, const int32_t* src, const float* val, int64_t n_recv, const float* R,
+                      const float* S, const float* w_edge, float f_shift, float f_scale, float s_f, float* H,
+                      float* cnt, void* stream) {
+    // scalars travel through a small device buffer so the kernel signature matches the whole-model path
+    cudaStream_t st = (cudaStream_t)stream;
+    float* dev = nullptr;
+    GCNN_CUDA_TRY(cudaMalloc(&dev, 3 * sizeof(float)));
+    const float host[3] = {f_shift, f_scale, s_f};
+    cudaError_t e = cudaMemcpyAsync(dev, host, sizeof(host), cudaMemcpyHostToDevice, st);
+    int rc = GCNN_OK;
+    if (e == cudaSuccess) {
+        EdgeLayout L{const_cast<int32_t*>(ptr), const_cast<int32_t*>(src), const_cast<float*>(val), nullptr};
+        rc = edge_forward(L, n_recv, R, S, w_edge, EdgeScalars{dev, dev + 1, dev + 2}, H, cnt, st);
+    }
+    cudaStreamSynchronize(st);
+    cudaFree(dev);
+    if (e != cudaSuccess) { set_error("scalar upload failed: %s", cudaGetErrorString(e)); return GCNN_CUDA_ERROR; }
+    return rc;
+}
+
+int gcnn_edge_backward(gcnn_workspace* ws, const int32_t* ptr, const int32_t* other, const float* val, int64_t n_send,
+                       const float* R, const float* S, const float* G, const float* w_edge, float f_shift,
+                       float f_scale, float s_f, float* dS, float* dw, void* stream) {
+    if (!ws || !ws->arena || !ws->cap.training) { set_error("edge_backward needs a training workspace"); return GCNN_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    float* dev = nullptr;
+    GCNN_CUDA_TRY(cudaMalloc(&dev, 3 * sizeof(float)));
+    const float host[3] = {f_shift, f_scale, s_f};
+    cudaError_t e = cudaMemcpyAsync(dev, host, sizeof(host), cudaMemcpyHostToDevice, st);
+    int rc = GCNN_OK;
+    if (e == cudaSuccess) {
+        EdgeLayout L{const_cast<int32_t*>(ptr), const_cast<int32_t*>(other), const_cast<float*>(val), nullptr};
+        int n_dw = 0;
+        rc = edge_backward(L, n_send, R, S, G, w_edge, EdgeScalars{dev, dev + 1, dev + 2}, dS, ws->dw_partials[0],
+                           &n_dw, st);
+        if (rc == GCNN_OK) {
+            ReduceJob job{ws->dw_partials[0], n_dw, D, D, 0};
+            rc = reduce_partials(&job, 1, dw, st);
+        }
+    }
+    cudaStreamSynchronize(st);
+    cudaFree(dev);
+    if (e != cudaSuccess) { set_error("scalar upload failed: %s", cudaGetErrorString(e)); return GCNN_CUDA_ERROR; }
+    return rc;
+}
+
+int gcnn_linear_forward(const float* X, const float* W, const float* b, int64_t m, int k, int relu, float* Y,
+                        void* stream) {
+    if (k != 64) { set_error("gcnn_linear_forward: only k = 64 is exposed (k = 128 is the fused concat layer)"); return GCNN_INVALID; }
+    LinFwdArgs a{X, nullptr, nullptr, W, b, nullptr, Y, m, k, relu};
+    return linear_forward(a, (cudaStream_t)stream);
+}
+
+}  // extern "C"

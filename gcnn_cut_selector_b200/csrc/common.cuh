@@ -1,0 +1,189 @@
+// Shared declarations for libgcnn_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "gcnn_b200.h"
+
+namespace gcnn {
+
+constexpr int D = GCNN_EMB;  // embedding width, 64 floats = 256 B per node row
+constexpr int NUM_SMS = 148;
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define GCNN_CUDA_TRY(expr)                                                                 \
+    do {                                                                                    \
+        cudaError_t err__ = (expr);                                                         \
+        if (err__ != cudaSuccess) {                                                         \
+            gcnn::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, __LINE__); \
+            return err__ == cudaErrorMemoryAllocation ? GCNN_OOM : GCNN_CUDA_ERROR;          \
+        }                                                                                   \
+    } while (0)
+
+#define GCNN_LAUNCH_CHECK()                                                                 \
+    do {                                                                                    \
+        gcnn::count_launch();                                                               \
+        cudaError_t err__ = cudaPeekAtLastError();                                          \
+        if (err__ != cudaSuccess) {                                                         \
+            gcnn::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(err__), __FILE__, __LINE__); \
+            return GCNN_CUDA_ERROR;                                                         \
+        }                                                                                   \
+    } while (0)
+
+#define GCNN_TRY(expr)                  \
+    do {                                \
+        int st__ = (expr);              \
+        if (st__ != GCNN_OK) return st__; \
+    } while (0)
+
+__host__ __device__ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- parameter layout: offsets into the flat trainable / pre-norm buffers (reference order, model.py:174-208) ----
+struct EmbOff { int W1, b1, W2, b2; };
+struct ConvOff { int Wl, bl, we, Wr, Wf, bf, Wo1, bo1, Wo2, bo2; };
+struct ParamOff {
+    EmbOff cons, var, cut;
+    ConvOff conv[3];
+    int Wh1, bh1, Wh2, bh2;
+};
+struct PrenormOff {
+    int cons_shift, cons_scale, cedge_shift, cedge_scale, var_shift, var_scale, cut_shift, cut_scale, kedge_shift,
+        kedge_scale;
+    int conv_sf[3], conv_sp[3];
+};
+
+constexpr EmbOff make_emb(int base, int f) { return EmbOff{base, base + f * D, base + f * D + D, base + f * D + D + D * D}; }
+constexpr int emb_size(int f) { return f * D + D + D * D + D; }
+constexpr ConvOff make_conv(int b) {
+    return ConvOff{b, b + 4096, b + 4160, b + 4224, b + 8320, b + 12416, b + 12480, b + 20672, b + 20736, b + 24832};
+}
+constexpr int CONV_SIZE = 24896;
+constexpr ParamOff make_param_off() {
+    ParamOff p{};
+    int o = 0;
+    p.cons = make_emb(o, GCNN_CONS_FEATS); o += emb_size(GCNN_CONS_FEATS);
+    p.var = make_emb(o, GCNN_VAR_FEATS);   o += emb_size(GCNN_VAR_FEATS);
+    p.cut = make_emb(o, GCNN_CUT_FEATS);   o += emb_size(GCNN_CUT_FEATS);
+    for (int i = 0; i < 3; ++i) { p.conv[i] = make_conv(o); o += CONV_SIZE; }
+    p.Wh1 = o; o += D * D;
+    p.bh1 = o; o += D;
+    p.Wh2 = o; o += D;
+    p.bh2 = o; o += 1;
+    return p;
+}
+constexpr ParamOff P = make_param_off();
+static_assert(P.bh2 + 1 == GCNN_N_TRAINABLE, "trainable parameter count");
+constexpr PrenormOff PN = {0, 4, 8, 9, 10, 24, 38, 44, 50, 51, {52, 54, 56}, {53, 55, 57}};
+
+// ---- edge layouts ------------------------------------------------------------------------------------------------
+struct EdgeLayout {   // edges grouped by one endpoint ("owner"), stable in original edge order inside a group
+    int32_t* ptr;     // [n_owner + 1]
+    int32_t* other;   // [E] index of the opposite endpoint
+    float* val;       // [E] raw edge feature
+    int32_t* perm;    // [E] original edge id
+};
+
+struct SortScratch {
+    int32_t *key_a, *val_a, *key_b, *val_b;  // ping-pong pair buffers [E]
+    int32_t* hist;                           // [256 * n_blocks]
+    int32_t* flags;                          // [0] = "already sorted", [1] = "index out of range" (sticky)
+};
+
+int build_layout(const int32_t* keys, const int32_t* others, const float* feats, int64_t E, int64_t n_owner,
+                 int64_t n_other, const SortScratch& sc, int32_t* err_flag, EdgeLayout out, cudaStream_t st);
+int64_t sort_hist_entries(int64_t E);
+
+// ---- edge kernels -------------------------------------------------------------------------------------------------
+struct EdgeScalars {  // device pointers to the scalars so no host sync is needed when they change (pretraining)
+    const float* f_shift;
+    const float* f_scale;
+    const float* s_f;
+};
+int edge_forward(const EdgeLayout& by_recv, int64_t n_recv, const float* R, const float* S, const float* w_edge,
+                 EdgeScalars sc, float* H, float* cnt, cudaStream_t st);
+int edge_backward(const EdgeLayout& by_send, int64_t n_send, const float* R, const float* S, const float* G,
+                  const float* w_edge, EdgeScalars sc, float* dS, float* dw_partials, int* n_partials,
+                  cudaStream_t st);
+int edge_backward_max_partials();
+// sum and sum of squares of (z_e - center) over all E x 64 joint pre-activations (double accumulators)
+int edge_z_stats(const EdgeLayout& by_recv, int64_t n_recv, const float* R, const float* S, const float* w_edge,
+                 EdgeScalars sc, double center, double* partials, double* out2, cudaStream_t st);
+
+// ---- node (dense) kernels -----------------------------------------------------------------------------------------
+enum BiasMode { BIAS_NONE = 0, BIAS_PLAIN = 1, BIAS_DEG = 2 };
+
+struct LinFwdArgs {
+    const float* X;      // [M, 64] (plain) or left half of the concat
+    const float* X2;     // right half of the concat (K = 128) or nullptr
+    const float* x_scale;  // device scalar multiplying X (left half) or nullptr
+    const float* W;      // [K, 64]
+    const float* b;      // [64] or nullptr
+    const int32_t* deg_ptr;  // segment pointer for BIAS_DEG (bias scaled by ptr[m+1]-ptr[m])
+    float* Y;            // [M, 64]
+    int64_t M;
+    int K;               // 64 or 128
+    int relu;
+};
+int linear_forward(const LinFwdArgs& a, cudaStream_t st);
+
+struct LinDgradArgs {
+    const float* dY;       // [M, 64]
+    const float* act;      // [M, 64] saved post-ReLU output; mask dY by act > 0 (nullptr: no mask)
+    const float* W;        // [K, 64]; dX[:, n] = sum_c dYp[:, c] W[n, c]
+    int K;                 // 64 or 128
+    float* dX;             // [M, 64] receives columns 0..63 of dYp W^T
+    const float* dx_scale; // device scalar applied to dX (columns 0..63), or nullptr
+    int accumulate;        // dX += instead of =
+    float* dX2;            // K = 128: columns 64..127 go here
+    int accumulate2;
+    const float* cnt;      // optional second output: dR = s_f * dX * cnt
+    const float* s_f;
+    float* dR;
+    int64_t M;
+};
+int linear_dgrad(const LinDgradArgs& a, cudaStream_t st);
+
+struct LinWgradArgs {
+    const float* X;        // [M, 64] or left half
+    const float* X2;       // right half (K = 128)
+    const float* x_scale;  // device scalar on the left half
+    const float* dY;       // [M, 64]
+    const float* act;      // mask (nullptr: none)
+    const int32_t* deg_ptr;  // bias gradient weighted by segment length (BIAS_DEG)
+    int K;
+    int64_t M;
+    int want_bias;
+    float* partials;       // [n_parts, K*64 + 64]
+    int* n_parts;          // out (host)
+};
+int linear_wgrad(const LinWgradArgs& a, cudaStream_t st);
+int wgrad_max_parts();
+
+// embedding layer 1: h = relu(((x + shift) * scale) W1 + b1), K in {4, 6, 14}
+int embed1_forward(const float* x, int K, const float* shift, const float* scale, const float* W, const float* b,
+                   float* Y, int64_t M, cudaStream_t st);
+int embed1_wgrad(const float* x, int K, const float* shift, const float* scale, const float* dY, const float* act,
+                 int64_t M, float* partials, int* n_parts, cudaStream_t st);
+
+// head layer 2 (64 -> 1) and its backward
+int head2_forward(const float* g, const float* w, const float* b, float* scores, int64_t M, cudaStream_t st);
+int head2_backward(const float* g, const float* w, const float* d_scores, float* dg_pre, float* partials,
+                   int* n_parts, int64_t M, cudaStream_t st);
+
+// deterministic fixed-order reduction of per-CTA partials into the flat gradient
+struct ReduceJob { const float* partials; int n_parts; int stride; int count; int dst; };
+int reduce_partials(const ReduceJob* jobs, int n_jobs, float* grads, cudaStream_t st);
+
+int mse_seed(const float* scores, const float* targets, int64_t n, float scale, float* d_scores, float* loss_sum,
+             cudaStream_t st);
+int adam_step(float* params, const float* grads, float* m, float* v, int64_t n, float lr_t, float beta1, float beta2,
+              float eps, const float* grad_divisor, cudaStream_t st);
+
+// column statistics of a dense [M, K] matrix about `center` (double accumulators): out[0..K) = sum, out[K..2K) = sumsq
+int col_stats(const float* x, int64_t M, int K, const double* center_dev, double* partials, double* out,
+              cudaStream_t st);
+
+}  // namespace gcnn

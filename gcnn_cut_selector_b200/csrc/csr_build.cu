@@ -1,0 +1,237 @@
+// F1: CSR / CSC edge layouts, built once per batch.
+//
+// Replaces the implicit edge order that tf.gather / tf.scatter_nd consume in the reference
+// (model.py:564-569, edge index contract utils.py:102-110, 226-234).  Integer-only and bit-exact with
+// numpy: perm == argsort(keys, kind='stable'), ptr == concatenate([0], cumsum(bincount(keys, minlength=n))).
+//
+// Reference-produced batches have row 0 (constraint / cut index) non-decreasing (csr -> vstack -> tocoo,
+// utils.py:102-104; block-diagonal offsets utils.py:403-407), so grouping by the left node is a pointer build.
+// That is detected ON THE DEVICE (no host sync): every sort kernel early-exits when the "already sorted" flag
+// is set.  Otherwise a stable LSD radix sort (8-bit digits, match.any ranking) orders (key, edge id) pairs.
+#include "common.cuh"
+
+namespace gcnn {
+
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_ITEMS = 16;                         // items per thread per tile
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;   // 4096 pairs per CTA
+constexpr int RADIX = 256;
+
+int64_t sort_hist_entries(int64_t E) { return RADIX * ceil_div(E > 0 ? E : 1, SORT_TILE); }
+
+// flags[0] := 1 if keys are non-decreasing (caller presets 1), err_flag := 1 if any index is out of range.
+__global__ void check_keys_kernel(const int32_t* __restrict__ keys, const int32_t* __restrict__ others, int64_t E,
+                                  int32_t n_owner, int32_t n_other, int32_t* sorted_flag, int32_t* err_flag) {
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    bool unsorted = false, bad = false;
+    if (e < E) {
+        int32_t k = keys[e], o = others[e];
+        bad = (k < 0) | (k >= n_owner) | (o < 0) | (o >= n_other);
+        if (e > 0) unsorted = keys[e - 1] > k;
+    }
+    if (__any_sync(0xffffffffu, unsorted) && (threadIdx.x & 31) == 0) *sorted_flag = 0;
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) *err_flag = 1;
+}
+
+__global__ void set_flag_kernel(int32_t* flag, int32_t v) { *flag = v; }
+
+// Clamp keys into range (so a bad index cannot make later kernels write out of bounds) and pair them with edge ids.
+__global__ void init_pairs_kernel(const int32_t* __restrict__ keys, int64_t E, int32_t n_owner,
+                                  const int32_t* __restrict__ sorted_flag, int32_t* __restrict__ key_out,
+                                  int32_t* __restrict__ val_out) {
+    if (*sorted_flag) return;
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e < E) {
+        int32_t k = keys[e];
+        key_out[e] = min(max(k, 0), n_owner - 1);
+        val_out[e] = (int32_t)e;
+    }
+}
+
+__global__ void __launch_bounds__(SORT_THREADS)
+radix_hist_kernel(const int32_t* __restrict__ key_in, int64_t E, int shift, const int32_t* __restrict__ sorted_flag,
+                  int32_t* __restrict__ hist, int n_blocks) {
+    if (*sorted_flag) return;
+    __shared__ int32_t h[RADIX];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    int64_t base = (int64_t)blockIdx.x * SORT_TILE;
+#pragma unroll 4
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        int64_t e = base + i * SORT_THREADS + threadIdx.x;
+        if (e < E) atomicAdd(&h[(key_in[e] >> shift) & (RADIX - 1)], 1);
+    }
+    __syncthreads();
+    hist[threadIdx.x * n_blocks + blockIdx.x] = h[threadIdx.x];  // digit-major so one scan gives global offsets
+}
+
+// Exclusive scan of n int32 in place, one CTA of 1024 threads (n = 256 * n_blocks is small).
+__global__ void __launch_bounds__(1024)
+exclusive_scan_kernel(int32_t* __restrict__ data, int64_t n, const int32_t* __restrict__ sorted_flag) {
+    if (*sorted_flag) return;
+    __shared__ int32_t warp_sums[32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int64_t per = ceil_div(n, 1024);
+    const int64_t lo = min(n, (int64_t)t * per), hi = min(n, lo + per);
+    int32_t sum = 0;
+    for (int64_t i = lo; i < hi; ++i) sum += data[i];
+    int32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int32_t w = warp_sums[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int32_t v = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += v;
+        }
+        warp_sums[lane] = wi - w;
+    }
+    __syncthreads();
+    int32_t run = warp_sums[warp] + incl - sum;
+    for (int64_t i = lo; i < hi; ++i) {
+        int32_t v = data[i];
+        data[i] = run;
+        run += v;
+    }
+}
+
+// Stable scatter: rank of an item among equal digits = (# in earlier CTAs) + (# in earlier rounds of this CTA)
+// + (# in earlier warps of this round) + (# in lower lanes of this warp), all in original order.
+__global__ void __launch_bounds__(SORT_THREADS)
+radix_scatter_kernel(const int32_t* __restrict__ key_in, const int32_t* __restrict__ val_in, int64_t E, int shift,
+                     const int32_t* __restrict__ sorted_flag, const int32_t* __restrict__ offsets, int n_blocks,
+                     int32_t* __restrict__ key_out, int32_t* __restrict__ val_out) {
+    if (*sorted_flag) return;
+    constexpr int WARPS = SORT_THREADS / 32;
+    __shared__ int32_t running[RADIX];          // global offset of the next item of each digit for this CTA
+    __shared__ int32_t warp_cnt[WARPS][RADIX];  // per-round per-warp digit counts -> exclusive offsets
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    running[t] = offsets[t * n_blocks + blockIdx.x];
+    const int64_t base = (int64_t)blockIdx.x * SORT_TILE;
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        for (int w = 0; w < WARPS; ++w) warp_cnt[w][t] = 0;
+        __syncthreads();
+        const int64_t e = base + i * SORT_THREADS + t;
+        const bool valid = e < E;
+        int32_t k = 0, v = 0, digit = RADIX;  // invalid lanes match only each other
+        if (valid) {
+            k = key_in[e];
+            v = val_in[e];
+            digit = (k >> shift) & (RADIX - 1);
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, digit);
+        const int rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+        if (valid && rank_in_warp == 0) warp_cnt[warp][digit] = __popc(peers);
+        __syncthreads();
+        {   // thread t owns digit t: exclusive prefix over warps, then advance the running offset
+            int32_t acc = 0;
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) {
+                int32_t c = warp_cnt[w][t];
+                warp_cnt[w][t] = acc;
+                acc += c;
+            }
+            // publish after everyone has read `running` for this round -> two-phase via a second sync below
+            __syncthreads();
+            if (valid) {
+                int32_t pos = running[digit] + warp_cnt[warp][digit] + rank_in_warp;
+                key_out[pos] = k;
+                val_out[pos] = v;
+            }
+            __syncthreads();
+            running[t] += acc;
+        }
+        __syncthreads();
+    }
+}
+
+// Position p of the grouped order holds original edge e = perm[p].  Writes ptr (pointer build by boundary detection),
+// the opposite endpoint, the raw feature and the permutation.  Launched with E + 1 threads.
+__global__ void finalize_layout_kernel(const int32_t* __restrict__ keys, const int32_t* __restrict__ others,
+                                       const float* __restrict__ feats, int64_t E, int32_t n_owner,
+                                       int32_t n_other, const int32_t* __restrict__ sorted_flag, const int32_t* __restrict__ sorted_keys,
+                                       const int32_t* __restrict__ sorted_perm, EdgeLayout out) {
+    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p > E) return;
+    const bool presorted = *sorted_flag != 0;
+    auto key_at = [&](int64_t q) -> int32_t {
+        int32_t k = presorted ? keys[q] : sorted_keys[q];
+        return min(max(k, 0), n_owner - 1);
+    };
+    const int32_t k = p < E ? key_at(p) : n_owner;
+    const int32_t prev = p > 0 ? key_at(p - 1) : -1;
+    for (int32_t r = prev + 1; r <= k; ++r) out.ptr[r] = (int32_t)p;
+    if (p < E) {
+        const int32_t e = presorted ? (int32_t)p : sorted_perm[p];
+        out.other[p] = min(max(others[e], 0), n_other - 1);  // clamped; err_flag reports it
+        out.val[p] = feats[e];
+        out.perm[p] = e;
+    }
+}
+
+static int bit_length(int64_t x) {
+    int b = 0;
+    while (x > 0) { ++b; x >>= 1; }
+    return b;
+}
+
+int build_layout(const int32_t* keys, const int32_t* others, const float* feats, int64_t E, int64_t n_owner,
+                 int64_t n_other, const SortScratch& sc, int32_t* err_flag, EdgeLayout out, cudaStream_t st) {
+    if (E < 0 || n_owner < 0 || n_other < 0 || E >= (int64_t)INT32_MAX || n_owner >= (int64_t)INT32_MAX) {
+        set_error("build_layout: sizes out of int32 range");
+        return GCNN_INVALID;
+    }
+    const int threads = 256;
+    int32_t* sorted_flag = sc.flags;
+    set_flag_kernel<<<1, 1, 0, st>>>(sorted_flag, 1);
+    GCNN_LAUNCH_CHECK();
+    if (E > 0) {
+        check_keys_kernel<<<(unsigned)ceil_div(E, threads), threads, 0, st>>>(keys, others, E, (int32_t)n_owner,
+                                                                              (int32_t)n_other, sorted_flag, err_flag);
+        GCNN_LAUNCH_CHECK();
+    }
+    const int32_t* sorted_keys = sc.key_a;
+    const int32_t* sorted_perm = sc.val_a;
+    if (E > 1 && n_owner > 1) {
+        const int n_blocks = (int)ceil_div(E, SORT_TILE);
+        init_pairs_kernel<<<(unsigned)ceil_div(E, threads), threads, 0, st>>>(keys, E, (int32_t)n_owner, sorted_flag,
+                                                                              sc.key_a, sc.val_a);
+        GCNN_LAUNCH_CHECK();
+        int32_t *ka = sc.key_a, *va = sc.val_a, *kb = sc.key_b, *vb = sc.val_b;
+        const int bits = bit_length(n_owner - 1);
+        for (int shift = 0; shift < bits; shift += 8) {
+            radix_hist_kernel<<<n_blocks, SORT_THREADS, 0, st>>>(ka, E, shift, sorted_flag, sc.hist, n_blocks);
+            GCNN_LAUNCH_CHECK();
+            exclusive_scan_kernel<<<1, 1024, 0, st>>>(sc.hist, (int64_t)RADIX * n_blocks, sorted_flag);
+            GCNN_LAUNCH_CHECK();
+            radix_scatter_kernel<<<n_blocks, SORT_THREADS, 0, st>>>(ka, va, E, shift, sorted_flag, sc.hist, n_blocks,
+                                                                    kb, vb);
+            GCNN_LAUNCH_CHECK();
+            int32_t* t;
+            t = ka; ka = kb; kb = t;
+            t = va; va = vb; vb = t;
+        }
+        sorted_keys = ka;
+        sorted_perm = va;
+    } else if (E > 0) {
+        // 0/1 edges or a single owner: any order is sorted; force the presorted path.
+        set_flag_kernel<<<1, 1, 0, st>>>(sorted_flag, 1);
+        GCNN_LAUNCH_CHECK();
+    }
+    if (E == 0) {  // no edges: every segment is empty
+        GCNN_CUDA_TRY(cudaMemsetAsync(out.ptr, 0, sizeof(int32_t) * (size_t)(n_owner + 1), st));
+        return GCNN_OK;
+    }
+    finalize_layout_kernel<<<(unsigned)ceil_div(E + 1, threads), threads, 0, st>>>(
+        keys, others, feats, E, (int32_t)n_owner, (int32_t)n_other, sorted_flag, sorted_keys, sorted_perm, out);
+    GCNN_LAUNCH_CHECK();
+    return GCNN_OK;
+}
+
+}  // namespace gcnn

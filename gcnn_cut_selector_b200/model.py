@@ -1,0 +1,387 @@
+"""``GCNN``: host-side mirror of the reference model class (model.py:136-300) over libgcnn_b200.so.
+
+Same constructor, call signature and method surface the reference's drivers use:
+``GCNN()``; ``model(batched_states, training)`` with the 10-tuple of model.py:283-284 -> flat fp32 ``[n_cuts]``;
+``model.call`` re-assignable, ``model.input_signature``; ``trainable_variables`` / ``variables``;
+``save_state`` / ``restore_state`` (the reference's pickle stream, model.py:47-67);
+``pretrain_init`` / ``pretrain`` / ``pretrain_next`` (model.py:69-133) with ``PreNormLayer`` semantics
+(model.py:384-437).  PyTorch is used for device memory and streams only; all arithmetic runs in the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import pickle
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Batch, InvalidArgumentError, ResourceExhaustedError, check  # noqa: F401
+
+EMB_SIZE, CONS_FEATS, EDGE_FEATS, VAR_FEATS, CUT_FEATS = 64, 4, 1, 14, 6
+
+
+class PreNormException(Exception):
+    """Raised inside ``call`` when an armed pre-norm layer received a batch (model.py:440)."""
+
+
+@dataclass
+class TensorSpec:
+    shape: tuple
+    dtype: object
+
+
+class PreNormLayer:
+    """Host-side state of one pre-norm layer (model.py:303-437); its shift/scale live in ``GCNN.flat_prenorm``."""
+
+    def __init__(self, model: "GCNN", index: int, name: str, n_units: int, shift_off: int | None, scale_off: int):
+        self._model, self.index, self.name, self.n_units = model, index, name, n_units
+        self._shift_off, self._scale_off = shift_off, scale_off
+        self.waiting_updates = False
+        self.received_updates = False
+        self.mean = self.var = self.m2 = self.count = None
+
+    @property
+    def shift(self):
+        if self._shift_off is None:
+            return None
+        return self._model.flat_prenorm[self._shift_off:self._shift_off + self.n_units]
+
+    @property
+    def scale(self):
+        return self._model.flat_prenorm[self._scale_off:self._scale_off + self.n_units]
+
+    def start_updates(self):  # model.py:384-392
+        self.mean, self.var, self.m2, self.count = 0, 0, 0, 0
+        self.waiting_updates, self.received_updates = True, False
+
+    def update_params(self, sample_mean, sample_var, sample_count):
+        """Chan parallel merge in fp32, line by line as model.py:416-423."""
+        f = np.float32
+        sample_mean, sample_var = np.asarray(sample_mean, f), np.asarray(sample_var, f)
+        sample_count = f(sample_count)
+        delta = sample_mean - self.mean
+        self.m2 = self.var * self.count + sample_var * sample_count + delta ** 2 * self.count * sample_count / (
+            self.count + sample_count)
+        self.count = self.count + sample_count
+        self.mean = self.mean + delta * sample_count / self.count
+        self.var = self.m2 / self.count if self.count > 0 else 1
+
+    def stop_updates(self):  # model.py:425-437
+        mean = np.asarray(self.mean, np.float32).reshape(-1)
+        var = np.asarray(self.var, np.float32).reshape(-1)
+        if self._shift_off is not None:
+            self.shift.copy_(torch.from_numpy(-mean))
+        var = np.where(var == 0, np.ones_like(var), var)
+        self.scale.copy_(torch.from_numpy((1 / np.sqrt(var)).astype(np.float32)))
+        self.mean = self.var = self.m2 = self.count = None
+        self.waiting_updates = False
+
+
+class _GCNNFunction(torch.autograd.Function):
+    """Bridges ``tape.gradient`` (model_trainer.py:272) to gcnn_forward / gcnn_backward."""
+
+    @staticmethod
+    def forward(ctx, flat_params, model, dev_inputs):
+        ctx.model, ctx.dev_inputs = model, dev_inputs
+        return model._forward(dev_inputs, save_activations=True)
+
+    @staticmethod
+    def backward(ctx, d_scores):
+        return ctx.model._backward(ctx.dev_inputs, d_scores.contiguous()), None, None
+
+
+class GCNN:
+    """The graph convolutional neural network model (reference: model.py:136-300), B200 implementation."""
+
+    def __init__(self, device=None, seed: int | None = None):
+        self._lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("GCNN needs a CUDA device: the hot path has no CPU fallback")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.name = "gcnn"
+        self.emb_size, self.cons_feats, self.edge_feats = EMB_SIZE, CONS_FEATS, EDGE_FEATS
+        self.var_feats, self.cut_feats = VAR_FEATS, CUT_FEATS
+        self.check_indices = True  # TF-CPU raises on an out-of-range gather index; costs one stream sync per call
+
+        self._table = _lib.param_table()
+        self.flat_params = torch.zeros(_lib.N_TRAINABLE, dtype=torch.float32, device=self.device, requires_grad=True)
+        self.flat_prenorm = torch.zeros(_lib.N_PRENORM, dtype=torch.float32, device=self.device)
+        self.flat_grads = torch.zeros(_lib.N_TRAINABLE, dtype=torch.float32, device=self.device)
+        self._init_weights(seed)
+
+        self.variables_topological_order = [name for name, _, _, _ in self._table]  # model.py:215
+        f32, i32 = torch.float32, torch.int32
+        self.input_signature = [(TensorSpec((None, CONS_FEATS), f32), TensorSpec((2, None), i32),
+                                 TensorSpec((None, EDGE_FEATS), f32), TensorSpec((None, VAR_FEATS), f32),
+                                 TensorSpec((None, CUT_FEATS), f32), TensorSpec((2, None), i32),
+                                 TensorSpec((None, EDGE_FEATS), f32), TensorSpec((), i32), TensorSpec((), i32),
+                                 TensorSpec((), i32)), TensorSpec((), torch.bool)]  # model.py:218-226
+
+        ws = C.c_void_p()
+        check(self._lib.gcnn_workspace_create(C.byref(ws)))
+        self._ws = ws
+        self._prenorm_layers = self._make_prenorm_layers()
+        self.call = self._call  # re-assignable like ``model.call = tf.function(model.call, ...)`` (model_trainer.py:144)
+
+        # optimiser state for the fused train step (Keras Adam, model_trainer.py:131)
+        self.adam_m = torch.zeros_like(self.flat_grads)
+        self.adam_v = torch.zeros_like(self.flat_grads)
+        self.adam_step = 0
+        self._loss_sum = torch.zeros(1, dtype=torch.float32, device=self.device)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_ws", None):
+                self._lib.gcnn_workspace_destroy(self._ws)
+                self._ws = None
+        except Exception:
+            pass
+
+    # ---- parameters ------------------------------------------------------------------------------------------------
+    def _view(self, entry):
+        name, shape, trainable, off = entry
+        n = int(np.prod(shape))
+        base = self.flat_params.detach() if trainable else self.flat_prenorm
+        return base[off:off + n].view(*shape)
+
+    @property
+    def variables(self):
+        """All 62 arrays as views of the flat buffers, in the reference's ``model.variables`` order."""
+        return [self._view(e) for e in self._table]
+
+    @property
+    def trainable_variables(self):
+        return [self._view(e) for e in self._table if e[2]]
+
+    @property
+    def trainable_gradients(self):
+        out = []
+        for name, shape, trainable, off in self._table:
+            if trainable:
+                out.append(self.flat_grads[off:off + int(np.prod(shape))].view(*shape))
+        return out
+
+    def _init_weights(self, seed):
+        """Keras defaults of the reference: orthogonal kernels, zero biases (model.py:175), shift 0 / scale 1
+        (model.py:334, 342)."""
+        gen = torch.Generator().manual_seed(int(seed) if seed is not None else torch.seed() % (2 ** 31))
+        flat = torch.zeros(_lib.N_TRAINABLE)
+        for name, shape, trainable, off in self._table:
+            if trainable and name.endswith("kernel"):
+                big = max(shape)
+                q, r = torch.linalg.qr(torch.randn(big, big, generator=gen))
+                q = q * torch.sign(torch.diagonal(r))
+                flat[off:off + shape[0] * shape[1]] = q[:shape[0], :shape[1]].reshape(-1)
+        pn = torch.zeros(_lib.N_PRENORM)
+        for name, shape, trainable, off in self._table:
+            if not trainable and name.endswith("scale"):
+                pn[off:off + shape[0]] = 1.0
+        with torch.no_grad():
+            self.flat_params.copy_(flat)
+            self.flat_prenorm.copy_(pn)
+
+    def save_state(self, path: str):
+        """model.py:47-56: one ``pickle.dump(ndarray)`` per variable in ``variables_topological_order``."""
+        with open(path, "wb") as fh:
+            for v in self.variables:
+                pickle.dump(v.detach().cpu().numpy(), fh)
+
+    def restore_state(self, path: str):
+        """model.py:58-67.  The stream is positional; a shape mismatch fails loudly."""
+        with open(path, "rb") as fh, torch.no_grad():
+            for (name, shape, _, _), v in zip(self._table, self.variables):
+                arr = np.asarray(pickle.load(fh), dtype=np.float32)
+                if tuple(arr.shape) != tuple(shape):
+                    raise ValueError(f"weights stream mismatch at {name}: got {arr.shape}, expected {shape}")
+                v.copy_(torch.from_numpy(arr))
+
+    # ---- inputs ---------------------------------------------------------------------------------------------------
+    def _to_device(self, x, dtype):
+        if not torch.is_tensor(x):
+            x = torch.from_numpy(np.ascontiguousarray(x))
+        return x.to(device=self.device, dtype=dtype, non_blocking=True).contiguous()
+
+    def prepare_inputs(self, inputs):
+        """Move the 10-tuple to the device (fp32 / int32, contiguous) and wrap it as a ``gcnn_batch``."""
+        (cons, cons_ei, cons_ef, var, cut, cut_ei, cut_ef, n_cons, n_vars, n_cuts) = inputs
+        f32, i32 = torch.float32, torch.int32
+        t = [self._to_device(cons, f32), self._to_device(cons_ei, i32), self._to_device(cons_ef, f32),
+             self._to_device(var, f32), self._to_device(cut, f32), self._to_device(cut_ei, i32),
+             self._to_device(cut_ef, f32)]
+        n_cons, n_vars, n_cuts = int(n_cons), int(n_vars), int(n_cuts)
+        if t[0].shape != (n_cons, CONS_FEATS) and not (n_cons == 0 and t[0].numel() == 0):
+            raise InvalidArgumentError(f"cons_feats {tuple(t[0].shape)} vs n_cons {n_cons}")
+        if t[3].numel() != n_vars * VAR_FEATS or t[4].numel() != n_cuts * CUT_FEATS:
+            raise InvalidArgumentError("var_feats / cut_feats do not match n_vars / n_cuts")
+        if t[1].dim() != 2 or t[1].shape[0] != 2 or t[5].dim() != 2 or t[5].shape[0] != 2:
+            raise InvalidArgumentError("edge indices must be [2, E]")
+        e_c, e_k = t[1].shape[1], t[5].shape[1]
+        if t[2].numel() != e_c or t[6].numel() != e_k:
+            raise InvalidArgumentError("edge features must be [E, 1]")
+        b = Batch(t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(), t[4].data_ptr(),
+                  t[5].data_ptr(), t[6].data_ptr(), n_cons, n_vars, n_cuts, e_c, e_k)
+        return b, t
+
+    def reserve(self, batch: Batch, training: bool):
+        check(self._lib.gcnn_workspace_reserve(self._ws, batch.n_cons, batch.n_vars, batch.n_cuts, batch.n_cons_edges,
+                                               batch.n_cut_edges, int(training)))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ---- forward / backward ----------------------------------------------------------------------------------------
+    def _forward(self, dev_inputs, save_activations: bool):
+        batch, _keep = dev_inputs
+        self.reserve(batch, save_activations)
+        scores = torch.empty(batch.n_cuts, dtype=torch.float32, device=self.device)
+        check(self._lib.gcnn_forward(self._ws, self.flat_params.data_ptr(), self.flat_prenorm.data_ptr(),
+                                     C.byref(batch), scores.data_ptr(), int(save_activations), self._stream()))
+        if self.check_indices:
+            check(self._lib.gcnn_check(self._ws, self._stream()))
+        return scores
+
+    def _backward(self, dev_inputs, d_scores):
+        batch, _keep = dev_inputs
+        check(self._lib.gcnn_backward(self._ws, self.flat_params.data_ptr(), self.flat_prenorm.data_ptr(),
+                                      C.byref(batch), d_scores.data_ptr(), self.flat_grads.data_ptr(), self._stream()))
+        return self.flat_grads.clone()
+
+    def _first_armed(self):
+        for layer in self._prenorm_layers:
+            if layer.waiting_updates:
+                return layer
+        return None
+
+    def _call(self, inputs, training=False):
+        """GCNN.call (model.py:257-300).  ``training`` only selects whether activations are kept for a backward
+        pass (the reference threads it through but has no dropout / batch-norm)."""
+        dev_inputs = self.prepare_inputs(inputs)
+        armed = self._first_armed()
+        if armed is not None:  # model.py:372-375: the first armed layer updates its statistics and aborts the call
+            self._update_prenorm(armed, dev_inputs)
+            armed.received_updates = True
+            raise PreNormException
+        training = bool(training)
+        if training and torch.is_grad_enabled() and self.flat_params.requires_grad:
+            return _GCNNFunction.apply(self.flat_params, self, dev_inputs)
+        return self._forward(dev_inputs, save_activations=False)
+
+    def __call__(self, inputs, training=False):
+        return self.call(inputs, training)
+
+    def get_concrete_function(self):
+        """``model.call.get_concrete_function()`` shim (model_benchmarker.py:309-310): returns the bound callable."""
+        return self.call
+
+    # ---- training step (model_trainer.py:269-273) -----------------------------------------------------------------
+    def loss_and_grads(self, inputs, targets, seed_scale: float | None = None):
+        """forward + MeanSquaredError + tape.gradient in one library call.  Returns (loss_sum tensor [1], scores);
+        gradients land in ``flat_grads``.  ``seed_scale`` defaults to 1/n_cuts (mean over all cuts of the batch)."""
+        dev_inputs = inputs if isinstance(inputs, tuple) and isinstance(inputs[0], Batch) else self.prepare_inputs(inputs)
+        batch, _keep = dev_inputs
+        targets = self._to_device(targets, torch.float32)
+        self.reserve(batch, True)
+        scores = torch.empty(batch.n_cuts, dtype=torch.float32, device=self.device)
+        scale = (1.0 / max(batch.n_cuts, 1)) if seed_scale is None else float(seed_scale)
+        check(self._lib.gcnn_forward_backward(self._ws, self.flat_params.data_ptr(), self.flat_prenorm.data_ptr(),
+                                              C.byref(batch), targets.data_ptr(), scale, scores.data_ptr(),
+                                              self.flat_grads.data_ptr(), self._loss_sum.data_ptr(), self._stream()))
+        return self._loss_sum, scores
+
+    def apply_gradients(self, lr: float, grad_divisor: torch.Tensor | None = None,
+                        beta1=0.9, beta2=0.999, eps=1e-7):
+        """Keras ``Adam.apply_gradients`` on the flat buffers (one launch instead of 46)."""
+        self.adam_step += 1
+        div = grad_divisor.data_ptr() if grad_divisor is not None else None
+        check(self._lib.gcnn_adam_step(self.flat_params.data_ptr(), self.flat_grads.data_ptr(), self.adam_m.data_ptr(),
+                                       self.adam_v.data_ptr(), _lib.N_TRAINABLE, lr, beta1, beta2, eps, self.adam_step,
+                                       div, self._stream()))
+
+    def train_step(self, inputs, targets, lr: float):
+        """One optimisation step on device-resident or host inputs; returns the mean loss as a device tensor."""
+        loss_sum, scores = self.loss_and_grads(inputs, targets)
+        self.apply_gradients(lr)
+        return loss_sum / max(scores.numel(), 1), scores
+
+    def train_step_host(self, host_batch: "HostBatch", lr: float) -> float:
+        """End-to-end step from (pinned) host buffers: H2D copies, forward, MSE, backward, Adam, loss back to host."""
+        b = host_batch.batch
+        self.reserve(b, True)
+        self.adam_step += 1
+        loss = C.c_float()
+        check(self._lib.gcnn_train_step_host(self._ws, self.flat_params.data_ptr(), self.flat_prenorm.data_ptr(),
+                                             self.adam_m.data_ptr(), self.adam_v.data_ptr(), C.byref(b),
+                                             host_batch.targets.data_ptr(), lr, self.adam_step, C.byref(loss),
+                                             self._stream()))
+        return float(loss.value)
+
+    def score_host(self, host_batch: "HostBatch") -> np.ndarray:
+        """Cut scoring from host buffers to a host array (the ``get_improvements(state, False).numpy()`` path of
+        model_benchmarker.py:106)."""
+        b = host_batch.batch
+        self.reserve(b, False)
+        out = host_batch.scores
+        check(self._lib.gcnn_score_host(self._ws, self.flat_params.data_ptr(), self.flat_prenorm.data_ptr(),
+                                        C.byref(b), out.data_ptr(), self._stream()))
+        return out.numpy()
+
+    # ---- pre-norm pretraining (model.py:69-133) -------------------------------------------------------------------
+    def _make_prenorm_layers(self):
+        offs = {name: off for name, _, _, off in self._table}
+        spec = [("cons_emb/prenorm", CONS_FEATS, True), ("cons_edge/prenorm", 1, True),
+                ("var_emb/prenorm", VAR_FEATS, True), ("cut_emb/prenorm", CUT_FEATS, True),
+                ("cut_edge/prenorm", 1, True)]
+        for conv in ("cons_conv", "var_conv", "cut_conv"):
+            spec += [(f"{conv}_final/prenorm", 1, False), (f"{conv}_post/prenorm", 1, False)]
+        return [PreNormLayer(self, i, name, n, offs[name + "/shift"] if has_shift else None, offs[name + "/scale"])
+                for i, (name, n, has_shift) in enumerate(spec)]
+
+    def _update_prenorm(self, layer: PreNormLayer, dev_inputs):
+        batch, _keep = dev_inputs
+        self.reserve(batch, False)
+        mean = (C.c_double * 64)()
+        var = (C.c_double * 64)()
+        count = C.c_double()
+        check(self._lib.gcnn_prenorm_stats(self._ws, self.flat_params.data_ptr(), self.flat_prenorm.data_ptr(),
+                                           C.byref(batch), layer.index, mean, var, C.byref(count), self._stream()))
+        n = layer.n_units
+        layer.update_params(np.array(mean[:n]), np.array(var[:n]), count.value)
+
+    def pretrain_init(self):
+        for layer in self._prenorm_layers:
+            layer.start_updates()
+
+    def pretrain_next(self):
+        for layer in self._prenorm_layers:
+            if layer.waiting_updates and layer.received_updates:
+                layer.stop_updates()
+                return layer, f"{self.name}/{layer.name}"
+        return None
+
+    def pretrain(self, *args, **kwargs) -> bool:
+        try:
+            with torch.no_grad():
+                self.call(*args, **kwargs)
+            return False
+        except PreNormException:
+            return True
+
+
+class HostBatch:
+    """A batch in pinned host memory plus its ``gcnn_batch`` of HOST pointers, for the ``*_host`` entry points."""
+
+    def __init__(self, batch11):
+        (cons, cons_ei, cons_ef, var, cut, cut_ei, cut_ef, n_cons, n_vars, n_cuts, targets) = batch11
+        pin = lambda a, dt: torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=dt))).pin_memory()
+        self.tensors = [pin(cons, np.float32), pin(cons_ei, np.int32), pin(cons_ef, np.float32), pin(var, np.float32),
+                        pin(cut, np.float32), pin(cut_ei, np.int32), pin(cut_ef, np.float32)]
+        self.targets = pin(targets, np.float32)
+        nc, nv, nk = int(np.sum(n_cons)), int(np.sum(n_vars)), int(np.sum(n_cuts))
+        self.scores = torch.empty(nk, dtype=torch.float32).pin_memory()
+        t = self.tensors
+        self.batch = Batch(t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(), t[4].data_ptr(),
+                           t[5].data_ptr(), t[6].data_ptr(), nc, nv, nk, t[1].shape[1], t[5].shape[1])
+        self.n_graphs = int(np.size(n_cons))
+        self.h2d_bytes = sum(x.numel() * x.element_size() for x in self.tensors) + self.targets.numel() * 4

@@ -1,0 +1,148 @@
+/*
+ * gcnn_b200.h -- C ABI of libgcnn_b200.so: the B200 (sm_100a) implementation of the GCNN message-passing hot path
+ * of stefanvanberkum/gcnn-cut-selector (reference: model.py, utils.py:339-426, model_trainer.py:259-273).
+ *
+ * The reference has no FFI of its own (pure Python over TensorFlow); every entry point below names the reference
+ * interface it replaces.  Conventions:
+ *   - plain pointers and sizes only; all `const float*` / `const int32_t*` arguments are DEVICE pointers unless the
+ *     function name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - every function returns an int status: GCNN_OK, GCNN_INVALID (bad argument / index out of range, the analogue
+ *     of TF-CPU's InvalidArgumentError from tf.gather, model.py:564), GCNN_CUDA_ERROR (see gcnn_last_error()),
+ *     GCNN_OOM (the analogue of tf.errors.ResourceExhaustedError, model_trainer.py:308 -- callers skip the batch);
+ *   - hot calls never allocate and never synchronise; only gcnn_workspace_reserve(), the *_host entry points,
+ *     gcnn_check() and gcnn_prenorm_stats() synchronise;
+ *   - the caller owns every tensor; the library owns only the workspace.
+ *
+ * Parameter layout: trainable parameters live in ONE flat fp32 buffer of GCNN_N_TRAINABLE floats, in the reference's
+ * `trainable_variables` order (model.py:174-208, 486-508); the 58 non-trainable pre-norm values (PreNormLayer
+ * shift/scale, model.py:335-343) live in a second flat buffer.  gcnn_param_info() enumerates all 62 arrays in the
+ * order of the reference's save_state stream (model.py:47-56).
+ */
+#ifndef GCNN_B200_H
+#define GCNN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCNN_OK 0
+#define GCNN_INVALID 1
+#define GCNN_CUDA_ERROR 2
+#define GCNN_OOM 3
+
+#define GCNN_EMB 64          /* model.py:167 */
+#define GCNN_CONS_FEATS 4    /* model.py:168 */
+#define GCNN_EDGE_FEATS 1    /* model.py:169 */
+#define GCNN_VAR_FEATS 14    /* model.py:170 */
+#define GCNN_CUT_FEATS 6     /* model.py:171 */
+#define GCNN_N_TRAINABLE 93121
+#define GCNN_N_PRENORM 58
+#define GCNN_N_ARRAYS 62
+#define GCNN_N_PRENORM_LAYERS 11
+
+typedef struct gcnn_workspace gcnn_workspace;
+
+/* The model input 10-tuple (model.py:257-284; batching contract utils.py:339-426).  Edge indices are [2, E] int32,
+ * row 0 = constraint / cut index, row 1 = variable index (utils.py:110, 234).  Edge features are [E, 1]. */
+typedef struct gcnn_batch {
+    const float* cons_feats;        /* [n_cons, 4]  */
+    const int32_t* cons_edge_inds;  /* [2, n_cons_edges] */
+    const float* cons_edge_feats;   /* [n_cons_edges, 1] */
+    const float* var_feats;         /* [n_vars, 14] */
+    const float* cut_feats;         /* [n_cuts, 6]  */
+    const int32_t* cut_edge_inds;   /* [2, n_cut_edges] */
+    const float* cut_edge_feats;    /* [n_cut_edges, 1] */
+    int64_t n_cons, n_vars, n_cuts; /* totals (model_trainer.py:259-261) */
+    int64_t n_cons_edges, n_cut_edges;
+} gcnn_batch;
+
+/* ---- library ------------------------------------------------------------------------------------------------ */
+int gcnn_version(void);
+const char* gcnn_last_error(void);
+int gcnn_kernel_launches(void); /* kernels launched by this library in this process so far */
+
+/* Enumerates the 62 arrays in save_state order (model.py:47-56, 215).  `offset` is into the trainable buffer when
+ * *trainable != 0, else into the pre-norm buffer. */
+int gcnn_param_info(int index, char* name, int name_cap, int64_t* rows, int64_t* cols, int* trainable,
+                    int64_t* offset);
+
+/* ---- workspace ---------------------------------------------------------------------------------------------- */
+int gcnn_workspace_create(gcnn_workspace** ws);
+int gcnn_workspace_destroy(gcnn_workspace* ws);
+/* Grow the arena so a batch of these sizes fits (training != 0 also reserves saved activations and backward
+ * scratch).  Synchronises and may cudaMalloc; GCNN_OOM if the device cannot hold it. */
+int gcnn_workspace_reserve(gcnn_workspace* ws, int64_t n_cons, int64_t n_vars, int64_t n_cuts,
+                           int64_t n_cons_edges, int64_t n_cut_edges, int training);
+int64_t gcnn_workspace_bytes(const gcnn_workspace* ws);
+/* Synchronise `stream` and report deferred errors (GCNN_INVALID if any edge index was out of range). */
+int gcnn_check(gcnn_workspace* ws, void* stream);
+
+/* ---- F1: CSR / CSC edge layout (replaces the implicit edge order tf.gather / tf.scatter_nd consume,
+ *      model.py:564-569).  which: 0 = constraint edges, 1 = cut edges.  Stable counting/radix sort, bit-exact with
+ *      numpy argsort(kind='stable') / bincount / cumsum.  Already-sorted sides (reference data, utils.py:102-104)
+ *      skip the sort on the device. */
+int gcnn_build_csr(gcnn_workspace* ws, int which, const int32_t* edge_inds, const float* edge_feats, int64_t n_edges,
+                   int64_t n_left, int64_t n_vars, int need_transposed, void* stream);
+/* Copy the built layout to caller device buffers (tests): side 0 = grouped by left node, 1 = grouped by variable.
+ * ptr [n+1], other [E] (index of the opposite endpoint), val [E], perm [E] (original edge id).  NULLs are skipped. */
+int gcnn_csr_export(gcnn_workspace* ws, int which, int side, int32_t* ptr, int32_t* other, float* val, int32_t* perm,
+                    void* stream);
+
+/* ---- whole model (GCNN.call, model.py:257-300) ---------------------------------------------------------------- */
+/* scores_out: [n_cuts] device.  save_activations != 0 keeps what gcnn_backward needs.  Builds the edge layouts. */
+int gcnn_forward(gcnn_workspace* ws, const float* params, const float* prenorm, const gcnn_batch* batch,
+                 float* scores_out, int save_activations, void* stream);
+/* tape.gradient (model_trainer.py:272): d_scores [n_cuts] device -> grads_out [GCNN_N_TRAINABLE] device (written,
+ * not accumulated).  Must follow gcnn_forward(save_activations=1) on the same workspace and batch. */
+int gcnn_backward(gcnn_workspace* ws, const float* params, const float* prenorm, const gcnn_batch* batch,
+                  const float* d_scores, float* grads_out, void* stream);
+/* MeanSquaredError + its gradient seed (model_trainer.py:271): d_scores = 2 (p - y) * scale, loss_sum_out[0] =
+ * sum (y - p)^2 (device scalar).  scale = 1/n for the single-process mean; 1 for data-parallel (see adam). */
+int gcnn_mse_seed(const float* scores, const float* targets, int64_t n, float scale, float* d_scores,
+                  float* loss_sum_out, void* stream);
+/* Keras Adam (model_trainer.py:131, 273; epsilon 1e-7 outside the bias correction).  If grad_divisor != NULL the
+ * gradient is divided by *grad_divisor (device scalar: the all-reduced global cut count) before use. */
+int gcnn_adam_step(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1,
+                   float beta2, float eps, int64_t step, const float* grad_divisor, void* stream);
+/* forward + MSE + backward in one call; grads_out/loss_sum_out as above; scores_out optional (may be NULL). */
+int gcnn_forward_backward(gcnn_workspace* ws, const float* params, const float* prenorm, const gcnn_batch* batch,
+                          const float* targets, float seed_scale, float* scores_out, float* grads_out,
+                          float* loss_sum_out, void* stream);
+
+/* ---- pre-norm pretraining (PreNormLayer.update_params, model.py:394-423) ------------------------------------- */
+/* Runs the forward up to pre-norm layer `layer` (0..10 in the order BaseModel.pretrain_next_rec visits them,
+ * model.py:100-117) and returns that layer's batch statistics on the HOST: mean[n_units], var[n_units] (population
+ * variance) and the sample count.  n_units is 4/1/14/6/1 for layers 0-4 and 1 for the conv layers.  Synchronises. */
+int gcnn_prenorm_stats(gcnn_workspace* ws, const float* params, const float* prenorm, const gcnn_batch* batch,
+                       int layer, double* mean_out, double* var_out, double* count_out, void* stream);
+
+/* ---- host-buffer entry points (what model_benchmarker.py:91-106 and model_trainer.py:269-273 do with numpy in,
+ *      numpy out).  All pointers in `host_batch` and targets/scores are HOST pointers (pinned for async copies). */
+int gcnn_score_host(gcnn_workspace* ws, const float* params, const float* prenorm, const gcnn_batch* host_batch,
+                    float* scores_host, void* stream);
+int gcnn_train_step_host(gcnn_workspace* ws, float* params, const float* prenorm, float* adam_m, float* adam_v,
+                         const gcnn_batch* host_batch, const float* targets_host, float lr, int64_t step,
+                         float* loss_host, void* stream);
+
+/* ---- per-op entry points (unit parity tests; same kernels the whole-model calls launch) ---------------------- */
+/* H[t] = sum_{e in seg(t)} relu(s_f * (R[t] + f_e * w + S[src_e])), cnt[t] = number of active terms per feature.
+ * ptr/src/val describe segments grouped by the receiving node.  f_e = (val + f_shift) * f_scale. */
+int gcnn_edge_forward(const int32_t* ptr, const int32_t* src, const float* val, int64_t n_recv, const float* R,
+                      const float* S, const float* w_edge, float f_shift, float f_scale, float s_f, float* H,
+                      float* cnt, void* stream);
+/* dS[s] = sum_{e in seg(s)} s_f * 1[s_f z_e > 0] * G[t_e]; dw = sum_e f_e dz_e.  Segments grouped by the SENDING
+ * node s; t_e = other[e] is the receiving node. */
+int gcnn_edge_backward(gcnn_workspace* ws, const int32_t* ptr, const int32_t* other, const float* val, int64_t n_send,
+                       const float* R, const float* S, const float* G, const float* w_edge, float f_shift,
+                       float f_scale, float s_f, float* dS, float* dw, void* stream);
+/* Y = act(X W + b): X [m, k] (k in {64, 128}), W [k, 64]; relu != 0 applies ReLU; b may be NULL. */
+int gcnn_linear_forward(const float* X, const float* W, const float* b, int64_t m, int k, int relu, float* Y,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCNN_B200_H */

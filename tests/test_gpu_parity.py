@@ -1,0 +1,402 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden fixtures.
+
+Tolerances (BASELINE.json north_star): edge indexing / offsets bit-exact; fp32 logits and gradients within 1e-5
+relative to the max-abs of the tensor, against the fp64 oracle on identical inputs and weights.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import gcnn_oracle as orc
+from gcnn_cut_selector_b200 import batching, synth
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def model(golden_dir):
+    from gcnn_cut_selector_b200 import GCNN
+    m = GCNN(device="cuda:0", seed=0)
+    m.restore_state(os.path.join(golden_dir, "state_stream.pkl"))
+    return m
+
+
+@pytest.fixture(scope="module")
+def oracle64(golden_dir):
+    return orc.OracleGCNN(orc.restore_state(os.path.join(golden_dir, "state_stream.pkl"), dtype=torch.float64),
+                          dtype=torch.float64)
+
+
+def rel_err(got, want):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    return np.abs(got - want).max() / max(np.abs(want).max(), 1e-30)
+
+
+def golden_inputs(z, prefix=""):
+    g = lambda k: z[prefix + k]
+    return (g("cons"), g("cons_ei"), g("cons_ef"), g("var"), g("cut"), g("cut_ei"), g("cut_ef"),
+            int(g("n_cons").sum()), int(g("n_vars").sum()), int(g("n_cuts").sum()))
+
+
+def assert_grads_close(flat_got, grads_ref: dict, tol=TOL):
+    flat_got = np.asarray(flat_got, np.float64)
+    gmax = max(float(g.abs().max()) for g in grads_ref.values())
+    o = 0
+    for name, shape in orc.TRAINABLE:
+        k = int(np.prod(shape))
+        ref = grads_ref[name].reshape(-1).numpy().astype(np.float64)
+        # per-tensor max-abs scale; tensors whose whole gradient is tiny are held to the global scale
+        scale = max(np.abs(ref).max(), 1e-3 * gmax)
+        err = np.abs(flat_got[o:o + k] - ref).max() / scale
+        assert err <= tol, f"{name}: rel err {err:.3e}"
+        o += k
+
+
+# ---- F1: CSR / CSC build, bit-exact -------------------------------------------------------------------------------
+def _csr_case(model, ei, ef, n_left, n_vars):
+    from gcnn_cut_selector_b200._lib import check
+    lib, dev = model._lib, model.device
+    E = ei.shape[1]
+    check(lib.gcnn_workspace_reserve(model._ws, n_left, n_vars, 1, E, 1, 1))
+    d_ei = torch.from_numpy(np.ascontiguousarray(ei.astype(np.int32))).to(dev)
+    d_ef = torch.from_numpy(np.ascontiguousarray(ef.astype(np.float32))).to(dev)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    check(lib.gcnn_build_csr(model._ws, 0, d_ei.data_ptr(), d_ef.data_ptr(), E, n_left, n_vars, 1, st))
+    for side, n_owner in ((0, n_left), (1, n_vars)):
+        ptr = torch.empty(n_owner + 1, dtype=torch.int32, device=dev)
+        other = torch.empty(E, dtype=torch.int32, device=dev)
+        val = torch.empty(E, dtype=torch.float32, device=dev)
+        perm = torch.empty(E, dtype=torch.int32, device=dev)
+        check(lib.gcnn_csr_export(model._ws, 0, side, ptr.data_ptr(), other.data_ptr(), val.data_ptr(),
+                                  perm.data_ptr(), st))
+        check(lib.gcnn_check(model._ws, st))
+        keys = ei[side].astype(np.int64)
+        want_perm = np.argsort(keys, kind="stable")
+        want_ptr = np.concatenate([[0], np.cumsum(np.bincount(keys, minlength=n_owner))])
+        np.testing.assert_array_equal(ptr.cpu().numpy(), want_ptr.astype(np.int32))
+        np.testing.assert_array_equal(perm.cpu().numpy(), want_perm.astype(np.int32))
+        np.testing.assert_array_equal(other.cpu().numpy(), ei[1 - side][want_perm].astype(np.int32))
+        np.testing.assert_array_equal(val.cpu().numpy(), ef.astype(np.float32)[want_perm])
+
+
+@pytest.mark.parametrize("case", ["sorted", "shuffled", "empty", "single", "one_owner", "isolated", "big", "hub"])
+def test_csr_build_bit_exact(model, case):
+    rng = np.random.default_rng(11)
+    if case == "sorted":
+        (c, ce, v, k, ke), _ = synth.make_sample("setcov", 3)
+        ei, ef, nl, nv = ce["indices"], ce["values"][:, 0], 500, 1000
+    elif case == "shuffled":
+        (c, ce, v, k, ke), _ = synth.shuffle_edges(synth.make_sample("setcov", 4), 1)
+        ei, ef, nl, nv = ce["indices"], ce["values"][:, 0], 500, 1000
+    elif case == "empty":
+        ei, ef, nl, nv = np.zeros((2, 0), np.int64), np.zeros(0), 5, 7
+    elif case == "single":
+        ei, ef, nl, nv = np.array([[3], [2]]), np.array([0.5]), 5, 7
+    elif case == "one_owner":
+        ei, ef, nl, nv = np.vstack([np.zeros(300, np.int64), rng.integers(0, 50, 300)]), rng.standard_normal(300), 1, 50
+    elif case == "isolated":  # many owners without edges, long pointer gaps
+        ei = np.vstack([np.sort(rng.choice(100000, 200)), rng.integers(0, 70000, 200)])
+        ef, nl, nv = rng.standard_normal(200), 100000, 70000
+    elif case == "big":  # > 16 bits of key, unsorted on both sides, multiple CTAs and radix passes
+        E = 1_000_003
+        ei, ef, nl, nv = np.vstack([rng.integers(0, 100_000, E), rng.integers(0, 70_001, E)]), rng.standard_normal(E), 100_000, 70_001
+    else:  # one variable adjacent to every row
+        ei = np.vstack([np.repeat(np.arange(3000), 2), np.tile([0, 1], 3000)])
+        ei[1, 1::2] = rng.integers(1, 9, 3000)
+        ef, nl, nv = rng.standard_normal(6000), 3000, 9
+    _csr_case(model, np.asarray(ei), np.asarray(ef), nl, nv)
+
+
+def test_out_of_range_index_raises(model, golden_dir):
+    from gcnn_cut_selector_b200 import InvalidArgumentError
+    z = np.load(os.path.join(golden_dir, "fwd_tiny3.npz"))
+    inputs = list(golden_inputs(z))
+    bad = inputs[1].copy()
+    bad[1, 3] = inputs[8]  # == n_vars
+    inputs[1] = bad
+    with pytest.raises(InvalidArgumentError):
+        model(tuple(inputs), False)
+    # the workspace stays usable
+    out = model(golden_inputs(z), False)
+    assert rel_err(out.cpu().numpy(), z["scores_f64"]) <= TOL
+
+
+# ---- per-op parity ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_recv,n_send,E", [(50, 70, 600), (1, 3, 5), (300, 2, 4000), (64, 64, 0)])
+def test_edge_forward_backward_ops(model, n_recv, n_send, E):
+    from gcnn_cut_selector_b200._lib import check
+    lib, dev = model._lib, model.device
+    rng = np.random.default_rng(E + n_recv)
+    recv = np.sort(rng.integers(0, n_recv, E))
+    send = rng.integers(0, n_send, E)
+    f = rng.standard_normal(E).astype(np.float32)
+    R = rng.standard_normal((n_recv, 64)).astype(np.float32)
+    S = rng.standard_normal((n_send, 64)).astype(np.float32)
+    w = rng.standard_normal(64).astype(np.float32)
+    G = rng.standard_normal((n_recv, 64)).astype(np.float32)
+    f_shift, f_scale, s_f = 0.25, 1.5, 0.7
+    # oracle in fp64
+    fe = (f.astype(np.float64) + f_shift) * f_scale
+    z = R.astype(np.float64)[recv] + fe[:, None] * w.astype(np.float64) + S.astype(np.float64)[send]
+    y = np.maximum(s_f * z, 0)
+    H = np.zeros((n_recv, 64)); np.add.at(H, recv, y)
+    cnt = np.zeros((n_recv, 64)); np.add.at(cnt, recv, (y > 0).astype(np.float64))
+    dz = s_f * (s_f * z > 0) * G.astype(np.float64)[recv]
+    dS = np.zeros((n_send, 64)); np.add.at(dS, send, dz)
+    dw = (fe[:, None] * dz).sum(0)
+
+    t = lambda a, dt=torch.float32: torch.from_numpy(np.ascontiguousarray(a)).to(dev, dt)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ptr = np.concatenate([[0], np.cumsum(np.bincount(recv, minlength=n_recv))]).astype(np.int32)
+    d_ptr, d_src, d_val = t(ptr, torch.int32), t(send.astype(np.int32), torch.int32), t(f)
+    dR_, dS_, dw_, dG = t(R), t(S), t(w), t(G)
+    dH = torch.empty(n_recv, 64, device=dev); dcnt = torch.empty(n_recv, 64, device=dev)
+    check(lib.gcnn_edge_forward(d_ptr.data_ptr(), d_src.data_ptr(), d_val.data_ptr(), n_recv, dR_.data_ptr(),
+                                dS_.data_ptr(), dw_.data_ptr(), f_shift, f_scale, s_f, dH.data_ptr(), dcnt.data_ptr(),
+                                st))
+    torch.cuda.synchronize()
+    if E:
+        assert rel_err(dH.cpu().numpy(), H) <= 2e-6
+    else:
+        assert np.all(dH.cpu().numpy() == 0)
+    np.testing.assert_array_equal(dcnt.cpu().numpy(), cnt.astype(np.float32))
+
+    # transposed layout for the backward
+    order = np.argsort(send, kind="stable")
+    ptr_s = np.concatenate([[0], np.cumsum(np.bincount(send, minlength=n_send))]).astype(np.int32)
+    check(lib.gcnn_workspace_reserve(model._ws, 8, 8, 8, 8, 8, 1))
+    d_ptr_s, d_oth, d_val_s = t(ptr_s, torch.int32), t(recv[order].astype(np.int32), torch.int32), t(f[order])
+    out_dS = torch.empty(n_send, 64, device=dev); out_dw = torch.empty(64, device=dev)
+    check(lib.gcnn_edge_backward(model._ws, d_ptr_s.data_ptr(), d_oth.data_ptr(), d_val_s.data_ptr(), n_send,
+                                 dR_.data_ptr(), dS_.data_ptr(), dG.data_ptr(), dw_.data_ptr(), f_shift, f_scale, s_f,
+                                 out_dS.data_ptr(), out_dw.data_ptr(), st))
+    torch.cuda.synchronize()
+    if E:
+        assert rel_err(out_dS.cpu().numpy(), dS) <= 2e-6
+        assert rel_err(out_dw.cpu().numpy(), dw) <= 2e-6
+    else:
+        assert np.all(out_dS.cpu().numpy() == 0) and np.all(out_dw.cpu().numpy() == 0)
+
+
+@pytest.mark.parametrize("m", [1, 127, 128, 129, 1000])
+def test_linear_forward_op(model, m):
+    from gcnn_cut_selector_b200._lib import check
+    rng = np.random.default_rng(m)
+    X, W, b = rng.standard_normal((m, 64)), rng.standard_normal((64, 64)), rng.standard_normal(64)
+    dev = model.device
+    t = lambda a: torch.from_numpy(a.astype(np.float32)).to(dev)
+    dX, dW, db = t(X), t(W), t(b)
+    Y = torch.empty(m, 64, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    check(model._lib.gcnn_linear_forward(dX.data_ptr(), dW.data_ptr(), db.data_ptr(), m, 64, 1, Y.data_ptr(), st))
+    torch.cuda.synchronize()
+    ref = np.maximum(X.astype(np.float32).astype(np.float64) @ W.astype(np.float32).astype(np.float64)
+                     + b.astype(np.float32).astype(np.float64), 0)
+    assert rel_err(Y.cpu().numpy(), ref) <= 2e-6
+
+
+# ---- whole model against the golden fixtures (reference source over the TF shim) ----------------------------------------
+@pytest.mark.parametrize("case", ["tiny3", "mini2", "isolated"])
+def test_forward_matches_golden(model, golden_dir, case):
+    z = np.load(os.path.join(golden_dir, f"fwd_{case}.npz"))
+    for training in (False, True):
+        with torch.no_grad():
+            out = model(golden_inputs(z), training)
+        assert out.shape == z["scores_f64"].shape and out.dtype == torch.float32
+        assert rel_err(out.cpu().numpy(), z["scores_f64"]) <= TOL
+
+
+@pytest.mark.parametrize("case", ["tiny3", "mini2", "isolated"])
+def test_gradients_match_golden(model, golden_dir, case):
+    z = np.load(os.path.join(golden_dir, f"fwd_{case}.npz"))
+    loss_sum, scores = model.loss_and_grads(golden_inputs(z), z["targets"])
+    torch.cuda.synchronize()
+    n = scores.numel()
+    assert abs(float(loss_sum) / n - float(z["loss_f64"])) <= TOL * float(z["loss_f64"])
+    ref = torch.from_numpy(z["grad_f64_as_f32"].astype(np.float64))
+    grads_ref, o = {}, 0
+    for name, shape in orc.TRAINABLE:
+        k = int(np.prod(shape))
+        grads_ref[name] = ref[o:o + k]
+        o += k
+    assert_grads_close(model.flat_grads.cpu().numpy(), grads_ref)
+
+
+def test_autograd_bridge_matches_fused_call(model, golden_dir):
+    z = np.load(os.path.join(golden_dir, "fwd_mini2.npz"))
+    model.loss_and_grads(golden_inputs(z), z["targets"])
+    fused = model.flat_grads.clone()
+    model.flat_params.grad = None
+    pred = model(golden_inputs(z), True)
+    y = torch.from_numpy(z["targets"]).to(model.device)
+    loss = ((y - pred) ** 2).mean()
+    loss.backward()
+    torch.testing.assert_close(model.flat_params.grad, fused, rtol=1e-6, atol=1e-9)
+    model.flat_params.grad = None
+
+
+# ---- the four problem classes at BASELINE shapes, against the fp64 oracle run here -------------------------------------
+@pytest.mark.parametrize("shape,n", [("setcov", 1), ("setcov", 3), ("combauc", 4), ("indset", 4), ("capfac", 1)])
+def test_problem_classes_forward_backward(model, oracle64, shape, n):
+    batch = batching.concat_samples(synth.make_samples(shape, n, seed0=1000 + n))
+    inputs, targets = batching.model_inputs(batch), batch[10]
+    loss_sum, scores = model.loss_and_grads(inputs, targets)
+    torch.cuda.synchronize()
+    loss, pred, grads = orc.loss_and_grads(oracle64, inputs, targets)
+    assert rel_err(scores.cpu().numpy(), pred.numpy()) <= TOL
+    assert abs(float(loss_sum) / scores.numel() - float(loss)) <= TOL * float(loss)
+    assert_grads_close(model.flat_grads.cpu().numpy(), grads)
+
+
+def test_edge_order_invariance_and_determinism(model):
+    samples = synth.make_samples("setcov", 2, seed0=5)
+    base = batching.concat_samples(samples)
+    shuf = batching.concat_samples([synth.shuffle_edges(s, 3 + i) for i, s in enumerate(samples)])
+    with torch.no_grad():
+        a = model(batching.model_inputs(base), False).cpu().numpy()
+        a2 = model(batching.model_inputs(base), False).cpu().numpy()
+        b = model(batching.model_inputs(shuf), False).cpu().numpy()
+    np.testing.assert_array_equal(a, a2)  # fixed reduction order: bit-reproducible
+    # stable sort restores (row, original order) grouping; with distinct columns inside a row the shuffled batch
+    # sums the same terms in a different order only inside segments -> 1e-6
+    assert rel_err(b, a) <= 1e-6
+    model.loss_and_grads(batching.model_inputs(base), base[10])
+    g1 = model.flat_grads.clone()
+    model.loss_and_grads(batching.model_inputs(base), base[10])
+    assert torch.equal(g1, model.flat_grads)
+
+
+def test_batch_equals_single_graph_calls(model):
+    samples = synth.make_samples("combauc", 3, seed0=77)
+    whole = batching.concat_samples(samples)
+    with torch.no_grad():
+        out = model(batching.model_inputs(whole), False).cpu().numpy()
+        parts = [model(batching.model_inputs(batching.concat_samples([s])), False).cpu().numpy() for s in samples]
+    assert rel_err(out, np.concatenate(parts)) <= 1e-6
+
+
+def test_empty_cut_set_and_empty_edges(model, oracle64):
+    (c, ce, v, k, ke), imp = synth.make_sample("mini", 21)
+    empty = {"indices": np.zeros((2, 0), np.int64), "values": np.zeros((0, 1))}
+    batch = batching.concat_samples([((c, ce, v, k, empty), imp)])
+    inputs = batching.model_inputs(batch)
+    loss_sum, scores = model.loss_and_grads(inputs, batch[10])
+    loss, pred, grads = orc.loss_and_grads(oracle64, inputs, batch[10])
+    assert rel_err(scores.cpu().numpy(), pred.numpy()) <= TOL
+    assert_grads_close(model.flat_grads.cpu().numpy(), grads)
+
+
+# ---- train step, pretraining, weights stream -------------------------------------------------------------------------
+def test_adam_train_steps_match_oracle(golden_dir):
+    """(a) the fused Adam kernel against the oracle's Keras-Adam on IDENTICAL gradients (fp32 rounding only);
+    (b) three full train steps against an independent oracle run: losses agree to 1e-5."""
+    from gcnn_cut_selector_b200 import GCNN
+    path = os.path.join(golden_dir, "state_stream.pkl")
+    m = GCNN(device="cuda:0", seed=1)
+    m.restore_state(path)
+    o_same = orc.OracleGCNN(orc.restore_state(path, dtype=torch.float64), dtype=torch.float64)
+    o_free = orc.OracleGCNN(orc.restore_state(path, dtype=torch.float64), dtype=torch.float64)
+    st_same, st_free = orc.AdamState(), orc.AdamState()
+    lr = 1e-3
+    for step in range(3):
+        batch = batching.concat_samples(synth.make_samples("mini", 2, seed0=300 + step))
+        inputs, targets = batching.model_inputs(batch), batch[10]
+        loss, _ = m.train_step(inputs, targets, lr)
+        g = m.flat_grads.cpu().numpy().astype(np.float64)
+        grads, off = {}, 0
+        for name, shape in orc.TRAINABLE:
+            k = int(np.prod(shape))
+            grads[name] = torch.from_numpy(g[off:off + k].reshape(shape))
+            off += k
+        orc.adam_step(o_same, st_same, grads, lr)
+        got = m.flat_params.detach().cpu().numpy().astype(np.float64)
+        want = orc.flatten_trainable(o_same.params).numpy()
+        assert np.abs(got - want).max() <= 5e-7, f"step {step}: {np.abs(got - want).max():.3e}"
+        oloss, _ = orc.train_step(o_free, st_free, inputs, targets, lr)
+        assert abs(float(loss) - float(oloss)) <= 1e-5 * float(oloss)
+
+
+def test_pretrain_protocol_matches_golden(golden_dir):
+    from gcnn_cut_selector_b200 import GCNN
+    z = np.load(os.path.join(golden_dir, "pretrain_tiny.npz"))
+    m = GCNN(device="cuda:0", seed=2)
+    m.restore_state(os.path.join(golden_dir, "state_stream.pkl"))
+    batches = [golden_inputs(z, f"b{b}_") for b in range(2)]
+    m.pretrain_init()
+    n = 0
+    while True:  # model_trainer.py:207-234
+        for b in batches:
+            if not m.pretrain(b, True):
+                break
+        if m.pretrain_next() is None:
+            break
+        n += 1
+    assert n == 11
+    got = m.flat_prenorm.cpu().numpy().astype(np.float64)
+    assert rel_err(got, z["prenorm_f64"]) <= 2e-5
+    with torch.no_grad():
+        out = m(batches[0], False)
+    assert rel_err(out.cpu().numpy(), z["scores_f64"]) <= 5e-5  # scales carry fp32 rounding of the statistics
+
+
+def test_save_restore_roundtrip(model, golden_dir, tmp_path):
+    path = str(tmp_path / "w.pkl")
+    model.save_state(path)
+    assert open(path, "rb").read() == open(os.path.join(golden_dir, "state_stream.pkl"), "rb").read()
+    assert model.variables_topological_order == [n for n, _, _ in orc.PARAM_SPECS]
+    assert len(model.trainable_variables) == 46 and len(model.variables) == 62
+
+
+def test_host_entry_points_match_device_path(golden_dir):
+    from gcnn_cut_selector_b200 import GCNN, HostBatch
+    path = os.path.join(golden_dir, "state_stream.pkl")
+    batch = batching.concat_samples(synth.make_samples("setcov", 2, seed0=9))
+    a, b = GCNN(device="cuda:0", seed=3), GCNN(device="cuda:0", seed=4)
+    a.restore_state(path); b.restore_state(path)
+    hb = HostBatch(batch)
+    with torch.no_grad():
+        dev_scores = a(batching.model_inputs(batch), False).cpu().numpy()
+    np.testing.assert_array_equal(b.score_host(hb), dev_scores)
+    loss_a, _ = a.train_step(batching.model_inputs(batch), batch[10], 1e-3)
+    loss_b = b.train_step_host(hb, 1e-3)
+    assert abs(float(loss_a) - loss_b) <= 1e-6 * abs(loss_b)
+    torch.testing.assert_close(a.flat_params.detach(), b.flat_params.detach(), rtol=0, atol=0)
+
+
+# ---- full BASELINE sizes: size-independent properties -----------------------------------------------------------------
+def test_config2_properties(model):
+    """32 setcov graphs (BASELINE config 2): block-diagonality -> the batch equals its two halves; bit-reproducible."""
+    samples = synth.make_samples("setcov", 32, seed0=2000, n_structures=8)
+    whole = batching.concat_samples(samples)
+    with torch.no_grad():
+        out = model(batching.model_inputs(whole), False)
+        out2 = model(batching.model_inputs(whole), False)
+        halves = [model(batching.model_inputs(batching.concat_samples(samples[i:i + 16])), False) for i in (0, 16)]
+    assert torch.equal(out, out2)
+    assert rel_err(out.cpu().numpy(), torch.cat(halves).cpu().numpy()) <= 1e-6
+    assert torch.isfinite(out).all()
+    # gradient of the whole batch = cut-count-weighted mean of the halves' gradients (linearity of the MSE mean)
+    model.loss_and_grads(batching.model_inputs(whole), whole[10])
+    g = model.flat_grads.clone()
+    acc = torch.zeros_like(g)
+    for i in (0, 16):
+        half = batching.concat_samples(samples[i:i + 16])
+        model.loss_and_grads(batching.model_inputs(half), half[10], seed_scale=1.0 / whole[4].shape[0])
+        acc += model.flat_grads
+    assert rel_err(acc.cpu().numpy(), g.cpu().numpy()) <= 1e-5
+
+
+def test_miplib_scale_forward(model):
+    """BASELINE config 5 (100k x 100k, 1M edges, heavy-tailed rows): finite, reproducible, edge-order invariant."""
+    sample = synth.make_sample("miplib", 5)
+    batch = batching.concat_samples([sample])
+    with torch.no_grad():
+        a = model(batching.model_inputs(batch), False)
+        b = model(batching.model_inputs(batching.concat_samples([synth.shuffle_edges(sample, 1)])), False)
+    assert a.shape == (5000,) and torch.isfinite(a).all()
+    assert rel_err(b.cpu().numpy(), a.cpu().numpy()) <= 1e-5
