@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""Benchmark of the GCNN hot path (BASELINE.json metric: GCNN train graphs/s and edge-messages/s; % of HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--graphs-per-gpu G]
+
+A "step" is one training step (CSR build + forward + MSE + backward + Adam; data-parallel all-reduce when N > 1) on
+one batch of G synthetic setcov-shape graphs per GPU (500 rows x 1000 columns, 25,000 non-zeros, 64 cuts of 100
+non-zeros; offset-concatenated exactly as utils.py:403-407).  G defaults to 32 = BASELINE config 2 per GPU (weak
+scaling); ``--graphs-per-gpu 128 --gpus 8`` is BASELINE config 4 (1,024 graphs/step).
+
+`value`  : graphs/s over all ranks with the batches already resident in HBM, CUDA-event time, max over ranks.
+`e2e`    : the same metric through the host-buffer entry point (pinned host -> device copies of every input each
+           step, loss read back each step).
+`roofline`: the kernel class with the largest share of the step, ALGORITHMIC bytes / CUDA-event time.
+`cpu_baseline` / ``--impl reference``: the TF-equivalent torch-CPU restatement (oracle/) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SETCOV_MSGS_PER_GRAPH = 2 * 25_000 + 6_400  # 2 E_cons + E_cut (three convolutions, model.py:294-296)
+METRIC, UNIT = "gcnn_train_graphs_per_s", "graphs/s"
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=5)
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def make_batches(n_batches: int, graphs: int, seed0: int):
+    from gcnn_cut_selector_b200 import batching, synth
+    out = []
+    for b in range(n_batches):
+        samples = synth.make_samples("setcov", graphs, seed0=seed0 + 1000 * b, n_structures=min(graphs, 8))
+        out.append(batching.concat_samples(samples))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference's CPU implementation of the path: TensorFlow is not installable here, so this is the faithful
+    fp32 torch-CPU restatement (oracle/), full train step, all host threads.  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import gcnn_oracle as orc
+    from gcnn_cut_selector_b200 import batching
+    torch.set_num_threads(os.cpu_count() or 1)
+    graphs = args.graphs_per_gpu
+    batches = make_batches(2, graphs, seed0=0)
+    model = orc.OracleGCNN(orc.init_params(seed=12345, dtype=torch.float32, identity_prenorm=True), dtype=torch.float32)
+    state = orc.AdamState()
+    steps, warmup = max(1, args.steps), max(1, min(args.warmup, 2))
+    for i in range(warmup):
+        orc.train_step(model, state, batching.model_inputs(batches[i % 2]), batches[i % 2][10], 1e-4)
+    t0 = time.perf_counter()
+    done = 0
+    for i in range(steps):
+        orc.train_step(model, state, batching.model_inputs(batches[i % 2]), batches[i % 2][10], 1e-4)
+        done += 1
+        if time.perf_counter() - t0 > 150:  # bounded: keep the whole run within a few minutes
+            break
+    dt = time.perf_counter() - t0
+    value = graphs * done / dt
+    sample = f"{done} train steps of {graphs} setcov graphs (torch-CPU restatement of model.py, fp32, Adam)"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
+            "warmup": warmup, "ms_per_step": 1e3 * dt / done, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"setcov x{graphs} graphs per step, train step on host CPU cores"},
+            "edge_messages_per_s": value * SETCOV_MSGS_PER_GRAPH,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_baseline(model, batch, graphs, budget_s=20.0):
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import gcnn_oracle as orc
+    from gcnn_cut_selector_b200 import batching
+    torch.set_num_threads(os.cpu_count() or 1)
+    params = {}
+    for (name, shape, _, _), v in zip(model._table, model.variables):
+        params[name] = v.detach().cpu().clone()
+    o = orc.OracleGCNN(params, dtype=torch.float32)
+    st = orc.AdamState()
+    inputs, targets = batching.model_inputs(batch), batch[10]
+    orc.train_step(o, st, inputs, targets, 1e-4)  # warm-up
+    t0, n = time.perf_counter(), 0
+    while n < 3 and (n == 0 or time.perf_counter() - t0 < budget_s):
+        orc.train_step(o, st, inputs, targets, 1e-4)
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": graphs * n / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} train steps of one {graphs}-graph setcov batch (faithful fp32 torch-CPU restatement of "
+                      f"model.py incl. per-edge Dense and Adam), {1e3 * dt / n:.0f} ms/step"}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from gcnn_cut_selector_b200 import GCNN, DataParallelTrainer, HostBatch, batching
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    graphs, K, W = args.graphs_per_gpu, args.steps, max(3, args.warmup)
+    lr = 1e-4
+
+    n_rot = 4
+    batches = make_batches(n_rot, graphs, seed0=10_000 * rank)
+    model = GCNN(device=dev, seed=0)
+    model.check_indices = False  # no per-step stream sync in the timed loop; checked once after it
+    trainer = DataParallelTrainer(model, lr) if world > 1 else None
+    if trainer:
+        trainer.broadcast_parameters()
+    host = [HostBatch(b) for b in batches]
+    dev_inputs = [model.prepare_inputs(batching.model_inputs(b)) for b in batches]
+    dev_targets = [torch.from_numpy(b[10]).to(dev) for b in batches]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    lib = model._lib
+
+    def step(i):
+        j = i % n_rot
+        if trainer:
+            trainer.step(dev_inputs[j], dev_targets[j])
+        else:
+            model.loss_and_grads(dev_inputs[j], dev_targets[j])
+            model.apply_gradients(lr)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        step(i)
+    barrier()
+
+    # ---- timed region: K steps, one CUDA-event pair per step, L2 flushed between steps ------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    launches0 = lib.gcnn_kernel_launches()
+    barrier()
+    for i in range(K):
+        flush.fill_(i & 0xFF)
+        ev[i][0].record()
+        step(W + i)
+        ev[i][1].record()
+    barrier()
+    launches = lib.gcnn_kernel_launches() - launches0
+    clocks = sampler.stop()
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    from gcnn_cut_selector_b200._lib import check
+    check(lib.gcnn_check(model._ws, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    # ---- per-kernel-class CUDA-event timing, same K steps again (events around every launch perturb a launch-bound
+    #      step, so this pass is separate from the one `value` comes from) -------------------------------------------
+    ncls = lib.gcnn_profile_num_classes()
+    ms, ln, by = (C.c_double * ncls)(), (C.c_int64 * ncls)(), (C.c_double * ncls)()
+    barrier()
+    lib.gcnn_profile_begin()
+    for i in range(K):
+        flush.fill_(i & 0xFF)
+        step(W + i)
+    check(lib.gcnn_profile_end(ms, ln, by, ncls))
+    peak, peak_src = measured_peak_gbs()
+    classes = []
+    for c in range(ncls):
+        if ln[c] == 0:
+            continue
+        gbs = by[c] / (ms[c] * 1e-3) / 1e9 if ms[c] > 0 else 0.0
+        classes.append({"kernel": lib.gcnn_profile_class_name(c).decode(), "launches_per_step": ln[c] / K,
+                        "ms_per_step": ms[c] / K, "algorithmic_mb_per_step": by[c] / K / 1e6,
+                        "achieved_gbs": gbs, "frac": gbs / peak})
+    kernel_ms = sum(c["ms_per_step"] for c in classes)
+    for c in classes:
+        c["share_of_kernel_time"] = c["ms_per_step"] / kernel_ms if kernel_ms else 0.0
+    top = max(classes, key=lambda c: c["ms_per_step"])
+    roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": top["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": top["frac"], "traffic": None, "peak_source": peak_src,
+                "bytes": "algorithmic bytes per launch (DESIGN.md section 4) / CUDA-event time per launch, "
+                         "events on the launch stream, separate pass of the same K steps"}
+    seg = [c for c in classes if c["kernel"] in ("edge_forward", "edge_backward")]
+    step_bytes = sum(c["algorithmic_mb_per_step"] for c in classes) * 1e6
+    step_roof = {"algorithmic_mb_per_step": step_bytes / 1e6,
+                 "achieved_gbs": step_bytes / (total_ms / K * 1e-3) / 1e9,
+                 "frac": step_bytes / (total_ms / K * 1e-3) / 1e9 / peak}
+
+    # ---- end to end through the host-buffer API: H2D of every input and D2H of the loss inside the timed region ----
+    def e2e_step(i):
+        hb = host[i % n_rot]
+        if trainer:
+            ins = model.prepare_inputs(tuple(hb.tensors) + (hb.batch.n_cons, hb.batch.n_vars, hb.batch.n_cuts))
+            loss = trainer.step(ins, hb.targets)
+            return float(loss.item())
+        return model.train_step_host(hb, lr)
+
+    for i in range(W):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        e2e_step(W + i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+
+    if rank == 0:
+        value = graphs * world * K / (total_ms * 1e-3)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"setcov (500x1000, 25k nnz, 64 cuts) x{graphs} graphs per GPU per step, "
+                                       f"train step = CSR build + fwd + MSE + bwd + Adam"
+                                       + (" + NCCL all-reduce of the flat gradient" if world > 1 else ""),
+                           "graphs_per_step": graphs * world, "parallelism": f"dp{world}",
+                           "l2": "256 MB flush between timed steps; 4 rotating batches"},
+                "edge_messages_per_s": value * SETCOV_MSGS_PER_GRAPH,
+                "clocks": clocks,
+                "e2e": {"value": graphs * world * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": host[0].h2d_bytes,
+                        "d2h_bytes_per_step": 4, "ms_per_step": 1e3 * e2e_s / K},
+                "gpu_launches": launches,
+                "roofline": roofline,
+                "roofline_segmented_reduction": seg,
+                "roofline_step": step_roof,
+                "kernels": classes}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(model, batches[0], graphs)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--graphs-per-gpu", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps == 20:
+            args.steps = 5
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

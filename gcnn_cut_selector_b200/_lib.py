@@ -40,6 +40,10 @@ SIGNATURES = {
     "gcnn_version": (_I, []),
     "gcnn_last_error": (C.c_char_p, []),
     "gcnn_kernel_launches": (_I, []),
+    "gcnn_profile_begin": (_I, []),
+    "gcnn_profile_end": (_I, [C.POINTER(C.c_double), C.POINTER(_I64), C.POINTER(C.c_double), _I]),
+    "gcnn_profile_num_classes": (_I, []),
+    "gcnn_profile_class_name": (C.c_char_p, [_I]),
     "gcnn_param_info": (_I, [_I, C.c_char_p, _I, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I), C.POINTER(_I64)]),
     "gcnn_workspace_create": (_I, [C.POINTER(_P)]),
     "gcnn_workspace_destroy": (_I, [_P]),

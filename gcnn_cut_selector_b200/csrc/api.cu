@@ -23,7 +23,43 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
-void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+struct Profiler {
+    static constexpr int MAX_SCOPES = 8192;
+    bool enabled = false;
+    int n = 0, current = -1;
+    cudaEvent_t ev[MAX_SCOPES][2];
+    int cls[MAX_SCOPES];
+    int launches[MAX_SCOPES];
+    double bytes[MAX_SCOPES];
+    int n_events = 0;  // events created so far (lazily)
+};
+static Profiler g_prof;
+
+void count_launch(int n) {
+    g_launches.fetch_add(n, std::memory_order_relaxed);
+    if (g_prof.enabled && g_prof.current >= 0) g_prof.launches[g_prof.current] += n;
+}
+
+ProfScope::ProfScope(int c, double algorithmic_bytes, cudaStream_t s) : slot(-1), st(s) {
+    if (!g_prof.enabled || g_prof.current >= 0 || g_prof.n >= Profiler::MAX_SCOPES) return;
+    slot = g_prof.n++;
+    while (g_prof.n_events <= slot) {
+        cudaEventCreate(&g_prof.ev[g_prof.n_events][0]);
+        cudaEventCreate(&g_prof.ev[g_prof.n_events][1]);
+        ++g_prof.n_events;
+    }
+    g_prof.cls[slot] = c;
+    g_prof.bytes[slot] = algorithmic_bytes;
+    g_prof.launches[slot] = 0;
+    g_prof.current = slot;
+    cudaEventRecord(g_prof.ev[slot][0], st);
+}
+ProfScope::~ProfScope() {
+    if (slot < 0) return;
+    cudaEventRecord(g_prof.ev[slot][1], st);
+    g_prof.current = -1;
+}
 
 struct Caps { int64_t nc = 0, nv = 0, nk = 0, ec = 0, ek = 0; int training = 0; };
 
@@ -206,7 +242,11 @@ static int forward_impl(gcnn_workspace* ws, const float* p, const float* pn, con
         const float* S = recv_is_left[i] ? a.B : a.A;
         EdgeScalars sc{pn + fshift[i], pn + fscale[i], pn + PN.conv_sf[i]};
         if (stop_layer == 5 + 2 * i) return GCNN_OK;
-        GCNN_TRY(edge_forward(L, n_recv, R, S, p + o.we, sc, a.H, a.cnt, st));
+        // algorithmic bytes (B_F): read both projection tables, 8 B of index + feature per edge and the
+        // segment pointer; write the reduced rows
+        const int64_t E_i = graph_of[i] == 0 ? ec : ek;
+        const double fwd_bytes = 256.0 * (double)(n_left[i] + nv + n_recv) + 8.0 * (double)E_i + 4.0 * (double)(n_recv + 1);
+        GCNN_TRY(edge_forward(L, n_recv, R, S, p + o.we, sc, a.H, a.cnt, st, fwd_bytes));
         LinFwdArgs pc{a.H, nullptr, nullptr, p + o.Wf, p + o.bf, L.ptr, a.C, n_recv, 64, 0};
         GCNN_TRY(linear_forward(pc, st));
         if (stop_layer == 6 + 2 * i) return GCNN_OK;
@@ -306,7 +346,12 @@ static int backward_impl(gcnn_workspace* ws, const float* p, const float* pn, co
         const float* S = recv_is_left[i] ? a.B : a.A;
         EdgeScalars sc{pn + fshift[i], pn + fscale[i], pn + PN.conv_sf[i]};
         int n_dw = 0;
-        GCNN_TRY(edge_backward(Ls, n_send, R, S, ws->t_G, p + o.we, sc, ws->t_dS, ws->dw_partials[i], &n_dw, st));
+        // algorithmic bytes: read G and the receiver table (n_recv rows each) and the sender table, write dS (n_send
+        // rows each), 8 B of index + feature per edge and the segment pointer
+        const int64_t E_i = graph_of[i] == 0 ? b->n_cons_edges : b->n_cut_edges;
+        const double bwd_bytes = 256.0 * (double)(2 * n_recv + 2 * n_send) + 8.0 * (double)E_i + 4.0 * (double)(n_send + 1);
+        GCNN_TRY(edge_backward(Ls, n_send, R, S, ws->t_G, p + o.we, sc, ws->t_dS, ws->dw_partials[i], &n_dw, st,
+                               bwd_bytes));
         add_job(ws->dw_partials[i], n_dw, D, D, o.we);
         const float* dA = recv_is_left[i] ? ws->t_dR : ws->t_dS;
         const float* dB = recv_is_left[i] ? ws->t_dS : ws->t_dR;
@@ -393,6 +438,37 @@ extern "C" {
 int gcnn_version(void) { return 100; }
 const char* gcnn_last_error(void) { return g_err; }
 int gcnn_kernel_launches(void) { return g_launches.load(); }
+
+int gcnn_profile_begin(void) {
+    g_prof.n = 0;
+    g_prof.current = -1;
+    g_prof.enabled = true;
+    return GCNN_OK;
+}
+
+int gcnn_profile_end(double* ms, int64_t* launches, double* bytes, int n_classes) {
+    g_prof.enabled = false;
+    if (n_classes < PROF_NCLASSES) { set_error("profile arrays need %d entries", (int)PROF_NCLASSES); return GCNN_INVALID; }
+    for (int c = 0; c < n_classes; ++c) { ms[c] = 0; launches[c] = 0; bytes[c] = 0; }
+    GCNN_CUDA_TRY(cudaDeviceSynchronize());
+    for (int i = 0; i < g_prof.n; ++i) {
+        float t = 0.f;
+        GCNN_CUDA_TRY(cudaEventElapsedTime(&t, g_prof.ev[i][0], g_prof.ev[i][1]));
+        ms[g_prof.cls[i]] += t;
+        launches[g_prof.cls[i]] += g_prof.launches[i];
+        bytes[g_prof.cls[i]] += g_prof.bytes[i];
+    }
+    g_prof.n = 0;
+    return GCNN_OK;
+}
+
+const char* gcnn_profile_class_name(int c) {
+    static const char* names[PROF_NCLASSES] = {"csr_build", "embed1_forward", "linear_forward", "edge_forward", "head2",
+                                               "linear_dgrad", "linear_wgrad", "embed1_wgrad", "edge_backward",
+                                               "reduce_partials", "mse_seed", "adam", "prenorm_stats"};
+    return (c >= 0 && c < PROF_NCLASSES) ? names[c] : "";
+}
+int gcnn_profile_num_classes(void) { return PROF_NCLASSES; }
 
 int gcnn_param_info(int index, char* name, int name_cap, int64_t* rows, int64_t* cols, int* trainable,
                     int64_t* offset) {

@@ -14,6 +14,18 @@ constexpr int NUM_SMS = 148;
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 
+// ---- optional per-kernel-class timing with CUDA events on the launching stream (bench.py roofline numbers) -------
+enum ProfClass {
+    PROF_CSR = 0, PROF_EMB1_FWD, PROF_LIN_FWD, PROF_EDGE_FWD, PROF_HEAD, PROF_LIN_DGRAD, PROF_LIN_WGRAD,
+    PROF_EMB1_WGRAD, PROF_EDGE_BWD, PROF_REDUCE, PROF_LOSS, PROF_ADAM, PROF_STATS, PROF_NCLASSES
+};
+struct ProfScope {  // records a start/stop event pair around the launches issued while it is alive (if enabled)
+    ProfScope(int cls, double algorithmic_bytes, cudaStream_t st);
+    ~ProfScope();
+    int slot;
+    cudaStream_t st;
+};
+
 #define GCNN_CUDA_TRY(expr)                                                                 \
     do {                                                                                    \
         cudaError_t err__ = (expr);                                                         \
@@ -103,10 +115,10 @@ struct EdgeScalars {  // device pointers to the scalars so no host sync is neede
     const float* s_f;
 };
 int edge_forward(const EdgeLayout& by_recv, int64_t n_recv, const float* R, const float* S, const float* w_edge,
-                 EdgeScalars sc, float* H, float* cnt, cudaStream_t st);
+                 EdgeScalars sc, float* H, float* cnt, cudaStream_t st, double prof_bytes = 0.0);
 int edge_backward(const EdgeLayout& by_send, int64_t n_send, const float* R, const float* S, const float* G,
                   const float* w_edge, EdgeScalars sc, float* dS, float* dw_partials, int* n_partials,
-                  cudaStream_t st);
+                  cudaStream_t st, double prof_bytes = 0.0);
 int edge_backward_max_partials();
 // sum and sum of squares of (z_e - center) over all E x 64 joint pre-activations (double accumulators)
 int edge_z_stats(const EdgeLayout& by_recv, int64_t n_recv, const float* R, const float* S, const float* w_edge,

@@ -187,6 +187,8 @@ int build_layout(const int32_t* keys, const int32_t* others, const float* feats,
         set_error("build_layout: sizes out of int32 range");
         return GCNN_INVALID;
     }
+    // algorithmic bytes: read (key, other, feature) per edge, write (other, feature, perm) per edge and the pointer
+    ProfScope prof(PROF_CSR, 24.0 * (double)E + 4.0 * (double)(n_owner + 1), st);
     const int threads = 256;
     int32_t* sorted_flag = sc.flags;
     set_flag_kernel<<<1, 1, 0, st>>>(sorted_flag, 1);

@@ -87,8 +87,9 @@ edge_forward_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__
 }
 
 int edge_forward(const EdgeLayout& L, int64_t n_recv, const float* R, const float* S, const float* w_edge,
-                 EdgeScalars sc, float* H, float* cnt, cudaStream_t st) {
+                 EdgeScalars sc, float* H, float* cnt, cudaStream_t st, double prof_bytes) {
     if (n_recv <= 0) return GCNN_OK;
+    ProfScope prof(PROF_EDGE_FWD, prof_bytes, st);
     edge_forward_kernel<<<(unsigned)ceil_div(n_recv, EDGE_WARPS), EDGE_THREADS, 0, st>>>(L.ptr, L.other, L.val, n_recv,
                                                                                          R, S, w_edge, sc, H, cnt);
     GCNN_LAUNCH_CHECK();
@@ -171,7 +172,8 @@ int edge_backward_max_partials() { return EDGE_BWD_MAX_CTAS; }
 
 int edge_backward(const EdgeLayout& L, int64_t n_send, const float* R, const float* S, const float* G,
                   const float* w_edge, EdgeScalars sc, float* dS, float* dw_partials, int* n_partials,
-                  cudaStream_t st) {
+                  cudaStream_t st, double prof_bytes) {
+    ProfScope prof(PROF_EDGE_BWD, prof_bytes, st);
     int ctas = (int)min((int64_t)EDGE_BWD_MAX_CTAS, ceil_div(n_send > 0 ? n_send : 1, EDGE_WARPS));
     *n_partials = ctas;
     edge_backward_kernel<<<ctas, EDGE_THREADS, 0, st>>>(L.ptr, L.other, L.val, n_send, R, S, G, w_edge, sc, dS,
@@ -232,6 +234,7 @@ __global__ void sum_double_partials_kernel(const double* __restrict__ partials, 
 
 int edge_z_stats(const EdgeLayout& L, int64_t n_recv, const float* R, const float* S, const float* w_edge,
                  EdgeScalars sc, double center, double* partials, double* out2, cudaStream_t st) {
+    ProfScope prof(PROF_STATS, 0.0, st);
     const int ctas = (int)min((int64_t)STATS_CTAS, ceil_div(n_recv > 0 ? n_recv : 1, EDGE_WARPS));
     edge_z_stats_kernel<<<ctas, EDGE_THREADS, 0, st>>>(L.ptr, L.other, L.val, n_recv, R, S, w_edge, sc, center,
                                                        partials);
@@ -276,6 +279,7 @@ col_stats_kernel(const float* __restrict__ x, int64_t M, int K, const double* __
 int col_stats(const float* x, int64_t M, int K, const double* center_dev, double* partials, double* out,
               cudaStream_t st) {
     if (K > 64) { set_error("col_stats: K > 64"); return GCNN_INVALID; }
+    ProfScope prof(PROF_STATS, 4.0 * (double)M * K, st);
     int Kp = 1;
     while (Kp < K) Kp <<= 1;
     const int ctas = (int)min((int64_t)STATS_CTAS, ceil_div(M > 0 ? M : 1, 256 / Kp));

@@ -99,6 +99,7 @@ static int set_smem(Kern kern, size_t bytes) {
 
 int linear_forward(const LinFwdArgs& a, cudaStream_t st) {
     if (a.M <= 0) return GCNN_OK;
+    ProfScope prof(PROF_LIN_FWD, 4.0 * ((double)a.M * (a.K + D) + (double)a.K * D + D), st);
     const unsigned grid = (unsigned)ceil_div(a.M, LIN_ROWS);
     if (a.K == 64) {
         const size_t smem = sizeof(float) * (LIN_ROWS * 68 + 64 * D);
@@ -186,6 +187,9 @@ int linear_dgrad(const LinDgradArgs& a, cudaStream_t st) {
     if (a.M <= 0) return GCNN_OK;
     if (a.K != 64 && a.K != 128) { set_error("linear_dgrad: K must be 64 or 128"); return GCNN_INVALID; }
     if (a.dR && a.accumulate) { set_error("linear_dgrad: dR needs a non-accumulating dX"); return GCNN_INVALID; }
+    const double rows_moved = 1.0 + (a.act ? 1.0 : 0.0) + a.K / 64 + (a.accumulate ? 1.0 : 0.0) +
+                              (a.K == 128 && a.accumulate2 ? 1.0 : 0.0) + (a.dR ? 2.0 : 0.0);
+    ProfScope prof(PROF_LIN_DGRAD, 256.0 * (double)a.M * rows_moved + 4.0 * a.K * D, st);
     const size_t smem = sizeof(float) * (LIN_ROWS * 68 + D * D);
     static int once = set_smem(linear_dgrad_kernel, smem);
     GCNN_TRY(once);
@@ -198,7 +202,7 @@ int linear_dgrad(const LinDgradArgs& a, cudaStream_t st) {
 // ---- wgrad: dW[k, c] = sum_m Xcat[m, k] * dYp[m, c],  db[c] = sum_m (deg_m) dYp[m, c] -----------------------------
 // Persistent CTAs stride over 32-row sub-tiles and keep the [K, 64] partial in registers.
 constexpr int WG_ROWS = 32;
-constexpr int WG_MAX_PARTS = NUM_SMS * 2;
+constexpr int WG_MAX_PARTS = NUM_SMS;
 int wgrad_max_parts() { return WG_MAX_PARTS; }
 
 template <int K>
@@ -281,6 +285,7 @@ linear_wgrad_kernel(LinWgradArgs a) {
 int linear_wgrad(const LinWgradArgs& a, cudaStream_t st) {
     const int parts = (int)min((int64_t)WG_MAX_PARTS, ceil_div(a.M > 0 ? a.M : 1, WG_ROWS));
     *a.n_parts = parts;
+    ProfScope prof(PROF_LIN_WGRAD, 4.0 * ((double)a.M * (a.K + D + (a.act ? D : 0)) + (double)a.K * D + D), st);
     if (a.K == 64) linear_wgrad_kernel<64><<<parts, LIN_THREADS, 0, st>>>(a);
     else if (a.K == 128) linear_wgrad_kernel<128><<<parts, LIN_THREADS, 0, st>>>(a);
     else { set_error("linear_wgrad: K must be 64 or 128"); return GCNN_INVALID; }
@@ -316,6 +321,7 @@ embed1_forward_kernel(const float* __restrict__ x, const float* __restrict__ shi
 int embed1_forward(const float* x, int K, const float* shift, const float* scale, const float* W, const float* b,
                    float* Y, int64_t M, cudaStream_t st) {
     if (M <= 0) return GCNN_OK;
+    ProfScope prof(PROF_EMB1_FWD, 4.0 * ((double)M * (K + D) + (double)K * D + D), st);
     const unsigned grid = (unsigned)min((int64_t)NUM_SMS * 8, ceil_div(M, 16));
     if (K == 4) embed1_forward_kernel<4><<<grid, 256, 0, st>>>(x, shift, scale, W, b, Y, M);
     else if (K == 6) embed1_forward_kernel<6><<<grid, 256, 0, st>>>(x, shift, scale, W, b, Y, M);
@@ -355,6 +361,7 @@ int embed1_wgrad(const float* x, int K, const float* shift, const float* scale, 
                  int64_t M, float* partials, int* n_parts, cudaStream_t st) {
     const int parts = (int)min((int64_t)WG_MAX_PARTS, ceil_div(M > 0 ? M : 1, 64));
     *n_parts = parts;
+    ProfScope prof(PROF_EMB1_WGRAD, 4.0 * ((double)M * (K + 2 * D) + (double)(K + 1) * D), st);
     if (K == 4) embed1_wgrad_kernel<4><<<parts, 256, 0, st>>>(x, shift, scale, dY, act, M, partials);
     else if (K == 6) embed1_wgrad_kernel<6><<<parts, 256, 0, st>>>(x, shift, scale, dY, act, M, partials);
     else if (K == 14) embed1_wgrad_kernel<14><<<parts, 256, 0, st>>>(x, shift, scale, dY, act, M, partials);
@@ -381,6 +388,7 @@ head2_forward_kernel(const float* __restrict__ g, const float* __restrict__ w, c
 
 int head2_forward(const float* g, const float* w, const float* b, float* scores, int64_t M, cudaStream_t st) {
     if (M <= 0) return GCNN_OK;
+    ProfScope prof(PROF_HEAD, 4.0 * (double)M * (D + 1), st);
     head2_forward_kernel<<<(unsigned)ceil_div(M, 16), 256, 0, st>>>(g, w, b, scores, M);
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
@@ -412,6 +420,7 @@ int head2_backward(const float* g, const float* w, const float* d_scores, float*
                    int* n_parts, int64_t M, cudaStream_t st) {
     const int parts = (int)min((int64_t)WG_MAX_PARTS, ceil_div(M > 0 ? M : 1, 64));
     *n_parts = parts;
+    ProfScope prof(PROF_HEAD, 4.0 * (double)M * (2 * D + 1), st);
     head2_backward_kernel<<<parts, 256, 0, st>>>(g, w, d_scores, dg_pre, partials, M);
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
@@ -441,6 +450,9 @@ reduce_partials_kernel(const __grid_constant__ ReduceJobs jobs, float* __restric
 int reduce_partials(const ReduceJob* jobs, int n_jobs, float* grads, cudaStream_t st) {
     if (n_jobs > MAX_JOBS) { set_error("reduce_partials: too many jobs"); return GCNN_INVALID; }
     if (n_jobs == 0) return GCNN_OK;
+    double out_floats = 0;
+    for (int i = 0; i < n_jobs; ++i) out_floats += jobs[i].count;
+    ProfScope prof(PROF_REDUCE, 8.0 * out_floats, st);  // one read + one write per gradient element at minimum
     ReduceJobs js;
     js.n = n_jobs;
     for (int i = 0; i < n_jobs; ++i) js.j[i] = jobs[i];
@@ -475,6 +487,7 @@ mse_seed_kernel(const float* __restrict__ scores, const float* __restrict__ targ
 
 int mse_seed(const float* scores, const float* targets, int64_t n, float scale, float* d_scores, float* loss_sum,
              cudaStream_t st) {
+    ProfScope prof(PROF_LOSS, 12.0 * (double)n, st);
     mse_seed_kernel<<<1, 1024, 0, st>>>(scores, targets, n, scale, d_scores, loss_sum);
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
@@ -496,6 +509,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 
 int adam_step(float* params, const float* grads, float* m, float* v, int64_t n, float lr_t, float beta1, float beta2,
               float eps, const float* grad_divisor, cudaStream_t st) {
+    ProfScope prof(PROF_ADAM, 28.0 * (double)n, st);
     adam_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(params, grads, m, v, n, lr_t, beta1, beta2, eps,
                                                             grad_divisor);
     GCNN_LAUNCH_CHECK();

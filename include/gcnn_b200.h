@@ -64,6 +64,14 @@ int gcnn_version(void);
 const char* gcnn_last_error(void);
 int gcnn_kernel_launches(void); /* kernels launched by this library in this process so far */
 
+/* Optional per-kernel-class timing: CUDA events recorded on the launching stream around every launch between
+ * begin and end.  end synchronises the device and fills, per class, total milliseconds, launches and ALGORITHMIC
+ * bytes (the compulsory traffic of each launch).  Used by bench.py for the roofline object. */
+int gcnn_profile_begin(void);
+int gcnn_profile_end(double* ms, int64_t* launches, double* algorithmic_bytes, int n_classes);
+int gcnn_profile_num_classes(void);
+const char* gcnn_profile_class_name(int cls);
+
 /* Enumerates the 62 arrays in save_state order (model.py:47-56, 215).  `offset` is into the trainable buffer when
  * *trainable != 0, else into the pre-norm buffer. */
 int gcnn_param_info(int index, char* name, int name_cap, int64_t* rows, int64_t* cols, int* trainable,
