@@ -3,6 +3,7 @@
 // Orchestration follows GCNN.call (model.py:257-300) and PartialGraphConvolution.call (model.py:533-575); the
 // backward is the hand-derived adjoint verified against autograd in the oracle tests.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -91,6 +92,10 @@ struct gcnn_workspace {
     // host staging mirrors (device side)
     float *s_cons, *s_cef, *s_var, *s_cut, *s_kef, *s_targets;
     int32_t *s_cei, *s_kei;
+    // tensor-core path: packed 3xTF32 weight images, one per 64 x 64 weight block
+    int use_tc = 1;
+    float* tc_images = nullptr;
+    int* tc_block_offsets = nullptr;
     // bookkeeping of the last forward (validated by backward)
     gcnn_batch last{};
     int have_activations = 0;
@@ -109,6 +114,26 @@ struct Carver {
         return p;
     }
 };
+
+// every 64 x 64 block of every [K, 64] kernel with K in {64, 128}: param offsets, fixed order
+static const std::vector<int>& tc_blocks() {
+    static const std::vector<int> blocks = [] {
+        std::vector<int> b = {P.cons.W2, P.var.W2, P.cut.W2};
+        for (int i = 0; i < 3; ++i) {
+            const ConvOff& o = P.conv[i];
+            for (int off : {o.Wl, o.Wr, o.Wf, o.Wo1, o.Wo1 + D * D, o.Wo2}) b.push_back(off);
+        }
+        b.push_back(P.Wh1);
+        return b;
+    }();
+    return blocks;
+}
+static int tc_block_index(int param_off) {
+    const std::vector<int>& b = tc_blocks();
+    for (size_t i = 0; i < b.size(); ++i)
+        if (b[i] == param_off) return (int)i;
+    return -1;
+}
 
 static int64_t max3(int64_t a, int64_t b, int64_t c) { return a > b ? (a > c ? a : c) : (b > c ? b : c); }
 
@@ -164,6 +189,9 @@ static size_t carve(gcnn_workspace* ws, char* base, const Caps& c) {
     ws->s_kef = cv.take<float>(ek);
     ws->s_targets = cv.take<float>(nk);
 
+    ws->tc_images = cv.take<float>((int64_t)tc_blocks().size() * TC_IMG_FLOATS);
+    ws->tc_block_offsets = cv.take<int>(64);
+
     if (c.training) {
         ws->dk1 = rows(nk); ws->dv1 = rows(nv); ws->dc1 = rows(nc);
         ws->dk0 = rows(nk); ws->dv0 = rows(nv); ws->dc0 = rows(nc);
@@ -191,11 +219,42 @@ static int check_batch(const gcnn_workspace* ws, const gcnn_batch* b, int traini
     return GCNN_OK;
 }
 
+// ---- dense-layer dispatch: tcgen05 3xTF32 tensor-core kernel (default) or the fp32 SIMT kernel (GCNN_TC=0) ---------
+static int dense_forward(gcnn_workspace* ws, const float* params, const LinFwdArgs& a, cudaStream_t st) {
+    if (!ws->use_tc) return linear_forward(a, st);
+    const int blk = tc_block_index((int)(a.W - params));
+    if (blk < 0) { set_error("dense_forward: weight is not a packed block"); return GCNN_INVALID; }
+    TcArgs t{};
+    t.X = a.X; t.X2 = a.X2; t.x_scale = a.x_scale; t.mask_act = nullptr; t.K = a.K; t.slabs = 1;
+    for (int j = 0; j < a.K / 64; ++j) t.img[0][j] = ws->tc_images + (int64_t)(blk + j) * TC_IMG_FLOATS;  // T images
+    t.bias = a.b; t.deg_ptr = a.deg_ptr; t.relu = a.relu; t.Y[0] = a.Y; t.M = a.M;
+    return tc_linear(t, PROF_LIN_FWD, 4.0 * ((double)a.M * (a.K + D) + (double)a.K * D + D), st);
+}
+
+static int dense_dgrad(gcnn_workspace* ws, const float* params, const LinDgradArgs& a, cudaStream_t st) {
+    if (!ws->use_tc) return linear_dgrad(a, st);
+    const int blk = tc_block_index((int)(a.W - params));
+    if (blk < 0) { set_error("dense_dgrad: weight is not a packed block"); return GCNN_INVALID; }
+    TcArgs t{};
+    t.X = a.dY; t.mask_act = a.act; t.K = 64; t.slabs = a.K / 64;
+    for (int s = 0; s < t.slabs; ++s)
+        t.img[s][0] = ws->tc_images + (int64_t)(blk + s) * TC_IMG_FLOATS + 2 * 64 * 64;  // N images
+    t.out_scale[0] = a.dx_scale; t.accumulate[0] = a.accumulate; t.Y[0] = a.dX;
+    t.accumulate[1] = a.accumulate2; t.Y[1] = a.dX2;
+    t.cnt = a.cnt; t.s_f = a.s_f; t.dR = a.dR; t.M = a.M;
+    const double rows_moved = 1.0 + (a.act ? 1.0 : 0.0) + a.K / 64 + (a.accumulate ? 1.0 : 0.0) +
+                              (a.K == 128 && a.accumulate2 ? 1.0 : 0.0) + (a.dR ? 2.0 : 0.0);
+    return tc_linear(t, PROF_LIN_DGRAD, 256.0 * (double)a.M * rows_moved + 4.0 * a.K * D, st);
+}
+
 // ---- forward -----------------------------------------------------------------------------------------------------
 // stop_layer: -1 runs everything; k in [5, 10] returns as soon as the input of pre-norm layer k exists.
 static int forward_impl(gcnn_workspace* ws, const float* p, const float* pn, const gcnn_batch* b, float* scores_out,
                         int stop_layer, cudaStream_t st) {
     const int64_t nc = b->n_cons, nv = b->n_vars, nk = b->n_cuts, ec = b->n_cons_edges, ek = b->n_cut_edges;
+
+    if (ws->use_tc)
+        GCNN_TRY(pack_weights(p, ws->tc_block_offsets, (int)tc_blocks().size(), ws->tc_images, st));
 
     // F1: edge layouts.  conv 0 reduces by constraint, conv 1 by variable (both over constraint edges),
     // conv 2 by cut; the opposite grouping of each edge set serves the backward pass.
@@ -217,7 +276,7 @@ static int forward_impl(gcnn_workspace* ws, const float* p, const float* pn, con
     for (auto& e : emb) {
         GCNN_TRY(embed1_forward(e.x, e.K, pn + e.shift, pn + e.scale, p + e.o->W1, p + e.o->b1, e.h1, e.n, st));
         LinFwdArgs a{e.h1, nullptr, nullptr, p + e.o->W2, p + e.o->b2, nullptr, e.out, e.n, 64, 1};
-        GCNN_TRY(linear_forward(a, st));
+        GCNN_TRY(dense_forward(ws, p, a, st));
     }
 
     // convolutions (model.py:294-296): {left feats, var feats, receiving side, graph, edge pre-norm}
@@ -234,9 +293,9 @@ static int forward_impl(gcnn_workspace* ws, const float* p, const float* pn, con
         const int64_t n_recv = recv_is_left[i] ? n_left[i] : nv;
         const float* recv_in = recv_is_left[i] ? left_in[i] : var_in[i];
         LinFwdArgs pa{left_in[i], nullptr, nullptr, p + o.Wl, p + o.bl, nullptr, a.A, n_left[i], 64, 0};
-        GCNN_TRY(linear_forward(pa, st));
+        GCNN_TRY(dense_forward(ws, p, pa, st));
         LinFwdArgs pb{var_in[i], nullptr, nullptr, p + o.Wr, nullptr, nullptr, a.B, nv, 64, 0};
-        GCNN_TRY(linear_forward(pb, st));
+        GCNN_TRY(dense_forward(ws, p, pb, st));
         const EdgeLayout& L = recv_is_left[i] ? ws->graph[graph_of[i]].by_left : ws->graph[graph_of[i]].by_var;
         const float* R = recv_is_left[i] ? a.A : a.B;
         const float* S = recv_is_left[i] ? a.B : a.A;
@@ -248,17 +307,17 @@ static int forward_impl(gcnn_workspace* ws, const float* p, const float* pn, con
         const double fwd_bytes = 256.0 * (double)(n_left[i] + nv + n_recv) + 8.0 * (double)E_i + 4.0 * (double)(n_recv + 1);
         GCNN_TRY(edge_forward(L, n_recv, R, S, p + o.we, sc, a.H, a.cnt, st, fwd_bytes));
         LinFwdArgs pc{a.H, nullptr, nullptr, p + o.Wf, p + o.bf, L.ptr, a.C, n_recv, 64, 0};
-        GCNN_TRY(linear_forward(pc, st));
+        GCNN_TRY(dense_forward(ws, p, pc, st));
         if (stop_layer == 6 + 2 * i) return GCNN_OK;
         LinFwdArgs p1{a.C, recv_in, pn + PN.conv_sp[i], p + o.Wo1, p + o.bo1, nullptr, a.U1, n_recv, 128, 1};
-        GCNN_TRY(linear_forward(p1, st));
+        GCNN_TRY(dense_forward(ws, p, p1, st));
         LinFwdArgs p2{a.U1, nullptr, nullptr, p + o.Wo2, p + o.bo2, nullptr, a.Y, n_recv, 64, 1};
-        GCNN_TRY(linear_forward(p2, st));
+        GCNN_TRY(dense_forward(ws, p, p2, st));
     }
 
     // head (model.py:299-300)
     LinFwdArgs h1{ws->conv[2].Y, nullptr, nullptr, p + P.Wh1, p + P.bh1, nullptr, ws->g1, nk, 64, 1};
-    GCNN_TRY(linear_forward(h1, st));
+    GCNN_TRY(dense_forward(ws, p, h1, st));
     GCNN_TRY(head2_forward(ws->g1, p + P.Wh2, p + P.bh2, scores_out ? scores_out : ws->scores, nk, st));
     return GCNN_OK;
 }
@@ -283,7 +342,7 @@ static int backward_impl(gcnn_workspace* ws, const float* p, const float* pn, co
         GCNN_TRY(linear_wgrad(w, st));
         add_job(ws->partials[slot++], n_parts, D * D + D, D * D + D, P.Wh1);
         LinDgradArgs d{ws->t_dg, nullptr, p + P.Wh1, 64, ws->dk1, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, nk};
-        GCNN_TRY(linear_dgrad(d, st));
+        GCNN_TRY(dense_dgrad(ws, p, d, st));
     }
 
     const float* left_in[3] = {ws->c0, ws->conv[0].Y, ws->k0};
@@ -316,7 +375,7 @@ static int backward_impl(gcnn_workspace* ws, const float* p, const float* pn, co
             GCNN_TRY(linear_wgrad(w, st));
             add_job(ws->partials[slot++], n_parts, D * D + D, D * D + D, o.Wo2);
             LinDgradArgs d{dY, a.Y, p + o.Wo2, 64, ws->t_dU1, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, n_recv};
-            GCNN_TRY(linear_dgrad(d, st));
+            GCNN_TRY(dense_dgrad(ws, p, d, st));
         }
         // output MLP layer 1: U1 = relu([s_p C, X_t] Wo1 + bo1)
         {
@@ -329,7 +388,7 @@ static int backward_impl(gcnn_workspace* ws, const float* p, const float* pn, co
             if (d_recv_in == ws->dv0) { acc2 = dv0_written ? 1 : 0; dv0_written = true; }
             LinDgradArgs d{ws->t_dU1, a.U1, p + o.Wo1, 128, ws->t_dC, pn + PN.conv_sp[i], 0, d_recv_in, acc2, nullptr,
                            nullptr, nullptr, n_recv};
-            GCNN_TRY(linear_dgrad(d, st));
+            GCNN_TRY(dense_dgrad(ws, p, d, st));
         }
         // hoisted feature_module_final: C = H Wf + deg bf;  G = dC Wf^T;  dR = s_f G cnt
         {
@@ -339,7 +398,7 @@ static int backward_impl(gcnn_workspace* ws, const float* p, const float* pn, co
             add_job(ws->partials[slot++], n_parts, D * D + D, D * D + D, o.Wf);
             LinDgradArgs d{ws->t_dC, nullptr, p + o.Wf, 64, ws->t_G, nullptr, 0, nullptr, 0, a.cnt, pn + PN.conv_sf[i],
                            ws->t_dR, n_recv};
-            GCNN_TRY(linear_dgrad(d, st));
+            GCNN_TRY(dense_dgrad(ws, p, d, st));
         }
         // edge backward over the transposed layout
         const float* R = recv_is_left[i] ? a.A : a.B;
@@ -364,7 +423,7 @@ static int backward_impl(gcnn_workspace* ws, const float* p, const float* pn, co
             // the left input's gradient was already written by the concat branch iff the left side receives
             LinDgradArgs d{dA, nullptr, p + o.Wl, 64, d_left[i], nullptr, recv_is_left[i] ? 1 : 0, nullptr, 0, nullptr,
                            nullptr, nullptr, n_left[i]};
-            GCNN_TRY(linear_dgrad(d, st));
+            GCNN_TRY(dense_dgrad(ws, p, d, st));
         }
         // right projection B = X_v Wr
         {
@@ -375,7 +434,7 @@ static int backward_impl(gcnn_workspace* ws, const float* p, const float* pn, co
             if (d_var[i] == ws->dv0) { acc = dv0_written ? 1 : 0; dv0_written = true; }
             else acc = 0;  // dv1 has conv 2's right projection as its only writer
             LinDgradArgs d{dB, nullptr, p + o.Wr, 64, d_var[i], nullptr, acc, nullptr, 0, nullptr, nullptr, nullptr, nv};
-            GCNN_TRY(linear_dgrad(d, st));
+            GCNN_TRY(dense_dgrad(ws, p, d, st));
         }
     }
 
@@ -389,7 +448,7 @@ static int backward_impl(gcnn_workspace* ws, const float* p, const float* pn, co
         GCNN_TRY(linear_wgrad(w, st));
         add_job(ws->partials[slot++], n_parts, D * D + D, D * D + D, e.o->W2);
         LinDgradArgs d{e.dout, e.out, p + e.o->W2, 64, ws->t_dh1, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, e.n};
-        GCNN_TRY(linear_dgrad(d, st));
+        GCNN_TRY(dense_dgrad(ws, p, d, st));
         GCNN_TRY(embed1_wgrad(e.x, e.K, pn + e.shift, pn + e.scale, ws->t_dh1, e.h1, e.n, ws->partials[slot], &n_parts,
                               st));
         add_job(ws->partials[slot++], n_parts, (e.K + 1) * D, (e.K + 1) * D, e.o->W1);
@@ -465,7 +524,8 @@ int gcnn_profile_end(double* ms, int64_t* launches, double* bytes, int n_classes
 const char* gcnn_profile_class_name(int c) {
     static const char* names[PROF_NCLASSES] = {"csr_build", "embed1_forward", "linear_forward", "edge_forward", "head2",
                                                "linear_dgrad", "linear_wgrad", "embed1_wgrad", "edge_backward",
-                                               "reduce_partials", "mse_seed", "adam", "prenorm_stats"};
+                                               "reduce_partials", "mse_seed", "adam", "prenorm_stats",
+                                               "pack_weights"};
     return (c >= 0 && c < PROF_NCLASSES) ? names[c] : "";
 }
 int gcnn_profile_num_classes(void) { return PROF_NCLASSES; }
@@ -522,6 +582,8 @@ int gcnn_workspace_create(gcnn_workspace** out) {
     if (!out) { set_error("null out pointer"); return GCNN_INVALID; }
     gcnn_workspace* ws = new (std::nothrow) gcnn_workspace();
     if (!ws) { set_error("host allocation failed"); return GCNN_OOM; }
+    const char* tc = getenv("GCNN_TC");  // GCNN_TC=0 selects the exact-fp32 SIMT dense kernels
+    ws->use_tc = !(tc && tc[0] == '0');
     *out = ws;
     return GCNN_OK;
 }
@@ -558,6 +620,8 @@ int gcnn_workspace_reserve(gcnn_workspace* ws, int64_t nc, int64_t nv, int64_t n
     ws->have_activations = 0;
     carve(ws, mem, c);
     GCNN_CUDA_TRY(cudaMemset(ws->flags, 0, sizeof(int32_t) * 64));
+    GCNN_CUDA_TRY(cudaMemcpy(ws->tc_block_offsets, tc_blocks().data(), sizeof(int) * tc_blocks().size(),
+                             cudaMemcpyHostToDevice));
     return GCNN_OK;
 }
 

@@ -17,7 +17,7 @@ void count_launch(int n = 1);
 // ---- optional per-kernel-class timing with CUDA events on the launching stream (bench.py roofline numbers) -------
 enum ProfClass {
     PROF_CSR = 0, PROF_EMB1_FWD, PROF_LIN_FWD, PROF_EDGE_FWD, PROF_HEAD, PROF_LIN_DGRAD, PROF_LIN_WGRAD,
-    PROF_EMB1_WGRAD, PROF_EDGE_BWD, PROF_REDUCE, PROF_LOSS, PROF_ADAM, PROF_STATS, PROF_NCLASSES
+    PROF_EMB1_WGRAD, PROF_EDGE_BWD, PROF_REDUCE, PROF_LOSS, PROF_ADAM, PROF_STATS, PROF_PACK, PROF_NCLASSES
 };
 struct ProfScope {  // records a start/stop event pair around the launches issued while it is alive (if enabled)
     ProfScope(int cls, double algorithmic_bytes, cudaStream_t st);
@@ -173,6 +173,30 @@ struct LinWgradArgs {
 };
 int linear_wgrad(const LinWgradArgs& a, cudaStream_t st);
 int wgrad_max_parts();
+
+// ---- tensor-core (tcgen05, 3xTF32) variant of linear_forward / linear_dgrad (node_tc.cu) ---------------------------
+struct TcArgs {
+    const float* X;         // [M, 64] A operand (left half when K = 128)
+    const float* X2;        // right half of the concat (K = 128)
+    const float* x_scale;   // device scalar on X (left half)
+    const float* mask_act;  // X *= 1[mask_act > 0] (dgrad through a ReLU), or nullptr
+    int K;                  // reduction length: 64 or 128
+    int slabs;              // 1, or 2 output slabs of 64 columns (dgrad of the 128-input layer); blockIdx.y
+    const float* img[2][2]; // [slab][64-wide K block] -> packed weight image [hi 16 KB][lo 16 KB]
+    const float* bias;      // [64] or nullptr
+    const int32_t* deg_ptr; // bias scaled by the segment length
+    int relu;
+    const float* out_scale[2];  // device scalar per slab or nullptr
+    int accumulate[2];
+    float* Y[2];            // [M, 64] per slab
+    const float* cnt;       // slab 0 second output: dR = s_f * Y * cnt
+    const float* s_f;
+    float* dR;
+    int64_t M;
+};
+int tc_linear(const TcArgs& a, int prof_class, double prof_bytes, cudaStream_t st);
+int pack_weights(const float* params, const int* block_offsets_dev, int n_blocks, float* images, cudaStream_t st);
+constexpr int TC_IMG_FLOATS = 4 * 64 * 64;  // T_hi, T_lo, N_hi, N_lo of one 64 x 64 weight block
 
 // embedding layer 1: h = relu(((x + shift) * scale) W1 + b1), K in {4, 6, 14}
 int embed1_forward(const float* x, int K, const float* shift, const float* scale, const float* W, const float* b,

@@ -65,39 +65,66 @@ radix_hist_kernel(const int32_t* __restrict__ key_in, int64_t E, int shift, cons
     hist[threadIdx.x * n_blocks + blockIdx.x] = h[threadIdx.x];  // digit-major so one scan gives global offsets
 }
 
-// Exclusive scan of n int32 in place, one CTA of 1024 threads (n = 256 * n_blocks is small).
+// Exclusive scan of n int32 in place, one CTA of 1024 threads; 16 elements per thread per pass (vector loads when the
+// pass is full), warp-shuffle + shared-memory block scan, running carry across passes.
 __global__ void __launch_bounds__(1024)
 exclusive_scan_kernel(int32_t* __restrict__ data, int64_t n, const int32_t* __restrict__ sorted_flag) {
     if (*sorted_flag) return;
+    constexpr int PER = 16;
     __shared__ int32_t warp_sums[32];
+    __shared__ int32_t carry_s;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const int64_t per = ceil_div(n, 1024);
-    const int64_t lo = min(n, (int64_t)t * per), hi = min(n, lo + per);
-    int32_t sum = 0;
-    for (int64_t i = lo; i < hi; ++i) sum += data[i];
-    int32_t incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    if (lane == 31) warp_sums[warp] = incl;
+    if (t == 0) carry_s = 0;
     __syncthreads();
-    if (warp == 0) {
-        int32_t w = warp_sums[lane], wi = w;
+    for (int64_t base = 0; base < n; base += 1024 * PER) {
+        const int64_t lo = base + (int64_t)t * PER;
+        const int32_t carry = carry_s;  // written by the previous pass before its trailing barrier
+        int32_t v[PER];
+        if (lo + PER <= n) {
+#pragma unroll
+            for (int q = 0; q < PER / 4; ++q) {
+                const int4 x = *reinterpret_cast<const int4*>(data + lo + q * 4);
+                v[q * 4 + 0] = x.x; v[q * 4 + 1] = x.y; v[q * 4 + 2] = x.z; v[q * 4 + 3] = x.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < PER; ++i) v[i] = (lo + i < n) ? data[lo + i] : 0;
+        }
+        int32_t sum = 0;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) { const int32_t x = v[i]; v[i] = sum; sum += x; }
+        int32_t incl = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            int32_t v = __shfl_up_sync(0xffffffffu, wi, o);
-            if (lane >= o) wi += v;
+            const int32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
         }
-        warp_sums[lane] = wi - w;
-    }
-    __syncthreads();
-    int32_t run = warp_sums[warp] + incl - sum;
-    for (int64_t i = lo; i < hi; ++i) {
-        int32_t v = data[i];
-        data[i] = run;
-        run += v;
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int32_t w = warp_sums[lane];
+            int32_t wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int32_t u = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += u;
+            }
+            warp_sums[lane] = wi - w;
+            if (lane == 31) carry_s = carry + wi;
+        }
+        __syncthreads();
+        const int32_t off = carry + warp_sums[warp] + incl - sum;
+        if (lo + PER <= n) {
+#pragma unroll
+            for (int q = 0; q < PER / 4; ++q)
+                *reinterpret_cast<int4*>(data + lo + q * 4) =
+                    make_int4(v[q * 4 + 0] + off, v[q * 4 + 1] + off, v[q * 4 + 2] + off, v[q * 4 + 3] + off);
+        } else {
+#pragma unroll
+            for (int i = 0; i < PER; ++i)
+                if (lo + i < n) data[lo + i] = v[i] + off;
+        }
+        __syncthreads();
     }
 }
 

@@ -433,30 +433,30 @@ struct ReduceJobs { ReduceJob j[MAX_JOBS]; int n; };
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const __grid_constant__ ReduceJobs jobs, float* __restrict__ grads) {
     const ReduceJob& job = jobs.j[blockIdx.y];
-    for (int i = blockIdx.x * 256 + threadIdx.x; i < job.count; i += gridDim.x * 256) {
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-        int p = 0;
-        for (; p + 4 <= job.n_parts; p += 4) {
-            s0 += job.partials[(int64_t)(p + 0) * job.stride + i];
-            s1 += job.partials[(int64_t)(p + 1) * job.stride + i];
-            s2 += job.partials[(int64_t)(p + 2) * job.stride + i];
-            s3 += job.partials[(int64_t)(p + 3) * job.stride + i];
-        }
-        for (; p < job.n_parts; ++p) s0 += job.partials[(int64_t)p * job.stride + i];
-        grads[job.dst + i] = (s0 + s1) + (s2 + s3);
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= job.count) return;
+    const float* src = job.partials + i;
+    float s[8] = {};
+    int p = 0;
+    for (; p + 8 <= job.n_parts; p += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s[u] += src[(int64_t)(p + u) * job.stride];
     }
+    for (; p < job.n_parts; ++p) s[0] += src[(int64_t)p * job.stride];
+    grads[job.dst + i] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
 }
 
 int reduce_partials(const ReduceJob* jobs, int n_jobs, float* grads, cudaStream_t st) {
     if (n_jobs > MAX_JOBS) { set_error("reduce_partials: too many jobs"); return GCNN_INVALID; }
     if (n_jobs == 0) return GCNN_OK;
     double out_floats = 0;
-    for (int i = 0; i < n_jobs; ++i) out_floats += jobs[i].count;
+    int max_count = 1;
+    for (int i = 0; i < n_jobs; ++i) { out_floats += jobs[i].count; max_count = jobs[i].count > max_count ? jobs[i].count : max_count; }
     ProfScope prof(PROF_REDUCE, 8.0 * out_floats, st);  // one read + one write per gradient element at minimum
     ReduceJobs js;
     js.n = n_jobs;
     for (int i = 0; i < n_jobs; ++i) js.j[i] = jobs[i];
-    dim3 grid(8, n_jobs);
+    dim3 grid((unsigned)ceil_div(max_count, 256), n_jobs);
     reduce_partials_kernel<<<grid, 256, 0, st>>>(js, grads);
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;

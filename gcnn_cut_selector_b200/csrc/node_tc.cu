@@ -1,0 +1,300 @@
+// Tensor-core path for the node-level dense layers: tcgen05.mma (kind::tf32) with TMEM accumulators, 3xTF32 split.
+//
+// Same reference ops as node.cu (Keras Dense forward and its input gradient); this file replaces the SIMT inner
+// product with 5th-generation tensor-core MMAs.  fp32 parity (1e-5) is kept by splitting every operand into a TF32
+// "hi" part and an fp32 residual "lo" part and issuing three MMAs per K-step into the same TMEM accumulator:
+//     x w  ~=  x_lo w_hi + x_hi w_lo + x_hi w_hi          (the dropped x_lo w_lo term is ~2^-22 relative)
+// The layers are memory-bound even at 3x the MMA work (K <= 128, N = 64), so the split costs nothing on the roofline.
+//
+// Tile: one CTA = 128 rows x 64 outputs.  A operand: the X tile, split and written to shared memory in the canonical
+// K-major SWIZZLE_128B layout (8-row x 128-byte atoms, 16-byte chunks XOR-ed with the row index); B operand: the
+// pre-packed weight image in the same layout (pack_weights_kernel, once per step).  One elected thread issues the MMAs
+// (UMMA 128x64x8) and commits to an mbarrier; all 8 warps then read their TMEM quadrant with tcgen05.ld and run the
+// fused epilogue (bias / degree-scaled bias / ReLU / scale / accumulate / dR).
+#include "common.cuh"
+
+namespace gcnn {
+
+constexpr int TC_THREADS = 256;
+constexpr int TC_ROWS = 128;
+constexpr uint32_t A_BLOCK_BYTES = TC_ROWS * 128;  // one 32-float-wide K block of the A tile
+constexpr uint32_t B_BLOCK_BYTES = 64 * 128;       // one 32-float-wide K block of a 64-row weight image
+constexpr int IMG_FLOATS = 64 * 64;                // one image part (hi or lo) of a 64 x 64 weight block
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols));
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], tf32 inputs, fp32 accumulate, M = 128, N = 64, K = 8
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// 32 lanes x 32 consecutive fp32 columns of TMEM -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row atoms 1024 B apart (cute::UMMA::SmemDescriptor).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);  // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                       // leading byte offset (unused for swizzled K-major), 16-byte units
+    d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+    return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B tf32, both K-major, N = 64, M = 128.
+constexpr uint32_t IDESC_TF32_128x64 = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+
+// Byte offset of the 16-byte chunk holding floats [k, k+4) of row r inside a K-major SWIZZLE_128B tile of `rows` rows.
+__device__ __forceinline__ uint32_t swz_chunk_off(int r, int k, int rows) {
+    const int kb = k >> 5, chunk = (k & 31) >> 2;
+    return (uint32_t)(kb * rows * 128 + (r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
+}
+
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+    hi = __uint_as_float(h);
+    lo = x - hi;
+}
+__device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
+    split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y);
+    split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
+}
+
+// ---- weight images --------------------------------------------------------------------------------------------------
+// For every 64 x 64 block Wb of a weight matrix (rows 64 j .. 64 j + 63 of a [K, 64] kernel) four images are written:
+//   T_hi, T_lo : B[n][k] = Wb[k][n]   (forward:  Y = X W)
+//   N_hi, N_lo : B[n][k] = Wb[n][k]   (dgrad:    dX = dY W^T)
+// each 64 rows x 64 floats in the K-major SWIZZLE_128B shared-memory layout, so a CTA copies them linearly.
+__global__ void __launch_bounds__(256)
+pack_weights_kernel(const float* __restrict__ params, const int* __restrict__ block_offsets, float* __restrict__ images) {
+    __shared__ float Wb[64][65];
+    const float* W = params + block_offsets[blockIdx.x];
+    float* img = images + (int64_t)blockIdx.x * 4 * IMG_FLOATS;
+    for (int i = threadIdx.x; i < 64 * 64; i += 256) Wb[i >> 6][i & 63] = W[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+        const int n = i >> 4, k = (i & 15) * 4;
+        const uint32_t off = swz_chunk_off(n, k, 64) >> 2;
+        float4 t = make_float4(Wb[k][n], Wb[k + 1][n], Wb[k + 2][n], Wb[k + 3][n]);
+        float4 u = make_float4(Wb[n][k], Wb[n][k + 1], Wb[n][k + 2], Wb[n][k + 3]);
+        float4 hi, lo;
+        split4(t, hi, lo);
+        *reinterpret_cast<float4*>(img + 0 * IMG_FLOATS + off) = hi;
+        *reinterpret_cast<float4*>(img + 1 * IMG_FLOATS + off) = lo;
+        split4(u, hi, lo);
+        *reinterpret_cast<float4*>(img + 2 * IMG_FLOATS + off) = hi;
+        *reinterpret_cast<float4*>(img + 3 * IMG_FLOATS + off) = lo;
+    }
+}
+
+int pack_weights(const float* params, const int* block_offsets_dev, int n_blocks, float* images, cudaStream_t st) {
+    ProfScope prof(PROF_PACK, 4.0 * 5 * IMG_FLOATS * n_blocks, st);
+    pack_weights_kernel<<<n_blocks, 256, 0, st>>>(params, block_offsets_dev, images);
+    GCNN_LAUNCH_CHECK();
+    return GCNN_OK;
+}
+
+// ---- the GEMM ------------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(TC_THREADS)
+tc_linear_kernel(const TcArgs a) {
+    constexpr int KB = K / 32;                      // 32-float-wide K blocks
+    constexpr uint32_t A_PART = KB * A_BLOCK_BYTES; // hi or lo part of the A tile
+    constexpr uint32_t B_PART = KB * B_BLOCK_BYTES;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t mma_bar;
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int slab = blockIdx.y;
+    const int64_t row0 = (int64_t)blockIdx.x * TC_ROWS;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
+    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+    uint8_t* A_hi = gen;
+    uint8_t* A_lo = gen + A_PART;
+    uint8_t* B_hi = gen + 2 * A_PART;
+    uint8_t* B_lo = gen + 2 * A_PART + B_PART;
+
+    if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), 64);
+    if (tid == 0) mbar_init(smem_u32(&mma_bar), 1);
+
+    // B: copy the packed weight image(s) for this slab, one per 64-wide K block
+#pragma unroll
+    for (int j = 0; j < K / 64; ++j) {
+        const float4* src = reinterpret_cast<const float4*>(a.img[slab][j]);  // [hi 16 KB][lo 16 KB]
+        for (int i = tid; i < IMG_FLOATS / 4; i += TC_THREADS) {
+            reinterpret_cast<float4*>(B_hi + j * 2 * B_BLOCK_BYTES)[i] = src[i];
+            reinterpret_cast<float4*>(B_lo + j * 2 * B_BLOCK_BYTES)[i] = src[IMG_FLOATS / 4 + i];
+        }
+    }
+    // A: load, transform (scale / concat / ReLU mask), split, swizzled store
+    const float xs = a.x_scale ? *a.x_scale : 1.f;
+    for (int i = tid; i < TC_ROWS * (K / 4); i += TC_THREADS) {
+        const int r = i / (K / 4), c4 = i % (K / 4);
+        const int64_t m = row0 + r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < a.M) {
+            if (c4 < 16) {
+                v = *reinterpret_cast<const float4*>(a.X + m * D + c4 * 4);
+                if (a.mask_act) {
+                    const float4 y = *reinterpret_cast<const float4*>(a.mask_act + m * D + c4 * 4);
+                    v.x = y.x > 0.f ? v.x : 0.f; v.y = y.y > 0.f ? v.y : 0.f;
+                    v.z = y.z > 0.f ? v.z : 0.f; v.w = y.w > 0.f ? v.w : 0.f;
+                }
+                v.x *= xs; v.y *= xs; v.z *= xs; v.w *= xs;
+            } else {
+                v = *reinterpret_cast<const float4*>(a.X2 + m * D + (c4 - 16) * 4);
+            }
+        }
+        float4 hi, lo;
+        split4(v, hi, lo);
+        const uint32_t off = swz_chunk_off(r, c4 * 4, TC_ROWS);
+        *reinterpret_cast<float4*>(A_hi + off) = hi;
+        *reinterpret_cast<float4*>(A_lo + off) = lo;
+    }
+    fence_async_smem();  // generic-proxy writes -> visible to the tensor-core (async) proxy
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_slot;
+
+    if (tid == 0) {
+        const uint32_t a_addr[2] = {base, base + A_PART};                            // hi, lo
+        const uint32_t b_addr[2] = {base + 2 * A_PART, base + 2 * A_PART + B_PART};  // hi, lo
+        const int sel[3][2] = {{1, 0}, {0, 1}, {0, 0}};                              // (A part, B part): lo*hi, hi*lo, hi*hi
+        uint32_t acc = 0;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t da = make_desc(a_addr[sel[p][0]] + kb * A_BLOCK_BYTES + ks * 32);
+                    const uint64_t db = make_desc(b_addr[sel[p][1]] + kb * B_BLOCK_BYTES + ks * 32);
+                    umma_tf32(tmem_d, da, db, IDESC_TF32_128x64, acc);
+                    acc = 1;
+                }
+            }
+        }
+        umma_commit(smem_u32(&mma_bar));  // implies tcgen05.fence::before_thread_sync
+    }
+    mbar_wait(smem_u32(&mma_bar), 0);
+    tc_fence_after();
+
+    // epilogue: warp w reads TMEM lanes [32 (w % 4), +32) (its quadrant), columns [32 (w / 4), +32)
+    const int q = warp & 3, ch = warp >> 2;
+    float v[32];
+    tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
+    const int64_t m = row0 + q * 32 + lane;
+    if (m < a.M) {
+        float bs = 1.f;
+        if (a.deg_ptr) bs = (float)(a.deg_ptr[m + 1] - a.deg_ptr[m]);
+        const float osc = a.out_scale[slab] ? *a.out_scale[slab] : 1.f;
+        float* dst = a.Y[slab] + m * D + ch * 32;
+        const bool second = slab == 0 && a.dR != nullptr;
+        const float s_f = second ? *a.s_f : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float4 y = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            if (a.bias) {
+                const float4 b4 = *reinterpret_cast<const float4*>(a.bias + ch * 32 + 4 * j);
+                y.x += bs * b4.x; y.y += bs * b4.y; y.z += bs * b4.z; y.w += bs * b4.w;
+            }
+            if (a.relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+            y.x *= osc; y.y *= osc; y.z *= osc; y.w *= osc;
+            if (a.accumulate[slab]) {
+                const float4 o = *reinterpret_cast<const float4*>(dst + 4 * j);
+                y.x += o.x; y.y += o.y; y.z += o.z; y.w += o.w;
+            }
+            *reinterpret_cast<float4*>(dst + 4 * j) = y;
+            if (second) {
+                const float4 c = *reinterpret_cast<const float4*>(a.cnt + m * D + ch * 32 + 4 * j);
+                *reinterpret_cast<float4*>(a.dR + m * D + ch * 32 + 4 * j) =
+                    make_float4(s_f * y.x * c.x, s_f * y.y * c.y, s_f * y.z * c.z, s_f * y.w * c.w);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_d, 64);
+}
+
+template <typename Kern>
+static int set_smem_tc(Kern kern, size_t bytes) {
+    GCNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return GCNN_OK;
+}
+
+int tc_linear(const TcArgs& a, int prof_class, double prof_bytes, cudaStream_t st) {
+    if (a.M <= 0) return GCNN_OK;
+    ProfScope prof(prof_class, prof_bytes, st);
+    dim3 grid((unsigned)ceil_div(a.M, TC_ROWS), a.slabs);
+    if (a.K == 64) {
+        const size_t smem = 2 * 2 * A_BLOCK_BYTES + 2 * 2 * B_BLOCK_BYTES + 1024;
+        static int once = set_smem_tc(tc_linear_kernel<64>, smem);
+        GCNN_TRY(once);
+        tc_linear_kernel<64><<<grid, TC_THREADS, smem, st>>>(a);
+    } else if (a.K == 128) {
+        const size_t smem = 2 * 4 * A_BLOCK_BYTES + 2 * 4 * B_BLOCK_BYTES + 1024;
+        static int once = set_smem_tc(tc_linear_kernel<128>, smem);
+        GCNN_TRY(once);
+        tc_linear_kernel<128><<<grid, TC_THREADS, smem, st>>>(a);
+    } else {
+        set_error("tc_linear: K must be 64 or 128");
+        return GCNN_INVALID;
+    }
+    GCNN_LAUNCH_CHECK();
+    return GCNN_OK;
+}
+
+}  // namespace gcnn
