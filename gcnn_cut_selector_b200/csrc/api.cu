@@ -247,6 +247,12 @@ static int dense_dgrad(gcnn_workspace* ws, const float* params, const LinDgradAr
     return tc_linear(t, PROF_LIN_DGRAD, 256.0 * (double)a.M * rows_moved + 4.0 * a.K * D, st);
 }
 
+static int dense_wgrad(gcnn_workspace* ws, const LinWgradArgs& a, cudaStream_t st) {
+    if (!ws->use_tc) return linear_wgrad(a, st);
+    TcWgradArgs t{a.X, a.X2, a.x_scale, a.dY, a.act, a.deg_ptr, a.K, a.M, a.partials, a.n_parts};
+    return tc_wgrad(t, st);
+}
+
 // ---- forward -----------------------------------------------------------------------------------------------------
 // stop_layer: -1 runs everything; k in [5, 10] returns as soon as the input of pre-norm layer k exists.
 static int forward_impl(gcnn_workspace* ws, const float* p, const float* pn, const gcnn_batch* b, float* scores_out,
@@ -339,7 +345,7 @@ static int backward_impl(gcnn_workspace* ws, const float* p, const float* pn, co
     {
         LinWgradArgs w{ws->conv[2].Y, nullptr, nullptr, ws->t_dg, nullptr, nullptr, 64, nk, 1, ws->partials[slot],
                        &n_parts};
-        GCNN_TRY(linear_wgrad(w, st));
+        GCNN_TRY(dense_wgrad(ws, w, st));
         add_job(ws->partials[slot++], n_parts, D * D + D, D * D + D, P.Wh1);
         LinDgradArgs d{ws->t_dg, nullptr, p + P.Wh1, 64, ws->dk1, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, nk};
         GCNN_TRY(dense_dgrad(ws, p, d, st));
@@ -372,7 +378,7 @@ static int backward_impl(gcnn_workspace* ws, const float* p, const float* pn, co
         // output MLP layer 2: Y = relu(U1 Wo2 + bo2)
         {
             LinWgradArgs w{a.U1, nullptr, nullptr, dY, a.Y, nullptr, 64, n_recv, 1, ws->partials[slot], &n_parts};
-            GCNN_TRY(linear_wgrad(w, st));
+            GCNN_TRY(dense_wgrad(ws, w, st));
             add_job(ws->partials[slot++], n_parts, D * D + D, D * D + D, o.Wo2);
             LinDgradArgs d{dY, a.Y, p + o.Wo2, 64, ws->t_dU1, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, n_recv};
             GCNN_TRY(dense_dgrad(ws, p, d, st));
@@ -381,7 +387,7 @@ static int backward_impl(gcnn_workspace* ws, const float* p, const float* pn, co
         {
             LinWgradArgs w{a.C, recv_in, pn + PN.conv_sp[i], ws->t_dU1, a.U1, nullptr, 128, n_recv, 1,
                            ws->partials[slot], &n_parts};
-            GCNN_TRY(linear_wgrad(w, st));
+            GCNN_TRY(dense_wgrad(ws, w, st));
             add_job(ws->partials[slot++], n_parts, 2 * D * D + D, 2 * D * D + D, o.Wo1);
             // which earlier op already wrote the receiving input's gradient?
             int acc2 = 0;
@@ -394,7 +400,7 @@ static int backward_impl(gcnn_workspace* ws, const float* p, const float* pn, co
         {
             LinWgradArgs w{a.H, nullptr, nullptr, ws->t_dC, nullptr, Lr.ptr, 64, n_recv, 1, ws->partials[slot],
                            &n_parts};
-            GCNN_TRY(linear_wgrad(w, st));
+            GCNN_TRY(dense_wgrad(ws, w, st));
             add_job(ws->partials[slot++], n_parts, D * D + D, D * D + D, o.Wf);
             LinDgradArgs d{ws->t_dC, nullptr, p + o.Wf, 64, ws->t_G, nullptr, 0, nullptr, 0, a.cnt, pn + PN.conv_sf[i],
                            ws->t_dR, n_recv};
@@ -418,7 +424,7 @@ static int backward_impl(gcnn_workspace* ws, const float* p, const float* pn, co
         {
             LinWgradArgs w{left_in[i], nullptr, nullptr, dA, nullptr, nullptr, 64, n_left[i], 1, ws->partials[slot],
                            &n_parts};
-            GCNN_TRY(linear_wgrad(w, st));
+            GCNN_TRY(dense_wgrad(ws, w, st));
             add_job(ws->partials[slot++], n_parts, D * D + D, D * D + D, o.Wl);
             // the left input's gradient was already written by the concat branch iff the left side receives
             LinDgradArgs d{dA, nullptr, p + o.Wl, 64, d_left[i], nullptr, recv_is_left[i] ? 1 : 0, nullptr, 0, nullptr,
@@ -428,7 +434,7 @@ static int backward_impl(gcnn_workspace* ws, const float* p, const float* pn, co
         // right projection B = X_v Wr
         {
             LinWgradArgs w{var_in[i], nullptr, nullptr, dB, nullptr, nullptr, 64, nv, 0, ws->partials[slot], &n_parts};
-            GCNN_TRY(linear_wgrad(w, st));
+            GCNN_TRY(dense_wgrad(ws, w, st));
             add_job(ws->partials[slot++], n_parts, D * D + D, D * D, o.Wr);
             int acc = 0;
             if (d_var[i] == ws->dv0) { acc = dv0_written ? 1 : 0; dv0_written = true; }
@@ -445,7 +451,7 @@ static int backward_impl(gcnn_workspace* ws, const float* p, const float* pn, co
         {b->cut_feats, GCNN_CUT_FEATS, PN.cut_shift, PN.cut_scale, &P.cut, ws->h1k, ws->k0, ws->dk0, nk}};
     for (auto& e : emb) {
         LinWgradArgs w{e.h1, nullptr, nullptr, e.dout, e.out, nullptr, 64, e.n, 1, ws->partials[slot], &n_parts};
-        GCNN_TRY(linear_wgrad(w, st));
+        GCNN_TRY(dense_wgrad(ws, w, st));
         add_job(ws->partials[slot++], n_parts, D * D + D, D * D + D, e.o->W2);
         LinDgradArgs d{e.dout, e.out, p + e.o->W2, 64, ws->t_dh1, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, e.n};
         GCNN_TRY(dense_dgrad(ws, p, d, st));

@@ -195,6 +195,19 @@ struct TcArgs {
     int64_t M;
 };
 int tc_linear(const TcArgs& a, int prof_class, double prof_bytes, cudaStream_t st);
+struct TcWgradArgs {
+    const float* X;         // [M, 64] (left half when K = 128)
+    const float* X2;        // right half (K = 128)
+    const float* x_scale;   // device scalar on the left half
+    const float* dY;        // [M, 64]
+    const float* mask_act;  // dY *= 1[mask_act > 0], or nullptr
+    const int32_t* deg_ptr; // bias gradient weighted by the segment length, or nullptr
+    int K;
+    int64_t M;
+    float* partials;        // [n_parts, K*64 + 64]
+    int* n_parts;           // out (host)
+};
+int tc_wgrad(const TcWgradArgs& a, cudaStream_t st);
 int pack_weights(const float* params, const int* block_offsets_dev, int n_blocks, float* images, cudaStream_t st);
 constexpr int TC_IMG_FLOATS = 4 * 64 * 64;  // T_hi, T_lo, N_hi, N_lo of one 64 x 64 weight block
 

@@ -49,6 +49,20 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+// streaming 16-byte load: activations are read once per kernel, keep them out of L1
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
 // D[tmem] (+)= A[smem desc] * B[smem desc], tf32 inputs, fp32 accumulate, M = 128, N = 64, K = 8
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate) {
@@ -168,40 +182,57 @@ tc_linear_kernel(const TcArgs a) {
     if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), 64);
     if (tid == 0) mbar_init(smem_u32(&mma_bar), 1);
 
-    // B: copy the packed weight image(s) for this slab, one per 64-wide K block
+    // B: asynchronous copy (cp.async, no registers) of the packed weight image(s) for this slab, one per 64-wide K block
 #pragma unroll
     for (int j = 0; j < K / 64; ++j) {
-        const float4* src = reinterpret_cast<const float4*>(a.img[slab][j]);  // [hi 16 KB][lo 16 KB]
+        const float* src = a.img[slab][j];  // [hi 16 KB][lo 16 KB]
         for (int i = tid; i < IMG_FLOATS / 4; i += TC_THREADS) {
-            reinterpret_cast<float4*>(B_hi + j * 2 * B_BLOCK_BYTES)[i] = src[i];
-            reinterpret_cast<float4*>(B_lo + j * 2 * B_BLOCK_BYTES)[i] = src[IMG_FLOATS / 4 + i];
+            cp_async16(smem_u32(B_hi + j * 2 * B_BLOCK_BYTES) + i * 16, src + i * 4);
+            cp_async16(smem_u32(B_lo + j * 2 * B_BLOCK_BYTES) + i * 16, src + IMG_FLOATS + i * 4);
         }
     }
-    // A: load, transform (scale / concat / ReLU mask), split, swizzled store
+    // A: issue every global load of this thread first (one HBM latency instead of eight), then transform (scale /
+    // concat / ReLU mask), split into tf32 hi + residual lo, and store swizzled
+    constexpr int NX = TC_ROWS * (K / 4) / TC_THREADS;
     const float xs = a.x_scale ? *a.x_scale : 1.f;
-    for (int i = tid; i < TC_ROWS * (K / 4); i += TC_THREADS) {
+    float4 xv[NX];
+#pragma unroll
+    for (int it = 0; it < NX; ++it) {
+        const int i = tid + it * TC_THREADS;
         const int r = i / (K / 4), c4 = i % (K / 4);
         const int64_t m = row0 + r;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (m < a.M) {
-            if (c4 < 16) {
-                v = *reinterpret_cast<const float4*>(a.X + m * D + c4 * 4);
-                if (a.mask_act) {
-                    const float4 y = *reinterpret_cast<const float4*>(a.mask_act + m * D + c4 * 4);
-                    v.x = y.x > 0.f ? v.x : 0.f; v.y = y.y > 0.f ? v.y : 0.f;
-                    v.z = y.z > 0.f ? v.z : 0.f; v.w = y.w > 0.f ? v.w : 0.f;
-                }
-                v.x *= xs; v.y *= xs; v.z *= xs; v.w *= xs;
-            } else {
-                v = *reinterpret_cast<const float4*>(a.X2 + m * D + (c4 - 16) * 4);
-            }
+        xv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < a.M) xv[it] = ldg_stream4((c4 < 16 ? a.X + m * D + c4 * 4 : a.X2 + m * D + (c4 - 16) * 4));
+    }
+    if (K == 64 && a.mask_act) {
+        float4 mv[NX];
+#pragma unroll
+        for (int it = 0; it < NX; ++it) {
+            const int i = tid + it * TC_THREADS;
+            const int r = i / (K / 4), c4 = i % (K / 4);
+            const int64_t m = row0 + r;
+            mv[it] = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (m < a.M) mv[it] = ldg_stream4(a.mask_act + m * D + c4 * 4);
         }
+#pragma unroll
+        for (int it = 0; it < NX; ++it) {
+            xv[it].x = mv[it].x > 0.f ? xv[it].x : 0.f; xv[it].y = mv[it].y > 0.f ? xv[it].y : 0.f;
+            xv[it].z = mv[it].z > 0.f ? xv[it].z : 0.f; xv[it].w = mv[it].w > 0.f ? xv[it].w : 0.f;
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < NX; ++it) {
+        const int i = tid + it * TC_THREADS;
+        const int r = i / (K / 4), c4 = i % (K / 4);
+        float4 v = xv[it];
+        if (c4 < 16) { v.x *= xs; v.y *= xs; v.z *= xs; v.w *= xs; }
         float4 hi, lo;
         split4(v, hi, lo);
         const uint32_t off = swz_chunk_off(r, c4 * 4, TC_ROWS);
         *reinterpret_cast<float4*>(A_hi + off) = hi;
         *reinterpret_cast<float4*>(A_lo + off) = lo;
     }
+    cp_async_wait_all();
     fence_async_smem();  // generic-proxy writes -> visible to the tensor-core (async) proxy
     tc_fence_before();
     __syncthreads();
@@ -269,6 +300,174 @@ tc_linear_kernel(const TcArgs a) {
     if (warp == 0) tmem_dealloc(tmem_d, 64);
 }
 
+// ---- weight gradient on the tensor cores ----------------------------------------------------------------------------
+// dW[f, c] = sum_m Xcat[m, f] * dYp[m, c] is a GEMM whose reduction runs over ROWS, so the row-major tiles
+// [row][32 floats] are MN-major operands (MN = the 32 contiguous features / columns, K = the rows): no transpose is
+// needed, A = X tile (M dim = features), B = dYp tile (N dim = output columns), UMMA K = 8 rows per instruction.
+// Persistent CTAs accumulate their row tiles in TMEM and write one partial each; reduce_partials() sums them in a
+// fixed order (deterministic, no atomics).  The bias gradient (column sums of dYp, optionally weighted by the segment
+// length) is accumulated in registers on the way in.
+// MN-major tf32 operands must use the 128B-swizzle-with-32B-base layout (cute::UMMA::Layout_MN_SW128_32B_Atom:
+// Swizzle<2,5,2>): a 128-byte line holds 32 consecutive MN elements of one K index (= one row), four lines form a
+// 512-byte atom, and the 32-byte chunk c of line r sits at chunk position c ^ (r & 3).
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)(A_BLOCK_BYTES >> 4) << 16;  // leading byte offset: next 32-wide MN block
+    d |= (uint64_t)(512 >> 4) << 32;            // stride byte offset: next 4-row K group
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;                     // SWIZZLE_128B_BASE32B
+    return d;
+}
+// Byte offset of floats [f, f+4) of row r in an MN-major tile of 128 rows per 32-wide block.
+__device__ __forceinline__ uint32_t swz_mn_off(int r, int f) {
+    const int fb = f >> 5, c = (f & 31) >> 3;
+    return (uint32_t)(fb * A_BLOCK_BYTES + (r >> 2) * 512 + (r & 3) * 128 + ((c ^ (r & 3)) << 5) + ((f & 7) >> 2) * 16);
+}
+constexpr uint32_t IDESC_TF32_MN_128x64 = IDESC_TF32_128x64 | (1u << 15) | (1u << 16);  // A and B MN-major
+
+template <int K>
+__global__ void __launch_bounds__(TC_THREADS)
+tc_wgrad_kernel(const TcWgradArgs a) {
+    constexpr int KB = K / 32;
+    constexpr uint32_t A_PART = KB * A_BLOCK_BYTES, B_PART = 2 * A_BLOCK_BYTES;
+    constexpr int NA = TC_ROWS * (K / 4) / TC_THREADS;  // float4 loads of X per thread per tile (8 or 16)
+    constexpr int NB = TC_ROWS * (D / 4) / TC_THREADS;  // float4 loads of dY per thread per tile (8)
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t mma_bar;
+    __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float bias_red[16][D];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+    // layout: A_hi | A_lo | B_hi | B_lo.  With K = 64 the M = 128 instruction reads two blocks past each A part
+    // (rows 64..127 of D are never read back); those reads stay inside this allocation.
+    uint8_t* A_hi = gen;
+    uint8_t* A_lo = gen + A_PART;
+    uint8_t* B_hi = gen + 2 * A_PART;
+    uint8_t* B_lo = gen + 2 * A_PART + B_PART;
+
+    if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), 64);
+    if (tid == 0) mbar_init(smem_u32(&mma_bar), 1);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_slot;
+
+    const int64_t n_tiles = ceil_div(a.M, TC_ROWS);
+    const float xs = a.x_scale ? *a.x_scale : 1.f;
+    float4 xa[NA], dy[NB];
+    float dw_row[NB];
+    float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    auto prefetch = [&](int64_t tile) {
+        const int64_t row0 = tile * TC_ROWS;
+#pragma unroll
+        for (int it = 0; it < NA; ++it) {
+            const int i = tid + it * TC_THREADS;
+            const int r = i / (K / 4), c4 = i % (K / 4);
+            const int64_t m = row0 + r;
+            xa[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < a.M) xa[it] = ldg_stream4(c4 < 16 ? a.X + m * D + c4 * 4 : a.X2 + m * D + (c4 - 16) * 4);
+        }
+#pragma unroll
+        for (int it = 0; it < NB; ++it) {
+            const int i = tid + it * TC_THREADS;
+            const int r = i >> 4, c4 = i & 15;
+            const int64_t m = row0 + r;
+            dy[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            dw_row[it] = 0.f;
+            if (m < a.M) {
+                dy[it] = ldg_stream4(a.dY + m * D + c4 * 4);
+                if (a.mask_act) {
+                    const float4 y = ldg_stream4(a.mask_act + m * D + c4 * 4);
+                    dy[it].x = y.x > 0.f ? dy[it].x : 0.f; dy[it].y = y.y > 0.f ? dy[it].y : 0.f;
+                    dy[it].z = y.z > 0.f ? dy[it].z : 0.f; dy[it].w = y.w > 0.f ? dy[it].w : 0.f;
+                }
+                dw_row[it] = a.deg_ptr ? (float)(a.deg_ptr[m + 1] - a.deg_ptr[m]) : 1.f;
+            }
+        }
+    };
+
+    int iter = 0;
+    if ((int64_t)blockIdx.x < n_tiles) prefetch(blockIdx.x);
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
+        if (iter > 0) mbar_wait(smem_u32(&mma_bar), (uint32_t)((iter - 1) & 1));  // tensor core done with the buffers
+#pragma unroll
+        for (int it = 0; it < NA; ++it) {
+            const int i = tid + it * TC_THREADS;
+            const int r = i / (K / 4), c4 = i % (K / 4);
+            float4 v = xa[it];
+            if (c4 < 16) { v.x *= xs; v.y *= xs; v.z *= xs; v.w *= xs; }
+            float4 hi, lo;
+            split4(v, hi, lo);
+            const uint32_t off = swz_mn_off(r, c4 * 4);
+            *reinterpret_cast<float4*>(A_hi + off) = hi;
+            *reinterpret_cast<float4*>(A_lo + off) = lo;
+        }
+#pragma unroll
+        for (int it = 0; it < NB; ++it) {
+            const int i = tid + it * TC_THREADS;
+            const int r = i >> 4, c4 = i & 15;
+            float4 hi, lo;
+            split4(dy[it], hi, lo);
+            const uint32_t off = swz_mn_off(r, c4 * 4);
+            *reinterpret_cast<float4*>(B_hi + off) = hi;
+            *reinterpret_cast<float4*>(B_lo + off) = lo;
+            bsum.x = fmaf(dw_row[it], dy[it].x, bsum.x); bsum.y = fmaf(dw_row[it], dy[it].y, bsum.y);
+            bsum.z = fmaf(dw_row[it], dy[it].z, bsum.z); bsum.w = fmaf(dw_row[it], dy[it].w, bsum.w);
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (tid == 0) {
+            const uint32_t a_addr[2] = {base, base + A_PART};
+            const uint32_t b_addr[2] = {base + 2 * A_PART, base + 2 * A_PART + B_PART};
+            const int sel[3][2] = {{1, 0}, {0, 1}, {0, 0}};
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+#pragma unroll
+                for (int ks = 0; ks < TC_ROWS / 8; ++ks) {
+                    const uint64_t da = make_desc_mn(a_addr[sel[p][0]] + ks * 1024);
+                    const uint64_t db = make_desc_mn(b_addr[sel[p][1]] + ks * 1024);
+                    umma_tf32(tmem_d, da, db, IDESC_TF32_MN_128x64, (iter > 0 || p > 0 || ks > 0) ? 1u : 0u);
+                }
+            }
+            umma_commit(smem_u32(&mma_bar));
+        }
+        if (tile + gridDim.x < n_tiles) prefetch(tile + gridDim.x);  // next tile's loads fly while the MMAs run
+    }
+    float* part = a.partials + (int64_t)blockIdx.x * (K * D + D);
+    const int q = warp & 3, ch = warp >> 2;
+    if (iter > 0) {
+        mbar_wait(smem_u32(&mma_bar), (uint32_t)((iter - 1) & 1));
+        tc_fence_after();
+        if (q * 32 < K) {  // warp-uniform: feature rows [32 q, 32 q + 32) exist
+            float v[32];
+            tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
+            float* dst = part + (q * 32 + lane) * D + ch * 32;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+    } else {
+        for (int i = tid; i < K * D; i += TC_THREADS) part[i] = 0.f;
+    }
+    // bias gradient: threads sharing a column group (tid & 15) are 16 row groups apart
+    *reinterpret_cast<float4*>(&bias_red[tid >> 4][(tid & 15) * 4]) = bsum;
+    tc_fence_before();
+    __syncthreads();
+    if (tid < D) {
+        float t = 0.f;
+#pragma unroll
+        for (int g = 0; g < 16; ++g) t += bias_red[g][tid];
+        part[K * D + tid] = t;
+    }
+    if (warp == 0) tmem_dealloc(tmem_d, 64);
+}
+
 template <typename Kern>
 static int set_smem_tc(Kern kern, size_t bytes) {
     GCNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -291,6 +490,28 @@ int tc_linear(const TcArgs& a, int prof_class, double prof_bytes, cudaStream_t s
         tc_linear_kernel<128><<<grid, TC_THREADS, smem, st>>>(a);
     } else {
         set_error("tc_linear: K must be 64 or 128");
+        return GCNN_INVALID;
+    }
+    GCNN_LAUNCH_CHECK();
+    return GCNN_OK;
+}
+
+int tc_wgrad(const TcWgradArgs& a, cudaStream_t st) {
+    const int parts = (int)min((int64_t)NUM_SMS, ceil_div(a.M > 0 ? a.M : 1, TC_ROWS));
+    *a.n_parts = parts;
+    ProfScope prof(PROF_LIN_WGRAD, 4.0 * ((double)a.M * (a.K + D + (a.mask_act ? D : 0)) + (double)a.K * D + D), st);
+    if (a.K == 64) {
+        const size_t smem = 8 * A_BLOCK_BYTES + 1024;
+        static int once = set_smem_tc(tc_wgrad_kernel<64>, smem);
+        GCNN_TRY(once);
+        tc_wgrad_kernel<64><<<parts, TC_THREADS, smem, st>>>(a);
+    } else if (a.K == 128) {
+        const size_t smem = 12 * A_BLOCK_BYTES + 1024;
+        static int once = set_smem_tc(tc_wgrad_kernel<128>, smem);
+        GCNN_TRY(once);
+        tc_wgrad_kernel<128><<<parts, TC_THREADS, smem, st>>>(a);
+    } else {
+        set_error("tc_wgrad: K must be 64 or 128");
         return GCNN_INVALID;
     }
     GCNN_LAUNCH_CHECK();
