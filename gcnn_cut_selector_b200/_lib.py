@@ -49,6 +49,7 @@ SIGNATURES = {
     "gcnn_workspace_destroy": (_I, [_P]),
     "gcnn_workspace_reserve": (_I, [_P, _I64, _I64, _I64, _I64, _I64, _I]),
     "gcnn_workspace_bytes": (_I64, [_P]),
+    "gcnn_set_option": (_I, [_P, C.c_char_p, _I]),
     "gcnn_check": (_I, [_P, _P]),
     "gcnn_build_csr": (_I, [_P, _I, _P, _P, _I64, _I64, _I64, _I, _P]),
     "gcnn_csr_export": (_I, [_P, _I, _I, _P, _P, _P, _P, _P]),

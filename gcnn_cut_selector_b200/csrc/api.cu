@@ -92,6 +92,13 @@ struct gcnn_workspace {
     // host staging mirrors (device side)
     float *s_cons, *s_cef, *s_var, *s_cut, *s_kef, *s_targets;
     int32_t *s_cei, *s_kei;
+    // auxiliary streams: independent kernels (CSR build, the two projections of a convolution, weight gradients) run
+    // concurrently with the main chain; fork/join with events, nothing synchronises the host
+    int use_streams = 1;
+    cudaStream_t aux[2] = {nullptr, nullptr};
+    cudaEvent_t ev[16] = {};
+    int ev_next = 0;
+    float* t_dh1b = nullptr;
     // tensor-core path: packed 3xTF32 weight images, one per 64 x 64 weight block
     int use_tc = 1;
     float* tc_images = nullptr;
@@ -196,7 +203,7 @@ static size_t carve(gcnn_workspace* ws, char* base, const Caps& c) {
         ws->dk1 = rows(nk); ws->dv1 = rows(nv); ws->dc1 = rows(nc);
         ws->dk0 = rows(nk); ws->dv0 = rows(nv); ws->dc0 = rows(nc);
         ws->t_dU1 = rows(nmax); ws->t_dC = rows(nmax); ws->t_G = rows(nmax); ws->t_dR = rows(nmax);
-        ws->t_dS = rows(nmax); ws->t_dh1 = rows(nmax); ws->t_dg = rows(nk);
+        ws->t_dS = rows(nmax); ws->t_dh1 = rows(nmax); ws->t_dh1b = rows(nmax); ws->t_dg = rows(nk);
         const int64_t parts = wgrad_max_parts();
         for (int i = 0; i < 32; ++i) ws->partials[i] = cv.take<float>(parts * (2 * D * D + D));
         for (int i = 0; i < 3; ++i) ws->dw_partials[i] = cv.take<float>((int64_t)edge_backward_max_partials() * D);
@@ -216,6 +223,20 @@ static int check_batch(const gcnn_workspace* ws, const gcnn_batch* b, int traini
     if (!ws->arena || !fits(ws->cap, b->n_cons, b->n_vars, b->n_cuts, b->n_cons_edges, b->n_cut_edges, training)) {
         set_error("workspace too small for this batch: call gcnn_workspace_reserve first"); return GCNN_INVALID;
     }
+    return GCNN_OK;
+}
+
+// ---- stream fork / join ------------------------------------------------------------------------------------------
+static cudaStream_t aux_stream(gcnn_workspace* ws, int i, cudaStream_t main_st) {
+    return (ws->use_streams && ws->aux[i]) ? ws->aux[i] : main_st;
+}
+// work enqueued on `to` after this call starts only when everything enqueued on `from` so far has finished
+static int stream_edge(gcnn_workspace* ws, cudaStream_t from, cudaStream_t to) {
+    if (from == to) return GCNN_OK;
+    cudaEvent_t e = ws->ev[ws->ev_next];
+    ws->ev_next = (ws->ev_next + 1) % 16;
+    GCNN_CUDA_TRY(cudaEventRecord(e, from));
+    GCNN_CUDA_TRY(cudaStreamWaitEvent(to, e, 0));
     return GCNN_OK;
 }
 
@@ -259,31 +280,39 @@ static int forward_impl(gcnn_workspace* ws, const float* p, const float* pn, con
                         int stop_layer, cudaStream_t st) {
     const int64_t nc = b->n_cons, nv = b->n_vars, nk = b->n_cuts, ec = b->n_cons_edges, ek = b->n_cut_edges;
 
+    cudaStream_t s1 = aux_stream(ws, 0, st), s2 = aux_stream(ws, 1, st);
+
+    // F1: edge layouts on an auxiliary stream, concurrent with the embeddings.  conv 0 reduces by constraint, conv 1
+    // by variable (both over constraint edges), conv 2 by cut; the opposite grouping serves the backward pass.
+    GCNN_TRY(stream_edge(ws, st, s1));
+    GCNN_TRY(build_layout(b->cons_edge_inds, b->cons_edge_inds + ec, b->cons_edge_feats, ec, nc, nv, ws->sort,
+                          ws->flags + 1, ws->graph[0].by_left, s1));
+    GCNN_TRY(build_layout(b->cons_edge_inds + ec, b->cons_edge_inds, b->cons_edge_feats, ec, nv, nc, ws->sort,
+                          ws->flags + 1, ws->graph[0].by_var, s1));
+    GCNN_TRY(build_layout(b->cut_edge_inds, b->cut_edge_inds + ek, b->cut_edge_feats, ek, nk, nv, ws->sort,
+                          ws->flags + 1, ws->graph[1].by_left, s1));
+    if (ws->cap.training)
+        GCNN_TRY(build_layout(b->cut_edge_inds + ek, b->cut_edge_inds, b->cut_edge_feats, ek, nv, nk, ws->sort,
+                              ws->flags + 1, ws->graph[1].by_var, s1));
+
     if (ws->use_tc)
         GCNN_TRY(pack_weights(p, ws->tc_block_offsets, (int)tc_blocks().size(), ws->tc_images, st));
 
-    // F1: edge layouts.  conv 0 reduces by constraint, conv 1 by variable (both over constraint edges),
-    // conv 2 by cut; the opposite grouping of each edge set serves the backward pass.
-    GCNN_TRY(build_layout(b->cons_edge_inds, b->cons_edge_inds + ec, b->cons_edge_feats, ec, nc, nv, ws->sort,
-                          ws->flags + 1, ws->graph[0].by_left, st));
-    GCNN_TRY(build_layout(b->cons_edge_inds + ec, b->cons_edge_inds, b->cons_edge_feats, ec, nv, nc, ws->sort,
-                          ws->flags + 1, ws->graph[0].by_var, st));
-    GCNN_TRY(build_layout(b->cut_edge_inds, b->cut_edge_inds + ek, b->cut_edge_feats, ek, nk, nv, ws->sort,
-                          ws->flags + 1, ws->graph[1].by_left, st));
-    if (ws->cap.training)
-        GCNN_TRY(build_layout(b->cut_edge_inds + ek, b->cut_edge_inds, b->cut_edge_feats, ek, nv, nk, ws->sort,
-                              ws->flags + 1, ws->graph[1].by_var, st));
-
-    // embeddings (model.py:287-291)
+    // embeddings (model.py:287-291): the variable embedding (largest) on its own stream
     struct { const float* x; int K; int shift, scale; const EmbOff* o; float *h1, *out; int64_t n; } emb[3] = {
         {b->cons_feats, GCNN_CONS_FEATS, PN.cons_shift, PN.cons_scale, &P.cons, ws->h1c, ws->c0, nc},
         {b->var_feats, GCNN_VAR_FEATS, PN.var_shift, PN.var_scale, &P.var, ws->h1v, ws->v0, nv},
         {b->cut_feats, GCNN_CUT_FEATS, PN.cut_shift, PN.cut_scale, &P.cut, ws->h1k, ws->k0, nk}};
-    for (auto& e : emb) {
-        GCNN_TRY(embed1_forward(e.x, e.K, pn + e.shift, pn + e.scale, p + e.o->W1, p + e.o->b1, e.h1, e.n, st));
+    GCNN_TRY(stream_edge(ws, st, s2));  // after pack_weights
+    for (int e_i = 0; e_i < 3; ++e_i) {
+        auto& e = emb[e_i];
+        cudaStream_t se = e_i == 1 ? s2 : st;
+        GCNN_TRY(embed1_forward(e.x, e.K, pn + e.shift, pn + e.scale, p + e.o->W1, p + e.o->b1, e.h1, e.n, se));
         LinFwdArgs a{e.h1, nullptr, nullptr, p + e.o->W2, p + e.o->b2, nullptr, e.out, e.n, 64, 1};
-        GCNN_TRY(dense_forward(ws, p, a, st));
+        GCNN_TRY(dense_forward(ws, p, a, se));
     }
+    GCNN_TRY(stream_edge(ws, s2, st));  // v0 ready
+    GCNN_TRY(stream_edge(ws, s1, st));  // edge layouts ready
 
     // convolutions (model.py:294-296): {left feats, var feats, receiving side, graph, edge pre-norm}
     const float* left_in[3] = {ws->c0, ws->conv[0].Y, ws->k0};
@@ -298,10 +327,13 @@ static int forward_impl(gcnn_workspace* ws, const float* p, const float* pn, con
         ConvActs& a = ws->conv[i];
         const int64_t n_recv = recv_is_left[i] ? n_left[i] : nv;
         const float* recv_in = recv_is_left[i] ? left_in[i] : var_in[i];
+        // the two projections are independent: left on the main stream, right on an auxiliary one
+        GCNN_TRY(stream_edge(ws, st, s2));
         LinFwdArgs pa{left_in[i], nullptr, nullptr, p + o.Wl, p + o.bl, nullptr, a.A, n_left[i], 64, 0};
         GCNN_TRY(dense_forward(ws, p, pa, st));
         LinFwdArgs pb{var_in[i], nullptr, nullptr, p + o.Wr, nullptr, nullptr, a.B, nv, 64, 0};
-        GCNN_TRY(dense_forward(ws, p, pb, st));
+        GCNN_TRY(dense_forward(ws, p, pb, s2));
+        GCNN_TRY(stream_edge(ws, s2, st));
         const EdgeLayout& L = recv_is_left[i] ? ws->graph[graph_of[i]].by_left : ws->graph[graph_of[i]].by_var;
         const float* R = recv_is_left[i] ? a.A : a.B;
         const float* S = recv_is_left[i] ? a.B : a.A;
@@ -338,6 +370,8 @@ static int backward_impl(gcnn_workspace* ws, const float* p, const float* pn, co
         jobs.push_back(ReduceJob{part, n_parts, stride, count, dst});
     };
     int n_parts = 0;
+    // weight gradients run on an auxiliary stream, concurrent with the input-gradient chain on the main stream
+    cudaStream_t s2 = aux_stream(ws, 1, st);
 
     // head
     GCNN_TRY(head2_backward(ws->g1, p + P.Wh2, d_scores, ws->t_dg, ws->partials[slot], &n_parts, nk, st));
@@ -345,7 +379,8 @@ static int backward_impl(gcnn_workspace* ws, const float* p, const float* pn, co
     {
         LinWgradArgs w{ws->conv[2].Y, nullptr, nullptr, ws->t_dg, nullptr, nullptr, 64, nk, 1, ws->partials[slot],
                        &n_parts};
-        GCNN_TRY(dense_wgrad(ws, w, st));
+        GCNN_TRY(stream_edge(ws, st, s2));
+            GCNN_TRY(dense_wgrad(ws, w, s2));
         add_job(ws->partials[slot++], n_parts, D * D + D, D * D + D, P.Wh1);
         LinDgradArgs d{ws->t_dg, nullptr, p + P.Wh1, 64, ws->dk1, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, nk};
         GCNN_TRY(dense_dgrad(ws, p, d, st));
@@ -378,7 +413,8 @@ static int backward_impl(gcnn_workspace* ws, const float* p, const float* pn, co
         // output MLP layer 2: Y = relu(U1 Wo2 + bo2)
         {
             LinWgradArgs w{a.U1, nullptr, nullptr, dY, a.Y, nullptr, 64, n_recv, 1, ws->partials[slot], &n_parts};
-            GCNN_TRY(dense_wgrad(ws, w, st));
+            GCNN_TRY(stream_edge(ws, st, s2));
+            GCNN_TRY(dense_wgrad(ws, w, s2));
             add_job(ws->partials[slot++], n_parts, D * D + D, D * D + D, o.Wo2);
             LinDgradArgs d{dY, a.Y, p + o.Wo2, 64, ws->t_dU1, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, n_recv};
             GCNN_TRY(dense_dgrad(ws, p, d, st));
@@ -387,7 +423,8 @@ static int backward_impl(gcnn_workspace* ws, const float* p, const float* pn, co
         {
             LinWgradArgs w{a.C, recv_in, pn + PN.conv_sp[i], ws->t_dU1, a.U1, nullptr, 128, n_recv, 1,
                            ws->partials[slot], &n_parts};
-            GCNN_TRY(dense_wgrad(ws, w, st));
+            GCNN_TRY(stream_edge(ws, st, s2));
+            GCNN_TRY(dense_wgrad(ws, w, s2));
             add_job(ws->partials[slot++], n_parts, 2 * D * D + D, 2 * D * D + D, o.Wo1);
             // which earlier op already wrote the receiving input's gradient?
             int acc2 = 0;
@@ -400,7 +437,8 @@ static int backward_impl(gcnn_workspace* ws, const float* p, const float* pn, co
         {
             LinWgradArgs w{a.H, nullptr, nullptr, ws->t_dC, nullptr, Lr.ptr, 64, n_recv, 1, ws->partials[slot],
                            &n_parts};
-            GCNN_TRY(dense_wgrad(ws, w, st));
+            GCNN_TRY(stream_edge(ws, st, s2));
+            GCNN_TRY(dense_wgrad(ws, w, s2));
             add_job(ws->partials[slot++], n_parts, D * D + D, D * D + D, o.Wf);
             LinDgradArgs d{ws->t_dC, nullptr, p + o.Wf, 64, ws->t_G, nullptr, 0, nullptr, 0, a.cnt, pn + PN.conv_sf[i],
                            ws->t_dR, n_recv};
@@ -424,7 +462,8 @@ static int backward_impl(gcnn_workspace* ws, const float* p, const float* pn, co
         {
             LinWgradArgs w{left_in[i], nullptr, nullptr, dA, nullptr, nullptr, 64, n_left[i], 1, ws->partials[slot],
                            &n_parts};
-            GCNN_TRY(dense_wgrad(ws, w, st));
+            GCNN_TRY(stream_edge(ws, st, s2));
+            GCNN_TRY(dense_wgrad(ws, w, s2));
             add_job(ws->partials[slot++], n_parts, D * D + D, D * D + D, o.Wl);
             // the left input's gradient was already written by the concat branch iff the left side receives
             LinDgradArgs d{dA, nullptr, p + o.Wl, 64, d_left[i], nullptr, recv_is_left[i] ? 1 : 0, nullptr, 0, nullptr,
@@ -434,7 +473,8 @@ static int backward_impl(gcnn_workspace* ws, const float* p, const float* pn, co
         // right projection B = X_v Wr
         {
             LinWgradArgs w{var_in[i], nullptr, nullptr, dB, nullptr, nullptr, 64, nv, 0, ws->partials[slot], &n_parts};
-            GCNN_TRY(dense_wgrad(ws, w, st));
+            GCNN_TRY(stream_edge(ws, st, s2));
+            GCNN_TRY(dense_wgrad(ws, w, s2));
             add_job(ws->partials[slot++], n_parts, D * D + D, D * D, o.Wr);
             int acc = 0;
             if (d_var[i] == ws->dv0) { acc = dv0_written ? 1 : 0; dv0_written = true; }
@@ -442,6 +482,7 @@ static int backward_impl(gcnn_workspace* ws, const float* p, const float* pn, co
             LinDgradArgs d{dB, nullptr, p + o.Wr, 64, d_var[i], nullptr, acc, nullptr, 0, nullptr, nullptr, nullptr, nv};
             GCNN_TRY(dense_dgrad(ws, p, d, st));
         }
+        GCNN_TRY(stream_edge(ws, s2, st));  // the scratch tensors the weight gradients read are rewritten next
     }
 
     // embeddings: out = relu(h1 W2 + b2), h1 = relu(xn W1 + b1)
@@ -449,16 +490,20 @@ static int backward_impl(gcnn_workspace* ws, const float* p, const float* pn, co
         {b->cons_feats, GCNN_CONS_FEATS, PN.cons_shift, PN.cons_scale, &P.cons, ws->h1c, ws->c0, ws->dc0, nc},
         {b->var_feats, GCNN_VAR_FEATS, PN.var_shift, PN.var_scale, &P.var, ws->h1v, ws->v0, ws->dv0, nv},
         {b->cut_feats, GCNN_CUT_FEATS, PN.cut_shift, PN.cut_scale, &P.cut, ws->h1k, ws->k0, ws->dk0, nk}};
-    for (auto& e : emb) {
+    GCNN_TRY(stream_edge(ws, st, s2));
+    for (int e_i = 0; e_i < 3; ++e_i) {  // three independent chains: the variable one (largest) on the auxiliary stream
+        auto& e = emb[e_i];
+        cudaStream_t se = e_i == 1 ? s2 : st;
+        float* dh1 = e_i == 1 ? ws->t_dh1b : ws->t_dh1;
         LinWgradArgs w{e.h1, nullptr, nullptr, e.dout, e.out, nullptr, 64, e.n, 1, ws->partials[slot], &n_parts};
-        GCNN_TRY(dense_wgrad(ws, w, st));
+        GCNN_TRY(dense_wgrad(ws, w, se));
         add_job(ws->partials[slot++], n_parts, D * D + D, D * D + D, e.o->W2);
-        LinDgradArgs d{e.dout, e.out, p + e.o->W2, 64, ws->t_dh1, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, e.n};
-        GCNN_TRY(dense_dgrad(ws, p, d, st));
-        GCNN_TRY(embed1_wgrad(e.x, e.K, pn + e.shift, pn + e.scale, ws->t_dh1, e.h1, e.n, ws->partials[slot], &n_parts,
-                              st));
+        LinDgradArgs d{e.dout, e.out, p + e.o->W2, 64, dh1, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, e.n};
+        GCNN_TRY(dense_dgrad(ws, p, d, se));
+        GCNN_TRY(embed1_wgrad(e.x, e.K, pn + e.shift, pn + e.scale, dh1, e.h1, e.n, ws->partials[slot], &n_parts, se));
         add_job(ws->partials[slot++], n_parts, (e.K + 1) * D, (e.K + 1) * D, e.o->W1);
     }
+    GCNN_TRY(stream_edge(ws, s2, st));
     return reduce_partials(jobs.data(), (int)jobs.size(), grads, st);
 }
 
@@ -590,6 +635,10 @@ int gcnn_workspace_create(gcnn_workspace** out) {
     if (!ws) { set_error("host allocation failed"); return GCNN_OOM; }
     const char* tc = getenv("GCNN_TC");  // GCNN_TC=0 selects the exact-fp32 SIMT dense kernels
     ws->use_tc = !(tc && tc[0] == '0');
+    const char* ms = getenv("GCNN_STREAMS");  // GCNN_STREAMS=0 serialises everything on the caller's stream
+    ws->use_streams = !(ms && ms[0] == '0');
+    for (int i = 0; i < 2; ++i) GCNN_CUDA_TRY(cudaStreamCreateWithFlags(&ws->aux[i], cudaStreamNonBlocking));
+    for (int i = 0; i < 16; ++i) GCNN_CUDA_TRY(cudaEventCreateWithFlags(&ws->ev[i], cudaEventDisableTiming));
     *out = ws;
     return GCNN_OK;
 }
@@ -597,6 +646,8 @@ int gcnn_workspace_create(gcnn_workspace** out) {
 int gcnn_workspace_destroy(gcnn_workspace* ws) {
     if (!ws) return GCNN_OK;
     if (ws->arena) cudaFree(ws->arena);
+    for (int i = 0; i < 2; ++i) if (ws->aux[i]) cudaStreamDestroy(ws->aux[i]);
+    for (int i = 0; i < 16; ++i) if (ws->ev[i]) cudaEventDestroy(ws->ev[i]);
     delete ws;
     return GCNN_OK;
 }
@@ -628,6 +679,14 @@ int gcnn_workspace_reserve(gcnn_workspace* ws, int64_t nc, int64_t nv, int64_t n
     GCNN_CUDA_TRY(cudaMemset(ws->flags, 0, sizeof(int32_t) * 64));
     GCNN_CUDA_TRY(cudaMemcpy(ws->tc_block_offsets, tc_blocks().data(), sizeof(int) * tc_blocks().size(),
                              cudaMemcpyHostToDevice));
+    return GCNN_OK;
+}
+
+int gcnn_set_option(gcnn_workspace* ws, const char* name, int value) {
+    if (!ws || !name) { set_error("null argument"); return GCNN_INVALID; }
+    if (!strcmp(name, "tensor_cores")) ws->use_tc = value != 0;
+    else if (!strcmp(name, "streams")) ws->use_streams = value != 0;
+    else { set_error("unknown option %s", name); return GCNN_INVALID; }
     return GCNN_OK;
 }
 

@@ -228,6 +228,10 @@ class GCNN:
         check(self._lib.gcnn_workspace_reserve(self._ws, batch.n_cons, batch.n_vars, batch.n_cuts, batch.n_cons_edges,
                                                batch.n_cut_edges, int(training)))
 
+    def set_option(self, name: str, value: int):
+        """Library options: "tensor_cores" (tcgen05 3xTF32 vs exact-fp32 SIMT dense layers), "streams"."""
+        check(self._lib.gcnn_set_option(self._ws, name.encode(), int(value)))
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 

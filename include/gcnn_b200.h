@@ -85,6 +85,10 @@ int gcnn_workspace_destroy(gcnn_workspace* ws);
 int gcnn_workspace_reserve(gcnn_workspace* ws, int64_t n_cons, int64_t n_vars, int64_t n_cuts,
                            int64_t n_cons_edges, int64_t n_cut_edges, int training);
 int64_t gcnn_workspace_bytes(const gcnn_workspace* ws);
+/* Options: "tensor_cores" (1 = tcgen05 3xTF32 dense layers [default], 0 = exact-fp32 SIMT dense layers; env GCNN_TC),
+ * "streams" (1 = independent kernels on auxiliary streams [default], 0 = everything on the caller's stream; env
+ * GCNN_STREAMS).  Takes effect from the next call. */
+int gcnn_set_option(gcnn_workspace* ws, const char* name, int value);
 /* Synchronise `stream` and report deferred errors (GCNN_INVALID if any edge index was out of range). */
 int gcnn_check(gcnn_workspace* ws, void* stream);
 
