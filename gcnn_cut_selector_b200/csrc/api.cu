@@ -285,15 +285,18 @@ static int forward_impl(gcnn_workspace* ws, const float* p, const float* pn, con
     // F1: edge layouts on an auxiliary stream, concurrent with the embeddings.  conv 0 reduces by constraint, conv 1
     // by variable (both over constraint edges), conv 2 by cut; the opposite grouping serves the backward pass.
     GCNN_TRY(stream_edge(ws, st, s1));
+    GCNN_CUDA_TRY(cudaMemsetAsync(ws->flags + 2, 0, 4 * sizeof(int32_t), s1));  // per-layout "unsorted" flags
+    const bool cons_sorted = (b->flags & GCNN_BATCH_CONS_EDGES_SORTED) != 0;
+    const bool cuts_sorted = (b->flags & GCNN_BATCH_CUT_EDGES_SORTED) != 0;
     GCNN_TRY(build_layout(b->cons_edge_inds, b->cons_edge_inds + ec, b->cons_edge_feats, ec, nc, nv, ws->sort,
-                          ws->flags + 1, ws->graph[0].by_left, s1));
+                          ws->flags + 1, ws->flags + 2, cons_sorted, ws->graph[0].by_left, s1));
     GCNN_TRY(build_layout(b->cons_edge_inds + ec, b->cons_edge_inds, b->cons_edge_feats, ec, nv, nc, ws->sort,
-                          ws->flags + 1, ws->graph[0].by_var, s1));
+                          ws->flags + 1, ws->flags + 3, false, ws->graph[0].by_var, s1));
     GCNN_TRY(build_layout(b->cut_edge_inds, b->cut_edge_inds + ek, b->cut_edge_feats, ek, nk, nv, ws->sort,
-                          ws->flags + 1, ws->graph[1].by_left, s1));
+                          ws->flags + 1, ws->flags + 4, cuts_sorted, ws->graph[1].by_left, s1));
     if (ws->cap.training)
         GCNN_TRY(build_layout(b->cut_edge_inds + ek, b->cut_edge_inds, b->cut_edge_feats, ek, nv, nk, ws->sort,
-                              ws->flags + 1, ws->graph[1].by_var, s1));
+                              ws->flags + 1, ws->flags + 5, false, ws->graph[1].by_var, s1));
 
     if (ws->use_tc)
         GCNN_TRY(pack_weights(p, ws->tc_block_offsets, (int)tc_blocks().size(), ws->tc_images, st));
@@ -534,7 +537,8 @@ static int read_error_flag(gcnn_workspace* ws, cudaStream_t st) {
     GCNN_CUDA_TRY(cudaStreamSynchronize(st));
     if (flag) {
         GCNN_CUDA_TRY(cudaMemsetAsync(ws->flags + 1, 0, sizeof(int32_t), st));
-        set_error("edge index out of range (InvalidArgument, cf. tf.gather in model.py:564)");
+        if (flag & 1) set_error("edge index out of range (InvalidArgument, cf. tf.gather in model.py:564)");
+        else set_error("batch flags claim edges sorted by row 0 (utils.py:102-104 order) but they are not");
         return GCNN_INVALID;
     }
     return GCNN_OK;
@@ -703,9 +707,12 @@ int gcnn_build_csr(gcnn_workspace* ws, int which, const int32_t* ei, const float
     const int64_t cap_left = which == 0 ? ws->cap.nc : ws->cap.nk, cap_e = which == 0 ? ws->cap.ec : ws->cap.ek;
     if (n_left > cap_left || n_vars > ws->cap.nv || E > cap_e) { set_error("workspace too small"); return GCNN_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
-    GCNN_TRY(build_layout(ei, ei + E, ef, E, n_left, n_vars, ws->sort, ws->flags + 1, ws->graph[which].by_left, st));
+    GCNN_CUDA_TRY(cudaMemsetAsync(ws->flags + 2, 0, 4 * sizeof(int32_t), st));
+    GCNN_TRY(build_layout(ei, ei + E, ef, E, n_left, n_vars, ws->sort, ws->flags + 1, ws->flags + 2, false,
+                          ws->graph[which].by_left, st));
     if (need_transposed)
-        GCNN_TRY(build_layout(ei + E, ei, ef, E, n_vars, n_left, ws->sort, ws->flags + 1, ws->graph[which].by_var, st));
+        GCNN_TRY(build_layout(ei + E, ei, ef, E, n_vars, n_left, ws->sort, ws->flags + 1, ws->flags + 3, false,
+                              ws->graph[which].by_var, st));
     ws->last.n_vars = n_vars;
     if (which == 0) { ws->last.n_cons = n_left; ws->last.n_cons_edges = E; }
     else { ws->last.n_cuts = n_left; ws->last.n_cut_edges = E; }

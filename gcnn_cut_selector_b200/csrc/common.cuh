@@ -100,12 +100,13 @@ struct EdgeLayout {   // edges grouped by one endpoint ("owner"), stable in orig
 
 struct SortScratch {
     int32_t *key_a, *val_a, *key_b, *val_b;  // ping-pong pair buffers [E]
-    int32_t* hist;                           // [256 * n_blocks]
-    int32_t* flags;                          // [0] = "already sorted", [1] = "index out of range" (sticky)
+    int32_t* hist;                           // two buffers of [256 * n_blocks]
+    int32_t* flags;                          // workspace flag words: [0] scratch, [1] sticky error bits, [6] always 0
 };
 
 int build_layout(const int32_t* keys, const int32_t* others, const float* feats, int64_t E, int64_t n_owner,
-                 int64_t n_other, const SortScratch& sc, int32_t* err_flag, EdgeLayout out, cudaStream_t st);
+                 int64_t n_other, const SortScratch& sc, int32_t* err_flag, int32_t* unsorted_flag, bool hint_sorted,
+                 EdgeLayout out, cudaStream_t st);
 int64_t sort_hist_entries(int64_t E);
 
 // ---- edge kernels -------------------------------------------------------------------------------------------------

@@ -17,59 +17,61 @@ constexpr int SORT_ITEMS = 16;                         // items per thread per t
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;   // 4096 pairs per CTA
 constexpr int RADIX = 256;
 
-int64_t sort_hist_entries(int64_t E) { return RADIX * ceil_div(E > 0 ? E : 1, SORT_TILE); }
+int64_t sort_hist_entries(int64_t E) { return 2 * RADIX * ceil_div(E > 0 ? E : 1, SORT_TILE); }  // two buffers
 
-// flags[0] := 1 if keys are non-decreasing (caller presets 1), err_flag := 1 if any index is out of range.
-__global__ void check_keys_kernel(const int32_t* __restrict__ keys, const int32_t* __restrict__ others, int64_t E,
-                                  int32_t n_owner, int32_t n_other, int32_t* sorted_flag, int32_t* err_flag) {
-    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    bool unsorted = false, bad = false;
-    if (e < E) {
-        int32_t k = keys[e], o = others[e];
-        bad = (k < 0) | (k >= n_owner) | (o < 0) | (o >= n_other);
-        if (e > 0) unsorted = keys[e - 1] > k;
-    }
-    if (__any_sync(0xffffffffu, unsorted) && (threadIdx.x & 31) == 0) *sorted_flag = 0;
-    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) *err_flag = 1;
-}
-
-__global__ void set_flag_kernel(int32_t* flag, int32_t v) { *flag = v; }
-
-// Clamp keys into range (so a bad index cannot make later kernels write out of bounds) and pair them with edge ids.
-__global__ void init_pairs_kernel(const int32_t* __restrict__ keys, int64_t E, int32_t n_owner,
-                                  const int32_t* __restrict__ sorted_flag, int32_t* __restrict__ key_out,
-                                  int32_t* __restrict__ val_out) {
-    if (*sorted_flag) return;
-    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (e < E) {
-        int32_t k = keys[e];
-        key_out[e] = min(max(k, 0), n_owner - 1);
-        val_out[e] = (int32_t)e;
-    }
-}
-
+// One pass over the edge list (one CTA per SORT_TILE edges):
+//   * index range check (err_flag bit 0) and sortedness check (unsorted_flag := 1 on a descent);
+//   * unless the caller vouches for sorted input: (clamped key, edge id) pairs for the radix sort, this tile's
+//     histogram of the first digit, and zeroing of the second histogram buffer.
+// A violated "sorted" hint sets err_flag bit 1.
+template <bool HINT_SORTED>
 __global__ void __launch_bounds__(SORT_THREADS)
-radix_hist_kernel(const int32_t* __restrict__ key_in, int64_t E, int shift, const int32_t* __restrict__ sorted_flag,
-                  int32_t* __restrict__ hist, int n_blocks) {
-    if (*sorted_flag) return;
+check_init_hist_kernel(const int32_t* __restrict__ keys, const int32_t* __restrict__ others, int64_t E,
+                       int32_t n_owner, int32_t n_other, int32_t* unsorted_flag, int32_t* err_flag, int hint_is_binding,
+                       int32_t* __restrict__ key_out, int32_t* __restrict__ val_out, int32_t* __restrict__ hist0,
+                       int32_t* __restrict__ hist1, int n_blocks) {
     __shared__ int32_t h[RADIX];
-    h[threadIdx.x] = 0;
-    __syncthreads();
-    int64_t base = (int64_t)blockIdx.x * SORT_TILE;
+    if (!HINT_SORTED) {
+        h[threadIdx.x] = 0;
+        hist1[(int64_t)blockIdx.x * RADIX + threadIdx.x] = 0;
+        __syncthreads();
+    }
+    const int64_t base = (int64_t)blockIdx.x * SORT_TILE;
+    bool unsorted = false, bad = false;
 #pragma unroll 4
     for (int i = 0; i < SORT_ITEMS; ++i) {
-        int64_t e = base + i * SORT_THREADS + threadIdx.x;
-        if (e < E) atomicAdd(&h[(key_in[e] >> shift) & (RADIX - 1)], 1);
+        const int64_t e = base + i * SORT_THREADS + threadIdx.x;
+        if (e < E) {
+            const int32_t k = keys[e], o = others[e];
+            bad |= (k < 0) | (k >= n_owner) | (o < 0) | (o >= n_other);
+            if (e > 0) unsorted |= keys[e - 1] > k;
+            if (!HINT_SORTED) {
+                const int32_t kc = min(max(k, 0), n_owner - 1);
+                key_out[e] = kc;
+                val_out[e] = (int32_t)e;
+                atomicAdd(&h[kc & (RADIX - 1)], 1);
+            }
+        }
     }
-    __syncthreads();
-    hist[threadIdx.x * n_blocks + blockIdx.x] = h[threadIdx.x];  // digit-major so one scan gives global offsets
+    if (__any_sync(0xffffffffu, unsorted) && (threadIdx.x & 31) == 0) {
+        *unsorted_flag = 1;
+        if (HINT_SORTED && hint_is_binding) atomicOr(err_flag, 2);
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(err_flag, 1);
+    if (!HINT_SORTED) {
+        __syncthreads();
+        hist0[threadIdx.x * n_blocks + blockIdx.x] = h[threadIdx.x];  // digit-major: one scan gives global offsets
+    }
 }
 
 // Exclusive scan of n int32 in place, one CTA of 1024 threads; 16 elements per thread per pass (vector loads when the
 // pass is full), warp-shuffle + shared-memory block scan, running carry across passes.
 __global__ void __launch_bounds__(1024)
-exclusive_scan_kernel(int32_t* __restrict__ data, int64_t n, const int32_t* __restrict__ sorted_flag) {
-    if (*sorted_flag) return;
+exclusive_scan_kernel(int32_t* __restrict__ data, int64_t n, const int32_t* __restrict__ unsorted_flag,
+                      int32_t* __restrict__ zero_buf) {
+    if (!*unsorted_flag) return;
+    if (zero_buf)  // histogram buffer the next scatter accumulates into
+        for (int64_t i = threadIdx.x; i < n; i += 1024) zero_buf[i] = 0;
     constexpr int PER = 16;
     __shared__ int32_t warp_sums[32];
     __shared__ int32_t carry_s;
@@ -129,12 +131,13 @@ exclusive_scan_kernel(int32_t* __restrict__ data, int64_t n, const int32_t* __re
 }
 
 // Stable scatter: rank of an item among equal digits = (# in earlier CTAs) + (# in earlier rounds of this CTA)
-// + (# in earlier warps of this round) + (# in lower lanes of this warp), all in original order.
+// + (# in earlier warps of this round) + (# in lower lanes of this warp), all in original order.  While scattering it
+// also builds the NEXT pass's per-tile digit histogram (integer atomics: order-independent result).
 __global__ void __launch_bounds__(SORT_THREADS)
 radix_scatter_kernel(const int32_t* __restrict__ key_in, const int32_t* __restrict__ val_in, int64_t E, int shift,
-                     const int32_t* __restrict__ sorted_flag, const int32_t* __restrict__ offsets, int n_blocks,
-                     int32_t* __restrict__ key_out, int32_t* __restrict__ val_out) {
-    if (*sorted_flag) return;
+                     const int32_t* __restrict__ unsorted_flag, const int32_t* __restrict__ offsets, int n_blocks,
+                     int32_t* __restrict__ key_out, int32_t* __restrict__ val_out, int32_t* __restrict__ hist_next) {
+    if (!*unsorted_flag) return;
     constexpr int WARPS = SORT_THREADS / 32;
     __shared__ int32_t running[RADIX];          // global offset of the next item of each digit for this CTA
     __shared__ int32_t warp_cnt[WARPS][RADIX];  // per-round per-warp digit counts -> exclusive offsets
@@ -156,24 +159,22 @@ radix_scatter_kernel(const int32_t* __restrict__ key_in, const int32_t* __restri
         const int rank_in_warp = __popc(peers & ((1u << lane) - 1u));
         if (valid && rank_in_warp == 0) warp_cnt[warp][digit] = __popc(peers);
         __syncthreads();
-        {   // thread t owns digit t: exclusive prefix over warps, then advance the running offset
-            int32_t acc = 0;
+        int32_t acc = 0;  // thread t owns digit t: exclusive prefix over warps
 #pragma unroll
-            for (int w = 0; w < WARPS; ++w) {
-                int32_t c = warp_cnt[w][t];
-                warp_cnt[w][t] = acc;
-                acc += c;
-            }
-            // publish after everyone has read `running` for this round -> two-phase via a second sync below
-            __syncthreads();
-            if (valid) {
-                int32_t pos = running[digit] + warp_cnt[warp][digit] + rank_in_warp;
-                key_out[pos] = k;
-                val_out[pos] = v;
-            }
-            __syncthreads();
-            running[t] += acc;
+        for (int w = 0; w < WARPS; ++w) {
+            const int32_t c = warp_cnt[w][t];
+            warp_cnt[w][t] = acc;
+            acc += c;
         }
+        __syncthreads();
+        if (valid) {
+            const int32_t pos = running[digit] + warp_cnt[warp][digit] + rank_in_warp;
+            key_out[pos] = k;
+            val_out[pos] = v;
+            if (hist_next) atomicAdd(&hist_next[((k >> (shift + 8)) & (RADIX - 1)) * n_blocks + pos / SORT_TILE], 1);
+        }
+        __syncthreads();
+        running[t] += acc;
         __syncthreads();
     }
 }
@@ -182,11 +183,11 @@ radix_scatter_kernel(const int32_t* __restrict__ key_in, const int32_t* __restri
 // the opposite endpoint, the raw feature and the permutation.  Launched with E + 1 threads.
 __global__ void finalize_layout_kernel(const int32_t* __restrict__ keys, const int32_t* __restrict__ others,
                                        const float* __restrict__ feats, int64_t E, int32_t n_owner,
-                                       int32_t n_other, const int32_t* __restrict__ sorted_flag, const int32_t* __restrict__ sorted_keys,
+                                       int32_t n_other, const int32_t* __restrict__ unsorted_flag, const int32_t* __restrict__ sorted_keys,
                                        const int32_t* __restrict__ sorted_perm, EdgeLayout out) {
     const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (p > E) return;
-    const bool presorted = *sorted_flag != 0;
+    const bool presorted = *unsorted_flag == 0;
     auto key_at = [&](int64_t q) -> int32_t {
         int32_t k = presorted ? keys[q] : sorted_keys[q];
         return min(max(k, 0), n_owner - 1);
@@ -209,56 +210,64 @@ static int bit_length(int64_t x) {
 }
 
 int build_layout(const int32_t* keys, const int32_t* others, const float* feats, int64_t E, int64_t n_owner,
-                 int64_t n_other, const SortScratch& sc, int32_t* err_flag, EdgeLayout out, cudaStream_t st) {
+                 int64_t n_other, const SortScratch& sc, int32_t* err_flag, int32_t* unsorted_flag, bool hint_sorted,
+                 EdgeLayout out, cudaStream_t st) {
     if (E < 0 || n_owner < 0 || n_other < 0 || E >= (int64_t)INT32_MAX || n_owner >= (int64_t)INT32_MAX) {
         set_error("build_layout: sizes out of int32 range");
         return GCNN_INVALID;
     }
     // algorithmic bytes: read (key, other, feature) per edge, write (other, feature, perm) per edge and the pointer
     ProfScope prof(PROF_CSR, 24.0 * (double)E + 4.0 * (double)(n_owner + 1), st);
-    const int threads = 256;
-    int32_t* sorted_flag = sc.flags;
-    set_flag_kernel<<<1, 1, 0, st>>>(sorted_flag, 1);
-    GCNN_LAUNCH_CHECK();
-    if (E > 0) {
-        check_keys_kernel<<<(unsigned)ceil_div(E, threads), threads, 0, st>>>(keys, others, E, (int32_t)n_owner,
-                                                                              (int32_t)n_other, sorted_flag, err_flag);
-        GCNN_LAUNCH_CHECK();
-    }
-    const int32_t* sorted_keys = sc.key_a;
-    const int32_t* sorted_perm = sc.val_a;
-    if (E > 1 && n_owner > 1) {
-        const int n_blocks = (int)ceil_div(E, SORT_TILE);
-        init_pairs_kernel<<<(unsigned)ceil_div(E, threads), threads, 0, st>>>(keys, E, (int32_t)n_owner, sorted_flag,
-                                                                              sc.key_a, sc.val_a);
-        GCNN_LAUNCH_CHECK();
-        int32_t *ka = sc.key_a, *va = sc.val_a, *kb = sc.key_b, *vb = sc.val_b;
-        const int bits = bit_length(n_owner - 1);
-        for (int shift = 0; shift < bits; shift += 8) {
-            radix_hist_kernel<<<n_blocks, SORT_THREADS, 0, st>>>(ka, E, shift, sorted_flag, sc.hist, n_blocks);
-            GCNN_LAUNCH_CHECK();
-            exclusive_scan_kernel<<<1, 1024, 0, st>>>(sc.hist, (int64_t)RADIX * n_blocks, sorted_flag);
-            GCNN_LAUNCH_CHECK();
-            radix_scatter_kernel<<<n_blocks, SORT_THREADS, 0, st>>>(ka, va, E, shift, sorted_flag, sc.hist, n_blocks,
-                                                                    kb, vb);
-            GCNN_LAUNCH_CHECK();
-            int32_t* t;
-            t = ka; ka = kb; kb = t;
-            t = va; va = vb; vb = t;
-        }
-        sorted_keys = ka;
-        sorted_perm = va;
-    } else if (E > 0) {
-        // 0/1 edges or a single owner: any order is sorted; force the presorted path.
-        set_flag_kernel<<<1, 1, 0, st>>>(sorted_flag, 1);
-        GCNN_LAUNCH_CHECK();
-    }
     if (E == 0) {  // no edges: every segment is empty
         GCNN_CUDA_TRY(cudaMemsetAsync(out.ptr, 0, sizeof(int32_t) * (size_t)(n_owner + 1), st));
         return GCNN_OK;
     }
+    const int n_blocks = (int)ceil_div(E, SORT_TILE);
+    const int64_t hist_n = (int64_t)RADIX * n_blocks;
+    int32_t *hist0 = sc.hist, *hist1 = sc.hist + hist_n;
+    // E <= 1 or a single owner: nothing to order (keys are clamped into [0, n_owner) downstream)
+    const bool trivially_sorted = E <= 1 || n_owner <= 1;
+    int32_t* scratch_flag = sc.flags;          // written, never read
+    const int32_t* zero_flag = sc.flags + 6;   // never written: reads as "sorted"
+    if (hint_sorted || trivially_sorted) {
+        check_init_hist_kernel<true><<<n_blocks, SORT_THREADS, 0, st>>>(
+            keys, others, E, (int32_t)n_owner, (int32_t)n_other, trivially_sorted ? scratch_flag : unsorted_flag,
+            err_flag, trivially_sorted ? 0 : 1, nullptr, nullptr, nullptr, nullptr, n_blocks);
+        GCNN_LAUNCH_CHECK();
+    } else {
+        check_init_hist_kernel<false><<<n_blocks, SORT_THREADS, 0, st>>>(
+            keys, others, E, (int32_t)n_owner, (int32_t)n_other, unsorted_flag, err_flag, 0, sc.key_a, sc.val_a, hist0,
+            hist1, n_blocks);
+        GCNN_LAUNCH_CHECK();
+    }
+    const int32_t* sorted_keys = sc.key_a;
+    const int32_t* sorted_perm = sc.val_a;
+    if (!hint_sorted && !trivially_sorted) {
+        int32_t *ka = sc.key_a, *va = sc.val_a, *kb = sc.key_b, *vb = sc.val_b;
+        int32_t *hcur = hist0, *hnext = hist1;
+        const int bits = bit_length(n_owner - 1);
+        for (int shift = 0, pass = 0; shift < bits; shift += 8, ++pass) {
+            const bool more = shift + 8 < bits;
+            // pass 0 finds hist1 zeroed by the first kernel; later passes zero their "next" buffer in the scan
+            exclusive_scan_kernel<<<1, 1024, 0, st>>>(hcur, hist_n, unsorted_flag, (more && pass > 0) ? hnext : nullptr);
+            GCNN_LAUNCH_CHECK();
+            radix_scatter_kernel<<<n_blocks, SORT_THREADS, 0, st>>>(ka, va, E, shift, unsorted_flag, hcur, n_blocks, kb,
+                                                                    vb, more ? hnext : nullptr);
+            GCNN_LAUNCH_CHECK();
+            int32_t* t;
+            t = ka; ka = kb; kb = t;
+            t = va; va = vb; vb = t;
+            t = hcur; hcur = hnext; hnext = t;
+        }
+        sorted_keys = ka;
+        sorted_perm = va;
+    }
+    const int threads = 256;
     finalize_layout_kernel<<<(unsigned)ceil_div(E + 1, threads), threads, 0, st>>>(
-        keys, others, feats, E, (int32_t)n_owner, (int32_t)n_other, sorted_flag, sorted_keys, sorted_perm, out);
+        keys, others, feats, E, (int32_t)n_owner, (int32_t)n_other,
+        // a violated hint leaves unsorted_flag = 1 with no sorted pairs: fall back to the input order (the error is
+        // reported through err_flag) by reading the always-zero word
+        ((trivially_sorted || hint_sorted) ? zero_flag : unsorted_flag), sorted_keys, sorted_perm, out);
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
 }

@@ -22,6 +22,24 @@ from ._lib import Batch, InvalidArgumentError, ResourceExhaustedError, check  # 
 EMB_SIZE, CONS_FEATS, EDGE_FEATS, VAR_FEATS, CUT_FEATS = 64, 4, 1, 14, 6
 
 
+def _row0_sorted(ei) -> bool:
+    """True when a HOST edge-index array has a non-decreasing row 0 (every reference-produced batch does,
+    utils.py:102-104, 403-407).  Device tensors are not inspected (that would synchronise)."""
+    if torch.is_tensor(ei):
+        if ei.is_cuda:
+            return False
+        ei = ei.numpy()
+    ei = np.asarray(ei)
+    if ei.ndim != 2 or ei.shape[0] != 2:
+        return False
+    return bool(ei.shape[1] < 2 or np.all(ei[0, 1:] >= ei[0, :-1]))
+
+
+def _sorted_flags(cons_ei, cut_ei) -> int:
+    return ((_lib.BATCH_CONS_EDGES_SORTED if _row0_sorted(cons_ei) else 0)
+            | (_lib.BATCH_CUT_EDGES_SORTED if _row0_sorted(cut_ei) else 0))
+
+
 class PreNormException(Exception):
     """Raised inside ``call`` when an armed pre-norm layer received a batch (model.py:440)."""
 
@@ -207,6 +225,7 @@ class GCNN:
         """Move the 10-tuple to the device (fp32 / int32, contiguous) and wrap it as a ``gcnn_batch``."""
         (cons, cons_ei, cons_ef, var, cut, cut_ei, cut_ef, n_cons, n_vars, n_cuts) = inputs
         f32, i32 = torch.float32, torch.int32
+        flags = _sorted_flags(cons_ei, cut_ei)  # host arrays only: a promise the device still verifies
         t = [self._to_device(cons, f32), self._to_device(cons_ei, i32), self._to_device(cons_ef, f32),
              self._to_device(var, f32), self._to_device(cut, f32), self._to_device(cut_ei, i32),
              self._to_device(cut_ef, f32)]
@@ -221,7 +240,7 @@ class GCNN:
         if t[2].numel() != e_c or t[6].numel() != e_k:
             raise InvalidArgumentError("edge features must be [E, 1]")
         b = Batch(t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(), t[4].data_ptr(),
-                  t[5].data_ptr(), t[6].data_ptr(), n_cons, n_vars, n_cuts, e_c, e_k)
+                  t[5].data_ptr(), t[6].data_ptr(), n_cons, n_vars, n_cuts, e_c, e_k, flags)
         return b, t
 
     def reserve(self, batch: Batch, training: bool):
@@ -386,6 +405,7 @@ class HostBatch:
         self.scores = torch.empty(nk, dtype=torch.float32).pin_memory()
         t = self.tensors
         self.batch = Batch(t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(), t[4].data_ptr(),
-                           t[5].data_ptr(), t[6].data_ptr(), nc, nv, nk, t[1].shape[1], t[5].shape[1])
+                           t[5].data_ptr(), t[6].data_ptr(), nc, nv, nk, t[1].shape[1], t[5].shape[1],
+                           _sorted_flags(t[1], t[5]))
         self.n_graphs = int(np.size(n_cons))
         self.h2d_bytes = sum(x.numel() * x.element_size() for x in self.tensors) + self.targets.numel() * 4

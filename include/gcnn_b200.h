@@ -57,7 +57,14 @@ typedef struct gcnn_batch {
     const float* cut_edge_feats;    /* [n_cut_edges, 1] */
     int64_t n_cons, n_vars, n_cuts; /* totals (model_trainer.py:259-261) */
     int64_t n_cons_edges, n_cut_edges;
+    /* Optional promises about the input (0 = none).  *_EDGES_SORTED: row 0 of that index tensor is non-decreasing,
+     * as in every batch the reference produces (csr -> coo order, utils.py:102-104, 226-228; offsets utils.py:403-407).
+     * The library still verifies it on the device and reports a violation as GCNN_INVALID at the next gcnn_check. */
+    int64_t flags;
 } gcnn_batch;
+
+#define GCNN_BATCH_CONS_EDGES_SORTED 1
+#define GCNN_BATCH_CUT_EDGES_SORTED 2
 
 /* ---- library ------------------------------------------------------------------------------------------------ */
 int gcnn_version(void);

@@ -133,6 +133,32 @@ def test_out_of_range_index_raises(model, golden_dir):
     assert rel_err(out.cpu().numpy(), z["scores_f64"]) <= TOL
 
 
+def test_violated_sorted_promise_is_reported(model):
+    """gcnn_batch.flags may promise row-0-sorted edges (what the reference's loader produces); the device verifies."""
+    from gcnn_cut_selector_b200 import InvalidArgumentError, _lib
+    sample = synth.shuffle_edges(synth.make_sample("mini", 3), 1)
+    batch = batching.concat_samples([sample])
+    dev = model.prepare_inputs(batching.model_inputs(batch))
+    assert dev[0].flags == 0  # the host check saw the shuffle
+    dev[0].flags = _lib.BATCH_CONS_EDGES_SORTED | _lib.BATCH_CUT_EDGES_SORTED
+    with pytest.raises(InvalidArgumentError, match="sorted"):
+        model._forward(dev, save_activations=False)
+    good = model.prepare_inputs(batching.model_inputs(batching.concat_samples([synth.make_sample("mini", 3)])))
+    assert good[0].flags == 3
+    assert torch.isfinite(model._forward(good, save_activations=False)).all()
+
+
+def test_device_tensor_inputs_take_the_unhinted_path(model, oracle64):
+    batch = batching.concat_samples(synth.make_samples("mini", 2, seed0=11))
+    inputs = batching.model_inputs(batch)
+    dev_inputs = tuple(torch.from_numpy(np.ascontiguousarray(x)).to(model.device) if isinstance(x, np.ndarray) else x
+                       for x in inputs)
+    assert model.prepare_inputs(dev_inputs)[0].flags == 0
+    with torch.no_grad():
+        out = model(dev_inputs, False)
+    assert rel_err(out.cpu().numpy(), oracle64.call(inputs).numpy()) <= TOL
+
+
 # ---- per-op parity ----------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n_recv,n_send,E", [(50, 70, 600), (1, 3, 5), (300, 2, 4000), (64, 64, 0)])
 def test_edge_forward_backward_ops(model, n_recv, n_send, E):
