@@ -356,6 +356,25 @@ def test_adam_train_steps_match_oracle(golden_dir):
         assert abs(float(loss) - float(oloss)) <= 1e-5 * float(oloss)
 
 
+def test_data_parallel_trainer_single_rank_equals_train_step(golden_dir):
+    """world size 1: un-normalised seed + division by the (reduced) cut count inside Adam == the plain train step."""
+    from gcnn_cut_selector_b200 import GCNN, DataParallelTrainer
+    path = os.path.join(golden_dir, "state_stream.pkl")
+    a, b = GCNN(device="cuda:0", seed=1), GCNN(device="cuda:0", seed=2)
+    a.restore_state(path); b.restore_state(path)
+    trainer = DataParallelTrainer(b, lr=1e-3)
+    for step in range(2):
+        batch = batching.concat_samples(synth.make_samples("mini", 2, seed0=500 + step))
+        inputs, targets = batching.model_inputs(batch), batch[10]
+        loss_a, _ = a.train_step(inputs, targets, 1e-3)
+        loss_b = trainer.step(inputs, targets)
+        assert abs(float(loss_a) - float(loss_b)) <= 1e-6 * abs(float(loss_a))
+        ga, gb = a.flat_grads.cpu().numpy(), (b.flat_grads / trainer.bucket[trainer.N]).cpu().numpy()
+        assert rel_err(gb, ga) <= 1e-6
+    # identical gradients up to one rounding -> parameters agree to a few ulps of the update
+    assert (a.flat_params.detach() - b.flat_params.detach()).abs().max().item() <= 2e-6
+
+
 def test_pretrain_protocol_matches_golden(golden_dir):
     from gcnn_cut_selector_b200 import GCNN
     z = np.load(os.path.join(golden_dir, "pretrain_tiny.npz"))
