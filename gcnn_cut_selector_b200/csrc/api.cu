@@ -98,6 +98,7 @@ struct gcnn_workspace {
     cudaStream_t aux[2] = {nullptr, nullptr};
     cudaEvent_t ev[16] = {};
     int ev_next = 0;
+    cudaEvent_t ev_layout[4] = {};  // cons by-left, cons by-var, cut by-left, cut by-var are ready
     float* t_dh1b = nullptr;
     // tensor-core path: packed 3xTF32 weight images, one per 64 x 64 weight block
     int use_tc = 1;
@@ -290,10 +291,13 @@ static int forward_impl(gcnn_workspace* ws, const float* p, const float* pn, con
     const bool cuts_sorted = (b->flags & GCNN_BATCH_CUT_EDGES_SORTED) != 0;
     GCNN_TRY(build_layout(b->cons_edge_inds, b->cons_edge_inds + ec, b->cons_edge_feats, ec, nc, nv, ws->sort,
                           ws->flags + 1, ws->flags + 2, cons_sorted, ws->graph[0].by_left, s1));
+    if (s1 != st) GCNN_CUDA_TRY(cudaEventRecord(ws->ev_layout[0], s1));
     GCNN_TRY(build_layout(b->cons_edge_inds + ec, b->cons_edge_inds, b->cons_edge_feats, ec, nv, nc, ws->sort,
                           ws->flags + 1, ws->flags + 3, false, ws->graph[0].by_var, s1));
+    if (s1 != st) GCNN_CUDA_TRY(cudaEventRecord(ws->ev_layout[1], s1));
     GCNN_TRY(build_layout(b->cut_edge_inds, b->cut_edge_inds + ek, b->cut_edge_feats, ek, nk, nv, ws->sort,
                           ws->flags + 1, ws->flags + 4, cuts_sorted, ws->graph[1].by_left, s1));
+    if (s1 != st) GCNN_CUDA_TRY(cudaEventRecord(ws->ev_layout[2], s1));
     if (ws->cap.training)
         GCNN_TRY(build_layout(b->cut_edge_inds + ek, b->cut_edge_inds, b->cut_edge_feats, ek, nv, nk, ws->sort,
                               ws->flags + 1, ws->flags + 5, false, ws->graph[1].by_var, s1));
@@ -315,7 +319,7 @@ static int forward_impl(gcnn_workspace* ws, const float* p, const float* pn, con
         GCNN_TRY(dense_forward(ws, p, a, se));
     }
     GCNN_TRY(stream_edge(ws, s2, st));  // v0 ready
-    GCNN_TRY(stream_edge(ws, s1, st));  // edge layouts ready
+    if (s1 != st) GCNN_CUDA_TRY(cudaEventRecord(ws->ev_layout[3], s1));  // everything on s1, incl. cut by-var
 
     // convolutions (model.py:294-296): {left feats, var feats, receiving side, graph, edge pre-norm}
     const float* left_in[3] = {ws->c0, ws->conv[0].Y, ws->k0};
@@ -341,7 +345,10 @@ static int forward_impl(gcnn_workspace* ws, const float* p, const float* pn, con
         const float* R = recv_is_left[i] ? a.A : a.B;
         const float* S = recv_is_left[i] ? a.B : a.A;
         EdgeScalars sc{pn + fshift[i], pn + fscale[i], pn + PN.conv_sf[i]};
-        if (stop_layer == 5 + 2 * i) return GCNN_OK;
+        // each convolution waits only for the edge layout it reduces over (the sort of the by-variable layout keeps
+        // running next to convolution 0)
+        if (s1 != st) GCNN_CUDA_TRY(cudaStreamWaitEvent(st, ws->ev_layout[i], 0));
+        if (stop_layer == 5 + 2 * i) { if (s1 != st) GCNN_CUDA_TRY(cudaStreamWaitEvent(st, ws->ev_layout[3], 0)); return GCNN_OK; }
         // algorithmic bytes (B_F): read both projection tables, 8 B of index + feature per edge and the
         // segment pointer; write the reduced rows
         const int64_t E_i = graph_of[i] == 0 ? ec : ek;
@@ -349,13 +356,14 @@ static int forward_impl(gcnn_workspace* ws, const float* p, const float* pn, con
         GCNN_TRY(edge_forward(L, n_recv, R, S, p + o.we, sc, a.H, a.cnt, st, fwd_bytes));
         LinFwdArgs pc{a.H, nullptr, nullptr, p + o.Wf, p + o.bf, L.ptr, a.C, n_recv, 64, 0};
         GCNN_TRY(dense_forward(ws, p, pc, st));
-        if (stop_layer == 6 + 2 * i) return GCNN_OK;
+        if (stop_layer == 6 + 2 * i) { if (s1 != st) GCNN_CUDA_TRY(cudaStreamWaitEvent(st, ws->ev_layout[3], 0)); return GCNN_OK; }
         LinFwdArgs p1{a.C, recv_in, pn + PN.conv_sp[i], p + o.Wo1, p + o.bo1, nullptr, a.U1, n_recv, 128, 1};
         GCNN_TRY(dense_forward(ws, p, p1, st));
         LinFwdArgs p2{a.U1, nullptr, nullptr, p + o.Wo2, p + o.bo2, nullptr, a.Y, n_recv, 64, 1};
         GCNN_TRY(dense_forward(ws, p, p2, st));
     }
 
+    if (s1 != st) GCNN_CUDA_TRY(cudaStreamWaitEvent(st, ws->ev_layout[3], 0));  // backward needs the cut by-var layout
     // head (model.py:299-300)
     LinFwdArgs h1{ws->conv[2].Y, nullptr, nullptr, p + P.Wh1, p + P.bh1, nullptr, ws->g1, nk, 64, 1};
     GCNN_TRY(dense_forward(ws, p, h1, st));
@@ -370,7 +378,7 @@ static int backward_impl(gcnn_workspace* ws, const float* p, const float* pn, co
     std::vector<ReduceJob> jobs;
     int slot = 0;
     auto add_job = [&](const float* part, int n_parts, int stride, int count, int dst) {
-        jobs.push_back(ReduceJob{part, n_parts, stride, count, dst});
+        jobs.push_back(ReduceJob{part, n_parts, stride, count, dst, nullptr});
     };
     int n_parts = 0;
     // weight gradients run on an auxiliary stream, concurrent with the input-gradient chain on the main stream
@@ -499,7 +507,7 @@ static int backward_impl(gcnn_workspace* ws, const float* p, const float* pn, co
         cudaStream_t se = e_i == 1 ? s2 : st;
         float* dh1 = e_i == 1 ? ws->t_dh1b : ws->t_dh1;
         LinWgradArgs w{e.h1, nullptr, nullptr, e.dout, e.out, nullptr, 64, e.n, 1, ws->partials[slot], &n_parts};
-        GCNN_TRY(dense_wgrad(ws, w, se));
+        GCNN_TRY(dense_wgrad(ws, w, s2));
         add_job(ws->partials[slot++], n_parts, D * D + D, D * D + D, e.o->W2);
         LinDgradArgs d{e.dout, e.out, p + e.o->W2, 64, dh1, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, e.n};
         GCNN_TRY(dense_dgrad(ws, p, d, se));
@@ -643,6 +651,7 @@ int gcnn_workspace_create(gcnn_workspace** out) {
     ws->use_streams = !(ms && ms[0] == '0');
     for (int i = 0; i < 2; ++i) GCNN_CUDA_TRY(cudaStreamCreateWithFlags(&ws->aux[i], cudaStreamNonBlocking));
     for (int i = 0; i < 16; ++i) GCNN_CUDA_TRY(cudaEventCreateWithFlags(&ws->ev[i], cudaEventDisableTiming));
+    for (int i = 0; i < 4; ++i) GCNN_CUDA_TRY(cudaEventCreateWithFlags(&ws->ev_layout[i], cudaEventDisableTiming));
     *out = ws;
     return GCNN_OK;
 }
@@ -652,6 +661,7 @@ int gcnn_workspace_destroy(gcnn_workspace* ws) {
     if (ws->arena) cudaFree(ws->arena);
     for (int i = 0; i < 2; ++i) if (ws->aux[i]) cudaStreamDestroy(ws->aux[i]);
     for (int i = 0; i < 16; ++i) if (ws->ev[i]) cudaEventDestroy(ws->ev[i]);
+    for (int i = 0; i < 4; ++i) if (ws->ev_layout[i]) cudaEventDestroy(ws->ev_layout[i]);
     delete ws;
     return GCNN_OK;
 }
@@ -942,7 +952,7 @@ int gcnn_edge_backward(gcnn_workspace* ws, const int32_t* ptr, const int32_t* ot
         rc = edge_backward(L, n_send, R, S, G, w_edge, EdgeScalars{dev, dev + 1, dev + 2}, dS, ws->dw_partials[0],
                            &n_dw, st);
         if (rc == GCNN_OK) {
-            ReduceJob job{ws->dw_partials[0], n_dw, D, D, 0};
+            ReduceJob job{ws->dw_partials[0], n_dw, D, D, 0, nullptr};
             rc = reduce_partials(&job, 1, dw, st);
         }
     }

@@ -224,7 +224,7 @@ int head2_backward(const float* g, const float* w, const float* d_scores, float*
                    int* n_parts, int64_t M, cudaStream_t st);
 
 // deterministic fixed-order reduction of per-CTA partials into the flat gradient
-struct ReduceJob { const float* partials; int n_parts; int stride; int count; int dst; };
+struct ReduceJob { const float* partials; int n_parts; int stride; int count; int dst; const float* scale; };
 int reduce_partials(const ReduceJob* jobs, int n_jobs, float* grads, cudaStream_t st);
 
 int mse_seed(const float* scores, const float* targets, int64_t n, float scale, float* d_scores, float* loss_sum,

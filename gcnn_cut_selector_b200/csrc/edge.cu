@@ -15,7 +15,7 @@ namespace gcnn {
 
 constexpr int EDGE_THREADS = 256;
 constexpr int EDGE_WARPS = EDGE_THREADS / 32;
-constexpr int EDGE_BWD_MAX_CTAS = NUM_SMS * 8;
+constexpr int EDGE_BWD_MAX_CTAS = NUM_SMS * 4;  // persistent: 8 CTAs of 256 threads fit per SM, 4 keep the dw partials few
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }

@@ -430,33 +430,59 @@ int head2_backward(const float* g, const float* w, const float* d_scores, float*
 constexpr int MAX_JOBS = 48;
 struct ReduceJobs { ReduceJob j[MAX_JOBS]; int n; };
 
+// Short outputs (edge-weight and head gradients: 64-65 floats, up to ~600 partials) would leave one thread walking
+// hundreds of partials serially, so the 256 threads of a CTA are arranged as (256 / LANES_W) partial-lanes x LANES_W
+// outputs; lane l sums partials l, l + L, l + 2L, ... and the lanes are combined in lane order -> still a fixed order.
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const __grid_constant__ ReduceJobs jobs, float* __restrict__ grads) {
+    __shared__ float red[256];
     const ReduceJob& job = jobs.j[blockIdx.y];
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= job.count) return;
-    const float* src = job.partials + i;
-    float s[8] = {};
-    int p = 0;
-    for (; p + 8 <= job.n_parts; p += 8) {
+    const int width = job.count <= 64 ? 64 : (job.count <= 128 ? 128 : 256);  // outputs per CTA
+    const int lanes = 256 / width;
+    const int c = threadIdx.x % width, lane = threadIdx.x / width;
+    const int i = blockIdx.x * width + c;
+    if (blockIdx.x * width >= job.count) return;  // whole CTA out of range (uniform)
+    float total = 0.f;
+    if (i < job.count) {
+        const float* src = job.partials + i;
+        float s[4] = {};
+        int p = lane;
+        for (; p + 3 * lanes < job.n_parts; p += 4 * lanes) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) s[u] += src[(int64_t)(p + u) * job.stride];
+            for (int u = 0; u < 4; ++u) s[u] += src[(int64_t)(p + u * lanes) * job.stride];
+        }
+        for (; p < job.n_parts; p += lanes) s[0] += src[(int64_t)p * job.stride];
+        total = (s[0] + s[1]) + (s[2] + s[3]);
     }
-    for (; p < job.n_parts; ++p) s[0] += src[(int64_t)p * job.stride];
-    grads[job.dst + i] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+    if (lanes == 1) {
+        if (i < job.count) grads[job.dst + i] = job.scale ? total * *job.scale : total;
+        return;
+    }
+    red[threadIdx.x] = total;
+    __syncthreads();
+    if (lane == 0 && i < job.count) {
+        float t = red[c];
+        for (int l = 1; l < lanes; ++l) t += red[l * width + c];
+        grads[job.dst + i] = job.scale ? t * *job.scale : t;
+    }
 }
 
 int reduce_partials(const ReduceJob* jobs, int n_jobs, float* grads, cudaStream_t st) {
     if (n_jobs > MAX_JOBS) { set_error("reduce_partials: too many jobs"); return GCNN_INVALID; }
     if (n_jobs == 0) return GCNN_OK;
     double out_floats = 0;
-    int max_count = 1;
-    for (int i = 0; i < n_jobs; ++i) { out_floats += jobs[i].count; max_count = jobs[i].count > max_count ? jobs[i].count : max_count; }
+    int max_ctas = 1;
+    for (int i = 0; i < n_jobs; ++i) {
+        out_floats += jobs[i].count;
+        const int width = jobs[i].count <= 64 ? 64 : (jobs[i].count <= 128 ? 128 : 256);
+        const int ctas = (int)ceil_div(jobs[i].count, width);
+        max_ctas = ctas > max_ctas ? ctas : max_ctas;
+    }
     ProfScope prof(PROF_REDUCE, 8.0 * out_floats, st);  // one read + one write per gradient element at minimum
     ReduceJobs js;
     js.n = n_jobs;
     for (int i = 0; i < n_jobs; ++i) js.j[i] = jobs[i];
-    dim3 grid((unsigned)ceil_div(max_count, 256), n_jobs);
+    dim3 grid((unsigned)max_ctas, n_jobs);
     reduce_partials_kernel<<<grid, 256, 0, st>>>(js, grads);
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
