@@ -102,6 +102,7 @@ struct gcnn_workspace {
     float* t_dh1b = nullptr;
     // tensor-core path: packed 3xTF32 weight images, one per 64 x 64 weight block
     int use_tc = 1;
+    int use_fused = 1;  // one tcgen05 chain kernel per convolution instead of four dense launches
     float* tc_images = nullptr;
     int* tc_block_offsets = nullptr;
     // bookkeeping of the last forward (validated by backward)
@@ -275,6 +276,71 @@ static int dense_wgrad(gcnn_workspace* ws, const LinWgradArgs& a, cudaStream_t s
     return tc_wgrad(t, st);
 }
 
+// ---- convolutions + head with the fused tensor-core node chain (tc_conv_forward) ------------------------------------
+// Launch plan: the projections that do not depend on a previous convolution (A0 on the main stream; B0, B1 and A2 on
+// an auxiliary stream) run right after the embeddings; then per convolution one edge kernel and ONE chain kernel that
+// also emits the projection the next convolution (or the head) needs.
+static int forward_convs_fused(gcnn_workspace* ws, const float* p, const float* pn, const gcnn_batch* b,
+                               float* scores_out, int stop_layer, cudaStream_t st, cudaStream_t s1, cudaStream_t s2) {
+    const int64_t nc = b->n_cons, nv = b->n_vars, nk = b->n_cuts, ec = b->n_cons_edges, ek = b->n_cut_edges;
+    auto img_t = [&](int param_off) { return ws->tc_images + (int64_t)tc_block_index(param_off) * TC_IMG_FLOATS; };
+    const bool keep = ws->cap.training != 0 || stop_layer >= 0;  // C / U1 are only read by the backward and by the statistics
+
+    GCNN_TRY(stream_edge(ws, st, s2));
+    {
+        LinFwdArgs a0{ws->c0, nullptr, nullptr, p + P.conv[0].Wl, p + P.conv[0].bl, nullptr, ws->conv[0].A, nc, 64, 0};
+        GCNN_TRY(dense_forward(ws, p, a0, st));
+        LinFwdArgs b0{ws->v0, nullptr, nullptr, p + P.conv[0].Wr, nullptr, nullptr, ws->conv[0].B, nv, 64, 0};
+        GCNN_TRY(dense_forward(ws, p, b0, s2));
+        LinFwdArgs b1{ws->v0, nullptr, nullptr, p + P.conv[1].Wr, nullptr, nullptr, ws->conv[1].B, nv, 64, 0};
+        GCNN_TRY(dense_forward(ws, p, b1, s2));
+        LinFwdArgs a2{ws->k0, nullptr, nullptr, p + P.conv[2].Wl, p + P.conv[2].bl, nullptr, ws->conv[2].A, nk, 64, 0};
+        GCNN_TRY(dense_forward(ws, p, a2, s2));
+    }
+    GCNN_TRY(stream_edge(ws, s2, st));
+
+    const float* recv_in[3] = {ws->c0, ws->v0, ws->k0};
+    const int64_t n_left[3] = {nc, nc, nk}, n_recv[3] = {nc, nv, nk};
+    const int recv_is_left[3] = {1, 0, 1}, graph_of[3] = {0, 0, 1};
+    const int fshift[3] = {PN.cedge_shift, PN.cedge_shift, PN.kedge_shift};
+    const int fscale[3] = {PN.cedge_scale, PN.cedge_scale, PN.kedge_scale};
+    // what each chain's last stage produces for the next consumer
+    const float* next_img[3] = {img_t(P.conv[1].Wl), img_t(P.conv[2].Wr), img_t(P.Wh1)};
+    const float* next_bias[3] = {p + P.conv[1].bl, nullptr, p + P.bh1};
+    float* next_out[3] = {ws->conv[1].A, ws->conv[2].B, ws->g1};
+    const int next_relu[3] = {0, 0, 1};
+    auto wait_all_layouts = [&]() -> int {
+        if (s1 != st) GCNN_CUDA_TRY(cudaStreamWaitEvent(st, ws->ev_layout[3], 0));
+        return GCNN_OK;
+    };
+    for (int i = 0; i < 3; ++i) {
+        const ConvOff& o = P.conv[i];
+        ConvActs& a = ws->conv[i];
+        const EdgeLayout& L = recv_is_left[i] ? ws->graph[graph_of[i]].by_left : ws->graph[graph_of[i]].by_var;
+        const float* R = recv_is_left[i] ? a.A : a.B;
+        const float* S = recv_is_left[i] ? a.B : a.A;
+        EdgeScalars sc{pn + fshift[i], pn + fscale[i], pn + PN.conv_sf[i]};
+        if (s1 != st) GCNN_CUDA_TRY(cudaStreamWaitEvent(st, ws->ev_layout[i], 0));
+        if (stop_layer == 5 + 2 * i) return wait_all_layouts();
+        const int64_t E_i = graph_of[i] == 0 ? ec : ek;
+        const double fwd_bytes = 256.0 * (double)(n_left[i] + nv + n_recv[i]) + 8.0 * (double)E_i + 4.0 * (double)(n_recv[i] + 1);
+        GCNN_TRY(edge_forward(L, n_recv[i], R, S, p + o.we, sc, a.H, a.cnt, st, fwd_bytes));
+        ConvFwdArgs c{};
+        c.H = a.H; c.Xt = recv_in[i]; c.deg_ptr = L.ptr; c.s_p = pn + PN.conv_sp[i];
+        c.img_f = img_t(o.Wf); c.bias_f = p + o.bf;
+        c.img_o1a = img_t(o.Wo1); c.img_o1b = img_t(o.Wo1 + D * D); c.bias_o1 = p + o.bo1;
+        c.img_o2 = img_t(o.Wo2); c.bias_o2 = p + o.bo2;
+        c.img_n = next_img[i]; c.bias_n = next_bias[i]; c.relu_n = next_relu[i];
+        c.C = keep ? a.C : nullptr; c.U1 = keep ? a.U1 : nullptr; c.Y = a.Y; c.Pn = next_out[i];
+        c.M = n_recv[i];
+        GCNN_TRY(tc_conv_forward(c, st));
+        if (stop_layer == 6 + 2 * i) return wait_all_layouts();
+    }
+    GCNN_TRY(wait_all_layouts());  // the backward needs the cut by-variable layout
+    GCNN_TRY(head2_forward(ws->g1, p + P.Wh2, p + P.bh2, scores_out ? scores_out : ws->scores, nk, st));
+    return GCNN_OK;
+}
+
 // ---- forward -----------------------------------------------------------------------------------------------------
 // stop_layer: -1 runs everything; k in [5, 10] returns as soon as the input of pre-norm layer k exists.
 static int forward_impl(gcnn_workspace* ws, const float* p, const float* pn, const gcnn_batch* b, float* scores_out,
@@ -320,6 +386,8 @@ static int forward_impl(gcnn_workspace* ws, const float* p, const float* pn, con
     }
     GCNN_TRY(stream_edge(ws, s2, st));  // v0 ready
     if (s1 != st) GCNN_CUDA_TRY(cudaEventRecord(ws->ev_layout[3], s1));  // everything on s1, incl. cut by-var
+
+    if (ws->use_tc && ws->use_fused) return forward_convs_fused(ws, p, pn, b, scores_out, stop_layer, st, s1, s2);
 
     // convolutions (model.py:294-296): {left feats, var feats, receiving side, graph, edge pre-norm}
     const float* left_in[3] = {ws->c0, ws->conv[0].Y, ws->k0};
@@ -649,6 +717,8 @@ int gcnn_workspace_create(gcnn_workspace** out) {
     ws->use_tc = !(tc && tc[0] == '0');
     const char* ms = getenv("GCNN_STREAMS");  // GCNN_STREAMS=0 serialises everything on the caller's stream
     ws->use_streams = !(ms && ms[0] == '0');
+    const char* fu = getenv("GCNN_FUSED");  // GCNN_FUSED=0: one launch per dense layer
+    ws->use_fused = !(fu && fu[0] == '0');
     for (int i = 0; i < 2; ++i) GCNN_CUDA_TRY(cudaStreamCreateWithFlags(&ws->aux[i], cudaStreamNonBlocking));
     for (int i = 0; i < 16; ++i) GCNN_CUDA_TRY(cudaEventCreateWithFlags(&ws->ev[i], cudaEventDisableTiming));
     for (int i = 0; i < 4; ++i) GCNN_CUDA_TRY(cudaEventCreateWithFlags(&ws->ev_layout[i], cudaEventDisableTiming));
@@ -700,6 +770,7 @@ int gcnn_set_option(gcnn_workspace* ws, const char* name, int value) {
     if (!ws || !name) { set_error("null argument"); return GCNN_INVALID; }
     if (!strcmp(name, "tensor_cores")) ws->use_tc = value != 0;
     else if (!strcmp(name, "streams")) ws->use_streams = value != 0;
+    else if (!strcmp(name, "fused")) ws->use_fused = value != 0;
     else { set_error("unknown option %s", name); return GCNN_INVALID; }
     return GCNN_OK;
 }

@@ -196,6 +196,20 @@ struct TcArgs {
     int64_t M;
 };
 int tc_linear(const TcArgs& a, int prof_class, double prof_bytes, cudaStream_t st);
+struct ConvFwdArgs {          // fused node chain of one convolution (tc_conv_forward)
+    const float* H;           // [M, 64] segmented sums
+    const float* Xt;          // [M, 64] receiving nodes' input features (right half of the concat)
+    const int32_t* deg_ptr;   // segment pointer: bias of S0 is scaled by the in-degree
+    const float* s_p;         // post_conv pre-norm scale (device scalar)
+    const float *img_f, *bias_f;               // hoisted feature_module_final Dense
+    const float *img_o1a, *img_o1b, *bias_o1;  // output layer 1 (K = 128: two weight images)
+    const float *img_o2, *bias_o2;             // output layer 2
+    const float *img_n, *bias_n;               // next projection / head layer 1 (img_n == nullptr: none)
+    int relu_n;
+    float *C, *U1, *Y, *Pn;   // outputs; C and U1 may be nullptr (inference)
+    int64_t M;
+};
+int tc_conv_forward(const ConvFwdArgs& a, cudaStream_t st);
 struct TcWgradArgs {
     const float* X;         // [M, 64] (left half when K = 128)
     const float* X2;        // right half (K = 128)

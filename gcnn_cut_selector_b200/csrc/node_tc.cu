@@ -300,6 +300,178 @@ tc_linear_kernel(const TcArgs a) {
     if (warp == 0) tmem_dealloc(tmem_d, 64);
 }
 
+template <typename Kern>
+static int set_smem_tc(Kern kern, size_t bytes) {
+    GCNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return GCNN_OK;
+}
+
+// ---- fused forward node chain of one convolution -----------------------------------------------------------------
+// PartialGraphConvolution after the segmented sum (model.py:563, 570-573) plus the next layer's projection, one CTA per
+// 128 receiving nodes, intermediates never leave the SM except for the copies the backward pass needs:
+//   S0: C  = H Wf + deg * bf                       (hoisted feature_module_final Dense)
+//   S1: U1 = relu([s_p C, X_t] Wo1 + bo1)          (post_conv scale, concat, output layer 1)
+//   S2: Y  = relu(U1 Wo2 + bo2)                    (output layer 2)
+//   S3: Pn = act(Y Wn + bn)                        (next convolution's left/right projection, or the head's first layer)
+// Each epilogue splits its result into TF32 hi/lo and writes it straight into the swizzled A-operand tile of the next
+// stage.  Shared memory: two 64 KB A regions (P, Q) + one 64 KB and one 32 KB weight buffer; the weights of later
+// stages stream in by cp.async while earlier stages compute.  All three 3xTF32 products accumulate in one TMEM tile.
+constexpr uint32_t REG_BYTES = 4 * A_BLOCK_BYTES;   // one A region: hi (2 K-blocks) + lo (2 K-blocks) = 64 KB
+constexpr uint32_t IMG_BYTES = 2 * IMG_FLOATS * 4;  // one weight image: hi + lo = 32 KB
+
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void copy_image_async(uint32_t dst_smem, const float* img, int tid) {
+    for (int i = tid; i < (int)(IMG_BYTES / 16); i += TC_THREADS) cp_async16(dst_smem + i * 16, img + i * 4);
+}
+
+// issue the 3 x (K/8) MMAs of one stage: A k-blocks come from up to two regions, B from up to two images
+__device__ __forceinline__ void issue_stage(uint32_t tmem_d, const uint32_t (&a_reg)[2], const uint32_t (&b_img)[2],
+                                            int n_groups /* 64-wide K groups: 1 or 2 */) {
+    const int sel[3][2] = {{1, 0}, {0, 1}, {0, 0}};  // (A part, B part): lo*hi, hi*lo, hi*hi
+    uint32_t acc = 0;
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+        for (int g = 0; g < n_groups; ++g) {
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t da = make_desc(a_reg[g] + sel[p][0] * 2 * A_BLOCK_BYTES + kb * A_BLOCK_BYTES + ks * 32);
+                    const uint64_t db = make_desc(b_img[g] + sel[p][1] * IMG_FLOATS * 4 + kb * B_BLOCK_BYTES + ks * 32);
+                    umma_tf32(tmem_d, da, db, IDESC_TF32_128x64, acc);
+                    acc = 1;
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_conv_forward_kernel(const ConvFwdArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t mma_bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t row0 = (int64_t)blockIdx.x * TC_ROWS;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t P = base, Q = base + REG_BYTES, WA = base + 2 * REG_BYTES, WB = base + 2 * REG_BYTES + 2 * IMG_BYTES;
+
+    if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), 64);
+    if (tid == 0) mbar_init(smem_u32(&mma_bar), 1);
+
+    // weights of S0 and S1
+    copy_image_async(WB, a.img_f, tid);
+    copy_image_async(WA, a.img_o1a, tid);
+    copy_image_async(WA + IMG_BYTES, a.img_o1b, tid);
+    cp_async_commit();
+
+    // A tiles of S0 (H -> P) and the right half of S1 (X_t -> Q): all loads first, then split + swizzled store
+    {
+        float4 hv[8], xv[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int i = tid + it * TC_THREADS, r = i >> 4, c4 = i & 15;
+            const int64_t m = row0 + r;
+            hv[it] = xv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < a.M) {
+                hv[it] = ldg_stream4(a.H + m * D + c4 * 4);
+                xv[it] = ldg_stream4(a.Xt + m * D + c4 * 4);
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int i = tid + it * TC_THREADS, r = i >> 4, c4 = i & 15;
+            const uint32_t off = swz_chunk_off(r, c4 * 4, TC_ROWS);
+            float4 hi, lo;
+            split4(hv[it], hi, lo);
+            *reinterpret_cast<float4*>(gen + off) = hi;
+            *reinterpret_cast<float4*>(gen + 2 * A_BLOCK_BYTES + off) = lo;
+            split4(xv[it], hi, lo);
+            *reinterpret_cast<float4*>(gen + REG_BYTES + off) = hi;
+            *reinterpret_cast<float4*>(gen + REG_BYTES + 2 * A_BLOCK_BYTES + off) = lo;
+        }
+    }
+
+    const int q = warp & 3, ch = warp >> 2;
+    const int r_own = q * 32 + lane;          // the D row this thread reads back
+    const int64_t m_own = row0 + r_own;
+    const bool row_ok = m_own < a.M;
+    const float s_p = *a.s_p;
+    float deg = 1.f;
+    if (row_ok && a.deg_ptr) deg = (float)(a.deg_ptr[m_own + 1] - a.deg_ptr[m_own]);
+    const int n_stages = a.img_n ? 4 : 3;
+    uint32_t tmem_d = 0;
+
+    for (int s = 0; s < n_stages; ++s) {
+        // weights this stage needs have landed (later stages' copies may still be in flight)
+        if (s == 0 || s == 3) cp_async_wait<0>(); else cp_async_wait<1>();
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (s == 0) tmem_d = tmem_slot;
+        if (tid == 0) {
+            if (s == 0)      { const uint32_t ar[2] = {P, 0}, bi[2] = {WB, 0};              issue_stage(tmem_d, ar, bi, 1); }
+            else if (s == 1) { const uint32_t ar[2] = {P, Q}, bi[2] = {WA, WA + IMG_BYTES}; issue_stage(tmem_d, ar, bi, 2); }
+            else if (s == 2) { const uint32_t ar[2] = {P, 0}, bi[2] = {WB, 0};              issue_stage(tmem_d, ar, bi, 1); }
+            else             { const uint32_t ar[2] = {Q, 0}, bi[2] = {WA, 0};              issue_stage(tmem_d, ar, bi, 1); }
+            umma_commit(smem_u32(&mma_bar));
+        }
+        mbar_wait(smem_u32(&mma_bar), (uint32_t)(s & 1));
+        tc_fence_after();
+        // the buffers this stage's MMAs read are free now: stream in the weights two stages ahead
+        if (s == 0) { copy_image_async(WB, a.img_o2, tid); cp_async_commit(); }
+        if (s == 1) { if (n_stages == 4) copy_image_async(WA, a.img_n, tid); cp_async_commit(); }
+
+        float v[32];
+        tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
+        const float* bias = s == 0 ? a.bias_f : s == 1 ? a.bias_o1 : s == 2 ? a.bias_o2 : a.bias_n;
+        const float bscale = s == 0 ? deg : 1.f;
+        const bool relu = s == 1 || s == 2 || (s == 3 && a.relu_n);
+        float* out = s == 0 ? a.C : s == 1 ? a.U1 : s == 2 ? a.Y : a.Pn;
+        const float to_next = s == 0 ? s_p : 1.f;                       // post_conv pre-norm scale (model.py:570)
+        uint8_t* next_region = (s == 1) ? gen : (s == 2 ? gen + REG_BYTES : (s == 0 ? gen : nullptr));  // S0->P, S1->P, S2->Q
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float4 y = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            if (bias) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bias + ch * 32 + 4 * j);
+                y.x += bscale * b4.x; y.y += bscale * b4.y; y.z += bscale * b4.z; y.w += bscale * b4.w;
+            }
+            if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+            if (out && row_ok) *reinterpret_cast<float4*>(out + m_own * D + ch * 32 + 4 * j) = y;
+            if (next_region && s + 1 < n_stages) {
+                float4 t = make_float4(y.x * to_next, y.y * to_next, y.z * to_next, y.w * to_next), hi, lo;
+                split4(t, hi, lo);
+                const uint32_t off = swz_chunk_off(r_own, ch * 32 + 4 * j, TC_ROWS);
+                *reinterpret_cast<float4*>(next_region + off) = hi;
+                *reinterpret_cast<float4*>(next_region + 2 * A_BLOCK_BYTES + off) = lo;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_d, 64);
+}
+
+int tc_conv_forward(const ConvFwdArgs& a, cudaStream_t st) {
+    if (a.M <= 0) return GCNN_OK;
+    const int stages = a.img_n ? 4 : 3;
+    // algorithmic bytes: read H and X_t, write the saved activations and the next projection, read the weights once
+    const double rows = 2.0 + (a.C ? 1 : 0) + (a.U1 ? 1 : 0) + 1.0 + (stages == 4 ? 1 : 0);
+    ProfScope prof(PROF_LIN_FWD, 256.0 * (double)a.M * rows + 4.0 * D * D * (stages + 1), st);
+    const size_t smem = 2 * REG_BYTES + 3 * IMG_BYTES + 1024;
+    static int once = set_smem_tc(tc_conv_forward_kernel, smem);
+    GCNN_TRY(once);
+    tc_conv_forward_kernel<<<(unsigned)ceil_div(a.M, TC_ROWS), TC_THREADS, smem, st>>>(a);
+    GCNN_LAUNCH_CHECK();
+    return GCNN_OK;
+}
+
 // ---- weight gradient on the tensor cores ----------------------------------------------------------------------------
 // dW[f, c] = sum_m Xcat[m, f] * dYp[m, c] is a GEMM whose reduction runs over ROWS, so the row-major tiles
 // [row][32 floats] are MN-major operands (MN = the 32 contiguous features / columns, K = the rows): no transpose is
@@ -466,12 +638,6 @@ tc_wgrad_kernel(const TcWgradArgs a) {
         part[K * D + tid] = t;
     }
     if (warp == 0) tmem_dealloc(tmem_d, 64);
-}
-
-template <typename Kern>
-static int set_smem_tc(Kern kern, size_t bytes) {
-    GCNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    return GCNN_OK;
 }
 
 int tc_linear(const TcArgs& a, int prof_class, double prof_bytes, cudaStream_t st) {
