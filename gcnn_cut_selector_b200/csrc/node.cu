@@ -343,12 +343,31 @@ embed1_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ shift
     __syncthreads();
     const int c = threadIdx.x & 63, r = threadIdx.x >> 6;
     float acc[K + 1] = {};
-    for (int64_t m = (int64_t)blockIdx.x * 4 + r; m < M; m += (int64_t)gridDim.x * 4) {
-        float d = dY[m * D + c];
-        if (act[m * D + c] <= 0.f) d = 0.f;
+    const int64_t stride = (int64_t)gridDim.x * 4;
+    // four rows per trip, every load of the trip issued before the first use (the loop is latency-, not
+    // bandwidth-limited: 148 CTAs x 4 row lanes walk up to 10^5 rows)
+    for (int64_t m0 = (int64_t)blockIdx.x * 4 + r; m0 < M; m0 += 4 * stride) {
+        float d[4], xv[4][K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) acc[k] = fmaf((x[m * K + k] + sh[k]) * scl[k], d, acc[k]);
-        acc[K] += d;
+        for (int u = 0; u < 4; ++u) {
+            const int64_t m = m0 + u * stride;
+            d[u] = 0.f;
+            if (m < M) {
+                d[u] = dY[m * D + c];
+                if (act[m * D + c] <= 0.f) d[u] = 0.f;
+#pragma unroll
+                for (int k = 0; k < K; ++k) xv[u][k] = x[m * K + k];
+            } else {
+#pragma unroll
+                for (int k = 0; k < K; ++k) xv[u][k] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[k] = fmaf((xv[u][k] + sh[k]) * scl[k], d[u], acc[k]);
+            acc[K] += d[u];
+        }
     }
 #pragma unroll
     for (int k = 0; k <= K; ++k) red[r][k * D + c] = acc[k];

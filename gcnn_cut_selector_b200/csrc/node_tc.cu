@@ -168,9 +168,11 @@ tc_linear_kernel(const TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t mma_bar;
     __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float bias_s[D];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int slab = blockIdx.y;
+    if (tid < D) bias_s[tid] = a.bias ? a.bias[tid] : 0.f;
     const int64_t row0 = (int64_t)blockIdx.x * TC_ROWS;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
     uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -259,40 +261,44 @@ tc_linear_kernel(const TcArgs a) {
         }
         umma_commit(smem_u32(&mma_bar));  // implies tcgen05.fence::before_thread_sync
     }
+    // epilogue operands that live in global memory are fetched BEFORE waiting on the tensor core: interleaved with the
+    // stores below they could not be hoisted (possible aliasing) and every row group would pay a full L2 round trip
+    const int q = warp & 3, ch = warp >> 2;
+    const int64_t m = row0 + q * 32 + lane;
+    const bool second = slab == 0 && a.dR != nullptr;
+    const bool acc_out = a.accumulate[slab] != 0;
+    float* dst = a.Y[slab] + m * D + ch * 32;
+    float4 pre[8];
+    float bs = 1.f, osc = 1.f, s_f = 0.f;
+    if (m < a.M) {
+        if (a.deg_ptr) bs = (float)(a.deg_ptr[m + 1] - a.deg_ptr[m]);
+        if (a.out_scale[slab]) osc = *a.out_scale[slab];
+        if (second) s_f = *a.s_f;
+        if (acc_out || second) {
+            const float* src = acc_out ? dst : a.cnt + m * D + ch * 32;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) pre[j] = *reinterpret_cast<const float4*>(src + 4 * j);
+        }
+    }
     mbar_wait(smem_u32(&mma_bar), 0);
     tc_fence_after();
 
-    // epilogue: warp w reads TMEM lanes [32 (w % 4), +32) (its quadrant), columns [32 (w / 4), +32)
-    const int q = warp & 3, ch = warp >> 2;
+    // warp w reads TMEM lanes [32 (w % 4), +32) (its quadrant), columns [32 (w / 4), +32)
     float v[32];
     tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
-    const int64_t m = row0 + q * 32 + lane;
     if (m < a.M) {
-        float bs = 1.f;
-        if (a.deg_ptr) bs = (float)(a.deg_ptr[m + 1] - a.deg_ptr[m]);
-        const float osc = a.out_scale[slab] ? *a.out_scale[slab] : 1.f;
-        float* dst = a.Y[slab] + m * D + ch * 32;
-        const bool second = slab == 0 && a.dR != nullptr;
-        const float s_f = second ? *a.s_f : 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             float4 y = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            if (a.bias) {
-                const float4 b4 = *reinterpret_cast<const float4*>(a.bias + ch * 32 + 4 * j);
-                y.x += bs * b4.x; y.y += bs * b4.y; y.z += bs * b4.z; y.w += bs * b4.w;
-            }
+            const float4 b4 = *reinterpret_cast<const float4*>(&bias_s[ch * 32 + 4 * j]);
+            y.x += bs * b4.x; y.y += bs * b4.y; y.z += bs * b4.z; y.w += bs * b4.w;
             if (a.relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
             y.x *= osc; y.y *= osc; y.z *= osc; y.w *= osc;
-            if (a.accumulate[slab]) {
-                const float4 o = *reinterpret_cast<const float4*>(dst + 4 * j);
-                y.x += o.x; y.y += o.y; y.z += o.z; y.w += o.w;
-            }
+            if (acc_out) { y.x += pre[j].x; y.y += pre[j].y; y.z += pre[j].z; y.w += pre[j].w; }
             *reinterpret_cast<float4*>(dst + 4 * j) = y;
-            if (second) {
-                const float4 c = *reinterpret_cast<const float4*>(a.cnt + m * D + ch * 32 + 4 * j);
+            if (second)
                 *reinterpret_cast<float4*>(a.dR + m * D + ch * 32 + 4 * j) =
-                    make_float4(s_f * y.x * c.x, s_f * y.y * c.y, s_f * y.z * c.z, s_f * y.w * c.w);
-            }
+                    make_float4(s_f * y.x * pre[j].x, s_f * y.y * pre[j].y, s_f * y.z * pre[j].z, s_f * y.w * pre[j].w);
         }
     }
     tc_fence_before();
@@ -354,10 +360,16 @@ tc_conv_forward_kernel(const ConvFwdArgs a) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t mma_bar;
     __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float bias_s[4][D];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t row0 = (int64_t)blockIdx.x * TC_ROWS;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+    {   // all four bias vectors up front (reading them from global memory between the epilogue stores would serialise)
+        const float* bsrc[4] = {a.bias_f, a.bias_o1, a.bias_o2, a.bias_n};
+        const int st_i = tid >> 6, c = tid & 63;
+        bias_s[st_i][c] = bsrc[st_i] ? bsrc[st_i][c] : 0.f;
+    }
     const uint32_t P = base, Q = base + REG_BYTES, WA = base + 2 * REG_BYTES, WB = base + 2 * REG_BYTES + 2 * IMG_BYTES;
 
     if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), 64);
@@ -429,7 +441,6 @@ tc_conv_forward_kernel(const ConvFwdArgs a) {
 
         float v[32];
         tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
-        const float* bias = s == 0 ? a.bias_f : s == 1 ? a.bias_o1 : s == 2 ? a.bias_o2 : a.bias_n;
         const float bscale = s == 0 ? deg : 1.f;
         const bool relu = s == 1 || s == 2 || (s == 3 && a.relu_n);
         float* out = s == 0 ? a.C : s == 1 ? a.U1 : s == 2 ? a.Y : a.Pn;
@@ -438,10 +449,8 @@ tc_conv_forward_kernel(const ConvFwdArgs a) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             float4 y = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            if (bias) {
-                const float4 b4 = *reinterpret_cast<const float4*>(bias + ch * 32 + 4 * j);
-                y.x += bscale * b4.x; y.y += bscale * b4.y; y.z += bscale * b4.z; y.w += bscale * b4.w;
-            }
+            const float4 b4 = *reinterpret_cast<const float4*>(&bias_s[s][ch * 32 + 4 * j]);
+            y.x += bscale * b4.x; y.y += bscale * b4.y; y.z += bscale * b4.z; y.w += bscale * b4.w;
             if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
             if (out && row_ok) *reinterpret_cast<float4*>(out + m_own * D + ch * 32 + 4 * j) = y;
             if (next_region && s + 1 < n_stages) {
