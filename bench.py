@@ -172,7 +172,8 @@ def run_b200(args):
     if trainer:
         trainer.broadcast_parameters()
     host = [HostBatch(b) for b in batches]
-    dev_inputs = [model.prepare_inputs(batching.model_inputs(b)) for b in batches]
+    # the loader's per-sample count vectors travel with the batch (utils.py:420-422)
+    dev_inputs = [model.prepare_inputs(batching.model_inputs(b, per_sample_counts=True)) for b in batches]
     dev_targets = [torch.from_numpy(b[10]).to(dev) for b in batches]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     lib = model._lib
@@ -255,7 +256,7 @@ def run_b200(args):
     def e2e_step(i):
         hb = host[i % n_rot]
         if trainer:
-            ins = model.prepare_inputs(tuple(hb.tensors) + (hb.batch.n_cons, hb.batch.n_vars, hb.batch.n_cuts))
+            ins = model.prepare_inputs(tuple(hb.tensors) + tuple(hb.counts))
             loss = trainer.step(ins, hb.targets)
             return float(loss.item())
         return model.train_step_host(hb, lr)

@@ -29,7 +29,9 @@ class Batch(C.Structure):
     _fields_ = [("cons_feats", C.c_void_p), ("cons_edge_inds", C.c_void_p), ("cons_edge_feats", C.c_void_p),
                 ("var_feats", C.c_void_p), ("cut_feats", C.c_void_p), ("cut_edge_inds", C.c_void_p),
                 ("cut_edge_feats", C.c_void_p), ("n_cons", C.c_int64), ("n_vars", C.c_int64), ("n_cuts", C.c_int64),
-                ("n_cons_edges", C.c_int64), ("n_cut_edges", C.c_int64), ("flags", C.c_int64)]
+                ("n_cons_edges", C.c_int64), ("n_cut_edges", C.c_int64), ("flags", C.c_int64),
+                ("sample_n_cons", C.c_void_p), ("sample_n_vars", C.c_void_p), ("sample_n_cuts", C.c_void_p),
+                ("n_samples", C.c_int64)]
 
 
 BATCH_CONS_EDGES_SORTED, BATCH_CUT_EDGES_SORTED = 1, 2

@@ -69,6 +69,10 @@ def load_batch(sample_files):
     return concat_samples(samples)
 
 
-def model_inputs(batch):
-    """The 10-tuple the model takes: features/indices plus the three *totals* (model_trainer.py:259-263)."""
+def model_inputs(batch, per_sample_counts: bool = False):
+    """The 10-tuple the model takes: features/indices plus the three *totals* (model_trainer.py:259-263).  With
+    ``per_sample_counts`` the last three entries stay the per-sample vectors ``load_batch`` returns; the B200 model
+    accepts either and uses the vectors to stage per-sample tables in shared memory."""
+    if per_sample_counts:
+        return tuple(batch[:10])
     return tuple(batch[:7]) + (int(np.sum(batch[7])), int(np.sum(batch[8])), int(np.sum(batch[9])))

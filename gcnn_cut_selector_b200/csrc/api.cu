@@ -100,6 +100,11 @@ struct gcnn_workspace {
     int ev_next = 0;
     cudaEvent_t ev_layout[4] = {};  // cons by-left, cons by-var, cut by-left, cut by-var are ready
     float* t_dh1b = nullptr;
+    // shared-memory tile variant of the forward edge kernel (needs the per-sample node counts).  Off by default: on
+    // B200 the generic kernel is bound by instruction issue, not by the L2 gathers, and measures faster (profiles/).
+    int use_tiles = 0;
+    EdgeTile* d_tiles[3] = {nullptr, nullptr, nullptr};
+    int64_t tile_cap = 0;
     // tensor-core path: packed 3xTF32 weight images, one per 64 x 64 weight block
     int use_tc = 1;
     int use_fused = 1;  // one tcgen05 chain kernel per convolution instead of four dense launches
@@ -198,6 +203,8 @@ static size_t carve(gcnn_workspace* ws, char* base, const Caps& c) {
     ws->s_kef = cv.take<float>(ek);
     ws->s_targets = cv.take<float>(nk);
 
+    ws->tile_cap = (nc + nv + nk) / 16 + 8192;
+    for (int i = 0; i < 3; ++i) ws->d_tiles[i] = cv.take<EdgeTile>(ws->tile_cap);
     ws->tc_images = cv.take<float>((int64_t)tc_blocks().size() * TC_IMG_FLOATS);
     ws->tc_block_offsets = cv.take<int>(64);
 
@@ -240,6 +247,35 @@ static int stream_edge(gcnn_workspace* ws, cudaStream_t from, cudaStream_t to) {
     GCNN_CUDA_TRY(cudaEventRecord(e, from));
     GCNN_CUDA_TRY(cudaStreamWaitEvent(to, e, 0));
     return GCNN_OK;
+}
+
+// ---- forward edge kernel dispatch: shared-memory tiles when the batch carries per-sample counts, else generic ------
+bool plan_edge_tiles(const int32_t* recv_counts, const int32_t* send_counts, int64_t n_samples, int rows_per_tile,
+                     std::vector<EdgeTile>& out, int* max_nsrc, int* max_rows);
+
+static int edge_forward_dispatch(gcnn_workspace* ws, const gcnn_batch* b, int conv, const EdgeLayout& L, int64_t n_recv,
+                                 const float* R, const float* S, const float* w_edge, EdgeScalars sc, float* H,
+                                 float* cnt, cudaStream_t st, double prof_bytes, int64_t n_edges) {
+    if (ws->use_tiles && b->n_samples > 0 && b->sample_n_cons && b->sample_n_vars && b->sample_n_cuts && n_recv > 0) {
+        const int32_t* recv = conv == 0 ? b->sample_n_cons : (conv == 1 ? b->sample_n_vars : b->sample_n_cuts);
+        const int32_t* send = conv == 1 ? b->sample_n_cons : b->sample_n_vars;
+        int64_t sum_r = 0, sum_s = 0;
+        for (int64_t s = 0; s < b->n_samples; ++s) { sum_r += recv[s]; sum_s += send[s]; }
+        const int64_t n_send = conv == 1 ? b->n_cons : b->n_vars;
+        std::vector<EdgeTile> tiles;
+        int max_nsrc = 0, max_rows = 0;
+        // dense segments only: staging a table pays off when rows gather many sources each
+        if (sum_r == n_recv && sum_s == n_send && n_edges >= 8 * n_recv &&
+            plan_edge_tiles(recv, send, b->n_samples, 128, tiles, &max_nsrc, &max_rows) &&
+            (int64_t)tiles.size() <= ws->tile_cap) {
+            // pageable source: the driver stages the copy before returning, so the vector may die right away
+            GCNN_CUDA_TRY(cudaMemcpyAsync(ws->d_tiles[conv], tiles.data(), sizeof(EdgeTile) * tiles.size(),
+                                          cudaMemcpyHostToDevice, st));
+            return edge_forward_tiles(ws->d_tiles[conv], (int)tiles.size(), max_nsrc, max_rows, n_recv, n_edges, L, R, S,
+                                      w_edge, sc, H, cnt, ws->flags + 1, st, prof_bytes);
+        }
+    }
+    return edge_forward(L, n_recv, R, S, w_edge, sc, H, cnt, st, prof_bytes, n_edges);
 }
 
 // ---- dense-layer dispatch: tcgen05 3xTF32 tensor-core kernel (default) or the fp32 SIMT kernel (GCNN_TC=0) ---------
@@ -324,7 +360,7 @@ static int forward_convs_fused(gcnn_workspace* ws, const float* p, const float* 
         if (stop_layer == 5 + 2 * i) return wait_all_layouts();
         const int64_t E_i = graph_of[i] == 0 ? ec : ek;
         const double fwd_bytes = 256.0 * (double)(n_left[i] + nv + n_recv[i]) + 8.0 * (double)E_i + 4.0 * (double)(n_recv[i] + 1);
-        GCNN_TRY(edge_forward(L, n_recv[i], R, S, p + o.we, sc, a.H, a.cnt, st, fwd_bytes));
+        GCNN_TRY(edge_forward_dispatch(ws, b, i, L, n_recv[i], R, S, p + o.we, sc, a.H, keep ? a.cnt : nullptr, st, fwd_bytes, E_i));
         ConvFwdArgs c{};
         c.H = a.H; c.Xt = recv_in[i]; c.deg_ptr = L.ptr; c.s_p = pn + PN.conv_sp[i];
         c.img_f = img_t(o.Wf); c.bias_f = p + o.bf;
@@ -421,7 +457,7 @@ static int forward_impl(gcnn_workspace* ws, const float* p, const float* pn, con
         // segment pointer; write the reduced rows
         const int64_t E_i = graph_of[i] == 0 ? ec : ek;
         const double fwd_bytes = 256.0 * (double)(n_left[i] + nv + n_recv) + 8.0 * (double)E_i + 4.0 * (double)(n_recv + 1);
-        GCNN_TRY(edge_forward(L, n_recv, R, S, p + o.we, sc, a.H, a.cnt, st, fwd_bytes));
+        GCNN_TRY(edge_forward_dispatch(ws, b, i, L, n_recv, R, S, p + o.we, sc, a.H, a.cnt, st, fwd_bytes, E_i));
         LinFwdArgs pc{a.H, nullptr, nullptr, p + o.Wf, p + o.bf, L.ptr, a.C, n_recv, 64, 0};
         GCNN_TRY(dense_forward(ws, p, pc, st));
         if (stop_layer == 6 + 2 * i) { if (s1 != st) GCNN_CUDA_TRY(cudaStreamWaitEvent(st, ws->ev_layout[3], 0)); return GCNN_OK; }
@@ -533,7 +569,7 @@ static int backward_impl(gcnn_workspace* ws, const float* p, const float* pn, co
         const int64_t E_i = graph_of[i] == 0 ? b->n_cons_edges : b->n_cut_edges;
         const double bwd_bytes = 256.0 * (double)(2 * n_recv + 2 * n_send) + 8.0 * (double)E_i + 4.0 * (double)(n_send + 1);
         GCNN_TRY(edge_backward(Ls, n_send, R, S, ws->t_G, p + o.we, sc, ws->t_dS, ws->dw_partials[i], &n_dw, st,
-                               bwd_bytes));
+                               bwd_bytes, E_i));
         add_job(ws->dw_partials[i], n_dw, D, D, o.we);
         const float* dA = recv_is_left[i] ? ws->t_dR : ws->t_dS;
         const float* dB = recv_is_left[i] ? ws->t_dS : ws->t_dR;
@@ -614,6 +650,7 @@ static int read_error_flag(gcnn_workspace* ws, cudaStream_t st) {
     if (flag) {
         GCNN_CUDA_TRY(cudaMemsetAsync(ws->flags + 1, 0, sizeof(int32_t), st));
         if (flag & 1) set_error("edge index out of range (InvalidArgument, cf. tf.gather in model.py:564)");
+        else if (flag & 4) set_error("an edge leaves its sample's node range although per-sample counts were given");
         else set_error("batch flags claim edges sorted by row 0 (utils.py:102-104 order) but they are not");
         return GCNN_INVALID;
     }
@@ -717,6 +754,8 @@ int gcnn_workspace_create(gcnn_workspace** out) {
     ws->use_tc = !(tc && tc[0] == '0');
     const char* ms = getenv("GCNN_STREAMS");  // GCNN_STREAMS=0 serialises everything on the caller's stream
     ws->use_streams = !(ms && ms[0] == '0');
+    const char* ti = getenv("GCNN_TILES");  // GCNN_TILES=1: shared-memory tile edge kernel when per-sample counts are given
+    ws->use_tiles = ti && ti[0] == '1';
     const char* fu = getenv("GCNN_FUSED");  // GCNN_FUSED=0: one launch per dense layer
     ws->use_fused = !(fu && fu[0] == '0');
     for (int i = 0; i < 2; ++i) GCNN_CUDA_TRY(cudaStreamCreateWithFlags(&ws->aux[i], cudaStreamNonBlocking));
@@ -771,6 +810,7 @@ int gcnn_set_option(gcnn_workspace* ws, const char* name, int value) {
     if (!strcmp(name, "tensor_cores")) ws->use_tc = value != 0;
     else if (!strcmp(name, "streams")) ws->use_streams = value != 0;
     else if (!strcmp(name, "fused")) ws->use_fused = value != 0;
+    else if (!strcmp(name, "tiles")) ws->use_tiles = value != 0;
     else { set_error("unknown option %s", name); return GCNN_INVALID; }
     return GCNN_OK;
 }
@@ -999,7 +1039,10 @@ int gcnn_edge_forward(const int32_t* ptr, const int32_t* src, const float* val, 
     int rc = GCNN_OK;
     if (e == cudaSuccess) {
         EdgeLayout L{const_cast<int32_t*>(ptr), const_cast<int32_t*>(src), const_cast<float*>(val), nullptr};
-        rc = edge_forward(L, n_recv, R, S, w_edge, EdgeScalars{dev, dev + 1, dev + 2}, H, cnt, st);
+        int32_t n_edges = 0;  // the segment pointer's last entry; this test entry point synchronises anyway
+        cudaMemcpyAsync(&n_edges, ptr + n_recv, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        rc = edge_forward(L, n_recv, R, S, w_edge, EdgeScalars{dev, dev + 1, dev + 2}, H, cnt, st, 0.0, n_edges);
     }
     cudaStreamSynchronize(st);
     cudaFree(dev);
@@ -1020,8 +1063,11 @@ int gcnn_edge_backward(gcnn_workspace* ws, const int32_t* ptr, const int32_t* ot
     if (e == cudaSuccess) {
         EdgeLayout L{const_cast<int32_t*>(ptr), const_cast<int32_t*>(other), const_cast<float*>(val), nullptr};
         int n_dw = 0;
+        int32_t n_edges = 0;
+        cudaMemcpyAsync(&n_edges, ptr + n_send, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
         rc = edge_backward(L, n_send, R, S, G, w_edge, EdgeScalars{dev, dev + 1, dev + 2}, dS, ws->dw_partials[0],
-                           &n_dw, st);
+                           &n_dw, st, 0.0, n_edges);
         if (rc == GCNN_OK) {
             ReduceJob job{ws->dw_partials[0], n_dw, D, D, 0, nullptr};
             rc = reduce_partials(&job, 1, dw, st);

@@ -116,11 +116,18 @@ struct EdgeScalars {  // device pointers to the scalars so no host sync is neede
     const float* s_f;
 };
 int edge_forward(const EdgeLayout& by_recv, int64_t n_recv, const float* R, const float* S, const float* w_edge,
-                 EdgeScalars sc, float* H, float* cnt, cudaStream_t st, double prof_bytes = 0.0);
+                 EdgeScalars sc, float* H, float* cnt, cudaStream_t st, double prof_bytes = 0.0,
+                 int64_t n_edges = 0);
 int edge_backward(const EdgeLayout& by_send, int64_t n_send, const float* R, const float* S, const float* G,
                   const float* w_edge, EdgeScalars sc, float* dS, float* dw_partials, int* n_partials,
-                  cudaStream_t st, double prof_bytes = 0.0);
+                  cudaStream_t st, double prof_bytes = 0.0, int64_t n_edges = 0);
 int edge_backward_max_partials();
+
+// tile variant of the forward edge kernel (edge_tile.cu): source table staged in shared memory per sample block
+struct EdgeTile { int32_t row0, row1, src0, nsrc; };
+int edge_forward_tiles(const EdgeTile* tiles_dev, int n_tiles, int max_nsrc, int max_rows, int64_t n_recv,
+                       int64_t n_edges, const EdgeLayout& L, const float* R, const float* S, const float* w_edge,
+                       EdgeScalars sc, float* H, float* cnt, int32_t* err_flag, cudaStream_t st, double prof_bytes);
 // sum and sum of squares of (z_e - center) over all E x 64 joint pre-activations (double accumulators)
 int edge_z_stats(const EdgeLayout& by_recv, int64_t n_recv, const float* R, const float* S, const float* w_edge,
                  EdgeScalars sc, double center, double* partials, double* out2, cudaStream_t st);

@@ -31,7 +31,35 @@ __device__ __forceinline__ float4 shfl_xor4(float4 v, int m) {
 
 // ------------------------------------------------------------------------------------------------------------------
 // Forward: H[t] = sum_{e in seg(t)} relu(s_f * (R[t] + f_e * w + S[src_e])),  cnt[t] = #active terms per feature.
+//
+// The kernel is bound by instruction issue, not by bandwidth (profiles/: ~67 % issue-slot utilisation at ~10 % of the
+// HBM roofline), so the inner loop is written for instruction count:
+//   * full groups of 8 edges run without any predication (4 steps x 2 edges, 4 gathers in flight per half-warp); only
+//     the last partial group of a chunk takes the predicated path;
+//   * the pre-activation uses Blackwell's packed FP32x2 pipe: FFMA2 + FADD2 + FMUL2 produce two features per
+//     instruction with the same per-operation rounding as the scalar sequence s_f * ((r + f w) + g);
+//   * one FSETP per feature feeds both predicated accumulations (value and active count).
 // ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 lo2(const float4 v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(const float4 v) { return make_float2(v.z, v.w); }
+
+// y = s_f * ((r + f * w) + g) for four features, two packed instructions triples
+__device__ __forceinline__ void preact4(const float4 r4, const float4 w4, const float4 g, const float f, const float s_f,
+                                        float2& y01, float2& y23) {
+    const float2 f2 = make_float2(f, f), s2 = make_float2(s_f, s_f);
+    y01 = __fmul2_rn(__fadd2_rn(__ffma2_rn(f2, lo2(w4), lo2(r4)), lo2(g)), s2);
+    y23 = __fmul2_rn(__fadd2_rn(__ffma2_rn(f2, hi2(w4), hi2(r4)), hi2(g)), s2);
+}
+
+template <bool TRAIN>
+__device__ __forceinline__ void relu_accumulate(const float2 y01, const float2 y23, float4& acc, float4& act) {
+    if (y01.x > 0.f) { acc.x += y01.x; if (TRAIN) act.x += 1.f; }
+    if (y01.y > 0.f) { acc.y += y01.y; if (TRAIN) act.y += 1.f; }
+    if (y23.x > 0.f) { acc.z += y23.x; if (TRAIN) act.z += 1.f; }
+    if (y23.y > 0.f) { acc.w += y23.y; if (TRAIN) act.w += 1.f; }
+}
+
+template <bool TRAIN>
 __global__ void __launch_bounds__(EDGE_THREADS)
 edge_forward_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ src, const float* __restrict__ val,
                     int64_t n_recv, const float* __restrict__ R, const float* __restrict__ S,
@@ -43,55 +71,66 @@ edge_forward_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__
     const int beg = ptr[row], end = ptr[row + 1];
     const float4 r4 = ld4(R + row * D + hl * 4);
     const float4 w4 = ldg4(w_edge + hl * 4);
+    const float* Sl = S + hl * 4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), act = acc;
 
     for (int base = beg; base < end; base += 32) {
-        const int n = min(32, end - base);
+        const int n = min(32, end - base);  // warp-uniform
         int my_src = 0;
         float my_f = 0.f;
         if (lane < n) {
             my_src = src[base + lane];
             my_f = (val[base + lane] + f_shift) * f_scale;
         }
-        // each half-warp takes every other edge; 4 gathers in flight per half-warp
-        for (int j0 = 0; j0 < n; j0 += 8) {
+        const int n_full = n & ~7;
+        int j0 = 0;
+        for (; j0 < n_full; j0 += 8) {  // 8 edges: each half-warp takes every other one, no predication
             float4 g[4];
             float f[4];
-            bool ok[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int j = j0 + 2 * u + half;
-                ok[u] = j < n;
-                const int s = __shfl_sync(0xffffffffu, my_src, ok[u] ? j : 0);
-                f[u] = __shfl_sync(0xffffffffu, my_f, ok[u] ? j : 0);
-                g[u] = ok[u] ? ld4(S + (int64_t)s * D + hl * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const int sj = __shfl_sync(0xffffffffu, my_src, j);
+                f[u] = __shfl_sync(0xffffffffu, my_f, j);
+                g[u] = ld4(Sl + (int64_t)sj * D);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                if (ok[u]) {
-                    float y;
-                    y = s_f * (r4.x + f[u] * w4.x + g[u].x); if (y > 0.f) { acc.x += y; act.x += 1.f; }
-                    y = s_f * (r4.y + f[u] * w4.y + g[u].y); if (y > 0.f) { acc.y += y; act.y += 1.f; }
-                    y = s_f * (r4.z + f[u] * w4.z + g[u].z); if (y > 0.f) { acc.z += y; act.z += 1.f; }
-                    y = s_f * (r4.w + f[u] * w4.w + g[u].w); if (y > 0.f) { acc.w += y; act.w += 1.f; }
-                }
+                float2 y01, y23;
+                preact4(r4, w4, g[u], f[u], s_f, y01, y23);
+                relu_accumulate<TRAIN>(y01, y23, acc, act);
+            }
+        }
+        for (; j0 < n; j0 += 2) {  // tail of the chunk: at most 7 edges
+            const int j = j0 + half;
+            const bool ok = j < n;
+            const int sj = __shfl_sync(0xffffffffu, my_src, j & 31);
+            const float f = __shfl_sync(0xffffffffu, my_f, j & 31);
+            if (ok) {
+                float2 y01, y23;
+                preact4(r4, w4, ld4(Sl + (int64_t)sj * D), f, s_f, y01, y23);
+                relu_accumulate<TRAIN>(y01, y23, acc, act);
             }
         }
     }
-    const float4 acc_o = shfl_xor4(acc, 16), act_o = shfl_xor4(act, 16);
+    const float4 acc_o = shfl_xor4(acc, 16);
     if (half == 0) {
         st4(H + row * D + hl * 4, make_float4(acc.x + acc_o.x, acc.y + acc_o.y, acc.z + acc_o.z, acc.w + acc_o.w));
-    } else {  // (even-edge half) + (odd-edge half) in the same order as the H sum
-        st4(cnt + row * D + hl * 4, make_float4(act_o.x + act.x, act_o.y + act.y, act_o.z + act.z, act_o.w + act.w));
+    }
+    if (TRAIN) {  // (even-edge half) + (odd-edge half); counts are small integers, exact in fp32
+        const float4 act_o = shfl_xor4(act, 16);
+        if (half == 1)
+            st4(cnt + row * D + hl * 4, make_float4(act_o.x + act.x, act_o.y + act.y, act_o.z + act.z, act_o.w + act.w));
     }
 }
 
 int edge_forward(const EdgeLayout& L, int64_t n_recv, const float* R, const float* S, const float* w_edge,
-                 EdgeScalars sc, float* H, float* cnt, cudaStream_t st, double prof_bytes) {
+                 EdgeScalars sc, float* H, float* cnt, cudaStream_t st, double prof_bytes, int64_t /*n_edges*/) {
     if (n_recv <= 0) return GCNN_OK;
     ProfScope prof(PROF_EDGE_FWD, prof_bytes, st);
-    edge_forward_kernel<<<(unsigned)ceil_div(n_recv, EDGE_WARPS), EDGE_THREADS, 0, st>>>(L.ptr, L.other, L.val, n_recv,
-                                                                                         R, S, w_edge, sc, H, cnt);
+    const unsigned grid = (unsigned)ceil_div(n_recv, EDGE_WARPS);
+    if (cnt) edge_forward_kernel<true><<<grid, EDGE_THREADS, 0, st>>>(L.ptr, L.other, L.val, n_recv, R, S, w_edge, sc, H, cnt);
+    else edge_forward_kernel<false><<<grid, EDGE_THREADS, 0, st>>>(L.ptr, L.other, L.val, n_recv, R, S, w_edge, sc, H, cnt);
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
 }
@@ -99,9 +138,18 @@ int edge_forward(const EdgeLayout& L, int64_t n_recv, const float* R, const floa
 // ------------------------------------------------------------------------------------------------------------------
 // Backward over the transposed layout (segments grouped by the SENDING node s, t_e = other[e] the receiver):
 //   dz_e = s_f * 1[s_f * (R[t_e] + f_e w + S[s]) > 0] * G[t_e];   dS[s] = sum_e dz_e;   dw = sum_e f_e dz_e.
-// The receiving side needs no edge pass: dR[t] = s_f * G[t] * cnt[t] (node.cu epilogue).
-// dw is reduced warp -> CTA (fixed order) into per-CTA partials; reduce_partials() finishes it.
+// The receiving side needs no edge pass: dR[t] = s_f * G[t] * cnt[t] (dense-layer epilogue).
+// Same loop structure as the forward; the masked G rows are accumulated UNSCALED and s_f is applied once per segment
+// (dS) and once per CTA (dw).  dw is reduced warp -> CTA (fixed order) into per-CTA partials.
 // ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void masked_accumulate(const float2 y01, const float2 y23, const float4 g, const float f,
+                                                  float4& acc, float4& dw) {
+    if (y01.x > 0.f) { acc.x += g.x; dw.x = fmaf(f, g.x, dw.x); }
+    if (y01.y > 0.f) { acc.y += g.y; dw.y = fmaf(f, g.y, dw.y); }
+    if (y23.x > 0.f) { acc.z += g.z; dw.z = fmaf(f, g.z, dw.z); }
+    if (y23.y > 0.f) { acc.w += g.w; dw.w = fmaf(f, g.w, dw.w); }
+}
+
 __global__ void __launch_bounds__(EDGE_THREADS)
 edge_backward_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ other,
                      const float* __restrict__ val, int64_t n_send, const float* __restrict__ R,
@@ -111,6 +159,8 @@ edge_backward_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict_
     const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15, warp = threadIdx.x >> 5;
     const float f_shift = sc.f_shift ? *sc.f_shift : 0.f, f_scale = sc.f_scale ? *sc.f_scale : 1.f, s_f = *sc.s_f;
     const float4 w4 = ldg4(w_edge + hl * 4);
+    const float* Rl = R + hl * 4;
+    const float* Gl = G + hl * 4;
     float4 dw = make_float4(0.f, 0.f, 0.f, 0.f);
 
     for (int64_t row = (int64_t)blockIdx.x * EDGE_WARPS + warp; row < n_send; row += (int64_t)gridDim.x * EDGE_WARPS) {
@@ -125,37 +175,46 @@ edge_backward_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict_
                 my_t = other[base + lane];
                 my_f = (val[base + lane] + f_shift) * f_scale;
             }
-            for (int j0 = 0; j0 < n; j0 += 4) {
+            const int n_full = n & ~3;
+            int j0 = 0;
+            for (; j0 < n_full; j0 += 4) {  // 4 edges, 2 per half-warp: 4 gathers (R and G rows) in flight per lane
                 float4 r[2], g[2];
                 float f[2];
-                bool ok[2];
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     const int j = j0 + 2 * u + half;
-                    ok[u] = j < n;
-                    const int t = __shfl_sync(0xffffffffu, my_t, ok[u] ? j : 0);
-                    f[u] = __shfl_sync(0xffffffffu, my_f, ok[u] ? j : 0);
-                    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    r[u] = ok[u] ? ld4(R + (int64_t)t * D + hl * 4) : z4;
-                    g[u] = ok[u] ? ld4(G + (int64_t)t * D + hl * 4) : z4;
+                    const int t = __shfl_sync(0xffffffffu, my_t, j);
+                    f[u] = __shfl_sync(0xffffffffu, my_f, j);
+                    r[u] = ld4(Rl + (int64_t)t * D);
+                    g[u] = ld4(Gl + (int64_t)t * D);
                 }
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
-                    if (ok[u]) {
-                        float d;
-                        d = (s_f * (r[u].x + f[u] * w4.x + s4.x) > 0.f) ? s_f * g[u].x : 0.f; acc.x += d; dw.x += f[u] * d;
-                        d = (s_f * (r[u].y + f[u] * w4.y + s4.y) > 0.f) ? s_f * g[u].y : 0.f; acc.y += d; dw.y += f[u] * d;
-                        d = (s_f * (r[u].z + f[u] * w4.z + s4.z) > 0.f) ? s_f * g[u].z : 0.f; acc.z += d; dw.z += f[u] * d;
-                        d = (s_f * (r[u].w + f[u] * w4.w + s4.w) > 0.f) ? s_f * g[u].w : 0.f; acc.w += d; dw.w += f[u] * d;
-                    }
+                    float2 y01, y23;
+                    preact4(r[u], w4, s4, f[u], s_f, y01, y23);  // same association as the forward: (R + f w) + S
+                    masked_accumulate(y01, y23, g[u], f[u], acc, dw);
+                }
+            }
+            for (; j0 < n; j0 += 2) {
+                const int j = j0 + half;
+                const bool ok = j < n;
+                const int t = __shfl_sync(0xffffffffu, my_t, j & 31);
+                const float f = __shfl_sync(0xffffffffu, my_f, j & 31);
+                if (ok) {
+                    float2 y01, y23;
+                    preact4(ld4(Rl + (int64_t)t * D), w4, s4, f, s_f, y01, y23);
+                    masked_accumulate(y01, y23, ld4(Gl + (int64_t)t * D), f, acc, dw);
                 }
             }
         }
         const float4 o = shfl_xor4(acc, 16);
-        if (half == 0) st4(dS + row * D + hl * 4, make_float4(acc.x + o.x, acc.y + o.y, acc.z + o.z, acc.w + o.w));
+        if (half == 0)
+            st4(dS + row * D + hl * 4,
+                make_float4(s_f * (acc.x + o.x), s_f * (acc.y + o.y), s_f * (acc.z + o.z), s_f * (acc.w + o.w)));
     }
     const float4 o = shfl_xor4(dw, 16);
-    if (half == 0) red[warp][hl] = make_float4(dw.x + o.x, dw.y + o.y, dw.z + o.z, dw.w + o.w);
+    if (half == 0)
+        red[warp][hl] = make_float4(s_f * (dw.x + o.x), s_f * (dw.y + o.y), s_f * (dw.z + o.z), s_f * (dw.w + o.w));
     __syncthreads();
     if (threadIdx.x < 16) {
         float4 t = red[0][threadIdx.x];
@@ -172,7 +231,7 @@ int edge_backward_max_partials() { return EDGE_BWD_MAX_CTAS; }
 
 int edge_backward(const EdgeLayout& L, int64_t n_send, const float* R, const float* S, const float* G,
                   const float* w_edge, EdgeScalars sc, float* dS, float* dw_partials, int* n_partials,
-                  cudaStream_t st, double prof_bytes) {
+                  cudaStream_t st, double prof_bytes, int64_t /*n_edges*/) {
     ProfScope prof(PROF_EDGE_BWD, prof_bytes, st);
     int ctas = (int)min((int64_t)EDGE_BWD_MAX_CTAS, ceil_div(n_send > 0 ? n_send : 1, EDGE_WARPS));
     *n_partials = ctas;

@@ -35,6 +35,18 @@ def _row0_sorted(ei) -> bool:
     return bool(ei.shape[1] < 2 or np.all(ei[0, 1:] >= ei[0, :-1]))
 
 
+def _host(x):
+    return x.detach().cpu().numpy() if torch.is_tensor(x) else np.asarray(x)
+
+
+def _sample_counts(n_cons, n_vars, n_cuts):
+    """Three contiguous int32 host vectors when all of n_cons / n_vars / n_cuts are per-sample vectors, else None."""
+    vecs = [_host(x) for x in (n_cons, n_vars, n_cuts)]
+    if any(v.ndim != 1 for v in vecs) or len({v.shape[0] for v in vecs}) != 1 or vecs[0].shape[0] == 0:
+        return None
+    return [np.ascontiguousarray(v, dtype=np.int32) for v in vecs]
+
+
 def _sorted_flags(cons_ei, cut_ei) -> int:
     return ((_lib.BATCH_CONS_EDGES_SORTED if _row0_sorted(cons_ei) else 0)
             | (_lib.BATCH_CUT_EDGES_SORTED if _row0_sorted(cut_ei) else 0))
@@ -229,7 +241,10 @@ class GCNN:
         t = [self._to_device(cons, f32), self._to_device(cons_ei, i32), self._to_device(cons_ef, f32),
              self._to_device(var, f32), self._to_device(cut, f32), self._to_device(cut_ei, i32),
              self._to_device(cut_ef, f32)]
-        n_cons, n_vars, n_cuts = int(n_cons), int(n_vars), int(n_cuts)
+        # n_cons / n_vars / n_cuts: the totals the reference passes (model_trainer.py:259-263), or the per-sample
+        # vectors load_batch returns (utils.py:420-422) -- the latter let the edge kernels stage per-sample tables
+        counts = _sample_counts(n_cons, n_vars, n_cuts)
+        n_cons, n_vars, n_cuts = (int(np.sum(_host(x))) for x in (n_cons, n_vars, n_cuts))
         if t[0].shape != (n_cons, CONS_FEATS) and not (n_cons == 0 and t[0].numel() == 0):
             raise InvalidArgumentError(f"cons_feats {tuple(t[0].shape)} vs n_cons {n_cons}")
         if t[3].numel() != n_vars * VAR_FEATS or t[4].numel() != n_cuts * CUT_FEATS:
@@ -241,6 +256,10 @@ class GCNN:
             raise InvalidArgumentError("edge features must be [E, 1]")
         b = Batch(t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(), t[4].data_ptr(),
                   t[5].data_ptr(), t[6].data_ptr(), n_cons, n_vars, n_cuts, e_c, e_k, flags)
+        if counts is not None:
+            b.sample_n_cons, b.sample_n_vars, b.sample_n_cuts = (c.ctypes.data for c in counts)
+            b.n_samples = counts[0].shape[0]
+            t = t + list(counts)  # keep the host arrays alive as long as the batch
         return b, t
 
     def reserve(self, batch: Batch, training: bool):
@@ -407,5 +426,10 @@ class HostBatch:
         self.batch = Batch(t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(), t[4].data_ptr(),
                            t[5].data_ptr(), t[6].data_ptr(), nc, nv, nk, t[1].shape[1], t[5].shape[1],
                            _sorted_flags(t[1], t[5]))
+        self.counts = _sample_counts(n_cons, n_vars, n_cuts)
+        if self.counts is not None:
+            b = self.batch
+            b.sample_n_cons, b.sample_n_vars, b.sample_n_cuts = (c.ctypes.data for c in self.counts)
+            b.n_samples = self.counts[0].shape[0]
         self.n_graphs = int(np.size(n_cons))
         self.h2d_bytes = sum(x.numel() * x.element_size() for x in self.tensors) + self.targets.numel() * 4

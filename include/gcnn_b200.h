@@ -61,6 +61,15 @@ typedef struct gcnn_batch {
      * as in every batch the reference produces (csr -> coo order, utils.py:102-104, 226-228; offsets utils.py:403-407).
      * The library still verifies it on the device and reports a violation as GCNN_INVALID at the next gcnn_check. */
     int64_t flags;
+    /* Optional per-sample node counts of the offset-concatenated batch, HOST pointers to n_samples int32 each (the
+     * n_cons / n_vars / n_cuts vectors utils.load_batch returns, utils.py:420-422); NULL / 0 when unknown.  They are a
+     * promise that sample s's edges only touch sample s's nodes (block-diagonal batch, utils.py:403-407); with it the
+     * edge kernels stage each sample's source table in shared memory.  A violated promise is reported as
+     * GCNN_INVALID at the next gcnn_check. */
+    const int32_t* sample_n_cons;
+    const int32_t* sample_n_vars;
+    const int32_t* sample_n_cuts;
+    int64_t n_samples;
 } gcnn_batch;
 
 #define GCNN_BATCH_CONS_EDGES_SORTED 1
