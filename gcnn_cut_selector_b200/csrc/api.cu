@@ -37,6 +37,11 @@ struct Profiler {
 };
 static Profiler g_prof;
 
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("GCNN_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 void count_launch(int n) {
     g_launches.fetch_add(n, std::memory_order_relaxed);
     if (g_prof.enabled && g_prof.current >= 0) g_prof.launches[g_prof.current] += n;

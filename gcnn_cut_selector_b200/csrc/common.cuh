@@ -51,6 +51,40 @@ struct ProfScope {  // records a start/stop event pair around the launches issue
         if (st__ != GCNN_OK) return st__; \
     } while (0)
 
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------------------------
+// A training step is a chain of ~80 short dependent kernels; with plain stream order every link pays the full
+// "grid drained -> memory flushed -> next grid scheduled" latency.  All kernels are launched with the programmatic
+// stream-serialization attribute and start with pdl_enter(): `griddepcontrol.wait` blocks until the previous grid in the
+// stream has completed and flushed (so every access after it is ordered as before), `griddepcontrol.launch_dependents`
+// then lets the NEXT grid be scheduled while this one still runs -- its CTAs are resident and parked on their own wait
+// by the time this grid finishes.  GCNN_PDL=0 launches without the attribute (the two instructions become no-ops).
+bool pdl_enabled();
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                        Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#define GCNN_LAUNCH(kern, grid, block, smem, st, ...) \
+    (void)gcnn::launch_kernel(kern, dim3(grid), dim3(block), (size_t)(smem), st, __VA_ARGS__)
+#endif
+
 __host__ __device__ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- parameter layout: offsets into the flat trainable / pre-norm buffers (reference order, model.py:174-208) ----

@@ -30,6 +30,7 @@ check_init_hist_kernel(const int32_t* __restrict__ keys, const int32_t* __restri
                        int32_t n_owner, int32_t n_other, int32_t* unsorted_flag, int32_t* err_flag, int hint_is_binding,
                        int32_t* __restrict__ key_out, int32_t* __restrict__ val_out, int32_t* __restrict__ hist0,
                        int32_t* __restrict__ hist1, int n_blocks) {
+    pdl_enter();
     __shared__ int32_t h[RADIX];
     if (!HINT_SORTED) {
         h[threadIdx.x] = 0;
@@ -69,6 +70,7 @@ check_init_hist_kernel(const int32_t* __restrict__ keys, const int32_t* __restri
 __global__ void __launch_bounds__(1024)
 exclusive_scan_kernel(int32_t* __restrict__ data, int64_t n, const int32_t* __restrict__ unsorted_flag,
                       int32_t* __restrict__ zero_buf) {
+    pdl_enter();
     if (!*unsorted_flag) return;
     if (zero_buf)  // histogram buffer the next scatter accumulates into
         for (int64_t i = threadIdx.x; i < n; i += 1024) zero_buf[i] = 0;
@@ -137,6 +139,7 @@ __global__ void __launch_bounds__(SORT_THREADS)
 radix_scatter_kernel(const int32_t* __restrict__ key_in, const int32_t* __restrict__ val_in, int64_t E, int shift,
                      const int32_t* __restrict__ unsorted_flag, const int32_t* __restrict__ offsets, int n_blocks,
                      int32_t* __restrict__ key_out, int32_t* __restrict__ val_out, int32_t* __restrict__ hist_next) {
+    pdl_enter();
     if (!*unsorted_flag) return;
     constexpr int WARPS = SORT_THREADS / 32;
     __shared__ int32_t running[RADIX];          // global offset of the next item of each digit for this CTA
@@ -185,6 +188,7 @@ __global__ void finalize_layout_kernel(const int32_t* __restrict__ keys, const i
                                        const float* __restrict__ feats, int64_t E, int32_t n_owner,
                                        int32_t n_other, const int32_t* __restrict__ unsorted_flag, const int32_t* __restrict__ sorted_keys,
                                        const int32_t* __restrict__ sorted_perm, EdgeLayout out) {
+    pdl_enter();
     const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (p > E) return;
     const bool presorted = *unsorted_flag == 0;
@@ -230,12 +234,12 @@ int build_layout(const int32_t* keys, const int32_t* others, const float* feats,
     int32_t* scratch_flag = sc.flags;          // written, never read
     const int32_t* zero_flag = sc.flags + 6;   // never written: reads as "sorted"
     if (hint_sorted || trivially_sorted) {
-        check_init_hist_kernel<true><<<n_blocks, SORT_THREADS, 0, st>>>(
+        GCNN_LAUNCH(check_init_hist_kernel<true>, n_blocks, SORT_THREADS, 0, st, 
             keys, others, E, (int32_t)n_owner, (int32_t)n_other, trivially_sorted ? scratch_flag : unsorted_flag,
             err_flag, trivially_sorted ? 0 : 1, nullptr, nullptr, nullptr, nullptr, n_blocks);
         GCNN_LAUNCH_CHECK();
     } else {
-        check_init_hist_kernel<false><<<n_blocks, SORT_THREADS, 0, st>>>(
+        GCNN_LAUNCH(check_init_hist_kernel<false>, n_blocks, SORT_THREADS, 0, st, 
             keys, others, E, (int32_t)n_owner, (int32_t)n_other, unsorted_flag, err_flag, 0, sc.key_a, sc.val_a, hist0,
             hist1, n_blocks);
         GCNN_LAUNCH_CHECK();
@@ -249,9 +253,9 @@ int build_layout(const int32_t* keys, const int32_t* others, const float* feats,
         for (int shift = 0, pass = 0; shift < bits; shift += 8, ++pass) {
             const bool more = shift + 8 < bits;
             // pass 0 finds hist1 zeroed by the first kernel; later passes zero their "next" buffer in the scan
-            exclusive_scan_kernel<<<1, 1024, 0, st>>>(hcur, hist_n, unsorted_flag, (more && pass > 0) ? hnext : nullptr);
+            GCNN_LAUNCH(exclusive_scan_kernel, 1, 1024, 0, st, hcur, hist_n, unsorted_flag, (more && pass > 0) ? hnext : nullptr);
             GCNN_LAUNCH_CHECK();
-            radix_scatter_kernel<<<n_blocks, SORT_THREADS, 0, st>>>(ka, va, E, shift, unsorted_flag, hcur, n_blocks, kb,
+            GCNN_LAUNCH(radix_scatter_kernel, n_blocks, SORT_THREADS, 0, st, ka, va, E, shift, unsorted_flag, hcur, n_blocks, kb,
                                                                     vb, more ? hnext : nullptr);
             GCNN_LAUNCH_CHECK();
             int32_t* t;
@@ -263,7 +267,7 @@ int build_layout(const int32_t* keys, const int32_t* others, const float* feats,
         sorted_perm = va;
     }
     const int threads = 256;
-    finalize_layout_kernel<<<(unsigned)ceil_div(E + 1, threads), threads, 0, st>>>(
+    GCNN_LAUNCH(finalize_layout_kernel, (unsigned)ceil_div(E + 1, threads), threads, 0, st, 
         keys, others, feats, E, (int32_t)n_owner, (int32_t)n_other,
         // a violated hint leaves unsorted_flag = 1 with no sorted pairs: fall back to the input order (the error is
         // reported through err_flag) by reading the always-zero word

@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(EDGE_THREADS)
 edge_forward_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ src, const float* __restrict__ val,
                     int64_t n_recv, const float* __restrict__ R, const float* __restrict__ S,
                     const float* __restrict__ w_edge, EdgeScalars sc, float* __restrict__ H, float* __restrict__ cnt) {
+    pdl_enter();
     const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
     const int64_t row = (int64_t)blockIdx.x * EDGE_WARPS + (threadIdx.x >> 5);
     if (row >= n_recv) return;
@@ -129,8 +130,8 @@ int edge_forward(const EdgeLayout& L, int64_t n_recv, const float* R, const floa
     if (n_recv <= 0) return GCNN_OK;
     ProfScope prof(PROF_EDGE_FWD, prof_bytes, st);
     const unsigned grid = (unsigned)ceil_div(n_recv, EDGE_WARPS);
-    if (cnt) edge_forward_kernel<true><<<grid, EDGE_THREADS, 0, st>>>(L.ptr, L.other, L.val, n_recv, R, S, w_edge, sc, H, cnt);
-    else edge_forward_kernel<false><<<grid, EDGE_THREADS, 0, st>>>(L.ptr, L.other, L.val, n_recv, R, S, w_edge, sc, H, cnt);
+    if (cnt) GCNN_LAUNCH(edge_forward_kernel<true>, grid, EDGE_THREADS, 0, st, L.ptr, L.other, L.val, n_recv, R, S, w_edge, sc, H, cnt);
+    else GCNN_LAUNCH(edge_forward_kernel<false>, grid, EDGE_THREADS, 0, st, L.ptr, L.other, L.val, n_recv, R, S, w_edge, sc, H, cnt);
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
 }
@@ -155,6 +156,7 @@ edge_backward_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict_
                      const float* __restrict__ val, int64_t n_send, const float* __restrict__ R,
                      const float* __restrict__ S, const float* __restrict__ G, const float* __restrict__ w_edge,
                      EdgeScalars sc, float* __restrict__ dS, float* __restrict__ dw_partials) {
+    pdl_enter();
     __shared__ float4 red[EDGE_WARPS][16];
     const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15, warp = threadIdx.x >> 5;
     const float f_shift = sc.f_shift ? *sc.f_shift : 0.f, f_scale = sc.f_scale ? *sc.f_scale : 1.f, s_f = *sc.s_f;
@@ -235,7 +237,7 @@ int edge_backward(const EdgeLayout& L, int64_t n_send, const float* R, const flo
     ProfScope prof(PROF_EDGE_BWD, prof_bytes, st);
     int ctas = (int)min((int64_t)EDGE_BWD_MAX_CTAS, ceil_div(n_send > 0 ? n_send : 1, EDGE_WARPS));
     *n_partials = ctas;
-    edge_backward_kernel<<<ctas, EDGE_THREADS, 0, st>>>(L.ptr, L.other, L.val, n_send, R, S, G, w_edge, sc, dS,
+    GCNN_LAUNCH(edge_backward_kernel, ctas, EDGE_THREADS, 0, st, L.ptr, L.other, L.val, n_send, R, S, G, w_edge, sc, dS,
                                                         dw_partials);
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
@@ -251,6 +253,7 @@ __global__ void __launch_bounds__(EDGE_THREADS)
 edge_z_stats_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ src, const float* __restrict__ val,
                     int64_t n_recv, const float* __restrict__ R, const float* __restrict__ S,
                     const float* __restrict__ w_edge, EdgeScalars sc, double center, double* __restrict__ partials) {
+    pdl_enter();
     __shared__ double red[2][EDGE_THREADS];
     const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15, warp = threadIdx.x >> 5;
     const float f_shift = sc.f_shift ? *sc.f_shift : 0.f, f_scale = sc.f_scale ? *sc.f_scale : 1.f;
@@ -284,6 +287,7 @@ edge_z_stats_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__
 
 __global__ void sum_double_partials_kernel(const double* __restrict__ partials, int n_parts, int width,
                                            double* __restrict__ out) {
+    pdl_enter();
     const int c = threadIdx.x;
     if (c >= width) return;
     double t = 0.0;
@@ -295,10 +299,10 @@ int edge_z_stats(const EdgeLayout& L, int64_t n_recv, const float* R, const floa
                  EdgeScalars sc, double center, double* partials, double* out2, cudaStream_t st) {
     ProfScope prof(PROF_STATS, 0.0, st);
     const int ctas = (int)min((int64_t)STATS_CTAS, ceil_div(n_recv > 0 ? n_recv : 1, EDGE_WARPS));
-    edge_z_stats_kernel<<<ctas, EDGE_THREADS, 0, st>>>(L.ptr, L.other, L.val, n_recv, R, S, w_edge, sc, center,
+    GCNN_LAUNCH(edge_z_stats_kernel, ctas, EDGE_THREADS, 0, st, L.ptr, L.other, L.val, n_recv, R, S, w_edge, sc, center,
                                                        partials);
     GCNN_LAUNCH_CHECK();
-    sum_double_partials_kernel<<<1, 32, 0, st>>>(partials, ctas, 2, out2);
+    GCNN_LAUNCH(sum_double_partials_kernel, 1, 32, 0, st, partials, ctas, 2, out2);
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
 }
@@ -307,6 +311,7 @@ int edge_z_stats(const EdgeLayout& L, int64_t n_recv, const float* R, const floa
 __global__ void __launch_bounds__(256)
 col_stats_kernel(const float* __restrict__ x, int64_t M, int K, const double* __restrict__ center,
                  double* __restrict__ partials) {
+    pdl_enter();
     __shared__ double red[256 * 2];
     // thread (r, c): c = column, r = row lane; K columns x (256 / Kp) row lanes, Kp = K rounded up to a power of two
     int Kp = 1;
@@ -342,9 +347,9 @@ int col_stats(const float* x, int64_t M, int K, const double* center_dev, double
     int Kp = 1;
     while (Kp < K) Kp <<= 1;
     const int ctas = (int)min((int64_t)STATS_CTAS, ceil_div(M > 0 ? M : 1, 256 / Kp));
-    col_stats_kernel<<<ctas, 256, 0, st>>>(x, M, K, center_dev, partials);
+    GCNN_LAUNCH(col_stats_kernel, ctas, 256, 0, st, x, M, K, center_dev, partials);
     GCNN_LAUNCH_CHECK();
-    sum_double_partials_kernel<<<1, 128, 0, st>>>(partials, ctas, 2 * K, out);
+    GCNN_LAUNCH(sum_double_partials_kernel, 1, 128, 0, st, partials, ctas, 2 * K, out);
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
 }

@@ -40,6 +40,7 @@ edge_forward_tile_kernel(const EdgeTile* __restrict__ tiles, const int32_t* __re
                          const float* __restrict__ S, const float* __restrict__ w_edge, EdgeScalars sc,
                          float* __restrict__ H, float* __restrict__ cnt, int32_t* __restrict__ err_flag,
                          int table_rows, int edge_cap) {
+    pdl_enter();
     extern __shared__ __align__(16) float smem_f[];
     const EdgeTile tile = tiles[blockIdx.x];
     const int fo = blockIdx.y * TILE_FW;
@@ -182,12 +183,12 @@ int edge_forward_tiles(const EdgeTile* tiles_dev, int n_tiles, int max_nsrc, int
     if (cnt) {
         static int once = tile_set_smem(edge_forward_tile_kernel<true>);
         GCNN_TRY(once);
-        edge_forward_tile_kernel<true><<<grid, TILE_THREADS, smem, st>>>(tiles_dev, L.ptr, L.other, L.val, R, S, w_edge,
+        GCNN_LAUNCH(edge_forward_tile_kernel<true>, grid, TILE_THREADS, smem, st, tiles_dev, L.ptr, L.other, L.val, R, S, w_edge,
                                                                          sc, H, cnt, err_flag, max_nsrc, edge_cap);
     } else {
         static int once = tile_set_smem(edge_forward_tile_kernel<false>);
         GCNN_TRY(once);
-        edge_forward_tile_kernel<false><<<grid, TILE_THREADS, smem, st>>>(tiles_dev, L.ptr, L.other, L.val, R, S, w_edge,
+        GCNN_LAUNCH(edge_forward_tile_kernel<false>, grid, TILE_THREADS, smem, st, tiles_dev, L.ptr, L.other, L.val, R, S, w_edge,
                                                                           sc, H, cnt, err_flag, max_nsrc, edge_cap);
     }
     GCNN_LAUNCH_CHECK();

@@ -48,6 +48,7 @@ __device__ __forceinline__ void tile_mma(const float* __restrict__ Xs, const flo
 template <int K>
 __global__ void __launch_bounds__(LIN_THREADS)
 linear_forward_kernel(LinFwdArgs a) {
+    pdl_enter();
     extern __shared__ __align__(16) float smem[];
     constexpr int LDX = K + 4;
     float* Xs = smem;                   // [128][K+4]
@@ -105,12 +106,12 @@ int linear_forward(const LinFwdArgs& a, cudaStream_t st) {
         const size_t smem = sizeof(float) * (LIN_ROWS * 68 + 64 * D);
         static int once = set_smem(linear_forward_kernel<64>, smem);
         GCNN_TRY(once);
-        linear_forward_kernel<64><<<grid, LIN_THREADS, smem, st>>>(a);
+        GCNN_LAUNCH(linear_forward_kernel<64>, grid, LIN_THREADS, smem, st, a);
     } else if (a.K == 128) {
         const size_t smem = sizeof(float) * (LIN_ROWS * 132 + 128 * D);
         static int once = set_smem(linear_forward_kernel<128>, smem);
         GCNN_TRY(once);
-        linear_forward_kernel<128><<<grid, LIN_THREADS, smem, st>>>(a);
+        GCNN_LAUNCH(linear_forward_kernel<128>, grid, LIN_THREADS, smem, st, a);
     } else {
         set_error("linear_forward: K must be 64 or 128");
         return GCNN_INVALID;
@@ -123,6 +124,7 @@ int linear_forward(const LinFwdArgs& a, cudaStream_t st) {
 // blockIdx.y selects the 64-wide slab n0 = 64 * blockIdx.y of the K input features.
 __global__ void __launch_bounds__(LIN_THREADS)
 linear_dgrad_kernel(LinDgradArgs a) {
+    pdl_enter();
     extern __shared__ __align__(16) float smem[];
     constexpr int LDX = D + 4;
     float* Xs = smem;                   // masked dY tile [128][68]
@@ -194,7 +196,7 @@ int linear_dgrad(const LinDgradArgs& a, cudaStream_t st) {
     static int once = set_smem(linear_dgrad_kernel, smem);
     GCNN_TRY(once);
     dim3 grid((unsigned)ceil_div(a.M, LIN_ROWS), a.K / 64);
-    linear_dgrad_kernel<<<grid, LIN_THREADS, smem, st>>>(a);
+    GCNN_LAUNCH(linear_dgrad_kernel, grid, LIN_THREADS, smem, st, a);
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
 }
@@ -208,6 +210,7 @@ int wgrad_max_parts() { return WG_MAX_PARTS; }
 template <int K>
 __global__ void __launch_bounds__(LIN_THREADS)
 linear_wgrad_kernel(LinWgradArgs a) {
+    pdl_enter();
     constexpr int KR = K / 16;  // k rows per thread: 4 (K=64) or 8 (K=128)
     __shared__ __align__(16) float Xs[WG_ROWS][K];
     __shared__ __align__(16) float Ds[WG_ROWS][D];
@@ -286,8 +289,8 @@ int linear_wgrad(const LinWgradArgs& a, cudaStream_t st) {
     const int parts = (int)min((int64_t)WG_MAX_PARTS, ceil_div(a.M > 0 ? a.M : 1, WG_ROWS));
     *a.n_parts = parts;
     ProfScope prof(PROF_LIN_WGRAD, 4.0 * ((double)a.M * (a.K + D + (a.act ? D : 0)) + (double)a.K * D + D), st);
-    if (a.K == 64) linear_wgrad_kernel<64><<<parts, LIN_THREADS, 0, st>>>(a);
-    else if (a.K == 128) linear_wgrad_kernel<128><<<parts, LIN_THREADS, 0, st>>>(a);
+    if (a.K == 64) GCNN_LAUNCH(linear_wgrad_kernel<64>, parts, LIN_THREADS, 0, st, a);
+    else if (a.K == 128) GCNN_LAUNCH(linear_wgrad_kernel<128>, parts, LIN_THREADS, 0, st, a);
     else { set_error("linear_wgrad: K must be 64 or 128"); return GCNN_INVALID; }
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
@@ -298,6 +301,7 @@ template <int K>
 __global__ void __launch_bounds__(256)
 embed1_forward_kernel(const float* __restrict__ x, const float* __restrict__ shift, const float* __restrict__ scale,
                       const float* __restrict__ W, const float* __restrict__ b, float* __restrict__ Y, int64_t M) {
+    pdl_enter();
     __shared__ float Ws[K * D + D];
     __shared__ float sh[K], scl[K];
     for (int i = threadIdx.x; i < K * D; i += 256) Ws[i] = W[i];
@@ -323,9 +327,9 @@ int embed1_forward(const float* x, int K, const float* shift, const float* scale
     if (M <= 0) return GCNN_OK;
     ProfScope prof(PROF_EMB1_FWD, 4.0 * ((double)M * (K + D) + (double)K * D + D), st);
     const unsigned grid = (unsigned)min((int64_t)NUM_SMS * 8, ceil_div(M, 16));
-    if (K == 4) embed1_forward_kernel<4><<<grid, 256, 0, st>>>(x, shift, scale, W, b, Y, M);
-    else if (K == 6) embed1_forward_kernel<6><<<grid, 256, 0, st>>>(x, shift, scale, W, b, Y, M);
-    else if (K == 14) embed1_forward_kernel<14><<<grid, 256, 0, st>>>(x, shift, scale, W, b, Y, M);
+    if (K == 4) GCNN_LAUNCH(embed1_forward_kernel<4>, grid, 256, 0, st, x, shift, scale, W, b, Y, M);
+    else if (K == 6) GCNN_LAUNCH(embed1_forward_kernel<6>, grid, 256, 0, st, x, shift, scale, W, b, Y, M);
+    else if (K == 14) GCNN_LAUNCH(embed1_forward_kernel<14>, grid, 256, 0, st, x, shift, scale, W, b, Y, M);
     else { set_error("embed1_forward: K must be 4, 6 or 14"); return GCNN_INVALID; }
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
@@ -337,6 +341,7 @@ __global__ void __launch_bounds__(256)
 embed1_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ shift, const float* __restrict__ scale,
                     const float* __restrict__ dY, const float* __restrict__ act, int64_t M,
                     float* __restrict__ partials) {
+    pdl_enter();
     __shared__ float red[4][(K + 1) * D];
     __shared__ float sh[K], scl[K];
     if (threadIdx.x < K) { sh[threadIdx.x] = shift[threadIdx.x]; scl[threadIdx.x] = scale[threadIdx.x]; }
@@ -381,9 +386,9 @@ int embed1_wgrad(const float* x, int K, const float* shift, const float* scale, 
     const int parts = (int)min((int64_t)WG_MAX_PARTS, ceil_div(M > 0 ? M : 1, 64));
     *n_parts = parts;
     ProfScope prof(PROF_EMB1_WGRAD, 4.0 * ((double)M * (K + 2 * D) + (double)(K + 1) * D), st);
-    if (K == 4) embed1_wgrad_kernel<4><<<parts, 256, 0, st>>>(x, shift, scale, dY, act, M, partials);
-    else if (K == 6) embed1_wgrad_kernel<6><<<parts, 256, 0, st>>>(x, shift, scale, dY, act, M, partials);
-    else if (K == 14) embed1_wgrad_kernel<14><<<parts, 256, 0, st>>>(x, shift, scale, dY, act, M, partials);
+    if (K == 4) GCNN_LAUNCH(embed1_wgrad_kernel<4>, parts, 256, 0, st, x, shift, scale, dY, act, M, partials);
+    else if (K == 6) GCNN_LAUNCH(embed1_wgrad_kernel<6>, parts, 256, 0, st, x, shift, scale, dY, act, M, partials);
+    else if (K == 14) GCNN_LAUNCH(embed1_wgrad_kernel<14>, parts, 256, 0, st, x, shift, scale, dY, act, M, partials);
     else { set_error("embed1_wgrad: K must be 4, 6 or 14"); return GCNN_INVALID; }
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
@@ -393,6 +398,7 @@ int embed1_wgrad(const float* x, int K, const float* shift, const float* scale, 
 __global__ void __launch_bounds__(256)
 head2_forward_kernel(const float* __restrict__ g, const float* __restrict__ w, const float* __restrict__ b,
                      float* __restrict__ scores, int64_t M) {
+    pdl_enter();
     const int hl = threadIdx.x & 15;
     const int64_t m = (int64_t)blockIdx.x * 16 + (threadIdx.x >> 4);
     float s = 0.f;
@@ -408,7 +414,7 @@ head2_forward_kernel(const float* __restrict__ g, const float* __restrict__ w, c
 int head2_forward(const float* g, const float* w, const float* b, float* scores, int64_t M, cudaStream_t st) {
     if (M <= 0) return GCNN_OK;
     ProfScope prof(PROF_HEAD, 4.0 * (double)M * (D + 1), st);
-    head2_forward_kernel<<<(unsigned)ceil_div(M, 16), 256, 0, st>>>(g, w, b, scores, M);
+    GCNN_LAUNCH(head2_forward_kernel, (unsigned)ceil_div(M, 16), 256, 0, st, g, w, b, scores, M);
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
 }
@@ -417,6 +423,7 @@ int head2_forward(const float* g, const float* w, const float* b, float* scores,
 __global__ void __launch_bounds__(256)
 head2_backward_kernel(const float* __restrict__ g, const float* __restrict__ w, const float* __restrict__ ds,
                       float* __restrict__ dg_pre, float* __restrict__ partials, int64_t M) {
+    pdl_enter();
     __shared__ float red[4][D + 1];
     const int c = threadIdx.x & 63, r = threadIdx.x >> 6;
     const float wc = w[c];
@@ -440,7 +447,7 @@ int head2_backward(const float* g, const float* w, const float* d_scores, float*
     const int parts = (int)min((int64_t)WG_MAX_PARTS, ceil_div(M > 0 ? M : 1, 64));
     *n_parts = parts;
     ProfScope prof(PROF_HEAD, 4.0 * (double)M * (2 * D + 1), st);
-    head2_backward_kernel<<<parts, 256, 0, st>>>(g, w, d_scores, dg_pre, partials, M);
+    GCNN_LAUNCH(head2_backward_kernel, parts, 256, 0, st, g, w, d_scores, dg_pre, partials, M);
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
 }
@@ -454,6 +461,7 @@ struct ReduceJobs { ReduceJob j[MAX_JOBS]; int n; };
 // outputs; lane l sums partials l, l + L, l + 2L, ... and the lanes are combined in lane order -> still a fixed order.
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const __grid_constant__ ReduceJobs jobs, float* __restrict__ grads) {
+    pdl_enter();
     __shared__ float red[256];
     const ReduceJob& job = jobs.j[blockIdx.y];
     const int width = job.count <= 64 ? 64 : (job.count <= 128 ? 128 : 256);  // outputs per CTA
@@ -502,7 +510,7 @@ int reduce_partials(const ReduceJob* jobs, int n_jobs, float* grads, cudaStream_
     js.n = n_jobs;
     for (int i = 0; i < n_jobs; ++i) js.j[i] = jobs[i];
     dim3 grid((unsigned)max_ctas, n_jobs);
-    reduce_partials_kernel<<<grid, 256, 0, st>>>(js, grads);
+    GCNN_LAUNCH(reduce_partials_kernel, grid, 256, 0, st, js, grads);
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
 }
@@ -511,6 +519,7 @@ int reduce_partials(const ReduceJob* jobs, int n_jobs, float* grads, cudaStream_
 __global__ void __launch_bounds__(1024)
 mse_seed_kernel(const float* __restrict__ scores, const float* __restrict__ targets, int64_t n, float scale,
                 float* __restrict__ d_scores, float* __restrict__ loss_sum) {
+    pdl_enter();
     __shared__ float red[32];
     float s = 0.f;
     for (int64_t i = threadIdx.x; i < n; i += 1024) {
@@ -533,7 +542,7 @@ mse_seed_kernel(const float* __restrict__ scores, const float* __restrict__ targ
 int mse_seed(const float* scores, const float* targets, int64_t n, float scale, float* d_scores, float* loss_sum,
              cudaStream_t st) {
     ProfScope prof(PROF_LOSS, 12.0 * (double)n, st);
-    mse_seed_kernel<<<1, 1024, 0, st>>>(scores, targets, n, scale, d_scores, loss_sum);
+    GCNN_LAUNCH(mse_seed_kernel, 1, 1024, 0, st, scores, targets, n, scale, d_scores, loss_sum);
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
 }
@@ -541,6 +550,7 @@ int mse_seed(const float* scores, const float* targets, int64_t n, float scale, 
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             int64_t n, float lr_t, float b1, float b2, float eps, const float* __restrict__ divisor) {
+    pdl_enter();
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
     float gi = g[i];
@@ -555,7 +565,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 int adam_step(float* params, const float* grads, float* m, float* v, int64_t n, float lr_t, float beta1, float beta2,
               float eps, const float* grad_divisor, cudaStream_t st) {
     ProfScope prof(PROF_ADAM, 28.0 * (double)n, st);
-    adam_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(params, grads, m, v, n, lr_t, beta1, beta2, eps,
+    GCNN_LAUNCH(adam_kernel, (unsigned)ceil_div(n, 256), 256, 0, st, params, grads, m, v, n, lr_t, beta1, beta2, eps,
                                                             grad_divisor);
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;

@@ -135,6 +135,7 @@ __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
 // each 64 rows x 64 floats in the K-major SWIZZLE_128B shared-memory layout, so a CTA copies them linearly.
 __global__ void __launch_bounds__(256)
 pack_weights_kernel(const float* __restrict__ params, const int* __restrict__ block_offsets, float* __restrict__ images) {
+    pdl_enter();
     __shared__ float Wb[64][65];
     const float* W = params + block_offsets[blockIdx.x];
     float* img = images + (int64_t)blockIdx.x * 4 * IMG_FLOATS;
@@ -157,7 +158,7 @@ pack_weights_kernel(const float* __restrict__ params, const int* __restrict__ bl
 
 int pack_weights(const float* params, const int* block_offsets_dev, int n_blocks, float* images, cudaStream_t st) {
     ProfScope prof(PROF_PACK, 4.0 * 5 * IMG_FLOATS * n_blocks, st);
-    pack_weights_kernel<<<n_blocks, 256, 0, st>>>(params, block_offsets_dev, images);
+    GCNN_LAUNCH(pack_weights_kernel, n_blocks, 256, 0, st, params, block_offsets_dev, images);
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
 }
@@ -166,6 +167,7 @@ int pack_weights(const float* params, const int* block_offsets_dev, int n_blocks
 template <int K>
 __global__ void __launch_bounds__(TC_THREADS)
 tc_linear_kernel(const TcArgs a) {
+    pdl_enter();
     constexpr int KB = K / 32;                      // 32-float-wide K blocks
     constexpr uint32_t A_PART = KB * A_BLOCK_BYTES; // hi or lo part of the A tile
     constexpr uint32_t B_PART = KB * B_BLOCK_BYTES;
@@ -363,6 +365,7 @@ __device__ __forceinline__ void issue_stage(uint32_t tmem_d, const uint32_t (&a_
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_conv_forward_kernel(const ConvFwdArgs a) {
+    pdl_enter();
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t mma_bar;
     __shared__ uint32_t tmem_slot;
@@ -482,7 +485,7 @@ int tc_conv_forward(const ConvFwdArgs& a, cudaStream_t st) {
     const size_t smem = 2 * REG_BYTES + 3 * IMG_BYTES + 1024;
     static int once = set_smem_tc(tc_conv_forward_kernel, smem);
     GCNN_TRY(once);
-    tc_conv_forward_kernel<<<(unsigned)ceil_div(a.M, TC_ROWS), TC_THREADS, smem, st>>>(a);
+    GCNN_LAUNCH(tc_conv_forward_kernel, (unsigned)ceil_div(a.M, TC_ROWS), TC_THREADS, smem, st, a);
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
 }
@@ -516,6 +519,7 @@ constexpr uint32_t IDESC_TF32_MN_128x64 = IDESC_TF32_128x64 | (1u << 15) | (1u <
 template <int K>
 __global__ void __launch_bounds__(TC_THREADS)
 tc_wgrad_kernel(const TcWgradArgs a) {
+    pdl_enter();
     constexpr int KB = K / 32;
     constexpr uint32_t A_PART = KB * A_BLOCK_BYTES, B_PART = 2 * A_BLOCK_BYTES;
     constexpr int NA = TC_ROWS * (K / 4) / TC_THREADS;  // float4 loads of X per thread per tile (8 or 16)
@@ -663,12 +667,12 @@ int tc_linear(const TcArgs& a, int prof_class, double prof_bytes, cudaStream_t s
         const size_t smem = 2 * 2 * A_BLOCK_BYTES + 2 * 2 * B_BLOCK_BYTES + 1024;
         static int once = set_smem_tc(tc_linear_kernel<64>, smem);
         GCNN_TRY(once);
-        tc_linear_kernel<64><<<grid, TC_THREADS, smem, st>>>(a);
+        GCNN_LAUNCH(tc_linear_kernel<64>, grid, TC_THREADS, smem, st, a);
     } else if (a.K == 128) {
         const size_t smem = 2 * 4 * A_BLOCK_BYTES + 2 * 4 * B_BLOCK_BYTES + 1024;
         static int once = set_smem_tc(tc_linear_kernel<128>, smem);
         GCNN_TRY(once);
-        tc_linear_kernel<128><<<grid, TC_THREADS, smem, st>>>(a);
+        GCNN_LAUNCH(tc_linear_kernel<128>, grid, TC_THREADS, smem, st, a);
     } else {
         set_error("tc_linear: K must be 64 or 128");
         return GCNN_INVALID;
@@ -685,12 +689,12 @@ int tc_wgrad(const TcWgradArgs& a, cudaStream_t st) {
         const size_t smem = 8 * A_BLOCK_BYTES + 1024;
         static int once = set_smem_tc(tc_wgrad_kernel<64>, smem);
         GCNN_TRY(once);
-        tc_wgrad_kernel<64><<<parts, TC_THREADS, smem, st>>>(a);
+        GCNN_LAUNCH(tc_wgrad_kernel<64>, parts, TC_THREADS, smem, st, a);
     } else if (a.K == 128) {
         const size_t smem = 12 * A_BLOCK_BYTES + 1024;
         static int once = set_smem_tc(tc_wgrad_kernel<128>, smem);
         GCNN_TRY(once);
-        tc_wgrad_kernel<128><<<parts, TC_THREADS, smem, st>>>(a);
+        GCNN_LAUNCH(tc_wgrad_kernel<128>, parts, TC_THREADS, smem, st, a);
     } else {
         set_error("tc_wgrad: K must be 64 or 128");
         return GCNN_INVALID;
