@@ -92,6 +92,9 @@ struct gcnn_workspace {
     float *dk1, *dv1, *dc1, *dk0, *dv0, *dc0, *t_dU1, *t_dC, *t_G, *t_dR, *t_dS, *t_dh1, *t_dg;
     float* partials[32];
     float* dw_partials[3];
+    // fused backward chains: per-convolution G, dR (receiving-side projection gradient), dS (sending side), partials
+    float *bG[3], *bdR[3], *bdS[3], *chain_partials[3];
+    int use_fused_bwd = 1;
     // stats
     double *st_partials, *st_out, *st_center;
     // host staging mirrors (device side)
@@ -221,6 +224,11 @@ static size_t carve(gcnn_workspace* ws, char* base, const Caps& c) {
         const int64_t parts = wgrad_max_parts();
         for (int i = 0; i < 32; ++i) ws->partials[i] = cv.take<float>(parts * (2 * D * D + D));
         for (int i = 0; i < 3; ++i) ws->dw_partials[i] = cv.take<float>((int64_t)edge_backward_max_partials() * D);
+        const int64_t n_send[3] = {nv, nc, nv};
+        for (int i = 0; i < 3; ++i) {
+            ws->bG[i] = rows(n_recv[i]); ws->bdR[i] = rows(n_recv[i]); ws->bdS[i] = rows(n_send[i]);
+            ws->chain_partials[i] = cv.take<float>((int64_t)NUM_SMS * conv_backward_part_floats());
+        }
     }
     return cv.off + 256;
 }
@@ -481,8 +489,12 @@ static int forward_impl(gcnn_workspace* ws, const float* p, const float* pn, con
 }
 
 // ---- backward ----------------------------------------------------------------------------------------------------
+static int backward_impl_fused(gcnn_workspace* ws, const float* p, const float* pn, const gcnn_batch* b,
+                               const float* d_scores, float* grads, cudaStream_t st);
+
 static int backward_impl(gcnn_workspace* ws, const float* p, const float* pn, const gcnn_batch* b,
                          const float* d_scores, float* grads, cudaStream_t st) {
+    if (ws->use_tc && ws->use_fused && ws->use_fused_bwd) return backward_impl_fused(ws, p, pn, b, d_scores, grads, st);
     const int64_t nc = b->n_cons, nv = b->n_vars, nk = b->n_cuts;
     std::vector<ReduceJob> jobs;
     int slot = 0;
@@ -627,6 +639,109 @@ static int backward_impl(gcnn_workspace* ws, const float* p, const float* pn, co
     return reduce_partials(jobs.data(), (int)jobs.size(), grads, st);
 }
 
+// ---- backward with one fused tensor-core chain per convolution (node_bwd.cu) ----------------------------------------
+// Critical path: head -> [chain i -> edge backward i] for i = 2, 1, 0 -> embeddings.  The chain of convolution i starts
+// with the input gradient of the layer that consumed Y_i (head layer 1, conv 2's right projection, conv 1's left
+// projection), so the only stand-alone dense launches left are the projections of the EMBEDDING outputs.
+static int backward_impl_fused(gcnn_workspace* ws, const float* p, const float* pn, const gcnn_batch* b,
+                               const float* d_scores, float* grads, cudaStream_t st) {
+    const int64_t nc = b->n_cons, nv = b->n_vars, nk = b->n_cuts;
+    std::vector<ReduceJob> jobs;
+    int slot = 0, n_parts = 0;
+    auto add_job = [&](const float* part, int n, int stride, int count, int dst) {
+        jobs.push_back(ReduceJob{part, n, stride, count, dst, nullptr});
+    };
+    auto img16 = [&](int param_off) -> const void* {
+        return ws->tc_images + (int64_t)tc_block_index(param_off) * TC_IMG_FLOATS + TC_IMG_TF32_FLOATS;
+    };
+    cudaStream_t s2 = aux_stream(ws, 1, st);
+
+    GCNN_TRY(head2_backward(ws->g1, p + P.Wh2, d_scores, ws->t_dg, ws->partials[slot], &n_parts, nk, st));
+    add_job(ws->partials[slot++], n_parts, D + 1, D + 1, P.Wh2);
+
+    const float* left_in[3] = {ws->c0, ws->conv[0].Y, ws->k0};
+    const float* var_in[3] = {ws->v0, ws->v0, ws->conv[1].Y};
+    const float* recv_in[3] = {ws->c0, ws->v0, ws->k0};
+    float* d_recv_in[3] = {ws->dc0, ws->dv0, ws->dk0};
+    const int64_t n_left[3] = {nc, nc, nk}, n_recv[3] = {nc, nv, nk}, n_send[3] = {nv, nc, nv};
+    const int recv_is_left[3] = {1, 0, 1}, graph_of[3] = {0, 0, 1};
+    const int fshift[3] = {PN.cedge_shift, PN.cedge_shift, PN.kedge_shift};
+    const int fscale[3] = {PN.cedge_scale, PN.cedge_scale, PN.kedge_scale};
+    // the layer that consumed Y_i: its weight block, whether it has a bias, and the gradient of its pre-activation
+    const int next_w[3] = {P.conv[1].Wl, P.conv[2].Wr, P.Wh1};
+    const int next_has_bias[3] = {1, 0, 1};
+    const float* next_dP[3] = {ws->bdS[1], ws->bdS[2], ws->t_dg};
+    const int PART = conv_backward_part_floats();
+
+    for (int i = 2; i >= 0; --i) {
+        const ConvOff& o = P.conv[i];
+        ConvActs& a = ws->conv[i];
+        const EdgeLayout& Lr = recv_is_left[i] ? ws->graph[graph_of[i]].by_left : ws->graph[graph_of[i]].by_var;
+        const EdgeLayout& Ls = recv_is_left[i] ? ws->graph[graph_of[i]].by_var : ws->graph[graph_of[i]].by_left;
+        ConvBwdArgs c{};
+        c.dP = next_dP[i]; c.Y = a.Y; c.U1 = a.U1; c.C = a.C; c.Xt = recv_in[i]; c.H = a.H; c.cnt = a.cnt;
+        c.deg_ptr = Lr.ptr; c.s_p = pn + PN.conv_sp[i]; c.s_f = pn + PN.conv_sf[i];
+        c.img_n = img16(next_w[i]); c.img_o2 = img16(o.Wo2); c.img_o1a = img16(o.Wo1); c.img_o1b = img16(o.Wo1 + D * D);
+        c.img_f = img16(o.Wf);
+        c.dXt = d_recv_in[i]; c.G = ws->bG[i]; c.dR = ws->bdR[i]; c.partials = ws->chain_partials[i]; c.M = n_recv[i];
+        GCNN_TRY(tc_conv_backward(c, &n_parts, st));
+        if (n_parts > 0) {
+            const float* cp = ws->chain_partials[i];
+            add_job(cp, n_parts, PART, D * D + (next_has_bias[i] ? D : 0), next_w[i]);
+            add_job(cp + (D * D + D), n_parts, PART, D * D + D, o.Wo2);
+            add_job(cp + 2 * (D * D + D), n_parts, PART, 2 * D * D + D, o.Wo1);
+            add_job(cp + 2 * (D * D + D) + 2 * D * D + D, n_parts, PART, D * D + D, o.Wf);
+        }
+        // edge backward over the transposed layout: dS = gradient of the sending side's projection
+        const float* R = recv_is_left[i] ? a.A : a.B;
+        const float* S = recv_is_left[i] ? a.B : a.A;
+        EdgeScalars sc{pn + fshift[i], pn + fscale[i], pn + PN.conv_sf[i]};
+        int n_dw = 0;
+        const int64_t E_i = graph_of[i] == 0 ? b->n_cons_edges : b->n_cut_edges;
+        const double bwd_bytes = 256.0 * (double)(2 * n_recv[i] + 2 * n_send[i]) + 8.0 * (double)E_i + 4.0 * (double)(n_send[i] + 1);
+        GCNN_TRY(edge_backward(Ls, n_send[i], R, S, ws->bG[i], p + o.we, sc, ws->bdS[i], ws->dw_partials[i], &n_dw, st,
+                               bwd_bytes, E_i));
+        add_job(ws->dw_partials[i], n_dw, D, D, o.we);
+    }
+
+    // projections of the embedding outputs: conv 2 left (k0), conv 1 right (v0), conv 0 left (c0) and right (v0)
+    struct Proj { const float* x; const float* dP; int W; int has_bias; float* dX; int64_t n; };
+    const Proj proj[4] = {{ws->k0, ws->bdR[2], P.conv[2].Wl, 1, ws->dk0, nk},
+                          {ws->v0, ws->bdR[1], P.conv[1].Wr, 0, ws->dv0, nv},
+                          {ws->c0, ws->bdR[0], P.conv[0].Wl, 1, ws->dc0, nc},
+                          {ws->v0, ws->bdS[0], P.conv[0].Wr, 0, ws->dv0, nv}};
+    (void)left_in; (void)var_in; (void)n_left;
+    GCNN_TRY(stream_edge(ws, st, s2));
+    for (int j = 0; j < 4; ++j) {
+        const Proj& pr = proj[j];
+        LinWgradArgs w{pr.x, nullptr, nullptr, pr.dP, nullptr, nullptr, 64, pr.n, pr.has_bias, ws->partials[slot], &n_parts};
+        GCNN_TRY(dense_wgrad(ws, w, s2));
+        add_job(ws->partials[slot++], n_parts, D * D + D, D * D + (pr.has_bias ? D : 0), pr.W);
+        LinDgradArgs d{pr.dP, nullptr, p + pr.W, 64, pr.dX, nullptr, 1, nullptr, 0, nullptr, nullptr, nullptr, pr.n};
+        GCNN_TRY(dense_dgrad(ws, p, d, st));
+    }
+
+    struct { const float* x; int K; int shift, scale; const EmbOff* o; float *h1, *out, *dout; int64_t n; } emb[3] = {
+        {b->cons_feats, GCNN_CONS_FEATS, PN.cons_shift, PN.cons_scale, &P.cons, ws->h1c, ws->c0, ws->dc0, nc},
+        {b->var_feats, GCNN_VAR_FEATS, PN.var_shift, PN.var_scale, &P.var, ws->h1v, ws->v0, ws->dv0, nv},
+        {b->cut_feats, GCNN_CUT_FEATS, PN.cut_shift, PN.cut_scale, &P.cut, ws->h1k, ws->k0, ws->dk0, nk}};
+    GCNN_TRY(stream_edge(ws, st, s2));
+    for (int e_i = 0; e_i < 3; ++e_i) {
+        auto& e = emb[e_i];
+        cudaStream_t se = e_i == 1 ? s2 : st;
+        float* dh1 = e_i == 1 ? ws->t_dh1b : ws->t_dh1;
+        LinWgradArgs w{e.h1, nullptr, nullptr, e.dout, e.out, nullptr, 64, e.n, 1, ws->partials[slot], &n_parts};
+        GCNN_TRY(dense_wgrad(ws, w, s2));
+        add_job(ws->partials[slot++], n_parts, D * D + D, D * D + D, e.o->W2);
+        LinDgradArgs d{e.dout, e.out, p + e.o->W2, 64, dh1, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, e.n};
+        GCNN_TRY(dense_dgrad(ws, p, d, se));
+        GCNN_TRY(embed1_wgrad(e.x, e.K, pn + e.shift, pn + e.scale, dh1, e.h1, e.n, ws->partials[slot], &n_parts, se));
+        add_job(ws->partials[slot++], n_parts, (e.K + 1) * D, (e.K + 1) * D, e.o->W1);
+    }
+    GCNN_TRY(stream_edge(ws, s2, st));
+    return reduce_partials(jobs.data(), (int)jobs.size(), grads, st);
+}
+
 static int h2d(void* dst, const void* src, size_t bytes, cudaStream_t st) {
     if (bytes == 0) return GCNN_OK;
     GCNN_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
@@ -698,7 +813,7 @@ const char* gcnn_profile_class_name(int c) {
     static const char* names[PROF_NCLASSES] = {"csr_build", "embed1_forward", "linear_forward", "edge_forward", "head2",
                                                "linear_dgrad", "linear_wgrad", "embed1_wgrad", "edge_backward",
                                                "reduce_partials", "mse_seed", "adam", "prenorm_stats",
-                                               "pack_weights"};
+                                               "pack_weights", "conv_backward_chain"};
     return (c >= 0 && c < PROF_NCLASSES) ? names[c] : "";
 }
 int gcnn_profile_num_classes(void) { return PROF_NCLASSES; }
@@ -763,6 +878,8 @@ int gcnn_workspace_create(gcnn_workspace** out) {
     ws->use_tiles = ti && ti[0] == '1';
     const char* fu = getenv("GCNN_FUSED");  // GCNN_FUSED=0: one launch per dense layer
     ws->use_fused = !(fu && fu[0] == '0');
+    const char* fb = getenv("GCNN_FUSED_BWD");  // GCNN_FUSED_BWD=0: stand-alone dgrad / wgrad launches in the backward
+    ws->use_fused_bwd = !(fb && fb[0] == '0');
     for (int i = 0; i < 2; ++i) GCNN_CUDA_TRY(cudaStreamCreateWithFlags(&ws->aux[i], cudaStreamNonBlocking));
     for (int i = 0; i < 16; ++i) GCNN_CUDA_TRY(cudaEventCreateWithFlags(&ws->ev[i], cudaEventDisableTiming));
     for (int i = 0; i < 4; ++i) GCNN_CUDA_TRY(cudaEventCreateWithFlags(&ws->ev_layout[i], cudaEventDisableTiming));
@@ -816,6 +933,7 @@ int gcnn_set_option(gcnn_workspace* ws, const char* name, int value) {
     else if (!strcmp(name, "streams")) ws->use_streams = value != 0;
     else if (!strcmp(name, "fused")) ws->use_fused = value != 0;
     else if (!strcmp(name, "tiles")) ws->use_tiles = value != 0;
+    else if (!strcmp(name, "fused_backward")) ws->use_fused_bwd = value != 0;
     else { set_error("unknown option %s", name); return GCNN_INVALID; }
     return GCNN_OK;
 }

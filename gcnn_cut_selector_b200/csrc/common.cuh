@@ -17,7 +17,7 @@ void count_launch(int n = 1);
 // ---- optional per-kernel-class timing with CUDA events on the launching stream (bench.py roofline numbers) -------
 enum ProfClass {
     PROF_CSR = 0, PROF_EMB1_FWD, PROF_LIN_FWD, PROF_EDGE_FWD, PROF_HEAD, PROF_LIN_DGRAD, PROF_LIN_WGRAD,
-    PROF_EMB1_WGRAD, PROF_EDGE_BWD, PROF_REDUCE, PROF_LOSS, PROF_ADAM, PROF_STATS, PROF_PACK, PROF_NCLASSES
+    PROF_EMB1_WGRAD, PROF_EDGE_BWD, PROF_REDUCE, PROF_LOSS, PROF_ADAM, PROF_STATS, PROF_PACK, PROF_CONV_BWD, PROF_NCLASSES
 };
 struct ProfScope {  // records a start/stop event pair around the launches issued while it is alive (if enabled)
     ProfScope(int cls, double algorithmic_bytes, cudaStream_t st);
@@ -251,6 +251,18 @@ struct ConvFwdArgs {          // fused node chain of one convolution (tc_conv_fo
     int64_t M;
 };
 int tc_conv_forward(const ConvFwdArgs& a, cudaStream_t st);
+struct ConvBwdArgs {          // fused backward node chain of one convolution (tc_conv_backward, node_bwd.cu)
+    const float* dP;          // [M, 64] gradient w.r.t. the pre-activation of the layer that consumed Y
+    const float *Y, *U1, *C, *Xt, *H, *cnt;  // saved forward activations, [M, 64] each
+    const int32_t* deg_ptr;   // segment pointer of the receiving side (bias of Wf is weighted by the in-degree)
+    const float *s_p, *s_f;   // device scalars: post_conv and feature_module_final pre-norm scales
+    const void *img_n, *img_o2, *img_o1a, *img_o1b, *img_f;  // bf16x3 N images (24 KB each)
+    float *dXt, *G, *dR;      // outputs [M, 64]: gradient of the concat's right half, dC Wf^T, s_f G cnt
+    float* partials;          // [n_parts, conv_backward_part_floats()]: Wn | bn | Wo2 | bo2 | Wo1 | bo1 | Wf | bf
+    int64_t M;
+};
+int tc_conv_backward(const ConvBwdArgs& a, int* n_parts, cudaStream_t st);
+int conv_backward_part_floats();
 struct TcWgradArgs {
     const float* X;         // [M, 64] (left half when K = 128)
     const float* X2;        // right half (K = 128)
@@ -265,7 +277,9 @@ struct TcWgradArgs {
 };
 int tc_wgrad(const TcWgradArgs& a, cudaStream_t st);
 int pack_weights(const float* params, const int* block_offsets_dev, int n_blocks, float* images, cudaStream_t st);
-constexpr int TC_IMG_FLOATS = 4 * 64 * 64;  // T_hi, T_lo, N_hi, N_lo of one 64 x 64 weight block
+constexpr int TC_IMG_TF32_FLOATS = 4 * 64 * 64;  // T_hi, T_lo, N_hi, N_lo (3xTF32) of one 64 x 64 weight block
+constexpr int TC_IMG_BF16_FLOATS = 3 * 64 * 64 / 2;  // three bf16 pieces of the N image (bf16x3, backward chains): 24 KB
+constexpr int TC_IMG_FLOATS = TC_IMG_TF32_FLOATS + TC_IMG_BF16_FLOATS;
 
 // embedding layer 1: h = relu(((x + shift) * scale) W1 + b1), K in {4, 6, 14}
 int embed1_forward(const float* x, int K, const float* shift, const float* scale, const float* W, const float* b,

@@ -1,0 +1,436 @@
+// Fused backward node chains on the tensor cores (tcgen05, bf16x3 operands, TMEM accumulators).
+//
+// The adjoint of PartialGraphConvolution's node-level part (model.py:563, 570-573) -- hand-derived in SURVEY.md 8a --
+// for 128 receiving nodes per tile, input gradients AND weight gradients in one persistent kernel:
+//   S3: dU2 = (dP Wn^T) * 1[Y > 0]             dWn  += Y^T dP          (the layer that consumed Y: next projection / head)
+//   S2: dU1 = (dU2 Wo2^T) * 1[U1 > 0]          dWo2 += U1^T dU2
+//   S1: dcat = dU1 Wo1^T; dC = s_p dcat[:, :64]; dXt = dcat[:, 64:]     dWo1 += [s_p C, X_t]^T dU1
+//   S0: G = dC Wf^T; dR = s_f G * cnt          dWf  += H^T dC          (bias of Wf is weighted by the in-degree)
+// Every intermediate stays in shared memory as a bf16x3 tile (tc_common.cuh): the same image is the K-major A operand of
+// the next stage's input-gradient MMA and the MN-major B operand of this stage's weight-gradient MMA.  Weight gradients
+// accumulate in TMEM across all tiles of a CTA and leave as ONE partial per CTA (reduce_partials sums them in a fixed
+// order: deterministic, no atomics).  Weight images stream through three 24 KB slots by bulk async copies.
+//
+// Shared memory: three 48 KB tile buffers B0..B2 + three weight slots = 216 KB, one CTA per SM.  Buffer plan per tile:
+//   S3: B0 = dP, B1 = Y            -> dU2 to B2
+//   S2: B0 = U1                    -> dU1 to B1
+//   S1: B0 = s_p C, B2 = X_t       -> dC to B1 (after the weight-gradient MMAs have drained), B0 = H
+//   S0: reads B1, B0
+// Two mbarriers track the tensor core: `bar_d` (input-gradient MMAs of the stage, gates the epilogue) and `bar_w`
+// (weight-gradient MMAs, gates the overwrite of the tiles they read).
+#include "tc_common.cuh"
+
+namespace gcnn {
+
+constexpr uint32_t IDESC_BF16_KK = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t IDESC_BF16_MN = IDESC_BF16_KK | (1u << 15) | (1u << 16);  // A and B MN-major
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// MN-major SWIZZLE_128B descriptor for 16-bit operands: 64 elements (128 B) contiguous along M/N per line, 8 K-lines per
+// 1024-byte atom; leading byte offset = next 64-wide M/N block, stride byte offset = next 8-line K group.
+__device__ __forceinline__ uint64_t make_desc_mn16(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+    return d;
+}
+
+// The six bf16 products kept by the x3 split, (A piece, B piece) = (2,0) (1,1) (0,2) (1,0) (0,1) (0,0): smallest terms
+// first; the dropped (1,2) (2,1) (2,2) terms are <= 2^-24 relative.
+
+// D[128 x 64] (+)= G[128 x 64] * Wimg^T: A = bf16x3 tile (K-major), B = bf16x3 N image of a 64 x 64 weight block
+__device__ __forceinline__ void issue_dgrad(uint32_t tmem_d, uint32_t a_tile, uint32_t w_img, uint32_t acc) {
+#pragma unroll
+    for (int p = 0; p < 6; ++p) {
+        const int pa = p == 0 ? 2 : (p == 1 || p == 3) ? 1 : 0;
+        const int pb = p == 0 ? 0 : p == 1 ? 1 : p == 2 ? 2 : p == 3 ? 0 : p == 4 ? 1 : 0;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            umma_bf16(tmem_d, make_desc(a_tile + pa * T16_PIECE + ks * 32), make_desc(w_img + pb * W16_PIECE + ks * 32),
+                      IDESC_BF16_KK, acc);
+            acc = 1;
+        }
+    }
+}
+
+// dW[f][c] (+)= sum over the 128 lines of act[line][f] * g[line][c]: both operands MN-major views of bf16x3 tiles, the
+// reduction (K) runs over lines, 16 per instruction.  The M = 128 instruction reads a second 64-feature block `lbo` bytes
+// after the first (the right half of the concat, or don't-care data whose result rows 64..127 are never read).
+__device__ __forceinline__ void issue_wgrad(uint32_t tmem_d, uint32_t act_tile, uint32_t lbo, uint32_t g_tile,
+                                            uint32_t acc) {
+#pragma unroll
+    for (int p = 0; p < 6; ++p) {
+        const int pa = p == 0 ? 2 : (p == 1 || p == 3) ? 1 : 0;
+        const int pb = p == 0 ? 0 : p == 1 ? 1 : p == 2 ? 2 : p == 3 ? 0 : p == 4 ? 1 : 0;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            umma_bf16(tmem_d, make_desc_mn16(act_tile + pa * T16_PIECE + ks * 2048, lbo),
+                      make_desc_mn16(g_tile + pb * T16_PIECE + ks * 2048, T16_BYTES), IDESC_BF16_MN, acc);
+            acc = 1;
+        }
+    }
+}
+
+// ---- bulk async copy of one weight image (24 KB) into a slot, completion on an mbarrier ------------------------------
+__device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// ---- tile movement -------------------------------------------------------------------------------------------------
+// load mapping: item i = tid + 256 it covers line i >> 3, 8-float chunk i & 7 (a warp reads 1 KB of consecutive memory)
+__device__ __forceinline__ void load_tile(float4 (&reg)[8], const float* __restrict__ src, int64_t row0, int64_t M,
+                                          int tid) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int i = tid + it * TC_THREADS;
+        const int64_t m = row0 + (i >> 3);
+        reg[2 * it] = reg[2 * it + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < M) {
+            const float* p = src + m * D + (i & 7) * 8;
+            reg[2 * it] = ldg_stream4(p);
+            reg[2 * it + 1] = ldg_stream4(p + 4);
+        }
+    }
+}
+__device__ __forceinline__ void store_tile(uint8_t* tile, const float4 (&reg)[8], float scale, int tid) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int i = tid + it * TC_THREADS;
+        const float4 x = reg[2 * it], y = reg[2 * it + 1];
+        const float v[8] = {x.x * scale, x.y * scale, x.z * scale, x.w * scale,
+                            y.x * scale, y.y * scale, y.z * scale, y.w * scale};
+        store_chunk3(tile, T16_PIECE, i >> 3, i & 7, v);
+    }
+}
+// epilogue mapping: a thread owns line `r`, columns [32 ch, 32 ch + 32)
+__device__ __forceinline__ void store_row32(uint8_t* tile, int r, int ch, const float (&v)[32]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float w[8] = {v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3],
+                            v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]};
+        store_chunk3(tile, T16_PIECE, r, ch * 4 + j, w);
+    }
+}
+// v *= 1[act > 0], the activation read back from the leading piece of its bf16x3 tile (a positive fp32 rounds to a
+// positive bf16: same exponent range)
+__device__ __forceinline__ void mask_row32(const uint8_t* act_tile, int r, int ch, float (&v)[32]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint4 q = *reinterpret_cast<const uint4*>(act_tile + t16_chunk_off(r, ch * 4 + j));
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int lo = (int)(int16_t)(w[k] & 0xFFFFu), hi = (int)(int16_t)(w[k] >> 16);
+            v[8 * j + 2 * k] = lo > 0 ? v[8 * j + 2 * k] : 0.f;
+            v[8 * j + 2 * k + 1] = hi > 0 ? v[8 * j + 2 * k + 1] : 0.f;
+        }
+    }
+}
+// Column sums over the 32 lanes of a warp by recursive halving: lane l returns sum over lanes of v[l].  Fixed order.
+__device__ __forceinline__ float warp_colsum32(const float (&v)[32], int lane) {
+    float t[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const bool up = (lane & 16) != 0;
+        const float keep = up ? v[i + 16] : v[i], send = up ? v[i] : v[i + 16];
+        t[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int s = 8; s >= 1; s >>= 1) {
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+            const bool up = (lane & s) != 0;
+            const float keep = up ? t[i + s] : t[i], send = up ? t[i] : t[i + s];
+            t[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    return t[0];
+}
+
+constexpr uint32_t CONV_BWD_SMEM = 3 * T16_BYTES + 3 * W16_BYTES + 1024;
+constexpr int CONV_BWD_PART = 3 * (D * D + D) + 2 * D * D + D;  // floats per CTA partial: Wn|bn|Wo2|bo2|Wo1|bo1|Wf|bf
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_conv_backward_kernel(const ConvBwdArgs a) {
+    pdl_enter();
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[5];  // 0: input-gradient MMAs, 1: weight-gradient MMAs, 2..4: weight slots
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+    uint8_t* const B0g = gen;
+    uint8_t* const B1g = gen + T16_BYTES;
+    uint8_t* const B2g = gen + 2 * T16_BYTES;
+    const uint32_t B0 = base, B1 = base + T16_BYTES, B2 = base + 2 * T16_BYTES;
+    const uint32_t W0 = base + 3 * T16_BYTES, W1 = W0 + W16_BYTES, W2 = W1 + W16_BYTES;
+    const uint32_t bar_d = smem_u32(&bars[0]), bar_w = smem_u32(&bars[1]);
+    const uint32_t wbar0 = smem_u32(&bars[2]), wbar1 = smem_u32(&bars[3]), wbar2 = smem_u32(&bars[4]);
+
+    if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), 512);
+    if (tid == 0) {
+        for (int i = 0; i < 5; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tm = tmem_slot;
+    const uint32_t accA = tm, accB = tm + 64, acc_wn = tm + 128, acc_wo2 = tm + 192, acc_wo1 = tm + 256, acc_wf = tm + 320;
+
+    const int64_t n_tiles = ceil_div(a.M, TC_ROWS);
+    if (tid == 0) {
+        bulk_load(W0, a.img_n, W16_BYTES, wbar0);
+        bulk_load(W1, a.img_o2, W16_BYTES, wbar1);
+        bulk_load(W2, a.img_o1a, W16_BYTES, wbar2);
+    }
+    const float s_p = *a.s_p, s_f = *a.s_f;
+    const int q = warp & 3, ch = warp >> 2;
+    const int r_own = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+
+    float4 ra[8], rb[8];            // register staging of the next activation tiles (load mapping)
+    float bsum_p[8] = {};           // column sums of dP (load mapping: columns 8 (tid & 7) .. +8)
+    float bacc[3] = {0.f, 0.f, 0.f};  // column sums of dU2, dU1, deg * dC (epilogue mapping: column 32 ch + lane)
+    uint32_t ph_d = 0, ph_w = 0;
+    int iter = 0;
+
+    load_tile(ra, a.dP, (int64_t)blockIdx.x * TC_ROWS, a.M, tid);
+    load_tile(rb, a.Y, (int64_t)blockIdx.x * TC_ROWS, a.M, tid);
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
+        const int64_t row0 = tile * TC_ROWS;
+        const int64_t m_own = row0 + r_own;
+        const bool row_ok = m_own < a.M;
+        const bool has_next = tile + gridDim.x < n_tiles;
+        const uint32_t wacc = iter > 0 ? 1u : 0u;
+
+        // ---------------- S3: through the layer that consumed Y ----------------
+        if (iter > 0) { mbar_wait(bar_w, ph_w); ph_w ^= 1; }  // S0 of the previous tile has drained: B0, B1 are free
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const float4 x = ra[2 * it], y = ra[2 * it + 1];
+            bsum_p[0] += x.x; bsum_p[1] += x.y; bsum_p[2] += x.z; bsum_p[3] += x.w;
+            bsum_p[4] += y.x; bsum_p[5] += y.y; bsum_p[6] += y.z; bsum_p[7] += y.w;
+        }
+        store_tile(B0g, ra, 1.f, tid);
+        store_tile(B1g, rb, 1.f, tid);
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (tid == 0) {
+            mbar_wait(wbar0, 0);
+            issue_dgrad(accA, B0, W0, 0);
+            umma_commit(bar_d);
+            issue_wgrad(acc_wn, B1, T16_BYTES, B0, wacc);
+            umma_commit(bar_w);
+        }
+        load_tile(ra, a.U1, row0, a.M, tid);
+        mbar_wait(bar_d, ph_d); ph_d ^= 1;
+        tc_fence_after();
+        if (tid == 0) bulk_load(W0, a.img_o1b, W16_BYTES, wbar0);
+        {
+            float v[32];
+            tmem_ld32(accA + lane_off + (uint32_t)(ch * 32), v);
+            mask_row32(B1g, r_own, ch, v);
+            store_row32(B2g, r_own, ch, v);
+            bacc[0] += warp_colsum32(v, lane);
+        }
+
+        // ---------------- S2: output layer 2 ----------------
+        mbar_wait(bar_w, ph_w); ph_w ^= 1;  // B0 (dP) and B1 (Y) are free
+        store_tile(B0g, ra, 1.f, tid);
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (tid == 0) {
+            mbar_wait(wbar1, 0);
+            issue_dgrad(accA, B2, W1, 0);
+            umma_commit(bar_d);
+            issue_wgrad(acc_wo2, B0, T16_BYTES, B2, wacc);
+            umma_commit(bar_w);
+        }
+        load_tile(ra, a.C, row0, a.M, tid);
+        load_tile(rb, a.Xt, row0, a.M, tid);
+        mbar_wait(bar_d, ph_d); ph_d ^= 1;
+        tc_fence_after();
+        if (tid == 0) bulk_load(W1, a.img_f, W16_BYTES, wbar1);
+        {
+            float v[32];
+            tmem_ld32(accA + lane_off + (uint32_t)(ch * 32), v);
+            mask_row32(B0g, r_own, ch, v);
+            store_row32(B1g, r_own, ch, v);
+            bacc[1] += warp_colsum32(v, lane);
+        }
+
+        // ---------------- S1: output layer 1 over the concat [s_p C, X_t] ----------------
+        mbar_wait(bar_w, ph_w); ph_w ^= 1;  // the tensor core is done with B0 (U1) and B2 (dU2) ...
+        __syncthreads();                    // ... and so are the S2 epilogues of the other warps (ReLU mask read from B0)
+        store_tile(B0g, ra, s_p, tid);
+        store_tile(B2g, rb, 1.f, tid);
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (tid == 0) {
+            mbar_wait(wbar2, (uint32_t)(iter & 1));
+            mbar_wait(wbar0, 1);
+            issue_dgrad(accA, B1, W2, 0);
+            issue_dgrad(accB, B1, W0, 0);
+            umma_commit(bar_d);
+            issue_wgrad(acc_wo1, B0, 2 * T16_BYTES, B1, wacc);
+            umma_commit(bar_w);
+        }
+        load_tile(ra, a.H, row0, a.M, tid);
+        float4 cn[8];
+        float deg = 0.f;
+        if (row_ok) {
+            deg = (float)(a.deg_ptr[m_own + 1] - a.deg_ptr[m_own]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cn[j] = ldg_stream4(a.cnt + m_own * D + ch * 32 + 4 * j);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cn[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        mbar_wait(bar_d, ph_d); ph_d ^= 1;
+        tc_fence_after();
+        if (tid == 0 && has_next) {
+            bulk_load(W0, a.img_n, W16_BYTES, wbar0);
+            bulk_load(W2, a.img_o1a, W16_BYTES, wbar2);
+        }
+        {
+            float v[32], x[32];
+            tmem_ld32(accB + lane_off + (uint32_t)(ch * 32), x);
+            if (row_ok) {
+                float* dst = a.dXt + m_own * D + ch * 32;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+            }
+            tmem_ld32(accA + lane_off + (uint32_t)(ch * 32), v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { v[i] *= s_p; x[i] = v[i] * deg; }
+            bacc[2] += warp_colsum32(x, lane);
+            mbar_wait(bar_w, ph_w); ph_w ^= 1;  // B0, B1, B2 are free
+            store_row32(B1g, r_own, ch, v);
+        }
+        store_tile(B0g, ra, 1.f, tid);
+
+        // ---------------- S0: hoisted feature_module_final ----------------
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (tid == 0) {
+            mbar_wait(wbar1, 1);
+            issue_dgrad(accA, B1, W1, 0);
+            umma_commit(bar_d);
+            issue_wgrad(acc_wf, B0, T16_BYTES, B1, wacc);
+            umma_commit(bar_w);
+        }
+        if (has_next) {
+            load_tile(ra, a.dP, row0 + (int64_t)gridDim.x * TC_ROWS, a.M, tid);
+            load_tile(rb, a.Y, row0 + (int64_t)gridDim.x * TC_ROWS, a.M, tid);
+        }
+        mbar_wait(bar_d, ph_d); ph_d ^= 1;
+        tc_fence_after();
+        if (tid == 0 && has_next) bulk_load(W1, a.img_o2, W16_BYTES, wbar1);
+        {
+            float v[32];
+            tmem_ld32(accA + lane_off + (uint32_t)(ch * 32), v);
+            if (row_ok) {
+                float* g = a.G + m_own * D + ch * 32;
+                float* dr = a.dR + m_own * D + ch * 32;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 y = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    *reinterpret_cast<float4*>(g + 4 * j) = y;
+                    *reinterpret_cast<float4*>(dr + 4 * j) =
+                        make_float4(s_f * y.x * cn[j].x, s_f * y.y * cn[j].y, s_f * y.z * cn[j].z, s_f * y.w * cn[j].w);
+                }
+            }
+        }
+    }
+
+    // ---------------- drain: weight-gradient accumulators and bias sums -> this CTA's partial ----------------
+    mbar_wait(bar_w, ph_w);
+    tc_fence_after();
+    float* part = a.partials + (int64_t)blockIdx.x * CONV_BWD_PART;
+    {
+        const uint32_t accs[4] = {acc_wn, acc_wo2, acc_wo1, acc_wf};
+        const int offs[4] = {0, D * D + D, 2 * (D * D + D), 2 * (D * D + D) + 2 * D * D + D};
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            if (w == 2 || q < 2) {  // 64-feature gradients live in TMEM lanes 0..63 (warp-uniform condition)
+                float v[32];
+                tmem_ld32(accs[w] + lane_off + (uint32_t)(ch * 32), v);
+                float* dst = part + offs[w] + (q * 32 + lane) * D + ch * 32;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+        }
+    }
+    // bias sums: the tile buffers are dead now, use B0 as scratch.  red_p[32 line groups][64], red_e[3][4 quadrants][64]
+    float* red_p = reinterpret_cast<float*>(B0g);
+    float* red_e = red_p + 32 * D;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red_p[(tid >> 3) * D + (tid & 7) * 8 + j] = bsum_p[j];
+#pragma unroll
+    for (int s = 0; s < 3; ++s) red_e[(s * 4 + q) * D + ch * 32 + lane] = bacc[s];
+    tc_fence_before();
+    __syncthreads();
+    if (tid < D) {
+        float t = 0.f;
+#pragma unroll
+        for (int g = 0; g < 32; ++g) t += red_p[g * D + tid];
+        part[D * D + tid] = t;
+    } else if (tid < 4 * D) {
+        const int s = (tid >> 6) - 1, c = tid & 63;
+        const float t = ((red_e[(s * 4 + 0) * D + c] + red_e[(s * 4 + 1) * D + c]) + red_e[(s * 4 + 2) * D + c]) +
+                        red_e[(s * 4 + 3) * D + c];
+        const int off = s == 0 ? (D * D + D) + D * D : s == 1 ? 2 * (D * D + D) + 2 * D * D : CONV_BWD_PART - D;
+        part[off + c] = t;
+    }
+    if (warp == 0) tmem_dealloc(tm, 512);
+}
+
+int conv_backward_part_floats() { return CONV_BWD_PART; }
+
+int tc_conv_backward(const ConvBwdArgs& a, int* n_parts, cudaStream_t st) {
+    *n_parts = 0;
+    if (a.M <= 0) return GCNN_OK;
+    const int parts = (int)min((int64_t)NUM_SMS, ceil_div(a.M, TC_ROWS));
+    *n_parts = parts;
+    // algorithmic bytes: read dP, Y, U1, C, X_t, H, cnt; write dXt, G, dR (one 256-byte row each per node); five weight
+    // images; one partial per CTA
+    ProfScope prof(PROF_CONV_BWD, 256.0 * 10.0 * (double)a.M + 5.0 * W16_BYTES + 4.0 * CONV_BWD_PART * parts, st);
+    static int once = [] {
+        cudaError_t e = cudaFuncSetAttribute(tc_conv_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)CONV_BWD_SMEM);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(tc_conv_backward_kernel): %s", cudaGetErrorString(e)); return (int)GCNN_CUDA_ERROR; }
+        return (int)GCNN_OK;
+    }();
+    GCNN_TRY(once);
+    GCNN_LAUNCH(tc_conv_backward_kernel, parts, TC_THREADS, CONV_BWD_SMEM, st, a);
+    GCNN_LAUNCH_CHECK();
+    return GCNN_OK;
+}
+
+}  // namespace gcnn

@@ -11,122 +11,10 @@
 // pre-packed weight image in the same layout (pack_weights_kernel, once per step).  One elected thread issues the MMAs
 // (UMMA 128x64x8) and commits to an mbarrier; all 8 warps then read their TMEM quadrant with tcgen05.ld and run the
 // fused epilogue (bias / degree-scaled bias / ReLU / scale / accumulate / dR).
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace gcnn {
 
-constexpr int TC_THREADS = 256;
-constexpr int TC_ROWS = 128;
-constexpr uint32_t A_BLOCK_BYTES = TC_ROWS * 128;  // one 32-float-wide K block of the A tile
-constexpr uint32_t B_BLOCK_BYTES = 64 * 128;       // one 32-float-wide K block of a 64-row weight image
-constexpr int IMG_FLOATS = 64 * 64;                // one image part (hi or lo) of a 64 x 64 weight block
-
-// ---- PTX wrappers -------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(cols));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols));
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
-// streaming 16-byte load: activations are read once per kernel, keep them out of L1
-__device__ __forceinline__ float4 ldg_stream4(const float* p) {
-    float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-}
-
-// D[tmem] (+)= A[smem desc] * B[smem desc], tf32 inputs, fp32 accumulate, M = 128, N = 64, K = 8
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-// 32 lanes x 32 consecutive fp32 columns of TMEM -> 32 registers per thread
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// Shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row atoms 1024 B apart (cute::UMMA::SmemDescriptor).
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);  // start address, 16-byte units
-    d |= (uint64_t)1 << 16;                       // leading byte offset (unused for swizzled K-major), 16-byte units
-    d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset between 8-row groups
-    d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
-    return d;
-}
-// Instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B tf32, both K-major, N = 64, M = 128.
-constexpr uint32_t IDESC_TF32_128x64 = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-
-// Byte offset of the 16-byte chunk holding floats [k, k+4) of row r inside a K-major SWIZZLE_128B tile of `rows` rows.
-__device__ __forceinline__ uint32_t swz_chunk_off(int r, int k, int rows) {
-    const int kb = k >> 5, chunk = (k & 31) >> 2;
-    return (uint32_t)(kb * rows * 128 + (r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
-}
-
-// x = hi + lo + O(2^-24 |x|) with BOTH parts exactly representable in TF32.  The tensor core drops the low 13 mantissa
-// bits of its inputs by truncation; rounding the residual to nearest here (instead of letting the MMA truncate it)
-// keeps the 3xTF32 error unbiased, so it grows like sqrt(K) instead of K along the reduction.
-__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    uint32_t h, l;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-    hi = __uint_as_float(h);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(x - hi));
-    lo = __uint_as_float(l);
-}
-__device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
-    split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y);
-    split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
-}
 
 // ---- weight images --------------------------------------------------------------------------------------------------
 // For every 64 x 64 block Wb of a weight matrix (rows 64 j .. 64 j + 63 of a [K, 64] kernel) four images are written:
@@ -138,7 +26,7 @@ pack_weights_kernel(const float* __restrict__ params, const int* __restrict__ bl
     pdl_enter();
     __shared__ float Wb[64][65];
     const float* W = params + block_offsets[blockIdx.x];
-    float* img = images + (int64_t)blockIdx.x * 4 * IMG_FLOATS;
+    float* img = images + (int64_t)blockIdx.x * TC_IMG_FLOATS;
     for (int i = threadIdx.x; i < 64 * 64; i += 256) Wb[i >> 6][i & 63] = W[i];
     __syncthreads();
     for (int i = threadIdx.x; i < 64 * 16; i += 256) {
@@ -154,10 +42,20 @@ pack_weights_kernel(const float* __restrict__ params, const int* __restrict__ bl
         *reinterpret_cast<float4*>(img + 2 * IMG_FLOATS + off) = hi;
         *reinterpret_cast<float4*>(img + 3 * IMG_FLOATS + off) = lo;
     }
+    // bf16x3 N image for the backward chains (node_bwd.cu): B[n][k] = Wb[n][k] as three bf16 pieces, 64 rows x 128 bytes
+    // each in the K-major SWIZZLE_128B layout (16-byte chunks of 8 bf16)
+    uint8_t* img16 = reinterpret_cast<uint8_t*>(img + TC_IMG_TF32_FLOATS);
+    for (int i = threadIdx.x; i < 64 * 8; i += 256) {
+        const int n = i >> 3, chunk = i & 7;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = Wb[n][chunk * 8 + j];
+        store_chunk3(img16, W16_PIECE, n, chunk, v);
+    }
 }
 
 int pack_weights(const float* params, const int* block_offsets_dev, int n_blocks, float* images, cudaStream_t st) {
-    ProfScope prof(PROF_PACK, 4.0 * 5 * IMG_FLOATS * n_blocks, st);
+    ProfScope prof(PROF_PACK, 4.0 * (IMG_FLOATS + TC_IMG_FLOATS) * n_blocks, st);
     GCNN_LAUNCH(pack_weights_kernel, n_blocks, 256, 0, st, params, block_offsets_dev, images);
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
