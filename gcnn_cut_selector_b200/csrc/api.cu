@@ -93,7 +93,7 @@ struct gcnn_workspace {
     float* partials[32];
     float* dw_partials[3];
     // fused backward chains: per-convolution G, dR (receiving-side projection gradient), dS (sending side), partials
-    float *bG[3], *bdR[3], *bdS[3], *chain_partials[3];
+    float *bG[3], *bdR[3], *bdS[3], *chain_partials[3], *emb_partials[3];
     int use_fused_bwd = 1;
     // stats
     double *st_partials, *st_out, *st_center;
@@ -228,6 +228,7 @@ static size_t carve(gcnn_workspace* ws, char* base, const Caps& c) {
         for (int i = 0; i < 3; ++i) {
             ws->bG[i] = rows(n_recv[i]); ws->bdR[i] = rows(n_recv[i]); ws->bdS[i] = rows(n_send[i]);
             ws->chain_partials[i] = cv.take<float>((int64_t)NUM_SMS * conv_backward_part_floats());
+            ws->emb_partials[i] = cv.take<float>((int64_t)NUM_SMS * embed_backward_part_floats());
         }
     }
     return cv.off + 256;
@@ -335,19 +336,7 @@ static int forward_convs_fused(gcnn_workspace* ws, const float* p, const float* 
     auto img_t = [&](int param_off) { return ws->tc_images + (int64_t)tc_block_index(param_off) * TC_IMG_FLOATS; };
     const bool keep = ws->cap.training != 0 || stop_layer >= 0;  // C / U1 are only read by the backward and by the statistics
 
-    GCNN_TRY(stream_edge(ws, st, s2));
-    {
-        LinFwdArgs a0{ws->c0, nullptr, nullptr, p + P.conv[0].Wl, p + P.conv[0].bl, nullptr, ws->conv[0].A, nc, 64, 0};
-        GCNN_TRY(dense_forward(ws, p, a0, st));
-        LinFwdArgs b0{ws->v0, nullptr, nullptr, p + P.conv[0].Wr, nullptr, nullptr, ws->conv[0].B, nv, 64, 0};
-        GCNN_TRY(dense_forward(ws, p, b0, s2));
-        LinFwdArgs b1{ws->v0, nullptr, nullptr, p + P.conv[1].Wr, nullptr, nullptr, ws->conv[1].B, nv, 64, 0};
-        GCNN_TRY(dense_forward(ws, p, b1, s2));
-        LinFwdArgs a2{ws->k0, nullptr, nullptr, p + P.conv[2].Wl, p + P.conv[2].bl, nullptr, ws->conv[2].A, nk, 64, 0};
-        GCNN_TRY(dense_forward(ws, p, a2, s2));
-    }
-    GCNN_TRY(stream_edge(ws, s2, st));
-
+    // (the projections A0, B0, B1, A2 were emitted by the embedding chains)
     const float* recv_in[3] = {ws->c0, ws->v0, ws->k0};
     const int64_t n_left[3] = {nc, nc, nk}, n_recv[3] = {nc, nv, nk};
     const int recv_is_left[3] = {1, 0, 1}, graph_of[3] = {0, 0, 1};
@@ -426,9 +415,23 @@ static int forward_impl(gcnn_workspace* ws, const float* p, const float* pn, con
         {b->var_feats, GCNN_VAR_FEATS, PN.var_shift, PN.var_scale, &P.var, ws->h1v, ws->v0, nv},
         {b->cut_feats, GCNN_CUT_FEATS, PN.cut_shift, PN.cut_scale, &P.cut, ws->h1k, ws->k0, nk}};
     GCNN_TRY(stream_edge(ws, st, s2));  // after pack_weights
+    const bool fused_fwd = ws->use_tc && ws->use_fused;
     for (int e_i = 0; e_i < 3; ++e_i) {
         auto& e = emb[e_i];
         cudaStream_t se = e_i == 1 ? s2 : st;
+        if (fused_fwd) {  // one chain per node type: both Dense layers + the projections that read the embedding
+            auto img_t = [&](int param_off) { return ws->tc_images + (int64_t)tc_block_index(param_off) * TC_IMG_FLOATS; };
+            EmbFwdArgs f{};
+            f.x = e.x; f.K = e.K; f.shift = pn + e.shift; f.scale = pn + e.scale; f.W1 = p + e.o->W1; f.b1 = p + e.o->b1;
+            f.img_w2 = img_t(e.o->W2); f.bias2 = p + e.o->b2; f.h1 = e.h1; f.out = e.out; f.M = e.n;
+            if (e_i == 0) { f.img_p[0] = img_t(P.conv[0].Wl); f.bias_p[0] = p + P.conv[0].bl; f.P[0] = ws->conv[0].A; }
+            else if (e_i == 1) {
+                f.img_p[0] = img_t(P.conv[0].Wr); f.P[0] = ws->conv[0].B;
+                f.img_p[1] = img_t(P.conv[1].Wr); f.P[1] = ws->conv[1].B;
+            } else { f.img_p[0] = img_t(P.conv[2].Wl); f.bias_p[0] = p + P.conv[2].bl; f.P[0] = ws->conv[2].A; }
+            GCNN_TRY(tc_embed_forward(f, se));
+            continue;
+        }
         GCNN_TRY(embed1_forward(e.x, e.K, pn + e.shift, pn + e.scale, p + e.o->W1, p + e.o->b1, e.h1, e.n, se));
         LinFwdArgs a{e.h1, nullptr, nullptr, p + e.o->W2, p + e.o->b2, nullptr, e.out, e.n, 64, 1};
         GCNN_TRY(dense_forward(ws, p, a, se));
@@ -659,11 +662,9 @@ static int backward_impl_fused(gcnn_workspace* ws, const float* p, const float* 
     GCNN_TRY(head2_backward(ws->g1, p + P.Wh2, d_scores, ws->t_dg, ws->partials[slot], &n_parts, nk, st));
     add_job(ws->partials[slot++], n_parts, D + 1, D + 1, P.Wh2);
 
-    const float* left_in[3] = {ws->c0, ws->conv[0].Y, ws->k0};
-    const float* var_in[3] = {ws->v0, ws->v0, ws->conv[1].Y};
     const float* recv_in[3] = {ws->c0, ws->v0, ws->k0};
     float* d_recv_in[3] = {ws->dc0, ws->dv0, ws->dk0};
-    const int64_t n_left[3] = {nc, nc, nk}, n_recv[3] = {nc, nv, nk}, n_send[3] = {nv, nc, nv};
+    const int64_t n_recv[3] = {nc, nv, nk}, n_send[3] = {nv, nc, nv};
     const int recv_is_left[3] = {1, 0, 1}, graph_of[3] = {0, 0, 1};
     const int fshift[3] = {PN.cedge_shift, PN.cedge_shift, PN.kedge_shift};
     const int fscale[3] = {PN.cedge_scale, PN.cedge_scale, PN.kedge_scale};
@@ -672,6 +673,38 @@ static int backward_impl_fused(gcnn_workspace* ws, const float* p, const float* 
     const int next_has_bias[3] = {1, 0, 1};
     const float* next_dP[3] = {ws->bdS[1], ws->bdS[2], ws->t_dg};
     const int PART = conv_backward_part_floats();
+
+    // one fused chain per embedding: gradients of the projections it feeds -> W2 -> W1 (node type e: 0 cons, 1 var, 2 cut)
+    auto embedding = [&](int e, cudaStream_t se) -> int {
+        EmbBwdArgs g{};
+        const EmbOff* eo = e == 0 ? &P.cons : (e == 1 ? &P.var : &P.cut);
+        int w0 = 0, w1 = -1, bias0 = 0;
+        if (e == 0) {        // c0 feeds conv 0's left projection (receiving side: dA0 = dR_0) and conv 0's concat
+            g.dP0 = ws->bdR[0]; g.dXt = ws->dc0; g.out = ws->c0; g.h1 = ws->h1c; g.x = b->cons_feats; g.K = GCNN_CONS_FEATS;
+            g.shift = pn + PN.cons_shift; g.scale = pn + PN.cons_scale; g.M = nc; w0 = P.conv[0].Wl; bias0 = 1;
+        } else if (e == 1) { // v0 feeds conv 0's right projection (dB0 = dS_0), conv 1's right projection (dB1 = dR_1), conv 1's concat
+            g.dP0 = ws->bdS[0]; g.dP1 = ws->bdR[1]; g.dXt = ws->dv0; g.out = ws->v0; g.h1 = ws->h1v; g.x = b->var_feats;
+            g.K = GCNN_VAR_FEATS; g.shift = pn + PN.var_shift; g.scale = pn + PN.var_scale; g.M = nv;
+            w0 = P.conv[0].Wr; w1 = P.conv[1].Wr;
+        } else {             // k0 feeds conv 2's left projection (dA2 = dR_2) and conv 2's concat
+            g.dP0 = ws->bdR[2]; g.dXt = ws->dk0; g.out = ws->k0; g.h1 = ws->h1k; g.x = b->cut_feats; g.K = GCNN_CUT_FEATS;
+            g.shift = pn + PN.cut_shift; g.scale = pn + PN.cut_scale; g.M = nk; w0 = P.conv[2].Wl; bias0 = 1;
+        }
+        g.img_p0 = img16(w0); g.img_p1 = w1 >= 0 ? img16(w1) : nullptr; g.img_w2 = img16(eo->W2);
+        g.partials = ws->emb_partials[e];
+        int np = 0;
+        GCNN_TRY(tc_embed_backward(g, &np, se));
+        if (np > 0) {
+            const int EP = embed_backward_part_floats();
+            const float* ep = ws->emb_partials[e];
+            add_job(ep, np, EP, D * D + (bias0 ? D : 0), w0);
+            if (w1 >= 0) add_job(ep + (D * D + D), np, EP, D * D, w1);
+            add_job(ep + 2 * (D * D + D), np, EP, D * D + D, eo->W2);
+            add_job(ep + 3 * (D * D + D), np, EP, g.K * D, eo->W1);
+            add_job(ep + 3 * (D * D + D) + D * D, np, EP, D, eo->b1);
+        }
+        return GCNN_OK;
+    };
 
     for (int i = 2; i >= 0; --i) {
         const ConvOff& o = P.conv[i];
@@ -692,6 +725,10 @@ static int backward_impl_fused(gcnn_workspace* ws, const float* p, const float* 
             add_job(cp + 2 * (D * D + D), n_parts, PART, 2 * D * D + D, o.Wo1);
             add_job(cp + 2 * (D * D + D) + 2 * D * D + D, n_parts, PART, D * D + D, o.Wf);
         }
+        if (i != 1) {  // the cut (after chain 2) and constraint (after chain 0) embeddings only wait for this chain
+            GCNN_TRY(stream_edge(ws, st, s2));
+            GCNN_TRY(embedding(i == 2 ? 2 : 0, s2));
+        }
         // edge backward over the transposed layout: dS = gradient of the sending side's projection
         const float* R = recv_is_left[i] ? a.A : a.B;
         const float* S = recv_is_left[i] ? a.B : a.A;
@@ -704,40 +741,7 @@ static int backward_impl_fused(gcnn_workspace* ws, const float* p, const float* 
         add_job(ws->dw_partials[i], n_dw, D, D, o.we);
     }
 
-    // projections of the embedding outputs: conv 2 left (k0), conv 1 right (v0), conv 0 left (c0) and right (v0)
-    struct Proj { const float* x; const float* dP; int W; int has_bias; float* dX; int64_t n; };
-    const Proj proj[4] = {{ws->k0, ws->bdR[2], P.conv[2].Wl, 1, ws->dk0, nk},
-                          {ws->v0, ws->bdR[1], P.conv[1].Wr, 0, ws->dv0, nv},
-                          {ws->c0, ws->bdR[0], P.conv[0].Wl, 1, ws->dc0, nc},
-                          {ws->v0, ws->bdS[0], P.conv[0].Wr, 0, ws->dv0, nv}};
-    (void)left_in; (void)var_in; (void)n_left;
-    GCNN_TRY(stream_edge(ws, st, s2));
-    for (int j = 0; j < 4; ++j) {
-        const Proj& pr = proj[j];
-        LinWgradArgs w{pr.x, nullptr, nullptr, pr.dP, nullptr, nullptr, 64, pr.n, pr.has_bias, ws->partials[slot], &n_parts};
-        GCNN_TRY(dense_wgrad(ws, w, s2));
-        add_job(ws->partials[slot++], n_parts, D * D + D, D * D + (pr.has_bias ? D : 0), pr.W);
-        LinDgradArgs d{pr.dP, nullptr, p + pr.W, 64, pr.dX, nullptr, 1, nullptr, 0, nullptr, nullptr, nullptr, pr.n};
-        GCNN_TRY(dense_dgrad(ws, p, d, st));
-    }
-
-    struct { const float* x; int K; int shift, scale; const EmbOff* o; float *h1, *out, *dout; int64_t n; } emb[3] = {
-        {b->cons_feats, GCNN_CONS_FEATS, PN.cons_shift, PN.cons_scale, &P.cons, ws->h1c, ws->c0, ws->dc0, nc},
-        {b->var_feats, GCNN_VAR_FEATS, PN.var_shift, PN.var_scale, &P.var, ws->h1v, ws->v0, ws->dv0, nv},
-        {b->cut_feats, GCNN_CUT_FEATS, PN.cut_shift, PN.cut_scale, &P.cut, ws->h1k, ws->k0, ws->dk0, nk}};
-    GCNN_TRY(stream_edge(ws, st, s2));
-    for (int e_i = 0; e_i < 3; ++e_i) {
-        auto& e = emb[e_i];
-        cudaStream_t se = e_i == 1 ? s2 : st;
-        float* dh1 = e_i == 1 ? ws->t_dh1b : ws->t_dh1;
-        LinWgradArgs w{e.h1, nullptr, nullptr, e.dout, e.out, nullptr, 64, e.n, 1, ws->partials[slot], &n_parts};
-        GCNN_TRY(dense_wgrad(ws, w, s2));
-        add_job(ws->partials[slot++], n_parts, D * D + D, D * D + D, e.o->W2);
-        LinDgradArgs d{e.dout, e.out, p + e.o->W2, 64, dh1, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, e.n};
-        GCNN_TRY(dense_dgrad(ws, p, d, se));
-        GCNN_TRY(embed1_wgrad(e.x, e.K, pn + e.shift, pn + e.scale, dh1, e.h1, e.n, ws->partials[slot], &n_parts, se));
-        add_job(ws->partials[slot++], n_parts, (e.K + 1) * D, (e.K + 1) * D, e.o->W1);
-    }
+    GCNN_TRY(embedding(1, st));
     GCNN_TRY(stream_edge(ws, s2, st));
     return reduce_partials(jobs.data(), (int)jobs.size(), grads, st);
 }
@@ -813,7 +817,7 @@ const char* gcnn_profile_class_name(int c) {
     static const char* names[PROF_NCLASSES] = {"csr_build", "embed1_forward", "linear_forward", "edge_forward", "head2",
                                                "linear_dgrad", "linear_wgrad", "embed1_wgrad", "edge_backward",
                                                "reduce_partials", "mse_seed", "adam", "prenorm_stats",
-                                               "pack_weights", "conv_backward_chain"};
+                                               "pack_weights", "conv_backward_chain", "embed_backward_chain"};
     return (c >= 0 && c < PROF_NCLASSES) ? names[c] : "";
 }
 int gcnn_profile_num_classes(void) { return PROF_NCLASSES; }

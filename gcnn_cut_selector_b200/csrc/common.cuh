@@ -17,7 +17,7 @@ void count_launch(int n = 1);
 // ---- optional per-kernel-class timing with CUDA events on the launching stream (bench.py roofline numbers) -------
 enum ProfClass {
     PROF_CSR = 0, PROF_EMB1_FWD, PROF_LIN_FWD, PROF_EDGE_FWD, PROF_HEAD, PROF_LIN_DGRAD, PROF_LIN_WGRAD,
-    PROF_EMB1_WGRAD, PROF_EDGE_BWD, PROF_REDUCE, PROF_LOSS, PROF_ADAM, PROF_STATS, PROF_PACK, PROF_CONV_BWD, PROF_NCLASSES
+    PROF_EMB1_WGRAD, PROF_EDGE_BWD, PROF_REDUCE, PROF_LOSS, PROF_ADAM, PROF_STATS, PROF_PACK, PROF_CONV_BWD, PROF_EMB_BWD, PROF_NCLASSES
 };
 struct ProfScope {  // records a start/stop event pair around the launches issued while it is alive (if enabled)
     ProfScope(int cls, double algorithmic_bytes, cudaStream_t st);
@@ -263,6 +263,32 @@ struct ConvBwdArgs {          // fused backward node chain of one convolution (t
 };
 int tc_conv_backward(const ConvBwdArgs& a, int* n_parts, cudaStream_t st);
 int conv_backward_part_floats();
+struct EmbFwdArgs {           // fused forward chain of one embedding (tc_embed_forward, node_tc.cu)
+    const float* x;           // [M, K] raw input features
+    int K;
+    const float *shift, *scale;  // input pre-norm (device, K floats each)
+    const float *W1, *b1;     // first Dense (fp32, [K, 64] and [64])
+    const float *img_w2, *bias2;       // second Dense: packed T image (3xTF32) and bias
+    const float* img_p[2];    // projection kernels fed by this embedding (img_p[1] may be nullptr)
+    const float* bias_p[2];   // their biases or nullptr
+    float *h1, *out, *P[2];   // outputs, [M, 64] each
+    int64_t M;
+};
+int tc_embed_forward(const EmbFwdArgs& a, cudaStream_t st);
+struct EmbBwdArgs {           // fused backward chain of one embedding (tc_embed_backward, node_bwd.cu)
+    const float* dP0;         // [M, 64] gradient of the first projection fed by this embedding
+    const float* dP1;         // second projection (variables feed two convolutions) or nullptr
+    const float* dXt;         // [M, 64] gradient from the concat branch that reads the embedding directly
+    const float *out, *h1;    // saved embedding output and hidden layer, [M, 64]
+    const float* x;           // [M, K] raw input features
+    const float *shift, *scale;  // input pre-norm (device, K floats each)
+    int K;
+    const void *img_p0, *img_p1, *img_w2;  // bf16x3 N images of the projection kernels and of W2
+    float* partials;          // [n_parts, embed_backward_part_floats()]: W_0 | b_0 | W_1 | b_1 | W2 | b2 | W1 (64 rows) | b1
+    int64_t M;
+};
+int tc_embed_backward(const EmbBwdArgs& a, int* n_parts, cudaStream_t st);
+int embed_backward_part_floats();
 struct TcWgradArgs {
     const float* X;         // [M, 64] (left half when K = 128)
     const float* X2;        // right half (K = 128)

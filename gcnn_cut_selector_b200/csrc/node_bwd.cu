@@ -433,4 +433,250 @@ int tc_conv_backward(const ConvBwdArgs& a, int* n_parts, cudaStream_t st) {
     return GCNN_OK;
 }
 
+// ---- fused backward chain of one embedding ---------------------------------------------------------------------------
+// The embedding out = relu(relu(xn W1 + b1) W2 + b2) (model.py:174-195) feeds one or two convolution projections
+// (P_j = out W_j [+ b_j]) and the right half of one concat.  One persistent kernel per node type:
+//   E0: dout = sum_j dP_j W_j^T + dXt;  g0 = dout * 1[out > 0]       dW_j += out^T dP_j
+//   E1: dh1 = (g0 W2^T) * 1[h1 > 0]                                   dW2  += h1^T g0
+//   E2:                                                               dW1  += xn^T dh1   (xn: K <= 14 features in a 64-wide tile)
+// Buffers: E0: B0 = dP_0, B1 = out, B2 = dP_1 -> g0 to B0;  E1: B2 = h1 -> dh1 to B1;  E2: B0 = xn.
+// The three weight images stay resident for the whole kernel.
+constexpr int EMB_BWD_PART = 4 * (D * D + D);  // W_0 | b_0 | W_1 | b_1 | W2 | b2 | W1 (64 rows, K valid) | b1
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_embed_backward_kernel(const EmbBwdArgs a) {
+    pdl_enter();
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[3];  // 0: input-gradient MMAs, 1: weight-gradient MMAs, 2: weight images
+    __shared__ uint32_t tmem_slot;
+    __shared__ float sh_shift[16], sh_scale[16];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+    uint8_t* const B0g = gen;
+    uint8_t* const B1g = gen + T16_BYTES;
+    uint8_t* const B2g = gen + 2 * T16_BYTES;
+    const uint32_t B0 = base, B1 = base + T16_BYTES, B2 = base + 2 * T16_BYTES;
+    const uint32_t W0 = base + 3 * T16_BYTES, W1 = W0 + W16_BYTES, W2 = W1 + W16_BYTES;
+    const uint32_t bar_d = smem_u32(&bars[0]), bar_w = smem_u32(&bars[1]), wbar = smem_u32(&bars[2]);
+    const bool two = a.dP1 != nullptr;
+    const int K = a.K;
+
+    if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), 512);
+    if (tid == 0) {
+        for (int i = 0; i < 3; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    }
+    if (tid < 16) {
+        sh_shift[tid] = tid < K ? a.shift[tid] : 0.f;
+        sh_scale[tid] = tid < K ? a.scale[tid] : 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tm = tmem_slot;
+    const uint32_t accA = tm, acc_w0 = tm + 64, acc_w1 = tm + 128, acc_w2 = tm + 192, acc_wx = tm + 256;
+    if (tid == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(wbar), "r"((two ? 3u : 2u) * W16_BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(W0), "l"(a.img_p0), "r"(W16_BYTES), "r"(wbar) : "memory");
+        if (two)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(W1), "l"(a.img_p1), "r"(W16_BYTES), "r"(wbar) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(W2), "l"(a.img_w2), "r"(W16_BYTES), "r"(wbar) : "memory");
+    }
+    const int64_t n_tiles = ceil_div(a.M, TC_ROWS);
+    const int q = warp & 3, ch = warp >> 2;
+    const int r_own = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+
+    float4 ra[8], rb[8], rc[8];
+    float bsum0[8] = {}, bsum1[8] = {};
+    float bacc[2] = {0.f, 0.f};  // column sums of g0 and dh1 (epilogue mapping)
+    uint32_t ph_d = 0, ph_w = 0;
+    int iter = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) rc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    load_tile(ra, a.dP0, (int64_t)blockIdx.x * TC_ROWS, a.M, tid);
+    load_tile(rb, a.out, (int64_t)blockIdx.x * TC_ROWS, a.M, tid);
+    if (two) load_tile(rc, a.dP1, (int64_t)blockIdx.x * TC_ROWS, a.M, tid);
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
+        const int64_t row0 = tile * TC_ROWS;
+        const int64_t m_own = row0 + r_own;
+        const bool row_ok = m_own < a.M;
+        const bool has_next = tile + gridDim.x < n_tiles;
+        const uint32_t wacc = iter > 0 ? 1u : 0u;
+
+        // ---------------- E0 ----------------
+        if (iter > 0) { mbar_wait(bar_w, ph_w); ph_w ^= 1; }
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const float4 x = ra[2 * it], y = ra[2 * it + 1], z = rc[2 * it], w = rc[2 * it + 1];
+            bsum0[0] += x.x; bsum0[1] += x.y; bsum0[2] += x.z; bsum0[3] += x.w;
+            bsum0[4] += y.x; bsum0[5] += y.y; bsum0[6] += y.z; bsum0[7] += y.w;
+            bsum1[0] += z.x; bsum1[1] += z.y; bsum1[2] += z.z; bsum1[3] += z.w;
+            bsum1[4] += w.x; bsum1[5] += w.y; bsum1[6] += w.z; bsum1[7] += w.w;
+        }
+        store_tile(B0g, ra, 1.f, tid);
+        store_tile(B1g, rb, 1.f, tid);
+        if (two) store_tile(B2g, rc, 1.f, tid);
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (tid == 0) {
+            if (iter == 0) mbar_wait(wbar, 0);
+            issue_dgrad(accA, B0, W0, 0);
+            if (two) issue_dgrad(accA, B2, W1, 1);
+            umma_commit(bar_d);
+            issue_wgrad(acc_w0, B1, T16_BYTES, B0, wacc);
+            if (two) issue_wgrad(acc_w1, B1, T16_BYTES, B2, wacc);
+            umma_commit(bar_w);
+        }
+        load_tile(ra, a.h1, row0, a.M, tid);
+        float4 dx[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            dx[j] = row_ok ? ldg_stream4(a.dXt + m_own * D + ch * 32 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        mbar_wait(bar_d, ph_d); ph_d ^= 1;
+        tc_fence_after();
+        {
+            float v[32];
+            tmem_ld32(accA + lane_off + (uint32_t)(ch * 32), v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                v[4 * j] += dx[j].x; v[4 * j + 1] += dx[j].y; v[4 * j + 2] += dx[j].z; v[4 * j + 3] += dx[j].w;
+            }
+            mask_row32(B1g, r_own, ch, v);
+            bacc[0] += warp_colsum32(v, lane);
+            mbar_wait(bar_w, ph_w); ph_w ^= 1;  // B0 (dP_0) and B2 (dP_1) are free
+            store_row32(B0g, r_own, ch, v);
+        }
+        store_tile(B2g, ra, 1.f, tid);
+
+        // ---------------- E1 ----------------
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (tid == 0) {
+            issue_dgrad(accA, B0, W2, 0);
+            umma_commit(bar_d);
+            issue_wgrad(acc_w2, B2, T16_BYTES, B0, wacc);
+            umma_commit(bar_w);
+        }
+        // raw input features of this thread's four (line, chunk) items: only chunks 0 and 1 can hold features (K <= 14)
+        float xn[4][8];
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int i = tid + it * TC_THREADS;
+            const int64_t m = row0 + (i >> 3);
+            const int c0 = (i & 7) * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = c0 + j;
+                xn[it][j] = (k < K && m < a.M) ? (__ldg(a.x + m * K + k) + sh_shift[k]) * sh_scale[k] : 0.f;
+            }
+        }
+        mbar_wait(bar_d, ph_d); ph_d ^= 1;
+        tc_fence_after();
+        {
+            float v[32];
+            tmem_ld32(accA + lane_off + (uint32_t)(ch * 32), v);
+            mask_row32(B2g, r_own, ch, v);
+            bacc[1] += warp_colsum32(v, lane);
+            store_row32(B1g, r_own, ch, v);
+        }
+
+        // ---------------- E2 ----------------
+        mbar_wait(bar_w, ph_w); ph_w ^= 1;  // B0 (g0) and B2 (h1) are free as far as the tensor core is concerned
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int i = tid + it * TC_THREADS;
+            store_chunk3(B0g, T16_PIECE, i >> 3, i & 7, xn[it]);
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (tid == 0) {
+            issue_wgrad(acc_wx, B0, T16_BYTES, B1, wacc);
+            umma_commit(bar_w);
+        }
+        if (has_next) {
+            const int64_t nrow0 = row0 + (int64_t)gridDim.x * TC_ROWS;
+            load_tile(ra, a.dP0, nrow0, a.M, tid);
+            load_tile(rb, a.out, nrow0, a.M, tid);
+            if (two) load_tile(rc, a.dP1, nrow0, a.M, tid);
+        }
+    }
+
+    mbar_wait(bar_w, ph_w);
+    tc_fence_after();
+    float* part = a.partials + (int64_t)blockIdx.x * EMB_BWD_PART;
+    {
+        const uint32_t accs[4] = {acc_w0, acc_w1, acc_w2, acc_wx};
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            if (q < 2 && (w != 1 || two)) {
+                float v[32];
+                tmem_ld32(accs[w] + lane_off + (uint32_t)(ch * 32), v);
+                float* dst = part + w * (D * D + D) + (q * 32 + lane) * D + ch * 32;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+        }
+    }
+    float* red_p = reinterpret_cast<float*>(B0g);  // [2][32 line groups][64]
+    float* red_e = red_p + 2 * 32 * D;             // [2][4 quadrants][64]
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        red_p[(tid >> 3) * D + (tid & 7) * 8 + j] = bsum0[j];
+        red_p[32 * D + (tid >> 3) * D + (tid & 7) * 8 + j] = bsum1[j];
+    }
+#pragma unroll
+    for (int s = 0; s < 2; ++s) red_e[(s * 4 + q) * D + ch * 32 + lane] = bacc[s];
+    tc_fence_before();
+    __syncthreads();
+    {
+        const int s = tid >> 6, c = tid & 63;  // s: 0 = b_0, 1 = b_1, 2 = b2, 3 = b1
+        float t = 0.f;
+        if (s < 2) {
+#pragma unroll
+            for (int g = 0; g < 32; ++g) t += red_p[s * 32 * D + g * D + c];
+        } else {
+            const int e = s - 2;
+            t = ((red_e[(e * 4 + 0) * D + c] + red_e[(e * 4 + 1) * D + c]) + red_e[(e * 4 + 2) * D + c]) +
+                red_e[(e * 4 + 3) * D + c];
+        }
+        part[s * (D * D + D) + D * D + c] = t;
+    }
+    if (warp == 0) tmem_dealloc(tm, 512);
+}
+
+int embed_backward_part_floats() { return EMB_BWD_PART; }
+
+int tc_embed_backward(const EmbBwdArgs& a, int* n_parts, cudaStream_t st) {
+    *n_parts = 0;
+    if (a.M <= 0) return GCNN_OK;
+    if (a.K > 14) { set_error("tc_embed_backward: at most 14 input features"); return GCNN_INVALID; }
+    const int parts = (int)min((int64_t)NUM_SMS, ceil_div(a.M, TC_ROWS));
+    *n_parts = parts;
+    const double rows_moved = (a.dP1 ? 5.0 : 4.0);  // dP_j, out, dXt, h1 (256 B per node each) + the raw features
+    ProfScope prof(PROF_EMB_BWD, (256.0 * rows_moved + 4.0 * a.K) * (double)a.M + 3.0 * W16_BYTES + 4.0 * EMB_BWD_PART * parts, st);
+    static int once = [] {
+        cudaError_t e = cudaFuncSetAttribute(tc_embed_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)CONV_BWD_SMEM);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(tc_embed_backward_kernel): %s", cudaGetErrorString(e)); return (int)GCNN_CUDA_ERROR; }
+        return (int)GCNN_OK;
+    }();
+    GCNN_TRY(once);
+    GCNN_LAUNCH(tc_embed_backward_kernel, parts, TC_THREADS, CONV_BWD_SMEM, st, a);
+    GCNN_LAUNCH_CHECK();
+    return GCNN_OK;
+}
+
 }  // namespace gcnn

@@ -388,6 +388,132 @@ int tc_conv_forward(const ConvFwdArgs& a, cudaStream_t st) {
     return GCNN_OK;
 }
 
+// ---- fused forward chain of one embedding ---------------------------------------------------------------------------
+// out = relu(relu(PreNorm(x) W1 + b1) W2 + b2) (model.py:174-195, applied :287-291) plus the convolution projections that
+// read the embedding directly (model.py:564-565: A0 = c0 Wl + bl; B0, B1 = v0 Wr; A2 = k0 Wl + bl), one CTA per 128 nodes:
+//   F0: h1 = relu(((x + shift) * scale) W1 + b1)   K <= 14 input features: fp32 FMAs straight into the A tile of F1
+//   F1: out = relu(h1 W2 + b2)                     tcgen05 3xTF32
+//   F2: P_j = out W_j + b_j, j = 0 [, 1]           tcgen05 3xTF32
+// h1 and out are also written to global memory (the backward pass and the concat of the convolutions read them).
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_embed_forward_kernel(const EmbFwdArgs a) {
+    pdl_enter();
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t mma_bar;
+    __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float bias_s[3][D];
+    __shared__ float sh_s[16], sc_s[16];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t row0 = (int64_t)blockIdx.x * TC_ROWS;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+    const int K = a.K;
+    const int n_proj = a.img_p[1] ? 2 : 1;
+    float* w1_s = reinterpret_cast<float*>(gen + REG_BYTES);  // W1 rows + b1 parked in region Q, which is idle during F0
+    {
+        if (tid < 3 * D) {
+            const float* bsrc = tid < D ? a.bias2 : (tid < 2 * D ? a.bias_p[0] : a.bias_p[1]);
+            bias_s[tid >> 6][tid & 63] = bsrc ? bsrc[tid & 63] : 0.f;
+        }
+        for (int i = tid; i < K * D; i += TC_THREADS) w1_s[i] = a.W1[i];
+        if (tid < D) w1_s[K * D + tid] = a.b1[tid];
+        if (tid < 16) { sh_s[tid] = tid < K ? a.shift[tid] : 0.f; sc_s[tid] = tid < K ? a.scale[tid] : 0.f; }
+    }
+    const uint32_t P = base, Q = base + REG_BYTES, WA = base + 2 * REG_BYTES, WB = base + 2 * REG_BYTES + 2 * IMG_BYTES;
+    if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), 64);
+    if (tid == 0) mbar_init(smem_u32(&mma_bar), 1);
+    copy_image_async(WB, a.img_w2, tid);
+    copy_image_async(WA, a.img_p[0], tid);
+    if (n_proj == 2) copy_image_async(WA + IMG_BYTES, a.img_p[1], tid);
+    cp_async_commit();
+
+    const int q = warp & 3, ch = warp >> 2;
+    const int r_own = q * 32 + lane;
+    const int64_t m_own = row0 + r_own;
+    const bool row_ok = m_own < a.M;
+    __syncthreads();  // W1 / pre-norm tables are in shared memory
+
+    // F0: this thread's row, columns [32 ch, 32 ch + 32)
+    {
+        float xn[14];
+#pragma unroll
+        for (int k = 0; k < 14; ++k) xn[k] = (k < K && row_ok) ? (__ldg(a.x + m_own * K + k) + sh_s[k]) * sc_s[k] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float4 y = *reinterpret_cast<const float4*>(&w1_s[K * D + ch * 32 + 4 * j]);
+#pragma unroll
+            for (int k = 0; k < 14; ++k) {
+                if (k < K) {
+                    const float4 w = *reinterpret_cast<const float4*>(&w1_s[k * D + ch * 32 + 4 * j]);
+                    y.x = fmaf(xn[k], w.x, y.x); y.y = fmaf(xn[k], w.y, y.y);
+                    y.z = fmaf(xn[k], w.z, y.z); y.w = fmaf(xn[k], w.w, y.w);
+                }
+            }
+            y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f);
+            if (!row_ok) y = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row_ok && a.h1) *reinterpret_cast<float4*>(a.h1 + m_own * D + ch * 32 + 4 * j) = y;
+            float4 hi, lo;
+            split4(y, hi, lo);
+            const uint32_t off = swz_chunk_off(r_own, ch * 32 + 4 * j, TC_ROWS);
+            *reinterpret_cast<float4*>(gen + off) = hi;
+            *reinterpret_cast<float4*>(gen + 2 * A_BLOCK_BYTES + off) = lo;
+        }
+    }
+    cp_async_wait<0>();
+    uint32_t tmem_d = 0;
+    const int n_stages = 1 + n_proj;
+    for (int s = 0; s < n_stages; ++s) {
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (s == 0) tmem_d = tmem_slot;
+        if (tid == 0) {
+            if (s == 0)      { const uint32_t ar[2] = {P, 0}, bi[2] = {WB, 0};             issue_stage(tmem_d, ar, bi, 1); }
+            else if (s == 1) { const uint32_t ar[2] = {Q, 0}, bi[2] = {WA, 0};             issue_stage(tmem_d, ar, bi, 1); }
+            else             { const uint32_t ar[2] = {Q, 0}, bi[2] = {WA + IMG_BYTES, 0}; issue_stage(tmem_d, ar, bi, 1); }
+            umma_commit(smem_u32(&mma_bar));
+        }
+        mbar_wait(smem_u32(&mma_bar), (uint32_t)(s & 1));
+        tc_fence_after();
+        float v[32];
+        tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
+        float* out = s == 0 ? a.out : (s == 1 ? a.P[0] : a.P[1]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float4 y = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            const float4 b4 = *reinterpret_cast<const float4*>(&bias_s[s][ch * 32 + 4 * j]);
+            y.x += b4.x; y.y += b4.y; y.z += b4.z; y.w += b4.w;
+            if (s == 0) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+            if (row_ok) *reinterpret_cast<float4*>(out + m_own * D + ch * 32 + 4 * j) = y;
+            if (s == 0) {
+                float4 hi, lo;
+                split4(y, hi, lo);
+                const uint32_t off = swz_chunk_off(r_own, ch * 32 + 4 * j, TC_ROWS);
+                *reinterpret_cast<float4*>(gen + REG_BYTES + off) = hi;
+                *reinterpret_cast<float4*>(gen + REG_BYTES + 2 * A_BLOCK_BYTES + off) = lo;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_d, 64);
+}
+
+int tc_embed_forward(const EmbFwdArgs& a, cudaStream_t st) {
+    if (a.M <= 0) return GCNN_OK;
+    if (a.K > 14) { set_error("tc_embed_forward: at most 14 input features"); return GCNN_INVALID; }
+    const int n_proj = a.img_p[1] ? 2 : 1;
+    // algorithmic bytes: read the raw features, write h1, out and the projections (256 B per node each), weights once
+    ProfScope prof(PROF_EMB1_FWD, (4.0 * a.K + 256.0 * (2 + n_proj)) * (double)a.M + 4.0 * (a.K * D + D * D * (1 + n_proj)), st);
+    const size_t smem = 2 * REG_BYTES + 3 * IMG_BYTES + 1024;
+    static int once = set_smem_tc(tc_embed_forward_kernel, smem);
+    GCNN_TRY(once);
+    GCNN_LAUNCH(tc_embed_forward_kernel, (unsigned)ceil_div(a.M, TC_ROWS), TC_THREADS, smem, st, a);
+    GCNN_LAUNCH_CHECK();
+    return GCNN_OK;
+}
+
 // ---- weight gradient on the tensor cores ----------------------------------------------------------------------------
 // dW[f, c] = sum_m Xcat[m, f] * dYp[m, c] is a GEMM whose reduction runs over ROWS, so the row-major tiles
 // [row][32 floats] are MN-major operands (MN = the 32 contiguous features / columns, K = the rows): no transpose is

@@ -24,15 +24,19 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-5
 
 
-GRAD_TOL = {"tc3xtf32": 3e-5, "fp32": 1e-5}
+GRAD_TOL = {"tc3xtf32": 3e-5, "tc_unfused": 3e-5, "fp32": 1e-5}
 
 
-@pytest.fixture(scope="module", params=["tc3xtf32", "fp32"])
+@pytest.fixture(scope="module", params=["tc3xtf32", "tc_unfused", "fp32"])
 def model(request, golden_dir):
+    """tc3xtf32: the default path (fused tcgen05 chains, 3xTF32 forward, bf16x3 backward); tc_unfused: one tensor-core
+    launch per dense layer and per gradient; fp32: exact-fp32 SIMT dense layers."""
     from gcnn_cut_selector_b200 import GCNN
     m = GCNN(device="cuda:0", seed=0)
     m.restore_state(os.path.join(golden_dir, "state_stream.pkl"))
-    m.set_option("tensor_cores", 1 if request.param == "tc3xtf32" else 0)
+    m.set_option("tensor_cores", 0 if request.param == "fp32" else 1)
+    m.set_option("fused", 0 if request.param == "tc_unfused" else 1)
+    m.set_option("fused_backward", 0 if request.param == "tc_unfused" else 1)
     m.grad_tol = GRAD_TOL[request.param]
     return m
 
