@@ -49,16 +49,23 @@ __device__ __forceinline__ uint64_t make_desc_mn16(uint32_t smem_addr, uint32_t 
 
 // The six bf16 products kept by the x3 split, (A piece, B piece) = (2,0) (1,1) (0,2) (1,0) (0,1) (0,0): smallest terms
 // first; the dropped (1,2) (2,1) (2,2) terms are <= 2^-24 relative.
+//
+// One thread issues ~300 MMAs per tile, so descriptor arithmetic is kept to one 32-bit add per operand: the start
+// address lives in the low 14 bits of the descriptor (16-byte units) and no operand crosses the 256 KB field range.
+__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) {
+    return desc + (uint64_t)(bytes >> 4);
+}
 
 // D[128 x 64] (+)= G[128 x 64] * Wimg^T: A = bf16x3 tile (K-major), B = bf16x3 N image of a 64 x 64 weight block
 __device__ __forceinline__ void issue_dgrad(uint32_t tmem_d, uint32_t a_tile, uint32_t w_img, uint32_t acc) {
+    const uint64_t da0 = make_desc(a_tile), db0 = make_desc(w_img);
 #pragma unroll
     for (int p = 0; p < 6; ++p) {
         const int pa = p == 0 ? 2 : (p == 1 || p == 3) ? 1 : 0;
         const int pb = p == 0 ? 0 : p == 1 ? 1 : p == 2 ? 2 : p == 3 ? 0 : p == 4 ? 1 : 0;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-            umma_bf16(tmem_d, make_desc(a_tile + pa * T16_PIECE + ks * 32), make_desc(w_img + pb * W16_PIECE + ks * 32),
+            umma_bf16(tmem_d, desc_advance(da0, pa * T16_PIECE + ks * 32), desc_advance(db0, pb * W16_PIECE + ks * 32),
                       IDESC_BF16_KK, acc);
             acc = 1;
         }
@@ -70,14 +77,15 @@ __device__ __forceinline__ void issue_dgrad(uint32_t tmem_d, uint32_t a_tile, ui
 // after the first (the right half of the concat, or don't-care data whose result rows 64..127 are never read).
 __device__ __forceinline__ void issue_wgrad(uint32_t tmem_d, uint32_t act_tile, uint32_t lbo, uint32_t g_tile,
                                             uint32_t acc) {
+    const uint64_t da0 = make_desc_mn16(act_tile, lbo), db0 = make_desc_mn16(g_tile, T16_BYTES);
 #pragma unroll
     for (int p = 0; p < 6; ++p) {
         const int pa = p == 0 ? 2 : (p == 1 || p == 3) ? 1 : 0;
         const int pb = p == 0 ? 0 : p == 1 ? 1 : p == 2 ? 2 : p == 3 ? 0 : p == 4 ? 1 : 0;
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
-            umma_bf16(tmem_d, make_desc_mn16(act_tile + pa * T16_PIECE + ks * 2048, lbo),
-                      make_desc_mn16(g_tile + pb * T16_PIECE + ks * 2048, T16_BYTES), IDESC_BF16_MN, acc);
+            umma_bf16(tmem_d, desc_advance(da0, pa * T16_PIECE + ks * 2048), desc_advance(db0, pb * T16_PIECE + ks * 2048),
+                      IDESC_BF16_MN, acc);
             acc = 1;
         }
     }
@@ -170,7 +178,7 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[5];  // 0: input-gradient MMAs, 1: weight-gradient MMAs, 2..4: weight slots
     __shared__ uint32_t tmem_slot;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = warp_index(), lane = tid & 31;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
     uint8_t* const B0g = gen;
@@ -232,7 +240,7 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             mbar_wait(wbar0, 0);
             issue_dgrad(accA, B0, W0, 0);
             umma_commit(bar_d);
@@ -258,7 +266,7 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             mbar_wait(wbar1, 0);
             issue_dgrad(accA, B2, W1, 0);
             umma_commit(bar_d);
@@ -287,7 +295,7 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             mbar_wait(wbar2, (uint32_t)(iter & 1));
             mbar_wait(wbar0, 1);
             issue_dgrad(accA, B1, W2, 0);
@@ -336,7 +344,7 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             mbar_wait(wbar1, 1);
             issue_dgrad(accA, B1, W1, 0);
             umma_commit(bar_d);
@@ -450,7 +458,7 @@ tc_embed_backward_kernel(const EmbBwdArgs a) {
     __shared__ __align__(8) uint64_t bars[3];  // 0: input-gradient MMAs, 1: weight-gradient MMAs, 2: weight images
     __shared__ uint32_t tmem_slot;
     __shared__ float sh_shift[16], sh_scale[16];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = warp_index(), lane = tid & 31;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
     uint8_t* const B0g = gen;
@@ -525,7 +533,7 @@ tc_embed_backward_kernel(const EmbBwdArgs a) {
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             if (iter == 0) mbar_wait(wbar, 0);
             issue_dgrad(accA, B0, W0, 0);
             if (two) issue_dgrad(accA, B2, W1, 1);
@@ -560,7 +568,7 @@ tc_embed_backward_kernel(const EmbBwdArgs a) {
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             issue_dgrad(accA, B0, W2, 0);
             umma_commit(bar_d);
             issue_wgrad(acc_w2, B2, T16_BYTES, B0, wacc);
@@ -600,7 +608,7 @@ tc_embed_backward_kernel(const EmbBwdArgs a) {
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             issue_wgrad(acc_wx, B0, T16_BYTES, B1, wacc);
             umma_commit(bar_w);
         }

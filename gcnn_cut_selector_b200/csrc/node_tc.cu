@@ -74,7 +74,7 @@ tc_linear_kernel(const TcArgs a) {
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(16) float bias_s[D];
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = warp_index(), lane = tid & 31;
     const int slab = blockIdx.y;
     if (tid < D) bias_s[tid] = a.bias ? a.bias[tid] : 0.f;
     const int64_t row0 = (int64_t)blockIdx.x * TC_ROWS;
@@ -145,7 +145,7 @@ tc_linear_kernel(const TcArgs a) {
     tc_fence_after();
     const uint32_t tmem_d = tmem_slot;
 
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
         const uint32_t a_addr[2] = {base, base + A_PART};                            // hi, lo
         const uint32_t b_addr[2] = {base + 2 * A_PART, base + 2 * A_PART + B_PART};  // hi, lo
         const int sel[3][2] = {{1, 0}, {0, 1}, {0, 0}};                              // (A part, B part): lo*hi, hi*lo, hi*hi
@@ -268,7 +268,7 @@ tc_conv_forward_kernel(const ConvFwdArgs a) {
     __shared__ __align__(8) uint64_t mma_bar;
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(16) float bias_s[4][D];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = warp_index(), lane = tid & 31;
     const int64_t row0 = (int64_t)blockIdx.x * TC_ROWS;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -333,7 +333,7 @@ tc_conv_forward_kernel(const ConvFwdArgs a) {
         __syncthreads();
         tc_fence_after();
         if (s == 0) tmem_d = tmem_slot;
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             if (s == 0)      { const uint32_t ar[2] = {P, 0}, bi[2] = {WB, 0};              issue_stage(tmem_d, ar, bi, 1); }
             else if (s == 1) { const uint32_t ar[2] = {P, Q}, bi[2] = {WA, WA + IMG_BYTES}; issue_stage(tmem_d, ar, bi, 2); }
             else if (s == 2) { const uint32_t ar[2] = {P, 0}, bi[2] = {WB, 0};              issue_stage(tmem_d, ar, bi, 1); }
@@ -403,7 +403,7 @@ tc_embed_forward_kernel(const EmbFwdArgs a) {
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(16) float bias_s[3][D];
     __shared__ float sh_s[16], sc_s[16];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = warp_index(), lane = tid & 31;
     const int64_t row0 = (int64_t)blockIdx.x * TC_ROWS;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -468,7 +468,7 @@ tc_embed_forward_kernel(const EmbFwdArgs a) {
         __syncthreads();
         tc_fence_after();
         if (s == 0) tmem_d = tmem_slot;
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             if (s == 0)      { const uint32_t ar[2] = {P, 0}, bi[2] = {WB, 0};             issue_stage(tmem_d, ar, bi, 1); }
             else if (s == 1) { const uint32_t ar[2] = {Q, 0}, bi[2] = {WA, 0};             issue_stage(tmem_d, ar, bi, 1); }
             else             { const uint32_t ar[2] = {Q, 0}, bi[2] = {WA + IMG_BYTES, 0}; issue_stage(tmem_d, ar, bi, 1); }
@@ -553,7 +553,7 @@ tc_wgrad_kernel(const TcWgradArgs a) {
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(16) float bias_red[16][D];
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = warp_index(), lane = tid & 31;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
     // layout: A_hi | A_lo | B_hi | B_lo.  With K = 64 the M = 128 instruction reads two blocks past each A part
@@ -637,7 +637,7 @@ tc_wgrad_kernel(const TcWgradArgs a) {
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             const uint32_t a_addr[2] = {base, base + A_PART};
             const uint32_t b_addr[2] = {base + 2 * A_PART, base + 2 * A_PART + B_PART};
             const int sel[3][2] = {{1, 0}, {0, 1}, {0, 0}};

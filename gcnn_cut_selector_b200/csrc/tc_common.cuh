@@ -53,6 +53,20 @@ __device__ __forceinline__ float4 ldg_stream4(const float* p) {
     return v;
 }
 
+// One lane of a fully converged warp.  The MMA issue paths are written as `if (warp == 0 && elect_one())` with `warp`
+// made provably warp-uniform by a shuffle (warp_index()): inside such a region the compiler knows a single lane is active
+// and moves descriptors into uniform registers directly, instead of wrapping every tcgen05.mma in a broadcast loop.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ int warp_index() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 // D[tmem] (+)= A[smem desc] * B[smem desc], tf32 inputs, fp32 accumulate, M = 128, N = 64, K = 8
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate) {
