@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgcnn_b200.so")
+LIB_PATH = os.environ.get("GCNN_LIB") or os.path.join(HERE, "libgcnn_b200.so")  # GCNN_LIB: an instrumented build (scripts/)
 
 OK, INVALID, CUDA_ERROR, OOM = 0, 1, 2, 3
 N_TRAINABLE, N_PRENORM, N_ARRAYS, N_PRENORM_LAYERS = 93121, 58, 62, 11

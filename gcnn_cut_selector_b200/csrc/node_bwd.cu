@@ -56,17 +56,19 @@ __device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) 
     return desc + (uint64_t)(bytes >> 4);
 }
 
-// D[128 x 64] (+)= G[128 x 64] * Wimg^T: A = bf16x3 tile (K-major), B = bf16x3 N image of a 64 x 64 weight block
+// D[128 x 64] (+)= G[128 x 64] * Wimg^T: A = bf16x3 tile (K-major), B = bf16x3 N image of a 64 x 64 weight block.
+// The product loop is NOT unrolled and the tile addresses are laundered through an empty asm: the MMA warp runs on a
+// small register budget, and ~600 hoisted loop-invariant descriptors would spill to local memory between the MMAs.
 __device__ __forceinline__ void issue_dgrad(uint32_t tmem_d, uint32_t a_tile, uint32_t w_img, uint32_t acc) {
+    asm volatile("" : "+r"(a_tile), "+r"(w_img));
     const uint64_t da0 = make_desc(a_tile), db0 = make_desc(w_img);
-#pragma unroll
+#pragma unroll 1
     for (int p = 0; p < 6; ++p) {
-        const int pa = p == 0 ? 2 : (p == 1 || p == 3) ? 1 : 0;
-        const int pb = p == 0 ? 0 : p == 1 ? 1 : p == 2 ? 2 : p == 3 ? 0 : p == 4 ? 1 : 0;
+        const uint32_t pa = (0x001012u >> (4 * p)) & 3u, pb = (0x010210u >> (4 * p)) & 3u;  // (2,0) (1,1) (0,2) (1,0) (0,1) (0,0)
+        const uint64_t da = da0 + (uint64_t)(pa * (T16_PIECE >> 4)), db = db0 + (uint64_t)(pb * (W16_PIECE >> 4));
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-            umma_bf16(tmem_d, desc_advance(da0, pa * T16_PIECE + ks * 32), desc_advance(db0, pb * W16_PIECE + ks * 32),
-                      IDESC_BF16_KK, acc);
+            umma_bf16(tmem_d, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), IDESC_BF16_KK, acc);
             acc = 1;
         }
     }
@@ -77,15 +79,15 @@ __device__ __forceinline__ void issue_dgrad(uint32_t tmem_d, uint32_t a_tile, ui
 // after the first (the right half of the concat, or don't-care data whose result rows 64..127 are never read).
 __device__ __forceinline__ void issue_wgrad(uint32_t tmem_d, uint32_t act_tile, uint32_t lbo, uint32_t g_tile,
                                             uint32_t acc) {
+    asm volatile("" : "+r"(act_tile), "+r"(g_tile));
     const uint64_t da0 = make_desc_mn16(act_tile, lbo), db0 = make_desc_mn16(g_tile, T16_BYTES);
-#pragma unroll
+#pragma unroll 1
     for (int p = 0; p < 6; ++p) {
-        const int pa = p == 0 ? 2 : (p == 1 || p == 3) ? 1 : 0;
-        const int pb = p == 0 ? 0 : p == 1 ? 1 : p == 2 ? 2 : p == 3 ? 0 : p == 4 ? 1 : 0;
+        const uint32_t pa = (0x001012u >> (4 * p)) & 3u, pb = (0x010210u >> (4 * p)) & 3u;
+        const uint64_t da = da0 + (uint64_t)(pa * (T16_PIECE >> 4)), db = db0 + (uint64_t)(pb * (T16_PIECE >> 4));
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
-            umma_bf16(tmem_d, desc_advance(da0, pa * T16_PIECE + ks * 2048), desc_advance(db0, pb * T16_PIECE + ks * 2048),
-                      IDESC_BF16_MN, acc);
+            umma_bf16(tmem_d, da + (uint64_t)(ks * (2048 >> 4)), db + (uint64_t)(ks * (2048 >> 4)), IDESC_BF16_MN, acc);
             acc = 1;
         }
     }
@@ -96,6 +98,28 @@ __device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src, ui
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// ---- warp roles -----------------------------------------------------------------------------------------------------
+// Warps 0..7 move and transform data (loads, bf16x3 splits, epilogues); warp 8 only talks to the tensor core and the
+// bulk-copy engine.  tcgen05.mma issue blocks the issuing thread at the tensor core's pace (about 50 cycles per MMA here,
+// bound by the operand reads from shared memory), so a compute warp that also issued MMAs would stall every other warp
+// at the next barrier.  Hand-off: the compute warps meet at a named barrier, then one of them arrives on `bar_ready`.
+constexpr int BWD_THREADS = 384;  // warpgroups 0, 1: compute; warpgroup 2: warp 8 issues, warps 9..11 idle
+// Register budget: 384 threads start with 168 registers each; the MMA warpgroup gives most of its share back
+// (setmaxnreg.dec) and the compute warpgroups grow to 224 (setmaxnreg.inc): 256 x 224 + 128 x 56 = 64,512 <= 65,536.
+__device__ __forceinline__ void regs_compute() { asm volatile("setmaxnreg.inc.sync.aligned.u32 224;"); }
+__device__ __forceinline__ void regs_mma() { asm volatile("setmaxnreg.dec.sync.aligned.u32 56;"); }
+__device__ __forceinline__ void compute_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// compute side: tiles of the next stage are in shared memory -> let the MMA warp go
+__device__ __forceinline__ void publish_tiles(uint32_t bar_ready, int tid) {
+    fence_async_smem();
+    tc_fence_before();
+    compute_barrier();
+    if (tid == 0) mbar_arrive(bar_ready);
 }
 
 // ---- tile movement -------------------------------------------------------------------------------------------------
@@ -169,16 +193,32 @@ __device__ __forceinline__ float warp_colsum32(const float (&v)[32], int lane) {
     return t[0];
 }
 
+// Optional stage timing (compile with -DGCNN_CHAIN_TIMING): thread 0 of CTA 0 records clock64() at the marked points of its
+// first two tiles into a global buffer read back by scripts/chain_timing.py.
+#ifdef GCNN_CHAIN_TIMING
+__device__ long long g_chain_ts[64];
+__device__ int g_chain_n;
+#define TS_MARK() do { if (tid == 0 && blockIdx.x == 0 && ts_n < 64) g_chain_ts[ts_n++] = clock64(); } while (0)
+#define TS_DECL() int ts_n = 0
+#define TS_DONE() do { if (tid == 0 && blockIdx.x == 0) g_chain_n = ts_n; } while (0)
+#else
+#define TS_MARK() do {} while (0)
+#define TS_DECL() do {} while (0)
+#define TS_DONE() do {} while (0)
+#endif
+
 constexpr uint32_t CONV_BWD_SMEM = 3 * T16_BYTES + 3 * W16_BYTES + 1024;
 constexpr int CONV_BWD_PART = 3 * (D * D + D) + 2 * D * D + D;  // floats per CTA partial: Wn|bn|Wo2|bo2|Wo1|bo1|Wf|bf
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(BWD_THREADS, 1)
 tc_conv_backward_kernel(const ConvBwdArgs a) {
-    pdl_enter();
+    const int tid = threadIdx.x;
+    TS_DECL();
+    TS_MARK();  // kernel entry
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[5];  // 0: input-gradient MMAs, 1: weight-gradient MMAs, 2..4: weight slots
+    __shared__ __align__(8) uint64_t bars[6];  // 0: input-gradient MMAs, 1: weight-gradient MMAs, 2..4: weight slots, 5: tiles ready
     __shared__ uint32_t tmem_slot;
-    const int tid = threadIdx.x, warp = warp_index(), lane = tid & 31;
+    const int warp = warp_index(), lane = tid & 31;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
     uint8_t* const B0g = gen;
@@ -188,23 +228,89 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
     const uint32_t W0 = base + 3 * T16_BYTES, W1 = W0 + W16_BYTES, W2 = W1 + W16_BYTES;
     const uint32_t bar_d = smem_u32(&bars[0]), bar_w = smem_u32(&bars[1]);
     const uint32_t wbar0 = smem_u32(&bars[2]), wbar1 = smem_u32(&bars[3]), wbar2 = smem_u32(&bars[4]);
+    const uint32_t bar_ready = smem_u32(&bars[5]);
 
     if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), 512);
     if (tid == 0) {
-        for (int i = 0; i < 5; ++i) mbar_init(smem_u32(&bars[i]), 1);
+        for (int i = 0; i < 6; ++i) mbar_init(smem_u32(&bars[i]), 1);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    TS_MARK();  // TMEM and barriers ready
+    pdl_enter();  // everything above is independent of the previous grid and overlaps its tail
+    TS_MARK();  // previous grid done
     const uint32_t tm = tmem_slot;
     const uint32_t accA = tm, accB = tm + 64, acc_wn = tm + 128, acc_wo2 = tm + 192, acc_wo1 = tm + 256, acc_wf = tm + 320;
 
     const int64_t n_tiles = ceil_div(a.M, TC_ROWS);
-    if (tid == 0) {
-        bulk_load(W0, a.img_n, W16_BYTES, wbar0);
-        bulk_load(W1, a.img_o2, W16_BYTES, wbar1);
-        bulk_load(W2, a.img_o1a, W16_BYTES, wbar2);
+
+    if (warp >= 8) {
+        // ================= MMA / weight-copy warp =================
+        regs_mma();
+        if (warp == 8 && elect_one()) {
+            bulk_load(W0, a.img_n, W16_BYTES, wbar0);
+            bulk_load(W1, a.img_o2, W16_BYTES, wbar1);
+            bulk_load(W2, a.img_o1a, W16_BYTES, wbar2);
+            uint32_t ph_r = 0, ph_dd = 0;
+            int it = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const bool has_next = tile + gridDim.x < n_tiles;
+                const uint32_t wacc = it > 0 ? 1u : 0u;
+                // S3
+                mbar_wait(bar_ready, ph_r); ph_r ^= 1;
+                tc_fence_after();
+                mbar_wait(wbar0, 0);
+                issue_dgrad(accA, B0, W0, 0);
+                umma_commit(bar_d);
+                issue_wgrad(acc_wn, B1, T16_BYTES, B0, wacc);
+                umma_commit(bar_w);
+                mbar_wait(bar_d, ph_dd); ph_dd ^= 1;  // slot 0 is free
+                bulk_load(W0, a.img_o1b, W16_BYTES, wbar0);
+                // S2
+                mbar_wait(bar_ready, ph_r); ph_r ^= 1;
+                tc_fence_after();
+                mbar_wait(wbar1, 0);
+                issue_dgrad(accA, B2, W1, 0);
+                umma_commit(bar_d);
+                issue_wgrad(acc_wo2, B0, T16_BYTES, B2, wacc);
+                umma_commit(bar_w);
+                mbar_wait(bar_d, ph_dd); ph_dd ^= 1;  // slot 1 is free
+                bulk_load(W1, a.img_f, W16_BYTES, wbar1);
+                // S1
+                mbar_wait(bar_ready, ph_r); ph_r ^= 1;
+                tc_fence_after();
+                mbar_wait(wbar2, (uint32_t)(it & 1));
+                mbar_wait(wbar0, 1);
+                issue_dgrad(accA, B1, W2, 0);
+                issue_dgrad(accB, B1, W0, 0);
+                umma_commit(bar_d);
+                issue_wgrad(acc_wo1, B0, 2 * T16_BYTES, B1, wacc);
+                umma_commit(bar_w);
+                mbar_wait(bar_d, ph_dd); ph_dd ^= 1;  // slots 0 and 2 are free
+                if (has_next) {
+                    bulk_load(W0, a.img_n, W16_BYTES, wbar0);
+                    bulk_load(W2, a.img_o1a, W16_BYTES, wbar2);
+                }
+                // S0
+                mbar_wait(bar_ready, ph_r); ph_r ^= 1;
+                tc_fence_after();
+                mbar_wait(wbar1, 1);
+                issue_dgrad(accA, B1, W1, 0);
+                umma_commit(bar_d);
+                issue_wgrad(acc_wf, B0, T16_BYTES, B1, wacc);
+                umma_commit(bar_w);
+                mbar_wait(bar_d, ph_dd); ph_dd ^= 1;  // slot 1 is free
+                if (has_next) bulk_load(W1, a.img_o2, W16_BYTES, wbar1);
+            }
+        }
+        __syncwarp();
+        tc_fence_before();
+        __syncthreads();  // matches the compute warps' final barrier before the TMEM release
+        return;
     }
+    // ================= compute warps =================
+    regs_compute();
     const float s_p = *a.s_p, s_f = *a.s_f;
     const int q = warp & 3, ch = warp >> 2;
     const int r_own = q * 32 + lane;
@@ -214,6 +320,7 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
     float bsum_p[8] = {};           // column sums of dP (load mapping: columns 8 (tid & 7) .. +8)
     float bacc[3] = {0.f, 0.f, 0.f};  // column sums of dU2, dU1, deg * dC (epilogue mapping: column 32 ch + lane)
     uint32_t ph_d = 0, ph_w = 0;
+    TS_MARK();  // prologue done (TMEM, barriers, role split, registers)
     int iter = 0;
 
     load_tile(ra, a.dP, (int64_t)blockIdx.x * TC_ROWS, a.M, tid);
@@ -224,9 +331,9 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
         const int64_t m_own = row0 + r_own;
         const bool row_ok = m_own < a.M;
         const bool has_next = tile + gridDim.x < n_tiles;
-        const uint32_t wacc = iter > 0 ? 1u : 0u;
 
         // ---------------- S3: through the layer that consumed Y ----------------
+        TS_MARK();  // tile start
         if (iter > 0) { mbar_wait(bar_w, ph_w); ph_w ^= 1; }  // S0 of the previous tile has drained: B0, B1 are free
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
@@ -236,21 +343,14 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
         }
         store_tile(B0g, ra, 1.f, tid);
         store_tile(B1g, rb, 1.f, tid);
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-        if (warp == 0 && elect_one()) {
-            mbar_wait(wbar0, 0);
-            issue_dgrad(accA, B0, W0, 0);
-            umma_commit(bar_d);
-            issue_wgrad(acc_wn, B1, T16_BYTES, B0, wacc);
-            umma_commit(bar_w);
-        }
+        TS_MARK();  // tiles stored
+        publish_tiles(bar_ready, tid);
+        TS_MARK();  // published
         load_tile(ra, a.U1, row0, a.M, tid);
+        TS_MARK();  // MMAs issued, prefetch loads issued
         mbar_wait(bar_d, ph_d); ph_d ^= 1;
+        TS_MARK();  // input-gradient MMAs done
         tc_fence_after();
-        if (tid == 0) bulk_load(W0, a.img_o1b, W16_BYTES, wbar0);
         {
             float v[32];
             tmem_ld32(accA + lane_off + (uint32_t)(ch * 32), v);
@@ -259,25 +359,20 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
             bacc[0] += warp_colsum32(v, lane);
         }
 
+        TS_MARK();  // epilogue done
         // ---------------- S2: output layer 2 ----------------
         mbar_wait(bar_w, ph_w); ph_w ^= 1;  // B0 (dP) and B1 (Y) are free
+        TS_MARK();  // weight-gradient MMAs done
         store_tile(B0g, ra, 1.f, tid);
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-        if (warp == 0 && elect_one()) {
-            mbar_wait(wbar1, 0);
-            issue_dgrad(accA, B2, W1, 0);
-            umma_commit(bar_d);
-            issue_wgrad(acc_wo2, B0, T16_BYTES, B2, wacc);
-            umma_commit(bar_w);
-        }
+        TS_MARK();  // tiles stored
+        publish_tiles(bar_ready, tid);
+        TS_MARK();  // published
         load_tile(ra, a.C, row0, a.M, tid);
         load_tile(rb, a.Xt, row0, a.M, tid);
+        TS_MARK();  // MMAs issued, prefetch loads issued
         mbar_wait(bar_d, ph_d); ph_d ^= 1;
+        TS_MARK();  // input-gradient MMAs done
         tc_fence_after();
-        if (tid == 0) bulk_load(W1, a.img_f, W16_BYTES, wbar1);
         {
             float v[32];
             tmem_ld32(accA + lane_off + (uint32_t)(ch * 32), v);
@@ -286,41 +381,22 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
             bacc[1] += warp_colsum32(v, lane);
         }
 
+        TS_MARK();  // epilogue done
         // ---------------- S1: output layer 1 over the concat [s_p C, X_t] ----------------
         mbar_wait(bar_w, ph_w); ph_w ^= 1;  // the tensor core is done with B0 (U1) and B2 (dU2) ...
-        __syncthreads();                    // ... and so are the S2 epilogues of the other warps (ReLU mask read from B0)
+        TS_MARK();  // weight-gradient MMAs done
+        compute_barrier();                  // ... and so are the S2 epilogues of the other warps (ReLU mask read from B0)
         store_tile(B0g, ra, s_p, tid);
         store_tile(B2g, rb, 1.f, tid);
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-        if (warp == 0 && elect_one()) {
-            mbar_wait(wbar2, (uint32_t)(iter & 1));
-            mbar_wait(wbar0, 1);
-            issue_dgrad(accA, B1, W2, 0);
-            issue_dgrad(accB, B1, W0, 0);
-            umma_commit(bar_d);
-            issue_wgrad(acc_wo1, B0, 2 * T16_BYTES, B1, wacc);
-            umma_commit(bar_w);
-        }
+        TS_MARK();  // tiles stored
+        publish_tiles(bar_ready, tid);
+        TS_MARK();  // published
         load_tile(ra, a.H, row0, a.M, tid);
-        float4 cn[8];
-        float deg = 0.f;
-        if (row_ok) {
-            deg = (float)(a.deg_ptr[m_own + 1] - a.deg_ptr[m_own]);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) cn[j] = ldg_stream4(a.cnt + m_own * D + ch * 32 + 4 * j);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) cn[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        const float deg = row_ok ? (float)(a.deg_ptr[m_own + 1] - a.deg_ptr[m_own]) : 0.f;
+        TS_MARK();  // MMAs issued, prefetch loads issued
         mbar_wait(bar_d, ph_d); ph_d ^= 1;
+        TS_MARK();  // input-gradient MMAs done
         tc_fence_after();
-        if (tid == 0 && has_next) {
-            bulk_load(W0, a.img_n, W16_BYTES, wbar0);
-            bulk_load(W2, a.img_o1a, W16_BYTES, wbar2);
-        }
         {
             float v[32], x[32];
             tmem_ld32(accB + lane_off + (uint32_t)(ch * 32), x);
@@ -335,29 +411,27 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
             for (int i = 0; i < 32; ++i) { v[i] *= s_p; x[i] = v[i] * deg; }
             bacc[2] += warp_colsum32(x, lane);
             mbar_wait(bar_w, ph_w); ph_w ^= 1;  // B0, B1, B2 are free
+        TS_MARK();  // weight-gradient MMAs done
             store_row32(B1g, r_own, ch, v);
         }
         store_tile(B0g, ra, 1.f, tid);
 
         // ---------------- S0: hoisted feature_module_final ----------------
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-        if (warp == 0 && elect_one()) {
-            mbar_wait(wbar1, 1);
-            issue_dgrad(accA, B1, W1, 0);
-            umma_commit(bar_d);
-            issue_wgrad(acc_wf, B0, T16_BYTES, B1, wacc);
-            umma_commit(bar_w);
-        }
+        TS_MARK();  // tiles stored
+        publish_tiles(bar_ready, tid);
+        TS_MARK();  // published
+        float4 cn[8];  // active-edge counts of this thread's row (epilogue mapping)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            cn[j] = row_ok ? ldg_stream4(a.cnt + m_own * D + ch * 32 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
         if (has_next) {
             load_tile(ra, a.dP, row0 + (int64_t)gridDim.x * TC_ROWS, a.M, tid);
             load_tile(rb, a.Y, row0 + (int64_t)gridDim.x * TC_ROWS, a.M, tid);
         }
+        TS_MARK();  // MMAs issued, prefetch loads issued
         mbar_wait(bar_d, ph_d); ph_d ^= 1;
+        TS_MARK();  // input-gradient MMAs done
         tc_fence_after();
-        if (tid == 0 && has_next) bulk_load(W1, a.img_o2, W16_BYTES, wbar1);
         {
             float v[32];
             tmem_ld32(accA + lane_off + (uint32_t)(ch * 32), v);
@@ -375,6 +449,7 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
         }
     }
 
+    TS_MARK();  // tiles done
     // ---------------- drain: weight-gradient accumulators and bias sums -> this CTA's partial ----------------
     mbar_wait(bar_w, ph_w);
     tc_fence_after();
@@ -397,13 +472,12 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
     // bias sums: the tile buffers are dead now, use B0 as scratch.  red_p[32 line groups][64], red_e[3][4 quadrants][64]
     float* red_p = reinterpret_cast<float*>(B0g);
     float* red_e = red_p + 32 * D;
-    __syncthreads();
+    compute_barrier();
 #pragma unroll
     for (int j = 0; j < 8; ++j) red_p[(tid >> 3) * D + (tid & 7) * 8 + j] = bsum_p[j];
 #pragma unroll
     for (int s = 0; s < 3; ++s) red_e[(s * 4 + q) * D + ch * 32 + lane] = bacc[s];
-    tc_fence_before();
-    __syncthreads();
+    compute_barrier();
     if (tid < D) {
         float t = 0.f;
 #pragma unroll
@@ -416,8 +490,23 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
         const int off = s == 0 ? (D * D + D) + D * D : s == 1 ? 2 * (D * D + D) + 2 * D * D : CONV_BWD_PART - D;
         part[off + c] = t;
     }
+    TS_MARK();  // drained
+    TS_DONE();
+    tc_fence_before();
+    __syncthreads();  // every warp, the MMA warp included
     if (warp == 0) tmem_dealloc(tm, 512);
 }
+
+#ifdef GCNN_CHAIN_TIMING
+extern "C" int gcnn_debug_chain_timing(long long* out, int cap) {  // timestamps of the last conv-backward launch
+    int n = 0;
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(&n, g_chain_n, sizeof(int));
+    n = n < cap ? n : cap;
+    cudaMemcpyFromSymbol(out, g_chain_ts, sizeof(long long) * n);
+    return n;
+}
+#endif
 
 int conv_backward_part_floats() { return CONV_BWD_PART; }
 
@@ -436,7 +525,7 @@ int tc_conv_backward(const ConvBwdArgs& a, int* n_parts, cudaStream_t st) {
         return (int)GCNN_OK;
     }();
     GCNN_TRY(once);
-    GCNN_LAUNCH(tc_conv_backward_kernel, parts, TC_THREADS, CONV_BWD_SMEM, st, a);
+    GCNN_LAUNCH(tc_conv_backward_kernel, parts, BWD_THREADS, CONV_BWD_SMEM, st, a);
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
 }
@@ -451,11 +540,10 @@ int tc_conv_backward(const ConvBwdArgs& a, int* n_parts, cudaStream_t st) {
 // The three weight images stay resident for the whole kernel.
 constexpr int EMB_BWD_PART = 4 * (D * D + D);  // W_0 | b_0 | W_1 | b_1 | W2 | b2 | W1 (64 rows, K valid) | b1
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(BWD_THREADS, 1)
 tc_embed_backward_kernel(const EmbBwdArgs a) {
-    pdl_enter();
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[3];  // 0: input-gradient MMAs, 1: weight-gradient MMAs, 2: weight images
+    __shared__ __align__(8) uint64_t bars[4];  // 0: input-gradient MMAs, 1: weight-gradient MMAs, 2: weight images, 3: tiles ready
     __shared__ uint32_t tmem_slot;
     __shared__ float sh_shift[16], sh_scale[16];
     const int tid = threadIdx.x, warp = warp_index(), lane = tid & 31;
@@ -467,33 +555,72 @@ tc_embed_backward_kernel(const EmbBwdArgs a) {
     const uint32_t B0 = base, B1 = base + T16_BYTES, B2 = base + 2 * T16_BYTES;
     const uint32_t W0 = base + 3 * T16_BYTES, W1 = W0 + W16_BYTES, W2 = W1 + W16_BYTES;
     const uint32_t bar_d = smem_u32(&bars[0]), bar_w = smem_u32(&bars[1]), wbar = smem_u32(&bars[2]);
+    const uint32_t bar_ready = smem_u32(&bars[3]);
     const bool two = a.dP1 != nullptr;
     const int K = a.K;
 
     if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), 512);
     if (tid == 0) {
-        for (int i = 0; i < 3; ++i) mbar_init(smem_u32(&bars[i]), 1);
-    }
-    if (tid < 16) {
-        sh_shift[tid] = tid < K ? a.shift[tid] : 0.f;
-        sh_scale[tid] = tid < K ? a.scale[tid] : 0.f;
+        for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&bars[i]), 1);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_enter();  // TMEM allocation and barrier setup above overlap the previous grid's tail
+    if (tid < 16) {  // (read by the compute warps after their first named barrier)
+        sh_shift[tid] = tid < K ? a.shift[tid] : 0.f;
+        sh_scale[tid] = tid < K ? a.scale[tid] : 0.f;
+    }
     const uint32_t tm = tmem_slot;
     const uint32_t accA = tm, acc_w0 = tm + 64, acc_w1 = tm + 128, acc_w2 = tm + 192, acc_wx = tm + 256;
-    if (tid == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(wbar), "r"((two ? 3u : 2u) * W16_BYTES) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(W0), "l"(a.img_p0), "r"(W16_BYTES), "r"(wbar) : "memory");
-        if (two)
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(W1), "l"(a.img_p1), "r"(W16_BYTES), "r"(wbar) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(W2), "l"(a.img_w2), "r"(W16_BYTES), "r"(wbar) : "memory");
-    }
     const int64_t n_tiles = ceil_div(a.M, TC_ROWS);
+    if (warp >= 8) {
+        // ================= MMA / weight-copy warp =================
+        regs_mma();
+        if (warp == 8 && elect_one()) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(wbar), "r"((two ? 3u : 2u) * W16_BYTES) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(W0), "l"(a.img_p0), "r"(W16_BYTES), "r"(wbar) : "memory");
+            if (two)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(W1), "l"(a.img_p1), "r"(W16_BYTES), "r"(wbar) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(W2), "l"(a.img_w2), "r"(W16_BYTES), "r"(wbar) : "memory");
+            uint32_t ph_r = 0;
+            int it = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const uint32_t wacc = it > 0 ? 1u : 0u;
+                // E0
+                mbar_wait(bar_ready, ph_r); ph_r ^= 1;
+                tc_fence_after();
+                if (it == 0) mbar_wait(wbar, 0);
+                issue_dgrad(accA, B0, W0, 0);
+                if (two) issue_dgrad(accA, B2, W1, 1);
+                umma_commit(bar_d);
+                issue_wgrad(acc_w0, B1, T16_BYTES, B0, wacc);
+                if (two) issue_wgrad(acc_w1, B1, T16_BYTES, B2, wacc);
+                umma_commit(bar_w);
+                // E1
+                mbar_wait(bar_ready, ph_r); ph_r ^= 1;
+                tc_fence_after();
+                issue_dgrad(accA, B0, W2, 0);
+                umma_commit(bar_d);
+                issue_wgrad(acc_w2, B2, T16_BYTES, B0, wacc);
+                umma_commit(bar_w);
+                // E2
+                mbar_wait(bar_ready, ph_r); ph_r ^= 1;
+                tc_fence_after();
+                issue_wgrad(acc_wx, B0, T16_BYTES, B1, wacc);
+                umma_commit(bar_w);
+            }
+        }
+        __syncwarp();
+        tc_fence_before();
+        __syncthreads();
+        return;
+    }
+    // ================= compute warps =================
+    regs_compute();
     const int q = warp & 3, ch = warp >> 2;
     const int r_own = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
@@ -514,7 +641,6 @@ tc_embed_backward_kernel(const EmbBwdArgs a) {
         const int64_t m_own = row0 + r_own;
         const bool row_ok = m_own < a.M;
         const bool has_next = tile + gridDim.x < n_tiles;
-        const uint32_t wacc = iter > 0 ? 1u : 0u;
 
         // ---------------- E0 ----------------
         if (iter > 0) { mbar_wait(bar_w, ph_w); ph_w ^= 1; }
@@ -529,19 +655,7 @@ tc_embed_backward_kernel(const EmbBwdArgs a) {
         store_tile(B0g, ra, 1.f, tid);
         store_tile(B1g, rb, 1.f, tid);
         if (two) store_tile(B2g, rc, 1.f, tid);
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-        if (warp == 0 && elect_one()) {
-            if (iter == 0) mbar_wait(wbar, 0);
-            issue_dgrad(accA, B0, W0, 0);
-            if (two) issue_dgrad(accA, B2, W1, 1);
-            umma_commit(bar_d);
-            issue_wgrad(acc_w0, B1, T16_BYTES, B0, wacc);
-            if (two) issue_wgrad(acc_w1, B1, T16_BYTES, B2, wacc);
-            umma_commit(bar_w);
-        }
+        publish_tiles(bar_ready, tid);
         load_tile(ra, a.h1, row0, a.M, tid);
         float4 dx[8];
 #pragma unroll
@@ -564,16 +678,7 @@ tc_embed_backward_kernel(const EmbBwdArgs a) {
         store_tile(B2g, ra, 1.f, tid);
 
         // ---------------- E1 ----------------
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-        if (warp == 0 && elect_one()) {
-            issue_dgrad(accA, B0, W2, 0);
-            umma_commit(bar_d);
-            issue_wgrad(acc_w2, B2, T16_BYTES, B0, wacc);
-            umma_commit(bar_w);
-        }
+        publish_tiles(bar_ready, tid);
         // raw input features of this thread's four (line, chunk) items: only chunks 0 and 1 can hold features (K <= 14)
         float xn[4][8];
 #pragma unroll
@@ -604,14 +709,7 @@ tc_embed_backward_kernel(const EmbBwdArgs a) {
             const int i = tid + it * TC_THREADS;
             store_chunk3(B0g, T16_PIECE, i >> 3, i & 7, xn[it]);
         }
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-        if (warp == 0 && elect_one()) {
-            issue_wgrad(acc_wx, B0, T16_BYTES, B1, wacc);
-            umma_commit(bar_w);
-        }
+        publish_tiles(bar_ready, tid);
         if (has_next) {
             const int64_t nrow0 = row0 + (int64_t)gridDim.x * TC_ROWS;
             load_tile(ra, a.dP0, nrow0, a.M, tid);
@@ -639,7 +737,7 @@ tc_embed_backward_kernel(const EmbBwdArgs a) {
     }
     float* red_p = reinterpret_cast<float*>(B0g);  // [2][32 line groups][64]
     float* red_e = red_p + 2 * 32 * D;             // [2][4 quadrants][64]
-    __syncthreads();
+    compute_barrier();
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         red_p[(tid >> 3) * D + (tid & 7) * 8 + j] = bsum0[j];
@@ -647,8 +745,7 @@ tc_embed_backward_kernel(const EmbBwdArgs a) {
     }
 #pragma unroll
     for (int s = 0; s < 2; ++s) red_e[(s * 4 + q) * D + ch * 32 + lane] = bacc[s];
-    tc_fence_before();
-    __syncthreads();
+    compute_barrier();
     {
         const int s = tid >> 6, c = tid & 63;  // s: 0 = b_0, 1 = b_1, 2 = b2, 3 = b1
         float t = 0.f;
@@ -662,6 +759,8 @@ tc_embed_backward_kernel(const EmbBwdArgs a) {
         }
         part[s * (D * D + D) + D * D + c] = t;
     }
+    tc_fence_before();
+    __syncthreads();  // every warp, the MMA warp included
     if (warp == 0) tmem_dealloc(tm, 512);
 }
 
@@ -682,7 +781,7 @@ int tc_embed_backward(const EmbBwdArgs& a, int* n_parts, cudaStream_t st) {
         return (int)GCNN_OK;
     }();
     GCNN_TRY(once);
-    GCNN_LAUNCH(tc_embed_backward_kernel, parts, TC_THREADS, CONV_BWD_SMEM, st, a);
+    GCNN_LAUNCH(tc_embed_backward_kernel, parts, BWD_THREADS, CONV_BWD_SMEM, st, a);
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
 }

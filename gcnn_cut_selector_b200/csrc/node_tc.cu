@@ -65,7 +65,6 @@ int pack_weights(const float* params, const int* block_offsets_dev, int n_blocks
 template <int K>
 __global__ void __launch_bounds__(TC_THREADS)
 tc_linear_kernel(const TcArgs a) {
-    pdl_enter();
     constexpr int KB = K / 32;                      // 32-float-wide K blocks
     constexpr uint32_t A_PART = KB * A_BLOCK_BYTES; // hi or lo part of the A tile
     constexpr uint32_t B_PART = KB * B_BLOCK_BYTES;
@@ -87,6 +86,7 @@ tc_linear_kernel(const TcArgs a) {
 
     if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), 64);
     if (tid == 0) mbar_init(smem_u32(&mma_bar), 1);
+    pdl_enter();  // TMEM allocation and barrier setup overlap the previous grid's tail; its data is read below
 
     // B: asynchronous copy (cp.async, no registers) of the packed weight image(s) for this slab, one per 64-wide K block
 #pragma unroll
@@ -263,7 +263,6 @@ __device__ __forceinline__ void issue_stage(uint32_t tmem_d, const uint32_t (&a_
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_conv_forward_kernel(const ConvFwdArgs a) {
-    pdl_enter();
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t mma_bar;
     __shared__ uint32_t tmem_slot;
@@ -281,6 +280,7 @@ tc_conv_forward_kernel(const ConvFwdArgs a) {
 
     if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), 64);
     if (tid == 0) mbar_init(smem_u32(&mma_bar), 1);
+    pdl_enter();  // TMEM allocation and barrier setup overlap the previous grid's tail; its data is read below
 
     // weights of S0 and S1
     copy_image_async(WB, a.img_f, tid);
@@ -397,7 +397,6 @@ int tc_conv_forward(const ConvFwdArgs& a, cudaStream_t st) {
 // h1 and out are also written to global memory (the backward pass and the concat of the convolutions read them).
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_embed_forward_kernel(const EmbFwdArgs a) {
-    pdl_enter();
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t mma_bar;
     __shared__ uint32_t tmem_slot;
@@ -422,6 +421,7 @@ tc_embed_forward_kernel(const EmbFwdArgs a) {
     const uint32_t P = base, Q = base + REG_BYTES, WA = base + 2 * REG_BYTES, WB = base + 2 * REG_BYTES + 2 * IMG_BYTES;
     if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), 64);
     if (tid == 0) mbar_init(smem_u32(&mma_bar), 1);
+    pdl_enter();  // TMEM allocation and barrier setup overlap the previous grid's tail; its data is read below
     copy_image_async(WB, a.img_w2, tid);
     copy_image_async(WA, a.img_p[0], tid);
     if (n_proj == 2) copy_image_async(WA + IMG_BYTES, a.img_p[1], tid);
@@ -543,7 +543,6 @@ constexpr uint32_t IDESC_TF32_MN_128x64 = IDESC_TF32_128x64 | (1u << 15) | (1u <
 template <int K>
 __global__ void __launch_bounds__(TC_THREADS)
 tc_wgrad_kernel(const TcWgradArgs a) {
-    pdl_enter();
     constexpr int KB = K / 32;
     constexpr uint32_t A_PART = KB * A_BLOCK_BYTES, B_PART = 2 * A_BLOCK_BYTES;
     constexpr int NA = TC_ROWS * (K / 4) / TC_THREADS;  // float4 loads of X per thread per tile (8 or 16)
@@ -565,6 +564,7 @@ tc_wgrad_kernel(const TcWgradArgs a) {
 
     if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), 64);
     if (tid == 0) mbar_init(smem_u32(&mma_bar), 1);
+    pdl_enter();  // TMEM allocation and barrier setup overlap the previous grid's tail; its data is read below
     tc_fence_before();
     __syncthreads();
     tc_fence_after();

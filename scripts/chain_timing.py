@@ -1,0 +1,50 @@
+"""Stage timing of the fused backward chain: builds an instrumented copy of the library (-DGCNN_CHAIN_TIMING), runs
+train steps on the bench workload and prints the clock64() deltas thread 0 of CTA 0 recorded in its first tiles.
+Usage (GPU box): python scripts/chain_timing.py"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+PKG = os.path.join(ROOT, "gcnn_cut_selector_b200")
+OUT = os.path.join(PKG, "build", "libgcnn_b200_timing.so")
+
+
+def build():
+    from gcnn_cut_selector_b200 import build as b
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    flags = [f for f in b.NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    srcs = [os.path.join(b.CSRC, s) for s in b.SOURCES]
+    subprocess.run(["/usr/local/cuda/bin/nvcc", *flags, "-DGCNN_CHAIN_TIMING", "-shared", "-o", OUT, *srcs, "-cudart", "static"],
+                   check=True)
+
+
+if __name__ == "__main__":
+    if "--build" in sys.argv or not os.path.exists(OUT):
+        build()
+    if "--build-only" in sys.argv:
+        sys.exit(0)
+    os.environ["GCNN_LIB"] = OUT
+    import torch
+    import bench
+    from gcnn_cut_selector_b200 import GCNN, _lib, batching
+    dev = torch.device("cuda:0")
+    model = GCNN(device=dev, seed=0)
+    model.check_indices = False
+    batches = bench.make_batches(2, 32, seed0=0)
+    inputs = [model.prepare_inputs(batching.model_inputs(b, per_sample_counts=True)) for b in batches]
+    targets = [torch.from_numpy(b[10]).to(dev) for b in batches]
+    for i in range(4):
+        model.loss_and_grads(inputs[i % 2], targets[i % 2])
+        model.apply_gradients(1e-4)
+    torch.cuda.synchronize()
+    lib = _lib.load()
+    lib.gcnn_debug_chain_timing.restype = C.c_int
+    buf = (C.c_longlong * 64)()
+    n = lib.gcnn_debug_chain_timing(buf, 64)
+    ts = [buf[i] for i in range(n)]
+    print("marks:", n)
+    for i in range(1, n):
+        print(f"  {i:2d}: +{ts[i] - ts[i - 1]:7d} cycles  (t={ts[i] - ts[0]})")
