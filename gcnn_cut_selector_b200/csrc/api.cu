@@ -97,9 +97,16 @@ struct gcnn_workspace {
     int use_fused_bwd = 1;
     // stats
     double *st_partials, *st_out, *st_center;
-    // host staging mirrors (device side)
-    float *s_cons, *s_cef, *s_var, *s_cut, *s_kef, *s_targets;
-    int32_t *s_cei, *s_kei;
+    // host staging mirrors (device side), two slots: batch i + 1 is copied in on the library's copy stream while the
+    // step on batch i runs (the reference's loader prefetches one batch the same way, model_trainer.py:153)
+    struct Stage {
+        float *cons, *cef, *var, *cut, *kef, *targets;
+        int32_t *cei, *kei;
+        gcnn_batch meta{};        // the staged batch with DEVICE pointers into this slot
+        cudaEvent_t staged = nullptr, consumed = nullptr;
+        int valid = 0;
+    } stage[2];
+    cudaStream_t copy_st = nullptr;
     // auxiliary streams: independent kernels (CSR build, the two projections of a convolution, weight gradients) run
     // concurrently with the main chain; fork/join with events, nothing synchronises the host
     int use_streams = 1;
@@ -202,14 +209,18 @@ static size_t carve(gcnn_workspace* ws, char* base, const Caps& c) {
     ws->st_out = cv.take<double>(2 * D);
     ws->st_center = cv.take<double>(D);
 
-    ws->s_cons = cv.take<float>(nc * GCNN_CONS_FEATS);
-    ws->s_cei = cv.take<int32_t>(2 * ec);
-    ws->s_cef = cv.take<float>(ec);
-    ws->s_var = cv.take<float>(nv * GCNN_VAR_FEATS);
-    ws->s_cut = cv.take<float>(nk * GCNN_CUT_FEATS);
-    ws->s_kei = cv.take<int32_t>(2 * ek);
-    ws->s_kef = cv.take<float>(ek);
-    ws->s_targets = cv.take<float>(nk);
+    for (int s = 0; s < 2; ++s) {
+        gcnn_workspace::Stage& g = ws->stage[s];
+        g.cons = cv.take<float>(nc * GCNN_CONS_FEATS);
+        g.cei = cv.take<int32_t>(2 * ec);
+        g.cef = cv.take<float>(ec);
+        g.var = cv.take<float>(nv * GCNN_VAR_FEATS);
+        g.cut = cv.take<float>(nk * GCNN_CUT_FEATS);
+        g.kei = cv.take<int32_t>(2 * ek);
+        g.kef = cv.take<float>(ek);
+        g.targets = cv.take<float>(nk);
+        g.valid = 0;
+    }
 
     ws->tile_cap = (nc + nv + nk) / 16 + 8192;
     for (int i = 0; i < 3; ++i) ws->d_tiles[i] = cv.take<EdgeTile>(ws->tile_cap);
@@ -752,18 +763,24 @@ static int h2d(void* dst, const void* src, size_t bytes, cudaStream_t st) {
     return GCNN_OK;
 }
 
-static int stage_batch(gcnn_workspace* ws, const gcnn_batch* hb, gcnn_batch* db, cudaStream_t st) {
-    *db = *hb;
-    GCNN_TRY(h2d(ws->s_cons, hb->cons_feats, sizeof(float) * hb->n_cons * GCNN_CONS_FEATS, st));
-    GCNN_TRY(h2d(ws->s_cei, hb->cons_edge_inds, sizeof(int32_t) * 2 * hb->n_cons_edges, st));
-    GCNN_TRY(h2d(ws->s_cef, hb->cons_edge_feats, sizeof(float) * hb->n_cons_edges, st));
-    GCNN_TRY(h2d(ws->s_var, hb->var_feats, sizeof(float) * hb->n_vars * GCNN_VAR_FEATS, st));
-    GCNN_TRY(h2d(ws->s_cut, hb->cut_feats, sizeof(float) * hb->n_cuts * GCNN_CUT_FEATS, st));
-    GCNN_TRY(h2d(ws->s_kei, hb->cut_edge_inds, sizeof(int32_t) * 2 * hb->n_cut_edges, st));
-    GCNN_TRY(h2d(ws->s_kef, hb->cut_edge_feats, sizeof(float) * hb->n_cut_edges, st));
-    db->cons_feats = ws->s_cons; db->cons_edge_inds = ws->s_cei; db->cons_edge_feats = ws->s_cef;
-    db->var_feats = ws->s_var; db->cut_feats = ws->s_cut; db->cut_edge_inds = ws->s_kei;
-    db->cut_edge_feats = ws->s_kef;
+// Copies a host batch into staging slot `slot` on the copy stream; the slot's previous consumer must have finished.
+static int stage_batch(gcnn_workspace* ws, int slot, const gcnn_batch* hb, const float* targets_host) {
+    gcnn_workspace::Stage& g = ws->stage[slot];
+    cudaStream_t cs = ws->copy_st;
+    if (g.valid) GCNN_CUDA_TRY(cudaStreamWaitEvent(cs, g.consumed, 0));
+    GCNN_TRY(h2d(g.cons, hb->cons_feats, sizeof(float) * hb->n_cons * GCNN_CONS_FEATS, cs));
+    GCNN_TRY(h2d(g.cei, hb->cons_edge_inds, sizeof(int32_t) * 2 * hb->n_cons_edges, cs));
+    GCNN_TRY(h2d(g.cef, hb->cons_edge_feats, sizeof(float) * hb->n_cons_edges, cs));
+    GCNN_TRY(h2d(g.var, hb->var_feats, sizeof(float) * hb->n_vars * GCNN_VAR_FEATS, cs));
+    GCNN_TRY(h2d(g.cut, hb->cut_feats, sizeof(float) * hb->n_cuts * GCNN_CUT_FEATS, cs));
+    GCNN_TRY(h2d(g.kei, hb->cut_edge_inds, sizeof(int32_t) * 2 * hb->n_cut_edges, cs));
+    GCNN_TRY(h2d(g.kef, hb->cut_edge_feats, sizeof(float) * hb->n_cut_edges, cs));
+    if (targets_host) GCNN_TRY(h2d(g.targets, targets_host, sizeof(float) * hb->n_cuts, cs));
+    GCNN_CUDA_TRY(cudaEventRecord(g.staged, cs));
+    g.meta = *hb;
+    g.meta.cons_feats = g.cons; g.meta.cons_edge_inds = g.cei; g.meta.cons_edge_feats = g.cef;
+    g.meta.var_feats = g.var; g.meta.cut_feats = g.cut; g.meta.cut_edge_inds = g.kei; g.meta.cut_edge_feats = g.kef;
+    g.valid = 1;
     return GCNN_OK;
 }
 
@@ -887,6 +904,11 @@ int gcnn_workspace_create(gcnn_workspace** out) {
     for (int i = 0; i < 2; ++i) GCNN_CUDA_TRY(cudaStreamCreateWithFlags(&ws->aux[i], cudaStreamNonBlocking));
     for (int i = 0; i < 16; ++i) GCNN_CUDA_TRY(cudaEventCreateWithFlags(&ws->ev[i], cudaEventDisableTiming));
     for (int i = 0; i < 4; ++i) GCNN_CUDA_TRY(cudaEventCreateWithFlags(&ws->ev_layout[i], cudaEventDisableTiming));
+    GCNN_CUDA_TRY(cudaStreamCreateWithFlags(&ws->copy_st, cudaStreamNonBlocking));
+    for (int s = 0; s < 2; ++s) {
+        GCNN_CUDA_TRY(cudaEventCreateWithFlags(&ws->stage[s].staged, cudaEventDisableTiming));
+        GCNN_CUDA_TRY(cudaEventCreateWithFlags(&ws->stage[s].consumed, cudaEventDisableTiming));
+    }
     *out = ws;
     return GCNN_OK;
 }
@@ -897,6 +919,11 @@ int gcnn_workspace_destroy(gcnn_workspace* ws) {
     for (int i = 0; i < 2; ++i) if (ws->aux[i]) cudaStreamDestroy(ws->aux[i]);
     for (int i = 0; i < 16; ++i) if (ws->ev[i]) cudaEventDestroy(ws->ev[i]);
     for (int i = 0; i < 4; ++i) if (ws->ev_layout[i]) cudaEventDestroy(ws->ev_layout[i]);
+    if (ws->copy_st) cudaStreamDestroy(ws->copy_st);
+    for (int s = 0; s < 2; ++s) {
+        if (ws->stage[s].staged) cudaEventDestroy(ws->stage[s].staged);
+        if (ws->stage[s].consumed) cudaEventDestroy(ws->stage[s].consumed);
+    }
     delete ws;
     return GCNN_OK;
 }
@@ -1120,38 +1147,74 @@ int gcnn_prenorm_stats(gcnn_workspace* ws, const float* params, const float* pre
     return GCNN_OK;
 }
 
-int gcnn_score_host(gcnn_workspace* ws, const float* params, const float* prenorm, const gcnn_batch* hb,
-                    float* scores_host, void* stream) {
-    GCNN_TRY(check_batch(ws, hb, 0));
+int gcnn_stage_host_batch(gcnn_workspace* ws, int slot, const gcnn_batch* hb, const float* targets_host) {
+    if (slot < 0 || slot > 1) { set_error("staging slot must be 0 or 1"); return GCNN_INVALID; }
+    GCNN_TRY(check_batch(ws, hb, targets_host ? 1 : 0));
+    return stage_batch(ws, slot, hb, targets_host);
+}
+
+int gcnn_score_staged(gcnn_workspace* ws, int slot, const float* params, const float* prenorm, float* scores_host,
+                      void* stream) {
+    if (!ws || slot < 0 || slot > 1 || !ws->stage[slot].valid) { set_error("no batch staged in this slot"); return GCNN_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
-    gcnn_batch db;
-    GCNN_TRY(stage_batch(ws, hb, &db, st));
-    GCNN_TRY(forward_impl(ws, params, prenorm, &db, ws->scores, -1, st));
+    gcnn_workspace::Stage& g = ws->stage[slot];
+    GCNN_TRY(check_batch(ws, &g.meta, 0));
+    GCNN_CUDA_TRY(cudaStreamWaitEvent(st, g.staged, 0));
+    GCNN_TRY(forward_impl(ws, params, prenorm, &g.meta, ws->scores, -1, st));
     ws->have_activations = 0;
-    if (hb->n_cuts > 0)
-        GCNN_CUDA_TRY(cudaMemcpyAsync(scores_host, ws->scores, sizeof(float) * hb->n_cuts, cudaMemcpyDeviceToHost, st));
+    GCNN_CUDA_TRY(cudaEventRecord(g.consumed, st));
+    if (g.meta.n_cuts > 0)
+        GCNN_CUDA_TRY(cudaMemcpyAsync(scores_host, ws->scores, sizeof(float) * g.meta.n_cuts, cudaMemcpyDeviceToHost, st));
     return read_error_flag(ws, st);
 }
 
-int gcnn_train_step_host(gcnn_workspace* ws, float* params, const float* prenorm, float* adam_m, float* adam_v,
-                         const gcnn_batch* hb, const float* targets_host, float lr, int64_t step, float* loss_host,
-                         void* stream) {
-    GCNN_TRY(check_batch(ws, hb, 1));
+int gcnn_train_step_staged(gcnn_workspace* ws, int slot, float* params, const float* prenorm, float* adam_m,
+                           float* adam_v, float lr, int64_t step, float* loss_host, void* stream) {
+    if (!ws || slot < 0 || slot > 1 || !ws->stage[slot].valid) { set_error("no batch staged in this slot"); return GCNN_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
-    gcnn_batch db;
-    GCNN_TRY(stage_batch(ws, hb, &db, st));
-    GCNN_TRY(h2d(ws->s_targets, targets_host, sizeof(float) * hb->n_cuts, st));
-    // gradients land in the first trainable-sized slice of the (otherwise idle) dS scratch? No: keep them separate.
+    gcnn_workspace::Stage& g = ws->stage[slot];
+    GCNN_TRY(check_batch(ws, &g.meta, 1));
+    GCNN_CUDA_TRY(cudaStreamWaitEvent(st, g.staged, 0));
     float* grads = ws->partials[31];
-    const float scale = hb->n_cuts > 0 ? 1.f / (float)hb->n_cuts : 0.f;
-    GCNN_TRY(gcnn_forward_backward(ws, params, prenorm, &db, ws->s_targets, scale, nullptr, grads, ws->loss_sum, st));
+    const int64_t nk = g.meta.n_cuts;
+    const float scale = nk > 0 ? 1.f / (float)nk : 0.f;
+    GCNN_TRY(gcnn_forward_backward(ws, params, prenorm, &g.meta, g.targets, scale, nullptr, grads, ws->loss_sum, st));
+    GCNN_CUDA_TRY(cudaEventRecord(g.consumed, st));
     GCNN_TRY(gcnn_adam_step(params, grads, adam_m, adam_v, GCNN_N_TRAINABLE, lr, 0.9f, 0.999f, 1e-7f, step, nullptr,
                             st));
     float loss_sum = 0.f;
     GCNN_CUDA_TRY(cudaMemcpyAsync(&loss_sum, ws->loss_sum, sizeof(float), cudaMemcpyDeviceToHost, st));
     GCNN_TRY(read_error_flag(ws, st));
-    if (loss_host) *loss_host = hb->n_cuts > 0 ? loss_sum / (float)hb->n_cuts : 0.f;
+    if (loss_host) *loss_host = nk > 0 ? loss_sum / (float)nk : 0.f;
     return GCNN_OK;
+}
+
+int gcnn_staged_batch(gcnn_workspace* ws, int slot, gcnn_batch* out, float** targets_dev, void* stream) {
+    if (!ws || slot < 0 || slot > 1 || !ws->stage[slot].valid || !out) { set_error("no batch staged in this slot"); return GCNN_INVALID; }
+    GCNN_CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, ws->stage[slot].staged, 0));
+    *out = ws->stage[slot].meta;
+    if (targets_dev) *targets_dev = ws->stage[slot].targets;
+    return GCNN_OK;
+}
+
+int gcnn_release_staged(gcnn_workspace* ws, int slot, void* stream) {
+    if (!ws || slot < 0 || slot > 1) { set_error("staging slot must be 0 or 1"); return GCNN_INVALID; }
+    GCNN_CUDA_TRY(cudaEventRecord(ws->stage[slot].consumed, (cudaStream_t)stream));
+    return GCNN_OK;
+}
+
+int gcnn_score_host(gcnn_workspace* ws, const float* params, const float* prenorm, const gcnn_batch* hb,
+                    float* scores_host, void* stream) {
+    GCNN_TRY(gcnn_stage_host_batch(ws, 0, hb, nullptr));
+    return gcnn_score_staged(ws, 0, params, prenorm, scores_host, stream);
+}
+
+int gcnn_train_step_host(gcnn_workspace* ws, float* params, const float* prenorm, float* adam_m, float* adam_v,
+                         const gcnn_batch* hb, const float* targets_host, float lr, int64_t step, float* loss_host,
+                         void* stream) {
+    if (!targets_host) { set_error("null targets"); return GCNN_INVALID; }
+    GCNN_TRY(gcnn_stage_host_batch(ws, 0, hb, targets_host));
+    return gcnn_train_step_staged(ws, 0, params, prenorm, adam_m, adam_v, lr, step, loss_host, stream);
 }
 
 int gcnn_edge_forward(const int32_t* ptr, const int32_t* src, const float* val, int64_t n_recv, const float* R,

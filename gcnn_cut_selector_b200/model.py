@@ -155,6 +155,7 @@ class GCNN:
         self._prenorm_layers = self._make_prenorm_layers()
         self.call = self._call  # re-assignable like ``model.call = tf.function(model.call, ...)`` (model_trainer.py:144)
 
+        self._staged = [None, None]
         # optimiser state for the fused train step (Keras Adam, model_trainer.py:131)
         self.adam_m = torch.zeros_like(self.flat_grads)
         self.adam_v = torch.zeros_like(self.flat_grads)
@@ -358,6 +359,42 @@ class GCNN:
                                              host_batch.targets.data_ptr(), lr, self.adam_step, C.byref(loss),
                                              self._stream()))
         return float(loss.value)
+
+    # ---- prefetching host path: batch i + 1 is copied in while the step on batch i runs (model_trainer.py:153) ------
+    def stage_host(self, host_batch: "HostBatch", slot: int, training: bool = True):
+        """Enqueue the host-to-device copies of ``host_batch`` into staging slot 0/1 (returns immediately)."""
+        b = host_batch.batch
+        self.reserve(b, training)
+        tgt = host_batch.targets.data_ptr() if training else None
+        check(self._lib.gcnn_stage_host_batch(self._ws, slot, C.byref(b), tgt))
+        self._staged[slot] = host_batch  # keeps the pinned buffers alive until the slot is consumed
+
+    def train_step_staged(self, slot: int, lr: float) -> float:
+        """Optimisation step on the batch staged in ``slot``; returns the mean loss (host float)."""
+        self.adam_step += 1
+        loss = C.c_float()
+        check(self._lib.gcnn_train_step_staged(self._ws, slot, self.flat_params.data_ptr(), self.flat_prenorm.data_ptr(),
+                                               self.adam_m.data_ptr(), self.adam_v.data_ptr(), lr, self.adam_step,
+                                               C.byref(loss), self._stream()))
+        return float(loss.value)
+
+    def loss_and_grads_staged(self, slot: int, seed_scale: float | None = None):
+        """``loss_and_grads`` on the batch staged in ``slot`` (data-parallel trainer).  Returns (loss_sum, n_cuts)."""
+        batch, tgt = Batch(), C.c_void_p()
+        check(self._lib.gcnn_staged_batch(self._ws, slot, C.byref(batch), C.byref(tgt), self._stream()))
+        scale = (1.0 / max(batch.n_cuts, 1)) if seed_scale is None else float(seed_scale)
+        check(self._lib.gcnn_forward_backward(self._ws, self.flat_params.data_ptr(), self.flat_prenorm.data_ptr(),
+                                              C.byref(batch), tgt, scale, None, self.flat_grads.data_ptr(),
+                                              self._loss_sum.data_ptr(), self._stream()))
+        check(self._lib.gcnn_release_staged(self._ws, slot, self._stream()))
+        return self._loss_sum, int(batch.n_cuts)
+
+    def score_staged(self, slot: int) -> np.ndarray:
+        """Cut scores of the batch staged in ``slot`` (inference), as a host array."""
+        out = self._staged[slot].scores
+        check(self._lib.gcnn_score_staged(self._ws, slot, self.flat_params.data_ptr(), self.flat_prenorm.data_ptr(),
+                                          out.data_ptr(), self._stream()))
+        return out.numpy()
 
     def score_host(self, host_batch: "HostBatch") -> np.ndarray:
         """Cut scoring from host buffers to a host array (the ``get_improvements(state, False).numpy()`` path of

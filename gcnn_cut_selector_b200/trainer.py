@@ -46,3 +46,13 @@ class DataParallelTrainer:
         reduce_bucket(self.bucket, self.group)
         m.apply_gradients(self.lr, grad_divisor=self.bucket[self.N:self.N + 1])
         return self.bucket[self.N + 1:self.N + 2] / self.bucket[self.N:self.N + 1]
+
+    def step_staged(self, slot: int):
+        """``step`` on the host batch staged in ``slot`` (GCNN.stage_host): its copy overlapped the previous step."""
+        m = self.model
+        loss_sum, n_cuts = m.loss_and_grads_staged(slot, seed_scale=1.0)
+        self.bucket[self.N] = float(n_cuts)
+        self.bucket[self.N + 1:self.N + 2].copy_(loss_sum)
+        reduce_bucket(self.bucket, self.group)
+        m.apply_gradients(self.lr, grad_divisor=self.bucket[self.N:self.N + 1])
+        return self.bucket[self.N + 1:self.N + 2] / self.bucket[self.N:self.N + 1]

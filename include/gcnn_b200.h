@@ -155,6 +155,20 @@ int gcnn_train_step_host(gcnn_workspace* ws, float* params, const float* prenorm
                          const gcnn_batch* host_batch, const float* targets_host, float lr, int64_t step,
                          float* loss_host, void* stream);
 
+/* Prefetching variants: the reference's loader keeps one batch in flight (tf.data prefetch(1), model_trainer.py:153).
+ * gcnn_stage_host_batch enqueues the host-to-device copies of a batch into staging slot 0 or 1 on a library-owned
+ * copy stream and returns immediately (host buffers must stay valid and pinned until the slot is consumed);
+ * the *_staged calls run on the staged batch, so the copy of batch i + 1 overlaps the step on batch i.
+ * gcnn_staged_batch hands out the slot's device-side batch descriptor, for callers that run forward/backward themselves, e.g.
+ * the data-parallel trainer; such callers mark the slot reusable with gcnn_release_staged. */
+int gcnn_stage_host_batch(gcnn_workspace* ws, int slot, const gcnn_batch* host_batch, const float* targets_host);
+int gcnn_score_staged(gcnn_workspace* ws, int slot, const float* params, const float* prenorm, float* scores_host,
+                      void* stream);
+int gcnn_train_step_staged(gcnn_workspace* ws, int slot, float* params, const float* prenorm, float* adam_m,
+                           float* adam_v, float lr, int64_t step, float* loss_host, void* stream);
+int gcnn_staged_batch(gcnn_workspace* ws, int slot, gcnn_batch* out, float** targets_dev, void* stream);
+int gcnn_release_staged(gcnn_workspace* ws, int slot, void* stream);
+
 /* ---- per-op entry points (unit parity tests; same kernels the whole-model calls launch) ---------------------- */
 /* H[t] = sum_{e in seg(t)} relu(s_f * (R[t] + f_e * w + S[src_e])), cnt[t] = number of active terms per feature.
  * ptr/src/val describe segments grouped by the receiving node.  f_e = (val + f_shift) * f_scale. */

@@ -474,6 +474,30 @@ def test_host_entry_points_match_device_path(golden_dir):
     torch.testing.assert_close(a.flat_params.detach(), b.flat_params.detach(), rtol=0, atol=0)
 
 
+def test_prefetching_host_path_matches_synchronous_path(golden_dir):
+    """Three train steps and a scoring call with one batch kept in flight (stage slot i + 1, then step on slot i) give
+    bit-identical parameters, losses and scores to the one-batch-at-a-time host calls."""
+    from gcnn_cut_selector_b200 import GCNN, HostBatch
+    path = os.path.join(golden_dir, "state_stream.pkl")
+    batches = [batching.concat_samples(synth.make_samples("setcov", 2 + i, seed0=20 + i)) for i in range(3)]
+    a, b = GCNN(device="cuda:0", seed=3), GCNN(device="cuda:0", seed=4)
+    a.restore_state(path); b.restore_state(path)
+    ha, hb = [HostBatch(x) for x in batches], [HostBatch(x) for x in batches]
+    for h in hb:  # reserve for the largest batch first: growing the workspace invalidates staged slots
+        b.reserve(h.batch, True)
+    losses_a = [a.train_step_host(h, 1e-3) for h in ha]
+    b.stage_host(hb[0], 0)
+    losses_b = []
+    for i in range(3):
+        if i + 1 < 3:
+            b.stage_host(hb[i + 1], (i + 1) & 1)
+        losses_b.append(b.train_step_staged(i & 1, 1e-3))
+    assert losses_a == losses_b
+    torch.testing.assert_close(a.flat_params.detach(), b.flat_params.detach(), rtol=0, atol=0)
+    b.stage_host(hb[1], 0, training=False)
+    np.testing.assert_array_equal(b.score_staged(0), a.score_host(ha[1]))
+
+
 # ---- full BASELINE sizes: size-independent properties -----------------------------------------------------------------
 def test_config2_properties(model):
     """32 setcov graphs (BASELINE config 2): block-diagonality -> the batch equals its two halves; bit-reproducible."""
