@@ -123,29 +123,32 @@ __device__ __forceinline__ void publish_tiles(uint32_t bar_ready, int tid) {
 }
 
 // ---- tile movement -------------------------------------------------------------------------------------------------
-// load mapping: item i = tid + 256 it covers line i >> 3, 8-float chunk i & 7 (a warp reads 1 KB of consecutive memory)
+// load mapping: float4 i = tid + 256 it (it = 0..7) is floats [4 (i & 15), +4) of line i >> 4, so every warp instruction
+// reads 512 contiguous bytes (two whole rows).  A thread's four floats become one 8-byte half chunk in each bf16 piece.
 __device__ __forceinline__ void load_tile(float4 (&reg)[8], const float* __restrict__ src, int64_t row0, int64_t M,
                                           int tid) {
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
+    for (int it = 0; it < 8; ++it) {
         const int i = tid + it * TC_THREADS;
-        const int64_t m = row0 + (i >> 3);
-        reg[2 * it] = reg[2 * it + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (m < M) {
-            const float* p = src + m * D + (i & 7) * 8;
-            reg[2 * it] = ldg_stream4(p);
-            reg[2 * it + 1] = ldg_stream4(p + 4);
-        }
+        const int64_t m = row0 + (i >> 4);
+        reg[it] = m < M ? ldg_stream4(src + m * D + (i & 15) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+}
+__device__ __forceinline__ void store_half_chunk3(uint8_t* tile, int line, int f4, float4 v) {
+    uint2 q0, q1, q2;
+    split3_pair(v.x, v.y, q0.x, q1.x, q2.x);
+    split3_pair(v.z, v.w, q0.y, q1.y, q2.y);
+    const uint32_t off = t16_chunk_off(line, f4 >> 1) + (uint32_t)(f4 & 1) * 8u;
+    *reinterpret_cast<uint2*>(tile + off) = q0;
+    *reinterpret_cast<uint2*>(tile + T16_PIECE + off) = q1;
+    *reinterpret_cast<uint2*>(tile + 2 * T16_PIECE + off) = q2;
 }
 __device__ __forceinline__ void store_tile(uint8_t* tile, const float4 (&reg)[8], float scale, int tid) {
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
+    for (int it = 0; it < 8; ++it) {
         const int i = tid + it * TC_THREADS;
-        const float4 x = reg[2 * it], y = reg[2 * it + 1];
-        const float v[8] = {x.x * scale, x.y * scale, x.z * scale, x.w * scale,
-                            y.x * scale, y.y * scale, y.z * scale, y.w * scale};
-        store_chunk3(tile, T16_PIECE, i >> 3, i & 7, v);
+        const float4 x = reg[it];
+        store_half_chunk3(tile, i >> 4, i & 15, make_float4(x.x * scale, x.y * scale, x.z * scale, x.w * scale));
     }
 }
 // epilogue mapping: a thread owns line `r`, columns [32 ch, 32 ch + 32)
@@ -172,6 +175,32 @@ __device__ __forceinline__ void mask_row32(const uint8_t* act_tile, int r, int c
         }
     }
 }
+// Coalesced global stores of an accumulator block.  After tcgen05.ld a lane holds 32 consecutive floats of ONE row, so
+// a direct store makes every warp instruction touch 32 different rows (32 separate 16-byte pieces).  Each warp instead
+// transposes its 32 rows x 128 bytes through a private 4 KB shared-memory patch (16-byte chunks XOR-swizzled by the row:
+// conflict-free both ways) and writes 4 rows x 128 contiguous bytes per instruction.  In the read-back mapping lane l
+// handles row 4 i + (l >> 3), floats [4 (l & 7), +4) of the block for i = 0..7; `op(i, row, x)` may transform the value.
+template <typename Op>
+__device__ __forceinline__ void warp_store_block(uint8_t* patch, const float (&v)[32], float* gblock, int rows_valid,
+                                                 int lane, Op op) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(patch + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = 4 * i + (lane >> 3);
+        float4 x = *reinterpret_cast<const float4*>(patch + r * 128 + (((lane & 7) ^ (r & 7)) << 4));
+        x = op(i, r, x);
+        if (r < rows_valid) *reinterpret_cast<float4*>(gblock + (int64_t)r * D + (lane & 7) * 4) = x;
+    }
+    __syncwarp();
+}
+struct StoreIdentity {
+    __device__ __forceinline__ float4 operator()(int, int, float4 x) const { return x; }
+};
+
 // Column sums over the 32 lanes of a warp by recursive halving: lane l returns sum over lanes of v[l].  Fixed order.
 __device__ __forceinline__ float warp_colsum32(const float (&v)[32], int lane) {
     float t[16];
@@ -317,7 +346,7 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
 
     float4 ra[8], rb[8];            // register staging of the next activation tiles (load mapping)
-    float bsum_p[8] = {};           // column sums of dP (load mapping: columns 8 (tid & 7) .. +8)
+    float bsum_p[4] = {};           // column sums of dP (load mapping: columns 4 (tid & 15) .. +4)
     float bacc[3] = {0.f, 0.f, 0.f};  // column sums of dU2, dU1, deg * dC (epilogue mapping: column 32 ch + lane)
     uint32_t ph_d = 0, ph_w = 0;
     TS_MARK();  // prologue done (TMEM, barriers, role split, registers)
@@ -336,10 +365,8 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
         TS_MARK();  // tile start
         if (iter > 0) { mbar_wait(bar_w, ph_w); ph_w ^= 1; }  // S0 of the previous tile has drained: B0, B1 are free
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-            const float4 x = ra[2 * it], y = ra[2 * it + 1];
-            bsum_p[0] += x.x; bsum_p[1] += x.y; bsum_p[2] += x.z; bsum_p[3] += x.w;
-            bsum_p[4] += y.x; bsum_p[5] += y.y; bsum_p[6] += y.z; bsum_p[7] += y.w;
+        for (int it = 0; it < 8; ++it) {
+            bsum_p[0] += ra[it].x; bsum_p[1] += ra[it].y; bsum_p[2] += ra[it].z; bsum_p[3] += ra[it].w;
         }
         store_tile(B0g, ra, 1.f, tid);
         store_tile(B1g, rb, 1.f, tid);
@@ -398,21 +425,19 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
         TS_MARK();  // input-gradient MMAs done
         tc_fence_after();
         {
-            float v[32], x[32];
-            tmem_ld32(accB + lane_off + (uint32_t)(ch * 32), x);
-            if (row_ok) {
-                float* dst = a.dXt + m_own * D + ch * 32;
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-            }
+            float v[32], x[32], dxt[32];
+            tmem_ld32(accB + lane_off + (uint32_t)(ch * 32), dxt);
             tmem_ld32(accA + lane_off + (uint32_t)(ch * 32), v);
 #pragma unroll
             for (int i = 0; i < 32; ++i) { v[i] *= s_p; x[i] = v[i] * deg; }
             bacc[2] += warp_colsum32(x, lane);
             mbar_wait(bar_w, ph_w); ph_w ^= 1;  // B0, B1, B2 are free
-        TS_MARK();  // weight-gradient MMAs done
+            TS_MARK();  // weight-gradient MMAs done
             store_row32(B1g, r_own, ch, v);
+            // dXt leaves through this warp's patch of B2 (X_t is dead): coalesced 128-byte row pieces
+            const int64_t wrow0 = row0 + q * 32;
+            const int rows_valid = (int)max((int64_t)0, min((int64_t)32, a.M - wrow0));
+            warp_store_block(B2g + warp * 4096, dxt, a.dXt + wrow0 * D + ch * 32, rows_valid, lane, StoreIdentity());
         }
         store_tile(B0g, ra, 1.f, tid);
 
@@ -420,10 +445,16 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
         TS_MARK();  // tiles stored
         publish_tiles(bar_ready, tid);
         TS_MARK();  // published
-        float4 cn[8];  // active-edge counts of this thread's row (epilogue mapping)
+        // active-edge counts in the coalesced store mapping (row 4 i + (lane >> 3) of this warp's 32, 4 floats at 4 (lane & 7))
+        const int64_t wrow0 = row0 + q * 32;
+        const int rows_valid = (int)max((int64_t)0, min((int64_t)32, a.M - wrow0));
+        float4 cn[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-            cn[j] = row_ok ? ldg_stream4(a.cnt + m_own * D + ch * 32 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + (lane >> 3);
+            cn[i] = r < rows_valid ? ldg_stream4(a.cnt + (wrow0 + r) * D + ch * 32 + (lane & 7) * 4)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         if (has_next) {
             load_tile(ra, a.dP, row0 + (int64_t)gridDim.x * TC_ROWS, a.M, tid);
             load_tile(rb, a.Y, row0 + (int64_t)gridDim.x * TC_ROWS, a.M, tid);
@@ -435,17 +466,15 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
         {
             float v[32];
             tmem_ld32(accA + lane_off + (uint32_t)(ch * 32), v);
-            if (row_ok) {
-                float* g = a.G + m_own * D + ch * 32;
-                float* dr = a.dR + m_own * D + ch * 32;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 y = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    *reinterpret_cast<float4*>(g + 4 * j) = y;
-                    *reinterpret_cast<float4*>(dr + 4 * j) =
-                        make_float4(s_f * y.x * cn[j].x, s_f * y.y * cn[j].y, s_f * y.z * cn[j].z, s_f * y.w * cn[j].w);
-                }
-            }
+            float* dr = a.dR + wrow0 * D + ch * 32;
+            // G and dR = s_f G cnt through this warp's patch of B2 (free since S1's weight-gradient MMAs drained)
+            warp_store_block(B2g + warp * 4096, v, a.G + wrow0 * D + ch * 32, rows_valid, lane,
+                             [&](int i, int r, float4 x) {
+                                 if (r < rows_valid)
+                                     *reinterpret_cast<float4*>(dr + (int64_t)r * D + (lane & 7) * 4) = make_float4(
+                                         s_f * x.x * cn[i].x, s_f * x.y * cn[i].y, s_f * x.z * cn[i].z, s_f * x.w * cn[i].w);
+                                 return x;
+                             });
         }
     }
 
@@ -462,26 +491,23 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
             if (w == 2 || q < 2) {  // 64-feature gradients live in TMEM lanes 0..63 (warp-uniform condition)
                 float v[32];
                 tmem_ld32(accs[w] + lane_off + (uint32_t)(ch * 32), v);
-                float* dst = part + offs[w] + (q * 32 + lane) * D + ch * 32;
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                warp_store_block(B2g + warp * 4096, v, part + offs[w] + (q * 32) * D + ch * 32, 32, lane, StoreIdentity());
             }
         }
     }
-    // bias sums: the tile buffers are dead now, use B0 as scratch.  red_p[32 line groups][64], red_e[3][4 quadrants][64]
+    // bias sums: the tile buffers are dead now, use B0 as scratch.  red_p[16 line groups][64], red_e[3][4 quadrants][64]
     float* red_p = reinterpret_cast<float*>(B0g);
-    float* red_e = red_p + 32 * D;
+    float* red_e = red_p + 16 * D;
     compute_barrier();
 #pragma unroll
-    for (int j = 0; j < 8; ++j) red_p[(tid >> 3) * D + (tid & 7) * 8 + j] = bsum_p[j];
+    for (int j = 0; j < 4; ++j) red_p[(tid >> 4) * D + (tid & 15) * 4 + j] = bsum_p[j];
 #pragma unroll
     for (int s = 0; s < 3; ++s) red_e[(s * 4 + q) * D + ch * 32 + lane] = bacc[s];
     compute_barrier();
     if (tid < D) {
         float t = 0.f;
 #pragma unroll
-        for (int g = 0; g < 32; ++g) t += red_p[g * D + tid];
+        for (int g = 0; g < 16; ++g) t += red_p[g * D + tid];
         part[D * D + tid] = t;
     } else if (tid < 4 * D) {
         const int s = (tid >> 6) - 1, c = tid & 63;
@@ -626,7 +652,7 @@ tc_embed_backward_kernel(const EmbBwdArgs a) {
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
 
     float4 ra[8], rb[8], rc[8];
-    float bsum0[8] = {}, bsum1[8] = {};
+    float bsum0[4] = {}, bsum1[4] = {};
     float bacc[2] = {0.f, 0.f};  // column sums of g0 and dh1 (epilogue mapping)
     uint32_t ph_d = 0, ph_w = 0;
     int iter = 0;
@@ -645,12 +671,9 @@ tc_embed_backward_kernel(const EmbBwdArgs a) {
         // ---------------- E0 ----------------
         if (iter > 0) { mbar_wait(bar_w, ph_w); ph_w ^= 1; }
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-            const float4 x = ra[2 * it], y = ra[2 * it + 1], z = rc[2 * it], w = rc[2 * it + 1];
-            bsum0[0] += x.x; bsum0[1] += x.y; bsum0[2] += x.z; bsum0[3] += x.w;
-            bsum0[4] += y.x; bsum0[5] += y.y; bsum0[6] += y.z; bsum0[7] += y.w;
-            bsum1[0] += z.x; bsum1[1] += z.y; bsum1[2] += z.z; bsum1[3] += z.w;
-            bsum1[4] += w.x; bsum1[5] += w.y; bsum1[6] += w.z; bsum1[7] += w.w;
+        for (int it = 0; it < 8; ++it) {
+            bsum0[0] += ra[it].x; bsum0[1] += ra[it].y; bsum0[2] += ra[it].z; bsum0[3] += ra[it].w;
+            bsum1[0] += rc[it].x; bsum1[1] += rc[it].y; bsum1[2] += rc[it].z; bsum1[3] += rc[it].w;
         }
         store_tile(B0g, ra, 1.f, tid);
         store_tile(B1g, rb, 1.f, tid);
@@ -728,20 +751,18 @@ tc_embed_backward_kernel(const EmbBwdArgs a) {
             if (q < 2 && (w != 1 || two)) {
                 float v[32];
                 tmem_ld32(accs[w] + lane_off + (uint32_t)(ch * 32), v);
-                float* dst = part + w * (D * D + D) + (q * 32 + lane) * D + ch * 32;
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                warp_store_block(B2g + warp * 4096, v, part + w * (D * D + D) + (q * 32) * D + ch * 32, 32, lane,
+                                 StoreIdentity());
             }
         }
     }
-    float* red_p = reinterpret_cast<float*>(B0g);  // [2][32 line groups][64]
-    float* red_e = red_p + 2 * 32 * D;             // [2][4 quadrants][64]
+    float* red_p = reinterpret_cast<float*>(B0g);  // [2][16 line groups][64]
+    float* red_e = red_p + 2 * 16 * D;             // [2][4 quadrants][64]
     compute_barrier();
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        red_p[(tid >> 3) * D + (tid & 7) * 8 + j] = bsum0[j];
-        red_p[32 * D + (tid >> 3) * D + (tid & 7) * 8 + j] = bsum1[j];
+    for (int j = 0; j < 4; ++j) {
+        red_p[(tid >> 4) * D + (tid & 15) * 4 + j] = bsum0[j];
+        red_p[16 * D + (tid >> 4) * D + (tid & 15) * 4 + j] = bsum1[j];
     }
 #pragma unroll
     for (int s = 0; s < 2; ++s) red_e[(s * 4 + q) * D + ch * 32 + lane] = bacc[s];
@@ -751,7 +772,7 @@ tc_embed_backward_kernel(const EmbBwdArgs a) {
         float t = 0.f;
         if (s < 2) {
 #pragma unroll
-            for (int g = 0; g < 32; ++g) t += red_p[s * 32 * D + g * D + c];
+            for (int g = 0; g < 16; ++g) t += red_p[s * 16 * D + g * D + c];
         } else {
             const int e = s - 2;
             t = ((red_e[(e * 4 + 0) * D + c] + red_e[(e * 4 + 1) * D + c]) + red_e[(e * 4 + 2) * D + c]) +
