@@ -736,9 +736,14 @@ static int backward_impl_fused(gcnn_workspace* ws, const float* p, const float* 
             add_job(cp + 2 * (D * D + D), n_parts, PART, 2 * D * D + D, o.Wo1);
             add_job(cp + 2 * (D * D + D) + 2 * D * D + D, n_parts, PART, D * D + D, o.Wf);
         }
-        if (i != 1) {  // the cut (after chain 2) and constraint (after chain 0) embeddings only wait for this chain
-            GCNN_TRY(stream_edge(ws, st, s2));
-            GCNN_TRY(embedding(i == 2 ? 2 : 0, s2));
+        // off the critical path, on the auxiliary stream: the embedding chains that only wait for this chain (cuts after
+        // chain 2, constraints after chain 0) and the fixed-order reduction of every partial written so far
+        GCNN_TRY(stream_edge(ws, st, s2));
+        if (i != 1) GCNN_TRY(embedding(i == 2 ? 2 : 0, s2));
+        static const bool early_reduce = [] { const char* e = getenv("GCNN_EARLY_REDUCE"); return !(e && e[0] == '0'); }();
+        if (s2 != st && early_reduce) {
+            GCNN_TRY(reduce_partials(jobs.data(), (int)jobs.size(), grads, s2));
+            jobs.clear();
         }
         // edge backward over the transposed layout: dS = gradient of the sending side's projection
         const float* R = recv_is_left[i] ? a.A : a.B;

@@ -17,7 +17,7 @@ constexpr int SORT_ITEMS = 16;                         // items per thread per t
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;   // 4096 pairs per CTA
 constexpr int RADIX = 256;
 
-int64_t sort_hist_entries(int64_t E) { return 2 * RADIX * ceil_div(E > 0 ? E : 1, SORT_TILE); }  // two buffers
+int64_t sort_hist_entries(int64_t E) { return 2 * RADIX * ceil_div(E > 0 ? E : 1, SORT_TILE) + RADIX; }  // two buffers + digit totals
 
 // One pass over the edge list (one CTA per SORT_TILE edges):
 //   * index range check (err_flag bit 0) and sortedness check (unsorted_flag := 1 on a descent);
@@ -65,39 +65,26 @@ check_init_hist_kernel(const int32_t* __restrict__ keys, const int32_t* __restri
     }
 }
 
-// Exclusive scan of n int32 in place, one CTA of 1024 threads; 16 elements per thread per pass (vector loads when the
-// pass is full), warp-shuffle + shared-memory block scan, running carry across passes.
-__global__ void __launch_bounds__(1024)
-exclusive_scan_kernel(int32_t* __restrict__ data, int64_t n, const int32_t* __restrict__ unsorted_flag,
-                      int32_t* __restrict__ zero_buf) {
+// Per-digit exclusive scan over the CTAs' counts: CTA d turns hist[d][0 .. n_blocks) into exclusive prefixes in place
+// and writes the digit's total.  256 independent small scans (one memory round trip) instead of one long serial scan;
+// the scatter kernel adds the exclusive scan over the 256 totals itself.
+__global__ void __launch_bounds__(RADIX)
+digit_scan_kernel(int32_t* __restrict__ hist, int n_blocks, const int32_t* __restrict__ unsorted_flag,
+                  int32_t* __restrict__ totals, int32_t* __restrict__ zero_buf) {
     pdl_enter();
     if (!*unsorted_flag) return;
-    if (zero_buf)  // histogram buffer the next scatter accumulates into
-        for (int64_t i = threadIdx.x; i < n; i += 1024) zero_buf[i] = 0;
-    constexpr int PER = 16;
-    __shared__ int32_t warp_sums[32];
+    __shared__ int32_t warp_sums[RADIX / 32];
     __shared__ int32_t carry_s;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    int32_t* row = hist + (int64_t)blockIdx.x * n_blocks;
+    if (zero_buf)  // this digit's slice of the histogram buffer the next scatter accumulates into
+        for (int i = t; i < n_blocks; i += RADIX) zero_buf[(int64_t)blockIdx.x * n_blocks + i] = 0;
     if (t == 0) carry_s = 0;
     __syncthreads();
-    for (int64_t base = 0; base < n; base += 1024 * PER) {
-        const int64_t lo = base + (int64_t)t * PER;
-        const int32_t carry = carry_s;  // written by the previous pass before its trailing barrier
-        int32_t v[PER];
-        if (lo + PER <= n) {
-#pragma unroll
-            for (int q = 0; q < PER / 4; ++q) {
-                const int4 x = *reinterpret_cast<const int4*>(data + lo + q * 4);
-                v[q * 4 + 0] = x.x; v[q * 4 + 1] = x.y; v[q * 4 + 2] = x.z; v[q * 4 + 3] = x.w;
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < PER; ++i) v[i] = (lo + i < n) ? data[lo + i] : 0;
-        }
-        int32_t sum = 0;
-#pragma unroll
-        for (int i = 0; i < PER; ++i) { const int32_t x = v[i]; v[i] = sum; sum += x; }
-        int32_t incl = sum;
+    for (int base = 0; base < n_blocks; base += RADIX) {
+        const int32_t carry = carry_s;
+        const int32_t x = base + t < n_blocks ? row[base + t] : 0;
+        int32_t incl = x;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int32_t u = __shfl_up_sync(0xffffffffu, incl, o);
@@ -105,31 +92,19 @@ exclusive_scan_kernel(int32_t* __restrict__ data, int64_t n, const int32_t* __re
         }
         if (lane == 31) warp_sums[warp] = incl;
         __syncthreads();
-        if (warp == 0) {
-            const int32_t w = warp_sums[lane];
-            int32_t wi = w;
+        int32_t before = 0, total = 0;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int32_t u = __shfl_up_sync(0xffffffffu, wi, o);
-                if (lane >= o) wi += u;
-            }
-            warp_sums[lane] = wi - w;
-            if (lane == 31) carry_s = carry + wi;
+        for (int w = 0; w < RADIX / 32; ++w) {
+            const int32_t c = warp_sums[w];
+            if (w < warp) before += c;
+            total += c;
         }
+        if (base + t < n_blocks) row[base + t] = carry + before + incl - x;
         __syncthreads();
-        const int32_t off = carry + warp_sums[warp] + incl - sum;
-        if (lo + PER <= n) {
-#pragma unroll
-            for (int q = 0; q < PER / 4; ++q)
-                *reinterpret_cast<int4*>(data + lo + q * 4) =
-                    make_int4(v[q * 4 + 0] + off, v[q * 4 + 1] + off, v[q * 4 + 2] + off, v[q * 4 + 3] + off);
-        } else {
-#pragma unroll
-            for (int i = 0; i < PER; ++i)
-                if (lo + i < n) data[lo + i] = v[i] + off;
-        }
+        if (t == 0) carry_s = carry + total;
         __syncthreads();
     }
+    if (t == 0) totals[blockIdx.x] = carry_s;
 }
 
 // Stable scatter: rank of an item among equal digits = (# in earlier CTAs) + (# in earlier rounds of this CTA)
@@ -137,15 +112,29 @@ exclusive_scan_kernel(int32_t* __restrict__ data, int64_t n, const int32_t* __re
 // also builds the NEXT pass's per-tile digit histogram (integer atomics: order-independent result).
 __global__ void __launch_bounds__(SORT_THREADS)
 radix_scatter_kernel(const int32_t* __restrict__ key_in, const int32_t* __restrict__ val_in, int64_t E, int shift,
-                     const int32_t* __restrict__ unsorted_flag, const int32_t* __restrict__ offsets, int n_blocks,
-                     int32_t* __restrict__ key_out, int32_t* __restrict__ val_out, int32_t* __restrict__ hist_next) {
+                     const int32_t* __restrict__ unsorted_flag, const int32_t* __restrict__ offsets,
+                     const int32_t* __restrict__ totals, int n_blocks, int32_t* __restrict__ key_out, int32_t* __restrict__ val_out, int32_t* __restrict__ hist_next) {
     pdl_enter();
     if (!*unsorted_flag) return;
     constexpr int WARPS = SORT_THREADS / 32;
     __shared__ int32_t running[RADIX];          // global offset of the next item of each digit for this CTA
     __shared__ int32_t warp_cnt[WARPS][RADIX];  // per-round per-warp digit counts -> exclusive offsets
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    running[t] = offsets[t * n_blocks + blockIdx.x];
+    {   // first slot of digit t for this CTA = (items of smaller digits) + (items of digit t in earlier CTAs)
+        const int32_t tot = totals[t];
+        int32_t incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) warp_cnt[0][warp] = incl;
+        __syncthreads();
+        int32_t before = 0;
+        for (int w = 0; w < warp; ++w) before += warp_cnt[0][w];
+        running[t] = before + incl - tot + offsets[t * n_blocks + blockIdx.x];
+        __syncthreads();
+    }
     const int64_t base = (int64_t)blockIdx.x * SORT_TILE;
     for (int i = 0; i < SORT_ITEMS; ++i) {
         for (int w = 0; w < WARPS; ++w) warp_cnt[w][t] = 0;
@@ -228,18 +217,18 @@ int build_layout(const int32_t* keys, const int32_t* others, const float* feats,
     }
     const int n_blocks = (int)ceil_div(E, SORT_TILE);
     const int64_t hist_n = (int64_t)RADIX * n_blocks;
-    int32_t *hist0 = sc.hist, *hist1 = sc.hist + hist_n;
+    int32_t *hist0 = sc.hist, *hist1 = sc.hist + hist_n, *totals = sc.hist + 2 * hist_n;
     // E <= 1 or a single owner: nothing to order (keys are clamped into [0, n_owner) downstream)
     const bool trivially_sorted = E <= 1 || n_owner <= 1;
     int32_t* scratch_flag = sc.flags;          // written, never read
     const int32_t* zero_flag = sc.flags + 6;   // never written: reads as "sorted"
     if (hint_sorted || trivially_sorted) {
-        GCNN_LAUNCH(check_init_hist_kernel<true>, n_blocks, SORT_THREADS, 0, st, 
+        GCNN_LAUNCH_ORDERED(check_init_hist_kernel<true>, n_blocks, SORT_THREADS, 0, st, 
             keys, others, E, (int32_t)n_owner, (int32_t)n_other, trivially_sorted ? scratch_flag : unsorted_flag,
             err_flag, trivially_sorted ? 0 : 1, nullptr, nullptr, nullptr, nullptr, n_blocks);
         GCNN_LAUNCH_CHECK();
     } else {
-        GCNN_LAUNCH(check_init_hist_kernel<false>, n_blocks, SORT_THREADS, 0, st, 
+        GCNN_LAUNCH_ORDERED(check_init_hist_kernel<false>, n_blocks, SORT_THREADS, 0, st, 
             keys, others, E, (int32_t)n_owner, (int32_t)n_other, unsorted_flag, err_flag, 0, sc.key_a, sc.val_a, hist0,
             hist1, n_blocks);
         GCNN_LAUNCH_CHECK();
@@ -253,10 +242,11 @@ int build_layout(const int32_t* keys, const int32_t* others, const float* feats,
         for (int shift = 0, pass = 0; shift < bits; shift += 8, ++pass) {
             const bool more = shift + 8 < bits;
             // pass 0 finds hist1 zeroed by the first kernel; later passes zero their "next" buffer in the scan
-            GCNN_LAUNCH(exclusive_scan_kernel, 1, 1024, 0, st, hcur, hist_n, unsorted_flag, (more && pass > 0) ? hnext : nullptr);
+            GCNN_LAUNCH_ORDERED(digit_scan_kernel, RADIX, RADIX, 0, st, hcur, n_blocks, unsorted_flag, totals,
+                        (more && pass > 0) ? hnext : nullptr);
             GCNN_LAUNCH_CHECK();
-            GCNN_LAUNCH(radix_scatter_kernel, n_blocks, SORT_THREADS, 0, st, ka, va, E, shift, unsorted_flag, hcur, n_blocks, kb,
-                                                                    vb, more ? hnext : nullptr);
+            GCNN_LAUNCH_ORDERED(radix_scatter_kernel, n_blocks, SORT_THREADS, 0, st, ka, va, E, shift, unsorted_flag, hcur, totals,
+                        n_blocks, kb, vb, more ? hnext : nullptr);
             GCNN_LAUNCH_CHECK();
             int32_t* t;
             t = ka; ka = kb; kb = t;
@@ -267,7 +257,7 @@ int build_layout(const int32_t* keys, const int32_t* others, const float* feats,
         sorted_perm = va;
     }
     const int threads = 256;
-    GCNN_LAUNCH(finalize_layout_kernel, (unsigned)ceil_div(E + 1, threads), threads, 0, st, 
+    GCNN_LAUNCH_ORDERED(finalize_layout_kernel, (unsigned)ceil_div(E + 1, threads), threads, 0, st, 
         keys, others, feats, E, (int32_t)n_owner, (int32_t)n_other,
         // a violated hint leaves unsorted_flag = 1 with no sorted pairs: fall back to the input order (the error is
         // reported through err_flag) by reading the always-zero word
