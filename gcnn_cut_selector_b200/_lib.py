@@ -69,6 +69,8 @@ SIGNATURES = {
     "gcnn_stage_host_batch": (_I, [_P, _I, _BP, _P]),
     "gcnn_score_staged": (_I, [_P, _I, _P, _P, _P, _P]),
     "gcnn_train_step_staged": (_I, [_P, _I, _P, _P, _P, _P, _F, _I64, C.POINTER(_F), _P]),
+    "gcnn_train_step_staged_async": (_I, [_P, _I, _P, _P, _P, _P, _F, _I64, _P]),
+    "gcnn_train_step_result": (_I, [_P, _I, C.POINTER(_F), _P]),
     "gcnn_staged_batch": (_I, [_P, _I, _BP, C.POINTER(_P), _P]),
     "gcnn_release_staged": (_I, [_P, _I, _P]),
     "gcnn_edge_forward": (_I, [_P, _P, _P, _I64, _P, _P, _P, _F, _F, _F, _P, _P, _P]),

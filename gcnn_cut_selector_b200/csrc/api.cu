@@ -103,9 +103,11 @@ struct gcnn_workspace {
         float *cons, *cef, *var, *cut, *kef, *targets;
         int32_t *cei, *kei;
         gcnn_batch meta{};        // the staged batch with DEVICE pointers into this slot
-        cudaEvent_t staged = nullptr, consumed = nullptr;
+        cudaEvent_t staged = nullptr, consumed = nullptr, result = nullptr;
         int valid = 0;
+        int64_t result_cuts = -1;  // cut count of the step whose result is pending (-1: none)
     } stage[2];
+    float* h_result = nullptr;    // pinned host: per slot {loss sum, error flag word}
     cudaStream_t copy_st = nullptr;
     // auxiliary streams: independent kernels (CSR build, the two projections of a convolution, weight gradients) run
     // concurrently with the main chain; fork/join with events, nothing synchronises the host
@@ -913,7 +915,9 @@ int gcnn_workspace_create(gcnn_workspace** out) {
     for (int s = 0; s < 2; ++s) {
         GCNN_CUDA_TRY(cudaEventCreateWithFlags(&ws->stage[s].staged, cudaEventDisableTiming));
         GCNN_CUDA_TRY(cudaEventCreateWithFlags(&ws->stage[s].consumed, cudaEventDisableTiming));
+        GCNN_CUDA_TRY(cudaEventCreateWithFlags(&ws->stage[s].result, cudaEventDisableTiming));
     }
+    GCNN_CUDA_TRY(cudaHostAlloc((void**)&ws->h_result, 4 * sizeof(float), cudaHostAllocDefault));
     *out = ws;
     return GCNN_OK;
 }
@@ -928,7 +932,9 @@ int gcnn_workspace_destroy(gcnn_workspace* ws) {
     for (int s = 0; s < 2; ++s) {
         if (ws->stage[s].staged) cudaEventDestroy(ws->stage[s].staged);
         if (ws->stage[s].consumed) cudaEventDestroy(ws->stage[s].consumed);
+        if (ws->stage[s].result) cudaEventDestroy(ws->stage[s].result);
     }
+    if (ws->h_result) cudaFreeHost(ws->h_result);
     delete ws;
     return GCNN_OK;
 }
@@ -1173,8 +1179,8 @@ int gcnn_score_staged(gcnn_workspace* ws, int slot, const float* params, const f
     return read_error_flag(ws, st);
 }
 
-int gcnn_train_step_staged(gcnn_workspace* ws, int slot, float* params, const float* prenorm, float* adam_m,
-                           float* adam_v, float lr, int64_t step, float* loss_host, void* stream) {
+int gcnn_train_step_staged_async(gcnn_workspace* ws, int slot, float* params, const float* prenorm, float* adam_m,
+                                 float* adam_v, float lr, int64_t step, void* stream) {
     if (!ws || slot < 0 || slot > 1 || !ws->stage[slot].valid) { set_error("no batch staged in this slot"); return GCNN_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
     gcnn_workspace::Stage& g = ws->stage[slot];
@@ -1187,11 +1193,31 @@ int gcnn_train_step_staged(gcnn_workspace* ws, int slot, float* params, const fl
     GCNN_CUDA_TRY(cudaEventRecord(g.consumed, st));
     GCNN_TRY(gcnn_adam_step(params, grads, adam_m, adam_v, GCNN_N_TRAINABLE, lr, 0.9f, 0.999f, 1e-7f, step, nullptr,
                             st));
-    float loss_sum = 0.f;
-    GCNN_CUDA_TRY(cudaMemcpyAsync(&loss_sum, ws->loss_sum, sizeof(float), cudaMemcpyDeviceToHost, st));
-    GCNN_TRY(read_error_flag(ws, st));
-    if (loss_host) *loss_host = nk > 0 ? loss_sum / (float)nk : 0.f;
+    // loss sum and the sticky error word travel to pinned host memory; gcnn_train_step_result waits for them
+    GCNN_CUDA_TRY(cudaMemcpyAsync(ws->h_result + 2 * slot, ws->loss_sum, sizeof(float), cudaMemcpyDeviceToHost, st));
+    GCNN_CUDA_TRY(cudaMemcpyAsync(ws->h_result + 2 * slot + 1, ws->flags + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    GCNN_CUDA_TRY(cudaEventRecord(g.result, st));
+    g.result_cuts = nk;
     return GCNN_OK;
+}
+
+int gcnn_train_step_result(gcnn_workspace* ws, int slot, float* loss_host, void* stream) {
+    if (!ws || slot < 0 || slot > 1 || ws->stage[slot].result_cuts < 0) { set_error("no step pending on this slot"); return GCNN_INVALID; }
+    gcnn_workspace::Stage& g = ws->stage[slot];
+    GCNN_CUDA_TRY(cudaEventSynchronize(g.result));
+    const int64_t nk = g.result_cuts;
+    g.result_cuts = -1;
+    int32_t flag;
+    memcpy(&flag, ws->h_result + 2 * slot + 1, sizeof(flag));
+    if (loss_host) *loss_host = nk > 0 ? ws->h_result[2 * slot] / (float)nk : 0.f;
+    if (flag) return read_error_flag(ws, (cudaStream_t)stream);  // re-reads, clears and reports the device word
+    return GCNN_OK;
+}
+
+int gcnn_train_step_staged(gcnn_workspace* ws, int slot, float* params, const float* prenorm, float* adam_m,
+                           float* adam_v, float lr, int64_t step, float* loss_host, void* stream) {
+    GCNN_TRY(gcnn_train_step_staged_async(ws, slot, params, prenorm, adam_m, adam_v, lr, step, stream));
+    return gcnn_train_step_result(ws, slot, loss_host, stream);
 }
 
 int gcnn_staged_batch(gcnn_workspace* ws, int slot, gcnn_batch* out, float** targets_dev, void* stream) {

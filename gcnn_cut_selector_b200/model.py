@@ -378,6 +378,19 @@ class GCNN:
                                                C.byref(loss), self._stream()))
         return float(loss.value)
 
+    def train_step_staged_async(self, slot: int, lr: float):
+        """Enqueue the optimisation step on the batch staged in ``slot`` without waiting for it; its mean loss is read
+        later with ``train_step_result(slot)`` (e.g. after the next step has been enqueued)."""
+        self.adam_step += 1
+        check(self._lib.gcnn_train_step_staged_async(self._ws, slot, self.flat_params.data_ptr(),
+                                                     self.flat_prenorm.data_ptr(), self.adam_m.data_ptr(),
+                                                     self.adam_v.data_ptr(), lr, self.adam_step, self._stream()))
+
+    def train_step_result(self, slot: int) -> float:
+        loss = C.c_float()
+        check(self._lib.gcnn_train_step_result(self._ws, slot, C.byref(loss), self._stream()))
+        return float(loss.value)
+
     def loss_and_grads_staged(self, slot: int, seed_scale: float | None = None):
         """``loss_and_grads`` on the batch staged in ``slot`` (data-parallel trainer).  Returns (loss_sum, n_cuts)."""
         batch, tgt = Batch(), C.c_void_p()

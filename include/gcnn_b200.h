@@ -166,6 +166,12 @@ int gcnn_score_staged(gcnn_workspace* ws, int slot, const float* params, const f
                       void* stream);
 int gcnn_train_step_staged(gcnn_workspace* ws, int slot, float* params, const float* prenorm, float* adam_m,
                            float* adam_v, float lr, int64_t step, float* loss_host, void* stream);
+/* gcnn_train_step_staged split in two: _async enqueues the step (and the copies of its loss and of the sticky index-error
+ * word to pinned host memory) without synchronising; gcnn_train_step_result waits for that step only and returns its
+ * mean loss.  Calling _result for step i after enqueueing step i + 1 keeps the GPU busy while the host prepares work. */
+int gcnn_train_step_staged_async(gcnn_workspace* ws, int slot, float* params, const float* prenorm, float* adam_m,
+                                 float* adam_v, float lr, int64_t step, void* stream);
+int gcnn_train_step_result(gcnn_workspace* ws, int slot, float* loss_host, void* stream);
 int gcnn_staged_batch(gcnn_workspace* ws, int slot, gcnn_batch* out, float** targets_dev, void* stream);
 int gcnn_release_staged(gcnn_workspace* ws, int slot, void* stream);
 

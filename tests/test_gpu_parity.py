@@ -494,6 +494,22 @@ def test_prefetching_host_path_matches_synchronous_path(golden_dir):
         losses_b.append(b.train_step_staged(i & 1, 1e-3))
     assert losses_a == losses_b
     torch.testing.assert_close(a.flat_params.detach(), b.flat_params.detach(), rtol=0, atol=0)
+    # same again with the loss of step i read only after step i + 1 is enqueued
+    c = GCNN(device="cuda:0", seed=5)
+    c.restore_state(path)
+    for h in hb:
+        c.reserve(h.batch, True)
+    c.stage_host(hb[0], 0)
+    losses_c = []
+    for i in range(3):
+        if i + 1 < 3:
+            c.stage_host(hb[i + 1], (i + 1) & 1)
+        c.train_step_staged_async(i & 1, 1e-3)
+        if i > 0:
+            losses_c.append(c.train_step_result((i - 1) & 1))
+    losses_c.append(c.train_step_result(2 & 1))
+    assert losses_a == losses_c
+    torch.testing.assert_close(a.flat_params.detach(), c.flat_params.detach(), rtol=0, atol=0)
     b.stage_host(hb[1], 0, training=False)
     np.testing.assert_array_equal(b.score_staged(0), a.score_host(ha[1]))
 
