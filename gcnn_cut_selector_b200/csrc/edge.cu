@@ -9,12 +9,15 @@
 // 64-float row with one float4 per lane, so a warp works on two edges at a time and each gathered row is one fully
 // coalesced 256-byte read.  Reduction order is fixed by the layout -> bit-reproducible, no atomics.
 // HBM-bound; algorithmic bytes per launch are stated in DESIGN.md.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gcnn {
 
 constexpr int EDGE_THREADS = 256;
 constexpr int EDGE_WARPS = EDGE_THREADS / 32;
+constexpr int EDGE_FWD_THREADS = 512;        // forward: two persistent CTAs per SM, their warps on neighbouring segments
 constexpr int EDGE_BWD_MAX_CTAS = NUM_SMS * 4;  // persistent: 8 CTAs of 256 threads fit per SM, 4 keep the dw partials few
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -60,19 +63,23 @@ __device__ __forceinline__ void relu_accumulate(const float2 y01, const float2 y
 }
 
 template <bool TRAIN>
-__global__ void __launch_bounds__(EDGE_THREADS)
+__global__ void __launch_bounds__(EDGE_FWD_THREADS)
 edge_forward_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ src, const float* __restrict__ val,
                     int64_t n_recv, const float* __restrict__ R, const float* __restrict__ S,
                     const float* __restrict__ w_edge, EdgeScalars sc, float* __restrict__ H, float* __restrict__ cnt) {
     pdl_enter();
     const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
-    const int64_t row = (int64_t)blockIdx.x * EDGE_WARPS + (threadIdx.x >> 5);
-    if (row >= n_recv) return;
+    const int warps = blockDim.x >> 5;
+    // CTA b owns the contiguous rows [b n / grid, (b + 1) n / grid): neighbouring segments belong to the same sample
+    // (block-diagonal batches) and gather from the same few hundred source rows, which then hit in this SM's L1 instead
+    // of going to L2 (the kernel's ceiling: E x 256 B of gathers against ~12 TB/s of L2)
+    const int64_t row_beg = n_recv * (int64_t)blockIdx.x / gridDim.x, row_end = n_recv * ((int64_t)blockIdx.x + 1) / gridDim.x;
     const float f_shift = sc.f_shift ? *sc.f_shift : 0.f, f_scale = sc.f_scale ? *sc.f_scale : 1.f, s_f = *sc.s_f;
-    const int beg = ptr[row], end = ptr[row + 1];
-    const float4 r4 = ld4(R + row * D + hl * 4);
     const float4 w4 = ldg4(w_edge + hl * 4);
     const float* Sl = S + hl * 4;
+    for (int64_t row = row_beg + (threadIdx.x >> 5); row < row_end; row += warps) {
+    const int beg = ptr[row], end = ptr[row + 1];
+    const float4 r4 = ld4(R + row * D + hl * 4);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), act = acc;
 
     for (int base = beg; base < end; base += 32) {
@@ -83,9 +90,10 @@ edge_forward_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__
             my_src = src[base + lane];
             my_f = (val[base + lane] + f_shift) * f_scale;
         }
-        const int n_full = n & ~7;
         int j0 = 0;
-        for (; j0 < n_full; j0 += 8) {  // 8 edges: each half-warp takes every other one, no predication
+        // (16-edge groups with 8 gathers in flight per lane were tried: 86+ registers cost more occupancy than the
+        // extra loads in flight gain -- 0.082-0.10 ms against 0.073 ms for the three forward launches of the benchmark step)
+        for (; j0 + 8 <= n; j0 += 8) {  // 8 edges: each half-warp takes every other one, no predication
             float4 g[4];
             float f[4];
 #pragma unroll
@@ -123,15 +131,18 @@ edge_forward_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__
         if (half == 1)
             st4(cnt + row * D + hl * 4, make_float4(act_o.x + act.x, act_o.y + act.y, act_o.z + act.z, act_o.w + act.w));
     }
+    }  // rows of this CTA
 }
 
 int edge_forward(const EdgeLayout& L, int64_t n_recv, const float* R, const float* S, const float* w_edge,
                  EdgeScalars sc, float* H, float* cnt, cudaStream_t st, double prof_bytes, int64_t /*n_edges*/) {
     if (n_recv <= 0) return GCNN_OK;
     ProfScope prof(PROF_EDGE_FWD, prof_bytes, st);
-    const unsigned grid = (unsigned)ceil_div(n_recv, EDGE_WARPS);
-    if (cnt) GCNN_LAUNCH(edge_forward_kernel<true>, grid, EDGE_THREADS, 0, st, L.ptr, L.other, L.val, n_recv, R, S, w_edge, sc, H, cnt);
-    else GCNN_LAUNCH(edge_forward_kernel<false>, grid, EDGE_THREADS, 0, st, L.ptr, L.other, L.val, n_recv, R, S, w_edge, sc, H, cnt);
+    static const int cta_threads = [] { const char* e = getenv("GCNN_EDGE_THREADS"); return e ? atoi(e) : EDGE_FWD_THREADS; }();
+    static const int ctas_per_sm = [] { const char* e = getenv("GCNN_EDGE_CTAS"); return e ? atoi(e) : 2; }();
+    const unsigned grid = (unsigned)min((int64_t)NUM_SMS * ctas_per_sm, ceil_div(n_recv, cta_threads / 32));
+    if (cnt) GCNN_LAUNCH(edge_forward_kernel<true>, grid, cta_threads, 0, st, L.ptr, L.other, L.val, n_recv, R, S, w_edge, sc, H, cnt);
+    else GCNN_LAUNCH(edge_forward_kernel<false>, grid, cta_threads, 0, st, L.ptr, L.other, L.val, n_recv, R, S, w_edge, sc, H, cnt);
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
 }
@@ -165,7 +176,9 @@ edge_backward_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict_
     const float* Gl = G + hl * 4;
     float4 dw = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    for (int64_t row = (int64_t)blockIdx.x * EDGE_WARPS + warp; row < n_send; row += (int64_t)gridDim.x * EDGE_WARPS) {
+    // contiguous rows per CTA (same reason as in the forward: neighbouring segments gather the same rows -> L1 hits)
+    const int64_t row_beg = n_send * (int64_t)blockIdx.x / gridDim.x, row_end = n_send * ((int64_t)blockIdx.x + 1) / gridDim.x;
+    for (int64_t row = row_beg + warp; row < row_end; row += EDGE_WARPS) {
         const int beg = ptr[row], end = ptr[row + 1];
         const float4 s4 = ld4(S + row * D + hl * 4);
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
