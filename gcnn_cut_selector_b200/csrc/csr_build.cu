@@ -13,8 +13,8 @@
 namespace gcnn {
 
 constexpr int SORT_THREADS = 256;
-constexpr int SORT_ITEMS = 16;                         // items per thread per tile
-constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;   // 4096 pairs per CTA
+constexpr int SORT_ITEMS = 4;                          // items per thread per tile
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;   // 1024 pairs per CTA: the scatter is latency-bound per CTA (16 items: 30 us, 4 items: 11 us for 800 k pairs)
 constexpr int RADIX = 256;
 
 int64_t sort_hist_entries(int64_t E) { return 2 * RADIX * ceil_div(E > 0 ? E : 1, SORT_TILE) + RADIX; }  // two buffers + digit totals
