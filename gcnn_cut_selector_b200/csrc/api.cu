@@ -95,6 +95,9 @@ struct gcnn_workspace {
     // fused backward chains: per-convolution G, dR (receiving-side projection gradient), dS (sending side), partials
     float *bG[3], *bdR[3], *bdS[3], *chain_partials[3], *emb_partials[3];
     int use_fused_bwd = 1;
+    // set by gcnn_forward_backward around a fused step: head layer 2, the loss seed and its backward are ONE launch
+    int head_fused = 0, head_parts = 0;
+    float* loss_out = nullptr;
     // stats
     double *st_partials, *st_out, *st_center;
     // host staging mirrors (device side), two slots: batch i + 1 is copied in on the library's copy stream while the
@@ -388,7 +391,8 @@ static int forward_convs_fused(gcnn_workspace* ws, const float* p, const float* 
         if (stop_layer == 6 + 2 * i) return wait_all_layouts();
     }
     GCNN_TRY(wait_all_layouts());  // the backward needs the cut by-variable layout
-    GCNN_TRY(head2_forward(ws->g1, p + P.Wh2, p + P.bh2, scores_out ? scores_out : ws->scores, nk, st));
+    if (!ws->head_fused)
+        GCNN_TRY(head2_forward(ws->g1, p + P.Wh2, p + P.bh2, scores_out ? scores_out : ws->scores, nk, st));
     return GCNN_OK;
 }
 
@@ -515,7 +519,7 @@ static int backward_impl(gcnn_workspace* ws, const float* p, const float* pn, co
     std::vector<ReduceJob> jobs;
     int slot = 0;
     auto add_job = [&](const float* part, int n_parts, int stride, int count, int dst) {
-        jobs.push_back(ReduceJob{part, n_parts, stride, count, dst, nullptr});
+        jobs.push_back(ReduceJob{part, n_parts, stride, count, dst, nullptr, nullptr});
     };
     int n_parts = 0;
     // weight gradients run on an auxiliary stream, concurrent with the input-gradient chain on the main stream
@@ -665,15 +669,21 @@ static int backward_impl_fused(gcnn_workspace* ws, const float* p, const float* 
     std::vector<ReduceJob> jobs;
     int slot = 0, n_parts = 0;
     auto add_job = [&](const float* part, int n, int stride, int count, int dst) {
-        jobs.push_back(ReduceJob{part, n, stride, count, dst, nullptr});
+        jobs.push_back(ReduceJob{part, n, stride, count, dst, nullptr, nullptr});
     };
     auto img16 = [&](int param_off) -> const void* {
         return ws->tc_images + (int64_t)tc_block_index(param_off) * TC_IMG_FLOATS + TC_IMG_TF32_FLOATS;
     };
     cudaStream_t s2 = aux_stream(ws, 1, st);
 
-    GCNN_TRY(head2_backward(ws->g1, p + P.Wh2, d_scores, ws->t_dg, ws->partials[slot], &n_parts, nk, st));
-    add_job(ws->partials[slot++], n_parts, D + 1, D + 1, P.Wh2);
+    if (ws->head_fused) {  // head_loss already produced t_dg and the partials [dw | db | squared error]
+        add_job(ws->partials[slot], ws->head_parts, D + 2, D + 1, P.Wh2);
+        jobs.push_back(ReduceJob{ws->partials[slot] + D + 1, ws->head_parts, D + 2, 1, 0, nullptr, ws->loss_out});
+        ++slot;
+    } else {
+        GCNN_TRY(head2_backward(ws->g1, p + P.Wh2, d_scores, ws->t_dg, ws->partials[slot], &n_parts, nk, st));
+        add_job(ws->partials[slot++], n_parts, D + 1, D + 1, P.Wh2);
+    }
 
     const float* recv_in[3] = {ws->c0, ws->v0, ws->k0};
     float* d_recv_in[3] = {ws->dc0, ws->dv0, ws->dk0};
@@ -1065,12 +1075,23 @@ int gcnn_forward_backward(gcnn_workspace* ws, const float* params, const float* 
     GCNN_TRY(check_batch(ws, batch, 1));
     cudaStream_t st = (cudaStream_t)stream;
     float* scores = scores_out ? scores_out : ws->scores;
-    GCNN_TRY(forward_impl(ws, params, prenorm, batch, scores, -1, st));
+    float* loss_out = loss_sum_out ? loss_sum_out : ws->loss_sum;
+    const bool fuse_head = ws->use_tc && ws->use_fused && ws->use_fused_bwd;
+    ws->head_fused = fuse_head ? 1 : 0;
+    ws->loss_out = loss_out;
+    int rc = forward_impl(ws, params, prenorm, batch, scores, -1, st);
     ws->last = *batch;
     ws->have_activations = 1;
-    GCNN_TRY(mse_seed(scores, targets, batch->n_cuts, seed_scale, ws->d_scores, loss_sum_out ? loss_sum_out : ws->loss_sum,
-                      st));
-    return backward_impl(ws, params, prenorm, batch, ws->d_scores, grads_out, st);
+    if (rc == GCNN_OK) {
+        if (fuse_head)
+            rc = head_loss(ws->g1, params + P.Wh2, params + P.bh2, targets, seed_scale, scores, ws->t_dg, ws->partials[0],
+                           &ws->head_parts, batch->n_cuts, st);
+        else
+            rc = mse_seed(scores, targets, batch->n_cuts, seed_scale, ws->d_scores, loss_out, st);
+    }
+    if (rc == GCNN_OK) rc = backward_impl(ws, params, prenorm, batch, ws->d_scores, grads_out, st);
+    ws->head_fused = 0;
+    return rc;
 }
 
 int gcnn_prenorm_stats(gcnn_workspace* ws, const float* params, const float* prenorm, const gcnn_batch* b, int layer,
@@ -1290,7 +1311,7 @@ int gcnn_edge_backward(gcnn_workspace* ws, const int32_t* ptr, const int32_t* ot
         rc = edge_backward(L, n_send, R, S, G, w_edge, EdgeScalars{dev, dev + 1, dev + 2}, dS, ws->dw_partials[0],
                            &n_dw, st, 0.0, n_edges);
         if (rc == GCNN_OK) {
-            ReduceJob job{ws->dw_partials[0], n_dw, D, D, 0, nullptr};
+            ReduceJob job{ws->dw_partials[0], n_dw, D, D, 0, nullptr, nullptr};
             rc = reduce_partials(&job, 1, dw, st);
         }
     }

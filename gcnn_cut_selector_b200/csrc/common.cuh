@@ -321,9 +321,14 @@ int embed1_wgrad(const float* x, int K, const float* shift, const float* scale, 
 int head2_forward(const float* g, const float* w, const float* b, float* scores, int64_t M, cudaStream_t st);
 int head2_backward(const float* g, const float* w, const float* d_scores, float* dg_pre, float* partials,
                    int* n_parts, int64_t M, cudaStream_t st);
+// head layer 2 + MSE seed + head layer 2 backward in one launch; per-CTA partial [dw (64) | db | squared-error sum]
+int head_loss(const float* g, const float* w, const float* b, const float* targets, float scale, float* scores,
+              float* dg_pre, float* partials, int* n_parts, int64_t M, cudaStream_t st);
 
 // deterministic fixed-order reduction of per-CTA partials into the flat gradient
-struct ReduceJob { const float* partials; int n_parts; int stride; int count; int dst; const float* scale; };
+struct ReduceJob {  // sum of n_parts partials (stride floats apart) -> grads[dst .. dst + count) or, if set, out[0 .. count)
+    const float* partials; int n_parts; int stride; int count; int dst; const float* scale; float* out;
+};
 int reduce_partials(const ReduceJob* jobs, int n_jobs, float* grads, cudaStream_t st);
 
 int mse_seed(const float* scores, const float* targets, int64_t n, float scale, float* d_scores, float* loss_sum,

@@ -419,6 +419,64 @@ int head2_forward(const float* g, const float* w, const float* b, float* scores,
     return GCNN_OK;
 }
 
+// Training: head layer 2, the MSE seed (model_trainer.py:271: mean over all cuts -> d_score = 2 (p - y) scale) and head
+// layer 2's backward in one launch -- three dependent 3-10 us launches on the critical path otherwise.  Same lane
+// mapping and summation order as head2_forward_kernel, so training and inference produce bit-identical scores.
+// Per-CTA partial: [dw (64) | db | sum of squared errors].
+__global__ void __launch_bounds__(256)
+head_loss_kernel(const float* __restrict__ g, const float* __restrict__ w, const float* __restrict__ b,
+                 const float* __restrict__ targets, float scale, float* __restrict__ scores,
+                 float* __restrict__ dg_pre, float* __restrict__ partials, int64_t M) {
+    pdl_enter();
+    __shared__ float red[16][D + 2];
+    const int hl = threadIdx.x & 15, rl = threadIdx.x >> 4;
+    const float4 w4 = ld4s(w + hl * 4);
+    const float bias = b[0];
+    float4 dw = make_float4(0.f, 0.f, 0.f, 0.f);
+    float db = 0.f, sq = 0.f;
+    for (int64_t m0 = (int64_t)blockIdx.x * 16; m0 < M; m0 += (int64_t)gridDim.x * 16) {
+        const int64_t m = m0 + rl;
+        const bool ok = m < M;  // uniform over the 16 lanes of a row
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok) a = ld4s(g + m * D + hl * 4);
+        float s = a.x * w4.x + a.y * w4.y + a.z * w4.z + a.w * w4.w;
+#pragma unroll
+        for (int o = 8; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (ok) {
+            const float p = s + bias;
+            const float d = p - targets[m];
+            const float ds = 2.f * d * scale;
+            st4s(dg_pre + m * D + hl * 4, make_float4(a.x > 0.f ? ds * w4.x : 0.f, a.y > 0.f ? ds * w4.y : 0.f,
+                                                      a.z > 0.f ? ds * w4.z : 0.f, a.w > 0.f ? ds * w4.w : 0.f));
+            dw.x = fmaf(a.x, ds, dw.x); dw.y = fmaf(a.y, ds, dw.y); dw.z = fmaf(a.z, ds, dw.z); dw.w = fmaf(a.w, ds, dw.w);
+            if (hl == 0) {
+                scores[m] = p;
+                db += ds;
+                sq = fmaf(d, d, sq);
+            }
+        }
+    }
+    red[rl][hl * 4 + 0] = dw.x; red[rl][hl * 4 + 1] = dw.y; red[rl][hl * 4 + 2] = dw.z; red[rl][hl * 4 + 3] = dw.w;
+    if (hl == 0) { red[rl][D] = db; red[rl][D + 1] = sq; }
+    __syncthreads();
+    if (threadIdx.x < D + 2) {
+        float t = 0.f;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) t += red[r][threadIdx.x];
+        partials[(int64_t)blockIdx.x * (D + 2) + threadIdx.x] = t;
+    }
+}
+
+int head_loss(const float* g, const float* w, const float* b, const float* targets, float scale, float* scores,
+              float* dg_pre, float* partials, int* n_parts, int64_t M, cudaStream_t st) {
+    const int parts = (int)min((int64_t)WG_MAX_PARTS, ceil_div(M > 0 ? M : 1, 64));
+    *n_parts = parts;
+    ProfScope prof(PROF_HEAD, 4.0 * (double)M * (2 * D + 2), st);
+    GCNN_LAUNCH(head_loss_kernel, parts, 256, 0, st, g, w, b, targets, scale, scores, dg_pre, partials, M);
+    GCNN_LAUNCH_CHECK();
+    return GCNN_OK;
+}
+
 // dg_pre[m, c] = ds[m] * w[c] * 1[g > 0];  partial dw[c] = sum_m g[m, c] ds[m];  partial db = sum_m ds[m]
 __global__ void __launch_bounds__(256)
 head2_backward_kernel(const float* __restrict__ g, const float* __restrict__ w, const float* __restrict__ ds,
@@ -456,41 +514,37 @@ int head2_backward(const float* g, const float* w, const float* d_scores, float*
 constexpr int MAX_JOBS = 48;
 struct ReduceJobs { ReduceJob j[MAX_JOBS]; int n; };
 
-// Short outputs (edge-weight and head gradients: 64-65 floats, up to ~600 partials) would leave one thread walking
-// hundreds of partials serially, so the 256 threads of a CTA are arranged as (256 / LANES_W) partial-lanes x LANES_W
-// outputs; lane l sums partials l, l + L, l + 2L, ... and the lanes are combined in lane order -> still a fixed order.
+// 64 outputs per CTA; the CTA's 256 threads are 4 partial-lanes x 64 outputs: lane l sums partials l, l + 4, l + 8, ...
+// (four independent accumulators each), the lanes are combined in lane order -> a fixed order, bit-reproducible.  Up to
+// 148 partials per output would otherwise be one serial chain of dependent L2 loads per thread.
+constexpr int RED_WIDTH = 64, RED_LANES = 256 / RED_WIDTH;
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const __grid_constant__ ReduceJobs jobs, float* __restrict__ grads) {
     pdl_enter();
     __shared__ float red[256];
     const ReduceJob& job = jobs.j[blockIdx.y];
-    const int width = job.count <= 64 ? 64 : (job.count <= 128 ? 128 : 256);  // outputs per CTA
-    const int lanes = 256 / width;
-    const int c = threadIdx.x % width, lane = threadIdx.x / width;
-    const int i = blockIdx.x * width + c;
-    if (blockIdx.x * width >= job.count) return;  // whole CTA out of range (uniform)
+    const int c = threadIdx.x % RED_WIDTH, lane = threadIdx.x / RED_WIDTH;
+    const int i = blockIdx.x * RED_WIDTH + c;
+    if (blockIdx.x * RED_WIDTH >= job.count) return;  // whole CTA out of range (uniform)
     float total = 0.f;
     if (i < job.count) {
         const float* src = job.partials + i;
         float s[4] = {};
         int p = lane;
-        for (; p + 3 * lanes < job.n_parts; p += 4 * lanes) {
+        for (; p + 3 * RED_LANES < job.n_parts; p += 4 * RED_LANES) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) s[u] += src[(int64_t)(p + u * lanes) * job.stride];
+            for (int u = 0; u < 4; ++u) s[u] += src[(int64_t)(p + u * RED_LANES) * job.stride];
         }
-        for (; p < job.n_parts; p += lanes) s[0] += src[(int64_t)p * job.stride];
+        for (; p < job.n_parts; p += RED_LANES) s[0] += src[(int64_t)p * job.stride];
         total = (s[0] + s[1]) + (s[2] + s[3]);
-    }
-    if (lanes == 1) {
-        if (i < job.count) grads[job.dst + i] = job.scale ? total * *job.scale : total;
-        return;
     }
     red[threadIdx.x] = total;
     __syncthreads();
     if (lane == 0 && i < job.count) {
         float t = red[c];
-        for (int l = 1; l < lanes; ++l) t += red[l * width + c];
-        grads[job.dst + i] = job.scale ? t * *job.scale : t;
+#pragma unroll
+        for (int l = 1; l < RED_LANES; ++l) t += red[l * RED_WIDTH + c];
+        (job.out ? job.out : grads + job.dst)[i] = job.scale ? t * *job.scale : t;
     }
 }
 
@@ -501,8 +555,7 @@ int reduce_partials(const ReduceJob* jobs, int n_jobs, float* grads, cudaStream_
     int max_ctas = 1;
     for (int i = 0; i < n_jobs; ++i) {
         out_floats += jobs[i].count;
-        const int width = jobs[i].count <= 64 ? 64 : (jobs[i].count <= 128 ? 128 : 256);
-        const int ctas = (int)ceil_div(jobs[i].count, width);
+        const int ctas = (int)ceil_div(jobs[i].count, RED_WIDTH);
         max_ctas = ctas > max_ctas ? ctas : max_ctas;
     }
     ProfScope prof(PROF_REDUCE, 8.0 * out_floats, st);  // one read + one write per gradient element at minimum
