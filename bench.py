@@ -242,8 +242,16 @@ def run_b200(args):
     for c in classes:
         c["share_of_kernel_time"] = c["ms_per_step"] / kernel_ms if kernel_ms else 0.0
     top = max(classes, key=lambda c: c["ms_per_step"])
+    # DRAM traffic per launch of the same kernel class from the committed `ncu --set full` capture of one whole step
+    # (profiles/r1_step_traffic.json, made by scripts/ncu_step_summary.py; never measured under the profiler here)
+    traffic = None
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_step_traffic.json")
+    if os.path.exists(tpath) and graphs == 32:
+        traffic = json.load(open(tpath)).get(top["kernel"], {}).get("dram_bytes_per_launch")
     roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": top["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": top["frac"], "traffic": None, "peak_source": peak_src,
+                "frac": top["frac"], "traffic": traffic,
+                "algorithmic_bytes_per_launch": top["algorithmic_mb_per_step"] * 1e6 / top["launches_per_step"],
+                "peak_source": peak_src,
                 "bytes": "algorithmic bytes per launch (DESIGN.md section 4) / CUDA-event time per launch, "
                          "events on the launch stream, separate pass of the same K steps"}
     seg = [c for c in classes if c["kernel"] in ("edge_forward", "edge_backward")]

@@ -10,6 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 PKG = os.path.join(ROOT, "gcnn_cut_selector_b200")
 OUT = os.path.join(PKG, "build", "libgcnn_b200_timing.so")
+os.environ["GCNN_LIB"] = OUT  # read when gcnn_cut_selector_b200._lib is first imported
 
 
 def build():
@@ -26,7 +27,6 @@ if __name__ == "__main__":
         build()
     if "--build-only" in sys.argv:
         sys.exit(0)
-    os.environ["GCNN_LIB"] = OUT
     import torch
     import bench
     from gcnn_cut_selector_b200 import GCNN, _lib, batching
