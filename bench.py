@@ -32,6 +32,13 @@ sys.path.insert(0, ROOT)
 
 SETCOV_MSGS_PER_GRAPH = 2 * 25_000 + 6_400  # 2 E_cons + E_cut (three convolutions, model.py:294-296)
 METRIC, UNIT = "gcnn_train_graphs_per_s", "graphs/s"
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def measured_peak_gbs():
@@ -122,7 +129,7 @@ def run_reference(args):
                              "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -324,7 +331,7 @@ def run_b200(args):
                 "kernels": classes}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(model, batches[0], graphs)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -338,6 +345,12 @@ def main():
     ap.add_argument("--graphs-per-gpu", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # Libraries write to file descriptor 1 on their own (NCCL prints its version banner at init): keep the real stdout
+    # for the ONE JSON line and send everything else to stderr.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         if args.steps == 100:
             args.steps = 5
