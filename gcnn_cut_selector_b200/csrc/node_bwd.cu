@@ -101,16 +101,24 @@ __device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src, ui
 }
 
 // ---- warp roles -----------------------------------------------------------------------------------------------------
-// Warps 0..7 move and transform data (loads, bf16x3 splits, epilogues); warp 8 only talks to the tensor core and the
+// Warps 0..15 move and transform data (loads, bf16x3 splits, epilogues); warp 16 only talks to the tensor core and the
 // bulk-copy engine.  tcgen05.mma issue blocks the issuing thread at the tensor core's pace (about 50 cycles per MMA here,
 // bound by the operand reads from shared memory), so a compute warp that also issued MMAs would stall every other warp
 // at the next barrier.  Hand-off: the compute warps meet at a named barrier, then one of them arrives on `bar_ready`.
-constexpr int BWD_THREADS = 384;  // warpgroups 0, 1: compute; warpgroup 2: warp 8 issues, warps 9..11 idle
-// Register budget: 384 threads start with 168 registers each; the MMA warpgroup gives most of its share back
-// (setmaxnreg.dec) and the compute warpgroups grow to 224 (setmaxnreg.inc): 256 x 224 + 128 x 56 = 64,512 <= 65,536.
-__device__ __forceinline__ void regs_compute() { asm volatile("setmaxnreg.inc.sync.aligned.u32 224;"); }
-__device__ __forceinline__ void regs_mma() { asm volatile("setmaxnreg.dec.sync.aligned.u32 56;"); }
-__device__ __forceinline__ void compute_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// Sixteen compute warps (four per scheduler) rather than eight: the split / epilogue code is chains of dependent ALU
+// operations, and with two warps per scheduler their latency was exposed.
+constexpr int CWARPS = 16;                    // compute warps
+constexpr int CTHREADS = CWARPS * 32;         // 512
+constexpr int BWD_THREADS = CTHREADS + 128;   // + the MMA warpgroup (warp 16 issues, warps 17..19 idle)
+constexpr int NCOL = D / (CWARPS / 4);        // columns per thread in the epilogue mapping: 16
+constexpr int NLD = TC_ROWS * (D / 4) / CTHREADS;  // float4 per thread per tile in the load mapping: 4
+constexpr int PATCH = 32 * NCOL * 4;          // bytes of a warp's transpose patch: 2 KB
+// Register budget: 640 threads start with 96 registers each; the MMA warpgroup gives part of its share back
+// (setmaxnreg.dec) and the compute warpgroups grow (setmaxnreg.inc).  The pool is what the CTA was launched with, so the
+// sum must not grow: 512 x 104 + 128 x 40 = 58,368 <= 640 x 96 = 61,440 (an inc beyond the pool blocks forever).
+__device__ __forceinline__ void regs_compute() { asm volatile("setmaxnreg.inc.sync.aligned.u32 104;"); }
+__device__ __forceinline__ void regs_mma() { asm volatile("setmaxnreg.dec.sync.aligned.u32 40;"); }
+__device__ __forceinline__ void compute_barrier() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -123,13 +131,13 @@ __device__ __forceinline__ void publish_tiles(uint32_t bar_ready, int tid) {
 }
 
 // ---- tile movement -------------------------------------------------------------------------------------------------
-// load mapping: float4 i = tid + 256 it (it = 0..7) is floats [4 (i & 15), +4) of line i >> 4, so every warp instruction
+// load mapping: float4 i = tid + 512 it (it = 0..3) is floats [4 (i & 15), +4) of line i >> 4, so every warp instruction
 // reads 512 contiguous bytes (two whole rows).  A thread's four floats become one 8-byte half chunk in each bf16 piece.
-__device__ __forceinline__ void load_tile(float4 (&reg)[8], const float* __restrict__ src, int64_t row0, int64_t M,
+__device__ __forceinline__ void load_tile(float4 (&reg)[NLD], const float* __restrict__ src, int64_t row0, int64_t M,
                                           int tid) {
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-        const int i = tid + it * TC_THREADS;
+    for (int it = 0; it < NLD; ++it) {
+        const int i = tid + it * CTHREADS;
         const int64_t m = row0 + (i >> 4);
         reg[it] = m < M ? ldg_stream4(src + m * D + (i & 15) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -143,29 +151,29 @@ __device__ __forceinline__ void store_half_chunk3(uint8_t* tile, int line, int f
     *reinterpret_cast<uint2*>(tile + T16_PIECE + off) = q1;
     *reinterpret_cast<uint2*>(tile + 2 * T16_PIECE + off) = q2;
 }
-__device__ __forceinline__ void store_tile(uint8_t* tile, const float4 (&reg)[8], float scale, int tid) {
+__device__ __forceinline__ void store_tile(uint8_t* tile, const float4 (&reg)[NLD], float scale, int tid) {
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-        const int i = tid + it * TC_THREADS;
+    for (int it = 0; it < NLD; ++it) {
+        const int i = tid + it * CTHREADS;
         const float4 x = reg[it];
         store_half_chunk3(tile, i >> 4, i & 15, make_float4(x.x * scale, x.y * scale, x.z * scale, x.w * scale));
     }
 }
-// epilogue mapping: a thread owns line `r`, columns [32 ch, 32 ch + 32)
-__device__ __forceinline__ void store_row32(uint8_t* tile, int r, int ch, const float (&v)[32]) {
+// epilogue mapping: a thread owns line `r`, columns [16 ch, 16 ch + 16)
+__device__ __forceinline__ void store_row(uint8_t* tile, int r, int ch, const float (&v)[NCOL]) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NCOL / 8; ++j) {
         const float w[8] = {v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3],
                             v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]};
-        store_chunk3(tile, T16_PIECE, r, ch * 4 + j, w);
+        store_chunk3(tile, T16_PIECE, r, ch * (NCOL / 8) + j, w);
     }
 }
 // v *= 1[act > 0], the activation read back from the leading piece of its bf16x3 tile (a positive fp32 rounds to a
 // positive bf16: same exponent range)
-__device__ __forceinline__ void mask_row32(const uint8_t* act_tile, int r, int ch, float (&v)[32]) {
+__device__ __forceinline__ void mask_row(const uint8_t* act_tile, int r, int ch, float (&v)[NCOL]) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const uint4 q = *reinterpret_cast<const uint4*>(act_tile + t16_chunk_off(r, ch * 4 + j));
+    for (int j = 0; j < NCOL / 8; ++j) {
+        const uint4 q = *reinterpret_cast<const uint4*>(act_tile + t16_chunk_off(r, ch * (NCOL / 8) + j));
         const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -175,51 +183,64 @@ __device__ __forceinline__ void mask_row32(const uint8_t* act_tile, int r, int c
         }
     }
 }
-// Coalesced global stores of an accumulator block.  After tcgen05.ld a lane holds 32 consecutive floats of ONE row, so
+// Coalesced global traffic for an accumulator block.  After tcgen05.ld a lane holds 16 consecutive floats of ONE row, so
 // a direct store makes every warp instruction touch 32 different rows (32 separate 16-byte pieces).  Each warp instead
-// transposes its 32 rows x 128 bytes through a private 4 KB shared-memory patch (16-byte chunks XOR-swizzled by the row:
-// conflict-free both ways) and writes 4 rows x 128 contiguous bytes per instruction.  In the read-back mapping lane l
-// handles row 4 i + (l >> 3), floats [4 (l & 7), +4) of the block for i = 0..7; `op(i, row, x)` may transform the value.
+// transposes its 32 rows x 64 bytes through a private 2 KB shared-memory patch (16-byte chunks XOR-swizzled by the row:
+// conflict-free both ways) and moves 8 rows x 64 contiguous bytes per instruction.  In the "wide" mapping lane l handles
+// row 8 i + (l >> 2), floats [4 (l & 3), +4) of the block for i = 0..3; `op(i, row, x)` may transform a stored value.
+__device__ __forceinline__ uint32_t patch_off(int r, int c) { return (uint32_t)(r * 64 + ((c ^ ((r >> 1) & 3)) << 4)); }
 template <typename Op>
-__device__ __forceinline__ void warp_store_block(uint8_t* patch, const float (&v)[32], float* gblock, int rows_valid,
+__device__ __forceinline__ void warp_store_block(uint8_t* patch, const float (&v)[NCOL], float* gblock, int rows_valid,
                                                  int lane, Op op) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-        *reinterpret_cast<float4*>(patch + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    for (int j = 0; j < NCOL / 4; ++j)
+        *reinterpret_cast<float4*>(patch + patch_off(lane, j)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     __syncwarp();
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int r = 4 * i + (lane >> 3);
-        float4 x = *reinterpret_cast<const float4*>(patch + r * 128 + (((lane & 7) ^ (r & 7)) << 4));
+    for (int i = 0; i < 4; ++i) {
+        const int r = 8 * i + (lane >> 2);
+        float4 x = *reinterpret_cast<const float4*>(patch + patch_off(r, lane & 3));
         x = op(i, r, x);
-        if (r < rows_valid) *reinterpret_cast<float4*>(gblock + (int64_t)r * D + (lane & 7) * 4) = x;
+        if (r < rows_valid) *reinterpret_cast<float4*>(gblock + (int64_t)r * D + (lane & 3) * 4) = x;
     }
     __syncwarp();
 }
 struct StoreIdentity {
     __device__ __forceinline__ float4 operator()(int, int, float4 x) const { return x; }
 };
-
-// Column sums over the 32 lanes of a warp by recursive halving: lane l returns sum over lanes of v[l].  Fixed order.
-__device__ __forceinline__ float warp_colsum32(const float (&v)[32], int lane) {
-    float t[16];
+// the reverse: values loaded in the wide mapping (w[i] = row 8 i + (l >> 2), floats 4 (l & 3)) -> this lane's row
+__device__ __forceinline__ void warp_gather_row(uint8_t* patch, const float4 (&w)[4], float (&v)[NCOL], int lane) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(patch + patch_off(8 * i + (lane >> 2), lane & 3)) = w[i];
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < NCOL / 4; ++j) {
+        const float4 x = *reinterpret_cast<const float4*>(patch + patch_off(lane, j));
+        v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
+    }
+    __syncwarp();
+}
+
+// Column sums over the 32 lanes of a warp by recursive halving; lanes l and l ^ 1 both return the sum over all lanes of
+// v[(l >> 1) & 15].  Fixed order.
+__device__ __forceinline__ float warp_colsum(const float (&v)[NCOL], int lane) {
+    float t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
         const bool up = (lane & 16) != 0;
-        const float keep = up ? v[i + 16] : v[i], send = up ? v[i] : v[i + 16];
+        const float keep = up ? v[i + 8] : v[i], send = up ? v[i] : v[i + 8];
         t[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
     }
 #pragma unroll
-    for (int s = 8; s >= 1; s >>= 1) {
+    for (int s = 4; s >= 1; s >>= 1) {
 #pragma unroll
         for (int i = 0; i < s; ++i) {
-            const bool up = (lane & s) != 0;
+            const bool up = (lane & (2 * s)) != 0;
             const float keep = up ? t[i + s] : t[i], send = up ? t[i] : t[i + s];
-            t[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+            t[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2 * s);
         }
     }
-    return t[0];
+    return t[0] + __shfl_xor_sync(0xffffffffu, t[0], 1);
 }
 
 // Optional stage timing (compile with -DGCNN_CHAIN_TIMING): thread 0 of CTA 0 records clock64() at the marked points of its
@@ -274,10 +295,10 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
 
     const int64_t n_tiles = ceil_div(a.M, TC_ROWS);
 
-    if (warp >= 8) {
+    if (warp >= CWARPS) {
         // ================= MMA / weight-copy warp =================
         regs_mma();
-        if (warp == 8 && elect_one()) {
+        if (warp == CWARPS && elect_one()) {
             bulk_load(W0, a.img_n, W16_BYTES, wbar0);
             bulk_load(W1, a.img_o2, W16_BYTES, wbar1);
             bulk_load(W2, a.img_o1a, W16_BYTES, wbar2);
@@ -341,13 +362,14 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
     // ================= compute warps =================
     regs_compute();
     const float s_p = *a.s_p, s_f = *a.s_f;
-    const int q = warp & 3, ch = warp >> 2;
+    const int q = warp & 3, ch = warp >> 2;  // TMEM lane quadrant, 16-column group
     const int r_own = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    uint8_t* const patch = B2g + warp * PATCH;  // this warp's transpose patch (inside B2 whenever B2 is idle)
 
-    float4 ra[8], rb[8];            // register staging of the next activation tiles (load mapping)
+    float4 ra[NLD], rb[NLD];        // register staging of the next activation tiles (load mapping)
     float bsum_p[4] = {};           // column sums of dP (load mapping: columns 4 (tid & 15) .. +4)
-    float bacc[3] = {0.f, 0.f, 0.f};  // column sums of dU2, dU1, deg * dC (epilogue mapping: column 32 ch + lane)
+    float bacc[3] = {0.f, 0.f, 0.f};  // column sums of dU2, dU1, deg * dC (epilogue mapping: column 16 ch + (lane >> 1))
     uint32_t ph_d = 0, ph_w = 0;
     TS_MARK();  // prologue done (TMEM, barriers, role split, registers)
     int iter = 0;
@@ -365,7 +387,7 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
         TS_MARK();  // tile start
         if (iter > 0) { mbar_wait(bar_w, ph_w); ph_w ^= 1; }  // S0 of the previous tile has drained: B0, B1 are free
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
+        for (int it = 0; it < NLD; ++it) {
             bsum_p[0] += ra[it].x; bsum_p[1] += ra[it].y; bsum_p[2] += ra[it].z; bsum_p[3] += ra[it].w;
         }
         store_tile(B0g, ra, 1.f, tid);
@@ -379,11 +401,11 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
         TS_MARK();  // input-gradient MMAs done
         tc_fence_after();
         {
-            float v[32];
-            tmem_ld32(accA + lane_off + (uint32_t)(ch * 32), v);
-            mask_row32(B1g, r_own, ch, v);
-            store_row32(B2g, r_own, ch, v);
-            bacc[0] += warp_colsum32(v, lane);
+            float v[NCOL];
+            tmem_ld16(accA + lane_off + (uint32_t)(ch * NCOL), v);
+            mask_row(B1g, r_own, ch, v);
+            store_row(B2g, r_own, ch, v);
+            bacc[0] += warp_colsum(v, lane);
         }
 
         TS_MARK();  // epilogue done
@@ -401,11 +423,11 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
         TS_MARK();  // input-gradient MMAs done
         tc_fence_after();
         {
-            float v[32];
-            tmem_ld32(accA + lane_off + (uint32_t)(ch * 32), v);
-            mask_row32(B0g, r_own, ch, v);
-            store_row32(B1g, r_own, ch, v);
-            bacc[1] += warp_colsum32(v, lane);
+            float v[NCOL];
+            tmem_ld16(accA + lane_off + (uint32_t)(ch * NCOL), v);
+            mask_row(B0g, r_own, ch, v);
+            store_row(B1g, r_own, ch, v);
+            bacc[1] += warp_colsum(v, lane);
         }
 
         TS_MARK();  // epilogue done
@@ -425,19 +447,19 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
         TS_MARK();  // input-gradient MMAs done
         tc_fence_after();
         {
-            float v[32], x[32], dxt[32];
-            tmem_ld32(accB + lane_off + (uint32_t)(ch * 32), dxt);
-            tmem_ld32(accA + lane_off + (uint32_t)(ch * 32), v);
+            float v[NCOL], x[NCOL], dxt[NCOL];
+            tmem_ld16(accB + lane_off + (uint32_t)(ch * NCOL), dxt);
+            tmem_ld16(accA + lane_off + (uint32_t)(ch * NCOL), v);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { v[i] *= s_p; x[i] = v[i] * deg; }
-            bacc[2] += warp_colsum32(x, lane);
+            for (int i = 0; i < NCOL; ++i) { v[i] *= s_p; x[i] = v[i] * deg; }
+            bacc[2] += warp_colsum(x, lane);
             mbar_wait(bar_w, ph_w); ph_w ^= 1;  // B0, B1, B2 are free
             TS_MARK();  // weight-gradient MMAs done
-            store_row32(B1g, r_own, ch, v);
-            // dXt leaves through this warp's patch of B2 (X_t is dead): coalesced 128-byte row pieces
+            store_row(B1g, r_own, ch, v);
+            // dXt leaves through this warp's patch of B2 (X_t is dead): coalesced 64-byte row pieces
             const int64_t wrow0 = row0 + q * 32;
             const int rows_valid = (int)max((int64_t)0, min((int64_t)32, a.M - wrow0));
-            warp_store_block(B2g + warp * 4096, dxt, a.dXt + wrow0 * D + ch * 32, rows_valid, lane, StoreIdentity());
+            warp_store_block(patch, dxt, a.dXt + wrow0 * D + ch * NCOL, rows_valid, lane, StoreIdentity());
         }
         store_tile(B0g, ra, 1.f, tid);
 
@@ -445,14 +467,14 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
         TS_MARK();  // tiles stored
         publish_tiles(bar_ready, tid);
         TS_MARK();  // published
-        // active-edge counts in the coalesced store mapping (row 4 i + (lane >> 3) of this warp's 32, 4 floats at 4 (lane & 7))
+        // active-edge counts in the wide (coalesced) mapping: row 8 i + (lane >> 2) of this warp's 32, floats 4 (lane & 3)
         const int64_t wrow0 = row0 + q * 32;
         const int rows_valid = (int)max((int64_t)0, min((int64_t)32, a.M - wrow0));
-        float4 cn[8];
+        float4 cn[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int r = 4 * i + (lane >> 3);
-            cn[i] = r < rows_valid ? ldg_stream4(a.cnt + (wrow0 + r) * D + ch * 32 + (lane & 7) * 4)
+        for (int i = 0; i < 4; ++i) {
+            const int r = 8 * i + (lane >> 2);
+            cn[i] = r < rows_valid ? ldg_stream4(a.cnt + (wrow0 + r) * D + ch * NCOL + (lane & 3) * 4)
                                    : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if (has_next) {
@@ -464,14 +486,14 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
         TS_MARK();  // input-gradient MMAs done
         tc_fence_after();
         {
-            float v[32];
-            tmem_ld32(accA + lane_off + (uint32_t)(ch * 32), v);
-            float* dr = a.dR + wrow0 * D + ch * 32;
+            float v[NCOL];
+            tmem_ld16(accA + lane_off + (uint32_t)(ch * NCOL), v);
+            float* dr = a.dR + wrow0 * D + ch * NCOL;
             // G and dR = s_f G cnt through this warp's patch of B2 (free since S1's weight-gradient MMAs drained)
-            warp_store_block(B2g + warp * 4096, v, a.G + wrow0 * D + ch * 32, rows_valid, lane,
+            warp_store_block(patch, v, a.G + wrow0 * D + ch * NCOL, rows_valid, lane,
                              [&](int i, int r, float4 x) {
                                  if (r < rows_valid)
-                                     *reinterpret_cast<float4*>(dr + (int64_t)r * D + (lane & 7) * 4) = make_float4(
+                                     *reinterpret_cast<float4*>(dr + (int64_t)r * D + (lane & 3) * 4) = make_float4(
                                          s_f * x.x * cn[i].x, s_f * x.y * cn[i].y, s_f * x.z * cn[i].z, s_f * x.w * cn[i].w);
                                  return x;
                              });
@@ -489,25 +511,25 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
             if (w == 2 || q < 2) {  // 64-feature gradients live in TMEM lanes 0..63 (warp-uniform condition)
-                float v[32];
-                tmem_ld32(accs[w] + lane_off + (uint32_t)(ch * 32), v);
-                warp_store_block(B2g + warp * 4096, v, part + offs[w] + (q * 32) * D + ch * 32, 32, lane, StoreIdentity());
+                float v[NCOL];
+                tmem_ld16(accs[w] + lane_off + (uint32_t)(ch * NCOL), v);
+                warp_store_block(patch, v, part + offs[w] + (q * 32) * D + ch * NCOL, 32, lane, StoreIdentity());
             }
         }
     }
-    // bias sums: the tile buffers are dead now, use B0 as scratch.  red_p[16 line groups][64], red_e[3][4 quadrants][64]
+    // bias sums: the tile buffers are dead now, use B0 as scratch.  red_p[32 line groups][64], red_e[3][4 quadrants][64]
     float* red_p = reinterpret_cast<float*>(B0g);
-    float* red_e = red_p + 16 * D;
+    float* red_e = red_p + 32 * D;
     compute_barrier();
 #pragma unroll
     for (int j = 0; j < 4; ++j) red_p[(tid >> 4) * D + (tid & 15) * 4 + j] = bsum_p[j];
-#pragma unroll
-    for (int s = 0; s < 3; ++s) red_e[(s * 4 + q) * D + ch * 32 + lane] = bacc[s];
+    if ((lane & 1) == 0)
+        for (int s = 0; s < 3; ++s) red_e[(s * 4 + q) * D + ch * NCOL + (lane >> 1)] = bacc[s];
     compute_barrier();
     if (tid < D) {
         float t = 0.f;
 #pragma unroll
-        for (int g = 0; g < 16; ++g) t += red_p[g * D + tid];
+        for (int g = 0; g < 32; ++g) t += red_p[g * D + tid];
         part[D * D + tid] = t;
     } else if (tid < 4 * D) {
         const int s = (tid >> 6) - 1, c = tid & 63;
@@ -600,10 +622,10 @@ tc_embed_backward_kernel(const EmbBwdArgs a) {
     const uint32_t tm = tmem_slot;
     const uint32_t accA = tm, acc_w0 = tm + 64, acc_w1 = tm + 128, acc_w2 = tm + 192, acc_wx = tm + 256;
     const int64_t n_tiles = ceil_div(a.M, TC_ROWS);
-    if (warp >= 8) {
+    if (warp >= CWARPS) {
         // ================= MMA / weight-copy warp =================
         regs_mma();
-        if (warp == 8 && elect_one()) {
+        if (warp == CWARPS && elect_one()) {
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(wbar), "r"((two ? 3u : 2u) * W16_BYTES) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          ::"r"(W0), "l"(a.img_p0), "r"(W16_BYTES), "r"(wbar) : "memory");
@@ -647,31 +669,32 @@ tc_embed_backward_kernel(const EmbBwdArgs a) {
     }
     // ================= compute warps =================
     regs_compute();
-    const int q = warp & 3, ch = warp >> 2;
+    const int q = warp & 3, ch = warp >> 2;  // TMEM lane quadrant, 16-column group
     const int r_own = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    uint8_t* const patch = B2g + warp * PATCH;  // this warp's transpose patch (inside B2 whenever B2 is idle)
 
-    float4 ra[8], rb[8], rc[8];
+    float4 ra[NLD], rb[NLD], rc[NLD];
     float bsum0[4] = {}, bsum1[4] = {};
     float bacc[2] = {0.f, 0.f};  // column sums of g0 and dh1 (epilogue mapping)
     uint32_t ph_d = 0, ph_w = 0;
     int iter = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) rc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < NLD; ++i) rc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     load_tile(ra, a.dP0, (int64_t)blockIdx.x * TC_ROWS, a.M, tid);
     load_tile(rb, a.out, (int64_t)blockIdx.x * TC_ROWS, a.M, tid);
     if (two) load_tile(rc, a.dP1, (int64_t)blockIdx.x * TC_ROWS, a.M, tid);
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
         const int64_t row0 = tile * TC_ROWS;
-        const int64_t m_own = row0 + r_own;
-        const bool row_ok = m_own < a.M;
         const bool has_next = tile + gridDim.x < n_tiles;
+        const int64_t wrow0 = row0 + q * 32;
+        const int rows_valid = (int)max((int64_t)0, min((int64_t)32, a.M - wrow0));
 
         // ---------------- E0 ----------------
         if (iter > 0) { mbar_wait(bar_w, ph_w); ph_w ^= 1; }
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
+        for (int it = 0; it < NLD; ++it) {
             bsum0[0] += ra[it].x; bsum0[1] += ra[it].y; bsum0[2] += ra[it].z; bsum0[3] += ra[it].w;
             bsum1[0] += rc[it].x; bsum1[1] += rc[it].y; bsum1[2] += rc[it].z; bsum1[3] += rc[it].w;
         }
@@ -680,33 +703,36 @@ tc_embed_backward_kernel(const EmbBwdArgs a) {
         if (two) store_tile(B2g, rc, 1.f, tid);
         publish_tiles(bar_ready, tid);
         load_tile(ra, a.h1, row0, a.M, tid);
-        float4 dx[8];
+        float4 dx[4];  // gradient from the concat branch, wide (coalesced) mapping
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-            dx[j] = row_ok ? ldg_stream4(a.dXt + m_own * D + ch * 32 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 4; ++i) {
+            const int r = 8 * i + (lane >> 2);
+            dx[i] = r < rows_valid ? ldg_stream4(a.dXt + (wrow0 + r) * D + ch * NCOL + (lane & 3) * 4)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         mbar_wait(bar_d, ph_d); ph_d ^= 1;
         tc_fence_after();
         {
-            float v[32];
-            tmem_ld32(accA + lane_off + (uint32_t)(ch * 32), v);
+            float v[NCOL], xr[NCOL];
+            tmem_ld16(accA + lane_off + (uint32_t)(ch * NCOL), v);
+            mbar_wait(bar_w, ph_w); ph_w ^= 1;  // B0 (dP_0) and B2 (dP_1) are free: B2 hosts the transpose patches
+            warp_gather_row(patch, dx, xr, lane);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                v[4 * j] += dx[j].x; v[4 * j + 1] += dx[j].y; v[4 * j + 2] += dx[j].z; v[4 * j + 3] += dx[j].w;
-            }
-            mask_row32(B1g, r_own, ch, v);
-            bacc[0] += warp_colsum32(v, lane);
-            mbar_wait(bar_w, ph_w); ph_w ^= 1;  // B0 (dP_0) and B2 (dP_1) are free
-            store_row32(B0g, r_own, ch, v);
+            for (int j = 0; j < NCOL; ++j) v[j] += xr[j];
+            mask_row(B1g, r_own, ch, v);
+            bacc[0] += warp_colsum(v, lane);
+            store_row(B0g, r_own, ch, v);
         }
+        compute_barrier();  // every warp is done with its patch before B2 receives the h1 tile
         store_tile(B2g, ra, 1.f, tid);
 
         // ---------------- E1 ----------------
         publish_tiles(bar_ready, tid);
         // raw input features of this thread's four (line, chunk) items: only chunks 0 and 1 can hold features (K <= 14)
-        float xn[4][8];
+        float xn[2][8];
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-            const int i = tid + it * TC_THREADS;
+        for (int it = 0; it < 2; ++it) {
+            const int i = tid + it * CTHREADS;
             const int64_t m = row0 + (i >> 3);
             const int c0 = (i & 7) * 8;
 #pragma unroll
@@ -718,18 +744,18 @@ tc_embed_backward_kernel(const EmbBwdArgs a) {
         mbar_wait(bar_d, ph_d); ph_d ^= 1;
         tc_fence_after();
         {
-            float v[32];
-            tmem_ld32(accA + lane_off + (uint32_t)(ch * 32), v);
-            mask_row32(B2g, r_own, ch, v);
-            bacc[1] += warp_colsum32(v, lane);
-            store_row32(B1g, r_own, ch, v);
+            float v[NCOL];
+            tmem_ld16(accA + lane_off + (uint32_t)(ch * NCOL), v);
+            mask_row(B2g, r_own, ch, v);
+            bacc[1] += warp_colsum(v, lane);
+            store_row(B1g, r_own, ch, v);
         }
 
         // ---------------- E2 ----------------
         mbar_wait(bar_w, ph_w); ph_w ^= 1;  // B0 (g0) and B2 (h1) are free as far as the tensor core is concerned
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-            const int i = tid + it * TC_THREADS;
+        for (int it = 0; it < 2; ++it) {
+            const int i = tid + it * CTHREADS;
             store_chunk3(B0g, T16_PIECE, i >> 3, i & 7, xn[it]);
         }
         publish_tiles(bar_ready, tid);
@@ -749,30 +775,29 @@ tc_embed_backward_kernel(const EmbBwdArgs a) {
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
             if (q < 2 && (w != 1 || two)) {
-                float v[32];
-                tmem_ld32(accs[w] + lane_off + (uint32_t)(ch * 32), v);
-                warp_store_block(B2g + warp * 4096, v, part + w * (D * D + D) + (q * 32) * D + ch * 32, 32, lane,
-                                 StoreIdentity());
+                float v[NCOL];
+                tmem_ld16(accs[w] + lane_off + (uint32_t)(ch * NCOL), v);
+                warp_store_block(patch, v, part + w * (D * D + D) + (q * 32) * D + ch * NCOL, 32, lane, StoreIdentity());
             }
         }
     }
-    float* red_p = reinterpret_cast<float*>(B0g);  // [2][16 line groups][64]
-    float* red_e = red_p + 2 * 16 * D;             // [2][4 quadrants][64]
+    float* red_p = reinterpret_cast<float*>(B0g);  // [2][32 line groups][64]
+    float* red_e = red_p + 2 * 32 * D;             // [2][4 quadrants][64]
     compute_barrier();
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         red_p[(tid >> 4) * D + (tid & 15) * 4 + j] = bsum0[j];
-        red_p[16 * D + (tid >> 4) * D + (tid & 15) * 4 + j] = bsum1[j];
+        red_p[32 * D + (tid >> 4) * D + (tid & 15) * 4 + j] = bsum1[j];
     }
-#pragma unroll
-    for (int s = 0; s < 2; ++s) red_e[(s * 4 + q) * D + ch * 32 + lane] = bacc[s];
+    if ((lane & 1) == 0)
+        for (int s = 0; s < 2; ++s) red_e[(s * 4 + q) * D + ch * NCOL + (lane >> 1)] = bacc[s];
     compute_barrier();
-    {
+    if (tid < 4 * D) {
         const int s = tid >> 6, c = tid & 63;  // s: 0 = b_0, 1 = b_1, 2 = b2, 3 = b1
         float t = 0.f;
         if (s < 2) {
 #pragma unroll
-            for (int g = 0; g < 16; ++g) t += red_p[s * 16 * D + g * D + c];
+            for (int g = 0; g < 32; ++g) t += red_p[s * 32 * D + g * D + c];
         } else {
             const int e = s - 2;
             t = ((red_e[(e * 4 + 0) * D + c] + red_e[(e * 4 + 1) * D + c]) + red_e[(e * 4 + 2) * D + c]) +
