@@ -82,7 +82,7 @@ __device__ __forceinline__ void issue_wgrad(uint32_t tmem_d, uint32_t act_tile, 
     asm volatile("" : "+r"(act_tile), "+r"(g_tile));
     const uint64_t da0 = make_desc_mn16(act_tile, lbo), db0 = make_desc_mn16(g_tile, T16_BYTES);
 #pragma unroll 1
-    for (int p = 0; p < 6; ++p) {
+    for (int p = 1; p < 6; ++p) {  // the activation operand carries two pieces: (1,1) (0,2) (1,0) (0,1) (0,0)
         const uint32_t pa = (0x001012u >> (4 * p)) & 3u, pb = (0x010210u >> (4 * p)) & 3u;
         const uint64_t da = da0 + (uint64_t)(pa * (T16_PIECE >> 4)), db = db0 + (uint64_t)(pb * (T16_PIECE >> 4));
 #pragma unroll
@@ -142,6 +142,10 @@ __device__ __forceinline__ void load_tile(float4 (&reg)[NLD], const float* __res
         reg[it] = m < M ? ldg_stream4(src + m * D + (i & 15) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
+// PIECES = 3 for gradient tiles (operands of the input-gradient MMAs, fp32-level accuracy through the chain); PIECES = 2
+// for the saved activations, which are only the A operand of a weight-gradient MMA (a sum over all rows: 16 operand bits
+// leave its relative L2 error near 3e-6) and the source of the ReLU masks.
+template <int PIECES>
 __device__ __forceinline__ void store_half_chunk3(uint8_t* tile, int line, int f4, float4 v) {
     uint2 q0, q1, q2;
     split3_pair(v.x, v.y, q0.x, q1.x, q2.x);
@@ -149,14 +153,15 @@ __device__ __forceinline__ void store_half_chunk3(uint8_t* tile, int line, int f
     const uint32_t off = t16_chunk_off(line, f4 >> 1) + (uint32_t)(f4 & 1) * 8u;
     *reinterpret_cast<uint2*>(tile + off) = q0;
     *reinterpret_cast<uint2*>(tile + T16_PIECE + off) = q1;
-    *reinterpret_cast<uint2*>(tile + 2 * T16_PIECE + off) = q2;
+    if (PIECES == 3) *reinterpret_cast<uint2*>(tile + 2 * T16_PIECE + off) = q2;
 }
+template <int PIECES>
 __device__ __forceinline__ void store_tile(uint8_t* tile, const float4 (&reg)[NLD], float scale, int tid) {
 #pragma unroll
     for (int it = 0; it < NLD; ++it) {
         const int i = tid + it * CTHREADS;
         const float4 x = reg[it];
-        store_half_chunk3(tile, i >> 4, i & 15, make_float4(x.x * scale, x.y * scale, x.z * scale, x.w * scale));
+        store_half_chunk3<PIECES>(tile, i >> 4, i & 15, make_float4(x.x * scale, x.y * scale, x.z * scale, x.w * scale));
     }
 }
 // epilogue mapping: a thread owns line `r`, columns [16 ch, 16 ch + 16)
@@ -390,8 +395,8 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
         for (int it = 0; it < NLD; ++it) {
             bsum_p[0] += ra[it].x; bsum_p[1] += ra[it].y; bsum_p[2] += ra[it].z; bsum_p[3] += ra[it].w;
         }
-        store_tile(B0g, ra, 1.f, tid);
-        store_tile(B1g, rb, 1.f, tid);
+        store_tile<3>(B0g, ra, 1.f, tid);
+        store_tile<2>(B1g, rb, 1.f, tid);
         TS_MARK();  // tiles stored
         publish_tiles(bar_ready, tid);
         TS_MARK();  // published
@@ -412,7 +417,7 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
         // ---------------- S2: output layer 2 ----------------
         mbar_wait(bar_w, ph_w); ph_w ^= 1;  // B0 (dP) and B1 (Y) are free
         TS_MARK();  // weight-gradient MMAs done
-        store_tile(B0g, ra, 1.f, tid);
+        store_tile<2>(B0g, ra, 1.f, tid);
         TS_MARK();  // tiles stored
         publish_tiles(bar_ready, tid);
         TS_MARK();  // published
@@ -435,8 +440,8 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
         mbar_wait(bar_w, ph_w); ph_w ^= 1;  // the tensor core is done with B0 (U1) and B2 (dU2) ...
         TS_MARK();  // weight-gradient MMAs done
         compute_barrier();                  // ... and so are the S2 epilogues of the other warps (ReLU mask read from B0)
-        store_tile(B0g, ra, s_p, tid);
-        store_tile(B2g, rb, 1.f, tid);
+        store_tile<2>(B0g, ra, s_p, tid);
+        store_tile<2>(B2g, rb, 1.f, tid);
         TS_MARK();  // tiles stored
         publish_tiles(bar_ready, tid);
         TS_MARK();  // published
@@ -461,7 +466,7 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
             const int rows_valid = (int)max((int64_t)0, min((int64_t)32, a.M - wrow0));
             warp_store_block(patch, dxt, a.dXt + wrow0 * D + ch * NCOL, rows_valid, lane, StoreIdentity());
         }
-        store_tile(B0g, ra, 1.f, tid);
+        store_tile<2>(B0g, ra, 1.f, tid);
 
         // ---------------- S0: hoisted feature_module_final ----------------
         TS_MARK();  // tiles stored
@@ -698,9 +703,9 @@ tc_embed_backward_kernel(const EmbBwdArgs a) {
             bsum0[0] += ra[it].x; bsum0[1] += ra[it].y; bsum0[2] += ra[it].z; bsum0[3] += ra[it].w;
             bsum1[0] += rc[it].x; bsum1[1] += rc[it].y; bsum1[2] += rc[it].z; bsum1[3] += rc[it].w;
         }
-        store_tile(B0g, ra, 1.f, tid);
-        store_tile(B1g, rb, 1.f, tid);
-        if (two) store_tile(B2g, rc, 1.f, tid);
+        store_tile<3>(B0g, ra, 1.f, tid);
+        store_tile<2>(B1g, rb, 1.f, tid);
+        if (two) store_tile<3>(B2g, rc, 1.f, tid);
         publish_tiles(bar_ready, tid);
         load_tile(ra, a.h1, row0, a.M, tid);
         float4 dx[4];  // gradient from the concat branch, wide (coalesced) mapping
@@ -724,7 +729,7 @@ tc_embed_backward_kernel(const EmbBwdArgs a) {
             store_row(B0g, r_own, ch, v);
         }
         compute_barrier();  // every warp is done with its patch before B2 receives the h1 tile
-        store_tile(B2g, ra, 1.f, tid);
+        store_tile<2>(B2g, ra, 1.f, tid);
 
         // ---------------- E1 ----------------
         publish_tiles(bar_ready, tid);
