@@ -24,6 +24,10 @@ namespace gcnn {
 
 constexpr uint32_t IDESC_BF16_KK = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 constexpr uint32_t IDESC_BF16_MN = IDESC_BF16_KK | (1u << 15) | (1u << 16);  // A and B MN-major
+// M = 64 variant for the weight gradients of 64-feature layers: the A operand is ONE 64-wide block (2 KB per 16 lines
+// instead of 4 KB with a don't-care second block) -- these kernels are bound by the tensor core's operand reads from
+// shared memory.  D row r lives in TMEM lane 32 (r / 16) + r % 16 (sixteen rows per 32-lane quadrant).
+constexpr uint32_t IDESC_BF16_MN_M64 = (IDESC_BF16_MN & ~(0x1Fu << 24)) | ((64u >> 4) << 24);
 
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate) {
@@ -77,6 +81,7 @@ __device__ __forceinline__ void issue_dgrad(uint32_t tmem_d, uint32_t a_tile, ui
 // dW[f][c] (+)= sum over the 128 lines of act[line][f] * g[line][c]: both operands MN-major views of bf16x3 tiles, the
 // reduction (K) runs over lines, 16 per instruction.  The M = 128 instruction reads a second 64-feature block `lbo` bytes
 // after the first (the right half of the concat, or don't-care data whose result rows 64..127 are never read).
+template <bool M64 = false>
 __device__ __forceinline__ void issue_wgrad(uint32_t tmem_d, uint32_t act_tile, uint32_t lbo, uint32_t g_tile,
                                             uint32_t acc) {
     asm volatile("" : "+r"(act_tile), "+r"(g_tile));
@@ -87,7 +92,8 @@ __device__ __forceinline__ void issue_wgrad(uint32_t tmem_d, uint32_t act_tile, 
         const uint64_t da = da0 + (uint64_t)(pa * (T16_PIECE >> 4)), db = db0 + (uint64_t)(pb * (T16_PIECE >> 4));
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
-            umma_bf16(tmem_d, da + (uint64_t)(ks * (2048 >> 4)), db + (uint64_t)(ks * (2048 >> 4)), IDESC_BF16_MN, acc);
+            umma_bf16(tmem_d, da + (uint64_t)(ks * (2048 >> 4)), db + (uint64_t)(ks * (2048 >> 4)),
+                      M64 ? IDESC_BF16_MN_M64 : IDESC_BF16_MN, acc);
             acc = 1;
         }
     }
@@ -318,7 +324,7 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
                 mbar_wait(wbar0, 0);
                 issue_dgrad(accA, B0, W0, 0);
                 umma_commit(bar_d);
-                issue_wgrad(acc_wn, B1, T16_BYTES, B0, wacc);
+                issue_wgrad<true>(acc_wn, B1, T16_BYTES, B0, wacc);
                 umma_commit(bar_w);
                 mbar_wait(bar_d, ph_dd); ph_dd ^= 1;  // slot 0 is free
                 bulk_load(W0, a.img_o1b, W16_BYTES, wbar0);
@@ -328,7 +334,7 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
                 mbar_wait(wbar1, 0);
                 issue_dgrad(accA, B2, W1, 0);
                 umma_commit(bar_d);
-                issue_wgrad(acc_wo2, B0, T16_BYTES, B2, wacc);
+                issue_wgrad<true>(acc_wo2, B0, T16_BYTES, B2, wacc);
                 umma_commit(bar_w);
                 mbar_wait(bar_d, ph_dd); ph_dd ^= 1;  // slot 1 is free
                 bulk_load(W1, a.img_f, W16_BYTES, wbar1);
@@ -353,7 +359,7 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
                 mbar_wait(wbar1, 1);
                 issue_dgrad(accA, B1, W1, 0);
                 umma_commit(bar_d);
-                issue_wgrad(acc_wf, B0, T16_BYTES, B1, wacc);
+                issue_wgrad<true>(acc_wf, B0, T16_BYTES, B1, wacc);
                 umma_commit(bar_w);
                 mbar_wait(bar_d, ph_dd); ph_dd ^= 1;  // slot 1 is free
                 if (has_next) bulk_load(W1, a.img_o2, W16_BYTES, wbar1);
@@ -515,11 +521,12 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
         const int offs[4] = {0, D * D + D, 2 * (D * D + D), 2 * (D * D + D) + 2 * D * D + D};
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
-            if (w == 2 || q < 2) {  // 64-feature gradients live in TMEM lanes 0..63 (warp-uniform condition)
-                float v[NCOL];
-                tmem_ld16(accs[w] + lane_off + (uint32_t)(ch * NCOL), v);
+            float v[NCOL];
+            tmem_ld16(accs[w] + lane_off + (uint32_t)(ch * NCOL), v);
+            if (w == 2)  // M = 128: feature row = TMEM lane
                 warp_store_block(patch, v, part + offs[w] + (q * 32) * D + ch * NCOL, 32, lane, StoreIdentity());
-            }
+            else         // M = 64: lanes 0..15 of quadrant q hold feature rows 16 q .. 16 q + 15
+                warp_store_block(patch, v, part + offs[w] + (q * 16) * D + ch * NCOL, 16, lane, StoreIdentity());
         }
     }
     // bias sums: the tile buffers are dead now, use B0 as scratch.  red_p[32 line groups][64], red_e[3][4 quadrants][64]
@@ -650,20 +657,20 @@ tc_embed_backward_kernel(const EmbBwdArgs a) {
                 issue_dgrad(accA, B0, W0, 0);
                 if (two) issue_dgrad(accA, B2, W1, 1);
                 umma_commit(bar_d);
-                issue_wgrad(acc_w0, B1, T16_BYTES, B0, wacc);
-                if (two) issue_wgrad(acc_w1, B1, T16_BYTES, B2, wacc);
+                issue_wgrad<true>(acc_w0, B1, T16_BYTES, B0, wacc);
+                if (two) issue_wgrad<true>(acc_w1, B1, T16_BYTES, B2, wacc);
                 umma_commit(bar_w);
                 // E1
                 mbar_wait(bar_ready, ph_r); ph_r ^= 1;
                 tc_fence_after();
                 issue_dgrad(accA, B0, W2, 0);
                 umma_commit(bar_d);
-                issue_wgrad(acc_w2, B2, T16_BYTES, B0, wacc);
+                issue_wgrad<true>(acc_w2, B2, T16_BYTES, B0, wacc);
                 umma_commit(bar_w);
                 // E2
                 mbar_wait(bar_ready, ph_r); ph_r ^= 1;
                 tc_fence_after();
-                issue_wgrad(acc_wx, B0, T16_BYTES, B1, wacc);
+                issue_wgrad<true>(acc_wx, B0, T16_BYTES, B1, wacc);
                 umma_commit(bar_w);
             }
         }
@@ -779,10 +786,10 @@ tc_embed_backward_kernel(const EmbBwdArgs a) {
         const uint32_t accs[4] = {acc_w0, acc_w1, acc_w2, acc_wx};
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
-            if (q < 2 && (w != 1 || two)) {
+            if (w != 1 || two) {  // M = 64 accumulators: lanes 0..15 of quadrant q hold feature rows 16 q .. 16 q + 15
                 float v[NCOL];
                 tmem_ld16(accs[w] + lane_off + (uint32_t)(ch * NCOL), v);
-                warp_store_block(patch, v, part + w * (D * D + D) + (q * 32) * D + ch * NCOL, 32, lane, StoreIdentity());
+                warp_store_block(patch, v, part + w * (D * D + D) + (q * 16) * D + ch * NCOL, 16, lane, StoreIdentity());
             }
         }
     }
