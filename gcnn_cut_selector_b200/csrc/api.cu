@@ -95,6 +95,7 @@ struct gcnn_workspace {
     // fused backward chains: per-convolution G, dR (receiving-side projection gradient), dS (sending side), partials
     float *bG[3], *bdR[3], *bdS[3], *chain_partials[3], *emb_partials[3];
     int use_fused_bwd = 1;
+    int use_bf16_fwd = 1;  // forward chains on bf16x3 tiles (node_fwd.cu) instead of 3xTF32 (node_tc.cu)
     // set by gcnn_forward_backward around a fused step: head layer 2, the loss seed and its backward are ONE launch
     int head_fused = 0, head_parts = 0;
     float* loss_out = nullptr;
@@ -349,7 +350,10 @@ static int dense_wgrad(gcnn_workspace* ws, const LinWgradArgs& a, cudaStream_t s
 static int forward_convs_fused(gcnn_workspace* ws, const float* p, const float* pn, const gcnn_batch* b,
                                float* scores_out, int stop_layer, cudaStream_t st, cudaStream_t s1, cudaStream_t s2) {
     const int64_t nc = b->n_cons, nv = b->n_vars, nk = b->n_cuts, ec = b->n_cons_edges, ek = b->n_cut_edges;
-    auto img_t = [&](int param_off) { return ws->tc_images + (int64_t)tc_block_index(param_off) * TC_IMG_FLOATS; };
+    const bool bf16 = ws->use_bf16_fwd != 0;  // bf16x3 T image sits after the 3xTF32 images and the bf16x3 N image
+    auto img_t = [&](int param_off) {
+        return ws->tc_images + (int64_t)tc_block_index(param_off) * TC_IMG_FLOATS + (bf16 ? TC_IMG_TF32_FLOATS + TC_IMG_BF16_ONE : 0);
+    };
     const bool keep = ws->cap.training != 0 || stop_layer >= 0;  // C / U1 are only read by the backward and by the statistics
 
     // (the projections A0, B0, B1, A2 were emitted by the embedding chains)
@@ -387,7 +391,7 @@ static int forward_convs_fused(gcnn_workspace* ws, const float* p, const float* 
         c.img_n = next_img[i]; c.bias_n = next_bias[i]; c.relu_n = next_relu[i];
         c.C = keep ? a.C : nullptr; c.U1 = keep ? a.U1 : nullptr; c.Y = a.Y; c.Pn = next_out[i];
         c.M = n_recv[i];
-        GCNN_TRY(tc_conv_forward(c, st));
+        GCNN_TRY(bf16 ? tc_conv_forward16(c, st) : tc_conv_forward(c, st));
         if (stop_layer == 6 + 2 * i) return wait_all_layouts();
     }
     GCNN_TRY(wait_all_layouts());  // the backward needs the cut by-variable layout
@@ -437,7 +441,10 @@ static int forward_impl(gcnn_workspace* ws, const float* p, const float* pn, con
         auto& e = emb[e_i];
         cudaStream_t se = e_i == 1 ? s2 : st;
         if (fused_fwd) {  // one chain per node type: both Dense layers + the projections that read the embedding
-            auto img_t = [&](int param_off) { return ws->tc_images + (int64_t)tc_block_index(param_off) * TC_IMG_FLOATS; };
+            const bool bf16 = ws->use_bf16_fwd != 0;
+            auto img_t = [&](int param_off) {
+                return ws->tc_images + (int64_t)tc_block_index(param_off) * TC_IMG_FLOATS + (bf16 ? TC_IMG_TF32_FLOATS + TC_IMG_BF16_ONE : 0);
+            };
             EmbFwdArgs f{};
             f.x = e.x; f.K = e.K; f.shift = pn + e.shift; f.scale = pn + e.scale; f.W1 = p + e.o->W1; f.b1 = p + e.o->b1;
             f.img_w2 = img_t(e.o->W2); f.bias2 = p + e.o->b2; f.h1 = e.h1; f.out = e.out; f.M = e.n;
@@ -446,7 +453,7 @@ static int forward_impl(gcnn_workspace* ws, const float* p, const float* pn, con
                 f.img_p[0] = img_t(P.conv[0].Wr); f.P[0] = ws->conv[0].B;
                 f.img_p[1] = img_t(P.conv[1].Wr); f.P[1] = ws->conv[1].B;
             } else { f.img_p[0] = img_t(P.conv[2].Wl); f.bias_p[0] = p + P.conv[2].bl; f.P[0] = ws->conv[2].A; }
-            GCNN_TRY(tc_embed_forward(f, se));
+            GCNN_TRY(bf16 ? tc_embed_forward16(f, se) : tc_embed_forward(f, se));
             continue;
         }
         GCNN_TRY(embed1_forward(e.x, e.K, pn + e.shift, pn + e.scale, p + e.o->W1, p + e.o->b1, e.h1, e.n, se));
@@ -916,6 +923,8 @@ int gcnn_workspace_create(gcnn_workspace** out) {
     ws->use_tiles = ti && ti[0] == '1';
     const char* fu = getenv("GCNN_FUSED");  // GCNN_FUSED=0: one launch per dense layer
     ws->use_fused = !(fu && fu[0] == '0');
+    const char* bf = getenv("GCNN_BF16_FWD");  // GCNN_BF16_FWD=0: 3xTF32 forward chains
+    ws->use_bf16_fwd = !(bf && bf[0] == '0');
     const char* fb = getenv("GCNN_FUSED_BWD");  // GCNN_FUSED_BWD=0: stand-alone dgrad / wgrad launches in the backward
     ws->use_fused_bwd = !(fb && fb[0] == '0');
     for (int i = 0; i < 2; ++i) GCNN_CUDA_TRY(cudaStreamCreateWithFlags(&ws->aux[i], cudaStreamNonBlocking));
@@ -986,6 +995,7 @@ int gcnn_set_option(gcnn_workspace* ws, const char* name, int value) {
     else if (!strcmp(name, "fused")) ws->use_fused = value != 0;
     else if (!strcmp(name, "tiles")) ws->use_tiles = value != 0;
     else if (!strcmp(name, "fused_backward")) ws->use_fused_bwd = value != 0;
+    else if (!strcmp(name, "bf16_forward")) ws->use_bf16_fwd = value != 0;
     else { set_error("unknown option %s", name); return GCNN_INVALID; }
     return GCNN_OK;
 }

@@ -255,6 +255,7 @@ struct ConvFwdArgs {          // fused node chain of one convolution (tc_conv_fo
     int64_t M;
 };
 int tc_conv_forward(const ConvFwdArgs& a, cudaStream_t st);
+int tc_conv_forward16(const ConvFwdArgs& a, cudaStream_t st);  // bf16x3 variant (node_fwd.cu): img_* are bf16x3 T images
 struct ConvBwdArgs {          // fused backward node chain of one convolution (tc_conv_backward, node_bwd.cu)
     const float* dP;          // [M, 64] gradient w.r.t. the pre-activation of the layer that consumed Y
     const float *Y, *U1, *C, *Xt, *H, *cnt;  // saved forward activations, [M, 64] each
@@ -279,6 +280,7 @@ struct EmbFwdArgs {           // fused forward chain of one embedding (tc_embed_
     int64_t M;
 };
 int tc_embed_forward(const EmbFwdArgs& a, cudaStream_t st);
+int tc_embed_forward16(const EmbFwdArgs& a, cudaStream_t st);  // bf16x3 variant (node_fwd.cu)
 struct EmbBwdArgs {           // fused backward chain of one embedding (tc_embed_backward, node_bwd.cu)
     const float* dP0;         // [M, 64] gradient of the first projection fed by this embedding
     const float* dP1;         // second projection (variables feed two convolutions) or nullptr
@@ -308,7 +310,8 @@ struct TcWgradArgs {
 int tc_wgrad(const TcWgradArgs& a, cudaStream_t st);
 int pack_weights(const float* params, const int* block_offsets_dev, int n_blocks, float* images, cudaStream_t st);
 constexpr int TC_IMG_TF32_FLOATS = 4 * 64 * 64;  // T_hi, T_lo, N_hi, N_lo (3xTF32) of one 64 x 64 weight block
-constexpr int TC_IMG_BF16_FLOATS = 3 * 64 * 64 / 2;  // three bf16 pieces of the N image (bf16x3, backward chains): 24 KB
+constexpr int TC_IMG_BF16_ONE = 3 * 64 * 64 / 2;     // one bf16x3 image (three bf16 pieces) in floats: 24 KB
+constexpr int TC_IMG_BF16_FLOATS = 2 * TC_IMG_BF16_ONE;  // N image (backward chains) then T image (forward chains)
 constexpr int TC_IMG_FLOATS = TC_IMG_TF32_FLOATS + TC_IMG_BF16_FLOATS;
 
 // embedding layer 1: h = relu(((x + shift) * scale) W1 + b1), K in {4, 6, 14}

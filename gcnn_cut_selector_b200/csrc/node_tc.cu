@@ -51,6 +51,10 @@ pack_weights_kernel(const float* __restrict__ params, const int* __restrict__ bl
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = Wb[n][chunk * 8 + j];
         store_chunk3(img16, W16_PIECE, n, chunk, v);
+        // ... and the bf16x3 T image for the forward chains (node_fwd.cu): B[n][k] = Wb[k][n]
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = Wb[chunk * 8 + j][n];
+        store_chunk3(img16 + W16_BYTES, W16_PIECE, n, chunk, v);
     }
 }
 
