@@ -46,28 +46,33 @@ __device__ __forceinline__ float4 shfl_xor4(float4 v, int m) {
 __device__ __forceinline__ float2 lo2(const float4 v) { return make_float2(v.x, v.y); }
 __device__ __forceinline__ float2 hi2(const float4 v) { return make_float2(v.z, v.w); }
 
-// y = s_f * ((r + f * w) + g) for four features, two packed instructions triples
-__device__ __forceinline__ void preact4(const float4 r4, const float4 w4, const float4 g, const float f, const float s_f,
+// z = (r + f * w) + g for four features, two packed instruction pairs.  The pre-norm scale s_f of
+// relu(s_f z) (model.py:498, 563) is NOT applied per edge: relu(s_f z) = s_f * [z > 0] z for s_f >= 0 and
+// s_f * [z < 0] z for s_f < 0, so the kernels sum the selected z (template flag NEG, chosen once per kernel from the sign
+// of s_f) and scale once per segment -- two packed multiplies fewer per edge.
+__device__ __forceinline__ void preact4(const float4 r4, const float4 w4, const float4 g, const float f,
                                         float2& y01, float2& y23) {
-    const float2 f2 = make_float2(f, f), s2 = make_float2(s_f, s_f);
-    y01 = __fmul2_rn(__fadd2_rn(__ffma2_rn(f2, lo2(w4), lo2(r4)), lo2(g)), s2);
-    y23 = __fmul2_rn(__fadd2_rn(__ffma2_rn(f2, hi2(w4), hi2(r4)), hi2(g)), s2);
+    const float2 f2 = make_float2(f, f);
+    y01 = __fadd2_rn(__ffma2_rn(f2, lo2(w4), lo2(r4)), lo2(g));
+    y23 = __fadd2_rn(__ffma2_rn(f2, hi2(w4), hi2(r4)), hi2(g));
 }
+template <bool NEG>
+__device__ __forceinline__ bool active(float z) { return NEG ? z < 0.f : z > 0.f; }
 
-template <bool TRAIN>
+template <bool TRAIN, bool NEG>
 __device__ __forceinline__ void relu_accumulate(const float2 y01, const float2 y23, float4& acc, float4& act) {
-    if (y01.x > 0.f) { acc.x += y01.x; if (TRAIN) act.x += 1.f; }
-    if (y01.y > 0.f) { acc.y += y01.y; if (TRAIN) act.y += 1.f; }
-    if (y23.x > 0.f) { acc.z += y23.x; if (TRAIN) act.z += 1.f; }
-    if (y23.y > 0.f) { acc.w += y23.y; if (TRAIN) act.w += 1.f; }
+    if (active<NEG>(y01.x)) { acc.x += y01.x; if (TRAIN) act.x += 1.f; }
+    if (active<NEG>(y01.y)) { acc.y += y01.y; if (TRAIN) act.y += 1.f; }
+    if (active<NEG>(y23.x)) { acc.z += y23.x; if (TRAIN) act.z += 1.f; }
+    if (active<NEG>(y23.y)) { acc.w += y23.y; if (TRAIN) act.w += 1.f; }
 }
 
-template <bool TRAIN>
-__global__ void __launch_bounds__(EDGE_FWD_THREADS)
-edge_forward_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ src, const float* __restrict__ val,
-                    int64_t n_recv, const float* __restrict__ R, const float* __restrict__ S,
-                    const float* __restrict__ w_edge, EdgeScalars sc, float* __restrict__ H, float* __restrict__ cnt) {
-    pdl_enter();
+template <bool TRAIN, bool NEG>
+__device__ __forceinline__ void edge_forward_rows(const int32_t* __restrict__ ptr, const int32_t* __restrict__ src,
+                                                  const float* __restrict__ val, int64_t n_recv,
+                                                  const float* __restrict__ R, const float* __restrict__ S,
+                                                  const float* __restrict__ w_edge, EdgeScalars sc,
+                                                  float* __restrict__ H, float* __restrict__ cnt) {
     const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
     const int warps = blockDim.x >> 5;
     // CTA b owns the contiguous rows [b n / grid, (b + 1) n / grid): neighbouring segments belong to the same sample
@@ -106,8 +111,8 @@ edge_forward_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 float2 y01, y23;
-                preact4(r4, w4, g[u], f[u], s_f, y01, y23);
-                relu_accumulate<TRAIN>(y01, y23, acc, act);
+                preact4(r4, w4, g[u], f[u], y01, y23);
+                relu_accumulate<TRAIN, NEG>(y01, y23, acc, act);
             }
         }
         for (; j0 < n; j0 += 2) {  // tail of the chunk: at most 7 edges
@@ -117,14 +122,15 @@ edge_forward_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__
             const float f = __shfl_sync(0xffffffffu, my_f, j & 31);
             if (ok) {
                 float2 y01, y23;
-                preact4(r4, w4, ld4(Sl + (int64_t)sj * D), f, s_f, y01, y23);
-                relu_accumulate<TRAIN>(y01, y23, acc, act);
+                preact4(r4, w4, ld4(Sl + (int64_t)sj * D), f, y01, y23);
+                relu_accumulate<TRAIN, NEG>(y01, y23, acc, act);
             }
         }
     }
     const float4 acc_o = shfl_xor4(acc, 16);
     if (half == 0) {
-        st4(H + row * D + hl * 4, make_float4(acc.x + acc_o.x, acc.y + acc_o.y, acc.z + acc_o.z, acc.w + acc_o.w));
+        st4(H + row * D + hl * 4, make_float4(s_f * (acc.x + acc_o.x), s_f * (acc.y + acc_o.y), s_f * (acc.z + acc_o.z),
+                                              s_f * (acc.w + acc_o.w)));
     }
     if (TRAIN) {  // (even-edge half) + (odd-edge half); counts are small integers, exact in fp32
         const float4 act_o = shfl_xor4(act, 16);
@@ -132,6 +138,16 @@ edge_forward_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__
             st4(cnt + row * D + hl * 4, make_float4(act_o.x + act.x, act_o.y + act.y, act_o.z + act.z, act_o.w + act.w));
     }
     }  // rows of this CTA
+}
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(EDGE_FWD_THREADS)
+edge_forward_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ src, const float* __restrict__ val,
+                    int64_t n_recv, const float* __restrict__ R, const float* __restrict__ S,
+                    const float* __restrict__ w_edge, EdgeScalars sc, float* __restrict__ H, float* __restrict__ cnt) {
+    pdl_enter();
+    if (*sc.s_f < 0.f) edge_forward_rows<TRAIN, true>(ptr, src, val, n_recv, R, S, w_edge, sc, H, cnt);
+    else edge_forward_rows<TRAIN, false>(ptr, src, val, n_recv, R, S, w_edge, sc, H, cnt);
 }
 
 int edge_forward(const EdgeLayout& L, int64_t n_recv, const float* R, const float* S, const float* w_edge,
@@ -154,21 +170,22 @@ int edge_forward(const EdgeLayout& L, int64_t n_recv, const float* R, const floa
 // Same loop structure as the forward; the masked G rows are accumulated UNSCALED and s_f is applied once per segment
 // (dS) and once per CTA (dw).  dw is reduced warp -> CTA (fixed order) into per-CTA partials.
 // ------------------------------------------------------------------------------------------------------------------
+template <bool NEG>
 __device__ __forceinline__ void masked_accumulate(const float2 y01, const float2 y23, const float4 g, const float f,
                                                   float4& acc, float4& dw) {
-    if (y01.x > 0.f) { acc.x += g.x; dw.x = fmaf(f, g.x, dw.x); }
-    if (y01.y > 0.f) { acc.y += g.y; dw.y = fmaf(f, g.y, dw.y); }
-    if (y23.x > 0.f) { acc.z += g.z; dw.z = fmaf(f, g.z, dw.z); }
-    if (y23.y > 0.f) { acc.w += g.w; dw.w = fmaf(f, g.w, dw.w); }
+    if (active<NEG>(y01.x)) { acc.x += g.x; dw.x = fmaf(f, g.x, dw.x); }
+    if (active<NEG>(y01.y)) { acc.y += g.y; dw.y = fmaf(f, g.y, dw.y); }
+    if (active<NEG>(y23.x)) { acc.z += g.z; dw.z = fmaf(f, g.z, dw.z); }
+    if (active<NEG>(y23.y)) { acc.w += g.w; dw.w = fmaf(f, g.w, dw.w); }
 }
 
-__global__ void __launch_bounds__(EDGE_THREADS)
-edge_backward_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ other,
-                     const float* __restrict__ val, int64_t n_send, const float* __restrict__ R,
-                     const float* __restrict__ S, const float* __restrict__ G, const float* __restrict__ w_edge,
-                     EdgeScalars sc, float* __restrict__ dS, float* __restrict__ dw_partials) {
-    pdl_enter();
-    __shared__ float4 red[EDGE_WARPS][16];
+template <bool NEG>
+__device__ __forceinline__ void edge_backward_rows(const int32_t* __restrict__ ptr, const int32_t* __restrict__ other,
+                                                   const float* __restrict__ val, int64_t n_send,
+                                                   const float* __restrict__ R, const float* __restrict__ S,
+                                                   const float* __restrict__ G, const float* __restrict__ w_edge,
+                                                   EdgeScalars sc, float* __restrict__ dS, float* __restrict__ dw_partials,
+                                                   float4 (*red)[16]) {
     const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15, warp = threadIdx.x >> 5;
     const float f_shift = sc.f_shift ? *sc.f_shift : 0.f, f_scale = sc.f_scale ? *sc.f_scale : 1.f, s_f = *sc.s_f;
     const float4 w4 = ldg4(w_edge + hl * 4);
@@ -206,8 +223,8 @@ edge_backward_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict_
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     float2 y01, y23;
-                    preact4(r[u], w4, s4, f[u], s_f, y01, y23);  // same association as the forward: (R + f w) + S
-                    masked_accumulate(y01, y23, g[u], f[u], acc, dw);
+                    preact4(r[u], w4, s4, f[u], y01, y23);  // same association as the forward: (R + f w) + S
+                    masked_accumulate<NEG>(y01, y23, g[u], f[u], acc, dw);
                 }
             }
             for (; j0 < n; j0 += 2) {
@@ -217,8 +234,8 @@ edge_backward_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict_
                 const float f = __shfl_sync(0xffffffffu, my_f, j & 31);
                 if (ok) {
                     float2 y01, y23;
-                    preact4(ld4(Rl + (int64_t)t * D), w4, s4, f, s_f, y01, y23);
-                    masked_accumulate(y01, y23, ld4(Gl + (int64_t)t * D), f, acc, dw);
+                    preact4(ld4(Rl + (int64_t)t * D), w4, s4, f, y01, y23);
+                    masked_accumulate<NEG>(y01, y23, ld4(Gl + (int64_t)t * D), f, acc, dw);
                 }
             }
         }
@@ -240,6 +257,17 @@ edge_backward_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict_
         }
         st4(dw_partials + (int64_t)blockIdx.x * D + threadIdx.x * 4, t);
     }
+}
+
+__global__ void __launch_bounds__(EDGE_THREADS)
+edge_backward_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ other,
+                     const float* __restrict__ val, int64_t n_send, const float* __restrict__ R,
+                     const float* __restrict__ S, const float* __restrict__ G, const float* __restrict__ w_edge,
+                     EdgeScalars sc, float* __restrict__ dS, float* __restrict__ dw_partials) {
+    pdl_enter();
+    __shared__ float4 red[EDGE_WARPS][16];
+    if (*sc.s_f < 0.f) edge_backward_rows<true>(ptr, other, val, n_send, R, S, G, w_edge, sc, dS, dw_partials, red);
+    else edge_backward_rows<false>(ptr, other, val, n_send, R, S, G, w_edge, sc, dS, dw_partials, red);
 }
 
 int edge_backward_max_partials() { return EDGE_BWD_MAX_CTAS; }
