@@ -98,6 +98,7 @@ struct gcnn_workspace {
     int use_bf16_fwd = 1;  // forward chains on bf16x3 tiles (node_fwd.cu) instead of 3xTF32 (node_tc.cu)
     // set by gcnn_forward_backward around a fused step: head layer 2, the loss seed and its backward are ONE launch
     int head_fused = 0, head_parts = 0;
+    int count_before_loss = 0;  // also write the batch's cut count (as a float) just before the loss sum
     float* loss_out = nullptr;
     // stats
     double *st_partials, *st_out, *st_center;
@@ -684,8 +685,13 @@ static int backward_impl_fused(gcnn_workspace* ws, const float* p, const float* 
     cudaStream_t s2 = aux_stream(ws, 1, st);
 
     if (ws->head_fused) {  // head_loss already produced t_dg and the partials [dw | db | squared error]
-        add_job(ws->partials[slot], ws->head_parts, D + 2, D + 1, P.Wh2);
-        jobs.push_back(ReduceJob{ws->partials[slot] + D + 1, ws->head_parts, D + 2, 1, 0, nullptr, ws->loss_out});
+        add_job(ws->partials[slot], ws->head_parts, D + 3, D + 1, P.Wh2);
+        // [rows | squared error] -> loss_out[-1 .. 0] (option "count_before_loss": the data-parallel bucket tail), else
+        // the squared error alone -> loss_out[0]
+        if (ws->count_before_loss)
+            jobs.push_back(ReduceJob{ws->partials[slot] + D + 1, ws->head_parts, D + 3, 2, 0, nullptr, ws->loss_out - 1});
+        else
+            jobs.push_back(ReduceJob{ws->partials[slot] + D + 2, ws->head_parts, D + 3, 1, 0, nullptr, ws->loss_out});
         ++slot;
     } else {
         GCNN_TRY(head2_backward(ws->g1, p + P.Wh2, d_scores, ws->t_dg, ws->partials[slot], &n_parts, nk, st));
@@ -996,6 +1002,7 @@ int gcnn_set_option(gcnn_workspace* ws, const char* name, int value) {
     else if (!strcmp(name, "tiles")) ws->use_tiles = value != 0;
     else if (!strcmp(name, "fused_backward")) ws->use_fused_bwd = value != 0;
     else if (!strcmp(name, "bf16_forward")) ws->use_bf16_fwd = value != 0;
+    else if (!strcmp(name, "count_before_loss")) ws->count_before_loss = value != 0;
     else { set_error("unknown option %s", name); return GCNN_INVALID; }
     return GCNN_OK;
 }
@@ -1098,6 +1105,10 @@ int gcnn_forward_backward(gcnn_workspace* ws, const float* params, const float* 
                            &ws->head_parts, batch->n_cuts, st);
         else
             rc = mse_seed(scores, targets, batch->n_cuts, seed_scale, ws->d_scores, loss_out, st);
+        if (rc == GCNN_OK && !fuse_head && ws->count_before_loss) {
+            const float n_cuts = (float)batch->n_cuts;  // (pageable source: staged by the driver before the call returns)
+            if (cudaMemcpyAsync(loss_out - 1, &n_cuts, sizeof(float), cudaMemcpyHostToDevice, st) != cudaSuccess) rc = GCNN_CUDA_ERROR;
+        }
     }
     if (rc == GCNN_OK) rc = backward_impl(ws, params, prenorm, batch, ws->d_scores, grads_out, st);
     ws->head_fused = 0;

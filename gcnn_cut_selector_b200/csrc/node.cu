@@ -422,18 +422,18 @@ int head2_forward(const float* g, const float* w, const float* b, float* scores,
 // Training: head layer 2, the MSE seed (model_trainer.py:271: mean over all cuts -> d_score = 2 (p - y) scale) and head
 // layer 2's backward in one launch -- three dependent 3-10 us launches on the critical path otherwise.  Same lane
 // mapping and summation order as head2_forward_kernel, so training and inference produce bit-identical scores.
-// Per-CTA partial: [dw (64) | db | sum of squared errors].
+// Per-CTA partial: [dw (64) | db | rows handled (the cut count, for data-parallel training) | sum of squared errors].
 __global__ void __launch_bounds__(256)
 head_loss_kernel(const float* __restrict__ g, const float* __restrict__ w, const float* __restrict__ b,
                  const float* __restrict__ targets, float scale, float* __restrict__ scores,
                  float* __restrict__ dg_pre, float* __restrict__ partials, int64_t M) {
     pdl_enter();
-    __shared__ float red[16][D + 2];
+    __shared__ float red[16][D + 3];
     const int hl = threadIdx.x & 15, rl = threadIdx.x >> 4;
     const float4 w4 = ld4s(w + hl * 4);
     const float bias = b[0];
     float4 dw = make_float4(0.f, 0.f, 0.f, 0.f);
-    float db = 0.f, sq = 0.f;
+    float db = 0.f, sq = 0.f, rows = 0.f;
     for (int64_t m0 = (int64_t)blockIdx.x * 16; m0 < M; m0 += (int64_t)gridDim.x * 16) {
         const int64_t m = m0 + rl;
         const bool ok = m < M;  // uniform over the 16 lanes of a row
@@ -452,18 +452,19 @@ head_loss_kernel(const float* __restrict__ g, const float* __restrict__ w, const
             if (hl == 0) {
                 scores[m] = p;
                 db += ds;
+                rows += 1.f;
                 sq = fmaf(d, d, sq);
             }
         }
     }
     red[rl][hl * 4 + 0] = dw.x; red[rl][hl * 4 + 1] = dw.y; red[rl][hl * 4 + 2] = dw.z; red[rl][hl * 4 + 3] = dw.w;
-    if (hl == 0) { red[rl][D] = db; red[rl][D + 1] = sq; }
+    if (hl == 0) { red[rl][D] = db; red[rl][D + 1] = rows; red[rl][D + 2] = sq; }
     __syncthreads();
-    if (threadIdx.x < D + 2) {
+    if (threadIdx.x < D + 3) {
         float t = 0.f;
 #pragma unroll
         for (int r = 0; r < 16; ++r) t += red[r][threadIdx.x];
-        partials[(int64_t)blockIdx.x * (D + 2) + threadIdx.x] = t;
+        partials[(int64_t)blockIdx.x * (D + 3) + threadIdx.x] = t;
     }
 }
 

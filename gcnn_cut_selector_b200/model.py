@@ -160,7 +160,8 @@ class GCNN:
         self.adam_m = torch.zeros_like(self.flat_grads)
         self.adam_v = torch.zeros_like(self.flat_grads)
         self.adam_step = 0
-        self._loss_sum = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._loss2 = torch.zeros(2, dtype=torch.float32, device=self.device)  # [cut count (optional) | loss sum]
+        self._loss_sum = self._loss2[1:2]
 
     def __del__(self):
         try:
@@ -319,9 +320,11 @@ class GCNN:
         return self.call
 
     # ---- training step (model_trainer.py:269-273) -----------------------------------------------------------------
-    def loss_and_grads(self, inputs, targets, seed_scale: float | None = None):
+    def loss_and_grads(self, inputs, targets, seed_scale: float | None = None, loss_out: torch.Tensor | None = None):
         """forward + MeanSquaredError + tape.gradient in one library call.  Returns (loss_sum tensor [1], scores);
-        gradients land in ``flat_grads``.  ``seed_scale`` defaults to 1/n_cuts (mean over all cuts of the batch)."""
+        gradients land in ``flat_grads``.  ``seed_scale`` defaults to 1/n_cuts (mean over all cuts of the batch).
+        ``loss_out``: a one-element fp32 device tensor to receive the loss sum instead of the internal buffer (with
+        option "count_before_loss" the element before it receives the cut count)."""
         dev_inputs = inputs if isinstance(inputs, tuple) and isinstance(inputs[0], Batch) else self.prepare_inputs(inputs)
         batch, _keep = dev_inputs
         targets = self._to_device(targets, torch.float32)
@@ -330,8 +333,10 @@ class GCNN:
         scale = (1.0 / max(batch.n_cuts, 1)) if seed_scale is None else float(seed_scale)
         check(self._lib.gcnn_forward_backward(self._ws, self.flat_params.data_ptr(), self.flat_prenorm.data_ptr(),
                                               C.byref(batch), targets.data_ptr(), scale, scores.data_ptr(),
-                                              self.flat_grads.data_ptr(), self._loss_sum.data_ptr(), self._stream()))
-        return self._loss_sum, scores
+                                              self.flat_grads.data_ptr(),
+                                              (loss_out if loss_out is not None else self._loss_sum).data_ptr(),
+                                              self._stream()))
+        return (loss_out if loss_out is not None else self._loss_sum), scores
 
     def apply_gradients(self, lr: float, grad_divisor: torch.Tensor | None = None,
                         beta1=0.9, beta2=0.999, eps=1e-7):
@@ -391,16 +396,17 @@ class GCNN:
         check(self._lib.gcnn_train_step_result(self._ws, slot, C.byref(loss), self._stream()))
         return float(loss.value)
 
-    def loss_and_grads_staged(self, slot: int, seed_scale: float | None = None):
+    def loss_and_grads_staged(self, slot: int, seed_scale: float | None = None, loss_out: torch.Tensor | None = None):
         """``loss_and_grads`` on the batch staged in ``slot`` (data-parallel trainer).  Returns (loss_sum, n_cuts)."""
         batch, tgt = Batch(), C.c_void_p()
         check(self._lib.gcnn_staged_batch(self._ws, slot, C.byref(batch), C.byref(tgt), self._stream()))
         scale = (1.0 / max(batch.n_cuts, 1)) if seed_scale is None else float(seed_scale)
         check(self._lib.gcnn_forward_backward(self._ws, self.flat_params.data_ptr(), self.flat_prenorm.data_ptr(),
                                               C.byref(batch), tgt, scale, None, self.flat_grads.data_ptr(),
-                                              self._loss_sum.data_ptr(), self._stream()))
+                                              (loss_out if loss_out is not None else self._loss_sum).data_ptr(),
+                                              self._stream()))
         check(self._lib.gcnn_release_staged(self._ws, slot, self._stream()))
-        return self._loss_sum, int(batch.n_cuts)
+        return (loss_out if loss_out is not None else self._loss_sum), int(batch.n_cuts)
 
     def score_staged(self, slot: int) -> np.ndarray:
         """Cut scores of the batch staged in ``slot`` (inference), as a host array."""

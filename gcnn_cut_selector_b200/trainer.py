@@ -31,28 +31,35 @@ class DataParallelTrainer:
         self.model, self.lr, self.group = model, lr, group
         self.bucket = torch.zeros(self.N + 2, dtype=torch.float32, device=model.device)
         model.flat_grads = self.bucket[:self.N]
+        # the library writes the local cut count and squared-error sum straight into the bucket tail (no torch ops on
+        # the step's critical path: a scalar assignment from the host alone costs ~60 us of pipeline stall)
+        self.tail_on_device = model.device.type == "cuda"
+        if self.tail_on_device:
+            model.set_option("count_before_loss", 1)
 
     def broadcast_parameters(self, src: int = 0):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             dist.broadcast(self.model.flat_params.detach(), src, group=self.group)
             dist.broadcast(self.model.flat_prenorm, src, group=self.group)
 
-    def step(self, inputs, targets):
-        """One data-parallel optimisation step; returns the global mean loss as a device tensor [1]."""
-        m = self.model
-        loss_sum, scores = m.loss_and_grads(inputs, targets, seed_scale=1.0)
-        self.bucket[self.N] = float(scores.numel())
-        self.bucket[self.N + 1:self.N + 2].copy_(loss_sum)
+    def _finish(self, want_loss: bool):
         reduce_bucket(self.bucket, self.group)
-        m.apply_gradients(self.lr, grad_divisor=self.bucket[self.N:self.N + 1])
-        return self.bucket[self.N + 1:self.N + 2] / self.bucket[self.N:self.N + 1]
+        self.model.apply_gradients(self.lr, grad_divisor=self.bucket[self.N:self.N + 1])
+        return self.bucket[self.N + 1:self.N + 2] / self.bucket[self.N:self.N + 1] if want_loss else None
+
+    def step(self, inputs, targets, want_loss: bool = True):
+        """One data-parallel optimisation step; returns the global mean loss as a device tensor [1] (``want_loss=False``
+        skips that division and returns None)."""
+        m = self.model
+        if self.tail_on_device:
+            m.loss_and_grads(inputs, targets, seed_scale=1.0, loss_out=self.bucket[self.N + 1:self.N + 2])
+        else:
+            loss_sum, scores = m.loss_and_grads(inputs, targets, seed_scale=1.0)
+            self.bucket[self.N] = float(scores.numel())
+            self.bucket[self.N + 1:self.N + 2].copy_(loss_sum)
+        return self._finish(want_loss)
 
     def step_staged(self, slot: int):
         """``step`` on the host batch staged in ``slot`` (GCNN.stage_host): its copy overlapped the previous step."""
-        m = self.model
-        loss_sum, n_cuts = m.loss_and_grads_staged(slot, seed_scale=1.0)
-        self.bucket[self.N] = float(n_cuts)
-        self.bucket[self.N + 1:self.N + 2].copy_(loss_sum)
-        reduce_bucket(self.bucket, self.group)
-        m.apply_gradients(self.lr, grad_divisor=self.bucket[self.N:self.N + 1])
-        return self.bucket[self.N + 1:self.N + 2] / self.bucket[self.N:self.N + 1]
+        self.model.loss_and_grads_staged(slot, seed_scale=1.0, loss_out=self.bucket[self.N + 1:self.N + 2])
+        return self._finish(True)

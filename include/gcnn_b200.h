@@ -135,7 +135,9 @@ int gcnn_mse_seed(const float* scores, const float* targets, int64_t n, float sc
  * gradient is divided by *grad_divisor (device scalar: the all-reduced global cut count) before use. */
 int gcnn_adam_step(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1,
                    float beta2, float eps, int64_t step, const float* grad_divisor, void* stream);
-/* forward + MSE + backward in one call; grads_out/loss_sum_out as above; scores_out optional (may be NULL). */
+/* forward + MSE + backward in one call; grads_out/loss_sum_out as above; scores_out optional (may be NULL).  With option
+ * "count_before_loss" set (gcnn_set_option) the batch's cut count is also written, as a float, to loss_sum_out[-1]: the
+ * data-parallel trainer points loss_sum_out into its all-reduce bucket [gradients | cut count | squared-error sum]. */
 int gcnn_forward_backward(gcnn_workspace* ws, const float* params, const float* prenorm, const gcnn_batch* batch,
                           const float* targets, float seed_scale, float* scores_out, float* grads_out,
                           float* loss_sum_out, void* stream);
