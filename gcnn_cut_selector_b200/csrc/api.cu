@@ -94,8 +94,11 @@ struct gcnn_workspace {
     float* dw_partials[3];
     // fused backward chains: per-convolution G, dR (receiving-side projection gradient), dS (sending side), partials
     float *bG[3], *bdR[3], *bdS[3], *chain_partials[3], *emb_partials[3];
+    uint2* edge_masks[3] = {nullptr, nullptr, nullptr};  // per-edge ReLU masks of each convolution (by original edge id)
+    int masks_valid[3] = {0, 0, 0};
     int use_fused_bwd = 1;
-    int use_bf16_fwd = 1;  // forward chains on bf16x3 tiles (node_fwd.cu) instead of 3xTF32 (node_tc.cu)
+    int use_bf16_fwd = 1;
+    int use_edge_masks = 1;  // forward edge kernel records per-edge ReLU masks, the backward reads them  // forward chains on bf16x3 tiles (node_fwd.cu) instead of 3xTF32 (node_tc.cu)
     // set by gcnn_forward_backward around a fused step: head layer 2, the loss seed and its backward are ONE launch
     int head_fused = 0, head_parts = 0;
     int count_before_loss = 0;  // also write the batch's cut count (as a float) just before the loss sum
@@ -247,6 +250,7 @@ static size_t carve(gcnn_workspace* ws, char* base, const Caps& c) {
             ws->bG[i] = rows(n_recv[i]); ws->bdR[i] = rows(n_recv[i]); ws->bdS[i] = rows(n_send[i]);
             ws->chain_partials[i] = cv.take<float>((int64_t)NUM_SMS * conv_backward_part_floats());
             ws->emb_partials[i] = cv.take<float>((int64_t)NUM_SMS * embed_backward_part_floats());
+            ws->edge_masks[i] = cv.take<uint2>(i == 2 ? ek : ec);
         }
     }
     return cv.off + 256;
@@ -303,11 +307,14 @@ static int edge_forward_dispatch(gcnn_workspace* ws, const gcnn_batch* b, int co
             // pageable source: the driver stages the copy before returning, so the vector may die right away
             GCNN_CUDA_TRY(cudaMemcpyAsync(ws->d_tiles[conv], tiles.data(), sizeof(EdgeTile) * tiles.size(),
                                           cudaMemcpyHostToDevice, st));
+            ws->masks_valid[conv] = 0;  // the tile kernel does not emit masks: the backward re-evaluates
             return edge_forward_tiles(ws->d_tiles[conv], (int)tiles.size(), max_nsrc, max_rows, n_recv, n_edges, L, R, S,
                                       w_edge, sc, H, cnt, ws->flags + 1, st, prof_bytes);
         }
     }
-    return edge_forward(L, n_recv, R, S, w_edge, sc, H, cnt, st, prof_bytes, n_edges);
+    void* masks = (cnt && ws->cap.training && ws->use_edge_masks) ? ws->edge_masks[conv] : nullptr;
+    ws->masks_valid[conv] = masks != nullptr;
+    return edge_forward(L, n_recv, R, S, w_edge, sc, H, cnt, st, prof_bytes, n_edges, masks);
 }
 
 // ---- dense-layer dispatch: tcgen05 3xTF32 tensor-core kernel (default) or the fp32 SIMT kernel (GCNN_TC=0) ---------
@@ -777,8 +784,13 @@ static int backward_impl_fused(gcnn_workspace* ws, const float* p, const float* 
         int n_dw = 0;
         const int64_t E_i = graph_of[i] == 0 ? b->n_cons_edges : b->n_cut_edges;
         const double bwd_bytes = 256.0 * (double)(2 * n_recv[i] + 2 * n_send[i]) + 8.0 * (double)E_i + 4.0 * (double)(n_send[i] + 1);
-        GCNN_TRY(edge_backward(Ls, n_send[i], R, S, ws->bG[i], p + o.we, sc, ws->bdS[i], ws->dw_partials[i], &n_dw, st,
-                               bwd_bytes, E_i));
+        if (ws->masks_valid[i])  // algorithmic bytes: G gathered per edge comes from L2; compulsory: G, dS rows, 20 B per edge
+            GCNN_TRY(edge_backward_masked(Ls, n_send[i], ws->bG[i], ws->edge_masks[i], sc, ws->bdS[i], ws->dw_partials[i],
+                                          &n_dw, st, 256.0 * (double)(n_recv[i] + n_send[i]) + 20.0 * (double)E_i +
+                                                         4.0 * (double)(n_send[i] + 1)));
+        else
+            GCNN_TRY(edge_backward(Ls, n_send[i], R, S, ws->bG[i], p + o.we, sc, ws->bdS[i], ws->dw_partials[i], &n_dw, st,
+                                   bwd_bytes, E_i));
         add_job(ws->dw_partials[i], n_dw, D, D, o.we);
     }
 
@@ -931,6 +943,8 @@ int gcnn_workspace_create(gcnn_workspace** out) {
     ws->use_fused = !(fu && fu[0] == '0');
     const char* bf = getenv("GCNN_BF16_FWD");  // GCNN_BF16_FWD=0: 3xTF32 forward chains
     ws->use_bf16_fwd = !(bf && bf[0] == '0');
+    const char* em = getenv("GCNN_EDGE_MASKS");  // GCNN_EDGE_MASKS=0: the edge backward re-evaluates the ReLU masks
+    ws->use_edge_masks = !(em && em[0] == '0');
     const char* fb = getenv("GCNN_FUSED_BWD");  // GCNN_FUSED_BWD=0: stand-alone dgrad / wgrad launches in the backward
     ws->use_fused_bwd = !(fb && fb[0] == '0');
     for (int i = 0; i < 2; ++i) GCNN_CUDA_TRY(cudaStreamCreateWithFlags(&ws->aux[i], cudaStreamNonBlocking));
@@ -1003,6 +1017,7 @@ int gcnn_set_option(gcnn_workspace* ws, const char* name, int value) {
     else if (!strcmp(name, "fused_backward")) ws->use_fused_bwd = value != 0;
     else if (!strcmp(name, "bf16_forward")) ws->use_bf16_fwd = value != 0;
     else if (!strcmp(name, "count_before_loss")) ws->count_before_loss = value != 0;
+    else if (!strcmp(name, "edge_masks")) ws->use_edge_masks = value != 0;
     else { set_error("unknown option %s", name); return GCNN_INVALID; }
     return GCNN_OK;
 }

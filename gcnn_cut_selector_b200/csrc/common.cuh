@@ -153,9 +153,13 @@ struct EdgeScalars {  // device pointers to the scalars so no host sync is neede
     const float* f_scale;
     const float* s_f;
 };
+// `masks` (training, optional): 8 bytes per edge, indexed by the ORIGINAL edge id, receives the per-edge ReLU mask
 int edge_forward(const EdgeLayout& by_recv, int64_t n_recv, const float* R, const float* S, const float* w_edge,
                  EdgeScalars sc, float* H, float* cnt, cudaStream_t st, double prof_bytes = 0.0,
-                 int64_t n_edges = 0);
+                 int64_t n_edges = 0, void* masks = nullptr);
+// backward that reads those masks instead of re-evaluating the pre-activation (one gathered row per edge, not two)
+int edge_backward_masked(const EdgeLayout& by_send, int64_t n_send, const float* G, const void* masks, EdgeScalars sc,
+                         float* dS, float* dw_partials, int* n_partials, cudaStream_t st, double prof_bytes = 0.0);
 int edge_backward(const EdgeLayout& by_send, int64_t n_send, const float* R, const float* S, const float* G,
                   const float* w_edge, EdgeScalars sc, float* dS, float* dw_partials, int* n_partials,
                   cudaStream_t st, double prof_bytes = 0.0, int64_t n_edges = 0);

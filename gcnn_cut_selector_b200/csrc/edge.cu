@@ -67,14 +67,35 @@ __device__ __forceinline__ void relu_accumulate(const float2 y01, const float2 y
     if (active<NEG>(y23.y)) { acc.w += y23.y; if (TRAIN) act.w += 1.f; }
 }
 
+// Per-edge ReLU mask for the backward pass: 64 bits per edge, word x = fields 0 | 1 << 16, word y = fields 2 | 3 << 16,
+// bit hl of field k = "feature 4 hl + k of this edge is active".  The two half-warps work on two edges at a time, so one
+// ballot per k covers both edges (low / high 16 lanes); lane 0 of each half packs its edge's four fields with two byte
+// permutes and stores 8 bytes at the edge's ORIGINAL index (the backward walks the transposed layout and finds the
+// edge through that layout's permutation).  With the mask the backward gathers one row per edge instead of two and
+// re-evaluates nothing.
+template <bool NEG>
+__device__ __forceinline__ void store_edge_mask(const float2 y01, const float2 y23, bool ok, int edge_id, int half, int hl,
+                                                uint2* __restrict__ masks) {
+    const unsigned b0 = __ballot_sync(0xffffffffu, ok && active<NEG>(y01.x));
+    const unsigned b1 = __ballot_sync(0xffffffffu, ok && active<NEG>(y01.y));
+    const unsigned b2 = __ballot_sync(0xffffffffu, ok && active<NEG>(y23.x));
+    const unsigned b3 = __ballot_sync(0xffffffffu, ok && active<NEG>(y23.y));
+    if (hl == 0 && ok) {
+        const unsigned sel = half ? 0x7632u : 0x5410u;
+        masks[edge_id] = make_uint2(__byte_perm(b0, b1, sel), __byte_perm(b2, b3, sel));
+    }
+}
+
 template <bool TRAIN, bool NEG>
 __device__ __forceinline__ void edge_forward_rows(const int32_t* __restrict__ ptr, const int32_t* __restrict__ src,
                                                   const float* __restrict__ val, int64_t n_recv,
                                                   const float* __restrict__ R, const float* __restrict__ S,
                                                   const float* __restrict__ w_edge, EdgeScalars sc,
-                                                  float* __restrict__ H, float* __restrict__ cnt) {
+                                                  float* __restrict__ H, float* __restrict__ cnt,
+                                                  const int32_t* __restrict__ perm, uint2* __restrict__ masks) {
     const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
     const int warps = blockDim.x >> 5;
+    const bool wm = TRAIN && masks != nullptr;  // kernel-uniform
     // CTA b owns the contiguous rows [b n / grid, (b + 1) n / grid): neighbouring segments belong to the same sample
     // (block-diagonal batches) and gather from the same few hundred source rows, which then hit in this SM's L1 instead
     // of going to L2 (the kernel's ceiling: E x 256 B of gathers against ~12 TB/s of L2)
@@ -89,11 +110,12 @@ __device__ __forceinline__ void edge_forward_rows(const int32_t* __restrict__ pt
 
     for (int base = beg; base < end; base += 32) {
         const int n = min(32, end - base);  // warp-uniform
-        int my_src = 0;
+        int my_src = 0, my_e = 0;
         float my_f = 0.f;
         if (lane < n) {
             my_src = src[base + lane];
             my_f = (val[base + lane] + f_shift) * f_scale;
+            if (wm) my_e = perm[base + lane];
         }
         int j0 = 0;
         // (16-edge groups with 8 gathers in flight per lane were tried: 86+ registers cost more occupancy than the
@@ -113,6 +135,8 @@ __device__ __forceinline__ void edge_forward_rows(const int32_t* __restrict__ pt
                 float2 y01, y23;
                 preact4(r4, w4, g[u], f[u], y01, y23);
                 relu_accumulate<TRAIN, NEG>(y01, y23, acc, act);
+                if (wm)
+                    store_edge_mask<NEG>(y01, y23, true, __shfl_sync(0xffffffffu, my_e, j0 + 2 * u + half), half, hl, masks);
             }
         }
         for (; j0 < n; j0 += 2) {  // tail of the chunk: at most 7 edges
@@ -120,11 +144,12 @@ __device__ __forceinline__ void edge_forward_rows(const int32_t* __restrict__ pt
             const bool ok = j < n;
             const int sj = __shfl_sync(0xffffffffu, my_src, j & 31);
             const float f = __shfl_sync(0xffffffffu, my_f, j & 31);
+            float2 y01 = make_float2(0.f, 0.f), y23 = y01;
             if (ok) {
-                float2 y01, y23;
                 preact4(r4, w4, ld4(Sl + (int64_t)sj * D), f, y01, y23);
                 relu_accumulate<TRAIN, NEG>(y01, y23, acc, act);
             }
+            if (wm) store_edge_mask<NEG>(y01, y23, ok, __shfl_sync(0xffffffffu, my_e, j & 31), half, hl, masks);
         }
     }
     const float4 acc_o = shfl_xor4(acc, 16);
@@ -144,21 +169,24 @@ template <bool TRAIN>
 __global__ void __launch_bounds__(EDGE_FWD_THREADS)
 edge_forward_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ src, const float* __restrict__ val,
                     int64_t n_recv, const float* __restrict__ R, const float* __restrict__ S,
-                    const float* __restrict__ w_edge, EdgeScalars sc, float* __restrict__ H, float* __restrict__ cnt) {
+                    const float* __restrict__ w_edge, EdgeScalars sc, float* __restrict__ H, float* __restrict__ cnt,
+                    const int32_t* __restrict__ perm, uint2* __restrict__ masks) {
     pdl_enter();
-    if (*sc.s_f < 0.f) edge_forward_rows<TRAIN, true>(ptr, src, val, n_recv, R, S, w_edge, sc, H, cnt);
-    else edge_forward_rows<TRAIN, false>(ptr, src, val, n_recv, R, S, w_edge, sc, H, cnt);
+    if (*sc.s_f < 0.f) edge_forward_rows<TRAIN, true>(ptr, src, val, n_recv, R, S, w_edge, sc, H, cnt, perm, masks);
+    else edge_forward_rows<TRAIN, false>(ptr, src, val, n_recv, R, S, w_edge, sc, H, cnt, perm, masks);
 }
 
 int edge_forward(const EdgeLayout& L, int64_t n_recv, const float* R, const float* S, const float* w_edge,
-                 EdgeScalars sc, float* H, float* cnt, cudaStream_t st, double prof_bytes, int64_t /*n_edges*/) {
+                 EdgeScalars sc, float* H, float* cnt, cudaStream_t st, double prof_bytes, int64_t /*n_edges*/,
+                 void* masks) {
+    uint2* mk = cnt ? static_cast<uint2*>(masks) : nullptr;
     if (n_recv <= 0) return GCNN_OK;
     ProfScope prof(PROF_EDGE_FWD, prof_bytes, st);
     static const int cta_threads = [] { const char* e = getenv("GCNN_EDGE_THREADS"); return e ? atoi(e) : EDGE_FWD_THREADS; }();
     static const int ctas_per_sm = [] { const char* e = getenv("GCNN_EDGE_CTAS"); return e ? atoi(e) : 2; }();
     const unsigned grid = (unsigned)min((int64_t)NUM_SMS * ctas_per_sm, ceil_div(n_recv, cta_threads / 32));
-    if (cnt) GCNN_LAUNCH(edge_forward_kernel<true>, grid, cta_threads, 0, st, L.ptr, L.other, L.val, n_recv, R, S, w_edge, sc, H, cnt);
-    else GCNN_LAUNCH(edge_forward_kernel<false>, grid, cta_threads, 0, st, L.ptr, L.other, L.val, n_recv, R, S, w_edge, sc, H, cnt);
+    if (cnt) GCNN_LAUNCH(edge_forward_kernel<true>, grid, cta_threads, 0, st, L.ptr, L.other, L.val, n_recv, R, S, w_edge, sc, H, cnt, L.perm, mk);
+    else GCNN_LAUNCH(edge_forward_kernel<false>, grid, cta_threads, 0, st, L.ptr, L.other, L.val, n_recv, R, S, w_edge, sc, H, cnt, L.perm, mk);
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
 }
@@ -268,6 +296,96 @@ edge_backward_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict_
     __shared__ float4 red[EDGE_WARPS][16];
     if (*sc.s_f < 0.f) edge_backward_rows<true>(ptr, other, val, n_send, R, S, G, w_edge, sc, dS, dw_partials, red);
     else edge_backward_rows<false>(ptr, other, val, n_send, R, S, G, w_edge, sc, dS, dw_partials, red);
+}
+
+// Backward with the forward's per-edge masks: dS[s] = s_f * sum_e mask_e * G[t_e], dw = s_f * sum_e f_e mask_e * G[t_e].
+// One gathered row (G) and one 8-byte mask per edge; the projections R, S are not read at all.
+__global__ void __launch_bounds__(EDGE_THREADS)
+edge_backward_masked_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ other,
+                            const float* __restrict__ val, const int32_t* __restrict__ perm, int64_t n_send,
+                            const float* __restrict__ G, const uint2* __restrict__ masks, EdgeScalars sc,
+                            float* __restrict__ dS, float* __restrict__ dw_partials) {
+    pdl_enter();
+    __shared__ float4 red[EDGE_WARPS][16];
+    const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15, warp = threadIdx.x >> 5;
+    const float f_shift = sc.f_shift ? *sc.f_shift : 0.f, f_scale = sc.f_scale ? *sc.f_scale : 1.f, s_f = *sc.s_f;
+    const float* Gl = G + hl * 4;
+    float4 dw = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto accumulate = [&](const uint2 m, const float4 g, const float f, float4& acc) {
+        const unsigned t0 = m.x >> hl, t1 = m.y >> hl;
+        if (t0 & 1u) { acc.x += g.x; dw.x = fmaf(f, g.x, dw.x); }
+        if (t0 & 0x10000u) { acc.y += g.y; dw.y = fmaf(f, g.y, dw.y); }
+        if (t1 & 1u) { acc.z += g.z; dw.z = fmaf(f, g.z, dw.z); }
+        if (t1 & 0x10000u) { acc.w += g.w; dw.w = fmaf(f, g.w, dw.w); }
+    };
+    const int64_t row_beg = n_send * (int64_t)blockIdx.x / gridDim.x, row_end = n_send * ((int64_t)blockIdx.x + 1) / gridDim.x;
+    for (int64_t row = row_beg + warp; row < row_end; row += EDGE_WARPS) {
+        const int beg = ptr[row], end = ptr[row + 1];
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int base = beg; base < end; base += 32) {
+            const int n = min(32, end - base);
+            int my_t = 0, my_e = 0;
+            float my_f = 0.f;
+            if (lane < n) {
+                my_t = other[base + lane];
+                my_e = perm[base + lane];
+                my_f = (val[base + lane] + f_shift) * f_scale;
+            }
+            int j0 = 0;
+            for (; j0 + 8 <= n; j0 += 8) {  // 8 edges, 4 per half-warp: 4 row gathers + 4 mask loads in flight per lane
+                float4 g[4];
+                uint2 m[4];
+                float f[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 + 2 * u + half;
+                    const int t = __shfl_sync(0xffffffffu, my_t, j);
+                    const int e = __shfl_sync(0xffffffffu, my_e, j);
+                    f[u] = __shfl_sync(0xffffffffu, my_f, j);
+                    g[u] = ld4(Gl + (int64_t)t * D);
+                    m[u] = __ldg(masks + e);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) accumulate(m[u], g[u], f[u], acc);
+            }
+            for (; j0 < n; j0 += 2) {
+                const int j = j0 + half;
+                const bool ok = j < n;
+                const int t = __shfl_sync(0xffffffffu, my_t, j & 31);
+                const int e = __shfl_sync(0xffffffffu, my_e, j & 31);
+                const float f = __shfl_sync(0xffffffffu, my_f, j & 31);
+                if (ok) accumulate(__ldg(masks + e), ld4(Gl + (int64_t)t * D), f, acc);
+            }
+        }
+        const float4 o = shfl_xor4(acc, 16);
+        if (half == 0)
+            st4(dS + row * D + hl * 4,
+                make_float4(s_f * (acc.x + o.x), s_f * (acc.y + o.y), s_f * (acc.z + o.z), s_f * (acc.w + o.w)));
+    }
+    const float4 o = shfl_xor4(dw, 16);
+    if (half == 0)
+        red[warp][hl] = make_float4(s_f * (dw.x + o.x), s_f * (dw.y + o.y), s_f * (dw.z + o.z), s_f * (dw.w + o.w));
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        float4 t = red[0][threadIdx.x];
+#pragma unroll
+        for (int w = 1; w < EDGE_WARPS; ++w) {
+            const float4 v = red[w][threadIdx.x];
+            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+        }
+        st4(dw_partials + (int64_t)blockIdx.x * D + threadIdx.x * 4, t);
+    }
+}
+
+int edge_backward_masked(const EdgeLayout& L, int64_t n_send, const float* G, const void* masks, EdgeScalars sc, float* dS,
+                         float* dw_partials, int* n_partials, cudaStream_t st, double prof_bytes) {
+    ProfScope prof(PROF_EDGE_BWD, prof_bytes, st);
+    int ctas = (int)min((int64_t)EDGE_BWD_MAX_CTAS, ceil_div(n_send > 0 ? n_send : 1, EDGE_WARPS));
+    *n_partials = ctas;
+    GCNN_LAUNCH(edge_backward_masked_kernel, ctas, EDGE_THREADS, 0, st, L.ptr, L.other, L.val, L.perm, n_send, G,
+                static_cast<const uint2*>(masks), sc, dS, dw_partials);
+    GCNN_LAUNCH_CHECK();
+    return GCNN_OK;
 }
 
 int edge_backward_max_partials() { return EDGE_BWD_MAX_CTAS; }
