@@ -61,6 +61,7 @@ SIGNATURES = {
     "gcnn_backward": (_I, [_P, _P, _P, _BP, _P, _P, _P]),
     "gcnn_mse_seed": (_I, [_P, _P, _I64, _F, _P, _P, _P]),
     "gcnn_adam_step": (_I, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I64, _P, _P]),
+    "gcnn_ranking_deviation": (_I, [_P, _P, _P, _I64, _I, _P, _P]),
     "gcnn_forward_backward": (_I, [_P, _P, _P, _BP, _P, _F, _P, _P, _P, _P]),
     "gcnn_prenorm_stats": (_I, [_P, _P, _P, _BP, _I, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                 C.POINTER(C.c_double), _P]),

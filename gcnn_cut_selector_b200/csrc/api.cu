@@ -1101,6 +1101,15 @@ int gcnn_adam_step(float* params, const float* grads, float* m, float* v, int64_
     return adam_step(params, grads, m, v, n, (float)lr_t, beta1, beta2, eps, grad_divisor, (cudaStream_t)stream);
 }
 
+int gcnn_ranking_deviation(const float* predictions, const float* improvements, const int32_t* cut_offsets,
+                            int64_t n_samples, int max_cuts, int32_t* deviation_out, void* stream) {
+    if (!predictions || !improvements || !cut_offsets || !deviation_out || n_samples < 0 || max_cuts < 0) {
+        set_error("bad ranking_deviation arguments");
+        return GCNN_INVALID;
+    }
+    return ranking_deviation(predictions, improvements, cut_offsets, n_samples, max_cuts, deviation_out, (cudaStream_t)stream);
+}
+
 int gcnn_forward_backward(gcnn_workspace* ws, const float* params, const float* prenorm, const gcnn_batch* batch,
                           const float* targets, float seed_scale, float* scores_out, float* grads_out,
                           float* loss_sum_out, void* stream) {

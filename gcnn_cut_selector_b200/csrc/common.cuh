@@ -343,6 +343,10 @@ int mse_seed(const float* scores, const float* targets, int64_t n, float scale, 
 int adam_step(float* params, const float* grads, float* m, float* v, int64_t n, float lr_t, float beta1, float beta2,
               float eps, const float* grad_divisor, cudaStream_t st);
 
+// first position at which the predicted and the true ranking of each sample's cuts differ (model_trainer.py:279-302)
+int ranking_deviation(const float* pred, const float* truth, const int32_t* offsets_dev, int64_t n_samples, int max_cuts,
+                      int32_t* deviation, cudaStream_t st);
+
 // column statistics of a dense [M, K] matrix about `center` (double accumulators): out[0..K) = sum, out[K..2K) = sumsq
 int col_stats(const float* x, int64_t M, int K, const double* center_dev, double* partials, double* out,
               cudaStream_t st);

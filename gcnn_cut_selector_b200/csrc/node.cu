@@ -625,4 +625,58 @@ int adam_step(float* params, const float* grads, float* m, float* v, int64_t n, 
     return GCNN_OK;
 }
 
+
+// ---- ranking accuracy (model_trainer.py:279-302) ----------------------------------------------------------------------
+// Per sample: stable descending ranks of the predictions and of the true improvements (Python's sorted(..., reverse=True)
+// keeps the original order of equal keys), then the first position at which the two rankings name different cuts
+// (`deviation`; the sample's cut count when they agree everywhere).  One CTA per sample, O(n^2) comparisons.
+// rank(i) = #{j : key[j] > key[i]} + #{j < i : key[j] == key[i]}; cut i sits at position rank(i) of the ranking.
+constexpr int RANK_THREADS = 128;
+__global__ void __launch_bounds__(RANK_THREADS)
+ranking_deviation_kernel(const float* __restrict__ pred, const float* __restrict__ truth,
+                         const int32_t* __restrict__ offsets, int32_t* __restrict__ deviation, int max_cuts) {
+    pdl_enter();
+    extern __shared__ int32_t rank_smem[];
+    int32_t* pred_rank = rank_smem;             // [max_cuts] cut index at each position of the predicted ranking
+    int32_t* true_rank = rank_smem + max_cuts;  // [max_cuts]
+    __shared__ int32_t first_diff;
+    const int s = blockIdx.x;
+    const int beg = offsets[s], n = offsets[s + 1] - beg;
+    const float* p = pred + beg;
+    const float* t = truth + beg;
+    if (threadIdx.x == 0) first_diff = n;
+    for (int i = threadIdx.x; i < n; i += RANK_THREADS) {
+        const float pi = p[i], ti = t[i];
+        int rp = 0, rt = 0;
+        for (int j = 0; j < n; ++j) {
+            const float pj = p[j], tj = t[j];
+            rp += (pj > pi) || (pj == pi && j < i);
+            rt += (tj > ti) || (tj == ti && j < i);
+        }
+        pred_rank[rp] = i;
+        true_rank[rt] = i;
+    }
+    __syncthreads();
+    for (int pos = threadIdx.x; pos < n; pos += RANK_THREADS)
+        if (pred_rank[pos] != true_rank[pos]) atomicMin(&first_diff, pos);  // integer min: order-independent
+    __syncthreads();
+    if (threadIdx.x == 0) deviation[s] = first_diff;
+}
+
+int ranking_deviation(const float* pred, const float* truth, const int32_t* offsets_dev, int64_t n_samples, int max_cuts,
+                      int32_t* deviation, cudaStream_t st) {
+    if (n_samples <= 0) return GCNN_OK;
+    const size_t smem = 2 * sizeof(int32_t) * (size_t)(max_cuts > 0 ? max_cuts : 1);
+    if (smem > 200 * 1024) { set_error("ranking_deviation: more than 25,600 cuts in one sample"); return GCNN_INVALID; }
+    if (smem > 48 * 1024) {
+        static int once = [] {
+            return cudaFuncSetAttribute(ranking_deviation_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess ? 0 : 1;
+        }();
+        if (once) { set_error("ranking_deviation: cannot raise the shared-memory limit"); return GCNN_CUDA_ERROR; }
+    }
+    GCNN_LAUNCH(ranking_deviation_kernel, (unsigned)n_samples, RANK_THREADS, smem, st, pred, truth, offsets_dev, deviation, max_cuts);
+    GCNN_LAUNCH_CHECK();
+    return GCNN_OK;
+}
+
 }  // namespace gcnn

@@ -142,6 +142,14 @@ int gcnn_forward_backward(gcnn_workspace* ws, const float* params, const float* 
                           const float* targets, float seed_scale, float* scores_out, float* grads_out,
                           float* loss_sum_out, void* stream);
 
+/* Ranking accuracy of the training / validation loop (model_trainer.py:279-302): for every sample s with cuts
+ * [cut_offsets[s], cut_offsets[s+1]) (device int32, n_samples + 1 entries) rank the cuts by prediction and by true bound
+ * improvement (descending, stable, as Python's sorted(..., reverse=True)) and write the first position at which the two
+ * rankings differ -- the sample's cut count when they agree -- to deviation_out[s] (device int32).  max_cuts bounds the
+ * largest sample.  The caller turns deviation / n_cuts >= fraction into the accuracy counts (model_trainer.py:299-301). */
+int gcnn_ranking_deviation(const float* predictions, const float* improvements, const int32_t* cut_offsets,
+                            int64_t n_samples, int max_cuts, int32_t* deviation_out, void* stream);
+
 /* ---- pre-norm pretraining (PreNormLayer.update_params, model.py:394-423) ------------------------------------- */
 /* Runs the forward up to pre-norm layer `layer` (0..10 in the order BaseModel.pretrain_next_rec visits them,
  * model.py:100-117) and returns that layer's batch statistics on the HOST: mean[n_units], var[n_units] (population

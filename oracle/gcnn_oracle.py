@@ -379,3 +379,28 @@ def load_batch(sample_files):
 def model_inputs(batch):
     """model_trainer.py:259-263: only the totals reach the model."""
     return tuple(batch[:7]) + (int(np.sum(batch[7])), int(np.sum(batch[8])), int(np.sum(batch[9])))
+
+
+def ranking_accuracy(predictions, improvements, n_cuts, fractions):
+    """The accuracy bookkeeping of ``process`` (model_trainer.py:279-302), restated line by line: per sample, sort the
+    cut indices by predicted and by true bound improvement (descending, Python ``sorted``: stable), find the first
+    deviating position, and count the sample for every fraction its correctly ranked prefix reaches.
+    Returns (acc [len(fractions)], deviations [n_samples])."""
+    import numpy as np
+    predictions = np.asarray(predictions, dtype=np.float32)
+    improvements = np.asarray(improvements, dtype=np.float32)
+    fractions = np.asarray(fractions, dtype=np.float64)
+    acc = np.zeros(len(fractions))
+    deviations = []
+    start = 0
+    for n in np.asarray(n_cuts).reshape(-1):
+        pred = predictions[start:start + n]
+        true = improvements[start:start + n]
+        start += n
+        pred_ranking = np.array(sorted(range(len(pred)), key=lambda x: pred[x], reverse=True))  # model_trainer.py:289
+        true_ranking = np.array(sorted(range(len(true)), key=lambda x: true[x], reverse=True))  # model_trainer.py:290
+        differences = (pred_ranking != true_ranking)
+        deviation = int(np.argmax(differences)) if np.any(differences) else len(pred)          # :293-298
+        deviations.append(deviation)
+        acc += (deviation / len(pred) >= fractions)                                             # :300-301
+    return acc, np.asarray(deviations, dtype=np.int32)

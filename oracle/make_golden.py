@@ -15,6 +15,8 @@ Outputs (all small):
   batch_tiny.npz       3 'tiny' samples -> reference ``load_batch`` outputs (bit-exact integer contract)
   fwd_<case>.npz       inputs, fp64 scores / loss / flat gradient (stored as fp32), fp32-run scores
   pretrain_tiny.npz    batches + pre-norm parameters after the reference's pretraining loop
+  metric_process.npz   preset predictions / targets -> mean loss and ranking accuracy from the reference's own
+                       ``model_trainer.process`` (evaluation branch)
   state_stream.pkl     the weights every fixture uses, written by the reference's own ``save_state`` (62 arrays)
 """
 import gzip
@@ -139,8 +141,49 @@ def pretrain_case(params):
     print("pretrain_tiny: 11 layers; order:", order)
 
 
+def metric_case():
+    """Ranking accuracy + mean loss of the reference's own ``process`` (model_trainer.py:239-316) on preset predictions
+    (ties included), evaluation branch.  The model is a stand-in that returns the preset predictions of each batch."""
+    import model_trainer as ref_trainer
+    rng = np.random.default_rng(77)
+    fractions = np.array([0.25, 0.5, 0.75, 1])
+    batches, preds = [], []
+    for b in range(3):
+        n_cuts = rng.integers(1, 12, size=4 + b).astype(np.int32)
+        total = int(n_cuts.sum())
+        true = np.round(rng.uniform(0, 0.1, total), 2).astype(np.float32)            # coarse grid -> ties
+        noise = rng.normal(0, 0.02, total) * (rng.random(total) < 0.5)
+        pred = np.round(true + noise, 2).astype(np.float32)
+        preds.append(pred)
+        dummy = tf.convert_to_tensor(np.zeros((1, 1), np.float32))
+        n = tf.convert_to_tensor(n_cuts)
+        batches.append((dummy, dummy, dummy, dummy, dummy, dummy, dummy, n, n, n, tf.convert_to_tensor(true)))
+
+    class Preset:
+        def __init__(self):
+            self.i = 0
+
+        def __call__(self, batched_states, training):
+            out = tf.convert_to_tensor(preds[self.i])
+            self.i += 1
+            return out
+
+    mean_loss, mean_acc = ref_trainer.process(Preset(), batches, fractions, ref_trainer.MeanSquaredError())
+    out = {"fractions": fractions, "mean_loss": np.float64(mean_loss), "mean_acc": np.asarray(mean_acc, np.float64),
+           "n_batches": np.int64(len(batches))}
+    for b, (batch, pred) in enumerate(zip(batches, preds)):
+        out[f"pred{b}"] = pred
+        out[f"true{b}"] = batch[10].numpy()
+        out[f"n_cuts{b}"] = batch[9].numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "metric_process.npz"), **out)
+    print("metric_process: mean_loss", mean_loss, "mean_acc", mean_acc)
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
+    if "--metric-only" in sys.argv:
+        metric_case()
+        return
     params = orc.init_params(seed=12345, dtype=torch.float32)  # weights live in fp32, like the reference's
     # the weights fixture IS the save_state stream written by the reference's own method (model.py:47-56)
     m, _ = reference_model(params, torch.float32)
@@ -164,6 +207,7 @@ def main():
     iso[0] = ((c, ce, v, k, {"indices": ke["indices"][:, keep], "values": ke["values"][keep]}), imp)
     fwd_case("isolated", iso, params)
     pretrain_case(params)
+    metric_case()
 
 
 if __name__ == "__main__":

@@ -35,6 +35,14 @@ class _Errors:
 errors = _Errors()
 
 
+class _Data:  # only named in type annotations of model_trainer.py (tf.data.Dataset)
+    class Dataset:
+        pass
+
+
+data = _Data()
+
+
 def _np(self):
     return self.detach().cpu().numpy()
 
@@ -142,6 +150,12 @@ def equal(a, b):
 
 def ones_like(x):
     return torch.ones_like(torch.as_tensor(x))
+
+
+def split(value, num_or_size_splits, axis=0):
+    """tf.split with a 1-D tensor of sizes (model_trainer.py:280-281)."""
+    sizes = [int(s) for s in (num_or_size_splits.tolist() if torch.is_tensor(num_or_size_splits) else num_or_size_splits)]
+    return list(torch.split(value, sizes, dim=axis))
 
 
 def numpy_function(func, inp, Tout):

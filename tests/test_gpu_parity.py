@@ -552,3 +552,33 @@ def test_miplib_scale_forward(model):
         b = model(batching.model_inputs(batching.concat_samples([synth.shuffle_edges(sample, 1)])), False)
     assert a.shape == (5000,) and torch.isfinite(a).all()
     assert rel_err(b.cpu().numpy(), a.cpu().numpy()) <= 1e-5
+
+
+# ---- ranking accuracy of the training loop (model_trainer.py:279-302) ----------------------------------------------------
+def test_ranking_deviation_bit_exact(golden_dir):
+    """The device kernel against the oracle's line-by-line restatement (itself pinned to the reference's own `process`
+    by tests/test_oracle_golden.py): integer deviations bit-exact, ties, single-cut samples, one large sample."""
+    from gcnn_cut_selector_b200 import ranking_accuracy, ranking_deviation
+    fr = np.array([0.25, 0.5, 0.75, 1])
+    z = np.load(os.path.join(golden_dir, "metric_process.npz"))
+    acc_total, n_samples = np.zeros(4), 0
+    for b in range(int(z["n_batches"])):
+        pred, true, n_cuts = z[f"pred{b}"], z[f"true{b}"], z[f"n_cuts{b}"]
+        want_acc, want_dev = orc.ranking_accuracy(pred, true, n_cuts, fr)
+        got = ranking_deviation(torch.from_numpy(pred).cuda(), true, n_cuts)
+        np.testing.assert_array_equal(got.cpu().numpy(), want_dev)
+        acc = ranking_accuracy(torch.from_numpy(pred).cuda(), true, n_cuts, fr)
+        np.testing.assert_array_equal(acc, want_acc)
+        acc_total += acc
+        n_samples += len(n_cuts)
+    np.testing.assert_allclose(acc_total / n_samples, z["mean_acc"], rtol=0, atol=1e-12)
+    rng = np.random.default_rng(5)
+    n_cuts = np.array([1, 64, 1, 7000, 333, 2], dtype=np.int64)  # 7000 cuts: the > 48 KB shared-memory path
+    total = int(n_cuts.sum())
+    true = np.round(rng.uniform(0, 1, total), 3).astype(np.float32)
+    pred = true.copy()
+    flip = rng.random(total) < 0.001
+    pred[flip] = np.round(rng.uniform(0, 1, int(flip.sum())), 3)
+    want_acc, want_dev = orc.ranking_accuracy(pred, true, n_cuts, fr)
+    got = ranking_deviation(torch.from_numpy(pred).cuda(), torch.from_numpy(true).cuda(), n_cuts)
+    np.testing.assert_array_equal(got.cpu().numpy(), want_dev)

@@ -165,3 +165,33 @@ def test_gradcheck_fp64_micrograph():
         w[idx] += h
         fd = float(lp - lm) / (2 * h)
         assert abs(fd - float(grads[name][idx])) <= 1e-5 * max(abs(fd), 1e-8), name
+
+
+def test_ranking_accuracy_matches_reference_process(golden_dir):
+    """oracle.ranking_accuracy against the mean loss / accuracy the reference's own model_trainer.process returned on
+    preset predictions with ties (fixture generated by oracle/make_golden.py from the unmodified reference source)."""
+    z = np.load(os.path.join(golden_dir, "metric_process.npz"))
+    acc, n_samples, loss_num, cuts = np.zeros(len(z["fractions"])), 0, 0.0, 0
+    for b in range(int(z["n_batches"])):
+        pred, true, n_cuts = z[f"pred{b}"], z[f"true{b}"], z[f"n_cuts{b}"]
+        a, dev = orc.ranking_accuracy(pred, true, n_cuts, z["fractions"])
+        assert dev.shape == n_cuts.shape and (dev <= n_cuts).all()
+        acc += a
+        n_samples += len(n_cuts)
+        loss_num += float(np.mean((pred.astype(np.float32) - true) ** 2, dtype=np.float32)) * int(n_cuts.sum())
+        cuts += int(n_cuts.sum())
+    np.testing.assert_allclose(acc / n_samples, z["mean_acc"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(loss_num / cuts, float(z["mean_loss"]), rtol=1e-6)
+
+
+def test_ranking_accuracy_hand_cases():
+    fr = [0.25, 0.5, 0.75, 1]
+    # identical order -> deviation = n; ties keep the original order in both rankings (stable sort)
+    acc, dev = orc.ranking_accuracy([3, 2, 2, 1], [30, 20, 20, 10], [4], fr)
+    assert dev.tolist() == [4] and acc.tolist() == [1, 1, 1, 1]
+    # first position already wrong
+    acc, dev = orc.ranking_accuracy([1, 2], [2, 1], [2], fr)
+    assert dev.tolist() == [0] and acc.tolist() == [0, 0, 0, 0]
+    # two samples: the second deviates at position 2 of 4 -> frac 0.5
+    acc, dev = orc.ranking_accuracy([5, 4, 4, 3, 2, 1], [1, 0, 9, 8, 6, 7], [2, 4], fr)
+    assert dev.tolist() == [2, 2] and acc.tolist() == [2, 2, 1, 1]
