@@ -873,10 +873,11 @@ int gcnn_profile_end(double* ms, int64_t* launches, double* bytes, int n_classes
 }
 
 const char* gcnn_profile_class_name(int c) {
-    static const char* names[PROF_NCLASSES] = {"csr_build", "embed1_forward", "linear_forward", "edge_forward", "head2",
+    static const char* names[PROF_NCLASSES] = {"csr_check", "embed_forward_chain", "conv_forward_chain", "edge_forward", "head2",
                                                "linear_dgrad", "linear_wgrad", "embed1_wgrad", "edge_backward",
                                                "reduce_partials", "mse_seed", "adam", "prenorm_stats",
-                                               "pack_weights", "conv_backward_chain", "embed_backward_chain"};
+                                               "pack_weights", "conv_backward_chain", "embed_backward_chain", "csr_scan",
+                                               "csr_scatter", "csr_finalize"};
     return (c >= 0 && c < PROF_NCLASSES) ? names[c] : "";
 }
 int gcnn_profile_num_classes(void) { return PROF_NCLASSES; }

@@ -16,8 +16,8 @@ void count_launch(int n = 1);
 
 // ---- optional per-kernel-class timing with CUDA events on the launching stream (bench.py roofline numbers) -------
 enum ProfClass {
-    PROF_CSR = 0, PROF_EMB1_FWD, PROF_LIN_FWD, PROF_EDGE_FWD, PROF_HEAD, PROF_LIN_DGRAD, PROF_LIN_WGRAD,
-    PROF_EMB1_WGRAD, PROF_EDGE_BWD, PROF_REDUCE, PROF_LOSS, PROF_ADAM, PROF_STATS, PROF_PACK, PROF_CONV_BWD, PROF_EMB_BWD, PROF_NCLASSES
+    PROF_CSR_CHECK = 0, PROF_EMB1_FWD, PROF_LIN_FWD, PROF_EDGE_FWD, PROF_HEAD, PROF_LIN_DGRAD, PROF_LIN_WGRAD,
+    PROF_EMB1_WGRAD, PROF_EDGE_BWD, PROF_REDUCE, PROF_LOSS, PROF_ADAM, PROF_STATS, PROF_PACK, PROF_CONV_BWD, PROF_EMB_BWD, PROF_CSR_SCAN, PROF_CSR_SCATTER, PROF_CSR_FINALIZE, PROF_NCLASSES
 };
 struct ProfScope {  // records a start/stop event pair around the launches issued while it is alive (if enabled)
     ProfScope(int cls, double algorithmic_bytes, cudaStream_t st);

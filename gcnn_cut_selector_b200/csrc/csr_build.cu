@@ -209,8 +209,9 @@ int build_layout(const int32_t* keys, const int32_t* others, const float* feats,
         set_error("build_layout: sizes out of int32 range");
         return GCNN_INVALID;
     }
-    // algorithmic bytes: read (key, other, feature) per edge, write (other, feature, perm) per edge and the pointer
-    ProfScope prof(PROF_CSR, 24.0 * (double)E + 4.0 * (double)(n_owner + 1), st);
+    // one profiling scope per kernel (bench.py classes csr_check / csr_scan / csr_scatter / csr_finalize); algorithmic bytes:
+    // check reads key + other per edge and, when it feeds a sort, writes the (key, edge id) pair; a scatter pass reads and
+    // writes one pair per edge; finalize reads key, other, feature (+ the sorted pair) and writes other, feature, perm + ptr
     if (E == 0) {  // no edges: every segment is empty
         GCNN_CUDA_TRY(cudaMemsetAsync(out.ptr, 0, sizeof(int32_t) * (size_t)(n_owner + 1), st));
         return GCNN_OK;
@@ -223,11 +224,13 @@ int build_layout(const int32_t* keys, const int32_t* others, const float* feats,
     int32_t* scratch_flag = sc.flags;          // written, never read
     const int32_t* zero_flag = sc.flags + 6;   // never written: reads as "sorted"
     if (hint_sorted || trivially_sorted) {
+        ProfScope prof(PROF_CSR_CHECK, 8.0 * (double)E, st);
         GCNN_LAUNCH_ORDERED(check_init_hist_kernel<true>, n_blocks, SORT_THREADS, 0, st, 
             keys, others, E, (int32_t)n_owner, (int32_t)n_other, trivially_sorted ? scratch_flag : unsorted_flag,
             err_flag, trivially_sorted ? 0 : 1, nullptr, nullptr, nullptr, nullptr, n_blocks);
         GCNN_LAUNCH_CHECK();
     } else {
+        ProfScope prof(PROF_CSR_CHECK, 16.0 * (double)E + 4.0 * (double)hist_n, st);
         GCNN_LAUNCH_ORDERED(check_init_hist_kernel<false>, n_blocks, SORT_THREADS, 0, st, 
             keys, others, E, (int32_t)n_owner, (int32_t)n_other, unsorted_flag, err_flag, 0, sc.key_a, sc.val_a, hist0,
             hist1, n_blocks);
@@ -242,9 +245,13 @@ int build_layout(const int32_t* keys, const int32_t* others, const float* feats,
         for (int shift = 0, pass = 0; shift < bits; shift += 8, ++pass) {
             const bool more = shift + 8 < bits;
             // pass 0 finds hist1 zeroed by the first kernel; later passes zero their "next" buffer in the scan
-            GCNN_LAUNCH_ORDERED(digit_scan_kernel, RADIX, RADIX, 0, st, hcur, n_blocks, unsorted_flag, totals,
-                        (more && pass > 0) ? hnext : nullptr);
-            GCNN_LAUNCH_CHECK();
+            {
+                ProfScope prof(PROF_CSR_SCAN, 8.0 * (double)hist_n, st);
+                GCNN_LAUNCH_ORDERED(digit_scan_kernel, RADIX, RADIX, 0, st, hcur, n_blocks, unsorted_flag, totals,
+                            (more && pass > 0) ? hnext : nullptr);
+                GCNN_LAUNCH_CHECK();
+            }
+            ProfScope prof(PROF_CSR_SCATTER, 16.0 * (double)E + 4.0 * (double)hist_n, st);
             GCNN_LAUNCH_ORDERED(radix_scatter_kernel, n_blocks, SORT_THREADS, 0, st, ka, va, E, shift, unsorted_flag, hcur, totals,
                         n_blocks, kb, vb, more ? hnext : nullptr);
             GCNN_LAUNCH_CHECK();
@@ -257,6 +264,7 @@ int build_layout(const int32_t* keys, const int32_t* others, const float* feats,
         sorted_perm = va;
     }
     const int threads = 256;
+    ProfScope prof(PROF_CSR_FINALIZE, ((hint_sorted || trivially_sorted) ? 24.0 : 32.0) * (double)E + 4.0 * (double)(n_owner + 1), st);
     GCNN_LAUNCH_ORDERED(finalize_layout_kernel, (unsigned)ceil_div(E + 1, threads), threads, 0, st, 
         keys, others, feats, E, (int32_t)n_owner, (int32_t)n_other,
         // a violated hint leaves unsorted_flag = 1 with no sorted pairs: fall back to the input order (the error is

@@ -8,8 +8,9 @@ import sys
 rows = list(csv.reader(open(sys.argv[1])))
 hdr, units = rows[0], rows[1]
 col = {k: i for i, k in enumerate(hdr)}
-CLASS = [("check_init_hist", "csr_build"), ("digit_scan", "csr_build"), ("radix_scatter", "csr_build"),
-         ("finalize_layout", "csr_build"), ("tc_embed_forward", "embed1_forward"), ("tc_conv_forward", "linear_forward"),
+CLASS = [("check_init_hist", "csr_check"), ("digit_scan", "csr_scan"), ("radix_scatter", "csr_scatter"),
+         ("finalize_layout", "csr_finalize"), ("tc_embed_forward", "embed_forward_chain"),
+         ("tc_conv_forward", "conv_forward_chain"), ("head_loss", "head2"),
          ("edge_forward", "edge_forward"), ("head2", "head2"), ("edge_backward", "edge_backward"),
          ("reduce_partials", "reduce_partials"), ("mse_seed", "mse_seed"), ("adam", "adam"), ("pack_weights", "pack_weights"),
          ("tc_conv_backward", "conv_backward_chain"), ("tc_embed_backward", "embed_backward_chain")]
