@@ -45,6 +45,13 @@ if __name__ == "__main__":
     buf = (C.c_longlong * 64)()
     n = lib.gcnn_debug_chain_timing(buf, 64)
     ts = [buf[i] for i in range(n)]
+    print("tc_conv_backward_kernel, thread 0 of CTA 0, last launch of the step (convolution 0: one 128-node tile per CTA).\n"
+          "Marks in code order: 0 kernel entry | 1 TMEM + barriers ready | 2 previous grid done (griddepcontrol.wait) |\n"
+          "3 prologue done | 4 tile start | S3: 5 tiles stored, 6 published, 7 prefetch issued, 8 input-gradient MMAs done,\n"
+          "9 epilogue done | S2: 10 weight-gradient MMAs done, 11 stored, 12 published, 13 prefetch issued, 14 MMAs done,\n"
+          "15 epilogue done | S1: 16 weight-gradient MMAs done, 17 stored, 18 published, 19 prefetch issued, 20 MMAs done,\n"
+          "21 weight-gradient MMAs done (epilogue part 1), 22 stored | S0: 23 published, 24 prefetch issued, 25 MMAs done,\n"
+          "26 epilogue done (tiles done) | 27 accumulators and bias sums drained.  1.965 GHz: 1,000 cycles = 0.51 us.")
     print("marks:", n)
     for i in range(1, n):
         print(f"  {i:2d}: +{ts[i] - ts[i - 1]:7d} cycles  (t={ts[i] - ts[0]})")
