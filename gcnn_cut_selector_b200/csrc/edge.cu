@@ -172,7 +172,19 @@ edge_forward_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__
                     const float* __restrict__ w_edge, EdgeScalars sc, float* __restrict__ H, float* __restrict__ cnt,
                     const int32_t* __restrict__ perm, uint2* __restrict__ masks) {
     pdl_enter();
-    if (*sc.s_f < 0.f) edge_forward_rows<TRAIN, true>(ptr, src, val, n_recv, R, S, w_edge, sc, H, cnt, perm, masks);
+    const float s_f = *sc.s_f;
+    if (s_f == 0.f) {  // relu(0 * z) = 0: nothing is active (degenerate pre-norm scale; keeps cnt and the masks exact)
+        const int lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+        const int64_t row_beg = n_recv * (int64_t)blockIdx.x / gridDim.x, row_end = n_recv * ((int64_t)blockIdx.x + 1) / gridDim.x;
+        for (int64_t row = row_beg + (threadIdx.x >> 5); row < row_end; row += warps) {
+            H[row * D + lane] = 0.f; H[row * D + 32 + lane] = 0.f;
+            if (TRAIN) { cnt[row * D + lane] = 0.f; cnt[row * D + 32 + lane] = 0.f; }
+            if (TRAIN && masks)
+                for (int p = ptr[row] + lane; p < ptr[row + 1]; p += 32) masks[perm[p]] = make_uint2(0u, 0u);
+        }
+        return;
+    }
+    if (s_f < 0.f) edge_forward_rows<TRAIN, true>(ptr, src, val, n_recv, R, S, w_edge, sc, H, cnt, perm, masks);
     else edge_forward_rows<TRAIN, false>(ptr, src, val, n_recv, R, S, w_edge, sc, H, cnt, perm, masks);
 }
 

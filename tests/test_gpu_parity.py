@@ -181,8 +181,9 @@ def test_device_tensor_inputs_take_the_unhinted_path(model, oracle64):
 
 
 # ---- per-op parity ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("s_f", [0.7, -1.3, 0.0])  # the sign of the pre-norm scale selects the active half-line of z
 @pytest.mark.parametrize("n_recv,n_send,E", [(50, 70, 600), (1, 3, 5), (300, 2, 4000), (64, 64, 0)])
-def test_edge_forward_backward_ops(model, n_recv, n_send, E):
+def test_edge_forward_backward_ops(model, n_recv, n_send, E, s_f):
     from gcnn_cut_selector_b200._lib import check
     lib, dev = model._lib, model.device
     rng = np.random.default_rng(E + n_recv)
@@ -193,7 +194,7 @@ def test_edge_forward_backward_ops(model, n_recv, n_send, E):
     S = rng.standard_normal((n_send, 64)).astype(np.float32)
     w = rng.standard_normal(64).astype(np.float32)
     G = rng.standard_normal((n_recv, 64)).astype(np.float32)
-    f_shift, f_scale, s_f = 0.25, 1.5, 0.7
+    f_shift, f_scale = 0.25, 1.5
     # oracle in fp64
     fe = (f.astype(np.float64) + f_shift) * f_scale
     z = R.astype(np.float64)[recv] + fe[:, None] * w.astype(np.float64) + S.astype(np.float64)[send]
@@ -214,7 +215,7 @@ def test_edge_forward_backward_ops(model, n_recv, n_send, E):
                                 dS_.data_ptr(), dw_.data_ptr(), f_shift, f_scale, s_f, dH.data_ptr(), dcnt.data_ptr(),
                                 st))
     torch.cuda.synchronize()
-    if E:
+    if E and s_f != 0.0:
         assert rel_err(dH.cpu().numpy(), H) <= 2e-6
     else:
         assert np.all(dH.cpu().numpy() == 0)
@@ -230,7 +231,7 @@ def test_edge_forward_backward_ops(model, n_recv, n_send, E):
                                  dR_.data_ptr(), dS_.data_ptr(), dG.data_ptr(), dw_.data_ptr(), f_shift, f_scale, s_f,
                                  out_dS.data_ptr(), out_dw.data_ptr(), st))
     torch.cuda.synchronize()
-    if E:
+    if E and s_f != 0.0:
         assert rel_err(out_dS.cpu().numpy(), dS) <= 2e-6
         assert rel_err(out_dw.cpu().numpy(), dw) <= 2e-6
     else:
@@ -309,6 +310,39 @@ def test_problem_classes_forward_backward(model, oracle64, shape, n):
     assert rel_err(scores.cpu().numpy(), pred.numpy()) <= TOL
     assert abs(float(loss_sum) / scores.numel() - float(loss)) <= TOL * float(loss)
     assert_grads_close(model.flat_grads.cpu().numpy(), grads, tol=model.grad_tol)
+
+
+def test_negative_and_zero_prenorm_scales(model, golden_dir):
+    """Pre-norm scales are data (restore_state can load anything): a negative feature_module_final scale flips which
+    half-line of the joint pre-activation is active, a zero one switches the convolution's message path off, negative
+    post-conv and input scales are plain multipliers.  Scores and gradients against the fp64 oracle with the same values."""
+    z = np.load(os.path.join(golden_dir, "fwd_mini2.npz"))
+    inputs, targets = golden_inputs(z), z["targets"]
+    saved = model.flat_prenorm.clone()
+    names = [n for n, _, tr in orc.PARAM_SPECS if not tr]
+    try:
+        pn = orc.flatten_prenorm(orc.restore_state(os.path.join(golden_dir, "state_stream.pkl"), dtype=torch.float64)).clone()
+        offs, o = {}, 0
+        for n, shape, tr in orc.PARAM_SPECS:
+            if not tr:
+                offs[n] = o
+                o += int(np.prod(shape))
+        pn[offs["cons_conv_final/prenorm/scale"]] = -0.8
+        pn[offs["cons_conv_post/prenorm/scale"]] = -1.7
+        pn[offs["var_conv_final/prenorm/scale"]] = 0.0
+        pn[offs["cut_conv_final/prenorm/scale"]] = -0.4
+        pn[offs["cons_edge/prenorm/scale"]] = -2.0
+        assert len(names) and pn.numel() == saved.numel()
+        model.flat_prenorm.copy_(pn.to(torch.float32))
+        params64 = orc.unflatten(model.flat_params.detach().cpu().double(), pn.double(), dtype=torch.float64)
+        oracle = orc.OracleGCNN(params64, dtype=torch.float64)
+        loss_sum, scores = model.loss_and_grads(inputs, targets)
+        torch.cuda.synchronize()
+        loss, pred, grads = orc.loss_and_grads(oracle, inputs, targets)
+        assert rel_err(scores.cpu().numpy(), pred.numpy()) <= TOL
+        assert_grads_close(model.flat_grads.cpu().numpy(), grads, tol=model.grad_tol)
+    finally:
+        model.flat_prenorm.copy_(saved)
 
 
 def test_edge_order_invariance_and_determinism(model):
