@@ -555,14 +555,16 @@ def test_prefetching_host_path_matches_synchronous_path(golden_dir):
 
 
 # ---- full BASELINE sizes: size-independent properties -----------------------------------------------------------------
-def test_config2_properties(model):
-    """32 setcov graphs (BASELINE config 2): block-diagonality -> the batch equals its two halves; bit-reproducible."""
-    samples = synth.make_samples("setcov", 32, seed0=2000, n_structures=8)
+@pytest.mark.parametrize("n_graphs", [32, 128])  # BASELINE config 2, and config 4's per-GPU share at 8 GPUs (3.2 M edges)
+def test_config2_properties(model, n_graphs):
+    """Full-size setcov batches: block-diagonality -> the batch equals its two halves; bit-reproducible."""
+    h = n_graphs // 2
+    samples = synth.make_samples("setcov", n_graphs, seed0=2000, n_structures=8)
     whole = batching.concat_samples(samples)
     with torch.no_grad():
         out = model(batching.model_inputs(whole), False)
         out2 = model(batching.model_inputs(whole), False)
-        halves = [model(batching.model_inputs(batching.concat_samples(samples[i:i + 16])), False) for i in (0, 16)]
+        halves = [model(batching.model_inputs(batching.concat_samples(samples[i:i + h])), False) for i in (0, h)]
     assert torch.equal(out, out2)
     assert rel_err(out.cpu().numpy(), torch.cat(halves).cpu().numpy()) <= 1e-6
     assert torch.isfinite(out).all()
@@ -570,11 +572,13 @@ def test_config2_properties(model):
     model.loss_and_grads(batching.model_inputs(whole), whole[10])
     g = model.flat_grads.clone()
     acc = torch.zeros_like(g)
-    for i in (0, 16):
-        half = batching.concat_samples(samples[i:i + 16])
+    for i in (0, h):
+        half = batching.concat_samples(samples[i:i + h])
         model.loss_and_grads(batching.model_inputs(half), half[10], seed_scale=1.0 / whole[4].shape[0])
         acc += model.flat_grads
     assert rel_err(acc.cpu().numpy(), g.cpu().numpy()) <= 1e-5
+    model.loss_and_grads(batching.model_inputs(whole), whole[10])
+    assert torch.equal(g, model.flat_grads)  # gradients are bit-reproducible too (fixed reduction orders everywhere)
 
 
 def test_miplib_scale_forward(model):
