@@ -419,7 +419,7 @@ static int forward_impl(gcnn_workspace* ws, const float* p, const float* pn, con
     // F1: edge layouts on an auxiliary stream, concurrent with the embeddings.  conv 0 reduces by constraint, conv 1
     // by variable (both over constraint edges), conv 2 by cut; the opposite grouping serves the backward pass.
     GCNN_TRY(stream_edge(ws, st, s1));
-    GCNN_CUDA_TRY(cudaMemsetAsync(ws->flags + 2, 0, 4 * sizeof(int32_t), s1));  // per-layout "unsorted" flags
+    GCNN_CUDA_TRY(cudaMemsetAsync(ws->flags + 2, 0, 12 * sizeof(int32_t), s1));  // per-layout "unsorted" [2..5] and "long rows" [10..13] words
     const bool cons_sorted = (b->flags & GCNN_BATCH_CONS_EDGES_SORTED) != 0;
     const bool cuts_sorted = (b->flags & GCNN_BATCH_CUT_EDGES_SORTED) != 0;
     GCNN_TRY(build_layout(b->cons_edge_inds, b->cons_edge_inds + ec, b->cons_edge_feats, ec, nc, nv, ws->sort,
@@ -1019,6 +1019,7 @@ int gcnn_set_option(gcnn_workspace* ws, const char* name, int value) {
     else if (!strcmp(name, "bf16_forward")) ws->use_bf16_fwd = value != 0;
     else if (!strcmp(name, "count_before_loss")) ws->count_before_loss = value != 0;
     else if (!strcmp(name, "edge_masks")) ws->use_edge_masks = value != 0;
+    else if (!strcmp(name, "long_row")) set_long_row_threshold(value);  // process-wide; layouts must be rebuilt after a change
     else { set_error("unknown option %s", name); return GCNN_INVALID; }
     return GCNN_OK;
 }
@@ -1036,11 +1037,14 @@ int gcnn_build_csr(gcnn_workspace* ws, int which, const int32_t* ei, const float
     const int64_t cap_left = which == 0 ? ws->cap.nc : ws->cap.nk, cap_e = which == 0 ? ws->cap.ec : ws->cap.ek;
     if (n_left > cap_left || n_vars > ws->cap.nv || E > cap_e) { set_error("workspace too small"); return GCNN_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
-    GCNN_CUDA_TRY(cudaMemsetAsync(ws->flags + 2, 0, 4 * sizeof(int32_t), st));
-    GCNN_TRY(build_layout(ei, ei + E, ef, E, n_left, n_vars, ws->sort, ws->flags + 1, ws->flags + 2, false,
+    // per-layout "unsorted" words (the same ones the whole-model forward uses: the edge kernels read them later)
+    int32_t* unsorted = ws->flags + 2 + 2 * which;
+    GCNN_CUDA_TRY(cudaMemsetAsync(unsorted, 0, 2 * sizeof(int32_t), st));
+    GCNN_CUDA_TRY(cudaMemsetAsync(unsorted + LONG_FLAG_OFFSET, 0, 2 * sizeof(int32_t), st));
+    GCNN_TRY(build_layout(ei, ei + E, ef, E, n_left, n_vars, ws->sort, ws->flags + 1, unsorted, false,
                           ws->graph[which].by_left, st));
     if (need_transposed)
-        GCNN_TRY(build_layout(ei + E, ei, ef, E, n_vars, n_left, ws->sort, ws->flags + 1, ws->flags + 3, false,
+        GCNN_TRY(build_layout(ei + E, ei, ef, E, n_vars, n_left, ws->sort, ws->flags + 1, unsorted + 1, false,
                               ws->graph[which].by_var, st));
     ws->last.n_vars = n_vars;
     if (which == 0) { ws->last.n_cons = n_left; ws->last.n_cons_edges = E; }

@@ -134,7 +134,14 @@ struct EdgeLayout {   // edges grouped by one endpoint ("owner"), stable in orig
     int32_t* other;   // [E] index of the opposite endpoint
     float* val;       // [E] raw edge feature
     int32_t* perm;    // [E] original edge id
+    const int32_t* reordered;  // device word: 0 = the layout kept the input order (perm[p] == p); set by build_layout
+    const int32_t* long_rows;  // device word, set by build_layout: bit 0 = some owner has more than long_row_threshold()
+                               // edges, bit 1 = some owner has more than max(32, 4 x mean degree) edges
 };
+// rows longer than this are reduced by a whole CTA in the edge kernels (csrc/edge.cu); GCNN_LONG_ROW overrides (experiments)
+int long_row_threshold();
+void set_long_row_threshold(int v);
+constexpr int LONG_FLAG_OFFSET = 8;  // build_layout writes the long-row word at unsorted_flag + 8
 
 struct SortScratch {
     int32_t *key_a, *val_a, *key_b, *val_b;  // ping-pong pair buffers [E]
@@ -144,7 +151,7 @@ struct SortScratch {
 
 int build_layout(const int32_t* keys, const int32_t* others, const float* feats, int64_t E, int64_t n_owner,
                  int64_t n_other, const SortScratch& sc, int32_t* err_flag, int32_t* unsorted_flag, bool hint_sorted,
-                 EdgeLayout out, cudaStream_t st);
+                 EdgeLayout& out, cudaStream_t st);
 int64_t sort_hist_entries(int64_t E);
 
 // ---- edge kernels -------------------------------------------------------------------------------------------------

@@ -8,6 +8,8 @@
 // utils.py:102-104; block-diagonal offsets utils.py:403-407), so grouping by the left node is a pointer build.
 // That is detected ON THE DEVICE (no host sync): every sort kernel early-exits when the "already sorted" flag
 // is set.  Otherwise a stable LSD radix sort (8-bit digits, match.any ranking) orders (key, edge id) pairs.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gcnn {
@@ -176,7 +178,8 @@ radix_scatter_kernel(const int32_t* __restrict__ key_in, const int32_t* __restri
 __global__ void finalize_layout_kernel(const int32_t* __restrict__ keys, const int32_t* __restrict__ others,
                                        const float* __restrict__ feats, int64_t E, int32_t n_owner,
                                        int32_t n_other, const int32_t* __restrict__ unsorted_flag, const int32_t* __restrict__ sorted_keys,
-                                       const int32_t* __restrict__ sorted_perm, EdgeLayout out) {
+                                       const int32_t* __restrict__ sorted_perm, EdgeLayout out, int32_t* __restrict__ long_flag,
+                                       const int long_row, const int heavy_row) {
     pdl_enter();
     const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (p > E) return;
@@ -188,6 +191,13 @@ __global__ void finalize_layout_kernel(const int32_t* __restrict__ keys, const i
     const int32_t k = p < E ? key_at(p) : n_owner;
     const int32_t prev = p > 0 ? key_at(p - 1) : -1;
     for (int32_t r = prev + 1; r <= k; ++r) out.ptr[r] = (int32_t)p;
+    // an owner has more than m edges iff two positions m apart carry the same key.  Bit 0: some row is longer than
+    // long_row (reduced by a whole CTA in the edge kernels); bit 1: some row is longer than heavy_row = max(32, 4 x the
+    // mean degree) -- the edge kernels then split the rows over CTAs by weight instead of by count.
+    if (p < E) {
+        const int bits = ((p >= long_row && key_at(p - long_row) == k) ? 1 : 0) | ((p >= heavy_row && key_at(p - heavy_row) == k) ? 2 : 0);
+        if (bits) atomicOr(long_flag, bits);
+    }
     if (p < E) {
         const int32_t e = presorted ? (int32_t)p : sorted_perm[p];
         out.other[p] = min(max(others[e], 0), n_other - 1);  // clamped; err_flag reports it
@@ -195,6 +205,11 @@ __global__ void finalize_layout_kernel(const int32_t* __restrict__ keys, const i
         out.perm[p] = e;
     }
 }
+
+// process-wide (like the error string): option "long_row" of gcnn_set_option, or GCNN_LONG_ROW in the environment
+static int g_long_row = [] { const char* e = getenv("GCNN_LONG_ROW"); const int x = e ? atoi(e) : 512; return x < 32 ? 32 : x; }();
+int long_row_threshold() { return g_long_row; }
+void set_long_row_threshold(int v) { g_long_row = v < 32 ? 32 : v; }
 
 static int bit_length(int64_t x) {
     int b = 0;
@@ -204,7 +219,7 @@ static int bit_length(int64_t x) {
 
 int build_layout(const int32_t* keys, const int32_t* others, const float* feats, int64_t E, int64_t n_owner,
                  int64_t n_other, const SortScratch& sc, int32_t* err_flag, int32_t* unsorted_flag, bool hint_sorted,
-                 EdgeLayout out, cudaStream_t st) {
+                 EdgeLayout& out, cudaStream_t st) {
     if (E < 0 || n_owner < 0 || n_other < 0 || E >= (int64_t)INT32_MAX || n_owner >= (int64_t)INT32_MAX) {
         set_error("build_layout: sizes out of int32 range");
         return GCNN_INVALID;
@@ -212,6 +227,8 @@ int build_layout(const int32_t* keys, const int32_t* others, const float* feats,
     // one profiling scope per kernel (bench.py classes csr_check / csr_scan / csr_scatter / csr_finalize); algorithmic bytes:
     // check reads key + other per edge and, when it feeds a sort, writes the (key, edge id) pair; a scatter pass reads and
     // writes one pair per edge; finalize reads key, other, feature (+ the sorted pair) and writes other, feature, perm + ptr
+    out.reordered = sc.flags + 6;  // the always-zero word (overwritten below when a sort may run)
+    out.long_rows = unsorted_flag + LONG_FLAG_OFFSET;  // cleared by the caller together with unsorted_flag
     if (E == 0) {  // no edges: every segment is empty
         GCNN_CUDA_TRY(cudaMemsetAsync(out.ptr, 0, sizeof(int32_t) * (size_t)(n_owner + 1), st));
         return GCNN_OK;
@@ -263,13 +280,16 @@ int build_layout(const int32_t* keys, const int32_t* others, const float* feats,
         sorted_keys = ka;
         sorted_perm = va;
     }
+    // what finalize reads is what the edge kernels read: 0 <=> perm[p] == p
+    out.reordered = (trivially_sorted || hint_sorted) ? zero_flag : unsorted_flag;
     const int threads = 256;
     ProfScope prof(PROF_CSR_FINALIZE, ((hint_sorted || trivially_sorted) ? 24.0 : 32.0) * (double)E + 4.0 * (double)(n_owner + 1), st);
     GCNN_LAUNCH_ORDERED(finalize_layout_kernel, (unsigned)ceil_div(E + 1, threads), threads, 0, st, 
         keys, others, feats, E, (int32_t)n_owner, (int32_t)n_other,
         // a violated hint leaves unsorted_flag = 1 with no sorted pairs: fall back to the input order (the error is
         // reported through err_flag) by reading the always-zero word
-        ((trivially_sorted || hint_sorted) ? zero_flag : unsorted_flag), sorted_keys, sorted_perm, out);
+        ((trivially_sorted || hint_sorted) ? zero_flag : unsorted_flag), sorted_keys, sorted_perm, out,
+        unsorted_flag + LONG_FLAG_OFFSET, long_row_threshold(), (int)max((int64_t)32, 4 * ceil_div(E, n_owner > 0 ? n_owner : 1)));
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
 }

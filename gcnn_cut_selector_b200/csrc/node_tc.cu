@@ -21,6 +21,9 @@ namespace gcnn {
 //   T_hi, T_lo : B[n][k] = Wb[k][n]   (forward:  Y = X W)
 //   N_hi, N_lo : B[n][k] = Wb[n][k]   (dgrad:    dX = dY W^T)
 // each 64 rows x 64 floats in the K-major SWIZZLE_128B shared-memory layout, so a CTA copies them linearly.
+// PACK_SPLIT CTAs share one block (each re-reads the 16 KB block from L2 and writes its share of the images): the kernel
+// sits at the head of the step's critical path and 22 CTAs alone are pure latency (14 us -> see profiles/).
+constexpr int PACK_SPLIT = 4;
 __global__ void __launch_bounds__(256)
 pack_weights_kernel(const float* __restrict__ params, const int* __restrict__ block_offsets, float* __restrict__ images) {
     pdl_enter();
@@ -29,7 +32,7 @@ pack_weights_kernel(const float* __restrict__ params, const int* __restrict__ bl
     float* img = images + (int64_t)blockIdx.x * TC_IMG_FLOATS;
     for (int i = threadIdx.x; i < 64 * 64; i += 256) Wb[i >> 6][i & 63] = W[i];
     __syncthreads();
-    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+    for (int i = threadIdx.x + 256 * blockIdx.y; i < 64 * 16; i += 256 * PACK_SPLIT) {
         const int n = i >> 4, k = (i & 15) * 4;
         const uint32_t off = swz_chunk_off(n, k, 64) >> 2;
         float4 t = make_float4(Wb[k][n], Wb[k + 1][n], Wb[k + 2][n], Wb[k + 3][n]);
@@ -45,7 +48,7 @@ pack_weights_kernel(const float* __restrict__ params, const int* __restrict__ bl
     // bf16x3 N image for the backward chains (node_bwd.cu): B[n][k] = Wb[n][k] as three bf16 pieces, 64 rows x 128 bytes
     // each in the K-major SWIZZLE_128B layout (16-byte chunks of 8 bf16)
     uint8_t* img16 = reinterpret_cast<uint8_t*>(img + TC_IMG_TF32_FLOATS);
-    for (int i = threadIdx.x; i < 64 * 8; i += 256) {
+    for (int i = threadIdx.x + 256 * blockIdx.y; i < 64 * 8; i += 256 * PACK_SPLIT) {
         const int n = i >> 3, chunk = i & 7;
         float v[8];
 #pragma unroll
@@ -60,7 +63,7 @@ pack_weights_kernel(const float* __restrict__ params, const int* __restrict__ bl
 
 int pack_weights(const float* params, const int* block_offsets_dev, int n_blocks, float* images, cudaStream_t st) {
     ProfScope prof(PROF_PACK, 4.0 * (IMG_FLOATS + TC_IMG_FLOATS) * n_blocks, st);
-    GCNN_LAUNCH(pack_weights_kernel, n_blocks, 256, 0, st, params, block_offsets_dev, images);
+    GCNN_LAUNCH(pack_weights_kernel, dim3(n_blocks, PACK_SPLIT), 256, 0, st, params, block_offsets_dev, images);
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
 }

@@ -24,6 +24,9 @@ SHAPES = {
     "capfac": (10201, 10100, 128, 40),
     "indset": (1950, 500, 64, 10),
     "miplib": (100_000, 100_000, 5_000, 100),
+    # test shape for the edge kernels' work decomposition: a block of heavy rows (120-390 edges, reduced by a whole CTA)
+    # behind rows of degree 0-6, hub columns (the transposed layout has long rows too), cut rows of 150 non-zeros
+    "skewed": (300, 400, 16, 150),
 }
 
 
@@ -102,6 +105,14 @@ def _structure(shape: str, rng) -> tuple[np.ndarray, int, int]:
         deg = np.where(heavy, np.exp(rng.uniform(np.log(100), np.log(1000), n_cons)), 1 + rng.poisson(5.0, n_cons))
         deg = _fit_total(np.round(deg), 1_000_000, 1, 1000, rng)
         ei = _edges_from_row_degrees(deg, n_vars, rng)
+    elif shape == "skewed":
+        deg = rng.integers(0, 7, n_cons)          # includes constraints without any edge
+        deg[-8:] = rng.integers(120, 391, 8)      # heavy rows next to each other
+        rows = np.repeat(np.arange(n_cons), deg)
+        hub = rng.random(rows.shape[0]) < np.where(rows >= n_cons - 8, 0.02, 0.6)  # most light entries hit five hub columns
+        cols = np.where(hub, rng.integers(0, 5, rows.shape[0]), rng.integers(5, n_vars, rows.shape[0]))
+        key = np.unique(rows.astype(np.int64) * n_vars + cols)  # distinct (row, column) pairs, row-major sorted
+        ei = np.vstack([key // n_vars, key % n_vars]).astype(np.int64)
     else:  # tiny / mini: a few edges per row, some isolated variables
         deg = rng.integers(1, max(2, min(n_vars, 6)), n_cons)
         ei = _edges_from_row_degrees(deg, n_vars, rng)

@@ -182,7 +182,8 @@ def test_device_tensor_inputs_take_the_unhinted_path(model, oracle64):
 
 # ---- per-op parity ----------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("s_f", [0.7, -1.3, 0.0])  # the sign of the pre-norm scale selects the active half-line of z
-@pytest.mark.parametrize("n_recv,n_send,E", [(50, 70, 600), (1, 3, 5), (300, 2, 4000), (64, 64, 0)])
+# (5, 3, 3000) and (300, 2, 4000): rows of 600 / 2000 edges take the whole-CTA path of the forward / backward kernels
+@pytest.mark.parametrize("n_recv,n_send,E", [(50, 70, 600), (1, 3, 5), (300, 2, 4000), (64, 64, 0), (5, 3, 3000), (2000, 900, 5000)])
 def test_edge_forward_backward_ops(model, n_recv, n_send, E, s_f):
     from gcnn_cut_selector_b200._lib import check
     lib, dev = model._lib, model.device
@@ -232,8 +233,9 @@ def test_edge_forward_backward_ops(model, n_recv, n_send, E, s_f):
                                  out_dS.data_ptr(), out_dw.data_ptr(), st))
     torch.cuda.synchronize()
     if E and s_f != 0.0:
-        assert rel_err(out_dS.cpu().numpy(), dS) <= 2e-6
-        assert rel_err(out_dw.cpu().numpy(), dw) <= 2e-6
+        tol = 2e-6 if E <= 500 * n_send else 1e-5  # one warp sums a 1,000-edge row serially in fp32 (as the reference does)
+        assert rel_err(out_dS.cpu().numpy(), dS) <= tol
+        assert rel_err(out_dw.cpu().numpy(), dw) <= tol
     else:
         assert np.all(out_dS.cpu().numpy() == 0) and np.all(out_dw.cpu().numpy() == 0)
 
@@ -300,8 +302,18 @@ def test_autograd_bridge_matches_fused_call(model, golden_dir):
 
 
 # ---- the four problem classes at BASELINE shapes, against the fp64 oracle run here -------------------------------------
-@pytest.mark.parametrize("shape,n", [("setcov", 1), ("setcov", 3), ("combauc", 4), ("indset", 4), ("capfac", 1)])
+# "skewed": heavy rows next to each other, hub columns, empty rows (weight-balanced CTA ranges); "skewed-coop" lowers the
+# long-row threshold so that those rows, the hub columns and the cut rows are reduced by whole CTAs (forward and backward)
+@pytest.mark.parametrize("shape,n", [("setcov", 1), ("setcov", 3), ("combauc", 4), ("indset", 4), ("capfac", 1), ("skewed", 3),
+                                     ("skewed-coop", 3)])
 def test_problem_classes_forward_backward(model, oracle64, shape, n):
+    if shape == "skewed-coop":
+        model.set_option("long_row", 64)
+        try:
+            test_problem_classes_forward_backward(model, oracle64, "skewed", n)
+        finally:
+            model.set_option("long_row", 512)
+        return
     batch = batching.concat_samples(synth.make_samples(shape, n, seed0=1000 + n))
     inputs, targets = batching.model_inputs(batch), batch[10]
     loss_sum, scores = model.loss_and_grads(inputs, targets)
