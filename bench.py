@@ -108,13 +108,15 @@ class ClockSampler(threading.Thread):
                 "source": "NVML, 5 ms period" if self.nvml is not None else "nvidia-smi polling"}
 
 
+def make_sample_sets(n_batches: int, graphs: int, seed0: int):
+    from gcnn_cut_selector_b200 import synth
+    return [synth.make_samples("setcov", graphs, seed0=seed0 + 1000 * b, n_structures=min(graphs, 8))
+            for b in range(n_batches)]
+
+
 def make_batches(n_batches: int, graphs: int, seed0: int):
-    from gcnn_cut_selector_b200 import batching, synth
-    out = []
-    for b in range(n_batches):
-        samples = synth.make_samples("setcov", graphs, seed0=seed0 + 1000 * b, n_structures=min(graphs, 8))
-        out.append(batching.concat_samples(samples))
-    return out
+    from gcnn_cut_selector_b200 import batching
+    return [batching.concat_samples(samples) for samples in make_sample_sets(n_batches, graphs, seed0)]
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -197,7 +199,8 @@ def run_b200(args):
     lr = 1e-4
 
     n_rot = 4
-    batches = make_batches(n_rot, graphs, seed0=10_000 * rank)
+    sample_sets = make_sample_sets(n_rot, graphs, seed0=10_000 * rank)
+    batches = [batching.concat_samples(samples) for samples in sample_sets]
     model = GCNN(device=dev, seed=0)
     model.check_indices = False  # no per-step stream sync in the timed loop; checked once after it
     trainer = DataParallelTrainer(model, lr) if world > 1 else None
@@ -316,21 +319,41 @@ def run_b200(args):
             p = pending.pop(0)
             _ = float(p.item()) if trainer else model.train_step_result(p)
 
-    e2e_stage(0)
-    for i in range(W):
-        e2e_step(i)
-    e2e_drain()
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(K):
-        e2e_step(W + i)
-    e2e_drain()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
+    def e2e_run():
+        e2e_stage(0)
+        for i in range(W):
+            e2e_step(i)
+        e2e_drain()
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            e2e_step(W + i)
+        e2e_drain()
+        barrier()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    e2e_s = e2e_run()
+
+    # ---- the same loop fed from packed sample records (gcnn_cut_selector_b200/shards.py): every step copies the 32
+    #      records of its batch from the pinned shard and the batch is assembled ON THE DEVICE (concatenation, index
+    #      offsets, casts of utils.load_batch, utils.py:395-423) inside the timed region; sorted edge lists travel as
+    #      row pointers.  Reported next to `e2e` as `e2e_records`.
+    import tempfile
+    from gcnn_cut_selector_b200 import shards
+    with tempfile.TemporaryDirectory() as tmp:
+        shard_path = os.path.join(tmp, f"bench_{rank}.shard")
+        shards.write_shard(shard_path, [s for samples in sample_sets for s in samples])
+        reader = shards.ShardReader(shard_path)
+    record_ids = [list(range(b * graphs, (b + 1) * graphs)) for b in range(n_rot)]
+    record_h2d = []
+
+    def e2e_stage(i):  # noqa: F811 -- e2e_step / e2e_run pick up the rebound stager
+        record_h2d.append(model.stage_records(reader, record_ids[i % n_rot], i & 1).h2d_bytes)
+
+    e2e_records_s = e2e_run()
 
     if rank == 0:
         value = graphs * world * K / (total_ms * 1e-3)
@@ -349,6 +372,13 @@ def run_b200(args):
                         "pipeline": "copies of batch i+1 overlap the step on batch i (two staging slots) and the loss "
                                     "of step i is read after step i+1 is enqueued; every step copies one full batch "
                                     "from pinned host memory and reads back one loss"},
+                "e2e_records": {"value": graphs * world * K / e2e_records_s, "unit": UNIT,
+                                "h2d_bytes_per_step": record_h2d[-1], "d2h_bytes_per_step": 4,
+                                "ms_per_step": 1e3 * e2e_records_s / K,
+                                "input": "the same loop fed with packed sample records (one per graph) from a pinned "
+                                         "shard; the batch is assembled on the device inside the timed region "
+                                         "(utils.load_batch's concatenation, index offsets and casts, utils.py:395-423); "
+                                         "sorted edge lists travel as row pointers"},
                 "gpu_launches": launches,
                 "roofline": roofline,
                 "roofline_segmented_reduction": seg,

@@ -68,6 +68,8 @@ SIGNATURES = {
     "gcnn_score_host": (_I, [_P, _P, _P, _BP, _P, _P]),
     "gcnn_train_step_host": (_I, [_P, _P, _P, _P, _P, _BP, _P, _F, _I64, C.POINTER(_F), _P]),
     "gcnn_stage_host_batch": (_I, [_P, _I, _BP, _P]),
+    "gcnn_record_bytes": (_I64, [_I64, _I64, _I64, _I64, _I64, _I]),
+    "gcnn_stage_records": (_I, [_P, _I, _P, _I64, C.POINTER(_I64)]),
     "gcnn_score_staged": (_I, [_P, _I, _P, _P, _P, _P]),
     "gcnn_train_step_staged": (_I, [_P, _I, _P, _P, _P, _P, _F, _I64, C.POINTER(_F), _P]),
     "gcnn_train_step_staged_async": (_I, [_P, _I, _P, _P, _P, _P, _F, _I64, _P]),

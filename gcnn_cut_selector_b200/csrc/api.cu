@@ -110,6 +110,10 @@ struct gcnn_workspace {
     struct Stage {
         float *cons, *cef, *var, *cut, *kef, *targets;
         int32_t *cei, *kei;
+        uint8_t* raw = nullptr;          // packed records as copied from the host (gcnn_stage_records)
+        int64_t raw_cap = 0;
+        RecordDesc* descs = nullptr;     // [MAX_RECORDS] device
+        RecordDesc* descs_host = nullptr;  // [MAX_RECORDS] pinned host
         gcnn_batch meta{};        // the staged batch with DEVICE pointers into this slot
         cudaEvent_t staged = nullptr, consumed = nullptr, result = nullptr;
         int valid = 0;
@@ -229,6 +233,10 @@ static size_t carve(gcnn_workspace* ws, char* base, const Caps& c) {
         g.kei = cv.take<int32_t>(2 * ek);
         g.kef = cv.take<float>(ek);
         g.targets = cv.take<float>(nk);
+        g.raw_cap = 4 * (nc * GCNN_CONS_FEATS + nv * GCNN_VAR_FEATS + nk * (GCNN_CUT_FEATS + 1) + 3 * (ec + ek)) +
+                    MAX_RECORDS * (GCNN_RECORD_HEADER_BYTES + 16 * REC_SECTIONS + 8);
+        g.raw = cv.take<uint8_t>(g.raw_cap);
+        g.descs = cv.take<RecordDesc>(MAX_RECORDS);
         g.valid = 0;
     }
 
@@ -832,7 +840,8 @@ static int read_error_flag(gcnn_workspace* ws, cudaStream_t st) {
     GCNN_CUDA_TRY(cudaStreamSynchronize(st));
     if (flag) {
         GCNN_CUDA_TRY(cudaMemsetAsync(ws->flags + 1, 0, sizeof(int32_t), st));
-        if (flag & 1) set_error("edge index out of range (InvalidArgument, cf. tf.gather in model.py:564)");
+        if (flag & 8) set_error("edge index + sample offset does not fit int32 (utils.py:403-414)");
+        else if (flag & 1) set_error("edge index out of range (InvalidArgument, cf. tf.gather in model.py:564)");
         else if (flag & 4) set_error("an edge leaves its sample's node range although per-sample counts were given");
         else set_error("batch flags claim edges sorted by row 0 (utils.py:102-104 order) but they are not");
         return GCNN_INVALID;
@@ -958,6 +967,8 @@ int gcnn_workspace_create(gcnn_workspace** out) {
         GCNN_CUDA_TRY(cudaEventCreateWithFlags(&ws->stage[s].result, cudaEventDisableTiming));
     }
     GCNN_CUDA_TRY(cudaHostAlloc((void**)&ws->h_result, 4 * sizeof(float), cudaHostAllocDefault));
+    for (int s = 0; s < 2; ++s)
+        GCNN_CUDA_TRY(cudaHostAlloc((void**)&ws->stage[s].descs_host, sizeof(RecordDesc) * MAX_RECORDS, cudaHostAllocDefault));
     *out = ws;
     return GCNN_OK;
 }
@@ -975,6 +986,8 @@ int gcnn_workspace_destroy(gcnn_workspace* ws) {
         if (ws->stage[s].result) cudaEventDestroy(ws->stage[s].result);
     }
     if (ws->h_result) cudaFreeHost(ws->h_result);
+    for (int s = 0; s < 2; ++s)
+        if (ws->stage[s].descs_host) cudaFreeHost(ws->stage[s].descs_host);
     delete ws;
     return GCNN_OK;
 }
@@ -1233,6 +1246,35 @@ int gcnn_stage_host_batch(gcnn_workspace* ws, int slot, const gcnn_batch* hb, co
     if (slot < 0 || slot > 1) { set_error("staging slot must be 0 or 1"); return GCNN_INVALID; }
     GCNN_TRY(check_batch(ws, hb, targets_host ? 1 : 0));
     return stage_batch(ws, slot, hb, targets_host);
+}
+
+int64_t gcnn_record_bytes(int64_t n_cons, int64_t n_vars, int64_t n_cuts, int64_t n_cons_edges, int64_t n_cut_edges,
+                          int flags) {
+    return record_layout(n_cons, n_vars, n_cuts, n_cons_edges, n_cut_edges, flags, nullptr);
+}
+
+int gcnn_stage_records(gcnn_workspace* ws, int slot, const void* const* records_host, int64_t n_records,
+                       int64_t* h2d_bytes_out) {
+    if (!ws || !ws->arena || slot < 0 || slot > 1 || (!records_host && n_records > 0)) {
+        set_error("gcnn_stage_records: bad arguments or workspace not reserved");
+        return GCNN_INVALID;
+    }
+    gcnn_workspace::Stage& g = ws->stage[slot];
+    cudaStream_t cs = ws->copy_st;
+    // the slot's previous consumer must be done with the batch tensors, and the previous assembly with descs_host
+    if (g.valid) GCNN_CUDA_TRY(cudaStreamWaitEvent(cs, g.consumed, 0));
+    if (g.valid) GCNN_CUDA_TRY(cudaEventSynchronize(g.staged));
+    AssembleOut out{g.cons, g.var, g.cut, g.targets, g.cef, g.kef, g.cei, g.kei, 0, 0};
+    gcnn_batch meta;
+    GCNN_TRY(assemble_records(records_host, n_records, g.raw, g.raw_cap, g.descs, g.descs_host, MAX_RECORDS, out,
+                              ws->cap.nc, ws->cap.nv, ws->cap.nk, ws->cap.ec, ws->cap.ek, &meta, h2d_bytes_out,
+                              ws->flags + 1, cs));
+    GCNN_CUDA_TRY(cudaEventRecord(g.staged, cs));
+    meta.cons_feats = g.cons; meta.cons_edge_inds = g.cei; meta.cons_edge_feats = g.cef;
+    meta.var_feats = g.var; meta.cut_feats = g.cut; meta.cut_edge_inds = g.kei; meta.cut_edge_feats = g.kef;
+    g.meta = meta;
+    g.valid = 1;
+    return GCNN_OK;
 }
 
 int gcnn_score_staged(gcnn_workspace* ws, int slot, const float* params, const float* prenorm, float* scores_host,

@@ -154,6 +154,31 @@ int build_layout(const int32_t* keys, const int32_t* others, const float* feats,
                  EdgeLayout& out, cudaStream_t st);
 int64_t sort_hist_entries(int64_t E);
 
+// ---- packed sample records (records.cu) ------------------------------------------------------------------------------
+constexpr int REC_SECTIONS = 10;
+
+// Per record: where its sections start (byte offsets into the staged raw buffer) and where they go (element offsets into
+// the batch tensors).  Built on the host from the record headers, uploaded with the records.
+struct RecordDesc {
+    int64_t sec[REC_SECTIONS];  // cons, var, cut, improvements, cons_ef, cut_ef, cons_rows, cons_cols, cut_rows, cut_cols
+    int64_t cons_off, var_off, cut_off, ec_off, ek_off;
+    int32_t n_cons, n_vars, n_cuts, ec, ek, flags;
+};
+
+struct AssembleOut {
+    float *cons, *var, *cut, *targets, *cef, *kef;
+    int32_t *cei, *kei;    // [2, E_total] each
+    int64_t ec_total, ek_total;
+};
+
+constexpr int64_t MAX_RECORDS = 4096;  // samples per batch the staging slots have descriptors for
+int64_t record_layout(int64_t n_cons, int64_t n_vars, int64_t n_cuts, int64_t ec, int64_t ek, int flags,
+                      int64_t sec_off[REC_SECTIONS]);
+int assemble_records(const void* const* records_host, int64_t n_records, uint8_t* raw, int64_t raw_cap,
+                     RecordDesc* descs_dev, RecordDesc* descs_host, int64_t max_records, const AssembleOut& out,
+                     int64_t cap_nc, int64_t cap_nv, int64_t cap_nk, int64_t cap_ec, int64_t cap_ek, gcnn_batch* meta,
+                     int64_t* h2d_bytes, int32_t* err_flag, cudaStream_t cs);
+
 // ---- edge kernels -------------------------------------------------------------------------------------------------
 struct EdgeScalars {  // device pointers to the scalars so no host sync is needed when they change (pretraining)
     const float* f_shift;

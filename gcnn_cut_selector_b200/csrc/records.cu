@@ -1,0 +1,191 @@
+// Batch assembly on the device from packed sample records.
+//
+// Reference: utils.load_batch (utils.py:339-426) un-gzips and un-pickles one file per sample, concatenates the feature
+// arrays (utils.py:395-399), adds the per-sample node offsets to every [2, E_s] edge-index block in int64
+// (utils.py:403-407) and casts to fp32 / int32 (utils.py:413-423) -- on the host, under the GIL, through
+// tf.numpy_function (utils.py:334).  Here a sample is packed ONCE into a binary record (gcnn_cut_selector_b200/shards.py;
+// layout in include/gcnn_b200.h) whose arrays already carry load_batch's element types; a batch is then k records copied
+// to the device as they are, and one kernel does what load_batch does: concatenate, shift, narrow.  Bit-exact with
+// load_batch: the features are copied verbatim (casting commutes with concatenation) and the index arithmetic is the
+// same int64 addition followed by a checked narrowing to int32 (numpy would wrap silently; an overflow sets error bit 8).
+//
+// Row indices of an edge list sorted by row (every list the reference produces, utils.py:102-104) may be stored as a row
+// pointer of n + 1 entries instead of E entries: 4 of the 12 bytes per edge do not cross PCIe; the kernel expands the
+// pointer with a binary search per edge (the pointer of one sample stays in L1).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace gcnn {
+
+constexpr int REC_THREADS = 256;
+
+__device__ __forceinline__ int32_t narrow_index(int64_t v, int32_t* err) {
+    if (v > (int64_t)INT32_MAX || v < (int64_t)INT32_MIN) atomicOr(err, 8);
+    return (int32_t)v;
+}
+
+// grid = (records, sections, REC_SLICES); a CTA copies one slice of one section of one record (a set-cover sample's
+// column list is 100 KB: one CTA per section would leave a few long CTAs next to many idle ones, and the kernel shares the
+// GPU with the training step of the previous batch)
+constexpr int REC_SLICES = 8;
+
+__global__ void __launch_bounds__(REC_THREADS)
+assemble_records_kernel(const uint8_t* __restrict__ raw, const RecordDesc* __restrict__ descs, AssembleOut out,
+                        int32_t* __restrict__ err) {
+    const RecordDesc d = descs[blockIdx.x];
+    const int s = blockIdx.y;
+    const uint8_t* src = raw + d.sec[s];
+    // this CTA's share [lo, hi) of n elements, cut at multiples of 4 elements (16 bytes)
+    auto share = [&](int64_t n, int64_t& lo, int64_t& hi) {
+        const int64_t per = ((n + REC_SLICES - 1) / REC_SLICES + 3) & ~(int64_t)3;
+        lo = min(n, per * blockIdx.z);
+        hi = min(n, lo + per);
+    };
+    auto copy_f32 = [&](float* dst, int64_t n) {
+        const float* p = reinterpret_cast<const float*>(src);
+        int64_t lo, hi;
+        share(n, lo, hi);
+        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {  // sections start 16-byte aligned in the record; lo is a multiple of 4
+            const int64_t n4 = (hi - lo) >> 2;
+            const float4* p4 = reinterpret_cast<const float4*>(p + lo);
+            float4* d4 = reinterpret_cast<float4*>(dst + lo);
+            int64_t i = threadIdx.x;
+            for (; i + 3 * REC_THREADS < n4; i += 4 * REC_THREADS) {  // four independent 16-byte loads in flight per thread
+                const float4 a = p4[i], b = p4[i + REC_THREADS], c = p4[i + 2 * REC_THREADS], e = p4[i + 3 * REC_THREADS];
+                d4[i] = a; d4[i + REC_THREADS] = b; d4[i + 2 * REC_THREADS] = c; d4[i + 3 * REC_THREADS] = e;
+            }
+            for (; i < n4; i += REC_THREADS) d4[i] = p4[i];
+            lo += n4 << 2;
+        }
+        for (int64_t i = lo + threadIdx.x; i < hi; i += REC_THREADS) dst[i] = p[i];
+    };
+    // row 0 of an index block: stored row indices, or a row pointer to expand; + the rows that precede this sample
+    auto rows = [&](int32_t* dst, int64_t n_edges, int32_t n_rows, int64_t shift, bool as_ptr) {
+        const int32_t* p = reinterpret_cast<const int32_t*>(src);
+        int64_t e0, e1;
+        share(n_edges, e0, e1);
+        for (int64_t e = e0 + threadIdx.x; e < e1; e += REC_THREADS) {
+            int32_t r;
+            if (as_ptr) {  // largest r in [0, n_rows) with p[r] <= e
+                int lo = 0, hi = n_rows - 1;
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if ((int64_t)p[mid] <= e) lo = mid; else hi = mid - 1;
+                }
+                r = lo;
+            } else r = p[e];
+            dst[e] = narrow_index((int64_t)r + shift, err);
+        }
+    };
+    auto cols = [&](int32_t* dst, int64_t n_edges, int64_t shift) {
+        const int32_t* p = reinterpret_cast<const int32_t*>(src);
+        int64_t e0, e1;
+        share(n_edges, e0, e1);
+        int64_t e = e0 + threadIdx.x;
+        for (; e + 3 * REC_THREADS < e1; e += 4 * REC_THREADS) {
+            const int32_t a = p[e], b = p[e + REC_THREADS], c = p[e + 2 * REC_THREADS], f = p[e + 3 * REC_THREADS];
+            dst[e] = narrow_index((int64_t)a + shift, err);
+            dst[e + REC_THREADS] = narrow_index((int64_t)b + shift, err);
+            dst[e + 2 * REC_THREADS] = narrow_index((int64_t)c + shift, err);
+            dst[e + 3 * REC_THREADS] = narrow_index((int64_t)f + shift, err);
+        }
+        for (; e < e1; e += REC_THREADS) dst[e] = narrow_index((int64_t)p[e] + shift, err);
+    };
+    switch (s) {
+        case 0: copy_f32(out.cons + d.cons_off * GCNN_CONS_FEATS, (int64_t)d.n_cons * GCNN_CONS_FEATS); break;
+        case 1: copy_f32(out.var + d.var_off * GCNN_VAR_FEATS, (int64_t)d.n_vars * GCNN_VAR_FEATS); break;
+        case 2: copy_f32(out.cut + d.cut_off * GCNN_CUT_FEATS, (int64_t)d.n_cuts * GCNN_CUT_FEATS); break;
+        case 3: copy_f32(out.targets + d.cut_off, d.n_cuts); break;
+        case 4: copy_f32(out.cef + d.ec_off, d.ec); break;
+        case 5: copy_f32(out.kef + d.ek_off, d.ek); break;
+        case 6: rows(out.cei + d.ec_off, d.ec, d.n_cons, d.cons_off, (d.flags & GCNN_RECORD_CONS_ROWS_AS_PTR) != 0); break;
+        case 7: cols(out.cei + out.ec_total + d.ec_off, d.ec, d.var_off); break;
+        case 8: rows(out.kei + d.ek_off, d.ek, d.n_cuts, d.cut_off, (d.flags & GCNN_RECORD_CUT_ROWS_AS_PTR) != 0); break;
+        default: cols(out.kei + out.ek_total + d.ek_off, d.ek, d.var_off); break;
+    }
+}
+
+static inline int64_t pad16(int64_t b) { return (b + 15) & ~(int64_t)15; }
+
+// Section sizes of a record with these counts, in record order; returns the record's total size (header included).
+int64_t record_layout(int64_t n_cons, int64_t n_vars, int64_t n_cuts, int64_t ec, int64_t ek, int flags,
+                      int64_t sec_off[REC_SECTIONS]) {
+    const int64_t bytes[REC_SECTIONS] = {
+        4 * n_cons * GCNN_CONS_FEATS, 4 * n_vars * GCNN_VAR_FEATS, 4 * n_cuts * GCNN_CUT_FEATS, 4 * n_cuts, 4 * ec, 4 * ek,
+        4 * ((flags & GCNN_RECORD_CONS_ROWS_AS_PTR) ? n_cons + 1 : ec), 4 * ec,
+        4 * ((flags & GCNN_RECORD_CUT_ROWS_AS_PTR) ? n_cuts + 1 : ek), 4 * ek};
+    int64_t off = GCNN_RECORD_HEADER_BYTES;
+    for (int s = 0; s < REC_SECTIONS; ++s) {
+        if (sec_off) sec_off[s] = off;
+        off += pad16(bytes[s]);
+    }
+    return off;
+}
+
+// Reads k record headers (host memory), lays the batch out, copies records + descriptors and launches the kernel on
+// `cs`.  raw / descs_dev / descs_host are the slot's staging areas; totals come back through `meta` (device pointers are
+// filled in by the caller).
+int assemble_records(const void* const* records_host, int64_t n_records, uint8_t* raw, int64_t raw_cap,
+                     RecordDesc* descs_dev, RecordDesc* descs_host, int64_t max_records, const AssembleOut& out_in,
+                     int64_t cap_nc, int64_t cap_nv, int64_t cap_nk, int64_t cap_ec, int64_t cap_ek, gcnn_batch* meta,
+                     int64_t* h2d_bytes, int32_t* err_flag, cudaStream_t cs) {
+    if (n_records < 0 || n_records > max_records) { set_error("too many records for one batch (%lld > %lld)", (long long)n_records, (long long)max_records); return GCNN_INVALID; }
+    int64_t nc = 0, nv = 0, nk = 0, ec = 0, ek = 0, raw_off = 0;
+    int all_flags = GCNN_RECORD_CONS_ROWS_AS_PTR | GCNN_RECORD_CUT_ROWS_AS_PTR | GCNN_RECORD_CONS_ROWS_SORTED | GCNN_RECORD_CUT_ROWS_SORTED;
+    for (int64_t r = 0; r < n_records; ++r) {
+        const int32_t* h = static_cast<const int32_t*>(records_host[r]);
+        if (!h || h[0] != GCNN_RECORD_MAGIC) { set_error("record %lld: bad magic", (long long)r); return GCNN_INVALID; }
+        RecordDesc& d = descs_host[r];
+        d.flags = h[1]; d.n_cons = h[2]; d.n_vars = h[3]; d.n_cuts = h[4]; d.ec = h[5]; d.ek = h[6];
+        if (d.n_cons < 0 || d.n_vars < 0 || d.n_cuts < 0 || d.ec < 0 || d.ek < 0) { set_error("record %lld: negative size", (long long)r); return GCNN_INVALID; }
+        int64_t sec[REC_SECTIONS];
+        const int64_t bytes = record_layout(d.n_cons, d.n_vars, d.n_cuts, d.ec, d.ek, d.flags, sec);
+        int64_t declared;
+        memcpy(&declared, h + 8, sizeof(declared));
+        if (declared != bytes) { set_error("record %lld: header says %lld bytes, layout needs %lld", (long long)r, (long long)declared, (long long)bytes); return GCNN_INVALID; }
+        if (raw_off + bytes > raw_cap) { set_error("records do not fit the staging area: reserve a larger workspace"); return GCNN_INVALID; }
+        for (int s = 0; s < REC_SECTIONS; ++s) d.sec[s] = raw_off + sec[s];
+        d.cons_off = nc; d.var_off = nv; d.cut_off = nk; d.ec_off = ec; d.ek_off = ek;
+        nc += d.n_cons; nv += d.n_vars; nk += d.n_cuts; ec += d.ec; ek += d.ek;
+        raw_off += bytes;
+        all_flags &= d.flags;
+    }
+    if (nc > cap_nc || nv > cap_nv || nk > cap_nk || ec > cap_ec || ek > cap_ek) {
+        set_error("workspace too small for these records: call gcnn_workspace_reserve first");
+        return GCNN_INVALID;
+    }
+    // host-to-device: records that are neighbours in host memory travel in one copy
+    int64_t run_begin = 0;
+    for (int64_t r = 0; r < n_records; ++r) {
+        const int64_t bytes = (r + 1 < n_records ? descs_host[r + 1].sec[0] : raw_off + GCNN_RECORD_HEADER_BYTES) - descs_host[r].sec[0];
+        const bool last = r + 1 == n_records;
+        const bool contiguous = !last && static_cast<const uint8_t*>(records_host[r + 1]) == static_cast<const uint8_t*>(records_host[r]) + bytes;
+        if (!contiguous) {
+            const int64_t dst = descs_host[run_begin].sec[0] - GCNN_RECORD_HEADER_BYTES;
+            const int64_t end = descs_host[r].sec[0] - GCNN_RECORD_HEADER_BYTES + bytes;
+            GCNN_CUDA_TRY(cudaMemcpyAsync(raw + dst, records_host[run_begin], (size_t)(end - dst), cudaMemcpyHostToDevice, cs));
+            run_begin = r + 1;
+        }
+    }
+    if (n_records > 0) {
+        GCNN_CUDA_TRY(cudaMemcpyAsync(descs_dev, descs_host, sizeof(RecordDesc) * (size_t)n_records, cudaMemcpyHostToDevice, cs));
+        AssembleOut out = out_in;
+        out.ec_total = ec; out.ek_total = ek;
+        GCNN_LAUNCH_ORDERED(assemble_records_kernel, dim3((unsigned)n_records, REC_SECTIONS, REC_SLICES), REC_THREADS, 0, cs, raw, descs_dev, out, err_flag);
+        GCNN_LAUNCH_CHECK();
+    }
+    *meta = gcnn_batch{};
+    meta->n_cons = nc; meta->n_vars = nv; meta->n_cuts = nk; meta->n_cons_edges = ec; meta->n_cut_edges = ek;
+    // sorted blocks shifted by increasing offsets stay sorted (utils.py:403-407)
+    if (n_records > 0) {
+        if (all_flags & GCNN_RECORD_CONS_ROWS_SORTED) meta->flags |= GCNN_BATCH_CONS_EDGES_SORTED;
+        if (all_flags & GCNN_RECORD_CUT_ROWS_SORTED) meta->flags |= GCNN_BATCH_CUT_EDGES_SORTED;
+    }
+    if (h2d_bytes) *h2d_bytes = raw_off + (int64_t)sizeof(RecordDesc) * n_records;
+    return GCNN_OK;
+}
+
+int64_t record_desc_bytes() { return (int64_t)sizeof(RecordDesc); }
+
+}  // namespace gcnn

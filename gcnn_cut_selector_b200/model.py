@@ -374,6 +374,19 @@ class GCNN:
         check(self._lib.gcnn_stage_host_batch(self._ws, slot, C.byref(b), tgt))
         self._staged[slot] = host_batch  # keeps the pinned buffers alive until the slot is consumed
 
+    def stage_records(self, reader, ids, slot: int, training: bool = True) -> "StagedRecords":
+        """Stage the batch made of records ``ids`` of a ``shards.ShardReader`` in slot 0/1: the packed records are copied
+        to the device as they are and one kernel assembles the batch there (the device-side ``utils.load_batch``,
+        utils.py:339-426).  Returns immediately; use the slot like one filled by ``stage_host``."""
+        nc, nv, nk, ec, ek = reader.totals(ids)
+        check(self._lib.gcnn_workspace_reserve(self._ws, nc, nv, nk, ec, ek, int(training)))
+        ptrs = reader.pointers(ids)
+        h2d = C.c_int64()
+        check(self._lib.gcnn_stage_records(self._ws, slot, ptrs.ctypes.data, ptrs.shape[0], C.byref(h2d)))
+        staged = StagedRecords(reader, nk, int(ptrs.shape[0]), int(h2d.value))
+        self._staged[slot] = staged  # keeps the pinned shard alive until the slot is consumed
+        return staged
+
     def train_step_staged(self, slot: int, lr: float) -> float:
         """Optimisation step on the batch staged in ``slot``; returns the mean loss (host float)."""
         self.adam_step += 1
@@ -465,6 +478,20 @@ class GCNN:
             return False
         except PreNormException:
             return True
+
+
+class StagedRecords:
+    """What ``GCNN.stage_records`` put into a staging slot (keeps the shard's pinned memory alive)."""
+
+    def __init__(self, reader, n_cuts: int, n_graphs: int, h2d_bytes: int):
+        self.reader, self.n_cuts, self.n_graphs, self.h2d_bytes = reader, n_cuts, n_graphs, h2d_bytes
+        self._scores = None
+
+    @property
+    def scores(self):  # pinned result buffer of score_staged; allocated on first use (training never needs it)
+        if self._scores is None:
+            self._scores = torch.empty(self.n_cuts, dtype=torch.float32).pin_memory()
+        return self._scores
 
 
 class HostBatch:

@@ -185,6 +185,40 @@ int gcnn_train_step_result(gcnn_workspace* ws, int slot, float* loss_host, void*
 int gcnn_staged_batch(gcnn_workspace* ws, int slot, gcnn_batch* out, float** targets_dev, void* stream);
 int gcnn_release_staged(gcnn_workspace* ws, int slot, void* stream);
 
+/* ---- packed sample records: batch assembly on the device (replaces the host side of utils.load_batch, utils.py:339-426:
+ *      gzip + pickle per sample, np.concatenate utils.py:395-399, int64 index shifts utils.py:403-407, casts
+ *      utils.py:413-423).  A sample is packed once into a record whose arrays already have load_batch's element types;
+ *      gcnn_stage_records copies k records to the device as they are and ONE kernel concatenates the features, adds the
+ *      per-sample node offsets to the edge indices (int64 add, checked narrowing to int32) and writes the batch into a
+ *      staging slot -- bit-exact with load_batch.  The slot is then used exactly like one filled by
+ *      gcnn_stage_host_batch (gcnn_train_step_staged_async, gcnn_score_staged, gcnn_staged_batch ...).
+ *
+ *      Record layout (little-endian; every section padded to a multiple of 16 bytes):
+ *        header, 64 bytes: int32 magic, flags, n_cons, n_vars, n_cuts, n_cons_edges, n_cut_edges, 0; int64 record bytes;
+ *                          24 zero bytes
+ *        fp32 cons_feats [n_cons,4] | var_feats [n_vars,14] | cut_feats [n_cuts,6] | improvements [n_cuts]
+ *             | cons_edge_feats [Ec] | cut_edge_feats [Ek]
+ *        int32 cons rows [Ec], or the row pointer [n_cons+1] with GCNN_RECORD_CONS_ROWS_AS_PTR | cons cols [Ec]
+ *              | cut rows [Ek], or [n_cuts+1] with GCNN_RECORD_CUT_ROWS_AS_PTR | cut cols [Ek]
+ *      Indices are local to the sample.  *_ROWS_AS_PTR is only valid for lists sorted by row (all the reference
+ *      produces, utils.py:102-104) and implies *_ROWS_SORTED; a batch of records that all carry *_ROWS_SORTED gets the
+ *      matching GCNN_BATCH_*_EDGES_SORTED promise. */
+#define GCNN_RECORD_MAGIC 0x31524347 /* "GCR1" */
+#define GCNN_RECORD_HEADER_BYTES 64
+#define GCNN_RECORD_CONS_ROWS_AS_PTR 1
+#define GCNN_RECORD_CUT_ROWS_AS_PTR 2
+#define GCNN_RECORD_CONS_ROWS_SORTED 4
+#define GCNN_RECORD_CUT_ROWS_SORTED 8
+#define GCNN_MAX_RECORDS 4096 /* samples per batch */
+/* Size in bytes of a record with these counts and flags (header included). */
+int64_t gcnn_record_bytes(int64_t n_cons, int64_t n_vars, int64_t n_cuts, int64_t n_cons_edges, int64_t n_cut_edges,
+                          int flags);
+/* records_host: n_records HOST pointers to records (pinned memory for asynchronous copies; neighbours in memory travel
+ * in one copy).  Enqueues copies and the assembly kernel on the library's copy stream and returns immediately; the
+ * workspace must have been reserved for the batch totals.  h2d_bytes_out (optional) receives the bytes copied. */
+int gcnn_stage_records(gcnn_workspace* ws, int slot, const void* const* records_host, int64_t n_records,
+                       int64_t* h2d_bytes_out);
+
 /* ---- per-op entry points (unit parity tests; same kernels the whole-model calls launch) ---------------------- */
 /* H[t] = sum_{e in seg(t)} relu(s_f * (R[t] + f_e * w + S[src_e])), cnt[t] = number of active terms per feature.
  * ptr/src/val describe segments grouped by the receiving node.  f_e = (val + f_shift) * f_scale. */
