@@ -191,11 +191,14 @@ __global__ void finalize_layout_kernel(const int32_t* __restrict__ keys, const i
     const int32_t k = p < E ? key_at(p) : n_owner;
     const int32_t prev = p > 0 ? key_at(p - 1) : -1;
     for (int32_t r = prev + 1; r <= k; ++r) out.ptr[r] = (int32_t)p;
-    // an owner has more than m edges iff two positions m apart carry the same key.  Bit 0: some row is longer than
-    // long_row (reduced by a whole CTA in the edge kernels); bit 1: some row is longer than heavy_row = max(32, 4 x the
-    // mean degree) -- the edge kernels then split the rows over CTAs by weight instead of by count.
-    if (p < E) {
-        const int bits = ((p >= long_row && key_at(p - long_row) == k) ? 1 : 0) | ((p >= heavy_row && key_at(p - heavy_row) == k) ? 2 : 0);
+    // Degree report for the edge kernels.  An owner with more than m edges covers more than m consecutive positions, so
+    // some position p = 0 (mod 16) of it has p - (m - 16) inside it too: every 16th thread compares two keys m - 16
+    // apart (owners a little shorter than m may be reported as well -- the report only selects a code path).
+    // Bit 0: some owner is longer than long_row (reduced by a whole CTA); bit 1: longer than heavy_row = max(32, 4 x
+    // the mean degree) -- the edge kernels then split the rows over CTAs by weight instead of by count.
+    if (p < E && (p & 15) == 0) {
+        const int64_t dl = long_row - 16, dh = heavy_row - 16;
+        const int bits = ((p >= dl && key_at(p - dl) == k) ? 1 : 0) | ((p >= dh && key_at(p - dh) == k) ? 2 : 0);
         if (bits) atomicOr(long_flag, bits);
     }
     if (p < E) {

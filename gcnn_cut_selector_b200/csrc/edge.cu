@@ -184,10 +184,11 @@ __device__ __forceinline__ void forward_chunk(const int n, const int base, const
     }
 }
 
+template <int WARPS>
 struct EdgeFwdSmem {
     int range[2];
     int next_row;
-    alignas(16) float part[EDGE_WARPS][2][D];  // long rows: per-warp partial sums (value, active count)
+    alignas(16) float part[WARPS][2][D];  // long rows: per-warp partial sums (value, active count)
 };
 
 // The forward row loop.  IDENT: the layout kept the input order (perm[p] == p, e.g. batches sorted by their left index,
@@ -200,14 +201,15 @@ struct EdgeFwdSmem {
 //     <= 32-edge chunks, and while the gathers of chunk i are in flight it already loads the indices / coefficients of
 //     chunk i + 1 (next chunk of the row, or first chunk of its next row) and the pointers of the row after that, so a
 //     short row does not cost three dependent memory latencies (pointer -> indices -> gathered rows).
-template <bool TRAIN, bool NEG, bool IDENT>
+template <bool TRAIN, bool NEG, bool IDENT, int WARPS>
 __device__ __forceinline__ void edge_forward_rows(const int32_t* __restrict__ ptr, const int32_t* __restrict__ src,
                                                   const float* __restrict__ val, int64_t n_recv,
                                                   const float* __restrict__ R, const float* __restrict__ S,
                                                   const float* __restrict__ w_edge, EdgeScalars sc,
                                                   float* __restrict__ H, float* __restrict__ cnt,
                                                   const int32_t* __restrict__ perm, uint2* __restrict__ masks,
-                                                  const int long_row, const bool by_weight, EdgeFwdSmem& sm) {
+                                                  const int long_row, const bool by_weight, const bool dynamic_rows,
+                                                  EdgeFwdSmem<WARPS>& sm) {
     const bool any_long = long_row > 0;
     const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15, warp = threadIdx.x >> 5;
     const bool wm = TRAIN && masks != nullptr;  // kernel-uniform
@@ -225,7 +227,7 @@ __device__ __forceinline__ void edge_forward_rows(const int32_t* __restrict__ pt
                 const int row = rb + __ffs(m) - 1;
                 m &= m - 1;
                 const int beg = ptr[row], end = ptr[row + 1];
-                const int share = ((end - beg + EDGE_WARPS - 1) / EDGE_WARPS + 7) & ~7;
+                const int share = ((end - beg + WARPS - 1) / WARPS + 7) & ~7;
                 const int a = min(end, beg + warp * share), b = min(end, a + share);
                 const float4 r4 = ld4(R + (int64_t)row * D + hl * 4);
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), act = acc;
@@ -248,7 +250,7 @@ __device__ __forceinline__ void edge_forward_rows(const int32_t* __restrict__ pt
                     const int which = threadIdx.x >> 6, c = threadIdx.x & (D - 1);
                     float t = sm.part[0][which][c];
 #pragma unroll
-                    for (int w = 1; w < EDGE_WARPS; ++w) t += sm.part[w][which][c];
+                    for (int w = 1; w < WARPS; ++w) t += sm.part[w][which][c];
                     if (which == 0) H[(int64_t)row * D + c] = s_f * t;
                     else if (TRAIN) cnt[(int64_t)row * D + c] = t;
                 }
@@ -257,9 +259,15 @@ __device__ __forceinline__ void edge_forward_rows(const int32_t* __restrict__ pt
         }
     }
 
-    if (threadIdx.x == 0) sm.next_row = r0 + EDGE_WARPS;
+    if (threadIdx.x == 0) sm.next_row = r0 + WARPS;
     __syncthreads();
-    auto grab = [&]() { int r = 0; if (lane == 0) r = atomicAdd(&sm.next_row, 1); return __shfl_sync(0xffffffffu, r, 0); };
+    int static_next = r0 + warp;
+    auto grab = [&]() {
+        if (!dynamic_rows) { static_next += WARPS; return static_next; }
+        int r = 0;
+        if (lane == 0) r = atomicAdd(&sm.next_row, 1);
+        return __shfl_sync(0xffffffffu, r, 0);
+    };
     int row = r0 + warp;
     if (row >= r1) return;
     int beg = ptr[row], end = ptr[row + 1];
@@ -316,16 +324,19 @@ __device__ __forceinline__ void edge_forward_rows(const int32_t* __restrict__ pt
 
 // 256 threads x 3 CTAs per SM (<= 85 registers): against 512 x 2 (64 registers, 32 warps per SM) the loop needs ~20 %
 // fewer instructions per edge (no rematerialised addresses / register moves), which outweighs the 8 warps fewer.
-template <bool TRAIN>
-__global__ void __launch_bounds__(EDGE_THREADS, 3)
+template <bool TRAIN, int THREADS, int MIN_CTAS>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS)
 edge_forward_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ src, const float* __restrict__ val,
                     int64_t n_recv, const float* __restrict__ R, const float* __restrict__ S,
                     const float* __restrict__ w_edge, EdgeScalars sc, float* __restrict__ H, float* __restrict__ cnt,
                     const int32_t* __restrict__ perm, uint2* __restrict__ masks, const int32_t* __restrict__ reordered,
-                    const int32_t* __restrict__ long_rows, const int long_row_arg) {
+                    const int32_t* __restrict__ long_rows, const int long_row_arg, const int dynamic_rows_arg) {
     pdl_enter();
-    __shared__ EdgeFwdSmem sm;
+    __shared__ EdgeFwdSmem<THREADS / 32> sm;
+    // the three scalars the kernel branches on, loaded back to back (one memory latency, not three)
     const float s_f = *sc.s_f;
+    const int report = long_rows ? *long_rows : 3;   // degree report of the layout; layouts built elsewhere carry none
+    const int reord = reordered ? *reordered : 1;
     if (s_f == 0.f) {  // relu(0 * z) = 0: nothing is active (degenerate pre-norm scale; keeps cnt and the masks exact)
         const int lane = threadIdx.x & 31, warps = blockDim.x >> 5;
         const int64_t row_beg = n_recv * (int64_t)blockIdx.x / gridDim.x, row_end = n_recv * ((int64_t)blockIdx.x + 1) / gridDim.x;
@@ -337,14 +348,12 @@ edge_forward_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__
         }
         return;
     }
-    const bool ident = TRAIN && reordered != nullptr && *reordered == 0;  // kernel-uniform
-    // degree report of the layout (layouts built elsewhere carry none: assume long and heavy rows may exist)
-    const int report = long_rows ? *long_rows : 3;
+    const bool ident = TRAIN && reord == 0;                // kernel-uniform
     const int long_row = (report & 1) ? long_row_arg : 0;  // 0 = no row needs a whole CTA
     const bool by_weight = report != 0;
-    if (s_f < 0.f) edge_forward_rows<TRAIN, true, false>(ptr, src, val, n_recv, R, S, w_edge, sc, H, cnt, perm, masks, long_row, by_weight, sm);
-    else if (ident) edge_forward_rows<TRAIN, false, true>(ptr, src, val, n_recv, R, S, w_edge, sc, H, cnt, perm, masks, long_row, by_weight, sm);
-    else edge_forward_rows<TRAIN, false, false>(ptr, src, val, n_recv, R, S, w_edge, sc, H, cnt, perm, masks, long_row, by_weight, sm);
+    if (s_f < 0.f) edge_forward_rows<TRAIN, true, false, THREADS / 32>(ptr, src, val, n_recv, R, S, w_edge, sc, H, cnt, perm, masks, long_row, by_weight, dynamic_rows_arg != 0 || by_weight, sm);
+    else if (ident) edge_forward_rows<TRAIN, false, true, THREADS / 32>(ptr, src, val, n_recv, R, S, w_edge, sc, H, cnt, perm, masks, long_row, by_weight, dynamic_rows_arg != 0 || by_weight, sm);
+    else edge_forward_rows<TRAIN, false, false, THREADS / 32>(ptr, src, val, n_recv, R, S, w_edge, sc, H, cnt, perm, masks, long_row, by_weight, dynamic_rows_arg != 0 || by_weight, sm);
 }
 
 int edge_forward(const EdgeLayout& L, int64_t n_recv, const float* R, const float* S, const float* w_edge,
@@ -354,9 +363,16 @@ int edge_forward(const EdgeLayout& L, int64_t n_recv, const float* R, const floa
     if (n_recv <= 0) return GCNN_OK;
     if (n_recv >= (int64_t)INT32_MAX) { set_error("edge_forward: more than 2^31 rows"); return GCNN_INVALID; }
     ProfScope prof(PROF_EDGE_FWD, prof_bytes, st);
-    const unsigned grid = (unsigned)min((int64_t)NUM_SMS * 3, ceil_div(n_recv, EDGE_WARPS));
-    if (cnt) GCNN_LAUNCH(edge_forward_kernel<true>, grid, EDGE_THREADS, 0, st, L.ptr, L.other, L.val, n_recv, R, S, w_edge, sc, H, cnt, L.perm, mk, L.reordered, L.long_rows, long_row_threshold());
-    else GCNN_LAUNCH(edge_forward_kernel<false>, grid, EDGE_THREADS, 0, st, L.ptr, L.other, L.val, n_recv, R, S, w_edge, sc, H, cnt, L.perm, mk, L.reordered, L.long_rows, long_row_threshold());
+    static const int cfg = [] { const char* e = getenv("GCNN_EDGE_CFG"); return e ? atoi(e) : 1; }();
+    static const int dyn = [] { const char* e = getenv("GCNN_EDGE_DYNAMIC"); return e ? atoi(e) : 1; }();
+    const int threads = cfg == 1 ? 256 : 512, per_sm = cfg == 1 ? 3 : 2;
+    const unsigned grid = (unsigned)min((int64_t)NUM_SMS * per_sm, ceil_div(n_recv, threads / 32));
+#define GCNN_EDGE_FWD_LAUNCH(TRAIN_, T_, C_)                                                                             \
+    GCNN_LAUNCH((edge_forward_kernel<TRAIN_, T_, C_>), grid, threads, 0, st, L.ptr, L.other, L.val, n_recv, R, S, w_edge, sc, \
+                H, cnt, L.perm, mk, L.reordered, L.long_rows, long_row_threshold(), dyn)
+    if (cfg == 1) { if (cnt) GCNN_EDGE_FWD_LAUNCH(true, 256, 3); else GCNN_EDGE_FWD_LAUNCH(false, 256, 3); }
+    else { if (cnt) GCNN_EDGE_FWD_LAUNCH(true, 512, 2); else GCNN_EDGE_FWD_LAUNCH(false, 512, 2); }
+#undef GCNN_EDGE_FWD_LAUNCH
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
 }

@@ -471,6 +471,30 @@ class GCNN:
                 return layer, f"{self.name}/{layer.name}"
         return None
 
+    def pretrain_fused(self, batches) -> int:
+        """The whole pre-norm pretraining of ``model_trainer.pretrain`` (model_trainer.py:194-236) in 7 passes over
+        ``batches`` (a re-iterable of model input tuples) instead of 11: the five input layers normalise raw features
+        (model.py:174-198), so their statistics depend on no parameter and share the first pass; the six convolution
+        layers form a chain (each needs everything before it frozen, model.py:100-117) and keep one pass each.  Every
+        layer sees the same batches in the same order as in the reference's loop, so the Chan merges (model.py:416-423)
+        and the frozen shift / scale values are identical to the 11-pass protocol.  Returns the number of passes."""
+        self.pretrain_init()
+        layers, passes = self._prenorm_layers, 0
+        for group in [layers[:5]] + [[layer] for layer in layers[5:]]:
+            seen = False
+            for b in batches:
+                dev_inputs = self.prepare_inputs(b)
+                for layer in group:
+                    self._update_prenorm(layer, dev_inputs)
+                    layer.received_updates = True
+                seen = True
+            if not seen:
+                break
+            for layer in group:
+                layer.stop_updates()
+            passes += 1
+        return passes
+
     def pretrain(self, *args, **kwargs) -> bool:
         try:
             with torch.no_grad():

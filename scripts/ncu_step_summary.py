@@ -28,9 +28,25 @@ def to_bytes(r, k):
     return val(r, k) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
 
 
+# The capture may hold more than one step and kernels of other libraries (torch's fill of the L2-flush buffer): keep
+# this library's kernels and cut out ONE step, from the first CSR-build kernel that follows an Adam update to the next
+# Adam update.
+def short(r):
+    return r[col["Kernel Name"]].split("(")[0].replace("void ", "").replace("gcnn::", "")
+
+
+ours = [r for r in rows[2:] if any(key in short(r) for key, _ in CLASS)]
+starts = [i for i, r in enumerate(ours) if "check_init_hist" in short(r) and (i == 0 or "adam" in short(ours[i - 1]))]
+window = ours
+for s0 in starts:
+    ends = [i for i in range(s0, len(ours)) if "adam" in short(ours[i])]
+    if ends and (s0 > 0 or len(starts) == 1):
+        window = ours[s0:ends[0] + 1]
+        break
+
 out, per_class = [], {}
-for r in rows[2:]:
-    name = r[col["Kernel Name"]].split("(")[0].replace("void ", "").replace("gcnn::", "")
+for r in window:
+    name = short(r)
     cls = next((c for key, c in CLASS if key in name), "other")
     dur = val(r, "gpu__time_duration.sum")
     dur_us = dur * {"usecond": 1, "nsecond": 1e-3, "msecond": 1e3}.get(units[col["gpu__time_duration.sum"]], 1)

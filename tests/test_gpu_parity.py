@@ -501,6 +501,32 @@ def test_pretrain_protocol_matches_golden(golden_dir):
     assert rel_err(out.cpu().numpy(), z["scores_f64"]) <= 5e-5  # scales carry fp32 rounding of the statistics
 
 
+def test_fused_pretraining_equals_the_eleven_pass_protocol(golden_dir):
+    """Seven passes (input layers together) freeze exactly the values the reference's one-layer-per-pass loop does."""
+    from gcnn_cut_selector_b200 import GCNN
+    z = np.load(os.path.join(golden_dir, "pretrain_tiny.npz"))
+    batches = [golden_inputs(z, f"b{b}_") for b in range(2)]
+    out = []
+    for fused in (False, True):
+        m = GCNN(device="cuda:0", seed=2)
+        m.restore_state(os.path.join(golden_dir, "state_stream.pkl"))
+        if fused:
+            assert m.pretrain_fused(batches) == 7
+        else:
+            m.pretrain_init()
+            passes = 0
+            while True:  # model_trainer.py:207-234
+                for b in batches:
+                    if not m.pretrain(b, True):
+                        break
+                if m.pretrain_next() is None:
+                    break
+                passes += 1
+            assert passes == 11
+        out.append(m.flat_prenorm.clone())
+    assert torch.equal(out[0], out[1])
+
+
 def test_save_restore_roundtrip(model, golden_dir, tmp_path):
     path = str(tmp_path / "w.pkl")
     model.save_state(path)
