@@ -7,8 +7,11 @@
 //
 // Mapping: one warp per segment (receiving node in the forward, sending node in the backward); a half-warp covers one
 // 64-float row with one float4 per lane, so a warp works on two edges at a time and each gathered row is one fully
-// coalesced 256-byte read.  Reduction order is fixed by the layout -> bit-reproducible, no atomics.
-// HBM-bound; algorithmic bytes per launch are stated in DESIGN.md.
+// coalesced 256-byte read.  Persistent CTAs own contiguous row ranges -- equal in rows for regular graphs, equal in
+// weight (edges + rows) when the CSR build reports heavy rows; rows beyond long_row_threshold() are reduced by a whole
+// CTA.  Reduction order is fixed by the layout and the launch shape -> bit-reproducible, no atomics.
+// Roofline: HBM for the algorithmic bytes (stated in DESIGN.md); what the kernels actually run against is the L2 / L1
+// gather rate and instruction issue (profiles/).
 #include <stdlib.h>
 
 #include "common.cuh"
