@@ -449,7 +449,8 @@ class GCNN:
         return [PreNormLayer(self, i, name, n, offs[name + "/shift"] if has_shift else None, offs[name + "/scale"])
                 for i, (name, n, has_shift) in enumerate(spec)]
 
-    def _update_prenorm(self, layer: PreNormLayer, dev_inputs):
+    def _prenorm_batch_stats(self, layer: PreNormLayer, dev_inputs):
+        """(mean, population variance, count) of the input of ``layer`` on this batch (model.py:410-413), on the host."""
         batch, _keep = dev_inputs
         self.reserve(batch, False)
         mean = (C.c_double * 64)()
@@ -458,7 +459,10 @@ class GCNN:
         check(self._lib.gcnn_prenorm_stats(self._ws, self.flat_params.data_ptr(), self.flat_prenorm.data_ptr(),
                                            C.byref(batch), layer.index, mean, var, C.byref(count), self._stream()))
         n = layer.n_units
-        layer.update_params(np.array(mean[:n]), np.array(var[:n]), count.value)
+        return np.array(mean[:n]), np.array(var[:n]), count.value
+
+    def _update_prenorm(self, layer: PreNormLayer, dev_inputs):
+        layer.update_params(*self._prenorm_batch_stats(layer, dev_inputs))
 
     def pretrain_init(self):
         for layer in self._prenorm_layers:

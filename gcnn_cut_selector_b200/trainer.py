@@ -22,6 +22,29 @@ def reduce_bucket(bucket: torch.Tensor, group=None) -> torch.Tensor:
     return bucket
 
 
+def gather_prenorm_stats(mean, var, count, group=None):
+    """Every rank's batch statistics of one pre-norm layer, as a list ``[(mean, var, count), ...]`` in rank order (one
+    small all-gather of fp64 triples; gloo on CPU, NCCL through a device copy).  Feeding the list, in order, to
+    ``PreNormLayer.update_params`` (Chan's merge, model.py:416-423) leaves every rank with the statistics a single
+    process would have after seeing the ranks' batches one after the other."""
+    import numpy as np
+    mean, var = np.atleast_1d(np.asarray(mean, np.float64)), np.atleast_1d(np.asarray(var, np.float64))
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return [(mean, var, float(count))]
+    local = torch.from_numpy(np.concatenate([[float(count)], mean, var]))
+    on_gpu = dist.get_backend(group) == "nccl"
+    if on_gpu:
+        local = local.cuda()
+    parts = [torch.empty_like(local) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(parts, local, group=group)
+    n = mean.shape[0]
+    out = []
+    for p in parts:
+        p = p.cpu().numpy()
+        out.append((p[1:1 + n], p[1 + n:1 + 2 * n], float(p[0])))
+    return out
+
+
 class DataParallelTrainer:
     """Owns the all-reduce bucket; ``model.flat_grads`` becomes a view of it so nothing is copied per step."""
 
@@ -41,6 +64,31 @@ class DataParallelTrainer:
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             dist.broadcast(self.model.flat_params.detach(), src, group=self.group)
             dist.broadcast(self.model.flat_prenorm, src, group=self.group)
+
+    def pretrain_fused(self, batches) -> int:
+        """Pre-norm pretraining over sharded data: the 7-pass schedule of ``GCNN.pretrain_fused`` where, for
+        every batch, each rank computes the statistics of ITS batch and all ranks merge all of them in rank order.  Every
+        rank ends with the same shift / scale values -- those a single process gets from the batch sequence
+        (rank 0's first batch, rank 1's first batch, ..., rank 0's second batch, ...).  All ranks must iterate the same
+        number of batches.  Returns the number of passes."""
+        m = self.model
+        m.pretrain_init()
+        layers, passes = m._prenorm_layers, 0
+        for group in [layers[:5]] + [[layer] for layer in layers[5:]]:
+            seen = False
+            for b in batches:
+                dev_inputs = m.prepare_inputs(b)
+                for layer in group:
+                    for stats in gather_prenorm_stats(*m._prenorm_batch_stats(layer, dev_inputs), group=self.group):
+                        layer.update_params(*stats)
+                    layer.received_updates = True
+                seen = True
+            if not seen:
+                break
+            for layer in group:
+                layer.stop_updates()
+            passes += 1
+        return passes
 
     def _finish(self, want_loss: bool):
         reduce_bucket(self.bucket, self.group)

@@ -15,7 +15,7 @@ import torch.multiprocessing as mp
 
 import gcnn_oracle as orc
 from gcnn_cut_selector_b200 import batching, synth
-from gcnn_cut_selector_b200.trainer import reduce_bucket
+from gcnn_cut_selector_b200.trainer import gather_prenorm_stats, reduce_bucket
 
 N = orc.N_TRAINABLE
 
@@ -78,3 +78,44 @@ def test_dp_bucket_reduction_matches_single_process(tmp_path):
 def test_reduce_bucket_is_identity_without_process_group():
     b = torch.arange(5, dtype=torch.float32)
     assert reduce_bucket(b.clone()).equal(b)
+
+
+# ---- pre-norm statistics over sharded data: all-gather of per-rank triples, Chan merge in rank order -------
+def _rank_batches(rank):
+    rng = np.random.default_rng(100 + rank)
+    return [rng.standard_normal((5 + 3 * rank + b, 4)) * (1 + rank) + b for b in range(3)]  # unequal counts per rank
+
+
+def _stats_worker(rank, world, port, out_dir):
+    from gcnn_cut_selector_b200.model import PreNormLayer
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    layer = PreNormLayer(None, 0, "cons_emb/prenorm", 4, None, 0)
+    layer.start_updates()
+    for x in _rank_batches(rank):
+        for stats in gather_prenorm_stats(x.mean(0), x.var(0), x.shape[0]):
+            layer.update_params(*stats)
+    np.save(os.path.join(out_dir, f"stats{rank}.npy"), np.concatenate([layer.mean, layer.var, [layer.count]]))
+    dist.destroy_process_group()
+
+
+def test_dp_prenorm_statistics_equal_the_single_process_merge(tmp_path):
+    from gcnn_cut_selector_b200.model import PreNormLayer
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_stats_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    s0, s1 = (np.load(tmp_path / f"stats{r}.npy") for r in range(2))
+    np.testing.assert_array_equal(s0, s1)  # every rank freezes the same values
+    # a single process that sees rank 0's and rank 1's batches alternately (model.py:416-423, batch by batch)
+    layer = PreNormLayer(None, 0, "cons_emb/prenorm", 4, None, 0)
+    layer.start_updates()
+    for b in range(3):
+        for rank in range(2):
+            x = _rank_batches(rank)[b]
+            layer.update_params(x.mean(0), x.var(0), x.shape[0])
+    np.testing.assert_array_equal(s0, np.concatenate([layer.mean, layer.var, [layer.count]]))
+    # ... which is the statistics of all rows together, up to fp32 rounding of the merges
+    allx = np.concatenate([x for rank in range(2) for x in _rank_batches(rank)])
+    assert np.abs(s0[:4] - allx.mean(0)).max() <= 1e-5 and np.abs(s0[4:8] - allx.var(0)).max() <= 1e-4
+    assert s0[8] == allx.shape[0]

@@ -507,10 +507,13 @@ def test_fused_pretraining_equals_the_eleven_pass_protocol(golden_dir):
     z = np.load(os.path.join(golden_dir, "pretrain_tiny.npz"))
     batches = [golden_inputs(z, f"b{b}_") for b in range(2)]
     out = []
-    for fused in (False, True):
+    for fused in (False, True, "dp"):
         m = GCNN(device="cuda:0", seed=2)
         m.restore_state(os.path.join(golden_dir, "state_stream.pkl"))
-        if fused:
+        if fused == "dp":  # world size 1: the data-parallel schedule degenerates to the fused one
+            from gcnn_cut_selector_b200 import DataParallelTrainer
+            assert DataParallelTrainer(m, 1e-3).pretrain_fused(batches) == 7
+        elif fused:
             assert m.pretrain_fused(batches) == 7
         else:
             m.pretrain_init()
@@ -524,7 +527,7 @@ def test_fused_pretraining_equals_the_eleven_pass_protocol(golden_dir):
                 passes += 1
             assert passes == 11
         out.append(m.flat_prenorm.clone())
-    assert torch.equal(out[0], out[1])
+    assert torch.equal(out[0], out[1]) and torch.equal(out[0], out[2])
 
 
 def test_save_restore_roundtrip(model, golden_dir, tmp_path):
