@@ -7,7 +7,8 @@
 // Reference-produced batches have row 0 (constraint / cut index) non-decreasing (csr -> vstack -> tocoo,
 // utils.py:102-104; block-diagonal offsets utils.py:403-407), so grouping by the left node is a pointer build.
 // That is detected ON THE DEVICE (no host sync): every sort kernel early-exits when the "already sorted" flag
-// is set.  Otherwise a stable LSD radix sort (8-bit digits, match.any ranking) orders (key, edge id) pairs.
+// is set.  Otherwise a stable LSD radix sort (match.any ranking) orders (key, edge id) pairs; the digit width is 8 bits,
+// or 9 when that saves a pass (17- and 18-bit keys: 128 k variables per GPU in BASELINE config 4, the MIPLIB-scale graph).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -17,26 +18,29 @@ namespace gcnn {
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_ITEMS = 4;                          // items per thread per tile
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;   // 1024 pairs per CTA: the scatter is latency-bound per CTA (16 items: 30 us, 4 items: 11 us for 800 k pairs)
-constexpr int RADIX = 256;
+constexpr int MAX_RADIX = 512;   // 9-bit digits
 
-int64_t sort_hist_entries(int64_t E) { return 2 * RADIX * ceil_div(E > 0 ? E : 1, SORT_TILE) + RADIX; }  // two buffers + digit totals
+int64_t sort_hist_entries(int64_t E) { return 2 * MAX_RADIX * ceil_div(E > 0 ? E : 1, SORT_TILE) + MAX_RADIX; }  // two buffers + digit totals
 
 // One pass over the edge list (one CTA per SORT_TILE edges):
 //   * index range check (err_flag bit 0) and sortedness check (unsorted_flag := 1 on a descent);
 //   * unless the caller vouches for sorted input: (clamped key, edge id) pairs for the radix sort, this tile's
 //     histogram of the first digit, and zeroing of the second histogram buffer.
 // A violated "sorted" hint sets err_flag bit 1.
-template <bool HINT_SORTED>
+template <bool HINT_SORTED, int BITS>
 __global__ void __launch_bounds__(SORT_THREADS)
 check_init_hist_kernel(const int32_t* __restrict__ keys, const int32_t* __restrict__ others, int64_t E,
                        int32_t n_owner, int32_t n_other, int32_t* unsorted_flag, int32_t* err_flag, int hint_is_binding,
                        int32_t* __restrict__ key_out, int32_t* __restrict__ val_out, int32_t* __restrict__ hist0,
                        int32_t* __restrict__ hist1, int n_blocks) {
     pdl_enter();
+    constexpr int RADIX = 1 << BITS;
     __shared__ int32_t h[RADIX];
     if (!HINT_SORTED) {
-        h[threadIdx.x] = 0;
-        hist1[(int64_t)blockIdx.x * RADIX + threadIdx.x] = 0;
+        for (int d = threadIdx.x; d < RADIX; d += SORT_THREADS) {
+            h[d] = 0;
+            hist1[(int64_t)blockIdx.x * RADIX + d] = 0;
+        }
         __syncthreads();
     }
     const int64_t base = (int64_t)blockIdx.x * SORT_TILE;
@@ -63,27 +67,29 @@ check_init_hist_kernel(const int32_t* __restrict__ keys, const int32_t* __restri
     if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(err_flag, 1);
     if (!HINT_SORTED) {
         __syncthreads();
-        hist0[threadIdx.x * n_blocks + blockIdx.x] = h[threadIdx.x];  // digit-major: one scan gives global offsets
+        for (int d = threadIdx.x; d < RADIX; d += SORT_THREADS)
+            hist0[(int64_t)d * n_blocks + blockIdx.x] = h[d];  // digit-major: one scan gives global offsets
     }
 }
 
 // Per-digit exclusive scan over the CTAs' counts: CTA d turns hist[d][0 .. n_blocks) into exclusive prefixes in place
-// and writes the digit's total.  256 independent small scans (one memory round trip) instead of one long serial scan;
-// the scatter kernel adds the exclusive scan over the 256 totals itself.
-__global__ void __launch_bounds__(RADIX)
+// and writes the digit's total.  One small scan per digit (one memory round trip) instead of one long serial scan;
+// the scatter kernel adds the exclusive scan over the digit totals itself.  Grid = number of digits.
+constexpr int SCAN_THREADS = 256;
+__global__ void __launch_bounds__(SCAN_THREADS)
 digit_scan_kernel(int32_t* __restrict__ hist, int n_blocks, const int32_t* __restrict__ unsorted_flag,
                   int32_t* __restrict__ totals, int32_t* __restrict__ zero_buf) {
     pdl_enter();
     if (!*unsorted_flag) return;
-    __shared__ int32_t warp_sums[RADIX / 32];
+    __shared__ int32_t warp_sums[SCAN_THREADS / 32];
     __shared__ int32_t carry_s;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     int32_t* row = hist + (int64_t)blockIdx.x * n_blocks;
     if (zero_buf)  // this digit's slice of the histogram buffer the next scatter accumulates into
-        for (int i = t; i < n_blocks; i += RADIX) zero_buf[(int64_t)blockIdx.x * n_blocks + i] = 0;
+        for (int i = t; i < n_blocks; i += SCAN_THREADS) zero_buf[(int64_t)blockIdx.x * n_blocks + i] = 0;
     if (t == 0) carry_s = 0;
     __syncthreads();
-    for (int base = 0; base < n_blocks; base += RADIX) {
+    for (int base = 0; base < n_blocks; base += SCAN_THREADS) {
         const int32_t carry = carry_s;
         const int32_t x = base + t < n_blocks ? row[base + t] : 0;
         int32_t incl = x;
@@ -96,7 +102,7 @@ digit_scan_kernel(int32_t* __restrict__ hist, int n_blocks, const int32_t* __res
         __syncthreads();
         int32_t before = 0, total = 0;
 #pragma unroll
-        for (int w = 0; w < RADIX / 32; ++w) {
+        for (int w = 0; w < SCAN_THREADS / 32; ++w) {
             const int32_t c = warp_sums[w];
             if (w < warp) before += c;
             total += c;
@@ -112,6 +118,7 @@ digit_scan_kernel(int32_t* __restrict__ hist, int n_blocks, const int32_t* __res
 // Stable scatter: rank of an item among equal digits = (# in earlier CTAs) + (# in earlier rounds of this CTA)
 // + (# in earlier warps of this round) + (# in lower lanes of this warp), all in original order.  While scattering it
 // also builds the NEXT pass's per-tile digit histogram (integer atomics: order-independent result).
+template <int BITS>
 __global__ void __launch_bounds__(SORT_THREADS)
 radix_scatter_kernel(const int32_t* __restrict__ key_in, const int32_t* __restrict__ val_in, int64_t E, int shift,
                      const int32_t* __restrict__ unsorted_flag, const int32_t* __restrict__ offsets,
@@ -119,12 +126,17 @@ radix_scatter_kernel(const int32_t* __restrict__ key_in, const int32_t* __restri
     pdl_enter();
     if (!*unsorted_flag) return;
     constexpr int WARPS = SORT_THREADS / 32;
+    constexpr int RADIX = 1 << BITS;
+    constexpr int DPT = RADIX / SORT_THREADS;   // digits per thread
     __shared__ int32_t running[RADIX];          // global offset of the next item of each digit for this CTA
     __shared__ int32_t warp_cnt[WARPS][RADIX];  // per-round per-warp digit counts -> exclusive offsets
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    {   // first slot of digit t for this CTA = (items of smaller digits) + (items of digit t in earlier CTAs)
-        const int32_t tot = totals[t];
-        int32_t incl = tot;
+    {   // first slot of digit d for this CTA = (items of smaller digits) + (items of digit d in earlier CTAs); thread t
+        // scans the DPT consecutive digits t DPT .. t DPT + DPT - 1
+        int32_t tot[DPT], sum = 0;
+#pragma unroll
+        for (int j = 0; j < DPT; ++j) { tot[j] = totals[t * DPT + j]; sum += tot[j]; }
+        int32_t incl = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int32_t u = __shfl_up_sync(0xffffffffu, incl, o);
@@ -132,14 +144,21 @@ radix_scatter_kernel(const int32_t* __restrict__ key_in, const int32_t* __restri
         }
         if (lane == 31) warp_cnt[0][warp] = incl;
         __syncthreads();
-        int32_t before = 0;
-        for (int w = 0; w < warp; ++w) before += warp_cnt[0][w];
-        running[t] = before + incl - tot + offsets[t * n_blocks + blockIdx.x];
+        int32_t excl = incl - sum;
+        for (int w = 0; w < warp; ++w) excl += warp_cnt[0][w];
+        __syncthreads();  // warp_cnt[0] is rewritten below
+#pragma unroll
+        for (int j = 0; j < DPT; ++j) {
+            running[t * DPT + j] = excl + offsets[(int64_t)(t * DPT + j) * n_blocks + blockIdx.x];
+            excl += tot[j];
+        }
         __syncthreads();
     }
     const int64_t base = (int64_t)blockIdx.x * SORT_TILE;
     for (int i = 0; i < SORT_ITEMS; ++i) {
-        for (int w = 0; w < WARPS; ++w) warp_cnt[w][t] = 0;
+        for (int w = 0; w < WARPS; ++w)
+#pragma unroll
+            for (int j = 0; j < DPT; ++j) warp_cnt[w][t + j * SORT_THREADS] = 0;
         __syncthreads();
         const int64_t e = base + i * SORT_THREADS + t;
         const bool valid = e < E;
@@ -153,22 +172,27 @@ radix_scatter_kernel(const int32_t* __restrict__ key_in, const int32_t* __restri
         const int rank_in_warp = __popc(peers & ((1u << lane) - 1u));
         if (valid && rank_in_warp == 0) warp_cnt[warp][digit] = __popc(peers);
         __syncthreads();
-        int32_t acc = 0;  // thread t owns digit t: exclusive prefix over warps
+        int32_t acc[DPT];  // thread t owns digits t, t + 256, ...: exclusive prefix over warps
 #pragma unroll
-        for (int w = 0; w < WARPS; ++w) {
-            const int32_t c = warp_cnt[w][t];
-            warp_cnt[w][t] = acc;
-            acc += c;
+        for (int j = 0; j < DPT; ++j) {
+            acc[j] = 0;
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) {
+                const int32_t c = warp_cnt[w][t + j * SORT_THREADS];
+                warp_cnt[w][t + j * SORT_THREADS] = acc[j];
+                acc[j] += c;
+            }
         }
         __syncthreads();
         if (valid) {
             const int32_t pos = running[digit] + warp_cnt[warp][digit] + rank_in_warp;
             key_out[pos] = k;
             val_out[pos] = v;
-            if (hist_next) atomicAdd(&hist_next[((k >> (shift + 8)) & (RADIX - 1)) * n_blocks + pos / SORT_TILE], 1);
+            if (hist_next) atomicAdd(&hist_next[(int64_t)((k >> (shift + BITS)) & (RADIX - 1)) * n_blocks + pos / SORT_TILE], 1);
         }
         __syncthreads();
-        running[t] += acc;
+#pragma unroll
+        for (int j = 0; j < DPT; ++j) running[t + j * SORT_THREADS] += acc[j];
         __syncthreads();
     }
 }
@@ -237,6 +261,9 @@ int build_layout(const int32_t* keys, const int32_t* others, const float* feats,
         return GCNN_OK;
     }
     const int n_blocks = (int)ceil_div(E, SORT_TILE);
+    // digit width: 9 bits when that saves a pass (keys of 17-18 and 25-27 bits), else 8
+    const int key_bits = bit_length(n_owner - 1);
+    const int BITS = (key_bits + 8) / 9 < (key_bits + 7) / 8 ? 9 : 8, RADIX = 1 << BITS;
     const int64_t hist_n = (int64_t)RADIX * n_blocks;
     int32_t *hist0 = sc.hist, *hist1 = sc.hist + hist_n, *totals = sc.hist + 2 * hist_n;
     // E <= 1 or a single owner: nothing to order (keys are clamped into [0, n_owner) downstream)
@@ -245,15 +272,20 @@ int build_layout(const int32_t* keys, const int32_t* others, const float* feats,
     const int32_t* zero_flag = sc.flags + 6;   // never written: reads as "sorted"
     if (hint_sorted || trivially_sorted) {
         ProfScope prof(PROF_CSR_CHECK, 8.0 * (double)E, st);
-        GCNN_LAUNCH_ORDERED(check_init_hist_kernel<true>, n_blocks, SORT_THREADS, 0, st, 
+        GCNN_LAUNCH_ORDERED((check_init_hist_kernel<true, 8>), n_blocks, SORT_THREADS, 0, st, 
             keys, others, E, (int32_t)n_owner, (int32_t)n_other, trivially_sorted ? scratch_flag : unsorted_flag,
             err_flag, trivially_sorted ? 0 : 1, nullptr, nullptr, nullptr, nullptr, n_blocks);
         GCNN_LAUNCH_CHECK();
     } else {
         ProfScope prof(PROF_CSR_CHECK, 16.0 * (double)E + 4.0 * (double)hist_n, st);
-        GCNN_LAUNCH_ORDERED(check_init_hist_kernel<false>, n_blocks, SORT_THREADS, 0, st, 
-            keys, others, E, (int32_t)n_owner, (int32_t)n_other, unsorted_flag, err_flag, 0, sc.key_a, sc.val_a, hist0,
-            hist1, n_blocks);
+        if (BITS == 9)
+            GCNN_LAUNCH_ORDERED((check_init_hist_kernel<false, 9>), n_blocks, SORT_THREADS, 0, st,
+                keys, others, E, (int32_t)n_owner, (int32_t)n_other, unsorted_flag, err_flag, 0, sc.key_a, sc.val_a, hist0,
+                hist1, n_blocks);
+        else
+            GCNN_LAUNCH_ORDERED((check_init_hist_kernel<false, 8>), n_blocks, SORT_THREADS, 0, st,
+                keys, others, E, (int32_t)n_owner, (int32_t)n_other, unsorted_flag, err_flag, 0, sc.key_a, sc.val_a, hist0,
+                hist1, n_blocks);
         GCNN_LAUNCH_CHECK();
     }
     const int32_t* sorted_keys = sc.key_a;
@@ -261,19 +293,23 @@ int build_layout(const int32_t* keys, const int32_t* others, const float* feats,
     if (!hint_sorted && !trivially_sorted) {
         int32_t *ka = sc.key_a, *va = sc.val_a, *kb = sc.key_b, *vb = sc.val_b;
         int32_t *hcur = hist0, *hnext = hist1;
-        const int bits = bit_length(n_owner - 1);
-        for (int shift = 0, pass = 0; shift < bits; shift += 8, ++pass) {
-            const bool more = shift + 8 < bits;
+        const int bits = key_bits;
+        for (int shift = 0, pass = 0; shift < bits; shift += BITS, ++pass) {
+            const bool more = shift + BITS < bits;
             // pass 0 finds hist1 zeroed by the first kernel; later passes zero their "next" buffer in the scan
             {
                 ProfScope prof(PROF_CSR_SCAN, 8.0 * (double)hist_n, st);
-                GCNN_LAUNCH_ORDERED(digit_scan_kernel, RADIX, RADIX, 0, st, hcur, n_blocks, unsorted_flag, totals,
+                GCNN_LAUNCH_ORDERED(digit_scan_kernel, RADIX, SCAN_THREADS, 0, st, hcur, n_blocks, unsorted_flag, totals,
                             (more && pass > 0) ? hnext : nullptr);
                 GCNN_LAUNCH_CHECK();
             }
             ProfScope prof(PROF_CSR_SCATTER, 16.0 * (double)E + 4.0 * (double)hist_n, st);
-            GCNN_LAUNCH_ORDERED(radix_scatter_kernel, n_blocks, SORT_THREADS, 0, st, ka, va, E, shift, unsorted_flag, hcur, totals,
-                        n_blocks, kb, vb, more ? hnext : nullptr);
+            if (BITS == 9)
+                GCNN_LAUNCH_ORDERED(radix_scatter_kernel<9>, n_blocks, SORT_THREADS, 0, st, ka, va, E, shift, unsorted_flag, hcur,
+                                    totals, n_blocks, kb, vb, more ? hnext : nullptr);
+            else
+                GCNN_LAUNCH_ORDERED(radix_scatter_kernel<8>, n_blocks, SORT_THREADS, 0, st, ka, va, E, shift, unsorted_flag, hcur,
+                                    totals, n_blocks, kb, vb, more ? hnext : nullptr);
             GCNN_LAUNCH_CHECK();
             int32_t* t;
             t = ka; ka = kb; kb = t;
