@@ -124,7 +124,7 @@ struct gcnn_workspace {
     // auxiliary streams: independent kernels (CSR build, the two projections of a convolution, weight gradients) run
     // concurrently with the main chain; fork/join with events, nothing synchronises the host
     int use_streams = 1;
-    cudaStream_t aux[2] = {nullptr, nullptr};
+    cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev[16] = {};
     int ev_next = 0;
     cudaEvent_t ev_layout[4] = {};  // cons by-left, cons by-var, cut by-left, cut by-var are ready
@@ -430,18 +430,27 @@ static int forward_impl(gcnn_workspace* ws, const float* p, const float* pn, con
     GCNN_CUDA_TRY(cudaMemsetAsync(ws->flags + 2, 0, 12 * sizeof(int32_t), s1));  // per-layout "unsorted" [2..5] and "long rows" [10..13] words
     const bool cons_sorted = (b->flags & GCNN_BATCH_CONS_EDGES_SORTED) != 0;
     const bool cuts_sorted = (b->flags & GCNN_BATCH_CUT_EDGES_SORTED) != 0;
+    // Layouts grouped by the left node of lists the caller vouches are sorted (reference batches) are a check + a pointer
+    // build that touch no sort scratch: they run on a third stream, next to the radix sorts of the by-variable layouts
+    // (the by-variable layout of the constraint edges is what convolution 1 waits for).
+    static const bool third_stream = [] { const char* e = getenv("GCNN_LAYOUT_STREAM"); return !e || atoi(e) != 0; }();
+    cudaStream_t s3 = third_stream ? aux_stream(ws, 2, st) : s1;
+    cudaStream_t sl_cons = (cons_sorted && s3 != s1) ? s3 : s1, sl_cuts = (cuts_sorted && s3 != s1) ? s3 : s1;
+    const bool use_s3 = sl_cons != s1 || sl_cuts != s1;
+    if (use_s3) GCNN_TRY(stream_edge(ws, s1, s3));  // after the flag words were cleared
     GCNN_TRY(build_layout(b->cons_edge_inds, b->cons_edge_inds + ec, b->cons_edge_feats, ec, nc, nv, ws->sort,
-                          ws->flags + 1, ws->flags + 2, cons_sorted, ws->graph[0].by_left, s1));
-    if (s1 != st) GCNN_CUDA_TRY(cudaEventRecord(ws->ev_layout[0], s1));
+                          ws->flags + 1, ws->flags + 2, cons_sorted, ws->graph[0].by_left, sl_cons));
+    if (s1 != st) GCNN_CUDA_TRY(cudaEventRecord(ws->ev_layout[0], sl_cons));
     GCNN_TRY(build_layout(b->cons_edge_inds + ec, b->cons_edge_inds, b->cons_edge_feats, ec, nv, nc, ws->sort,
                           ws->flags + 1, ws->flags + 3, false, ws->graph[0].by_var, s1));
     if (s1 != st) GCNN_CUDA_TRY(cudaEventRecord(ws->ev_layout[1], s1));
     GCNN_TRY(build_layout(b->cut_edge_inds, b->cut_edge_inds + ek, b->cut_edge_feats, ek, nk, nv, ws->sort,
-                          ws->flags + 1, ws->flags + 4, cuts_sorted, ws->graph[1].by_left, s1));
-    if (s1 != st) GCNN_CUDA_TRY(cudaEventRecord(ws->ev_layout[2], s1));
+                          ws->flags + 1, ws->flags + 4, cuts_sorted, ws->graph[1].by_left, sl_cuts));
+    if (s1 != st) GCNN_CUDA_TRY(cudaEventRecord(ws->ev_layout[2], sl_cuts));
     if (ws->cap.training)
         GCNN_TRY(build_layout(b->cut_edge_inds + ek, b->cut_edge_inds, b->cut_edge_feats, ek, nv, nk, ws->sort,
                               ws->flags + 1, ws->flags + 5, false, ws->graph[1].by_var, s1));
+    if (use_s3) GCNN_TRY(stream_edge(ws, s3, s1));  // ev_layout[3] (recorded on s1 below) covers the third stream too
 
     if (ws->use_tc)
         GCNN_TRY(pack_weights(p, ws->tc_block_offsets, (int)tc_blocks().size(), ws->tc_images, st));
@@ -957,7 +966,7 @@ int gcnn_workspace_create(gcnn_workspace** out) {
     ws->use_edge_masks = !(em && em[0] == '0');
     const char* fb = getenv("GCNN_FUSED_BWD");  // GCNN_FUSED_BWD=0: stand-alone dgrad / wgrad launches in the backward
     ws->use_fused_bwd = !(fb && fb[0] == '0');
-    for (int i = 0; i < 2; ++i) GCNN_CUDA_TRY(cudaStreamCreateWithFlags(&ws->aux[i], cudaStreamNonBlocking));
+    for (int i = 0; i < 3; ++i) GCNN_CUDA_TRY(cudaStreamCreateWithFlags(&ws->aux[i], cudaStreamNonBlocking));
     for (int i = 0; i < 16; ++i) GCNN_CUDA_TRY(cudaEventCreateWithFlags(&ws->ev[i], cudaEventDisableTiming));
     for (int i = 0; i < 4; ++i) GCNN_CUDA_TRY(cudaEventCreateWithFlags(&ws->ev_layout[i], cudaEventDisableTiming));
     GCNN_CUDA_TRY(cudaStreamCreateWithFlags(&ws->copy_st, cudaStreamNonBlocking));
@@ -976,7 +985,7 @@ int gcnn_workspace_create(gcnn_workspace** out) {
 int gcnn_workspace_destroy(gcnn_workspace* ws) {
     if (!ws) return GCNN_OK;
     if (ws->arena) cudaFree(ws->arena);
-    for (int i = 0; i < 2; ++i) if (ws->aux[i]) cudaStreamDestroy(ws->aux[i]);
+    for (int i = 0; i < 3; ++i) if (ws->aux[i]) cudaStreamDestroy(ws->aux[i]);
     for (int i = 0; i < 16; ++i) if (ws->ev[i]) cudaEventDestroy(ws->ev[i]);
     for (int i = 0; i < 4; ++i) if (ws->ev_layout[i]) cudaEventDestroy(ws->ev_layout[i]);
     if (ws->copy_st) cudaStreamDestroy(ws->copy_st);
