@@ -140,6 +140,17 @@ def test_csr_build_bit_exact(model, case):
     _csr_case(model, np.asarray(ei), np.asarray(ef), nl, nv)
 
 
+@pytest.mark.parametrize("n_owner", [2, 255, 256, 257, 511, 512, 513, 65_535, 65_536, 65_537, 131_072, 262_144, 262_145])
+def test_csr_digit_width_boundaries(model, n_owner):
+    """Key widths around the points where the radix sort changes its pass count or digit width (8-bit digits; 9-bit ones
+    for 9-, 17- and 18-bit keys), unsorted on both sides, keys hitting 0 and n_owner - 1, several tiles per pass."""
+    rng = np.random.default_rng(n_owner)
+    E = 20_011
+    rows, cols = rng.integers(0, n_owner, E), rng.integers(0, n_owner + 3, E)
+    rows[:4], cols[:4] = [0, n_owner - 1, 0, n_owner - 1], [n_owner + 2, 0, 0, n_owner + 2]
+    _csr_case(model, np.vstack([rows, cols]), rng.standard_normal(E), n_owner, n_owner + 3)
+
+
 def test_out_of_range_index_raises(model, golden_dir):
     from gcnn_cut_selector_b200 import InvalidArgumentError
     z = np.load(os.path.join(golden_dir, "fwd_tiny3.npz"))
