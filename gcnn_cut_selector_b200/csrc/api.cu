@@ -121,6 +121,7 @@ struct gcnn_workspace {
     } stage[2];
     float* h_result = nullptr;    // pinned host: per slot {loss sum, error flag word}
     cudaStream_t copy_st = nullptr;
+    cudaStream_t result_st = nullptr;  // device-to-host copies of a step's loss / error word, off the compute stream
     // auxiliary streams: independent kernels (CSR build, the two projections of a convolution, weight gradients) run
     // concurrently with the main chain; fork/join with events, nothing synchronises the host
     int use_streams = 1;
@@ -970,6 +971,7 @@ int gcnn_workspace_create(gcnn_workspace** out) {
     for (int i = 0; i < 16; ++i) GCNN_CUDA_TRY(cudaEventCreateWithFlags(&ws->ev[i], cudaEventDisableTiming));
     for (int i = 0; i < 4; ++i) GCNN_CUDA_TRY(cudaEventCreateWithFlags(&ws->ev_layout[i], cudaEventDisableTiming));
     GCNN_CUDA_TRY(cudaStreamCreateWithFlags(&ws->copy_st, cudaStreamNonBlocking));
+    GCNN_CUDA_TRY(cudaStreamCreateWithFlags(&ws->result_st, cudaStreamNonBlocking));
     for (int s = 0; s < 2; ++s) {
         GCNN_CUDA_TRY(cudaEventCreateWithFlags(&ws->stage[s].staged, cudaEventDisableTiming));
         GCNN_CUDA_TRY(cudaEventCreateWithFlags(&ws->stage[s].consumed, cudaEventDisableTiming));
@@ -989,6 +991,7 @@ int gcnn_workspace_destroy(gcnn_workspace* ws) {
     for (int i = 0; i < 16; ++i) if (ws->ev[i]) cudaEventDestroy(ws->ev[i]);
     for (int i = 0; i < 4; ++i) if (ws->ev_layout[i]) cudaEventDestroy(ws->ev_layout[i]);
     if (ws->copy_st) cudaStreamDestroy(ws->copy_st);
+    if (ws->result_st) cudaStreamDestroy(ws->result_st);
     for (int s = 0; s < 2; ++s) {
         if (ws->stage[s].staged) cudaEventDestroy(ws->stage[s].staged);
         if (ws->stage[s].consumed) cudaEventDestroy(ws->stage[s].consumed);
@@ -1311,14 +1314,22 @@ int gcnn_train_step_staged_async(gcnn_workspace* ws, int slot, float* params, co
     float* grads = ws->partials[31];
     const int64_t nk = g.meta.n_cuts;
     const float scale = nk > 0 ? 1.f / (float)nk : 0.f;
-    GCNN_TRY(gcnn_forward_backward(ws, params, prenorm, &g.meta, g.targets, scale, nullptr, grads, ws->loss_sum, st));
-    GCNN_CUDA_TRY(cudaEventRecord(g.consumed, st));
+    // each slot has its own loss word: the copy below runs on another stream and may still be pending when the next
+    // step's loss kernel writes
+    float* loss_dev = ws->loss_sum + 8 + 8 * slot;
+    GCNN_TRY(gcnn_forward_backward(ws, params, prenorm, &g.meta, g.targets, scale, nullptr, grads, loss_dev, st));
     GCNN_TRY(gcnn_adam_step(params, grads, adam_m, adam_v, GCNN_N_TRAINABLE, lr, 0.9f, 0.999f, 1e-7f, step, nullptr,
                             st));
-    // loss sum and the sticky error word travel to pinned host memory; gcnn_train_step_result waits for them
-    GCNN_CUDA_TRY(cudaMemcpyAsync(ws->h_result + 2 * slot, ws->loss_sum, sizeof(float), cudaMemcpyDeviceToHost, st));
-    GCNN_CUDA_TRY(cudaMemcpyAsync(ws->h_result + 2 * slot + 1, ws->flags + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    GCNN_CUDA_TRY(cudaEventRecord(g.result, st));
+    // One event after the optimiser update marks both "slot consumed" (recorded after Adam rather than before it: an
+    // event between two kernels costs the second one its programmatic early launch, and the next batch's copies have
+    // slack) and "results ready".  Loss sum and the sticky error word travel to pinned host memory on a side stream, so
+    // the two small copies do not sit between this step's last kernel and the next step's first one;
+    // gcnn_train_step_result waits for them.
+    GCNN_CUDA_TRY(cudaEventRecord(g.consumed, st));
+    GCNN_CUDA_TRY(cudaStreamWaitEvent(ws->result_st, g.consumed, 0));
+    GCNN_CUDA_TRY(cudaMemcpyAsync(ws->h_result + 2 * slot, loss_dev, sizeof(float), cudaMemcpyDeviceToHost, ws->result_st));
+    GCNN_CUDA_TRY(cudaMemcpyAsync(ws->h_result + 2 * slot + 1, ws->flags + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, ws->result_st));
+    GCNN_CUDA_TRY(cudaEventRecord(g.result, ws->result_st));
     g.result_cuts = nk;
     return GCNN_OK;
 }
