@@ -94,6 +94,47 @@ def test_shard_file_and_conversion_from_reference_sample_files(golden_dir, tmp_p
     assert np.all(np.diff(ptrs.astype(np.int64)) == np.diff(reader.offsets)[:-1])  # neighbours in memory
 
 
+def _random_sample(rng, n_cons, n_vars, n_cuts, ec, ek, sort_rows):
+    def edges(n_left, e):
+        ei = np.vstack([rng.integers(0, max(n_left, 1), e), rng.integers(0, max(n_vars, 1), e)]).astype(np.int64)
+        if sort_rows:
+            ei = ei[:, np.argsort(ei[0], kind="stable")]
+        return {"indices": ei, "values": rng.standard_normal((e, 1))}
+    ec = ec if n_cons and n_vars else 0
+    ek = ek if n_cuts and n_vars else 0
+    return ({"values": rng.standard_normal((n_cons, 4))}, edges(n_cons, ec), {"values": rng.standard_normal((n_vars, 14))},
+            {"values": rng.standard_normal((n_cuts, 6))}, edges(n_cuts, ek)), rng.uniform(0, 0.1, n_cuts)
+
+
+def test_records_round_trip_property():
+    """Random ragged samples (empty node sets, empty edge lists, sorted and unsorted rows, rows stored as indices or as a
+    pointer): pack -> unpack is the identity on load_batch's element types, and batches of unpacked records equal the
+    oracle's restatement of utils.py:395-423 on the original samples."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(0, 2 ** 32 - 1), st.lists(st.tuples(st.integers(0, 9), st.integers(0, 12), st.integers(0, 5),
+                                                         st.integers(0, 40), st.integers(0, 25), st.booleans(),
+                                                         st.booleans()), min_size=1, max_size=4))
+    def check(seed, specs):
+        rng = np.random.default_rng(seed)
+        samples, unpacked = [], []
+        for n_cons, n_vars, n_cuts, ec, ek, sort_rows, compress in specs:
+            sample = _random_sample(rng, n_cons, n_vars, n_cuts, ec, ek, sort_rows)
+            rec = shards.pack_sample(*sample, compress_rows=compress)
+            flags, nc, nv, nk, e1, e2, total = shards.record_counts(rec)
+            assert (nc, nv, nk) == (n_cons, n_vars, n_cuts) and total == len(rec)
+            if flags & shards.CONS_ROWS_AS_PTR:
+                assert compress and flags & shards.CONS_ROWS_SORTED
+            samples.append(sample)
+            unpacked.append(shards.unpack_record(rec))
+        want, got = orc.concat_samples(samples), batching.concat_samples(unpacked)
+        for w, g in zip(want, got):
+            np.testing.assert_array_equal(np.asarray(w), g)
+
+    check()
+
+
 # ---- GPU: assembly on the device --------------------------------------------------------------------------------------
 def _staged_tensors(model, slot):
     from gcnn_cut_selector_b200.model import Batch
