@@ -56,9 +56,11 @@ SIGNATURES = {
     "gcnn_set_option": (_I, [_P, C.c_char_p, _I]),
     "gcnn_check": (_I, [_P, _P]),
     "gcnn_build_csr": (_I, [_P, _I, _P, _P, _I64, _I64, _I64, _I, _P]),
+    "gcnn_build_csr_blocks": (_I, [_P, _I, _P, _P, _I64, _I64, _I64, _P, _P, _I64, _P]),
     "gcnn_csr_export": (_I, [_P, _I, _I, _P, _P, _P, _P, _P]),
     "gcnn_forward": (_I, [_P, _P, _P, _BP, _P, _I, _P]),
     "gcnn_backward": (_I, [_P, _P, _P, _BP, _P, _P, _P]),
+    "gcnn_activation_stamp": (_I64, [_P]),
     "gcnn_mse_seed": (_I, [_P, _P, _I64, _F, _P, _P, _P]),
     "gcnn_adam_step": (_I, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I64, _P, _P]),
     "gcnn_ranking_deviation": (_I, [_P, _P, _P, _I64, _I, _P, _P]),

@@ -73,6 +73,14 @@ struct ConvActs { float *A, *B, *H, *cnt, *C, *U1, *Y; };
 
 struct GraphLayouts { EdgeLayout by_left, by_var; };
 
+// Block-diagonal structure of a batch: node offsets of its samples per node type (0 constraints, 1 variables, 2 cuts),
+// device arrays of n + 1 int32 each; max_nodes = the largest sample per type (sizes the shared-memory tables).
+struct BlockInfo {
+    const int32_t* off[3] = {nullptr, nullptr, nullptr};
+    int64_t n = 0;
+    int64_t max_nodes[3] = {0, 0, 0};
+};
+
 }  // namespace gcnn
 
 using namespace gcnn;
@@ -108,17 +116,34 @@ struct gcnn_workspace {
     // host staging mirrors (device side), two slots: batch i + 1 is copied in on the library's copy stream while the
     // step on batch i runs (the reference's loader prefetches one batch the same way, model_trainer.py:153)
     struct Stage {
-        float *cons, *cef, *var, *cut, *kef, *targets;
-        int32_t *cei, *kei;
+        float *cons = nullptr, *cef = nullptr, *var = nullptr, *cut = nullptr, *kef = nullptr, *targets = nullptr;
+        int32_t *cei = nullptr, *kei = nullptr;
         uint8_t* raw = nullptr;          // packed records as copied from the host (gcnn_stage_records)
         int64_t raw_cap = 0;
         RecordDesc* descs = nullptr;     // [MAX_RECORDS] device
         RecordDesc* descs_host = nullptr;  // [MAX_RECORDS] pinned host
+        int32_t* blocks = nullptr;       // [3][MAX_RECORDS + 1] device: node offsets of the batch's samples
+        int32_t* blocks_host = nullptr;  // the same, pinned host (source of the copy)
+        BlockInfo blk;                   // block structure of the staged batch (device pointers into `blocks`), n = 0: none
         gcnn_batch meta{};        // the staged batch with DEVICE pointers into this slot
         cudaEvent_t staged = nullptr, consumed = nullptr, result = nullptr;
         int valid = 0;
         int64_t result_cuts = -1;  // cut count of the step whose result is pending (-1: none)
     } stage[2];
+    char* stage_arena = nullptr;   // the staging slots' own allocation (never freed while a slot is valid)
+    size_t stage_bytes = 0;
+    Caps stage_cap;
+    // block-diagonal structure of the batch being processed (see edge_block.cu): offsets uploaded from the caller's
+    // per-sample count vectors through a small ring of pinned buffers, or pointing into a staging slot
+    int use_blocks = 1;
+    BlockInfo cur_blk;
+    int32_t* blk_dev = nullptr;                // [3][MAX_RECORDS + 1] in the arena
+    int32_t* blk_pin[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t blk_ev[4] = {};
+    int blk_next = 0;
+    int conv_blocked[3] = {0, 0, 0};           // the forward of convolution i ran on the block kernels
+    int device = 0;                            // CUDA device the workspace lives on
+    int64_t act_stamp = 0;                     // generation of the saved activations (gcnn_activation_stamp)
     float* h_result = nullptr;    // pinned host: per slot {loss sum, error flag word}
     cudaStream_t copy_st = nullptr;
     cudaStream_t result_st = nullptr;  // device-to-host copies of a step's loss / error word, off the compute stream
@@ -130,11 +155,6 @@ struct gcnn_workspace {
     int ev_next = 0;
     cudaEvent_t ev_layout[4] = {};  // cons by-left, cons by-var, cut by-left, cut by-var are ready
     float* t_dh1b = nullptr;
-    // shared-memory tile variant of the forward edge kernel (needs the per-sample node counts).  Off by default: on
-    // B200 the generic kernel is bound by instruction issue, not by the L2 gathers, and measures faster (profiles/).
-    int use_tiles = 0;
-    EdgeTile* d_tiles[3] = {nullptr, nullptr, nullptr};
-    int64_t tile_cap = 0;
     // tensor-core path: packed 3xTF32 weight images, one per 64 x 64 weight block
     int use_tc = 1;
     int use_fused = 1;  // one tcgen05 chain kernel per convolution instead of four dense launches
@@ -146,6 +166,16 @@ struct gcnn_workspace {
 };
 
 namespace gcnn {
+
+// Every entry point that takes a workspace runs on the workspace's device, whatever the caller's current device is.
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev); else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 struct Carver {
     char* base;
@@ -224,8 +254,47 @@ static size_t carve(gcnn_workspace* ws, char* base, const Caps& c) {
     ws->st_out = cv.take<double>(2 * D);
     ws->st_center = cv.take<double>(D);
 
+    ws->blk_dev = cv.take<int32_t>(3 * (MAX_RECORDS + 1));
+    ws->tc_images = cv.take<float>((int64_t)tc_blocks().size() * TC_IMG_FLOATS);
+    ws->tc_block_offsets = cv.take<int>(64);
+
+    if (c.training) {
+        ws->dk1 = rows(nk); ws->dv1 = rows(nv); ws->dc1 = rows(nc);
+        ws->dk0 = rows(nk); ws->dv0 = rows(nv); ws->dc0 = rows(nc);
+        ws->t_dU1 = rows(nmax); ws->t_dC = rows(nmax); ws->t_G = rows(nmax); ws->t_dR = rows(nmax);
+        ws->t_dS = rows(nmax); ws->t_dh1 = rows(nmax); ws->t_dh1b = rows(nmax); ws->t_dg = rows(nk);
+        const int64_t parts = wgrad_max_parts();
+        for (int i = 0; i < 32; ++i) ws->partials[i] = cv.take<float>(parts * (2 * D * D + D));
+        const int64_t dw_parts = edge_backward_max_partials() > edge_block_backward_max_partials()
+                                     ? edge_backward_max_partials() : edge_block_backward_max_partials();
+        for (int i = 0; i < 3; ++i) ws->dw_partials[i] = cv.take<float>(dw_parts * D);
+        const int64_t n_send[3] = {nv, nc, nv};
+        for (int i = 0; i < 3; ++i) {
+            ws->bG[i] = rows(n_recv[i]); ws->bdR[i] = rows(n_recv[i]); ws->bdS[i] = rows(n_send[i]);
+            ws->chain_partials[i] = cv.take<float>((int64_t)NUM_SMS * conv_backward_part_floats());
+            ws->emb_partials[i] = cv.take<float>((int64_t)NUM_SMS * embed_backward_part_floats());
+            ws->edge_masks[i] = cv.take<uint2>(i == 2 ? ek : ec);
+        }
+    }
+    return cv.off + 256;
+}
+
+// The two host-staging slots live in their OWN allocation: growing the main arena (a larger batch i + 1 reserved while
+// batch i is still staged, as the prefetch loop of INTEGRATION.md does with ragged batches) must not drop a batch that is
+// staged but not yet consumed.  When the staging area itself has to grow, valid slots are copied across.
+struct StagePtrs {
+    float *cons, *cef, *var, *cut, *kef, *targets;
+    int32_t *cei, *kei;
+    uint8_t* raw;
+    int64_t raw_cap;
+    RecordDesc* descs;
+    int32_t* blocks;  // [3][MAX_RECORDS + 1] node offsets of the batch's samples (constraints, variables, cuts)
+};
+static size_t carve_stage(StagePtrs out[2], char* base, const Caps& c) {
+    Carver cv{base};
+    const int64_t nc = c.nc, nv = c.nv, nk = c.nk, ec = c.ec, ek = c.ek;
     for (int s = 0; s < 2; ++s) {
-        gcnn_workspace::Stage& g = ws->stage[s];
+        StagePtrs& g = out[s];
         g.cons = cv.take<float>(nc * GCNN_CONS_FEATS);
         g.cei = cv.take<int32_t>(2 * ec);
         g.cef = cv.take<float>(ec);
@@ -238,29 +307,7 @@ static size_t carve(gcnn_workspace* ws, char* base, const Caps& c) {
                     MAX_RECORDS * (GCNN_RECORD_HEADER_BYTES + 16 * REC_SECTIONS + 8);
         g.raw = cv.take<uint8_t>(g.raw_cap);
         g.descs = cv.take<RecordDesc>(MAX_RECORDS);
-        g.valid = 0;
-    }
-
-    ws->tile_cap = (nc + nv + nk) / 16 + 8192;
-    for (int i = 0; i < 3; ++i) ws->d_tiles[i] = cv.take<EdgeTile>(ws->tile_cap);
-    ws->tc_images = cv.take<float>((int64_t)tc_blocks().size() * TC_IMG_FLOATS);
-    ws->tc_block_offsets = cv.take<int>(64);
-
-    if (c.training) {
-        ws->dk1 = rows(nk); ws->dv1 = rows(nv); ws->dc1 = rows(nc);
-        ws->dk0 = rows(nk); ws->dv0 = rows(nv); ws->dc0 = rows(nc);
-        ws->t_dU1 = rows(nmax); ws->t_dC = rows(nmax); ws->t_G = rows(nmax); ws->t_dR = rows(nmax);
-        ws->t_dS = rows(nmax); ws->t_dh1 = rows(nmax); ws->t_dh1b = rows(nmax); ws->t_dg = rows(nk);
-        const int64_t parts = wgrad_max_parts();
-        for (int i = 0; i < 32; ++i) ws->partials[i] = cv.take<float>(parts * (2 * D * D + D));
-        for (int i = 0; i < 3; ++i) ws->dw_partials[i] = cv.take<float>((int64_t)edge_backward_max_partials() * D);
-        const int64_t n_send[3] = {nv, nc, nv};
-        for (int i = 0; i < 3; ++i) {
-            ws->bG[i] = rows(n_recv[i]); ws->bdR[i] = rows(n_recv[i]); ws->bdS[i] = rows(n_send[i]);
-            ws->chain_partials[i] = cv.take<float>((int64_t)NUM_SMS * conv_backward_part_floats());
-            ws->emb_partials[i] = cv.take<float>((int64_t)NUM_SMS * embed_backward_part_floats());
-            ws->edge_masks[i] = cv.take<uint2>(i == 2 ? ek : ec);
-        }
+        g.blocks = cv.take<int32_t>(3 * (MAX_RECORDS + 1));
     }
     return cv.off + 256;
 }
@@ -294,32 +341,59 @@ static int stream_edge(gcnn_workspace* ws, cudaStream_t from, cudaStream_t to) {
     return GCNN_OK;
 }
 
-// ---- forward edge kernel dispatch: shared-memory tiles when the batch carries per-sample counts, else generic ------
-bool plan_edge_tiles(const int32_t* recv_counts, const int32_t* send_counts, int64_t n_samples, int rows_per_tile,
-                     std::vector<EdgeTile>& out, int* max_nsrc, int* max_rows);
-
-static int edge_forward_dispatch(gcnn_workspace* ws, const gcnn_batch* b, int conv, const EdgeLayout& L, int64_t n_recv,
-                                 const float* R, const float* S, const float* w_edge, EdgeScalars sc, float* H,
-                                 float* cnt, cudaStream_t st, double prof_bytes, int64_t n_edges) {
-    if (ws->use_tiles && b->n_samples > 0 && b->sample_n_cons && b->sample_n_vars && b->sample_n_cuts && n_recv > 0) {
-        const int32_t* recv = conv == 0 ? b->sample_n_cons : (conv == 1 ? b->sample_n_vars : b->sample_n_cuts);
-        const int32_t* send = conv == 1 ? b->sample_n_cons : b->sample_n_vars;
-        int64_t sum_r = 0, sum_s = 0;
-        for (int64_t s = 0; s < b->n_samples; ++s) { sum_r += recv[s]; sum_s += send[s]; }
-        const int64_t n_send = conv == 1 ? b->n_cons : b->n_vars;
-        std::vector<EdgeTile> tiles;
-        int max_nsrc = 0, max_rows = 0;
-        // dense segments only: staging a table pays off when rows gather many sources each
-        if (sum_r == n_recv && sum_s == n_send && n_edges >= 8 * n_recv &&
-            plan_edge_tiles(recv, send, b->n_samples, 128, tiles, &max_nsrc, &max_rows) &&
-            (int64_t)tiles.size() <= ws->tile_cap) {
-            // pageable source: the driver stages the copy before returning, so the vector may die right away
-            GCNN_CUDA_TRY(cudaMemcpyAsync(ws->d_tiles[conv], tiles.data(), sizeof(EdgeTile) * tiles.size(),
-                                          cudaMemcpyHostToDevice, st));
-            ws->masks_valid[conv] = 0;  // the tile kernel does not emit masks: the backward re-evaluates
-            return edge_forward_tiles(ws->d_tiles[conv], (int)tiles.size(), max_nsrc, max_rows, n_recv, n_edges, L, R, S,
-                                      w_edge, sc, H, cnt, ws->flags + 1, st, prof_bytes);
+// ---- block structure of the batch ------------------------------------------------------------------------------------
+// Turns the caller's per-sample count vectors (host, utils.py:420-422) into device offset arrays.  The vectors are a
+// promise (every edge stays inside its sample); counts that do not add up to the batch totals are ignored.
+static int upload_blocks(gcnn_workspace* ws, const gcnn_batch* b, cudaStream_t st, BlockInfo& out) {
+    out = BlockInfo();
+    if (!ws->use_blocks || b->n_samples <= 0 || b->n_samples > MAX_RECORDS || !b->sample_n_cons || !b->sample_n_vars ||
+        !b->sample_n_cuts)
+        return GCNN_OK;
+    const int slot = ws->blk_next;
+    ws->blk_next = (ws->blk_next + 1) % 4;
+    GCNN_CUDA_TRY(cudaEventSynchronize(ws->blk_ev[slot]));  // the copy that last read this pinned buffer (4 calls ago)
+    int32_t* h = ws->blk_pin[slot];
+    const int32_t* counts[3] = {b->sample_n_cons, b->sample_n_vars, b->sample_n_cuts};
+    const int64_t totals[3] = {b->n_cons, b->n_vars, b->n_cuts};
+    const int64_t n = b->n_samples, stride = MAX_RECORDS + 1;
+    BlockInfo bi;
+    for (int t = 0; t < 3; ++t) {
+        int64_t run = 0;
+        for (int64_t s = 0; s < n; ++s) {
+            const int64_t c = counts[t][s];
+            if (c < 0) return GCNN_OK;
+            h[t * stride + s] = (int32_t)run;
+            run += c;
+            if (c > bi.max_nodes[t]) bi.max_nodes[t] = c;
         }
+        if (run != totals[t]) return GCNN_OK;
+        h[t * stride + n] = (int32_t)run;
+        bi.off[t] = ws->blk_dev + t * stride;
+    }
+    bi.n = n;
+    for (int t = 0; t < 3; ++t)
+        GCNN_CUDA_TRY(cudaMemcpyAsync(ws->blk_dev + t * stride, h + t * stride, sizeof(int32_t) * (size_t)(n + 1),
+                                      cudaMemcpyHostToDevice, st));
+    GCNN_CUDA_TRY(cudaEventRecord(ws->blk_ev[slot], st));
+    out = bi;
+    return GCNN_OK;
+}
+
+// node types of convolution i: receiving side, sending side (0 constraints, 1 variables, 2 cuts)
+static const int CONV_RECV_T[3] = {0, 1, 2}, CONV_SEND_T[3] = {1, 0, 1};
+
+// ---- forward edge kernel dispatch: shared-memory block kernel when the batch carries its block structure, else generic
+static int edge_forward_dispatch(gcnn_workspace* ws, int conv, const EdgeLayout& L, int64_t n_recv, const float* R,
+                                 const float* S, const float* w_edge, EdgeScalars sc, float* H, float* cnt,
+                                 cudaStream_t st, double prof_bytes, int64_t n_edges) {
+    const BlockInfo& bi = ws->cur_blk;
+    const int rt = CONV_RECV_T[conv], stp = CONV_SEND_T[conv];
+    ws->conv_blocked[conv] = 0;
+    if (bi.n > 0 && n_recv > 0 && edge_block_fits(bi.max_nodes[stp], 0, false)) {
+        ws->conv_blocked[conv] = 1;
+        ws->masks_valid[conv] = 0;  // the block backward recomputes the ReLU masks from staged tables
+        return edge_block_forward(L, bi.off[rt], bi.off[stp], bi.n, bi.max_nodes[stp], R, S, w_edge, sc, H, cnt,
+                                  ws->flags + 1, st, prof_bytes);
     }
     void* masks = (cnt && ws->cap.training && ws->use_edge_masks) ? ws->edge_masks[conv] : nullptr;
     ws->masks_valid[conv] = masks != nullptr;
@@ -399,7 +473,7 @@ static int forward_convs_fused(gcnn_workspace* ws, const float* p, const float* 
         if (stop_layer == 5 + 2 * i) return wait_all_layouts();
         const int64_t E_i = graph_of[i] == 0 ? ec : ek;
         const double fwd_bytes = 256.0 * (double)(n_left[i] + nv + n_recv[i]) + 8.0 * (double)E_i + 4.0 * (double)(n_recv[i] + 1);
-        GCNN_TRY(edge_forward_dispatch(ws, b, i, L, n_recv[i], R, S, p + o.we, sc, a.H, keep ? a.cnt : nullptr, st, fwd_bytes, E_i));
+        GCNN_TRY(edge_forward_dispatch(ws, i, L, n_recv[i], R, S, p + o.we, sc, a.H, keep ? a.cnt : nullptr, st, fwd_bytes, E_i));
         ConvFwdArgs c{};
         c.H = a.H; c.Xt = recv_in[i]; c.deg_ptr = L.ptr; c.s_p = pn + PN.conv_sp[i];
         c.img_f = img_t(o.Wf); c.bias_f = p + o.bf;
@@ -420,10 +494,14 @@ static int forward_convs_fused(gcnn_workspace* ws, const float* p, const float* 
 // ---- forward -----------------------------------------------------------------------------------------------------
 // stop_layer: -1 runs everything; k in [5, 10] returns as soon as the input of pre-norm layer k exists.
 static int forward_impl(gcnn_workspace* ws, const float* p, const float* pn, const gcnn_batch* b, float* scores_out,
-                        int stop_layer, cudaStream_t st) {
+                        int stop_layer, cudaStream_t st, const BlockInfo* staged_blocks = nullptr) {
     const int64_t nc = b->n_cons, nv = b->n_vars, nk = b->n_cuts, ec = b->n_cons_edges, ek = b->n_cut_edges;
 
     cudaStream_t s1 = aux_stream(ws, 0, st), s2 = aux_stream(ws, 1, st);
+    // block structure first: the offset arrays are read by kernels on every stream forked below
+    if (staged_blocks) ws->cur_blk = ws->use_blocks ? *staged_blocks : BlockInfo();
+    else GCNN_TRY(upload_blocks(ws, b, st, ws->cur_blk));
+    const BlockInfo& bi = ws->cur_blk;
 
     // F1: edge layouts on an auxiliary stream, concurrent with the embeddings.  conv 0 reduces by constraint, conv 1
     // by variable (both over constraint edges), conv 2 by cut; the opposite grouping serves the backward pass.
@@ -442,15 +520,27 @@ static int forward_impl(gcnn_workspace* ws, const float* p, const float* pn, con
     GCNN_TRY(build_layout(b->cons_edge_inds, b->cons_edge_inds + ec, b->cons_edge_feats, ec, nc, nv, ws->sort,
                           ws->flags + 1, ws->flags + 2, cons_sorted, ws->graph[0].by_left, sl_cons));
     if (s1 != st) GCNN_CUDA_TRY(cudaEventRecord(ws->ev_layout[0], sl_cons));
-    GCNN_TRY(build_layout(b->cons_edge_inds + ec, b->cons_edge_inds, b->cons_edge_feats, ec, nv, nc, ws->sort,
-                          ws->flags + 1, ws->flags + 3, false, ws->graph[0].by_var, s1));
+    // by-variable layouts: one CTA-local counting sort per sample when the batch carries its block structure and the
+    // list is sorted by its left index (then a block's edges are contiguous); the device-wide radix sort otherwise
+    const bool tr_ok = bi.n > 0 && transpose_blocks_fits(bi.max_nodes[1]);
+    if (tr_ok && cons_sorted)
+        GCNN_TRY(transpose_blocks(b->cons_edge_inds + ec, b->cons_edge_inds, b->cons_edge_feats, ec, nc, nv, bi.off[0],
+                                  bi.off[1], bi.n, bi.max_nodes[1], ws->flags + 1, ws->flags + 3, ws->graph[0].by_var, s1));
+    else
+        GCNN_TRY(build_layout(b->cons_edge_inds + ec, b->cons_edge_inds, b->cons_edge_feats, ec, nv, nc, ws->sort,
+                              ws->flags + 1, ws->flags + 3, false, ws->graph[0].by_var, s1));
     if (s1 != st) GCNN_CUDA_TRY(cudaEventRecord(ws->ev_layout[1], s1));
     GCNN_TRY(build_layout(b->cut_edge_inds, b->cut_edge_inds + ek, b->cut_edge_feats, ek, nk, nv, ws->sort,
                           ws->flags + 1, ws->flags + 4, cuts_sorted, ws->graph[1].by_left, sl_cuts));
     if (s1 != st) GCNN_CUDA_TRY(cudaEventRecord(ws->ev_layout[2], sl_cuts));
-    if (ws->cap.training)
-        GCNN_TRY(build_layout(b->cut_edge_inds + ek, b->cut_edge_inds, b->cut_edge_feats, ek, nv, nk, ws->sort,
-                              ws->flags + 1, ws->flags + 5, false, ws->graph[1].by_var, s1));
+    if (ws->cap.training) {
+        if (tr_ok && cuts_sorted)
+            GCNN_TRY(transpose_blocks(b->cut_edge_inds + ek, b->cut_edge_inds, b->cut_edge_feats, ek, nk, nv, bi.off[2],
+                                      bi.off[1], bi.n, bi.max_nodes[1], ws->flags + 1, ws->flags + 5, ws->graph[1].by_var, s1));
+        else
+            GCNN_TRY(build_layout(b->cut_edge_inds + ek, b->cut_edge_inds, b->cut_edge_feats, ek, nv, nk, ws->sort,
+                                  ws->flags + 1, ws->flags + 5, false, ws->graph[1].by_var, s1));
+    }
     if (use_s3) GCNN_TRY(stream_edge(ws, s3, s1));  // ev_layout[3] (recorded on s1 below) covers the third stream too
 
     if (ws->use_tc)
@@ -523,7 +613,7 @@ static int forward_impl(gcnn_workspace* ws, const float* p, const float* pn, con
         // segment pointer; write the reduced rows
         const int64_t E_i = graph_of[i] == 0 ? ec : ek;
         const double fwd_bytes = 256.0 * (double)(n_left[i] + nv + n_recv) + 8.0 * (double)E_i + 4.0 * (double)(n_recv + 1);
-        GCNN_TRY(edge_forward_dispatch(ws, b, i, L, n_recv, R, S, p + o.we, sc, a.H, a.cnt, st, fwd_bytes, E_i));
+        GCNN_TRY(edge_forward_dispatch(ws, i, L, n_recv, R, S, p + o.we, sc, a.H, a.cnt, st, fwd_bytes, E_i));
         LinFwdArgs pc{a.H, nullptr, nullptr, p + o.Wf, p + o.bf, L.ptr, a.C, n_recv, 64, 0};
         GCNN_TRY(dense_forward(ws, p, pc, st));
         if (stop_layer == 6 + 2 * i) { if (s1 != st) GCNN_CUDA_TRY(cudaStreamWaitEvent(st, ws->ev_layout[3], 0)); return GCNN_OK; }
@@ -802,7 +892,13 @@ static int backward_impl_fused(gcnn_workspace* ws, const float* p, const float* 
         int n_dw = 0;
         const int64_t E_i = graph_of[i] == 0 ? b->n_cons_edges : b->n_cut_edges;
         const double bwd_bytes = 256.0 * (double)(2 * n_recv[i] + 2 * n_send[i]) + 8.0 * (double)E_i + 4.0 * (double)(n_send[i] + 1);
-        if (ws->masks_valid[i])  // algorithmic bytes: G gathered per edge comes from L2; compulsory: G, dS rows, 20 B per edge
+        const BlockInfo& bi = ws->cur_blk;
+        if (ws->conv_blocked[i] && bi.n > 0 && edge_block_backward_fits(bi.max_nodes[CONV_RECV_T[i]]))
+            // block kernel: receivers' R and G rows staged in shared memory, masks recomputed (reads R, G, S, writes dS)
+            GCNN_TRY(edge_block_backward(Ls, bi.off[CONV_SEND_T[i]], bi.off[CONV_RECV_T[i]], bi.n, bi.max_nodes[CONV_RECV_T[i]],
+                                         R, S, ws->bG[i], p + o.we, sc, ws->bdS[i], ws->dw_partials[i], &n_dw, ws->flags + 1,
+                                         st, bwd_bytes));
+        else if (ws->masks_valid[i])  // algorithmic bytes: G gathered per edge comes from L2; compulsory: G, dS rows, 20 B per edge
             GCNN_TRY(edge_backward_masked(Ls, n_send[i], ws->bG[i], ws->edge_masks[i], sc, ws->bdS[i], ws->dw_partials[i],
                                           &n_dw, st, 256.0 * (double)(n_recv[i] + n_send[i]) + 20.0 * (double)E_i +
                                                          4.0 * (double)(n_send[i] + 1)));
@@ -823,11 +919,40 @@ static int h2d(void* dst, const void* src, size_t bytes, cudaStream_t st) {
     return GCNN_OK;
 }
 
+// Fills a staging slot's block structure from host count vectors (pinned copy source owned by the slot).
+static int stage_blocks(gcnn_workspace* ws, gcnn_workspace::Stage& g, const int32_t* const counts[3], int64_t n,
+                        const int64_t totals[3], cudaStream_t cs) {
+    g.blk = BlockInfo();
+    if (n <= 0 || n > MAX_RECORDS || !counts[0] || !counts[1] || !counts[2]) return GCNN_OK;
+    const int64_t stride = MAX_RECORDS + 1;
+    BlockInfo bi;
+    for (int t = 0; t < 3; ++t) {
+        int64_t run = 0;
+        for (int64_t s = 0; s < n; ++s) {
+            const int64_t c = counts[t][s];
+            if (c < 0) return GCNN_OK;
+            g.blocks_host[t * stride + s] = (int32_t)run;
+            run += c;
+            if (c > bi.max_nodes[t]) bi.max_nodes[t] = c;
+        }
+        if (run != totals[t]) return GCNN_OK;
+        g.blocks_host[t * stride + n] = (int32_t)run;
+        bi.off[t] = g.blocks + t * stride;
+    }
+    bi.n = n;
+    for (int t = 0; t < 3; ++t)
+        GCNN_CUDA_TRY(cudaMemcpyAsync(g.blocks + t * stride, g.blocks_host + t * stride, sizeof(int32_t) * (size_t)(n + 1),
+                                      cudaMemcpyHostToDevice, cs));
+    g.blk = bi;
+    return GCNN_OK;
+}
+
 // Copies a host batch into staging slot `slot` on the copy stream; the slot's previous consumer must have finished.
 static int stage_batch(gcnn_workspace* ws, int slot, const gcnn_batch* hb, const float* targets_host) {
     gcnn_workspace::Stage& g = ws->stage[slot];
     cudaStream_t cs = ws->copy_st;
     if (g.valid) GCNN_CUDA_TRY(cudaStreamWaitEvent(cs, g.consumed, 0));
+    if (g.valid) GCNN_CUDA_TRY(cudaEventSynchronize(g.staged));  // the previous copy out of blocks_host is done
     GCNN_TRY(h2d(g.cons, hb->cons_feats, sizeof(float) * hb->n_cons * GCNN_CONS_FEATS, cs));
     GCNN_TRY(h2d(g.cei, hb->cons_edge_inds, sizeof(int32_t) * 2 * hb->n_cons_edges, cs));
     GCNN_TRY(h2d(g.cef, hb->cons_edge_feats, sizeof(float) * hb->n_cons_edges, cs));
@@ -836,11 +961,48 @@ static int stage_batch(gcnn_workspace* ws, int slot, const gcnn_batch* hb, const
     GCNN_TRY(h2d(g.kei, hb->cut_edge_inds, sizeof(int32_t) * 2 * hb->n_cut_edges, cs));
     GCNN_TRY(h2d(g.kef, hb->cut_edge_feats, sizeof(float) * hb->n_cut_edges, cs));
     if (targets_host) GCNN_TRY(h2d(g.targets, targets_host, sizeof(float) * hb->n_cuts, cs));
+    const int32_t* const counts[3] = {hb->sample_n_cons, hb->sample_n_vars, hb->sample_n_cuts};
+    const int64_t totals[3] = {hb->n_cons, hb->n_vars, hb->n_cuts};
+    GCNN_TRY(stage_blocks(ws, g, counts, hb->n_samples, totals, cs));
     GCNN_CUDA_TRY(cudaEventRecord(g.staged, cs));
     g.meta = *hb;
     g.meta.cons_feats = g.cons; g.meta.cons_edge_inds = g.cei; g.meta.cons_edge_feats = g.cef;
     g.meta.var_feats = g.var; g.meta.cut_feats = g.cut; g.meta.cut_edge_inds = g.kei; g.meta.cut_edge_feats = g.kef;
+    // the count vectors were consumed above; the staged batch carries its block structure in g.blk
+    g.meta.sample_n_cons = g.meta.sample_n_vars = g.meta.sample_n_cuts = nullptr;
+    g.meta.n_samples = 0;
     g.valid = 1;
+    return GCNN_OK;
+}
+
+// Points a slot at freshly carved staging memory; a valid slot's tensors are copied across first (device to device;
+// the caller has synchronised the device, so nothing is in flight).
+static int move_stage(gcnn_workspace::Stage& g, const StagePtrs& n) {
+    if (g.valid) {
+        const gcnn_batch& m = g.meta;
+        auto d2d = [&](void* dst, const void* src, size_t bytes) -> int {
+            if (bytes == 0) return GCNN_OK;
+            GCNN_CUDA_TRY(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice));
+            return GCNN_OK;
+        };
+        GCNN_TRY(d2d(n.cons, g.cons, sizeof(float) * m.n_cons * GCNN_CONS_FEATS));
+        GCNN_TRY(d2d(n.cei, g.cei, sizeof(int32_t) * 2 * m.n_cons_edges));
+        GCNN_TRY(d2d(n.cef, g.cef, sizeof(float) * m.n_cons_edges));
+        GCNN_TRY(d2d(n.var, g.var, sizeof(float) * m.n_vars * GCNN_VAR_FEATS));
+        GCNN_TRY(d2d(n.cut, g.cut, sizeof(float) * m.n_cuts * GCNN_CUT_FEATS));
+        GCNN_TRY(d2d(n.kei, g.kei, sizeof(int32_t) * 2 * m.n_cut_edges));
+        GCNN_TRY(d2d(n.kef, g.kef, sizeof(float) * m.n_cut_edges));
+        GCNN_TRY(d2d(n.targets, g.targets, sizeof(float) * m.n_cuts));
+        GCNN_TRY(d2d(n.blocks, g.blocks, sizeof(int32_t) * 3 * (MAX_RECORDS + 1)));
+    }
+    g.cons = n.cons; g.cei = n.cei; g.cef = n.cef; g.var = n.var; g.cut = n.cut; g.kei = n.kei; g.kef = n.kef;
+    g.targets = n.targets; g.raw = n.raw; g.raw_cap = n.raw_cap; g.descs = n.descs; g.blocks = n.blocks;
+    if (g.valid) {
+        g.meta.cons_feats = g.cons; g.meta.cons_edge_inds = g.cei; g.meta.cons_edge_feats = g.cef;
+        g.meta.var_feats = g.var; g.meta.cut_feats = g.cut; g.meta.cut_edge_inds = g.kei; g.meta.cut_edge_feats = g.kef;
+        if (g.blk.n > 0)
+            for (int t = 0; t < 3; ++t) g.blk.off[t] = g.blocks + t * (MAX_RECORDS + 1);
+    }
     return GCNN_OK;
 }
 
@@ -857,6 +1019,15 @@ static int read_error_flag(gcnn_workspace* ws, cudaStream_t st) {
         return GCNN_INVALID;
     }
     return GCNN_OK;
+}
+
+// A batch descriptor handed out by gcnn_staged_batch points into a staging slot: its block structure lives there.
+static const BlockInfo* staged_blocks_for(const gcnn_workspace* ws, const gcnn_batch* b) {
+    for (int s = 0; s < 2; ++s)
+        if (ws->stage[s].valid && ws->stage[s].blk.n > 0 && b->cons_feats == ws->stage[s].cons &&
+            b->var_feats == ws->stage[s].var)
+            return &ws->stage[s].blk;
+    return nullptr;
 }
 
 }  // namespace gcnn
@@ -957,8 +1128,9 @@ int gcnn_workspace_create(gcnn_workspace** out) {
     ws->use_tc = !(tc && tc[0] == '0');
     const char* ms = getenv("GCNN_STREAMS");  // GCNN_STREAMS=0 serialises everything on the caller's stream
     ws->use_streams = !(ms && ms[0] == '0');
-    const char* ti = getenv("GCNN_TILES");  // GCNN_TILES=1: shared-memory tile edge kernel when per-sample counts are given
-    ws->use_tiles = ti && ti[0] == '1';
+    const char* bl = getenv("GCNN_BLOCKS");  // GCNN_BLOCKS=0: ignore per-sample counts (generic edge kernels, radix sort)
+    ws->use_blocks = !(bl && bl[0] == '0');
+    GCNN_CUDA_TRY(cudaGetDevice(&ws->device));
     const char* fu = getenv("GCNN_FUSED");  // GCNN_FUSED=0: one launch per dense layer
     ws->use_fused = !(fu && fu[0] == '0');
     const char* bf = getenv("GCNN_BF16_FWD");  // GCNN_BF16_FWD=0: 3xTF32 forward chains
@@ -978,15 +1150,30 @@ int gcnn_workspace_create(gcnn_workspace** out) {
         GCNN_CUDA_TRY(cudaEventCreateWithFlags(&ws->stage[s].result, cudaEventDisableTiming));
     }
     GCNN_CUDA_TRY(cudaHostAlloc((void**)&ws->h_result, 4 * sizeof(float), cudaHostAllocDefault));
-    for (int s = 0; s < 2; ++s)
+    for (int s = 0; s < 2; ++s) {
         GCNN_CUDA_TRY(cudaHostAlloc((void**)&ws->stage[s].descs_host, sizeof(RecordDesc) * MAX_RECORDS, cudaHostAllocDefault));
+        GCNN_CUDA_TRY(cudaHostAlloc((void**)&ws->stage[s].blocks_host, sizeof(int32_t) * 3 * (MAX_RECORDS + 1), cudaHostAllocDefault));
+    }
+    for (int i = 0; i < 4; ++i) {
+        GCNN_CUDA_TRY(cudaHostAlloc((void**)&ws->blk_pin[i], sizeof(int32_t) * 3 * (MAX_RECORDS + 1), cudaHostAllocDefault));
+        GCNN_CUDA_TRY(cudaEventCreateWithFlags(&ws->blk_ev[i], cudaEventDisableTiming));
+    }
     *out = ws;
     return GCNN_OK;
 }
 
 int gcnn_workspace_destroy(gcnn_workspace* ws) {
     if (!ws) return GCNN_OK;
+    DeviceGuard guard(ws->device);
+    cudaDeviceSynchronize();
     if (ws->arena) cudaFree(ws->arena);
+    if (ws->stage_arena) cudaFree(ws->stage_arena);
+    for (int i = 0; i < 4; ++i) {
+        if (ws->blk_pin[i]) cudaFreeHost(ws->blk_pin[i]);
+        if (ws->blk_ev[i]) cudaEventDestroy(ws->blk_ev[i]);
+    }
+    for (int s = 0; s < 2; ++s)
+        if (ws->stage[s].blocks_host) cudaFreeHost(ws->stage[s].blocks_host);
     for (int i = 0; i < 3; ++i) if (ws->aux[i]) cudaStreamDestroy(ws->aux[i]);
     for (int i = 0; i < 16; ++i) if (ws->ev[i]) cudaEventDestroy(ws->ev[i]);
     for (int i = 0; i < 4; ++i) if (ws->ev_layout[i]) cudaEventDestroy(ws->ev_layout[i]);
@@ -1007,6 +1194,7 @@ int gcnn_workspace_destroy(gcnn_workspace* ws) {
 int gcnn_workspace_reserve(gcnn_workspace* ws, int64_t nc, int64_t nv, int64_t nk, int64_t ec, int64_t ek,
                            int training) {
     if (!ws || nc < 0 || nv < 0 || nk < 0 || ec < 0 || ek < 0) { set_error("bad reserve arguments"); return GCNN_INVALID; }
+    DeviceGuard guard(ws->device);
     training = training ? 1 : 0;
     if (ws->arena && fits(ws->cap, nc, nv, nk, ec, ek, training)) return GCNN_OK;
     Caps c = ws->cap;
@@ -1015,6 +1203,26 @@ int gcnn_workspace_reserve(gcnn_workspace* ws, int64_t nc, int64_t nv, int64_t n
     gcnn_workspace probe;
     const size_t bytes = carve(&probe, nullptr, c);
     GCNN_CUDA_TRY(cudaDeviceSynchronize());
+    // staging slots first (their own allocation): a batch that is staged but not yet consumed survives the growth
+    if (!ws->stage_arena || !fits(ws->stage_cap, nc, nv, nk, ec, ek, 0)) {
+        Caps sc = c;
+        sc.training = 0;
+        StagePtrs ptrs[2];
+        const size_t sbytes = carve_stage(ptrs, nullptr, sc);
+        char* smem = nullptr;
+        cudaError_t err = cudaMalloc(&smem, sbytes);
+        if (err != cudaSuccess) {
+            cudaGetLastError();
+            set_error("staging area of %zu bytes does not fit on the device: %s", sbytes, cudaGetErrorString(err));
+            return err == cudaErrorMemoryAllocation ? GCNN_OOM : GCNN_CUDA_ERROR;
+        }
+        carve_stage(ptrs, smem, sc);
+        for (int s = 0; s < 2; ++s) GCNN_TRY(move_stage(ws->stage[s], ptrs[s]));
+        if (ws->stage_arena) cudaFree(ws->stage_arena);
+        ws->stage_arena = smem;
+        ws->stage_bytes = sbytes;
+        ws->stage_cap = sc;
+    }
     if (ws->arena) { cudaFree(ws->arena); ws->arena = nullptr; ws->arena_bytes = 0; ws->cap = Caps(); }
     char* mem = nullptr;
     cudaError_t err = cudaMalloc(&mem, bytes);
@@ -1027,6 +1235,7 @@ int gcnn_workspace_reserve(gcnn_workspace* ws, int64_t nc, int64_t nv, int64_t n
     ws->arena_bytes = bytes;
     ws->cap = c;
     ws->have_activations = 0;
+    ws->cur_blk = BlockInfo();
     carve(ws, mem, c);
     GCNN_CUDA_TRY(cudaMemset(ws->flags, 0, sizeof(int32_t) * 64));
     GCNN_CUDA_TRY(cudaMemcpy(ws->tc_block_offsets, tc_blocks().data(), sizeof(int) * tc_blocks().size(),
@@ -1039,7 +1248,7 @@ int gcnn_set_option(gcnn_workspace* ws, const char* name, int value) {
     if (!strcmp(name, "tensor_cores")) ws->use_tc = value != 0;
     else if (!strcmp(name, "streams")) ws->use_streams = value != 0;
     else if (!strcmp(name, "fused")) ws->use_fused = value != 0;
-    else if (!strcmp(name, "tiles")) ws->use_tiles = value != 0;
+    else if (!strcmp(name, "blocks")) ws->use_blocks = value != 0;
     else if (!strcmp(name, "fused_backward")) ws->use_fused_bwd = value != 0;
     else if (!strcmp(name, "bf16_forward")) ws->use_bf16_fwd = value != 0;
     else if (!strcmp(name, "count_before_loss")) ws->count_before_loss = value != 0;
@@ -1053,12 +1262,14 @@ int64_t gcnn_workspace_bytes(const gcnn_workspace* ws) { return ws ? (int64_t)ws
 
 int gcnn_check(gcnn_workspace* ws, void* stream) {
     if (!ws || !ws->arena) { set_error("workspace not reserved"); return GCNN_INVALID; }
+    DeviceGuard guard(ws->device);
     return read_error_flag(ws, (cudaStream_t)stream);
 }
 
 int gcnn_build_csr(gcnn_workspace* ws, int which, const int32_t* ei, const float* ef, int64_t E, int64_t n_left,
                    int64_t n_vars, int need_transposed, void* stream) {
     if (!ws || !ws->arena || which < 0 || which > 1) { set_error("bad build_csr arguments"); return GCNN_INVALID; }
+    DeviceGuard guard(ws->device);
     const int64_t cap_left = which == 0 ? ws->cap.nc : ws->cap.nk, cap_e = which == 0 ? ws->cap.ec : ws->cap.ek;
     if (n_left > cap_left || n_vars > ws->cap.nv || E > cap_e) { set_error("workspace too small"); return GCNN_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
@@ -1077,9 +1288,55 @@ int gcnn_build_csr(gcnn_workspace* ws, int which, const int32_t* ei, const float
     return GCNN_OK;
 }
 
+int gcnn_build_csr_blocks(gcnn_workspace* ws, int which, const int32_t* ei, const float* ef, int64_t E, int64_t n_left,
+                          int64_t n_vars, const int32_t* sample_n_left, const int32_t* sample_n_vars, int64_t n_samples,
+                          void* stream) {
+    if (!ws || !ws->arena || which < 0 || which > 1 || !sample_n_left || !sample_n_vars || n_samples <= 0 ||
+        n_samples > MAX_RECORDS) {
+        set_error("bad build_csr_blocks arguments");
+        return GCNN_INVALID;
+    }
+    DeviceGuard guard(ws->device);
+    const int64_t cap_left = which == 0 ? ws->cap.nc : ws->cap.nk, cap_e = which == 0 ? ws->cap.ec : ws->cap.ek;
+    if (n_left > cap_left || n_vars > ws->cap.nv || E > cap_e) { set_error("workspace too small"); return GCNN_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    // offsets through the same upload path the whole-model calls use (node type `which` = 0 takes the constraint slot)
+    gcnn_batch b{};
+    std::vector<int32_t> zeros((size_t)n_samples, 0);
+    b.n_samples = n_samples;
+    b.n_vars = n_vars;
+    b.sample_n_vars = sample_n_vars;
+    b.sample_n_cons = which == 0 ? sample_n_left : zeros.data();
+    b.sample_n_cuts = which == 1 ? sample_n_left : zeros.data();
+    b.n_cons = which == 0 ? n_left : 0;
+    b.n_cuts = which == 1 ? n_left : 0;
+    BlockInfo bi;
+    const int saved = ws->use_blocks;
+    ws->use_blocks = 1;
+    const int rc = upload_blocks(ws, &b, st, bi);
+    ws->use_blocks = saved;
+    GCNN_TRY(rc);
+    if (bi.n == 0 || !transpose_blocks_fits(bi.max_nodes[1])) {
+        set_error("per-sample counts do not add up to the totals, or a sample has too many variables for the block sort");
+        return GCNN_INVALID;
+    }
+    int32_t* unsorted = ws->flags + 2 + 2 * which;
+    GCNN_CUDA_TRY(cudaMemsetAsync(unsorted, 0, 2 * sizeof(int32_t), st));
+    GCNN_CUDA_TRY(cudaMemsetAsync(unsorted + LONG_FLAG_OFFSET, 0, 2 * sizeof(int32_t), st));
+    GCNN_TRY(build_layout(ei, ei + E, ef, E, n_left, n_vars, ws->sort, ws->flags + 1, unsorted, true,
+                          ws->graph[which].by_left, st));
+    GCNN_TRY(transpose_blocks(ei + E, ei, ef, E, n_left, n_vars, bi.off[which == 0 ? 0 : 2], bi.off[1], bi.n,
+                              bi.max_nodes[1], ws->flags + 1, unsorted + 1, ws->graph[which].by_var, st));
+    ws->last.n_vars = n_vars;
+    if (which == 0) { ws->last.n_cons = n_left; ws->last.n_cons_edges = E; }
+    else { ws->last.n_cuts = n_left; ws->last.n_cut_edges = E; }
+    return GCNN_OK;
+}
+
 int gcnn_csr_export(gcnn_workspace* ws, int which, int side, int32_t* ptr, int32_t* other, float* val, int32_t* perm,
                     void* stream) {
     if (!ws || !ws->arena || which < 0 || which > 1 || side < 0 || side > 1) { set_error("bad export arguments"); return GCNN_INVALID; }
+    DeviceGuard guard(ws->device);
     const EdgeLayout& L = side == 0 ? ws->graph[which].by_left : ws->graph[which].by_var;
     const int64_t E = which == 0 ? ws->last.n_cons_edges : ws->last.n_cut_edges;
     const int64_t n = side == 1 ? ws->last.n_vars : (which == 0 ? ws->last.n_cons : ws->last.n_cuts);
@@ -1098,15 +1355,22 @@ int gcnn_csr_export(gcnn_workspace* ws, int which, int side, int32_t* ptr, int32
 
 int gcnn_forward(gcnn_workspace* ws, const float* params, const float* prenorm, const gcnn_batch* batch,
                  float* scores_out, int save_activations, void* stream) {
+    if (!ws) { set_error("null workspace"); return GCNN_INVALID; }
+    DeviceGuard guard(ws->device);
     GCNN_TRY(check_batch(ws, batch, save_activations ? 1 : 0));
-    GCNN_TRY(forward_impl(ws, params, prenorm, batch, scores_out, -1, (cudaStream_t)stream));
+    ws->have_activations = 0;
+    GCNN_TRY(forward_impl(ws, params, prenorm, batch, scores_out, -1, (cudaStream_t)stream, staged_blocks_for(ws, batch)));
     ws->last = *batch;
-    ws->have_activations = 1;
+    // only a saving forward leaves activations a backward may use; every one gets a new stamp (gcnn_activation_stamp)
+    ws->have_activations = save_activations ? 1 : 0;
+    if (save_activations) ++ws->act_stamp;
     return GCNN_OK;
 }
 
 int gcnn_backward(gcnn_workspace* ws, const float* params, const float* prenorm, const gcnn_batch* batch,
                   const float* d_scores, float* grads_out, void* stream) {
+    if (!ws) { set_error("null workspace"); return GCNN_INVALID; }
+    DeviceGuard guard(ws->device);
     GCNN_TRY(check_batch(ws, batch, 1));
     if (!ws->have_activations || ws->last.n_cons != batch->n_cons || ws->last.n_vars != batch->n_vars ||
         ws->last.n_cuts != batch->n_cuts || ws->last.n_cons_edges != batch->n_cons_edges ||
@@ -1116,6 +1380,8 @@ int gcnn_backward(gcnn_workspace* ws, const float* params, const float* prenorm,
     }
     return backward_impl(ws, params, prenorm, batch, d_scores, grads_out, (cudaStream_t)stream);
 }
+
+int64_t gcnn_activation_stamp(const gcnn_workspace* ws) { return ws && ws->have_activations ? ws->act_stamp : -1; }
 
 int gcnn_mse_seed(const float* scores, const float* targets, int64_t n, float scale, float* d_scores,
                   float* loss_sum_out, void* stream) {
@@ -1143,6 +1409,8 @@ int gcnn_ranking_deviation(const float* predictions, const float* improvements, 
 int gcnn_forward_backward(gcnn_workspace* ws, const float* params, const float* prenorm, const gcnn_batch* batch,
                           const float* targets, float seed_scale, float* scores_out, float* grads_out,
                           float* loss_sum_out, void* stream) {
+    if (!ws) { set_error("null workspace"); return GCNN_INVALID; }
+    DeviceGuard guard(ws->device);
     GCNN_TRY(check_batch(ws, batch, 1));
     cudaStream_t st = (cudaStream_t)stream;
     float* scores = scores_out ? scores_out : ws->scores;
@@ -1150,9 +1418,10 @@ int gcnn_forward_backward(gcnn_workspace* ws, const float* params, const float* 
     const bool fuse_head = ws->use_tc && ws->use_fused && ws->use_fused_bwd;
     ws->head_fused = fuse_head ? 1 : 0;
     ws->loss_out = loss_out;
-    int rc = forward_impl(ws, params, prenorm, batch, scores, -1, st);
+    int rc = forward_impl(ws, params, prenorm, batch, scores, -1, st, staged_blocks_for(ws, batch));
     ws->last = *batch;
     ws->have_activations = 1;
+    ++ws->act_stamp;
     if (rc == GCNN_OK) {
         if (fuse_head)
             rc = head_loss(ws->g1, params + P.Wh2, params + P.bh2, targets, seed_scale, scores, ws->t_dg, ws->partials[0],
@@ -1171,6 +1440,8 @@ int gcnn_forward_backward(gcnn_workspace* ws, const float* params, const float* 
 
 int gcnn_prenorm_stats(gcnn_workspace* ws, const float* params, const float* prenorm, const gcnn_batch* b, int layer,
                        double* mean_out, double* var_out, double* count_out, void* stream) {
+    if (!ws) { set_error("null workspace"); return GCNN_INVALID; }
+    DeviceGuard guard(ws->device);
     GCNN_TRY(check_batch(ws, b, 0));
     if (layer < 0 || layer >= GCNN_N_PRENORM_LAYERS) { set_error("pre-norm layer index out of range"); return GCNN_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
@@ -1255,7 +1526,8 @@ int gcnn_prenorm_stats(gcnn_workspace* ws, const float* params, const float* pre
 }
 
 int gcnn_stage_host_batch(gcnn_workspace* ws, int slot, const gcnn_batch* hb, const float* targets_host) {
-    if (slot < 0 || slot > 1) { set_error("staging slot must be 0 or 1"); return GCNN_INVALID; }
+    if (!ws || slot < 0 || slot > 1) { set_error("staging slot must be 0 or 1"); return GCNN_INVALID; }
+    DeviceGuard guard(ws->device);
     GCNN_TRY(check_batch(ws, hb, targets_host ? 1 : 0));
     return stage_batch(ws, slot, hb, targets_host);
 }
@@ -1271,6 +1543,7 @@ int gcnn_stage_records(gcnn_workspace* ws, int slot, const void* const* records_
         set_error("gcnn_stage_records: bad arguments or workspace not reserved");
         return GCNN_INVALID;
     }
+    DeviceGuard guard(ws->device);
     gcnn_workspace::Stage& g = ws->stage[slot];
     cudaStream_t cs = ws->copy_st;
     // the slot's previous consumer must be done with the batch tensors, and the previous assembly with descs_host
@@ -1281,6 +1554,16 @@ int gcnn_stage_records(gcnn_workspace* ws, int slot, const void* const* records_
     GCNN_TRY(assemble_records(records_host, n_records, g.raw, g.raw_cap, g.descs, g.descs_host, MAX_RECORDS, out,
                               ws->cap.nc, ws->cap.nv, ws->cap.nk, ws->cap.ec, ws->cap.ek, &meta, h2d_bytes_out,
                               ws->flags + 1, cs));
+    {   // the records' node counts are the batch's block structure
+        std::vector<int32_t> cnt[3];
+        for (int t = 0; t < 3; ++t) cnt[t].resize((size_t)n_records);
+        for (int64_t i = 0; i < n_records; ++i) {
+            cnt[0][i] = g.descs_host[i].n_cons; cnt[1][i] = g.descs_host[i].n_vars; cnt[2][i] = g.descs_host[i].n_cuts;
+        }
+        const int32_t* const counts[3] = {cnt[0].data(), cnt[1].data(), cnt[2].data()};
+        const int64_t totals[3] = {meta.n_cons, meta.n_vars, meta.n_cuts};
+        GCNN_TRY(stage_blocks(ws, g, counts, n_records, totals, cs));
+    }
     GCNN_CUDA_TRY(cudaEventRecord(g.staged, cs));
     meta.cons_feats = g.cons; meta.cons_edge_inds = g.cei; meta.cons_edge_feats = g.cef;
     meta.var_feats = g.var; meta.cut_feats = g.cut; meta.cut_edge_inds = g.kei; meta.cut_edge_feats = g.kef;
@@ -1292,11 +1575,12 @@ int gcnn_stage_records(gcnn_workspace* ws, int slot, const void* const* records_
 int gcnn_score_staged(gcnn_workspace* ws, int slot, const float* params, const float* prenorm, float* scores_host,
                       void* stream) {
     if (!ws || slot < 0 || slot > 1 || !ws->stage[slot].valid) { set_error("no batch staged in this slot"); return GCNN_INVALID; }
+    DeviceGuard guard(ws->device);
     cudaStream_t st = (cudaStream_t)stream;
     gcnn_workspace::Stage& g = ws->stage[slot];
     GCNN_TRY(check_batch(ws, &g.meta, 0));
     GCNN_CUDA_TRY(cudaStreamWaitEvent(st, g.staged, 0));
-    GCNN_TRY(forward_impl(ws, params, prenorm, &g.meta, ws->scores, -1, st));
+    GCNN_TRY(forward_impl(ws, params, prenorm, &g.meta, ws->scores, -1, st, &g.blk));
     ws->have_activations = 0;
     GCNN_CUDA_TRY(cudaEventRecord(g.consumed, st));
     if (g.meta.n_cuts > 0)
@@ -1307,6 +1591,7 @@ int gcnn_score_staged(gcnn_workspace* ws, int slot, const float* params, const f
 int gcnn_train_step_staged_async(gcnn_workspace* ws, int slot, float* params, const float* prenorm, float* adam_m,
                                  float* adam_v, float lr, int64_t step, void* stream) {
     if (!ws || slot < 0 || slot > 1 || !ws->stage[slot].valid) { set_error("no batch staged in this slot"); return GCNN_INVALID; }
+    DeviceGuard guard(ws->device);
     cudaStream_t st = (cudaStream_t)stream;
     gcnn_workspace::Stage& g = ws->stage[slot];
     GCNN_TRY(check_batch(ws, &g.meta, 1));
@@ -1336,6 +1621,7 @@ int gcnn_train_step_staged_async(gcnn_workspace* ws, int slot, float* params, co
 
 int gcnn_train_step_result(gcnn_workspace* ws, int slot, float* loss_host, void* stream) {
     if (!ws || slot < 0 || slot > 1 || ws->stage[slot].result_cuts < 0) { set_error("no step pending on this slot"); return GCNN_INVALID; }
+    DeviceGuard guard(ws->device);
     gcnn_workspace::Stage& g = ws->stage[slot];
     GCNN_CUDA_TRY(cudaEventSynchronize(g.result));
     const int64_t nk = g.result_cuts;
@@ -1355,6 +1641,7 @@ int gcnn_train_step_staged(gcnn_workspace* ws, int slot, float* params, const fl
 
 int gcnn_staged_batch(gcnn_workspace* ws, int slot, gcnn_batch* out, float** targets_dev, void* stream) {
     if (!ws || slot < 0 || slot > 1 || !ws->stage[slot].valid || !out) { set_error("no batch staged in this slot"); return GCNN_INVALID; }
+    DeviceGuard guard(ws->device);
     GCNN_CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, ws->stage[slot].staged, 0));
     *out = ws->stage[slot].meta;
     if (targets_dev) *targets_dev = ws->stage[slot].targets;
@@ -1363,6 +1650,7 @@ int gcnn_staged_batch(gcnn_workspace* ws, int slot, gcnn_batch* out, float** tar
 
 int gcnn_release_staged(gcnn_workspace* ws, int slot, void* stream) {
     if (!ws || slot < 0 || slot > 1) { set_error("staging slot must be 0 or 1"); return GCNN_INVALID; }
+    DeviceGuard guard(ws->device);
     GCNN_CUDA_TRY(cudaEventRecord(ws->stage[slot].consumed, (cudaStream_t)stream));
     return GCNN_OK;
 }
@@ -1408,6 +1696,7 @@ int gcnn_edge_backward(gcnn_workspace* ws, const int32_t* ptr, const int32_t* ot
                        const float* R, const float* S, const float* G, const float* w_edge, float f_shift,
                        float f_scale, float s_f, float* dS, float* dw, void* stream) {
     if (!ws || !ws->arena || !ws->cap.training) { set_error("edge_backward needs a training workspace"); return GCNN_INVALID; }
+    DeviceGuard guard(ws->device);
     cudaStream_t st = (cudaStream_t)stream;
     float* dev = nullptr;
     GCNN_CUDA_TRY(cudaMalloc(&dev, 3 * sizeof(float)));

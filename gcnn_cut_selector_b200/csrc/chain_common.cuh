@@ -6,6 +6,11 @@
 
 namespace gcnn {
 
+#ifndef GCNN_ACT_PIECES
+#define GCNN_ACT_PIECES 3
+#endif
+constexpr int ACT_PIECES = GCNN_ACT_PIECES;  // bf16 pieces of a saved activation in the weight-gradient MMAs
+
 constexpr uint32_t IDESC_BF16_KK = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 constexpr uint32_t IDESC_BF16_MN = IDESC_BF16_KK | (1u << 15) | (1u << 16);  // A and B MN-major
 // M = 64 variant for the weight gradients of 64-feature layers: the A operand is ONE 64-wide block (2 KB per 16 lines
@@ -71,7 +76,7 @@ __device__ __forceinline__ void issue_wgrad(uint32_t tmem_d, uint32_t act_tile, 
     asm volatile("" : "+r"(act_tile), "+r"(g_tile));
     const uint64_t da0 = make_desc_mn16(act_tile, lbo), db0 = make_desc_mn16(g_tile, T16_BYTES);
 #pragma unroll 1
-    for (int p = 1; p < 6; ++p) {  // the activation operand carries two pieces: (1,1) (0,2) (1,0) (0,1) (0,0)
+    for (int p = ACT_PIECES == 3 ? 0 : 1; p < 6; ++p) {  // two activation pieces: (1,1) (0,2) (1,0) (0,1) (0,0); three: + (2,0)
         const uint32_t pa = (0x001012u >> (4 * p)) & 3u, pb = (0x010210u >> (4 * p)) & 3u;
         const uint64_t da = da0 + (uint64_t)(pa * (T16_PIECE >> 4)), db = db0 + (uint64_t)(pb * (T16_PIECE >> 4));
 #pragma unroll
@@ -132,9 +137,10 @@ __device__ __forceinline__ void load_tile(float4 (&reg)[NLD], const float* __res
         reg[it] = m < M ? ldg_stream4(src + m * D + (i & 15) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
-// PIECES = 3 for gradient tiles (operands of the input-gradient MMAs, fp32-level accuracy through the chain); PIECES = 2
-// for the saved activations, which are only the A operand of a weight-gradient MMA (a sum over all rows: 16 operand bits
-// leave its relative L2 error near 3e-6) and the source of the ReLU masks.
+// PIECES = 3 for gradient tiles (operands of the input-gradient MMAs, fp32-level accuracy through the chain).  The saved
+// activations -- only the A operand of a weight-gradient MMA and the source of the ReLU masks -- carry ACT_PIECES
+// pieces: 3 (default: all six products, dropped terms <= 2^-24, weight gradients within 1e-5 of the fp64 oracle) or 2
+// (-DGCNN_ACT_PIECES=2: five products, ~3e-6 relative L2 error per weight gradient; kept for the A/B in profiles/).
 template <int PIECES>
 __device__ __forceinline__ void store_half_chunk3(uint8_t* tile, int line, int f4, float4 v) {
     uint2 q0, q1, q2;

@@ -197,11 +197,23 @@ int edge_backward(const EdgeLayout& by_send, int64_t n_send, const float* R, con
                   cudaStream_t st, double prof_bytes = 0.0, int64_t n_edges = 0);
 int edge_backward_max_partials();
 
-// tile variant of the forward edge kernel (edge_tile.cu): source table staged in shared memory per sample block
-struct EdgeTile { int32_t row0, row1, src0, nsrc; };
-int edge_forward_tiles(const EdgeTile* tiles_dev, int n_tiles, int max_nsrc, int max_rows, int64_t n_recv,
-                       int64_t n_edges, const EdgeLayout& L, const float* R, const float* S, const float* w_edge,
-                       EdgeScalars sc, float* H, float* cnt, int32_t* err_flag, cudaStream_t st, double prof_bytes);
+// ---- block-diagonal batches (edge_block.cu): the loader's per-sample node counts (utils.py:420-422) turn the batch into
+// blocks whose gathered tables fit in shared memory.  Offsets are device arrays of n_blocks + 1 int32 each.
+bool edge_block_fits(int64_t max_send_rows, int64_t max_recv_rows, bool training);
+bool edge_block_backward_fits(int64_t max_recv_rows);
+int edge_block_forward(const EdgeLayout& by_recv, const int32_t* recv_off, const int32_t* send_off, int64_t n_blocks,
+                       int64_t max_send_rows, const float* R, const float* S, const float* w_edge, EdgeScalars sc, float* H,
+                       float* cnt, int32_t* err_flag, cudaStream_t st, double prof_bytes);
+int edge_block_backward(const EdgeLayout& by_send, const int32_t* send_off, const int32_t* recv_off, int64_t n_blocks,
+                        int64_t max_recv_rows, const float* R, const float* S, const float* G, const float* w_edge,
+                        EdgeScalars sc, float* dS, float* dw_partials, int* n_partials, int32_t* err_flag, cudaStream_t st,
+                        double prof_bytes);
+int edge_block_backward_max_partials();
+// transposed (by-variable) layout of an edge list sorted by its left index, one CTA-local stable counting sort per block
+bool transpose_blocks_fits(int64_t max_vars);
+int transpose_blocks(const int32_t* keys_var, const int32_t* keys_left, const float* feats, int64_t E, int64_t n_left,
+                     int64_t n_var, const int32_t* left_off, const int32_t* var_off, int64_t n_blocks, int64_t max_vars,
+                     int32_t* err_flag, int32_t* unsorted_flag, EdgeLayout& out, cudaStream_t st);
 // sum and sum of squares of (z_e - center) over all E x 64 joint pre-activations (double accumulators)
 int edge_z_stats(const EdgeLayout& by_recv, int64_t n_recv, const float* R, const float* S, const float* w_edge,
                  EdgeScalars sc, double center, double* partials, double* out2, cudaStream_t st);

@@ -170,7 +170,7 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
             bsum_p[0] += ra[it].x; bsum_p[1] += ra[it].y; bsum_p[2] += ra[it].z; bsum_p[3] += ra[it].w;
         }
         store_tile<3>(B0g, ra, 1.f, tid);
-        store_tile<2>(B1g, rb, 1.f, tid);
+        store_tile<ACT_PIECES>(B1g, rb, 1.f, tid);
         TS_MARK();  // tiles stored
         publish_tiles(bar_ready, tid);
         TS_MARK();  // published
@@ -191,7 +191,7 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
         // ---------------- S2: output layer 2 ----------------
         mbar_wait(bar_w, ph_w); ph_w ^= 1;  // B0 (dP) and B1 (Y) are free
         TS_MARK();  // weight-gradient MMAs done
-        store_tile<2>(B0g, ra, 1.f, tid);
+        store_tile<ACT_PIECES>(B0g, ra, 1.f, tid);
         TS_MARK();  // tiles stored
         publish_tiles(bar_ready, tid);
         TS_MARK();  // published
@@ -214,8 +214,8 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
         mbar_wait(bar_w, ph_w); ph_w ^= 1;  // the tensor core is done with B0 (U1) and B2 (dU2) ...
         TS_MARK();  // weight-gradient MMAs done
         compute_barrier();                  // ... and so are the S2 epilogues of the other warps (ReLU mask read from B0)
-        store_tile<2>(B0g, ra, s_p, tid);
-        store_tile<2>(B2g, rb, 1.f, tid);
+        store_tile<ACT_PIECES>(B0g, ra, s_p, tid);
+        store_tile<ACT_PIECES>(B2g, rb, 1.f, tid);
         TS_MARK();  // tiles stored
         publish_tiles(bar_ready, tid);
         TS_MARK();  // published
@@ -240,7 +240,7 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
             const int rows_valid = (int)max((int64_t)0, min((int64_t)32, a.M - wrow0));
             warp_store_block(patch, dxt, a.dXt + wrow0 * D + ch * NCOL, rows_valid, lane, StoreIdentity());
         }
-        store_tile<2>(B0g, ra, 1.f, tid);
+        store_tile<ACT_PIECES>(B0g, ra, 1.f, tid);
 
         // ---------------- S0: hoisted feature_module_final ----------------
         TS_MARK();  // tiles stored
@@ -479,7 +479,7 @@ tc_embed_backward_kernel(const EmbBwdArgs a) {
             bsum1[0] += rc[it].x; bsum1[1] += rc[it].y; bsum1[2] += rc[it].z; bsum1[3] += rc[it].w;
         }
         store_tile<3>(B0g, ra, 1.f, tid);
-        store_tile<2>(B1g, rb, 1.f, tid);
+        store_tile<ACT_PIECES>(B1g, rb, 1.f, tid);
         if (two) store_tile<3>(B2g, rc, 1.f, tid);
         publish_tiles(bar_ready, tid);
         load_tile(ra, a.h1, row0, a.M, tid);
@@ -504,7 +504,7 @@ tc_embed_backward_kernel(const EmbBwdArgs a) {
             store_row(B0g, r_own, ch, v);
         }
         compute_barrier();  // every warp is done with its patch before B2 receives the h1 tile
-        store_tile<2>(B2g, ra, 1.f, tid);
+        store_tile<ACT_PIECES>(B2g, ra, 1.f, tid);
 
         // ---------------- E1 ----------------
         publish_tiles(bar_ready, tid);

@@ -115,10 +115,15 @@ class _GCNNFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, flat_params, model, dev_inputs):
         ctx.model, ctx.dev_inputs = model, dev_inputs
-        return model._forward(dev_inputs, save_activations=True)
+        out = model._forward(dev_inputs, save_activations=True)
+        ctx.stamp = model._activation_stamp()  # the workspace's activations are shared: a later forward overwrites them
+        return out
 
     @staticmethod
     def backward(ctx, d_scores):
+        if ctx.model._activation_stamp() != ctx.stamp:
+            raise RuntimeError("the activations of this forward pass were overwritten by a later call on the same model; "
+                               "run backward() before the next forward (or use loss_and_grads)")
         return ctx.model._backward(ctx.dev_inputs, d_scores.contiguous()), None, None
 
 
@@ -150,7 +155,8 @@ class GCNN:
                                  TensorSpec((), i32)), TensorSpec((), torch.bool)]  # model.py:218-226
 
         ws = C.c_void_p()
-        check(self._lib.gcnn_workspace_create(C.byref(ws)))
+        with torch.cuda.device(self.device):  # the workspace (streams, events, arena) lives on the model's device
+            check(self._lib.gcnn_workspace_create(C.byref(ws)))
         self._ws = ws
         self._prenorm_layers = self._make_prenorm_layers()
         self.call = self._call  # re-assignable like ``model.call = tf.function(model.call, ...)`` (model_trainer.py:144)
@@ -198,7 +204,10 @@ class GCNN:
     def _init_weights(self, seed):
         """Keras defaults of the reference: orthogonal kernels, zero biases (model.py:175), shift 0 / scale 1
         (model.py:334, 342)."""
-        gen = torch.Generator().manual_seed(int(seed) if seed is not None else torch.seed() % (2 ** 31))
+        # seed=None draws from torch's default generator (like the reference draws from the framework's global seed):
+        # reproducible under torch.manual_seed and without reseeding the caller's generator
+        gen = torch.Generator().manual_seed(int(seed) if seed is not None
+                                            else int(torch.randint(0, 2 ** 31 - 1, (1,)).item()))
         flat = torch.zeros(_lib.N_TRAINABLE)
         for name, shape, trainable, off in self._table:
             if trainable and name.endswith("kernel"):
@@ -244,7 +253,8 @@ class GCNN:
              self._to_device(var, f32), self._to_device(cut, f32), self._to_device(cut_ei, i32),
              self._to_device(cut_ef, f32)]
         # n_cons / n_vars / n_cuts: the totals the reference passes (model_trainer.py:259-263), or the per-sample
-        # vectors load_batch returns (utils.py:420-422) -- the latter let the edge kernels stage per-sample tables
+        # vectors load_batch returns (utils.py:420-422) -- the latter give the library the batch's block structure:
+        # per-sample gathered tables in shared memory and per-sample transposed layouts (csrc/edge_block.cu)
         counts = _sample_counts(n_cons, n_vars, n_cuts)
         n_cons, n_vars, n_cuts = (int(np.sum(_host(x))) for x in (n_cons, n_vars, n_cuts))
         if t[0].shape != (n_cons, CONS_FEATS) and not (n_cons == 0 and t[0].numel() == 0):
@@ -265,31 +275,43 @@ class GCNN:
         return b, t
 
     def reserve(self, batch: Batch, training: bool):
+        """Grow the workspace for a batch of these sizes.  Batches already staged with ``stage_host`` / ``stage_records``
+        survive the growth (the staging slots have their own allocation)."""
         check(self._lib.gcnn_workspace_reserve(self._ws, batch.n_cons, batch.n_vars, batch.n_cuts, batch.n_cons_edges,
                                                batch.n_cut_edges, int(training)))
 
     def set_option(self, name: str, value: int):
-        """Library options: "tensor_cores" (tcgen05 3xTF32 vs exact-fp32 SIMT dense layers), "streams"."""
+        """Library options (include/gcnn_b200.h): "tensor_cores", "streams", "blocks", ..."""
         check(self._lib.gcnn_set_option(self._ws, name.encode(), int(value)))
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _activation_stamp(self) -> int:
+        return int(self._lib.gcnn_activation_stamp(self._ws))
+
+    def _check_indices(self):
+        """TF-CPU raises InvalidArgument on an out-of-range gather index (model.py:564); here the kernels clamp and set
+        a sticky device word, read back (one stream synchronisation) when ``check_indices`` is on."""
+        if self.check_indices:
+            check(self._lib.gcnn_check(self._ws, self._stream()))
 
     # ---- forward / backward ----------------------------------------------------------------------------------------
     def _forward(self, dev_inputs, save_activations: bool):
         batch, _keep = dev_inputs
         self.reserve(batch, save_activations)
         scores = torch.empty(batch.n_cuts, dtype=torch.float32, device=self.device)
-        check(self._lib.gcnn_forward(self._ws, self.flat_params.data_ptr(), self.flat_prenorm.data_ptr(),
-                                     C.byref(batch), scores.data_ptr(), int(save_activations), self._stream()))
-        if self.check_indices:
-            check(self._lib.gcnn_check(self._ws, self._stream()))
+        with torch.cuda.device(self.device):
+            check(self._lib.gcnn_forward(self._ws, self.flat_params.data_ptr(), self.flat_prenorm.data_ptr(),
+                                         C.byref(batch), scores.data_ptr(), int(save_activations), self._stream()))
+            self._check_indices()
         return scores
 
     def _backward(self, dev_inputs, d_scores):
         batch, _keep = dev_inputs
-        check(self._lib.gcnn_backward(self._ws, self.flat_params.data_ptr(), self.flat_prenorm.data_ptr(),
-                                      C.byref(batch), d_scores.data_ptr(), self.flat_grads.data_ptr(), self._stream()))
+        with torch.cuda.device(self.device):
+            check(self._lib.gcnn_backward(self._ws, self.flat_params.data_ptr(), self.flat_prenorm.data_ptr(),
+                                          C.byref(batch), d_scores.data_ptr(), self.flat_grads.data_ptr(), self._stream()))
         return self.flat_grads.clone()
 
     def _first_armed(self):
@@ -331,21 +353,24 @@ class GCNN:
         self.reserve(batch, True)
         scores = torch.empty(batch.n_cuts, dtype=torch.float32, device=self.device)
         scale = (1.0 / max(batch.n_cuts, 1)) if seed_scale is None else float(seed_scale)
-        check(self._lib.gcnn_forward_backward(self._ws, self.flat_params.data_ptr(), self.flat_prenorm.data_ptr(),
-                                              C.byref(batch), targets.data_ptr(), scale, scores.data_ptr(),
-                                              self.flat_grads.data_ptr(),
-                                              (loss_out if loss_out is not None else self._loss_sum).data_ptr(),
-                                              self._stream()))
+        with torch.cuda.device(self.device):
+            check(self._lib.gcnn_forward_backward(self._ws, self.flat_params.data_ptr(), self.flat_prenorm.data_ptr(),
+                                                  C.byref(batch), targets.data_ptr(), scale, scores.data_ptr(),
+                                                  self.flat_grads.data_ptr(),
+                                                  (loss_out if loss_out is not None else self._loss_sum).data_ptr(),
+                                                  self._stream()))
+            self._check_indices()
         return (loss_out if loss_out is not None else self._loss_sum), scores
 
     def apply_gradients(self, lr: float, grad_divisor: torch.Tensor | None = None,
                         beta1=0.9, beta2=0.999, eps=1e-7):
         """Keras ``Adam.apply_gradients`` on the flat buffers (one launch instead of 46)."""
-        self.adam_step += 1
         div = grad_divisor.data_ptr() if grad_divisor is not None else None
-        check(self._lib.gcnn_adam_step(self.flat_params.data_ptr(), self.flat_grads.data_ptr(), self.adam_m.data_ptr(),
-                                       self.adam_v.data_ptr(), _lib.N_TRAINABLE, lr, beta1, beta2, eps, self.adam_step,
-                                       div, self._stream()))
+        with torch.cuda.device(self.device):
+            check(self._lib.gcnn_adam_step(self.flat_params.data_ptr(), self.flat_grads.data_ptr(),
+                                           self.adam_m.data_ptr(), self.adam_v.data_ptr(), _lib.N_TRAINABLE, lr, beta1,
+                                           beta2, eps, self.adam_step + 1, div, self._stream()))
+        self.adam_step += 1  # only a step that was enqueued counts (Adam's bias correction depends on it)
 
     def train_step(self, inputs, targets, lr: float):
         """One optimisation step on device-resident or host inputs; returns the mean loss as a device tensor."""
@@ -357,12 +382,13 @@ class GCNN:
         """End-to-end step from (pinned) host buffers: H2D copies, forward, MSE, backward, Adam, loss back to host."""
         b = host_batch.batch
         self.reserve(b, True)
-        self.adam_step += 1
         loss = C.c_float()
-        check(self._lib.gcnn_train_step_host(self._ws, self.flat_params.data_ptr(), self.flat_prenorm.data_ptr(),
-                                             self.adam_m.data_ptr(), self.adam_v.data_ptr(), C.byref(b),
-                                             host_batch.targets.data_ptr(), lr, self.adam_step, C.byref(loss),
-                                             self._stream()))
+        with torch.cuda.device(self.device):
+            check(self._lib.gcnn_train_step_host(self._ws, self.flat_params.data_ptr(), self.flat_prenorm.data_ptr(),
+                                                 self.adam_m.data_ptr(), self.adam_v.data_ptr(), C.byref(b),
+                                                 host_batch.targets.data_ptr(), lr, self.adam_step + 1, C.byref(loss),
+                                                 self._stream()))
+        self.adam_step += 1
         return float(loss.value)
 
     # ---- prefetching host path: batch i + 1 is copied in while the step on batch i runs (model_trainer.py:153) ------
@@ -371,7 +397,8 @@ class GCNN:
         b = host_batch.batch
         self.reserve(b, training)
         tgt = host_batch.targets.data_ptr() if training else None
-        check(self._lib.gcnn_stage_host_batch(self._ws, slot, C.byref(b), tgt))
+        with torch.cuda.device(self.device):
+            check(self._lib.gcnn_stage_host_batch(self._ws, slot, C.byref(b), tgt))
         self._staged[slot] = host_batch  # keeps the pinned buffers alive until the slot is consumed
 
     def stage_records(self, reader, ids, slot: int, training: bool = True) -> "StagedRecords":
@@ -379,53 +406,61 @@ class GCNN:
         to the device as they are and one kernel assembles the batch there (the device-side ``utils.load_batch``,
         utils.py:339-426).  Returns immediately; use the slot like one filled by ``stage_host``."""
         nc, nv, nk, ec, ek = reader.totals(ids)
-        check(self._lib.gcnn_workspace_reserve(self._ws, nc, nv, nk, ec, ek, int(training)))
         ptrs = reader.pointers(ids)
         h2d = C.c_int64()
-        check(self._lib.gcnn_stage_records(self._ws, slot, ptrs.ctypes.data, ptrs.shape[0], C.byref(h2d)))
+        with torch.cuda.device(self.device):
+            check(self._lib.gcnn_workspace_reserve(self._ws, nc, nv, nk, ec, ek, int(training)))
+            check(self._lib.gcnn_stage_records(self._ws, slot, ptrs.ctypes.data, ptrs.shape[0], C.byref(h2d)))
         staged = StagedRecords(reader, nk, int(ptrs.shape[0]), int(h2d.value))
         self._staged[slot] = staged  # keeps the pinned shard alive until the slot is consumed
         return staged
 
     def train_step_staged(self, slot: int, lr: float) -> float:
         """Optimisation step on the batch staged in ``slot``; returns the mean loss (host float)."""
-        self.adam_step += 1
         loss = C.c_float()
-        check(self._lib.gcnn_train_step_staged(self._ws, slot, self.flat_params.data_ptr(), self.flat_prenorm.data_ptr(),
-                                               self.adam_m.data_ptr(), self.adam_v.data_ptr(), lr, self.adam_step,
-                                               C.byref(loss), self._stream()))
+        with torch.cuda.device(self.device):
+            check(self._lib.gcnn_train_step_staged(self._ws, slot, self.flat_params.data_ptr(),
+                                                   self.flat_prenorm.data_ptr(), self.adam_m.data_ptr(),
+                                                   self.adam_v.data_ptr(), lr, self.adam_step + 1, C.byref(loss),
+                                                   self._stream()))
+        self.adam_step += 1
         return float(loss.value)
 
     def train_step_staged_async(self, slot: int, lr: float):
         """Enqueue the optimisation step on the batch staged in ``slot`` without waiting for it; its mean loss is read
         later with ``train_step_result(slot)`` (e.g. after the next step has been enqueued)."""
+        with torch.cuda.device(self.device):
+            check(self._lib.gcnn_train_step_staged_async(self._ws, slot, self.flat_params.data_ptr(),
+                                                         self.flat_prenorm.data_ptr(), self.adam_m.data_ptr(),
+                                                         self.adam_v.data_ptr(), lr, self.adam_step + 1, self._stream()))
         self.adam_step += 1
-        check(self._lib.gcnn_train_step_staged_async(self._ws, slot, self.flat_params.data_ptr(),
-                                                     self.flat_prenorm.data_ptr(), self.adam_m.data_ptr(),
-                                                     self.adam_v.data_ptr(), lr, self.adam_step, self._stream()))
 
     def train_step_result(self, slot: int) -> float:
         loss = C.c_float()
-        check(self._lib.gcnn_train_step_result(self._ws, slot, C.byref(loss), self._stream()))
+        with torch.cuda.device(self.device):
+            check(self._lib.gcnn_train_step_result(self._ws, slot, C.byref(loss), self._stream()))
         return float(loss.value)
 
     def loss_and_grads_staged(self, slot: int, seed_scale: float | None = None, loss_out: torch.Tensor | None = None):
         """``loss_and_grads`` on the batch staged in ``slot`` (data-parallel trainer).  Returns (loss_sum, n_cuts)."""
         batch, tgt = Batch(), C.c_void_p()
-        check(self._lib.gcnn_staged_batch(self._ws, slot, C.byref(batch), C.byref(tgt), self._stream()))
-        scale = (1.0 / max(batch.n_cuts, 1)) if seed_scale is None else float(seed_scale)
-        check(self._lib.gcnn_forward_backward(self._ws, self.flat_params.data_ptr(), self.flat_prenorm.data_ptr(),
-                                              C.byref(batch), tgt, scale, None, self.flat_grads.data_ptr(),
-                                              (loss_out if loss_out is not None else self._loss_sum).data_ptr(),
-                                              self._stream()))
-        check(self._lib.gcnn_release_staged(self._ws, slot, self._stream()))
+        with torch.cuda.device(self.device):
+            check(self._lib.gcnn_staged_batch(self._ws, slot, C.byref(batch), C.byref(tgt), self._stream()))
+            scale = (1.0 / max(batch.n_cuts, 1)) if seed_scale is None else float(seed_scale)
+            check(self._lib.gcnn_forward_backward(self._ws, self.flat_params.data_ptr(), self.flat_prenorm.data_ptr(),
+                                                  C.byref(batch), tgt, scale, None, self.flat_grads.data_ptr(),
+                                                  (loss_out if loss_out is not None else self._loss_sum).data_ptr(),
+                                                  self._stream()))
+            check(self._lib.gcnn_release_staged(self._ws, slot, self._stream()))
+            self._check_indices()
         return (loss_out if loss_out is not None else self._loss_sum), int(batch.n_cuts)
 
     def score_staged(self, slot: int) -> np.ndarray:
         """Cut scores of the batch staged in ``slot`` (inference), as a host array."""
         out = self._staged[slot].scores
-        check(self._lib.gcnn_score_staged(self._ws, slot, self.flat_params.data_ptr(), self.flat_prenorm.data_ptr(),
-                                          out.data_ptr(), self._stream()))
+        with torch.cuda.device(self.device):
+            check(self._lib.gcnn_score_staged(self._ws, slot, self.flat_params.data_ptr(), self.flat_prenorm.data_ptr(),
+                                              out.data_ptr(), self._stream()))
         return out.numpy()
 
     def score_host(self, host_batch: "HostBatch") -> np.ndarray:
@@ -434,8 +469,9 @@ class GCNN:
         b = host_batch.batch
         self.reserve(b, False)
         out = host_batch.scores
-        check(self._lib.gcnn_score_host(self._ws, self.flat_params.data_ptr(), self.flat_prenorm.data_ptr(),
-                                        C.byref(b), out.data_ptr(), self._stream()))
+        with torch.cuda.device(self.device):
+            check(self._lib.gcnn_score_host(self._ws, self.flat_params.data_ptr(), self.flat_prenorm.data_ptr(),
+                                            C.byref(b), out.data_ptr(), self._stream()))
         return out.numpy()
 
     # ---- pre-norm pretraining (model.py:69-133) -------------------------------------------------------------------
@@ -456,8 +492,9 @@ class GCNN:
         mean = (C.c_double * 64)()
         var = (C.c_double * 64)()
         count = C.c_double()
-        check(self._lib.gcnn_prenorm_stats(self._ws, self.flat_params.data_ptr(), self.flat_prenorm.data_ptr(),
-                                           C.byref(batch), layer.index, mean, var, C.byref(count), self._stream()))
+        with torch.cuda.device(self.device):
+            check(self._lib.gcnn_prenorm_stats(self._ws, self.flat_params.data_ptr(), self.flat_prenorm.data_ptr(),
+                                               C.byref(batch), layer.index, mean, var, C.byref(count), self._stream()))
         n = layer.n_units
         return np.array(mean[:n]), np.array(var[:n]), count.value
 

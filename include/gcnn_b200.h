@@ -64,8 +64,8 @@ typedef struct gcnn_batch {
     /* Optional per-sample node counts of the offset-concatenated batch, HOST pointers to n_samples int32 each (the
      * n_cons / n_vars / n_cuts vectors utils.load_batch returns, utils.py:420-422); NULL / 0 when unknown.  They are a
      * promise that sample s's edges only touch sample s's nodes (block-diagonal batch, utils.py:403-407); with it the
-     * edge kernels stage each sample's source table in shared memory.  A violated promise is reported as
-     * GCNN_INVALID at the next gcnn_check. */
+     * edge kernels stage each sample's gathered tables in shared memory and the by-variable layout is built per sample
+     * (csrc/edge_block.cu).  A violated promise is reported as GCNN_INVALID at the next gcnn_check. */
     const int32_t* sample_n_cons;
     const int32_t* sample_n_vars;
     const int32_t* sample_n_cuts;
@@ -101,9 +101,10 @@ int gcnn_workspace_destroy(gcnn_workspace* ws);
 int gcnn_workspace_reserve(gcnn_workspace* ws, int64_t n_cons, int64_t n_vars, int64_t n_cuts,
                            int64_t n_cons_edges, int64_t n_cut_edges, int training);
 int64_t gcnn_workspace_bytes(const gcnn_workspace* ws);
-/* Options: "tensor_cores" (1 = tcgen05 3xTF32 dense layers [default], 0 = exact-fp32 SIMT dense layers; env GCNN_TC),
+/* Options: "tensor_cores" (1 = tcgen05 dense layers [default], 0 = exact-fp32 SIMT dense layers; env GCNN_TC),
  * "streams" (1 = independent kernels on auxiliary streams [default], 0 = everything on the caller's stream; env
- * GCNN_STREAMS).  Takes effect from the next call. */
+ * GCNN_STREAMS), "blocks" (1 = use the batch's per-sample counts: shared-memory block edge kernels and per-sample
+ * transposed layouts [default], 0 = generic kernels; env GCNN_BLOCKS).  Takes effect from the next call. */
 int gcnn_set_option(gcnn_workspace* ws, const char* name, int value);
 /* Synchronise `stream` and report deferred errors (GCNN_INVALID if any edge index was out of range). */
 int gcnn_check(gcnn_workspace* ws, void* stream);
@@ -114,6 +115,13 @@ int gcnn_check(gcnn_workspace* ws, void* stream);
  *      skip the sort on the device. */
 int gcnn_build_csr(gcnn_workspace* ws, int which, const int32_t* edge_inds, const float* edge_feats, int64_t n_edges,
                    int64_t n_left, int64_t n_vars, int need_transposed, void* stream);
+/* The same two layouts for a block-diagonal list whose row 0 is sorted (every batch the reference's loader produces):
+ * sample_n_left / sample_n_vars are HOST vectors of n_samples per-sample node counts (utils.py:420-422).  The
+ * by-variable layout is then one CTA-local stable counting sort per sample (one launch) instead of the device-wide radix
+ * sort -- same output, bit for bit.  GCNN_INVALID when the counts do not add up or a sample is too large. */
+int gcnn_build_csr_blocks(gcnn_workspace* ws, int which, const int32_t* edge_inds, const float* edge_feats,
+                          int64_t n_edges, int64_t n_left, int64_t n_vars, const int32_t* sample_n_left,
+                          const int32_t* sample_n_vars, int64_t n_samples, void* stream);
 /* Copy the built layout to caller device buffers (tests): side 0 = grouped by left node, 1 = grouped by variable.
  * ptr [n+1], other [E] (index of the opposite endpoint), val [E], perm [E] (original edge id).  NULLs are skipped. */
 int gcnn_csr_export(gcnn_workspace* ws, int which, int side, int32_t* ptr, int32_t* other, float* val, int32_t* perm,
@@ -127,6 +135,11 @@ int gcnn_forward(gcnn_workspace* ws, const float* params, const float* prenorm, 
  * not accumulated).  Must follow gcnn_forward(save_activations=1) on the same workspace and batch. */
 int gcnn_backward(gcnn_workspace* ws, const float* params, const float* prenorm, const gcnn_batch* batch,
                   const float* d_scores, float* grads_out, void* stream);
+/* Generation of the activations kept by the last gcnn_forward(save_activations=1) / gcnn_forward_backward on this
+ * workspace, or -1 when none are kept.  A caller that separates forward and backward (an autograd bridge) records the
+ * stamp after its forward and must find the same value before calling gcnn_backward: any later forward on the workspace
+ * overwrites the shared activations. */
+int64_t gcnn_activation_stamp(const gcnn_workspace* ws);
 /* MeanSquaredError + its gradient seed (model_trainer.py:271): d_scores = 2 (p - y) * scale, loss_sum_out[0] =
  * sum (y - p)^2 (device scalar).  scale = 1/n for the single-process mean; 1 for data-parallel (see adam). */
 int gcnn_mse_seed(const float* scores, const float* targets, int64_t n, float scale, float* d_scores,
