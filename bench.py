@@ -35,6 +35,22 @@ METRIC, UNIT = "gcnn_train_graphs_per_s", "graphs/s"
 _REAL_STDOUT = None
 
 
+def workload_name(graphs: int) -> str:
+    """The same string on both arms (`config.workload`): BASELINE config 2 per GPU when graphs == 32."""
+    return (f"setcov (500x1000, 25k nnz, 64 cuts of 100 nnz) x{graphs} graphs per GPU per step, "
+            f"train step = CSR build + fwd + MSE + bwd + Adam")
+
+
+def model_bytes(nc, nv, nk, ec, ek):
+    """algorithmic bytes of one whole-model forward (B_model); a training step is 3 x this."""
+    emb = 16 * nc + 56 * nv + 24 * nk + 4 * ec + 4 * ek + 256 * (nc + nv + nk)
+    convs = 0
+    for n_l, n_t, e in ((nc, nc, ec), (nc, nv, ec), (nk, nk, ek)):
+        b_f = 256 * (n_l + nv + n_t) + 8 * e + 4 * (n_t + 1)
+        convs += 512 * (n_l + nv) + b_f + 768 * n_t
+    return emb + convs + 260 * nk
+
+
 def emit(line: dict):
     out = _REAL_STDOUT or sys.stdout
     out.write(json.dumps(line) + "\n")
@@ -134,7 +150,7 @@ def run_reference(args):
     batches = make_batches(2, graphs, seed0=0)
     model = orc.OracleGCNN(orc.init_params(seed=12345, dtype=torch.float32, identity_prenorm=True), dtype=torch.float32)
     state = orc.AdamState()
-    steps, warmup = max(1, args.steps), max(1, min(args.warmup, 2))
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
     for i in range(warmup):
         orc.train_step(model, state, batching.model_inputs(batches[i % 2]), batches[i % 2][10], 1e-4)
     t0 = time.perf_counter()
@@ -150,7 +166,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
             "warmup": warmup, "ms_per_step": 1e3 * dt / done, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"setcov x{graphs} graphs per step, train step on host CPU cores"},
+            "config": {"workload": workload_name(graphs), "graphs_per_step": graphs,
+                       "where": "host CPU cores (torch-CPU restatement of the reference's TF ops)"},
             "edge_messages_per_s": value * SETCOV_MSGS_PER_GRAPH,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                              "sample": sample},
@@ -183,35 +200,24 @@ def cpu_baseline(model, batch, graphs, budget_s=20.0):
                       f"model.py incl. per-edge Dense and Adam), {1e3 * dt / n:.0f} ms/step"}
 
 
-def run_b200(args):
+def measure_training(model, trainer, graphs, K, W, world, rank, dev, detail: bool, n_rot: int = 4, seed_base: int = 0):
+    """K timed training steps on `graphs` setcov graphs per GPU: device-resident (`value`), per-kernel-class pass
+    (`detail`), host-fed (`e2e`) and record-fed (`e2e_records`) loops.  Returns a dict (identical on every rank)."""
     import torch
     import torch.distributed as dist
-    from gcnn_cut_selector_b200 import GCNN, DataParallelTrainer, HostBatch, batching
+    from gcnn_cut_selector_b200 import HostBatch, batching
+    from gcnn_cut_selector_b200._lib import check
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    graphs, K, W = args.graphs_per_gpu, args.steps, max(3, args.warmup)
     lr = 1e-4
-
-    n_rot = 4
-    sample_sets = make_sample_sets(n_rot, graphs, seed0=10_000 * rank)
+    sample_sets = make_sample_sets(n_rot, graphs, seed0=seed_base + 10_000 * rank)
     batches = [batching.concat_samples(samples) for samples in sample_sets]
-    model = GCNN(device=dev, seed=0)
-    model.check_indices = False  # no per-step stream sync in the timed loop; checked once after it
-    trainer = DataParallelTrainer(model, lr) if world > 1 else None
-    if trainer:
-        trainer.broadcast_parameters()
     host = [HostBatch(b) for b in batches]
     # the loader's per-sample count vectors travel with the batch (utils.py:420-422)
     dev_inputs = [model.prepare_inputs(batching.model_inputs(b, per_sample_counts=True)) for b in batches]
     dev_targets = [torch.from_numpy(b[10]).to(dev) for b in batches]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     lib = model._lib
+    local = dev.index
 
     def step(i):
         j = i % n_rot
@@ -225,6 +231,12 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     for i in range(W):
         step(i)
@@ -244,69 +256,47 @@ def run_b200(args):
     barrier()
     launches = lib.gcnn_kernel_launches() - launches0
     clocks = sampler.stop()
-    total_ms = sum(a.elapsed_time(b) for a, b in ev)
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    from gcnn_cut_selector_b200._lib import check
+    total_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev))
     check(lib.gcnn_check(model._ws, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    out = {"graphs_per_gpu": graphs, "ms_per_step": total_ms / K, "value": graphs * world * K / (total_ms * 1e-3),
+           "launches": launches, "clocks": clocks, "h2d_bytes_per_step": host[0].h2d_bytes}
 
     # ---- per-kernel-class CUDA-event timing, same K steps again (events around every launch perturb a launch-bound
     #      step, so this pass is separate from the one `value` comes from) -------------------------------------------
-    ncls = lib.gcnn_profile_num_classes()
-    ms, ln, by = (C.c_double * ncls)(), (C.c_int64 * ncls)(), (C.c_double * ncls)()
-    barrier()
-    model.set_option("streams", 0)  # serialise so every event pair brackets exactly one kernel class
-    lib.gcnn_profile_begin()
-    for i in range(K):
-        flush.fill_(i & 0xFF)
-        step(W + i)
-    check(lib.gcnn_profile_end(ms, ln, by, ncls))
-    model.set_option("streams", 1)
-    peak, peak_src = measured_peak_gbs()
-    classes = []
-    for c in range(ncls):
-        if ln[c] == 0:
-            continue
-        gbs = by[c] / (ms[c] * 1e-3) / 1e9 if ms[c] > 0 else 0.0
-        classes.append({"kernel": lib.gcnn_profile_class_name(c).decode(), "launches_per_step": ln[c] / K,
-                        "ms_per_step": ms[c] / K, "algorithmic_mb_per_step": by[c] / K / 1e6,
-                        "achieved_gbs": gbs, "frac": gbs / peak})
-    kernel_ms = sum(c["ms_per_step"] for c in classes)
-    for c in classes:
-        c["share_of_kernel_time"] = c["ms_per_step"] / kernel_ms if kernel_ms else 0.0
-    top = max(classes, key=lambda c: c["ms_per_step"])
-    # DRAM traffic per launch of the same kernel class from the committed `ncu --set full` capture of one whole step
-    # (profiles/r1_step_traffic.json, made by scripts/ncu_step_summary.py; never measured under the profiler here)
-    traffic = None
-    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_step_traffic.json")
-    if os.path.exists(tpath) and graphs == 32:
-        traffic = json.load(open(tpath)).get(top["kernel"], {}).get("dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": top["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": top["frac"], "traffic": traffic,
-                "algorithmic_bytes_per_launch": top["algorithmic_mb_per_step"] * 1e6 / top["launches_per_step"],
-                "peak_source": peak_src,
-                "bytes": "algorithmic bytes per launch (DESIGN.md section 4) / CUDA-event time per launch, "
-                         "events on the launch stream, separate pass of the same K steps"}
-    seg = [c for c in classes if c["kernel"] in ("edge_forward", "edge_backward")]
-    step_bytes = sum(c["algorithmic_mb_per_step"] for c in classes) * 1e6
-    step_roof = {"algorithmic_mb_per_step": step_bytes / 1e6,
-                 "achieved_gbs": step_bytes / (total_ms / K * 1e-3) / 1e9,
-                 "frac": step_bytes / (total_ms / K * 1e-3) / 1e9 / peak}
+    if detail:
+        ncls = lib.gcnn_profile_num_classes()
+        ms, ln, by = (C.c_double * ncls)(), (C.c_int64 * ncls)(), (C.c_double * ncls)()
+        barrier()
+        model.set_option("streams", 0)  # serialise so every event pair brackets exactly one kernel class
+        lib.gcnn_profile_begin()
+        for i in range(K):
+            flush.fill_(i & 0xFF)
+            step(W + i)
+        check(lib.gcnn_profile_end(ms, ln, by, ncls))
+        model.set_option("streams", 1)
+        peak, _ = measured_peak_gbs()
+        classes = []
+        for c in range(ncls):
+            if ln[c] == 0:
+                continue
+            gbs = by[c] / (ms[c] * 1e-3) / 1e9 if ms[c] > 0 else 0.0
+            classes.append({"kernel": lib.gcnn_profile_class_name(c).decode(), "launches_per_step": ln[c] / K,
+                            "ms_per_step": ms[c] / K, "algorithmic_mb_per_step": by[c] / K / 1e6,
+                            "achieved_gbs": gbs, "frac": gbs / peak})
+        kernel_ms = sum(c["ms_per_step"] for c in classes)
+        for c in classes:
+            c["share_of_kernel_time"] = c["ms_per_step"] / kernel_ms if kernel_ms else 0.0
+        out["kernels"] = classes
 
     # ---- end to end through the host-buffer API: H2D of every input and D2H of the loss inside the timed region.
     #      One batch is kept in flight, like the reference's loader (tf.data prefetch(1), model_trainer.py:153): step i
-    #      first enqueues the copies of batch i + 1 into the other staging slot, then runs on batch i and reads its loss.
-    def e2e_stage(i):
-        model.stage_host(host[i % n_rot], i & 1)
-
-    # The loss of step i is read back after step i + 1 has been enqueued (it lands in pinned host memory on its own),
-    # so the host prepares work while the GPU runs: at most two steps are in flight.
+    #      first enqueues the copies of batch i + 1 into the other staging slot, then runs on batch i; the loss of step
+    #      i is read back after step i + 1 has been enqueued (it lands in pinned host memory on its own).
     pending = []
+    stager = {"fn": lambda i: model.stage_host(host[i % n_rot], i & 1)}
 
     def e2e_step(i):
-        e2e_stage(i + 1)
+        stager["fn"](i + 1)
         if trainer:
             pending.append(trainer.step_staged(i & 1).clone())
             return float(pending.pop(0).item()) if len(pending) > 1 else None
@@ -320,7 +310,7 @@ def run_b200(args):
             _ = float(p.item()) if trainer else model.train_step_result(p)
 
     def e2e_run():
-        e2e_stage(0)
+        stager["fn"](0)
         for i in range(W):
             e2e_step(i)
         e2e_drain()
@@ -330,14 +320,13 @@ def run_b200(args):
             e2e_step(W + i)
         e2e_drain()
         barrier()
-        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return max_over_ranks(time.perf_counter() - t0)
 
     e2e_s = e2e_run()
+    out["e2e"] = {"value": graphs * world * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": host[0].h2d_bytes,
+                  "d2h_bytes_per_step": 4, "ms_per_step": 1e3 * e2e_s / K}
 
-    # ---- the same loop fed from packed sample records (gcnn_cut_selector_b200/shards.py): every step copies the 32
+    # ---- the same loop fed from packed sample records (gcnn_cut_selector_b200/shards.py): every step copies the
     #      records of its batch from the pinned shard and the batch is assembled ON THE DEVICE (concatenation, index
     #      offsets, casts of utils.load_batch, utils.py:395-423) inside the timed region; sorted edge lists travel as
     #      row pointers.  Reported next to `e2e` as `e2e_records`.
@@ -349,43 +338,193 @@ def run_b200(args):
         reader = shards.ShardReader(shard_path)
     record_ids = [list(range(b * graphs, (b + 1) * graphs)) for b in range(n_rot)]
     record_h2d = []
+    stager["fn"] = lambda i: record_h2d.append(model.stage_records(reader, record_ids[i % n_rot], i & 1).h2d_bytes)
+    rec_s = e2e_run()
+    out["e2e_records"] = {"value": graphs * world * K / rec_s, "unit": UNIT, "h2d_bytes_per_step": record_h2d[-1],
+                          "d2h_bytes_per_step": 4, "ms_per_step": 1e3 * rec_s / K}
+    out["_batch0"] = batches[0]
+    return out
 
-    def e2e_stage(i):  # noqa: F811 -- e2e_step / e2e_run pick up the rebound stager
-        record_h2d.append(model.stage_records(reader, record_ids[i % n_rot], i & 1).h2d_bytes)
 
-    e2e_records_s = e2e_run()
+def time_device(fn, reps, flush=None):
+    """Mean CUDA-event milliseconds of `fn` over `reps` calls on the current stream (L2 flushed between calls)."""
+    import torch
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    total = 0.0
+    for i in range(reps):
+        if flush is not None:
+            flush.fill_(i & 0xFF)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        total += e0.elapsed_time(e1)
+    return total / reps
+
+
+def measure_other_configs(model, dev, reps: int = 30):
+    """BASELINE configs 1, 3 and 5 on one GPU (parity for the same shapes: tests/test_gpu_parity.py)."""
+    import torch
+    from gcnn_cut_selector_b200 import HostBatch, batching, synth
+    peak, _ = measured_peak_gbs()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out = {}
+
+    def sizes(batch):
+        return (int(np.sum(batch[7])), int(np.sum(batch[8])), int(np.sum(batch[9])), batch[1].shape[1], batch[5].shape[1])
+
+    def host_latency(fn, n):
+        lat = []
+        for _ in range(5):
+            fn()
+        for _ in range(n):
+            t0 = time.perf_counter()
+            fn()
+            lat.append(time.perf_counter() - t0)
+        return 1e3 * float(np.median(lat)), 1e3 * float(np.percentile(lat, 95))
+
+    # config 1: forward + backward (+ Adam) on ONE setcov sample -- launch / latency bound, not bandwidth bound
+    batch = batching.concat_samples(synth.make_samples("setcov", 1, seed0=77))
+    nc, nv, nk, ec, ek = sizes(batch)
+    inp = model.prepare_inputs(batching.model_inputs(batch, per_sample_counts=True))
+    tgt = torch.from_numpy(batch[10]).to(dev)
+    hb = HostBatch(batch)
+
+    def train_dev():
+        model.loss_and_grads(inp, tgt)
+        model.apply_gradients(1e-4)
+
+    ms = time_device(train_dev, reps, flush)
+    p50, p95 = host_latency(lambda: model.train_step_host(hb, 1e-4), reps)
+    b_step = 3 * model_bytes(nc, nv, nk, ec, ek)
+    out["config1"] = {"workload": "one setcov sample (500x1000, 25k nnz, 64 cuts), train step", "device_ms": ms,
+                      "graphs_per_s": 1e3 / ms, "host_in_host_out_ms_p50": p50, "host_in_host_out_ms_p95": p95,
+                      "algorithmic_mb": b_step / 1e6, "hbm_frac": b_step / (ms * 1e-3) / 1e9 / peak,
+                      "bound": "launch latency (about 40 dependent kernels of a few microseconds each)"}
+
+    # config 3: inference cut scoring on the other three problem classes, batch 1 (plugin path,
+    # model_benchmarker.py:106) and batch 4 (model_tester.py:51)
+    c3 = []
+    for shape in ("combauc", "capfac", "indset"):
+        for n in (1, 4):
+            batch = batching.concat_samples(synth.make_samples(shape, n, seed0=300))
+            nc, nv, nk, ec, ek = sizes(batch)
+            inp = model.prepare_inputs(batching.model_inputs(batch, per_sample_counts=True))
+            hb = HostBatch(batch)
+            with torch.no_grad():
+                ms = time_device(lambda: model._forward(inp, save_activations=False), reps, flush)
+            p50, p95 = host_latency(lambda: model.score_host(hb), reps)
+            c3.append({"shape": shape, "graphs": n, "n_cons": nc, "n_vars": nv, "n_cuts": nk, "edges": ec + ek,
+                       "device_forward_ms": ms, "cuts_per_s": nk / (ms * 1e-3),
+                       "edge_messages_per_s": (2 * ec + ek) / (ms * 1e-3),
+                       "score_host_ms_p50": p50, "score_host_ms_p95": p95})
+    out["config3"] = {"workload": "combauc / capfac / indset shapes, inference cut scoring, batch 1 and 4", "cases": c3}
+
+    # config 5: one MIPLIB-scale graph, forward scoring; whole-model algorithmic bytes (SURVEY 8d: 686 MB) / time
+    batch = batching.concat_samples([synth.make_sample("miplib", 5)])
+    nc, nv, nk, ec, ek = sizes(batch)
+    inp = model.prepare_inputs(batching.model_inputs(batch))
+    with torch.no_grad():
+        ms = time_device(lambda: model._forward(inp, save_activations=False), max(10, reps // 3), flush)
+    b_model = model_bytes(nc, nv, nk, ec, ek)
+    out["config5"] = {"workload": "MIPLIB-scale graph (100k x 100k, 1M + 0.5M edges, 5k cuts), forward scoring",
+                      "device_forward_ms": ms, "graphs_per_s": 1e3 / ms, "cuts_per_s": nk / (ms * 1e-3),
+                      "edge_messages_per_s": (2 * ec + ek) / (ms * 1e-3),
+                      "roofline": {"bound": "hbm", "algorithmic_mb": b_model / 1e6,
+                                   "achieved": b_model / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                   "frac": b_model / (ms * 1e-3) / 1e9 / peak}}
+    return out
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from gcnn_cut_selector_b200 import GCNN, DataParallelTrainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    graphs, K, W = args.graphs_per_gpu, args.steps, max(3, args.warmup)
+    lr = 1e-4
+    model = GCNN(device=dev, seed=0)
+    model.check_indices = False  # no per-step stream sync in the timed loop; checked once after it
+    trainer = DataParallelTrainer(model, lr) if world > 1 else None
+    if trainer:
+        trainer.broadcast_parameters()
+
+    main_res = measure_training(model, trainer, graphs, K, W, world, rank, dev, detail=True)
+    # BASELINE config 4: 1,024 graphs per step over the N GPUs of the box (512 / 256 / 128 per GPU)
+    config4 = None
+    if world > 1 and not args.no_extra_configs and 1024 % world == 0:
+        r4 = measure_training(model, trainer, 1024 // world, max(5, K // 4), 3, world, rank, dev, detail=False, n_rot=2,
+                              seed_base=777)
+        config4 = {"workload": "1,024 setcov graphs per step, data parallel", "graphs_per_gpu": 1024 // world,
+                   "value": r4["value"], "unit": UNIT, "ms_per_step": r4["ms_per_step"],
+                   "edge_messages_per_s": r4["value"] * SETCOV_MSGS_PER_GRAPH, "e2e": r4["e2e"],
+                   "e2e_records": r4["e2e_records"], "steps": max(5, K // 4)}
+    others = None
+    if world == 1 and not args.no_extra_configs:
+        others = measure_other_configs(model, dev)
 
     if rank == 0:
-        value = graphs * world * K / (total_ms * 1e-3)
+        peak, peak_src = measured_peak_gbs()
+        classes = main_res["kernels"]
+        top = max(classes, key=lambda c: c["ms_per_step"])
+        # DRAM traffic per launch of the same kernel class from the committed `ncu --set full` capture of one whole step
+        # (profiles/r2_step_traffic.json, made by scripts/ncu_step_summary.py; never measured under the profiler here)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r2_step_traffic.json")
+        if os.path.exists(tpath) and graphs == 32:
+            traffic = json.load(open(tpath)).get(top["kernel"], {}).get("dram_bytes_per_launch")
+        roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": top["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": top["frac"], "traffic": traffic,
+                    "algorithmic_bytes_per_launch": top["algorithmic_mb_per_step"] * 1e6 / top["launches_per_step"],
+                    "peak_source": peak_src,
+                    "bytes": "algorithmic bytes per launch (DESIGN.md section 4) / CUDA-event time per launch, "
+                             "events on the launch stream, separate pass of the same K steps"}
+        seg = [c for c in classes if c["kernel"] in ("edge_forward", "edge_backward")]
+        step_bytes = 3 * model_bytes(16_000, 32_000, 2_048, 800_000, 204_800) / 32 * graphs  # SURVEY 8d: B_step
+        step_ms = main_res["ms_per_step"]
+        step_roof = {"algorithmic_mb_per_step": step_bytes / 1e6, "achieved_gbs": step_bytes / (step_ms * 1e-3) / 1e9,
+                     "frac": step_bytes / (step_ms * 1e-3) / 1e9 / peak,
+                     "bytes": "SURVEY.md 8d B_step = 3 x B_model per graph (17.4 MB for a setcov sample)"}
+        value = main_res["value"]
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"setcov (500x1000, 25k nnz, 64 cuts) x{graphs} graphs per GPU per step, "
-                                       f"train step = CSR build + fwd + MSE + bwd + Adam"
-                                       + (" + NCCL all-reduce of the flat gradient" if world > 1 else ""),
+                "config": {"workload": workload_name(graphs),
+                           "collective": "all-reduce of the flat gradient over NVLink" if world > 1 else None,
                            "graphs_per_step": graphs * world, "parallelism": f"dp{world}",
                            "l2": "256 MB flush between timed steps; 4 rotating batches"},
                 "edge_messages_per_s": value * SETCOV_MSGS_PER_GRAPH,
-                "clocks": clocks,
-                "e2e": {"value": graphs * world * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": host[0].h2d_bytes,
-                        "d2h_bytes_per_step": 4, "ms_per_step": 1e3 * e2e_s / K,
-                        "pipeline": "copies of batch i+1 overlap the step on batch i (two staging slots) and the loss "
-                                    "of step i is read after step i+1 is enqueued; every step copies one full batch "
-                                    "from pinned host memory and reads back one loss"},
-                "e2e_records": {"value": graphs * world * K / e2e_records_s, "unit": UNIT,
-                                "h2d_bytes_per_step": record_h2d[-1], "d2h_bytes_per_step": 4,
-                                "ms_per_step": 1e3 * e2e_records_s / K,
-                                "input": "the same loop fed with packed sample records (one per graph) from a pinned "
-                                         "shard; the batch is assembled on the device inside the timed region "
-                                         "(utils.load_batch's concatenation, index offsets and casts, utils.py:395-423); "
-                                         "sorted edge lists travel as row pointers"},
-                "gpu_launches": launches,
+                "clocks": main_res["clocks"],
+                "e2e": dict(main_res["e2e"],
+                            pipeline="copies of batch i+1 overlap the step on batch i (two staging slots) and the loss "
+                                     "of step i is read after step i+1 is enqueued; every step copies one full batch "
+                                     "from pinned host memory and reads back one loss"),
+                "e2e_records": dict(main_res["e2e_records"],
+                                    input="the same loop fed with packed sample records (one per graph) from a pinned "
+                                          "shard; the batch is assembled on the device inside the timed region "
+                                          "(utils.load_batch's concatenation, index offsets and casts, utils.py:395-423); "
+                                          "sorted edge lists travel as row pointers"),
+                "gpu_launches": main_res["launches"],
                 "roofline": roofline,
                 "roofline_segmented_reduction": seg,
                 "roofline_step": step_roof,
                 "kernels": classes}
+        if config4:
+            line["config4"] = config4
+        if others:
+            line["configs"] = others
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(model, batches[0], graphs)
+            line["cpu_baseline"] = cpu_baseline(model, main_res["_batch0"], graphs)
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -399,6 +538,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--graphs-per-gpu", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip BASELINE configs 1/3/5 (N = 1) and 4 (N > 1)")
     args = ap.parse_args()
     # Libraries write to file descriptor 1 on their own (NCCL prints its version banner at init): keep the real stdout
     # for the ONE JSON line and send everything else to stderr.

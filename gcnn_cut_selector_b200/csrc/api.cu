@@ -225,6 +225,8 @@ static size_t carve(gcnn_workspace* ws, char* base, const Caps& c) {
             ls[s]->other = cv.take<int32_t>(E);
             ls[s]->val = cv.take<float>(E);
             ls[s]->perm = cv.take<int32_t>(E);
+            ls[s]->pair_buf = cv.take<int2>(E + 64);  // (the block kernels copy whole 16-pair chunks: up to a chunk past the end)
+            ls[s]->pair = nullptr;
         }
     }
     ws->sort.key_a = cv.take<int32_t>(emax);
@@ -271,8 +273,8 @@ static size_t carve(gcnn_workspace* ws, char* base, const Caps& c) {
         const int64_t n_send[3] = {nv, nc, nv};
         for (int i = 0; i < 3; ++i) {
             ws->bG[i] = rows(n_recv[i]); ws->bdR[i] = rows(n_recv[i]); ws->bdS[i] = rows(n_send[i]);
-            ws->chain_partials[i] = cv.take<float>((int64_t)NUM_SMS * conv_backward_part_floats());
-            ws->emb_partials[i] = cv.take<float>((int64_t)NUM_SMS * embed_backward_part_floats());
+            ws->chain_partials[i] = cv.take<float>((int64_t)chain_max_parts() * conv_backward_part_floats());
+            ws->emb_partials[i] = cv.take<float>((int64_t)chain_max_parts() * embed_backward_part_floats());
             ws->edge_masks[i] = cv.take<uint2>(i == 2 ? ek : ec);
         }
     }
@@ -389,11 +391,11 @@ static int edge_forward_dispatch(gcnn_workspace* ws, int conv, const EdgeLayout&
     const BlockInfo& bi = ws->cur_blk;
     const int rt = CONV_RECV_T[conv], stp = CONV_SEND_T[conv];
     ws->conv_blocked[conv] = 0;
-    if (bi.n > 0 && n_recv > 0 && edge_block_fits(bi.max_nodes[stp], 0, false)) {
+    if (bi.n > 0 && n_recv > 0 && L.pair && edge_block_fits(bi.max_nodes[stp], 0, false)) {
         ws->conv_blocked[conv] = 1;
         ws->masks_valid[conv] = 0;  // the block backward recomputes the ReLU masks from staged tables
-        return edge_block_forward(L, bi.off[rt], bi.off[stp], bi.n, bi.max_nodes[stp], R, S, w_edge, sc, H, cnt,
-                                  ws->flags + 1, st, prof_bytes);
+        return edge_block_forward(L, bi.off[rt], bi.off[stp], bi.n, n_recv, bi.max_nodes[stp], R, S, w_edge, sc, H, cnt,
+                                  st, prof_bytes);
     }
     void* masks = (cnt && ws->cap.training && ws->use_edge_masks) ? ws->edge_masks[conv] : nullptr;
     ws->masks_valid[conv] = masks != nullptr;
@@ -517,29 +519,41 @@ static int forward_impl(gcnn_workspace* ws, const float* p, const float* pn, con
     cudaStream_t sl_cons = (cons_sorted && s3 != s1) ? s3 : s1, sl_cuts = (cuts_sorted && s3 != s1) ? s3 : s1;
     const bool use_s3 = sl_cons != s1 || sl_cuts != s1;
     if (use_s3) GCNN_TRY(stream_edge(ws, s1, s3));  // after the flag words were cleared
+    // with the batch's block structure every layout also gets its {index clamped into the block, normalised
+    // coefficient} pairs for the block edge kernels (constraint edges: node types 0 x 1, cut edges: 2 x 1)
+    LayoutBlocks lb[2][2];  // [graph][side: 0 by left, 1 by variable]
+    for (int g = 0; g < 2; ++g) {
+        const int lt = g == 0 ? 0 : 2;
+        const float* fsh = pn + (g == 0 ? PN.cedge_shift : PN.kedge_shift);
+        const float* fsc = pn + (g == 0 ? PN.cedge_scale : PN.kedge_scale);
+        lb[g][0] = LayoutBlocks{bi.off[lt], bi.off[1], bi.n, fsh, fsc};
+        lb[g][1] = LayoutBlocks{bi.off[1], bi.off[lt], bi.n, fsh, fsc};
+    }
     GCNN_TRY(build_layout(b->cons_edge_inds, b->cons_edge_inds + ec, b->cons_edge_feats, ec, nc, nv, ws->sort,
-                          ws->flags + 1, ws->flags + 2, cons_sorted, ws->graph[0].by_left, sl_cons));
+                          ws->flags + 1, ws->flags + 2, cons_sorted, ws->graph[0].by_left, sl_cons, &lb[0][0]));
     if (s1 != st) GCNN_CUDA_TRY(cudaEventRecord(ws->ev_layout[0], sl_cons));
     // by-variable layouts: one CTA-local counting sort per sample when the batch carries its block structure and the
     // list is sorted by its left index (then a block's edges are contiguous); the device-wide radix sort otherwise
     const bool tr_ok = bi.n > 0 && transpose_blocks_fits(bi.max_nodes[1]);
     if (tr_ok && cons_sorted)
         GCNN_TRY(transpose_blocks(b->cons_edge_inds + ec, b->cons_edge_inds, b->cons_edge_feats, ec, nc, nv, bi.off[0],
-                                  bi.off[1], bi.n, bi.max_nodes[1], ws->flags + 1, ws->flags + 3, ws->graph[0].by_var, s1));
+                                  bi.off[1], bi.n, bi.max_nodes[1], lb[0][1].f_shift, lb[0][1].f_scale, ws->flags + 1,
+                                  ws->flags + 3, ws->graph[0].by_var, s1));
     else
         GCNN_TRY(build_layout(b->cons_edge_inds + ec, b->cons_edge_inds, b->cons_edge_feats, ec, nv, nc, ws->sort,
-                              ws->flags + 1, ws->flags + 3, false, ws->graph[0].by_var, s1));
+                              ws->flags + 1, ws->flags + 3, false, ws->graph[0].by_var, s1, &lb[0][1]));
     if (s1 != st) GCNN_CUDA_TRY(cudaEventRecord(ws->ev_layout[1], s1));
     GCNN_TRY(build_layout(b->cut_edge_inds, b->cut_edge_inds + ek, b->cut_edge_feats, ek, nk, nv, ws->sort,
-                          ws->flags + 1, ws->flags + 4, cuts_sorted, ws->graph[1].by_left, sl_cuts));
+                          ws->flags + 1, ws->flags + 4, cuts_sorted, ws->graph[1].by_left, sl_cuts, &lb[1][0]));
     if (s1 != st) GCNN_CUDA_TRY(cudaEventRecord(ws->ev_layout[2], sl_cuts));
     if (ws->cap.training) {
         if (tr_ok && cuts_sorted)
             GCNN_TRY(transpose_blocks(b->cut_edge_inds + ek, b->cut_edge_inds, b->cut_edge_feats, ek, nk, nv, bi.off[2],
-                                      bi.off[1], bi.n, bi.max_nodes[1], ws->flags + 1, ws->flags + 5, ws->graph[1].by_var, s1));
+                                      bi.off[1], bi.n, bi.max_nodes[1], lb[1][1].f_shift, lb[1][1].f_scale, ws->flags + 1,
+                                      ws->flags + 5, ws->graph[1].by_var, s1));
         else
             GCNN_TRY(build_layout(b->cut_edge_inds + ek, b->cut_edge_inds, b->cut_edge_feats, ek, nv, nk, ws->sort,
-                                  ws->flags + 1, ws->flags + 5, false, ws->graph[1].by_var, s1));
+                                  ws->flags + 1, ws->flags + 5, false, ws->graph[1].by_var, s1, &lb[1][1]));
     }
     if (use_s3) GCNN_TRY(stream_edge(ws, s3, s1));  // ev_layout[3] (recorded on s1 below) covers the third stream too
 
@@ -893,11 +907,10 @@ static int backward_impl_fused(gcnn_workspace* ws, const float* p, const float* 
         const int64_t E_i = graph_of[i] == 0 ? b->n_cons_edges : b->n_cut_edges;
         const double bwd_bytes = 256.0 * (double)(2 * n_recv[i] + 2 * n_send[i]) + 8.0 * (double)E_i + 4.0 * (double)(n_send[i] + 1);
         const BlockInfo& bi = ws->cur_blk;
-        if (ws->conv_blocked[i] && bi.n > 0 && edge_block_backward_fits(bi.max_nodes[CONV_RECV_T[i]]))
+        if (ws->conv_blocked[i] && bi.n > 0 && Ls.pair && edge_block_backward_fits(bi.max_nodes[CONV_RECV_T[i]]))
             // block kernel: receivers' R and G rows staged in shared memory, masks recomputed (reads R, G, S, writes dS)
-            GCNN_TRY(edge_block_backward(Ls, bi.off[CONV_SEND_T[i]], bi.off[CONV_RECV_T[i]], bi.n, bi.max_nodes[CONV_RECV_T[i]],
-                                         R, S, ws->bG[i], p + o.we, sc, ws->bdS[i], ws->dw_partials[i], &n_dw, ws->flags + 1,
-                                         st, bwd_bytes));
+            GCNN_TRY(edge_block_backward(Ls, bi.off[CONV_SEND_T[i]], bi.off[CONV_RECV_T[i]], bi.n, n_send[i], bi.max_nodes[CONV_RECV_T[i]],
+                                         R, S, ws->bG[i], p + o.we, sc, ws->bdS[i], ws->dw_partials[i], &n_dw, st, bwd_bytes));
         else if (ws->masks_valid[i])  // algorithmic bytes: G gathered per edge comes from L2; compulsory: G, dS rows, 20 B per edge
             GCNN_TRY(edge_backward_masked(Ls, n_send[i], ws->bG[i], ws->edge_masks[i], sc, ws->bdS[i], ws->dw_partials[i],
                                           &n_dw, st, 256.0 * (double)(n_recv[i] + n_send[i]) + 20.0 * (double)E_i +
@@ -1326,7 +1339,7 @@ int gcnn_build_csr_blocks(gcnn_workspace* ws, int which, const int32_t* ei, cons
     GCNN_TRY(build_layout(ei, ei + E, ef, E, n_left, n_vars, ws->sort, ws->flags + 1, unsorted, true,
                           ws->graph[which].by_left, st));
     GCNN_TRY(transpose_blocks(ei + E, ei, ef, E, n_left, n_vars, bi.off[which == 0 ? 0 : 2], bi.off[1], bi.n,
-                              bi.max_nodes[1], ws->flags + 1, unsorted + 1, ws->graph[which].by_var, st));
+                              bi.max_nodes[1], nullptr, nullptr, ws->flags + 1, unsorted + 1, ws->graph[which].by_var, st));
     ws->last.n_vars = n_vars;
     if (which == 0) { ws->last.n_cons = n_left; ws->last.n_cons_edges = E; }
     else { ws->last.n_cuts = n_left; ws->last.n_cut_edges = E; }

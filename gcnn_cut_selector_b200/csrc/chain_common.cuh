@@ -52,19 +52,46 @@ __device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) 
 // D[128 x 64] (+)= G[128 x 64] * Wimg^T: A = bf16x3 tile (K-major), B = bf16x3 N image of a 64 x 64 weight block.
 // The product loop is NOT unrolled and the tile addresses are laundered through an empty asm: the MMA warp runs on a
 // small register budget, and ~600 hoisted loop-invariant descriptors would spill to local memory between the MMAs.
-__device__ __forceinline__ void issue_dgrad(uint32_t tmem_d, uint32_t a_tile, uint32_t w_img, uint32_t acc) {
+//
+// The tensor core rounds every accumulation toward zero, so a chain of MMAs into one accumulator picks up a bias of
+// about half an ulp per full-magnitude accumulation (the four k-steps of the leading (0,0) product): ~2.4e-7 per layer,
+// ~2e-6 in the scores after the ~8 dense layers of a forward pass and, through an ill-conditioned gradient sum, 1.3e-5
+// in one weight gradient of the 32-graph batch (profiles/r2_grad_errors_*.json).  GCNN_DGRAD_SPLIT (default on) sends
+// the even and the odd k-steps to TWO accumulators `pair_off` columns apart; the epilogue adds them in fp32 with round to
+// nearest (tmem_ld16_sum): half the truncations per accumulator at no extra MMA.
+#ifndef GCNN_DGRAD_SPLIT
+#define GCNN_DGRAD_SPLIT 1
+#endif
+__device__ __forceinline__ void issue_dgrad(uint32_t tmem_d, uint32_t a_tile, uint32_t w_img, uint32_t acc, uint32_t pair_off) {
     asm volatile("" : "+r"(a_tile), "+r"(w_img));
     const uint64_t da0 = make_desc(a_tile), db0 = make_desc(w_img);
+    uint32_t acc_odd = acc;
+    const uint32_t tmem_odd = GCNN_DGRAD_SPLIT ? tmem_d + pair_off : tmem_d;
 #pragma unroll 1
     for (int p = 0; p < 6; ++p) {
         const uint32_t pa = (0x001012u >> (4 * p)) & 3u, pb = (0x010210u >> (4 * p)) & 3u;  // (2,0) (1,1) (0,2) (1,0) (0,1) (0,0)
         const uint64_t da = da0 + (uint64_t)(pa * (T16_PIECE >> 4)), db = db0 + (uint64_t)(pb * (W16_PIECE >> 4));
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-            umma_bf16(tmem_d, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), IDESC_BF16_KK, acc);
-            acc = 1;
+            if (GCNN_DGRAD_SPLIT && (ks & 1)) {
+                umma_bf16(tmem_odd, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), IDESC_BF16_KK, acc_odd);
+                acc_odd = 1;
+            } else {
+                umma_bf16(tmem_d, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), IDESC_BF16_KK, acc);
+                acc = 1;
+            }
         }
     }
+}
+// accumulator block of a dgrad chain: the even-k accumulator plus (GCNN_DGRAD_SPLIT) its odd-k companion
+__device__ __forceinline__ void tmem_ld16_sum(uint32_t taddr, uint32_t pair_off, float (&v)[16]) {
+    tmem_ld16(taddr, v);
+#if GCNN_DGRAD_SPLIT
+    float w[16];
+    tmem_ld16(taddr + pair_off, w);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += w[i];
+#endif
 }
 
 // dW[f][c] (+)= sum over the 128 lines of act[line][f] * g[line][c]: both operands MN-major views of bf16x3 tiles, the

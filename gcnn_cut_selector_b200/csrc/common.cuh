@@ -137,6 +137,20 @@ struct EdgeLayout {   // edges grouped by one endpoint ("owner"), stable in orig
     const int32_t* reordered;  // device word: 0 = the layout kept the input order (perm[p] == p); set by build_layout
     const int32_t* long_rows;  // device word, set by build_layout: bit 0 = some owner has more than long_row_threshold()
                                // edges, bit 1 = some owner has more than max(32, 4 x mean degree) edges
+    // Block-diagonal batches (edge_block.cu): {other endpoint clamped into the owner's block, normalised coefficient
+    // (val + shift) * scale as float bits} per position -- one 8-byte load per edge, no range checks in the kernels.
+    // nullptr unless the layout was built with the batch's block structure; pair_buf is the workspace buffer behind it.
+    const int2* pair;
+    int2* pair_buf;
+};
+// what a layout build needs to write EdgeLayout::pair: node offsets of the blocks on the owner and on the other side,
+// and the edge pre-norm parameters (device scalars, nullable)
+struct LayoutBlocks {
+    const int32_t* owner_off = nullptr;
+    const int32_t* other_off = nullptr;
+    int64_t n_blocks = 0;
+    const float* f_shift = nullptr;
+    const float* f_scale = nullptr;
 };
 // rows longer than this are reduced by a whole CTA in the edge kernels (csrc/edge.cu); GCNN_LONG_ROW overrides (experiments)
 int long_row_threshold();
@@ -151,7 +165,7 @@ struct SortScratch {
 
 int build_layout(const int32_t* keys, const int32_t* others, const float* feats, int64_t E, int64_t n_owner,
                  int64_t n_other, const SortScratch& sc, int32_t* err_flag, int32_t* unsorted_flag, bool hint_sorted,
-                 EdgeLayout& out, cudaStream_t st);
+                 EdgeLayout& out, cudaStream_t st, const LayoutBlocks* blocks = nullptr);
 int64_t sort_hist_entries(int64_t E);
 
 // ---- packed sample records (records.cu) ------------------------------------------------------------------------------
@@ -202,18 +216,18 @@ int edge_backward_max_partials();
 bool edge_block_fits(int64_t max_send_rows, int64_t max_recv_rows, bool training);
 bool edge_block_backward_fits(int64_t max_recv_rows);
 int edge_block_forward(const EdgeLayout& by_recv, const int32_t* recv_off, const int32_t* send_off, int64_t n_blocks,
-                       int64_t max_send_rows, const float* R, const float* S, const float* w_edge, EdgeScalars sc, float* H,
-                       float* cnt, int32_t* err_flag, cudaStream_t st, double prof_bytes);
+                       int64_t n_recv, int64_t max_send_rows, const float* R, const float* S, const float* w_edge,
+                       EdgeScalars sc, float* H, float* cnt, cudaStream_t st, double prof_bytes);
 int edge_block_backward(const EdgeLayout& by_send, const int32_t* send_off, const int32_t* recv_off, int64_t n_blocks,
-                        int64_t max_recv_rows, const float* R, const float* S, const float* G, const float* w_edge,
-                        EdgeScalars sc, float* dS, float* dw_partials, int* n_partials, int32_t* err_flag, cudaStream_t st,
-                        double prof_bytes);
+                        int64_t n_send, int64_t max_recv_rows, const float* R, const float* S, const float* G, const float* w_edge,
+                        EdgeScalars sc, float* dS, float* dw_partials, int* n_partials, cudaStream_t st, double prof_bytes);
 int edge_block_backward_max_partials();
 // transposed (by-variable) layout of an edge list sorted by its left index, one CTA-local stable counting sort per block
 bool transpose_blocks_fits(int64_t max_vars);
 int transpose_blocks(const int32_t* keys_var, const int32_t* keys_left, const float* feats, int64_t E, int64_t n_left,
                      int64_t n_var, const int32_t* left_off, const int32_t* var_off, int64_t n_blocks, int64_t max_vars,
-                     int32_t* err_flag, int32_t* unsorted_flag, EdgeLayout& out, cudaStream_t st);
+                     const float* f_shift, const float* f_scale, int32_t* err_flag, int32_t* unsorted_flag, EdgeLayout& out,
+                     cudaStream_t st);
 // sum and sum of squares of (z_e - center) over all E x 64 joint pre-activations (double accumulators)
 int edge_z_stats(const EdgeLayout& by_recv, int64_t n_recv, const float* R, const float* S, const float* w_edge,
                  EdgeScalars sc, double center, double* partials, double* out2, cudaStream_t st);
@@ -316,6 +330,7 @@ struct ConvBwdArgs {          // fused backward node chain of one convolution (t
 };
 int tc_conv_backward(const ConvBwdArgs& a, int* n_parts, cudaStream_t st);
 int conv_backward_part_floats();
+int chain_max_parts();
 struct EmbFwdArgs {           // fused forward chain of one embedding (tc_embed_forward, node_tc.cu)
     const float* x;           // [M, K] raw input features
     int K;

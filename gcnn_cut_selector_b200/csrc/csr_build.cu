@@ -203,7 +203,8 @@ __global__ void finalize_layout_kernel(const int32_t* __restrict__ keys, const i
                                        const float* __restrict__ feats, int64_t E, int32_t n_owner,
                                        int32_t n_other, const int32_t* __restrict__ unsorted_flag, const int32_t* __restrict__ sorted_keys,
                                        const int32_t* __restrict__ sorted_perm, EdgeLayout out, int32_t* __restrict__ long_flag,
-                                       const int long_row, const int heavy_row) {
+                                       const int long_row, const int heavy_row, const LayoutBlocks blk,
+                                       int32_t* __restrict__ err_flag) {
     pdl_enter();
     const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (p > E) return;
@@ -227,9 +228,24 @@ __global__ void finalize_layout_kernel(const int32_t* __restrict__ keys, const i
     }
     if (p < E) {
         const int32_t e = presorted ? (int32_t)p : sorted_perm[p];
-        out.other[p] = min(max(others[e], 0), n_other - 1);  // clamped; err_flag reports it
-        out.val[p] = feats[e];
+        const int32_t o = others[e];
+        const float f = feats[e];
+        out.other[p] = min(max(o, 0), n_other - 1);  // clamped; err_flag reports it
+        out.val[p] = f;
         out.perm[p] = e;
+        if (blk.n_blocks > 0) {
+            // the owner's block b (largest b with owner_off[b] <= k) bounds the other endpoint: the block kernels index
+            // their shared-memory tables with it unchecked, so it is clamped here (a violation sets error bit 4)
+            int lo = 0, hi = (int)blk.n_blocks - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (blk.owner_off[mid] <= k) lo = mid; else hi = mid - 1;
+            }
+            const int32_t o0 = blk.other_off[lo], o1 = blk.other_off[lo + 1];
+            if (o < o0 || o >= o1) atomicOr(err_flag, 4);
+            const float sh = blk.f_shift ? *blk.f_shift : 0.f, scl = blk.f_scale ? *blk.f_scale : 1.f;
+            out.pair_buf[p] = make_int2(min(max(o, o0), max(o1 - 1, o0)), __float_as_int((f + sh) * scl));
+        }
     }
 }
 
@@ -246,7 +262,9 @@ static int bit_length(int64_t x) {
 
 int build_layout(const int32_t* keys, const int32_t* others, const float* feats, int64_t E, int64_t n_owner,
                  int64_t n_other, const SortScratch& sc, int32_t* err_flag, int32_t* unsorted_flag, bool hint_sorted,
-                 EdgeLayout& out, cudaStream_t st) {
+                 EdgeLayout& out, cudaStream_t st, const LayoutBlocks* blocks) {
+    const LayoutBlocks blk = (blocks && out.pair_buf) ? *blocks : LayoutBlocks();
+    out.pair = blk.n_blocks > 0 ? out.pair_buf : nullptr;
     if (E < 0 || n_owner < 0 || n_other < 0 || E >= (int64_t)INT32_MAX || n_owner >= (int64_t)INT32_MAX) {
         set_error("build_layout: sizes out of int32 range");
         return GCNN_INVALID;
@@ -328,7 +346,8 @@ int build_layout(const int32_t* keys, const int32_t* others, const float* feats,
         // a violated hint leaves unsorted_flag = 1 with no sorted pairs: fall back to the input order (the error is
         // reported through err_flag) by reading the always-zero word
         ((trivially_sorted || hint_sorted) ? zero_flag : unsorted_flag), sorted_keys, sorted_perm, out,
-        unsorted_flag + LONG_FLAG_OFFSET, long_row_threshold(), (int)max((int64_t)32, 4 * ceil_div(E, n_owner > 0 ? n_owner : 1)));
+        unsorted_flag + LONG_FLAG_OFFSET, long_row_threshold(), (int)max((int64_t)32, 4 * ceil_div(E, n_owner > 0 ? n_owner : 1)),
+        blk, err_flag);
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
 }

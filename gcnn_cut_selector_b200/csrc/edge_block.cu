@@ -7,14 +7,21 @@
 // the caller passes the loader's per-sample node counts (utils.py:420-422) the batch is a list of BLOCKS
 // (rows [recv_off[b], recv_off[b+1]) x sources [send_off[b], send_off[b+1])) and one CTA can hold the whole source side
 // of a block in shared memory.  The generic kernels gather E x 256 B from L2 (E / N ~ 25-50 gathers per table row for
-// set cover) and sit at the L2 -> SM gather rate; here a CTA = (block, row split, FW-feature slice)
-//   1. copies the block's source slice S[send_off[b] .. , fo .. fo + FW) to shared memory once (cp.async, coalesced),
-//   2. walks its rows, one warp per row, 32 / (FW / 4) edges per step: every gather is a conflict-free ld.shared.v4,
-//   3. reduces the lane groups of a row with shuffles in a fixed order -> bit-reproducible, no atomics.
+// set cover) at 19 instructions per edge; here a CTA = (block, row split, FW-feature slice)
+//   1. copies the block's source slice S[send_off[b] .. , fo .. fo + FW) to shared memory once (cp.async, coalesced);
+//   2. walks its rows with LANE GROUPS: a group = FW / 4 lanes = one edge's slice, one ld.shared.v4 per lane (a
+//      quarter-warp reads one 128-byte table row: conflict-free).  Every group walks its OWN row, edge by edge in edge
+//      order (the order of the reference's sequential scatter), so a group's accumulators are its row's sums: no
+//      cross-lane reduction, no per-row hand-off.  The 32 / LPE groups of a warp step through their rows in lockstep;
+//      a group whose row is shorter gathers a poison row (-huge) whose terms are never active.  With few long rows
+//      (the 64 cut rows of a sample) the groups of a warp share one row instead (SPLIT) and are combined at the end.
+//   3. reads each edge as ONE 8-byte {source index, normalised coefficient} pair (EdgeLayout::pair, written by the
+//      layout build with indices clamped into the block, so the kernels need no range checks): the load is uniform per
+//      group and served by L1; the table address is one IMAD.
 // The ReLU bookkeeping is branch-free: m = (z > 0) as 1.0f / 0.0f, acc += z * m and cnt += m on the packed FP32x2 pipe
 // (z * 1 and z * 0 are exact, so the sums are the ones the predicated form gives).  The backward stages BOTH the
 // receivers' projection rows R and their gradient rows G, recomputes z with the forward's association and needs no
-// per-edge masks.  A violated block promise (an edge leaving its sample) sets error bit 4 and is clamped.
+// per-edge masks.  Fixed traversal and combination order -> bit-reproducible, no atomics.
 //
 // The transposed layout of a block is a stable counting sort inside one CTA (keys = the block's variables): one launch
 // instead of the eight of the device-wide radix sort, bit-identical output (csr_build.cu; np.argsort(kind='stable')).
@@ -38,6 +45,26 @@ __device__ __forceinline__ void cp16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp8(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ int2 lds_pair(uint32_t a) {
+    int2 v;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+
+// Edge pairs travel global -> shared memory asynchronously, one chunk (RING_CH pairs per lane group) ahead of the steps
+// that consume them: a group's cp.async copies for chunk c + 1 (or for the first chunk of the warp's next round of rows)
+// are issued when chunk c starts, so the ~900-cycle L2 latency of the pair list is hidden behind ~16 steps of eight
+// warps per scheduler instead of stalling every unrolled iteration (profiles/: 7 of 8 warps on the long scoreboard).
+constexpr int RING_CH = 16;
+constexpr int RING_GROUP = RING_CH * 8 + 8;  // bytes per group buffer: 16 pairs + 8 bytes of skew, so that the groups of a
+                                             // warp read their t-th pair from different banks
+template <int FW>
+constexpr int ring_bytes() { return BLK_WARPS * 2 * (32 / (FW / 4)) * RING_GROUP; }  // warps x 2 buffers x groups
 __device__ __forceinline__ float4 bld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void bst4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
@@ -89,9 +116,18 @@ __device__ __forceinline__ void stage_table(uint32_t dst, const float* __restric
     }
 }
 
-// One <= 32-edge chunk of a row travels from the lanes that loaded it to the lane groups that consume it through a
-// 256-byte per-warp slot: {byte offset of the edge's table row, normalised coefficient}.
-struct EdgeSlot { uint32_t off; float f; };
+// backward tables: row i = [R slice | G slice] (FW * 8 bytes); for FW = 16 odd rows are stored [G | R] (see walk_backward)
+template <int FW>
+__device__ __forceinline__ void stage_pair_table(uint32_t dst, const float* __restrict__ R, const float* __restrict__ G,
+                                                 int row0, int n, int fo) {
+    constexpr int C = FW / 4;
+    for (int i = threadIdx.x; i < n * C * 2; i += BLK_THREADS) {
+        const int row = i / (2 * C), rem = i - row * 2 * C, which = rem / C, c = rem - which * C;
+        uint32_t off = (uint32_t)row * (uint32_t)(FW * 8) + (uint32_t)which * (uint32_t)(FW * 4) + (uint32_t)c * 16u;
+        if (FW == 16) off ^= ((uint32_t)row & 1u) * 64u;
+        cp16(dst + off, (which ? G : R) + (int64_t)(row0 + row) * D + fo + c * 4);
+    }
+}
 
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 
@@ -106,104 +142,140 @@ __device__ __forceinline__ float2 active2(const float2 z) {  // 1.0f where relu(
     return NEG ? f2(z.x < 0.f ? 1.f : 0.f, z.y < 0.f ? 1.f : 0.f) : f2(z.x > 0.f ? 1.f : 0.f, z.y > 0.f ? 1.f : 0.f);
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// Forward: H[t] = s_f * sum_{e in seg(t)} [z_e active] z_e,  cnt[t] = # active terms, for this CTA's rows and slice.
-// ------------------------------------------------------------------------------------------------------------------
-template <int FW, bool TRAIN, bool NEG>
-__device__ __forceinline__ void block_forward_rows(const int32_t* __restrict__ ptr, const int32_t* __restrict__ src,
-                                                   const float* __restrict__ val, const int ra, const int rb, const int s0,
-                                                   const int ns, const uint32_t table, const float* __restrict__ R,
-                                                   const float* __restrict__ w_edge, EdgeScalars sc, float* __restrict__ H,
-                                                   float* __restrict__ cnt, const int fo, int32_t* __restrict__ err_flag,
-                                                   EdgeSlot* __restrict__ slot) {
-    constexpr int LPE = FW / 4, EPS = 32 / LPE;  // lanes per edge, edges per step
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane / LPE, l = lane - grp * LPE;
-    const float f_shift = sc.f_shift ? *sc.f_shift : 0.f, f_scale = sc.f_scale ? *sc.f_scale : 1.f, s_f = *sc.s_f;
-    const float4 w4 = bld4(w_edge + fo + l * 4);
-    const uint32_t tl = table + (uint32_t)l * 16u;
-    int row = ra + warp;
-    if (row >= rb) return;
-    int beg = ptr[row], end = ptr[row + 1];
-    int nrow = row + BLK_WARPS, nbeg = 0, nend = 0;
-    float4 r4 = bld4(R + (int64_t)row * D + fo + l * 4), r_next = r4;
-    if (nrow < rb) { nbeg = ptr[nrow]; nend = ptr[nrow + 1]; r_next = bld4(R + (int64_t)nrow * D + fo + l * 4); }
-    float2 a01 = f2(0.f, 0.f), a23 = a01, c01 = a01, c23 = a01;
-    int base = beg;
-    int x_src = s0;
-    float x_val = 0.f;
-    bool bad = false;
-    if (base + lane < end) { x_src = src[base + lane]; x_val = val[base + lane]; bad |= (x_src < s0) | (x_src >= s0 + ns); }
-    auto accumulate = [&](const float4 g, const float f) {
-        float2 z01, z23;
-        preact(r4, w4, g, f, z01, z23);
-        const float2 m01 = active2<NEG>(z01), m23 = active2<NEG>(z23);
-        a01 = __ffma2_rn(z01, m01, a01);
-        a23 = __ffma2_rn(z23, m23, a23);
-        if (TRAIN) { c01 = __fadd2_rn(c01, m01); c23 = __fadd2_rn(c23, m23); }
-    };
-    for (;;) {
-        const int n = ns > 0 ? min(32, end - base) : 0;  // warp-uniform; <= 0 for a row without edges
-        const int rel = x_src - s0;  // (lanes without an edge hold s0)
-        const uint32_t my_off = (uint32_t)min(max(rel, 0), max(ns - 1, 0)) * (uint32_t)(FW * 4);
-        const float my_f = (x_val + f_shift) * f_scale;
-        // stage the next chunk (of this row, or the first one of the warp's next row) while this one is processed
-        const bool same_row = base + 32 < end;
-        const int pf_base = same_row ? base + 32 : nbeg, pf_end = same_row ? end : nend;
-        x_src = s0; x_val = 0.f;
-        if (pf_base + lane < pf_end) {
-            x_src = src[pf_base + lane]; x_val = val[pf_base + lane];
-            bad |= (x_src < s0) | (x_src >= s0 + ns);  // an edge that leaves its block breaks the caller's promise
-        }
-        __syncwarp();  // the previous chunk's readers are done with the slot
-        slot[lane] = EdgeSlot{my_off, my_f};
-        __syncwarp();
-        int j0 = 0;
-#pragma unroll 4
-        for (; j0 + EPS <= n; j0 += EPS) {  // full steps: EPS edges, one per lane group, no predication
-            const EdgeSlot e = slot[j0 + grp];
-            accumulate(lds4(tl + e.off), e.f);
-        }
-        if (j0 + grp < n) {  // tail of the chunk
-            const EdgeSlot e = slot[j0 + grp];
-            accumulate(lds4(tl + e.off), e.f);
-        }
-        if (same_row) { base += 32; continue; }
-        // row done: combine the lane groups (fixed order) and store
-#pragma unroll
-        for (int m = LPE; m < 32; m <<= 1) {
-            a01.x += __shfl_xor_sync(0xffffffffu, a01.x, m); a01.y += __shfl_xor_sync(0xffffffffu, a01.y, m);
-            a23.x += __shfl_xor_sync(0xffffffffu, a23.x, m); a23.y += __shfl_xor_sync(0xffffffffu, a23.y, m);
-            if (TRAIN) {
-                c01.x += __shfl_xor_sync(0xffffffffu, c01.x, m); c01.y += __shfl_xor_sync(0xffffffffu, c01.y, m);
-                c23.x += __shfl_xor_sync(0xffffffffu, c23.x, m); c23.y += __shfl_xor_sync(0xffffffffu, c23.y, m);
-            }
-        }
-        if (grp == 0) bst4(H + (int64_t)row * D + fo + l * 4, make_float4(s_f * a01.x, s_f * a01.y, s_f * a23.x, s_f * a23.y));
-        if (TRAIN && grp == 1) bst4(cnt + (int64_t)row * D + fo + l * 4, make_float4(c01.x, c01.y, c23.x, c23.y));
-        if (nrow >= rb) break;
-        row = nrow; beg = nbeg; end = nend; base = beg; r4 = r_next;
-        a01 = f2(0.f, 0.f); a23 = a01; c01 = a01; c23 = a01;
-        nrow += BLK_WARPS; nbeg = 0; nend = 0;
-        if (nrow < rb) { nbeg = ptr[nrow]; nend = ptr[nrow + 1]; r_next = bld4(R + (int64_t)nrow * D + fo + l * 4); }
-    }
-    if (bad) atomicOr(err_flag, 4);
+// A lane group's share of the current round: rows go to the warps' groups round-robin, RPW = G / SPLIT rows per warp per
+// round; with SPLIT > 1 the SPLIT groups of a row take contiguous shares of its edges.
+template <int SPLIT>
+__device__ __forceinline__ void group_segment(int beg, int end, int sub, int& e, int& n) {
+    if (SPLIT == 1) { e = beg; n = end - beg; return; }
+    const int seg = (end - beg + SPLIT - 1) / SPLIT;
+    e = min(end, beg + sub * seg);
+    n = min(end, e + seg) - e;
 }
 
-template <int FW, bool TRAIN>
+// ------------------------------------------------------------------------------------------------------------------
+// Forward: H[t] = s_f * sum_{e in seg(t)} [z_e active] z_e,  cnt[t] = # active terms, for this CTA's rows and slice.
+// `tbase` = shared-memory address of (table row 0, this lane's 16 bytes) MINUS s0 rows, so the address of the row of
+// absolute source index i is tbase + i * FW * 4; `poison` = address of the poison row's 16 bytes for this lane.
+// ------------------------------------------------------------------------------------------------------------------
+template <int FW, bool TRAIN, bool NEG, int SPLIT>
+__device__ __forceinline__ void walk_forward(const int32_t* __restrict__ ptr, const int2* __restrict__ pair, const int ra,
+                                             const int rb, const bool table_ok, const uint32_t tbase, const int poison_idx,
+                                             const uint32_t ring, const float* __restrict__ R,
+                                             const float* __restrict__ w_edge, const float s_f, float* __restrict__ H,
+                                             float* __restrict__ cnt, const int fo) {
+    constexpr int LPE = FW / 4, G = 32 / LPE, RPW = G / SPLIT;  // lanes per edge, groups per warp, rows per warp per round
+    constexpr int CPL = RING_CH / LPE;                          // pair copies per lane per chunk
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane / LPE, l = lane - grp * LPE;
+    const int sub = grp % SPLIT, rsel = grp / SPLIT;
+    const float4 w4 = bld4(w_edge + fo + l * 4);
+    // this group's two chunk buffers: ring + ((warp * 2 + buf) * G + grp) * RING_CH * 8
+    const uint32_t gring = ring + (uint32_t)((warp * 2 * G + grp) * RING_GROUP);
+    constexpr uint32_t BUF = (uint32_t)(G * RING_GROUP);
+    // chunk c of a group's segment: RING_CH pairs copied unconditionally (the pair buffers are padded; entries beyond
+    // the segment are overwritten with the poison pair when the chunk is consumed)
+    auto issue = [&](const int2* __restrict__ src, const int c, const uint32_t buf) {
+        const int2* __restrict__ p = src + c * RING_CH + l;
+#pragma unroll
+        for (int u = 0; u < CPL; ++u) cp8(gring + buf * BUF + (uint32_t)((l + u * LPE) * 8), p + u * LPE);
+        cp_commit();
+    };
+    // entries [n - j0, RING_CH) of the chunk that just landed do not belong to the segment: point them at the poison row
+    auto patch = [&](const int n_left, const uint32_t buf) {
+#pragma unroll
+        for (int u = 0; u < CPL; ++u)
+            if (l + u * LPE >= n_left)
+                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(gring + buf * BUF + (uint32_t)((l + u * LPE) * 8)), "r"(poison_idx), "r"(0) : "memory");
+    };
+    constexpr int STRIDE = BLK_WARPS * RPW;
+    int row = ra + warp * RPW + rsel;
+    int beg = 0, end = 0;
+    float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < rb) { beg = ptr[row]; end = ptr[row + 1]; r4 = bld4(R + (int64_t)row * D + fo + l * 4); }
+    int e, n;
+    group_segment<SPLIT>(beg, end, sub, e, n);
+    if (!table_ok) n = 0;
+    uint32_t cur = 0;
+    issue(pair + e, 0, cur);  // first chunk of the first round
+    while (__any_sync(0xffffffffu, row < rb)) {
+        // the next round's pointers and receiver slices are in flight while this round is walked
+        const int nrow = row + STRIDE;
+        int nbeg = 0, nend = 0;
+        float4 r_next = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (nrow < rb) { nbeg = ptr[nrow]; nend = ptr[nrow + 1]; r_next = bld4(R + (int64_t)nrow * D + fo + l * 4); }
+        const int nmax = __reduce_max_sync(0xffffffffu, n);
+        const int2* __restrict__ pp = pair + e;
+        float2 a01 = f2(0.f, 0.f), a23 = a01, c01 = a01, c23 = a01;
+        auto step = [&](const uint32_t addr, const float f) {
+            const float4 g = lds4(addr);
+            float2 z01, z23;
+            preact(r4, w4, g, f, z01, z23);
+            const float2 m01 = active2<NEG>(z01), m23 = active2<NEG>(z23);
+            a01 = __ffma2_rn(z01, m01, a01);
+            a23 = __ffma2_rn(z23, m23, a23);
+            if (TRAIN) { c01 = __fadd2_rn(c01, m01); c23 = __fadd2_rn(c23, m23); }
+        };
+        int ne = 0, nn = 0;  // the group's segment in the next round
+        bool next_issued = false;
+        for (int j0 = 0, c = 0; j0 < nmax; j0 += RING_CH, ++c) {
+            cp_wait0();      // this lane's copies of chunk c have landed ...
+            patch(n - j0, cur);
+            __syncwarp();    // ... and so have the other lanes'; everybody is done reading the other buffer
+            if (j0 + RING_CH < nmax) issue(pp, c + 1, cur ^ 1u);
+            else {           // last chunk of the round: fetch the first chunk of the next round behind it
+                group_segment<SPLIT>(nbeg, nend, sub, ne, nn);
+                if (!table_ok) nn = 0;
+                issue(pair + ne, 0, cur ^ 1u);
+                next_issued = true;
+            }
+            const uint32_t buf = gring + cur * BUF;
+            const int jn = min(RING_CH, nmax - j0);
+#pragma unroll 4
+            for (int t = 0; t < jn; ++t) {  // a group that is done gathers the poison row (z = r - huge, never active)
+                const int2 p = lds_pair(buf + (uint32_t)t * 8u);
+                step(tbase + (uint32_t)p.x * (uint32_t)(FW * 4), __int_as_float(p.y));
+            }
+            cur ^= 1u;
+        }
+        if (!next_issued) {  // a round without edges
+            group_segment<SPLIT>(nbeg, nend, sub, ne, nn);
+            if (!table_ok) nn = 0;
+            cp_wait0();
+            __syncwarp();
+            issue(pair + ne, 0, cur);
+        }
+        if (SPLIT > 1) {  // combine the groups of a row (fixed order)
+#pragma unroll
+            for (int m = LPE; m < LPE * SPLIT; m <<= 1) {
+                a01.x += __shfl_xor_sync(0xffffffffu, a01.x, m); a01.y += __shfl_xor_sync(0xffffffffu, a01.y, m);
+                a23.x += __shfl_xor_sync(0xffffffffu, a23.x, m); a23.y += __shfl_xor_sync(0xffffffffu, a23.y, m);
+                if (TRAIN) {
+                    c01.x += __shfl_xor_sync(0xffffffffu, c01.x, m); c01.y += __shfl_xor_sync(0xffffffffu, c01.y, m);
+                    c23.x += __shfl_xor_sync(0xffffffffu, c23.x, m); c23.y += __shfl_xor_sync(0xffffffffu, c23.y, m);
+                }
+            }
+        }
+        if (row < rb) {
+            if (sub == 0) bst4(H + (int64_t)row * D + fo + l * 4, make_float4(s_f * a01.x, s_f * a01.y, s_f * a23.x, s_f * a23.y));
+            if (TRAIN && sub == (SPLIT > 1 ? 1 : 0)) bst4(cnt + (int64_t)row * D + fo + l * 4, make_float4(c01.x, c01.y, c23.x, c23.y));
+        }
+        row = nrow; r4 = r_next; e = ne; n = nn;
+    }
+    cp_wait0();
+}
+
+template <int FW, bool TRAIN, int SPLIT>
 __global__ void __launch_bounds__(BLK_THREADS, 1)
-edge_block_forward_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ src, const float* __restrict__ val,
-                          const int32_t* __restrict__ recv_off, const int32_t* __restrict__ send_off, const int K,
-                          const float* __restrict__ R, const float* __restrict__ S, const float* __restrict__ w_edge,
-                          EdgeScalars sc, float* __restrict__ H, float* __restrict__ cnt, int32_t* __restrict__ err_flag,
-                          const int table_rows) {
+edge_block_forward_kernel(const int32_t* __restrict__ ptr, const int2* __restrict__ pair, const int32_t* __restrict__ recv_off,
+                          const int32_t* __restrict__ send_off, const int K, const float* __restrict__ R,
+                          const float* __restrict__ S, const float* __restrict__ w_edge, const float* __restrict__ s_f_ptr,
+                          float* __restrict__ H, float* __restrict__ cnt, const int table_rows) {
     extern __shared__ __align__(16) uint8_t blk_smem[];
     __shared__ int s_range[2];
-    __shared__ __align__(16) EdgeSlot s_slot[BLK_WARPS][32];
     pdl_enter();
     const int b = blockIdx.x / K, k = blockIdx.x - b * K, fo = blockIdx.y * FW;
     const int r0 = recv_off[b], r1 = recv_off[b + 1], s0 = send_off[b];
     const int ns = min(send_off[b + 1] - s0, table_rows);  // (the host sized the table from the same offsets)
-    const float s_f = *sc.s_f;
+    const float s_f = *s_f_ptr;
     int ra, rb;
     block_row_split(ptr, r0, r1, k, K, s_range, ra, rb);
     if (s_f == 0.f) {  // relu(0 * z) = 0: nothing is active
@@ -217,112 +289,148 @@ edge_block_forward_kernel(const int32_t* __restrict__ ptr, const int32_t* __rest
     }
     const uint32_t table = smem_addr(blk_smem);
     stage_table<FW, FW * 4>(table, S, s0, ns, fo);
+    // poison row behind the table: a lane group without an edge gathers it and can never be active
+    const uint32_t poison_row = (uint32_t)table_rows * (uint32_t)(FW * 4);
+    if (threadIdx.x < FW) reinterpret_cast<float*>(blk_smem + poison_row)[threadIdx.x] = s_f < 0.f ? 3.0e38f : -3.0e38f;
     cp_wait_all();
     __syncthreads();
-    EdgeSlot* slot = s_slot[threadIdx.x >> 5];
-    if (s_f < 0.f) block_forward_rows<FW, TRAIN, true>(ptr, src, val, ra, rb, s0, ns, table, R, w_edge, sc, H, cnt, fo, err_flag, slot);
-    else block_forward_rows<FW, TRAIN, false>(ptr, src, val, ra, rb, s0, ns, table, R, w_edge, sc, H, cnt, fo, err_flag, slot);
+    const int l = (threadIdx.x & 31) % (FW / 4);
+    const uint32_t tbase = table + (uint32_t)l * 16u - (uint32_t)s0 * (uint32_t)(FW * 4);
+    const int poison_idx = s0 + table_rows;  // the source index whose table row is the poison row
+    const uint32_t ring = table + (uint32_t)(table_rows + 1) * (uint32_t)(FW * 4);  // behind the table and its poison row
+    if (s_f < 0.f) walk_forward<FW, TRAIN, true, SPLIT>(ptr, pair, ra, rb, ns > 0, tbase, poison_idx, ring, R, w_edge, s_f, H, cnt, fo);
+    else walk_forward<FW, TRAIN, false, SPLIT>(ptr, pair, ra, rb, ns > 0, tbase, poison_idx, ring, R, w_edge, s_f, H, cnt, fo);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Backward over the transposed layout (rows = SENDING nodes s of the block, t_e = other[e] the receiver):
+// Backward over the transposed layout (rows = SENDING nodes s of the block, t_e = pair.x the receiver):
 //   dS[s] = s_f * sum_e [z_e active] G[t_e],   dw = s_f * sum_e f_e [z_e active] G[t_e],   z_e = (R[t_e] + f_e w) + S[s].
-// Both receiver tables (R: forward projection, G: incoming gradient) are staged; S[s] is the row's own projection.
+// Both receiver tables are staged, interleaved per row as [R slice | G slice]; S[s] is the row's own projection.
 // ------------------------------------------------------------------------------------------------------------------
-template <int FW, bool NEG>
-__device__ __forceinline__ void block_backward_rows(const int32_t* __restrict__ ptr, const int32_t* __restrict__ other,
-                                                    const float* __restrict__ val, const int ra, const int rb, const int t0,
-                                                    const int nt, const uint32_t table,
-                                                    const float* __restrict__ S, const float* __restrict__ w_edge,
-                                                    EdgeScalars sc, float* __restrict__ dS, const int fo, float2& dw01,
-                                                    float2& dw23, int32_t* __restrict__ err_flag, EdgeSlot* __restrict__ slot) {
-    constexpr int LPE = FW / 4, EPS = 32 / LPE;
+template <int FW, bool NEG, int SPLIT>
+__device__ __forceinline__ void walk_backward(const int32_t* __restrict__ ptr, const int2* __restrict__ pair, const int ra,
+                                              const int rb, const bool table_ok, const uint32_t tbase, const int poison_idx,
+                                              const uint32_t ring, const float* __restrict__ S,
+                                              const float* __restrict__ w_edge, const float s_f, float* __restrict__ dS,
+                                              const int fo, float2& dw01, float2& dw23, const int t0) {
+    constexpr int LPE = FW / 4, G = 32 / LPE, RPW = G / SPLIT;
+    constexpr int CPL = RING_CH / LPE;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane / LPE, l = lane - grp * LPE;
-    const float f_shift = sc.f_shift ? *sc.f_shift : 0.f, f_scale = sc.f_scale ? *sc.f_scale : 1.f, s_f = *sc.s_f;
+    const int sub = grp % SPLIT, rsel = grp / SPLIT;
     const float4 w4 = bld4(w_edge + fo + l * 4);
-    const uint32_t tl = table + (uint32_t)l * 16u;  // a table row is [R slice | G slice], 2 FW floats
-    int row = ra + warp;
-    if (row >= rb) return;
-    int beg = ptr[row], end = ptr[row + 1];
-    int nrow = row + BLK_WARPS, nbeg = 0, nend = 0;
-    float4 s4 = bld4(S + (int64_t)row * D + fo + l * 4), s_next = s4;
-    if (nrow < rb) { nbeg = ptr[nrow]; nend = ptr[nrow + 1]; s_next = bld4(S + (int64_t)nrow * D + fo + l * 4); }
-    float2 a01 = f2(0.f, 0.f), a23 = a01;
-    int base = beg;
-    int x_t = t0;
-    float x_val = 0.f;
-    bool bad = false;
-    if (base + lane < end) { x_t = other[base + lane]; x_val = val[base + lane]; bad |= (x_t < t0) | (x_t >= t0 + nt); }
-    auto accumulate = [&](const float4 r, const float4 g, const float f) {
-        float2 z01, z23;
-        preact(r, w4, s4, f, z01, z23);  // the forward's association: (R[t] + f w) + S[s]
-        const float2 m01 = active2<NEG>(z01), m23 = active2<NEG>(z23);
-        const float2 g01 = __fmul2_rn(m01, f2(g.x, g.y)), g23 = __fmul2_rn(m23, f2(g.z, g.w));
-        a01 = __fadd2_rn(a01, g01);
-        a23 = __fadd2_rn(a23, g23);
-        const float2 ff = f2(f, f);
-        dw01 = __ffma2_rn(ff, g01, dw01);
-        dw23 = __ffma2_rn(ff, g23, dw23);
-    };
-    for (;;) {
-        const int n = nt > 0 ? min(32, end - base) : 0;
-        const int rel = x_t - t0;
-        const uint32_t my_off = (uint32_t)min(max(rel, 0), max(nt - 1, 0)) * (uint32_t)(FW * 8);
-        const float my_f = (x_val + f_shift) * f_scale;
-        const bool same_row = base + 32 < end;
-        const int pf_base = same_row ? base + 32 : nbeg, pf_end = same_row ? end : nend;
-        x_t = t0; x_val = 0.f;
-        if (pf_base + lane < pf_end) {
-            x_t = other[pf_base + lane]; x_val = val[pf_base + lane];
-            bad |= (x_t < t0) | (x_t >= t0 + nt);
-        }
-        __syncwarp();
-        slot[lane] = EdgeSlot{my_off, my_f};
-        __syncwarp();
-        int j0 = 0;
-#pragma unroll 4
-        for (; j0 + EPS <= n; j0 += EPS) {
-            const EdgeSlot e = slot[j0 + grp];
-            accumulate(lds4(tl + e.off), lds4(tl + e.off + FW * 4), e.f);
-        }
-        if (j0 + grp < n) {
-            const EdgeSlot e = slot[j0 + grp];
-            accumulate(lds4(tl + e.off), lds4(tl + e.off + FW * 4), e.f);
-        }
-        if (same_row) { base += 32; continue; }
+    const uint32_t gring = ring + (uint32_t)((warp * 2 * G + grp) * RING_GROUP);
+    constexpr uint32_t BUF = (uint32_t)(G * RING_GROUP);
+    // chunk c of a group's segment: RING_CH pairs copied unconditionally (the pair buffers are padded; entries beyond
+    // the segment are overwritten with the poison pair when the chunk is consumed)
+    auto issue = [&](const int2* __restrict__ src, const int c, const uint32_t buf) {
+        const int2* __restrict__ p = src + c * RING_CH + l;
 #pragma unroll
-        for (int m = LPE; m < 32; m <<= 1) {
-            a01.x += __shfl_xor_sync(0xffffffffu, a01.x, m); a01.y += __shfl_xor_sync(0xffffffffu, a01.y, m);
-            a23.x += __shfl_xor_sync(0xffffffffu, a23.x, m); a23.y += __shfl_xor_sync(0xffffffffu, a23.y, m);
-        }
-        if (grp == 0) bst4(dS + (int64_t)row * D + fo + l * 4, make_float4(s_f * a01.x, s_f * a01.y, s_f * a23.x, s_f * a23.y));
-        if (nrow >= rb) break;
-        row = nrow; beg = nbeg; end = nend; base = beg; s4 = s_next;
-        a01 = f2(0.f, 0.f); a23 = a01;
-        nrow += BLK_WARPS; nbeg = 0; nend = 0;
+        for (int u = 0; u < CPL; ++u) cp8(gring + buf * BUF + (uint32_t)((l + u * LPE) * 8), p + u * LPE);
+        cp_commit();
+    };
+    // entries [n - j0, RING_CH) of the chunk that just landed do not belong to the segment: point them at the poison row
+    auto patch = [&](const int n_left, const uint32_t buf) {
+#pragma unroll
+        for (int u = 0; u < CPL; ++u)
+            if (l + u * LPE >= n_left)
+                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(gring + buf * BUF + (uint32_t)((l + u * LPE) * 8)), "r"(poison_idx), "r"(0) : "memory");
+    };
+    constexpr int STRIDE = BLK_WARPS * RPW;
+    int row = ra + warp * RPW + rsel;
+    int beg = 0, end = 0;
+    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < rb) { beg = ptr[row]; end = ptr[row + 1]; s4 = bld4(S + (int64_t)row * D + fo + l * 4); }
+    int e, n;
+    group_segment<SPLIT>(beg, end, sub, e, n);
+    if (!table_ok) n = 0;
+    uint32_t cur = 0;
+    issue(pair + e, 0, cur);
+    while (__any_sync(0xffffffffu, row < rb)) {
+        const int nrow = row + STRIDE;
+        int nbeg = 0, nend = 0;
+        float4 s_next = make_float4(0.f, 0.f, 0.f, 0.f);
         if (nrow < rb) { nbeg = ptr[nrow]; nend = ptr[nrow + 1]; s_next = bld4(S + (int64_t)nrow * D + fo + l * 4); }
+        const int nmax = __reduce_max_sync(0xffffffffu, n);
+        const int2* __restrict__ pp = pair + e;
+        float2 a01 = f2(0.f, 0.f), a23 = a01;
+        auto step = [&](const uint32_t addr, const float f) {
+            const float4 r = lds4(addr), g = lds4(addr ^ (uint32_t)(FW * 4));  // [R | G] halves of the table row
+            float2 z01, z23;
+            preact(r, w4, s4, f, z01, z23);  // the forward's association: (R[t] + f w) + S[s]
+            const float2 m01 = active2<NEG>(z01), m23 = active2<NEG>(z23);
+            const float2 g01 = __fmul2_rn(m01, f2(g.x, g.y)), g23 = __fmul2_rn(m23, f2(g.z, g.w));
+            a01 = __fadd2_rn(a01, g01);
+            a23 = __fadd2_rn(a23, g23);
+            const float2 ff = f2(f, f);
+            dw01 = __ffma2_rn(ff, g01, dw01);
+            dw23 = __ffma2_rn(ff, g23, dw23);
+        };
+        // address of receiver i's R half: rows of FW * 8 bytes; odd rows hold [G | R] so that two 64-byte slices read by
+        // one quarter-warp (FW = 16) fall into different bank halves whenever the rows differ in parity
+        auto row_addr = [&](const int i) {
+            const uint32_t li = (uint32_t)(i - t0);
+            return (tbase + li * (uint32_t)(FW * 8)) ^ (FW == 16 ? (li & 1u) * 64u : 0u);
+        };
+        int ne = 0, nn = 0;
+        bool next_issued = false;
+        for (int j0 = 0, c = 0; j0 < nmax; j0 += RING_CH, ++c) {
+            cp_wait0();
+            patch(n - j0, cur);
+            __syncwarp();
+            if (j0 + RING_CH < nmax) issue(pp, c + 1, cur ^ 1u);
+            else {
+                group_segment<SPLIT>(nbeg, nend, sub, ne, nn);
+                if (!table_ok) nn = 0;
+                issue(pair + ne, 0, cur ^ 1u);
+                next_issued = true;
+            }
+            const uint32_t buf = gring + cur * BUF;
+            const int jn = min(RING_CH, nmax - j0);
+#pragma unroll 4
+            for (int t = 0; t < jn; ++t) {
+                const int2 p = lds_pair(buf + (uint32_t)t * 8u);
+                step(row_addr(p.x), __int_as_float(p.y));
+            }
+            cur ^= 1u;
+        }
+        if (!next_issued) {
+            group_segment<SPLIT>(nbeg, nend, sub, ne, nn);
+            if (!table_ok) nn = 0;
+            cp_wait0();
+            __syncwarp();
+            issue(pair + ne, 0, cur);
+        }
+        if (SPLIT > 1) {
+#pragma unroll
+            for (int m = LPE; m < LPE * SPLIT; m <<= 1) {
+                a01.x += __shfl_xor_sync(0xffffffffu, a01.x, m); a01.y += __shfl_xor_sync(0xffffffffu, a01.y, m);
+                a23.x += __shfl_xor_sync(0xffffffffu, a23.x, m); a23.y += __shfl_xor_sync(0xffffffffu, a23.y, m);
+            }
+        }
+        if (row < rb && sub == 0)
+            bst4(dS + (int64_t)row * D + fo + l * 4, make_float4(s_f * a01.x, s_f * a01.y, s_f * a23.x, s_f * a23.y));
+        row = nrow; s4 = s_next; e = ne; n = nn;
     }
-    if (bad) atomicOr(err_flag, 4);
+    cp_wait0();
 }
 
-template <int FW>
+template <int FW, int SPLIT>
 __global__ void __launch_bounds__(BLK_THREADS, 1)
-edge_block_backward_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ other, const float* __restrict__ val,
-                           const int32_t* __restrict__ send_off, const int32_t* __restrict__ recv_off, const int K,
-                           const float* __restrict__ R, const float* __restrict__ S, const float* __restrict__ G,
-                           const float* __restrict__ w_edge, EdgeScalars sc, float* __restrict__ dS,
-                           float* __restrict__ dw_partials, int32_t* __restrict__ err_flag, const int table_rows) {
+edge_block_backward_kernel(const int32_t* __restrict__ ptr, const int2* __restrict__ pair, const int32_t* __restrict__ send_off,
+                           const int32_t* __restrict__ recv_off, const int K, const float* __restrict__ R,
+                           const float* __restrict__ S, const float* __restrict__ G, const float* __restrict__ w_edge,
+                           const float* __restrict__ s_f_ptr, float* __restrict__ dS, float* __restrict__ dw_partials,
+                           const int table_rows) {
     extern __shared__ __align__(16) uint8_t blk_smem[];
     __shared__ int s_range[2];
     __shared__ __align__(16) float red[BLK_WARPS][FW];
-    __shared__ __align__(16) EdgeSlot s_slot[BLK_WARPS][32];
     pdl_enter();
     constexpr int LPE = FW / 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane / LPE, l = lane - grp * LPE;
     const int b = blockIdx.x / K, k = blockIdx.x - b * K, fo = blockIdx.y * FW;
     const int r0 = send_off[b], r1 = send_off[b + 1], t0 = recv_off[b];
     const int nt = min(recv_off[b + 1] - t0, table_rows);
-    const float s_f = *sc.s_f;
+    const float s_f = *s_f_ptr;
     int ra, rb;
     block_row_split(ptr, r0, r1, k, K, s_range, ra, rb);
     float2 dw01 = f2(0.f, 0.f), dw23 = dw01;
@@ -331,13 +439,22 @@ edge_block_backward_kernel(const int32_t* __restrict__ ptr, const int32_t* __res
         for (int i = threadIdx.x; i < (rb - ra) * C; i += BLK_THREADS)
             bst4(dS + (int64_t)(ra + i / C) * D + fo + (i % C) * 4, make_float4(0.f, 0.f, 0.f, 0.f));
     } else {
-        const uint32_t table = smem_addr(blk_smem);
-        stage_table<FW, FW * 8>(table, R, t0, nt, fo);
-        stage_table<FW, FW * 8>(table + FW * 4, G, t0, nt, fo);
+        // 256-byte aligned: the [R | G] halves of a row are addressed with XOR
+        const uint32_t table = (smem_addr(blk_smem) + 255u) & ~255u;
+        uint8_t* const table_gen = blk_smem + (table - smem_addr(blk_smem));
+        stage_pair_table<FW>(table, R, G, t0, nt, fo);
+        // poison row behind the tables (an EVEN row index, so its layout is [R slice = -/+ huge | G slice = 0])
+        const uint32_t poison_row = (uint32_t)((table_rows + 1) & ~1) * (uint32_t)(FW * 8);
+        if (threadIdx.x < 2 * FW)
+            reinterpret_cast<float*>(table_gen + poison_row)[threadIdx.x] = threadIdx.x < FW ? (s_f < 0.f ? 3.0e38f : -3.0e38f) : 0.f;
         cp_wait_all();
         __syncthreads();
-        if (s_f < 0.f) block_backward_rows<FW, true>(ptr, other, val, ra, rb, t0, nt, table, S, w_edge, sc, dS, fo, dw01, dw23, err_flag, s_slot[warp]);
-        else block_backward_rows<FW, false>(ptr, other, val, ra, rb, t0, nt, table, S, w_edge, sc, dS, fo, dw01, dw23, err_flag, s_slot[warp]);
+        // (t0 rows are subtracted in the row index, not the address: the parity swizzle of FW = 16 uses block-local rows)
+        const uint32_t tbase = table + (uint32_t)l * 16u;
+        const int poison_idx = t0 + ((table_rows + 1) & ~1);  // the (even, block-local) receiver index of the poison row
+        const uint32_t ring = table + poison_row + (uint32_t)(FW * 8);
+        if (s_f < 0.f) walk_backward<FW, true, SPLIT>(ptr, pair, ra, rb, nt > 0, tbase, poison_idx, ring, S, w_edge, s_f, dS, fo, dw01, dw23, t0);
+        else walk_backward<FW, false, SPLIT>(ptr, pair, ra, rb, nt > 0, tbase, poison_idx, ring, S, w_edge, s_f, dS, fo, dw01, dw23, t0);
     }
     // edge-weight gradient of this CTA: lane groups -> warp (shuffles), warps -> CTA (shared memory), all in a fixed order
 #pragma unroll
@@ -359,8 +476,11 @@ edge_block_backward_kernel(const int32_t* __restrict__ ptr, const int32_t* __res
 // Feature-slice width and row splits for a convolution over `n_blocks` blocks whose largest staged side has
 // `max_table_rows` rows (`tables` tables of that many rows are staged: 1 forward, 2 backward).  0 = does not fit.
 static int plan_slice_width(int64_t max_table_rows, int tables) {
+    static const int only = [] { const char* e = getenv("GCNN_BLOCK_FW"); return e ? atoi(e) : 0; }();  // experiments
     for (int fw : {32, 16})
-        if (max_table_rows * fw * 4 * tables <= BLK_SMEM_BUDGET) return fw;
+        if ((only == 0 || only == fw) &&
+            256 + (max_table_rows + 2) * fw * 4 * tables + (fw == 32 ? ring_bytes<32>() : ring_bytes<16>()) <= BLK_SMEM_BUDGET)
+            return fw;  // + the poison row (+ one row of alignment slack) + the pair ring
     return 0;
 }
 static int plan_row_splits(int64_t n_blocks, int fw) {
@@ -373,7 +493,6 @@ static int plan_row_splits(int64_t n_blocks, int fw) {
 bool edge_block_fits(int64_t max_send_rows, int64_t max_recv_rows, bool training) {
     return plan_slice_width(max_send_rows, 1) != 0 && (!training || plan_slice_width(max_recv_rows, 2) != 0);
 }
-
 bool edge_block_backward_fits(int64_t max_recv_rows) { return plan_slice_width(max_recv_rows, 2) != 0; }
 
 template <typename Kern>
@@ -382,26 +501,38 @@ static int set_max_smem(Kern kern) {
     return GCNN_OK;
 }
 
+// One row per lane group when a CTA's rows fill (most of) its groups; the groups of a warp share one row otherwise (few
+// long rows: the 64 cut rows of a sample).  GCNN_BLOCK_SPLIT=0/1 forces one mapping (experiments).
+static bool split_rows(int64_t n_rows, int64_t n_ctas_x, int fw) {
+    static const int forced = [] { const char* e = getenv("GCNN_BLOCK_SPLIT"); return e ? atoi(e) : -1; }();
+    if (forced >= 0) return forced != 0;
+    const int64_t groups = (int64_t)BLK_WARPS * (32 / (fw / 4));
+    return n_rows < n_ctas_x * groups * 3 / 4;
+}
+
 int edge_block_forward(const EdgeLayout& by_recv, const int32_t* recv_off, const int32_t* send_off, int64_t n_blocks,
-                       int64_t max_send_rows, const float* R, const float* S, const float* w_edge, EdgeScalars sc, float* H,
-                       float* cnt, int32_t* err_flag, cudaStream_t st, double prof_bytes) {
+                       int64_t n_recv, int64_t max_send_rows, const float* R, const float* S, const float* w_edge,
+                       EdgeScalars sc, float* H, float* cnt, cudaStream_t st, double prof_bytes) {
     if (n_blocks <= 0) return GCNN_OK;
     const int fw = plan_slice_width(max_send_rows, 1);
-    if (fw == 0) { set_error("edge_block_forward: a block's source table does not fit in shared memory"); return GCNN_INVALID; }
+    if (fw == 0 || !by_recv.pair) { set_error("edge_block_forward: no block layout, or a block's source table does not fit in shared memory"); return GCNN_INVALID; }
     const int K = plan_row_splits(n_blocks, fw);
     const int rows = (int)(max_send_rows > 0 ? max_send_rows : 1);
-    const size_t smem = (size_t)rows * fw * 4;
+    const size_t smem = (size_t)(rows + 1) * fw * 4 + (fw == 32 ? ring_bytes<32>() : ring_bytes<16>());
     const dim3 grid((unsigned)(n_blocks * K), D / fw);
+    const bool split = split_rows(n_recv, grid.x, fw);
     ProfScope prof(PROF_EDGE_FWD, prof_bytes, st);
-#define GCNN_BLK_FWD(FW_, TRAIN_)                                                                                         \
+#define GCNN_BLK_FWD(FW_, TRAIN_, SPLIT_)                                                                                 \
     do {                                                                                                                   \
-        static int once = set_max_smem(edge_block_forward_kernel<FW_, TRAIN_>);                                            \
+        static int once = set_max_smem(edge_block_forward_kernel<FW_, TRAIN_, SPLIT_>);                                    \
         GCNN_TRY(once);                                                                                                    \
-        GCNN_LAUNCH((edge_block_forward_kernel<FW_, TRAIN_>), grid, BLK_THREADS, smem, st, by_recv.ptr, by_recv.other,      \
-                    by_recv.val, recv_off, send_off, K, R, S, w_edge, sc, H, cnt, err_flag, rows);                         \
+        GCNN_LAUNCH((edge_block_forward_kernel<FW_, TRAIN_, SPLIT_>), grid, BLK_THREADS, smem, st, by_recv.ptr,            \
+                    by_recv.pair, recv_off, send_off, K, R, S, w_edge, sc.s_f, H, cnt, rows);                             \
     } while (0)
-    if (fw == 32) { if (cnt) GCNN_BLK_FWD(32, true); else GCNN_BLK_FWD(32, false); }
-    else { if (cnt) GCNN_BLK_FWD(16, true); else GCNN_BLK_FWD(16, false); }
+#define GCNN_BLK_FWD2(FW_, TRAIN_) do { if (split) GCNN_BLK_FWD(FW_, TRAIN_, (32 / (FW_ / 4))); else GCNN_BLK_FWD(FW_, TRAIN_, 1); } while (0)
+    if (fw == 32) { if (cnt) GCNN_BLK_FWD2(32, true); else GCNN_BLK_FWD2(32, false); }
+    else { if (cnt) GCNN_BLK_FWD2(16, true); else GCNN_BLK_FWD2(16, false); }
+#undef GCNN_BLK_FWD2
 #undef GCNN_BLK_FWD
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
@@ -410,95 +541,121 @@ int edge_block_forward(const EdgeLayout& by_recv, const int32_t* recv_off, const
 int edge_block_backward_max_partials() { return (int)(MAX_RECORDS > NUM_SMS ? MAX_RECORDS : NUM_SMS); }  // grid.x <= max(148, blocks)
 
 int edge_block_backward(const EdgeLayout& by_send, const int32_t* send_off, const int32_t* recv_off, int64_t n_blocks,
-                        int64_t max_recv_rows, const float* R, const float* S, const float* G, const float* w_edge,
-                        EdgeScalars sc, float* dS, float* dw_partials, int* n_partials, int32_t* err_flag, cudaStream_t st,
+                        int64_t n_send, int64_t max_recv_rows, const float* R, const float* S, const float* G,
+                        const float* w_edge, EdgeScalars sc, float* dS, float* dw_partials, int* n_partials, cudaStream_t st,
                         double prof_bytes) {
     *n_partials = 0;
     if (n_blocks <= 0) return GCNN_OK;
     const int fw = plan_slice_width(max_recv_rows, 2);
-    if (fw == 0) { set_error("edge_block_backward: a block's receiver tables do not fit in shared memory"); return GCNN_INVALID; }
+    if (fw == 0 || !by_send.pair) { set_error("edge_block_backward: no block layout, or a block's receiver tables do not fit in shared memory"); return GCNN_INVALID; }
     const int K = plan_row_splits(n_blocks, fw);
     const int rows = (int)(max_recv_rows > 0 ? max_recv_rows : 1);
-    const size_t smem = (size_t)rows * fw * 4 * 2;
+    const size_t smem = 256 + (size_t)(((rows + 1) & ~1) + 1) * fw * 4 * 2 + (fw == 32 ? ring_bytes<32>() : ring_bytes<16>());
     const dim3 grid((unsigned)(n_blocks * K), D / fw);
     *n_partials = (int)grid.x;
+    const bool split = split_rows(n_send, grid.x, fw);
     ProfScope prof(PROF_EDGE_BWD, prof_bytes, st);
-#define GCNN_BLK_BWD(FW_)                                                                                                  \
+#define GCNN_BLK_BWD(FW_, SPLIT_)                                                                                          \
     do {                                                                                                                   \
-        static int once = set_max_smem(edge_block_backward_kernel<FW_>);                                                   \
+        static int once = set_max_smem(edge_block_backward_kernel<FW_, SPLIT_>);                                           \
         GCNN_TRY(once);                                                                                                    \
-        GCNN_LAUNCH(edge_block_backward_kernel<FW_>, grid, BLK_THREADS, smem, st, by_send.ptr, by_send.other, by_send.val,  \
-                    send_off, recv_off, K, R, S, G, w_edge, sc, dS, dw_partials, err_flag, rows);                          \
+        GCNN_LAUNCH((edge_block_backward_kernel<FW_, SPLIT_>), grid, BLK_THREADS, smem, st, by_send.ptr, by_send.pair,      \
+                    send_off, recv_off, K, R, S, G, w_edge, sc.s_f, dS, dw_partials, rows);                                \
     } while (0)
-    if (fw == 32) GCNN_BLK_BWD(32); else GCNN_BLK_BWD(16);
+    if (fw == 32) { if (split) GCNN_BLK_BWD(32, 4); else GCNN_BLK_BWD(32, 1); }
+    else { if (split) GCNN_BLK_BWD(16, 8); else GCNN_BLK_BWD(16, 1); }
 #undef GCNN_BLK_BWD
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Transposed layout of a block-diagonal edge list sorted by its left index: one CTA per block runs a stable counting
-// sort on the block's variable indices.  Output identical to build_layout's radix path (perm == argsort(keys, stable)).
-//   pass 1  warp w histograms its contiguous share of the block's edges into its own row hist[w][.] (match.any
-//           aggregation, no atomics);
-//   scan    per variable: exclusive prefix over the warps' counts + exclusive prefix over variables -> ptr, slot bases;
-//   pass 2  every warp walks its share again in order and places each edge at base + (rank among equal keys so far).
+// Transposed layout of a block-diagonal edge list sorted by its left index: a stable counting sort on the block's
+// variable indices inside CTAs.  Output identical to build_layout's radix path (perm == argsort(keys, stable)).
+// CTA (b, r) owns variable range r of block b (R ranges per block, so that 32 blocks still fill the GPU: the scattered
+// 4-byte stores of the placement pass cost one LSU cycle each and bound the kernel):
+//   pass 1  every warp reads its contiguous share of ALL the block's edges; keys inside the CTA's range go to the warp's
+//           own histogram row hist[w][.] (shared-memory atomics inside a warp-private row), keys below it are counted;
+//   scan    per variable: exclusive prefix over the warps' counts + exclusive prefix over variables -> ptr, slot bases
+//           (the range starts behind the edges of all lower variables of the block);
+//   pass 2  every warp walks its share again in order, 32 edges per round, and places the edges of the CTA's range at
+//           base + (rank among equal keys so far).  A round of 32 consecutive edges of a row-sorted list hardly ever holds
+//           the same variable twice, so the duplicate test is a tag write / read-back per lane in the warp's histogram
+//           row; only a round that does hold duplicates pays for match.any to rank them in edge order.
+// Also writes the layout's {receiver index clamped into the block, normalised coefficient} pairs for the block kernels.
 // ------------------------------------------------------------------------------------------------------------------
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 transpose_blocks_kernel(const int32_t* __restrict__ keys_var, const int32_t* __restrict__ keys_left,
                         const float* __restrict__ feats, const int64_t E, const int32_t n_left, const int32_t n_var,
                         const int32_t* __restrict__ left_off, const int32_t* __restrict__ var_off, const int n_blocks,
-                        const int var_cap, EdgeLayout out, int32_t* __restrict__ err_flag, int32_t* __restrict__ reordered_flag,
+                        const int var_cap, const int range_cap, EdgeLayout out, const float* __restrict__ f_shift,
+                        const float* __restrict__ f_scale, int32_t* __restrict__ err_flag, int32_t* __restrict__ reordered_flag,
                         int32_t* __restrict__ long_flag, const int long_row, const int heavy_row) {
     extern __shared__ __align__(16) uint8_t blk_smem[];
     __shared__ int s_e[2];
-    __shared__ int s_warp_tot[WARPS];
+    __shared__ int s_warp_tot[WARPS], s_warp_below[WARPS];
     pdl_enter();
     constexpr int T = WARPS * 32;
-    int32_t* hist = reinterpret_cast<int32_t*>(blk_smem);  // [WARPS][var_cap]
-    int32_t* total = hist + (size_t)WARPS * var_cap;       // [var_cap]
+    int32_t* hist = reinterpret_cast<int32_t*>(blk_smem);  // [WARPS][range_cap]
+    int32_t* total = hist + (size_t)WARPS * range_cap;     // [range_cap]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.x;
+    const int b = blockIdx.x, R = gridDim.y, r = blockIdx.y;
     const int l0 = left_off[b], l1 = left_off[b + 1], v0 = var_off[b];
     const int nv = min(var_off[b + 1] - v0, var_cap);
+    const int per_range = (nv + R - 1) / R;
+    const int lo = min(nv, r * per_range), hi = min(nv, lo + min(per_range, range_cap)), nr = hi - lo;
+    const float sh = f_shift ? *f_shift : 0.f, scl = f_scale ? *f_scale : 1.f;
     // the block's edges: [first e with left index >= l0, first e with left index >= l1) of the sorted list
     if (warp < 2) {
-        const int r = warp_lower_bound(keys_left, (int)E, warp == 0 ? l0 : l1, lane);  // (keys_left[E] is never read: i >= hi votes)
-        if (lane == 0) s_e[warp] = r;
+        const int x = warp_lower_bound(keys_left, (int)E, warp == 0 ? l0 : l1, lane);
+        if (lane == 0) s_e[warp] = x;
     }
-    for (int i = tid; i < WARPS * nv; i += T) hist[(i / nv) * var_cap + (i % nv)] = 0;
+    for (int i = tid; i < WARPS * nr; i += T) hist[(i / nr) * range_cap + (i % nr)] = 0;
     __syncthreads();
     const int e0 = s_e[0], e1 = max(s_e[1], s_e[0]);
     const int n_e = e1 - e0;
     const int share = ((n_e + WARPS - 1) / WARPS + 31) & ~31;
     const int wa = min(n_e, warp * share), wb = min(n_e, wa + share);
-    int32_t* my_hist = hist + (size_t)warp * var_cap;
-    bool bad = false;
-    if (b == 0 && tid == 0) *reordered_flag = 1;  // positions of this layout differ from the input order
+    int32_t* my_hist = hist + (size_t)warp * range_cap;
+    bool bad = nv <= 0 && n_e > 0;
+    if (b == 0 && r == 0 && tid == 0) *reordered_flag = 1;  // positions of this layout differ from the input order
     // pass 1
-    for (int base = wa; base < wb; base += 32) {
-        const int e = e0 + base + lane;
-        const bool valid = base + lane < wb;
-        int v = -1;
-        if (valid) {
-            const int key = keys_var[e];
-            bad |= (key < v0) | (key >= v0 + nv);
-            v = min(max(key - v0, 0), max(nv - 1, 0));
+    int below = 0;
+    if (nv > 0) {
+        constexpr int UNR = 8;
+        for (int base = wa; base < wb; base += 32 * UNR) {
+            int key[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int i = base + u * 32 + lane;
+                key[u] = i < wb ? keys_var[e0 + i] : v0 + nv;  // (a key beyond every range)
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                if (base + u * 32 + lane < wb) {
+                    bad |= (key[u] < v0) | (key[u] >= v0 + nv);
+                    const int v = min(max(key[u] - v0, 0), nv - 1);
+                    if (v < lo) ++below;
+                    else if (v < hi) atomicAdd(&my_hist[v - lo], 1);
+                }
+            }
         }
-        const unsigned peers = __match_any_sync(0xffffffffu, v);
-        if (valid && nv > 0 && (peers & ((1u << lane) - 1u)) == 0u) my_hist[v] += __popc(peers);
-        __syncwarp();
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+    if (lane == 0) s_warp_below[warp] = below;
     __syncthreads();
-    // scan: thread t owns variables [t * per, t * per + per)
-    const int per = (nv + T - 1) / T;
+    int below_total = 0;
+    for (int w = 0; w < WARPS; ++w) below_total += s_warp_below[w];
+    // scan: thread t owns variables [t * per, t * per + per) of the range
+    const int per = (nr + T - 1) / T;
     int local = 0, flags = 0;
     for (int j = 0; j < per; ++j) {
         const int v = tid * per + j;
-        if (v < nv) {
+        if (v < nr) {
             int tot = 0;
-            for (int w = 0; w < WARPS; ++w) tot += hist[(size_t)w * var_cap + v];
+            for (int w = 0; w < WARPS; ++w) tot += hist[(size_t)w * range_cap + v];
             total[v] = tot;
             local += tot;
             flags |= (tot > long_row ? 1 : 0) | (tot > heavy_row ? 2 : 0);
@@ -512,82 +669,121 @@ transpose_blocks_kernel(const int32_t* __restrict__ keys_var, const int32_t* __r
     }
     if (lane == 31) s_warp_tot[warp] = incl;
     __syncthreads();
-    int run = incl - local;
+    int run = below_total + incl - local;
     for (int w = 0; w < warp; ++w) run += s_warp_tot[w];
     for (int j = 0; j < per; ++j) {
         const int v = tid * per + j;
-        if (v < nv) {
-            out.ptr[v0 + v] = e0 + run;
+        if (v < nr) {
+            out.ptr[v0 + lo + v] = e0 + run;
             int slot = run;
             for (int w = 0; w < WARPS; ++w) {
-                const int c = hist[(size_t)w * var_cap + v];
-                hist[(size_t)w * var_cap + v] = slot;
+                const int c = hist[(size_t)w * range_cap + v];
+                hist[(size_t)w * range_cap + v] = slot;
                 slot += c;
             }
             run += total[v];
         }
     }
-    if (b == n_blocks - 1 && tid == 0) out.ptr[n_var] = (int32_t)E;
+    if (b == n_blocks - 1 && r == R - 1 && tid == 0) out.ptr[n_var] = (int32_t)E;
     if (flags) atomicOr(long_flag, flags);
     __syncthreads();
-    // pass 2
-    for (int base = wa; base < wb; base += 32) {
-        const int e = e0 + base + lane;
-        const bool valid = base + lane < wb;
-        int v = -1, left = 0;
-        float f = 0.f;
-        if (valid) {
-            v = min(max(keys_var[e] - v0, 0), max(nv - 1, 0));
-            left = keys_left[e];
-            f = feats[e];
+    // pass 2.  The duplicate test runs on the warp's own histogram row: a lane first reads its slot base, then swaps in a
+    // tag (~lane, negative) and reads it back after the warp has synchronised -- a lane that does not find its own tag
+    // shares its key with another lane of the round.
+    if (nr > 0) {
+        constexpr int UNR = 4;
+        for (int base = wa; base < wb; base += 32 * UNR) {
+            int key[UNR], left[UNR];
+            float f[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int i = base + u * 32 + lane;
+                const bool ok = i < wb;
+                key[u] = ok ? keys_var[e0 + i] : v0 + nv;
+                left[u] = ok ? keys_left[e0 + i] : 0;
+                f[u] = ok ? feats[e0 + i] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                if (base + u * 32 >= wb) break;  // warp-uniform
+                const int e = e0 + base + u * 32 + lane;
+                const int vb = min(max(key[u] - v0, 0), nv - 1);
+                const bool valid = base + u * 32 + lane < wb && vb >= lo && vb < hi;
+                const int v = valid ? vb - lo : 0;
+                int slot = 0;
+                if (valid) slot = my_hist[v];   // every lane of a key reads the same base (no writes since the last sync)
+                __syncwarp();
+                if (valid) my_hist[v] = ~lane;  // tag; one of the lanes sharing a key wins
+                __syncwarp();
+                const bool dup = valid && my_hist[v] != ~lane;
+                int rank = 0, count = 1;
+                if (__any_sync(0xffffffffu, dup)) {  // rare: rank equal keys in edge (= lane) order
+                    const unsigned peers = __match_any_sync(0xffffffffu, valid ? v : -1 - lane);
+                    rank = __popc(peers & ((1u << lane) - 1u));
+                    count = __popc(peers);
+                }
+                __syncwarp();
+                if (valid) {
+                    if (rank == 0) my_hist[v] = slot + count;  // the first lane of each key restores the advanced base
+                    const int pos = e0 + slot + rank;
+                    const int lc = min(max(left[u], l0), max(l1 - 1, l0));
+                    out.other[pos] = min(max(left[u], 0), n_left - 1);
+                    out.val[pos] = f[u];
+                    out.perm[pos] = e;
+                    out.pair_buf[pos] = make_int2(lc, __float_as_int((f[u] + sh) * scl));
+                    bad |= (left[u] < l0) | (left[u] >= l1);
+                }
+                __syncwarp();
+            }
         }
-        const unsigned peers = __match_any_sync(0xffffffffu, v);
-        const int rank = __popc(peers & ((1u << lane) - 1u));
-        int slot = 0;
-        if (valid && nv > 0) slot = my_hist[v];
-        __syncwarp();
-        if (valid && nv > 0) {
-            if (rank == 0) my_hist[v] = slot + __popc(peers);
-            const int pos = e0 + slot + rank;
-            out.other[pos] = min(max(left, 0), n_left - 1);
-            out.val[pos] = f;
-            out.perm[pos] = e;
-        }
-        __syncwarp();
     }
     if (bad) atomicOr(err_flag, 4);
 }
 
-// warps per CTA for blocks of up to `max_vars` variables (0 = does not fit: use the radix sort)
-static int plan_transpose_warps(int64_t max_vars) {
+// variable ranges per block (CTAs per block) and warps per CTA for blocks of up to `max_vars` variables; warps == 0: does
+// not fit, use the radix sort
+static void plan_transpose(int64_t n_blocks, int64_t max_vars, int& ranges, int& warps, int& range_cap) {
+    int64_t r = n_blocks > 0 ? NUM_SMS / n_blocks : 1;
+    ranges = (int)(r < 1 ? 1 : (r > 8 ? 8 : r));
+    range_cap = (int)((max_vars + ranges - 1) / ranges);
+    if (range_cap < 1) range_cap = 1;
+    warps = 0;
     for (int w : {32, 16, 8})
-        if ((int64_t)(w + 1) * max_vars * 4 <= BLK_SMEM_BUDGET) return w;
-    return 0;
+        if ((int64_t)(w + 1) * range_cap * 4 <= BLK_SMEM_BUDGET) { warps = w; break; }
 }
-bool transpose_blocks_fits(int64_t max_vars) { return plan_transpose_warps(max_vars) != 0; }
+bool transpose_blocks_fits(int64_t max_vars) {
+    int ranges, warps, cap;
+    plan_transpose(NUM_SMS, max_vars, ranges, warps, cap);  // the worst case: one range per block
+    return warps != 0;
+}
 
 int transpose_blocks(const int32_t* keys_var, const int32_t* keys_left, const float* feats, int64_t E, int64_t n_left,
                      int64_t n_var, const int32_t* left_off, const int32_t* var_off, int64_t n_blocks, int64_t max_vars,
-                     int32_t* err_flag, int32_t* unsorted_flag, EdgeLayout& out, cudaStream_t st) {
+                     const float* f_shift, const float* f_scale, int32_t* err_flag, int32_t* unsorted_flag, EdgeLayout& out,
+                     cudaStream_t st) {
     out.reordered = unsorted_flag;
     out.long_rows = unsorted_flag + LONG_FLAG_OFFSET;
-    const int warps = plan_transpose_warps(max_vars);
+    out.pair = out.pair_buf;
+    int ranges, warps, range_cap;
+    plan_transpose(n_blocks, max_vars, ranges, warps, range_cap);
     if (warps == 0 || E >= (int64_t)INT32_MAX) { set_error("transpose_blocks: block too large"); return GCNN_INVALID; }
     if (E == 0 || n_blocks <= 0) {
         GCNN_CUDA_TRY(cudaMemsetAsync(out.ptr, 0, sizeof(int32_t) * (size_t)(n_var + 1), st));
         return GCNN_OK;
     }
     const int cap = (int)(max_vars > 0 ? max_vars : 1);
-    const size_t smem = (size_t)(warps + 1) * cap * 4;
+    const size_t smem = (size_t)(warps + 1) * range_cap * 4;
     const int heavy = (int)max((int64_t)32, 4 * ceil_div(E, n_var > 0 ? n_var : 1));
-    ProfScope prof(PROF_CSR_SCATTER, 12.0 * (double)E + 12.0 * (double)E + 4.0 * (double)(n_var + 1), st);
+    const dim3 grid((unsigned)n_blocks, (unsigned)ranges);
+    ProfScope prof(PROF_CSR_SCATTER, 12.0 * (double)E + 20.0 * (double)E + 4.0 * (double)(n_var + 1), st);
 #define GCNN_TR(W_)                                                                                                        \
     do {                                                                                                                   \
         static int once = set_max_smem(transpose_blocks_kernel<W_>);                                                       \
         GCNN_TRY(once);                                                                                                    \
-        GCNN_LAUNCH_ORDERED(transpose_blocks_kernel<W_>, (unsigned)n_blocks, W_ * 32, smem, st, keys_var, keys_left, feats, \
-                            E, (int32_t)n_left, (int32_t)n_var, left_off, var_off, (int)n_blocks, cap, out, err_flag,      \
-                            unsorted_flag, unsorted_flag + LONG_FLAG_OFFSET, long_row_threshold(), heavy);                 \
+        GCNN_LAUNCH_ORDERED(transpose_blocks_kernel<W_>, grid, W_ * 32, smem, st, keys_var, keys_left, feats, E,            \
+                            (int32_t)n_left, (int32_t)n_var, left_off, var_off, (int)n_blocks, cap, range_cap, out,       \
+                            f_shift, f_scale, err_flag, unsorted_flag, unsorted_flag + LONG_FLAG_OFFSET,                  \
+                            long_row_threshold(), heavy);                                                                  \
     } while (0)
     if (warps == 32) GCNN_TR(32); else if (warps == 16) GCNN_TR(16); else GCNN_TR(8);
 #undef GCNN_TR

@@ -18,6 +18,8 @@
 //   S0: reads B1, B0
 // Two mbarriers track the tensor core: `bar_d` (input-gradient MMAs of the stage, gates the epilogue) and `bar_w`
 // (weight-gradient MMAs, gates the overwrite of the tiles they read).
+#include <stdlib.h>
+
 #include "chain_common.cuh"
 
 namespace gcnn {
@@ -71,6 +73,7 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
     TS_MARK();  // previous grid done
     const uint32_t tm = tmem_slot;
     const uint32_t accA = tm, accB = tm + 64, acc_wn = tm + 128, acc_wo2 = tm + 192, acc_wo1 = tm + 256, acc_wf = tm + 320;
+    // (columns 384..511: the odd-k companions of accA and accB, chain_common.cuh)
 
     const int64_t n_tiles = ceil_div(a.M, TC_ROWS);
 
@@ -90,7 +93,7 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
                 mbar_wait(bar_ready, ph_r); ph_r ^= 1;
                 tc_fence_after();
                 mbar_wait(wbar0, 0);
-                issue_dgrad(accA, B0, W0, 0);
+                issue_dgrad(accA, B0, W0, 0, 384);
                 umma_commit(bar_d);
                 issue_wgrad<true>(acc_wn, B1, T16_BYTES, B0, wacc);
                 umma_commit(bar_w);
@@ -100,7 +103,7 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
                 mbar_wait(bar_ready, ph_r); ph_r ^= 1;
                 tc_fence_after();
                 mbar_wait(wbar1, 0);
-                issue_dgrad(accA, B2, W1, 0);
+                issue_dgrad(accA, B2, W1, 0, 384);
                 umma_commit(bar_d);
                 issue_wgrad<true>(acc_wo2, B0, T16_BYTES, B2, wacc);
                 umma_commit(bar_w);
@@ -111,8 +114,8 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
                 tc_fence_after();
                 mbar_wait(wbar2, (uint32_t)(it & 1));
                 mbar_wait(wbar0, 1);
-                issue_dgrad(accA, B1, W2, 0);
-                issue_dgrad(accB, B1, W0, 0);
+                issue_dgrad(accA, B1, W2, 0, 384);
+                issue_dgrad(accB, B1, W0, 0, 384);
                 umma_commit(bar_d);
                 issue_wgrad(acc_wo1, B0, 2 * T16_BYTES, B1, wacc);
                 umma_commit(bar_w);
@@ -125,7 +128,7 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
                 mbar_wait(bar_ready, ph_r); ph_r ^= 1;
                 tc_fence_after();
                 mbar_wait(wbar1, 1);
-                issue_dgrad(accA, B1, W1, 0);
+                issue_dgrad(accA, B1, W1, 0, 384);
                 umma_commit(bar_d);
                 issue_wgrad<true>(acc_wf, B0, T16_BYTES, B1, wacc);
                 umma_commit(bar_w);
@@ -181,7 +184,7 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
         tc_fence_after();
         {
             float v[NCOL];
-            tmem_ld16(accA + lane_off + (uint32_t)(ch * NCOL), v);
+            tmem_ld16_sum(accA + lane_off + (uint32_t)(ch * NCOL), 384, v);
             mask_row(B1g, r_own, ch, v);
             store_row(B2g, r_own, ch, v);
             bacc[0] += warp_colsum(v, lane);
@@ -203,7 +206,7 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
         tc_fence_after();
         {
             float v[NCOL];
-            tmem_ld16(accA + lane_off + (uint32_t)(ch * NCOL), v);
+            tmem_ld16_sum(accA + lane_off + (uint32_t)(ch * NCOL), 384, v);
             mask_row(B0g, r_own, ch, v);
             store_row(B1g, r_own, ch, v);
             bacc[1] += warp_colsum(v, lane);
@@ -227,8 +230,8 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
         tc_fence_after();
         {
             float v[NCOL], x[NCOL], dxt[NCOL];
-            tmem_ld16(accB + lane_off + (uint32_t)(ch * NCOL), dxt);
-            tmem_ld16(accA + lane_off + (uint32_t)(ch * NCOL), v);
+            tmem_ld16_sum(accB + lane_off + (uint32_t)(ch * NCOL), 384, dxt);
+            tmem_ld16_sum(accA + lane_off + (uint32_t)(ch * NCOL), 384, v);
 #pragma unroll
             for (int i = 0; i < NCOL; ++i) { v[i] *= s_p; x[i] = v[i] * deg; }
             bacc[2] += warp_colsum(x, lane);
@@ -266,7 +269,7 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
         tc_fence_after();
         {
             float v[NCOL];
-            tmem_ld16(accA + lane_off + (uint32_t)(ch * NCOL), v);
+            tmem_ld16_sum(accA + lane_off + (uint32_t)(ch * NCOL), 384, v);
             float* dr = a.dR + wrow0 * D + ch * NCOL;
             // G and dR = s_f G cnt through this warp's patch of B2 (free since S1's weight-gradient MMAs drained)
             warp_store_block(patch, v, a.G + wrow0 * D + ch * NCOL, rows_valid, lane,
@@ -337,11 +340,17 @@ extern "C" int gcnn_debug_chain_timing(long long* out, int cap) {  // timestamps
 #endif
 
 int conv_backward_part_floats() { return CONV_BWD_PART; }
+// CTAs (= weight-gradient partials) of a backward chain: one per SM.  GCNN_CHAIN_PARTS overrides it for accuracy
+// experiments (more CTAs = fewer tiles accumulated per TMEM accumulator).
+int chain_max_parts() {
+    static const int n = [] { const char* e = getenv("GCNN_CHAIN_PARTS"); const int x = e ? atoi(e) : NUM_SMS; return x < 1 ? NUM_SMS : x; }();
+    return n;
+}
 
 int tc_conv_backward(const ConvBwdArgs& a, int* n_parts, cudaStream_t st) {
     *n_parts = 0;
     if (a.M <= 0) return GCNN_OK;
-    const int parts = (int)min((int64_t)NUM_SMS, ceil_div(a.M, TC_ROWS));
+    const int parts = (int)min((int64_t)chain_max_parts(), ceil_div(a.M, TC_ROWS));
     *n_parts = parts;
     // algorithmic bytes: read dP, Y, U1, C, X_t, H, cnt; write dXt, G, dR (one 256-byte row each per node); five weight
     // images; one partial per CTA
@@ -422,8 +431,8 @@ tc_embed_backward_kernel(const EmbBwdArgs a) {
                 mbar_wait(bar_ready, ph_r); ph_r ^= 1;
                 tc_fence_after();
                 if (it == 0) mbar_wait(wbar, 0);
-                issue_dgrad(accA, B0, W0, 0);
-                if (two) issue_dgrad(accA, B2, W1, 1);
+                issue_dgrad(accA, B0, W0, 0, 320);
+                if (two) issue_dgrad(accA, B2, W1, 1, 320);
                 umma_commit(bar_d);
                 issue_wgrad<true>(acc_w0, B1, T16_BYTES, B0, wacc);
                 if (two) issue_wgrad<true>(acc_w1, B1, T16_BYTES, B2, wacc);
@@ -431,7 +440,7 @@ tc_embed_backward_kernel(const EmbBwdArgs a) {
                 // E1
                 mbar_wait(bar_ready, ph_r); ph_r ^= 1;
                 tc_fence_after();
-                issue_dgrad(accA, B0, W2, 0);
+                issue_dgrad(accA, B0, W2, 0, 320);
                 umma_commit(bar_d);
                 issue_wgrad<true>(acc_w2, B2, T16_BYTES, B0, wacc);
                 umma_commit(bar_w);
@@ -494,7 +503,7 @@ tc_embed_backward_kernel(const EmbBwdArgs a) {
         tc_fence_after();
         {
             float v[NCOL], xr[NCOL];
-            tmem_ld16(accA + lane_off + (uint32_t)(ch * NCOL), v);
+            tmem_ld16_sum(accA + lane_off + (uint32_t)(ch * NCOL), 320, v);
             mbar_wait(bar_w, ph_w); ph_w ^= 1;  // B0 (dP_0) and B2 (dP_1) are free: B2 hosts the transpose patches
             warp_gather_row(patch, dx, xr, lane);
 #pragma unroll
@@ -525,7 +534,7 @@ tc_embed_backward_kernel(const EmbBwdArgs a) {
         tc_fence_after();
         {
             float v[NCOL];
-            tmem_ld16(accA + lane_off + (uint32_t)(ch * NCOL), v);
+            tmem_ld16_sum(accA + lane_off + (uint32_t)(ch * NCOL), 320, v);
             mask_row(B2g, r_own, ch, v);
             bacc[1] += warp_colsum(v, lane);
             store_row(B1g, r_own, ch, v);
@@ -596,7 +605,7 @@ int tc_embed_backward(const EmbBwdArgs& a, int* n_parts, cudaStream_t st) {
     *n_parts = 0;
     if (a.M <= 0) return GCNN_OK;
     if (a.K > 14) { set_error("tc_embed_backward: at most 14 input features"); return GCNN_INVALID; }
-    const int parts = (int)min((int64_t)NUM_SMS, ceil_div(a.M, TC_ROWS));
+    const int parts = (int)min((int64_t)chain_max_parts(), ceil_div(a.M, TC_ROWS));
     *n_parts = parts;
     const double rows_moved = (a.dP1 ? 5.0 : 4.0);  // dP_j, out, dXt, h1 (256 B per node each) + the raw features
     ProfScope prof(PROF_EMB_BWD, (256.0 * rows_moved + 4.0 * a.K) * (double)a.M + 3.0 * W16_BYTES + 4.0 * EMB_BWD_PART * parts, st);

@@ -1,0 +1,14 @@
+#!/bin/bash
+# round 2, GPU call 4: pair-walker block kernels: parity + A/B + launch list
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/r2d_tests.log 2>&1; echo "tests exit $?" >> gpurun_out/r2d_tests.log
+tail -5 gpurun_out/r2d_tests.log
+for cfg in "auto:X=1" "generic:GCNN_BLOCKS=0" "fw16:GCNN_BLOCK_FW=16" "split1:GCNN_BLOCK_SPLIT=1" "split0:GCNN_BLOCK_SPLIT=0"; do
+  name=${cfg%%:*}; env=${cfg#*:}
+  env $env python bench.py --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/r2d_bench_$name.json 2> gpurun_out/r2d_bench_$name.err
+done
+python bench.py --steps 30 --warmup 5 --no-cpu-baseline --graphs-per-gpu 128 > gpurun_out/r2d_bench_auto_g128.json 2> gpurun_out/r2d_bench_auto_g128.err
+GCNN_BLOCKS=0 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --graphs-per-gpu 128 > gpurun_out/r2d_bench_generic_g128.json 2> gpurun_out/r2d_bench_generic_g128.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file gpurun_out/r2d_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r2d_ncu_list.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'edge_block|transpose_blocks' -s 12 -c 8 -o gpurun_out/r2d_blocks -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r2d_ncu_full.log 2>&1
+python scripts/show_bench.py gpurun_out/r2d_bench_*.json | grep -E "==|edge_|csr_|sum of"

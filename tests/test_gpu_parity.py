@@ -435,11 +435,11 @@ def test_wrong_per_sample_counts_are_reported(model):
     with torch.no_grad():
         assert torch.isfinite(model(batching.model_inputs(batch), False)).all()
     # counts that do not add up to the totals are ignored (generic path), not an error
-    batch[8] = np.array([1500, 400], np.int32)
-    bad = list(batching.model_inputs(batch, per_sample_counts=True))
-    ok = batching.model_inputs(batch)
+    good = batching.concat_samples(synth.make_samples("setcov", 2, seed0=1))
+    ok = batching.model_inputs(good)
     dev, _keep = model.prepare_inputs(ok)
-    dev.sample_n_cons, dev.sample_n_vars, dev.sample_n_cuts = (np.ascontiguousarray(x, np.int32).ctypes.data for x in bad[7:10])
+    wrong = [np.ascontiguousarray(x, np.int32) for x in (good[7], np.array([1500, 400]), good[9])]
+    dev.sample_n_cons, dev.sample_n_vars, dev.sample_n_cuts = (x.ctypes.data for x in wrong)
     dev.n_samples = 2
     with torch.no_grad():
         a = model._forward((dev, _keep), save_activations=False)
