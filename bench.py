@@ -417,10 +417,12 @@ def measure_other_configs(model, dev, reps: int = 30):
             with torch.no_grad():
                 ms = time_device(lambda: model._forward(inp, save_activations=False), reps, flush)
             p50, p95 = host_latency(lambda: model.score_host(hb), reps)
+            g50, g95 = host_latency(lambda: model.score_host(hb, graph=True), reps)  # one CUDA graph per shape
             c3.append({"shape": shape, "graphs": n, "n_cons": nc, "n_vars": nv, "n_cuts": nk, "edges": ec + ek,
                        "device_forward_ms": ms, "cuts_per_s": nk / (ms * 1e-3),
                        "edge_messages_per_s": (2 * ec + ek) / (ms * 1e-3),
-                       "score_host_ms_p50": p50, "score_host_ms_p95": p95})
+                       "score_host_ms_p50": p50, "score_host_ms_p95": p95,
+                       "score_host_graph_ms_p50": g50, "score_host_graph_ms_p95": g95})
     out["config3"] = {"workload": "combauc / capfac / indset shapes, inference cut scoring, batch 1 and 4", "cases": c3}
 
     # config 5: one MIPLIB-scale graph, forward scoring; whole-model algorithmic bytes (686 MB) / time

@@ -6,6 +6,6 @@ There is no CPU fallback: constructing ``GCNN`` without the built library or wit
 from . import batching, shards, synth  # noqa: F401
 from ._lib import GcnnError, InvalidArgumentError, ResourceExhaustedError  # noqa: F401
 from .batching import load_batch  # noqa: F401
-from .metrics import ranking_accuracy, ranking_deviation  # noqa: F401
+from .metrics import ranking_accuracy, ranking_deviation, select_cuts  # noqa: F401
 from .model import GCNN, HostBatch, PreNormException, PreNormLayer, StagedRecords  # noqa: F401
 from .trainer import DataParallelTrainer, reduce_bucket  # noqa: F401

@@ -64,10 +64,13 @@ SIGNATURES = {
     "gcnn_mse_seed": (_I, [_P, _P, _I64, _F, _P, _P, _P]),
     "gcnn_adam_step": (_I, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I64, _P, _P]),
     "gcnn_ranking_deviation": (_I, [_P, _P, _P, _I64, _I, _P, _P]),
+    "gcnn_select_cuts": (_I, [_P, _P, _P, _I64, _I64, C.c_double, C.c_double, _I64, _P, _P, _P]),
     "gcnn_forward_backward": (_I, [_P, _P, _P, _BP, _P, _F, _P, _P, _P, _P]),
     "gcnn_prenorm_stats": (_I, [_P, _P, _P, _BP, _I, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                 C.POINTER(C.c_double), _P]),
     "gcnn_score_host": (_I, [_P, _P, _P, _BP, _P, _P]),
+    "gcnn_score_host_graph": (_I, [_P, _P, _P, _BP, _P, _P]),
+    "gcnn_serve_graph_count": (_I, [_P]),
     "gcnn_train_step_host": (_I, [_P, _P, _P, _P, _P, _BP, _P, _F, _I64, C.POINTER(_F), _P]),
     "gcnn_stage_host_batch": (_I, [_P, _I, _BP, _P]),
     "gcnn_record_bytes": (_I64, [_I64, _I64, _I64, _I64, _I64, _I]),

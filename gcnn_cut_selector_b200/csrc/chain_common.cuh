@@ -7,7 +7,7 @@
 namespace gcnn {
 
 #ifndef GCNN_ACT_PIECES
-#define GCNN_ACT_PIECES 3
+#define GCNN_ACT_PIECES 2
 #endif
 constexpr int ACT_PIECES = GCNN_ACT_PIECES;  // bf16 pieces of a saved activation in the weight-gradient MMAs
 
@@ -53,45 +53,22 @@ __device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) 
 // The product loop is NOT unrolled and the tile addresses are laundered through an empty asm: the MMA warp runs on a
 // small register budget, and ~600 hoisted loop-invariant descriptors would spill to local memory between the MMAs.
 //
-// The tensor core rounds every accumulation toward zero, so a chain of MMAs into one accumulator picks up a bias of
-// about half an ulp per full-magnitude accumulation (the four k-steps of the leading (0,0) product): ~2.4e-7 per layer,
-// ~2e-6 in the scores after the ~8 dense layers of a forward pass and, through an ill-conditioned gradient sum, 1.3e-5
-// in one weight gradient of the 32-graph batch (profiles/r2_grad_errors_*.json).  GCNN_DGRAD_SPLIT (default on) sends
-// the even and the odd k-steps to TWO accumulators `pair_off` columns apart; the epilogue adds them in fp32 with round to
-// nearest (tmem_ld16_sum): half the truncations per accumulator at no extra MMA.
-#ifndef GCNN_DGRAD_SPLIT
-#define GCNN_DGRAD_SPLIT 1
-#endif
-__device__ __forceinline__ void issue_dgrad(uint32_t tmem_d, uint32_t a_tile, uint32_t w_img, uint32_t acc, uint32_t pair_off) {
+// (Tried in round 2: even / odd k-steps into two accumulators that the epilogue adds with round-to-nearest, to halve the
+// tensor core's truncating accumulations.  Scores moved from 2.6e-6 to 1.6e-6 of the fp64 oracle, the worst gradient
+// tensor did not improve and the backward chains took 9 % longer -- not kept; profiles/r2_grad_errors.md.)
+__device__ __forceinline__ void issue_dgrad(uint32_t tmem_d, uint32_t a_tile, uint32_t w_img, uint32_t acc) {
     asm volatile("" : "+r"(a_tile), "+r"(w_img));
     const uint64_t da0 = make_desc(a_tile), db0 = make_desc(w_img);
-    uint32_t acc_odd = acc;
-    const uint32_t tmem_odd = GCNN_DGRAD_SPLIT ? tmem_d + pair_off : tmem_d;
 #pragma unroll 1
     for (int p = 0; p < 6; ++p) {
         const uint32_t pa = (0x001012u >> (4 * p)) & 3u, pb = (0x010210u >> (4 * p)) & 3u;  // (2,0) (1,1) (0,2) (1,0) (0,1) (0,0)
         const uint64_t da = da0 + (uint64_t)(pa * (T16_PIECE >> 4)), db = db0 + (uint64_t)(pb * (W16_PIECE >> 4));
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-            if (GCNN_DGRAD_SPLIT && (ks & 1)) {
-                umma_bf16(tmem_odd, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), IDESC_BF16_KK, acc_odd);
-                acc_odd = 1;
-            } else {
-                umma_bf16(tmem_d, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), IDESC_BF16_KK, acc);
-                acc = 1;
-            }
+            umma_bf16(tmem_d, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), IDESC_BF16_KK, acc);
+            acc = 1;
         }
     }
-}
-// accumulator block of a dgrad chain: the even-k accumulator plus (GCNN_DGRAD_SPLIT) its odd-k companion
-__device__ __forceinline__ void tmem_ld16_sum(uint32_t taddr, uint32_t pair_off, float (&v)[16]) {
-    tmem_ld16(taddr, v);
-#if GCNN_DGRAD_SPLIT
-    float w[16];
-    tmem_ld16(taddr + pair_off, w);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] += w[i];
-#endif
 }
 
 // dW[f][c] (+)= sum over the 128 lines of act[line][f] * g[line][c]: both operands MN-major views of bf16x3 tiles, the
@@ -166,8 +143,10 @@ __device__ __forceinline__ void load_tile(float4 (&reg)[NLD], const float* __res
 }
 // PIECES = 3 for gradient tiles (operands of the input-gradient MMAs, fp32-level accuracy through the chain).  The saved
 // activations -- only the A operand of a weight-gradient MMA and the source of the ReLU masks -- carry ACT_PIECES
-// pieces: 3 (default: all six products, dropped terms <= 2^-24, weight gradients within 1e-5 of the fp64 oracle) or 2
-// (-DGCNN_ACT_PIECES=2: five products, ~3e-6 relative L2 error per weight gradient; kept for the A/B in profiles/).
+// pieces: 2 (default: five products; a sum over all rows leaves ~3e-6 relative L2 error) or 3 (-DGCNN_ACT_PIECES=3: all six
+// products).  Measured on every fixture (profiles/r2_grad_errors.md): the third piece changes no gradient error beyond the
+// third digit -- the error of the tensor-core path comes from the truncating accumulation of the MMAs, not from the
+// dropped (2,0) product -- and costs 20 % more weight-gradient MMAs.
 template <int PIECES>
 __device__ __forceinline__ void store_half_chunk3(uint8_t* tile, int line, int f4, float4 v) {
     uint2 q0, q1, q2;

@@ -406,6 +406,10 @@ int adam_step(float* params, const float* grads, float* m, float* v, int64_t n, 
 int ranking_deviation(const float* pred, const float* truth, const int32_t* offsets_dev, int64_t n_samples, int max_cuts,
                       int32_t* deviation, cudaStream_t st);
 
+// ranking + parallelism filter of the cut-selector plug-in (model_benchmarker.py:108-157), one CTA (select.cu)
+int select_cuts(const float* quality, const float* par_forced, const float* par, int64_t n, int64_t n_forced, double p_max,
+                double p_max_ub, int64_t max_selected, int32_t* order_out, int32_t* n_selected_out, cudaStream_t st);
+
 // column statistics of a dense [M, K] matrix about `center` (double accumulators): out[0..K) = sum, out[K..2K) = sumsq
 int col_stats(const float* x, int64_t M, int K, const double* center_dev, double* partials, double* out,
               cudaStream_t st);

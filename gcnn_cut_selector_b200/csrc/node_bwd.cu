@@ -73,7 +73,6 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
     TS_MARK();  // previous grid done
     const uint32_t tm = tmem_slot;
     const uint32_t accA = tm, accB = tm + 64, acc_wn = tm + 128, acc_wo2 = tm + 192, acc_wo1 = tm + 256, acc_wf = tm + 320;
-    // (columns 384..511: the odd-k companions of accA and accB, chain_common.cuh)
 
     const int64_t n_tiles = ceil_div(a.M, TC_ROWS);
 
@@ -93,7 +92,7 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
                 mbar_wait(bar_ready, ph_r); ph_r ^= 1;
                 tc_fence_after();
                 mbar_wait(wbar0, 0);
-                issue_dgrad(accA, B0, W0, 0, 384);
+                issue_dgrad(accA, B0, W0, 0);
                 umma_commit(bar_d);
                 issue_wgrad<true>(acc_wn, B1, T16_BYTES, B0, wacc);
                 umma_commit(bar_w);
@@ -103,7 +102,7 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
                 mbar_wait(bar_ready, ph_r); ph_r ^= 1;
                 tc_fence_after();
                 mbar_wait(wbar1, 0);
-                issue_dgrad(accA, B2, W1, 0, 384);
+                issue_dgrad(accA, B2, W1, 0);
                 umma_commit(bar_d);
                 issue_wgrad<true>(acc_wo2, B0, T16_BYTES, B2, wacc);
                 umma_commit(bar_w);
@@ -114,8 +113,8 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
                 tc_fence_after();
                 mbar_wait(wbar2, (uint32_t)(it & 1));
                 mbar_wait(wbar0, 1);
-                issue_dgrad(accA, B1, W2, 0, 384);
-                issue_dgrad(accB, B1, W0, 0, 384);
+                issue_dgrad(accA, B1, W2, 0);
+                issue_dgrad(accB, B1, W0, 0);
                 umma_commit(bar_d);
                 issue_wgrad(acc_wo1, B0, 2 * T16_BYTES, B1, wacc);
                 umma_commit(bar_w);
@@ -128,7 +127,7 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
                 mbar_wait(bar_ready, ph_r); ph_r ^= 1;
                 tc_fence_after();
                 mbar_wait(wbar1, 1);
-                issue_dgrad(accA, B1, W1, 0, 384);
+                issue_dgrad(accA, B1, W1, 0);
                 umma_commit(bar_d);
                 issue_wgrad<true>(acc_wf, B0, T16_BYTES, B1, wacc);
                 umma_commit(bar_w);
@@ -184,7 +183,7 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
         tc_fence_after();
         {
             float v[NCOL];
-            tmem_ld16_sum(accA + lane_off + (uint32_t)(ch * NCOL), 384, v);
+            tmem_ld16(accA + lane_off + (uint32_t)(ch * NCOL), v);
             mask_row(B1g, r_own, ch, v);
             store_row(B2g, r_own, ch, v);
             bacc[0] += warp_colsum(v, lane);
@@ -206,7 +205,7 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
         tc_fence_after();
         {
             float v[NCOL];
-            tmem_ld16_sum(accA + lane_off + (uint32_t)(ch * NCOL), 384, v);
+            tmem_ld16(accA + lane_off + (uint32_t)(ch * NCOL), v);
             mask_row(B0g, r_own, ch, v);
             store_row(B1g, r_own, ch, v);
             bacc[1] += warp_colsum(v, lane);
@@ -230,8 +229,8 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
         tc_fence_after();
         {
             float v[NCOL], x[NCOL], dxt[NCOL];
-            tmem_ld16_sum(accB + lane_off + (uint32_t)(ch * NCOL), 384, dxt);
-            tmem_ld16_sum(accA + lane_off + (uint32_t)(ch * NCOL), 384, v);
+            tmem_ld16(accB + lane_off + (uint32_t)(ch * NCOL), dxt);
+            tmem_ld16(accA + lane_off + (uint32_t)(ch * NCOL), v);
 #pragma unroll
             for (int i = 0; i < NCOL; ++i) { v[i] *= s_p; x[i] = v[i] * deg; }
             bacc[2] += warp_colsum(x, lane);
@@ -269,7 +268,7 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
         tc_fence_after();
         {
             float v[NCOL];
-            tmem_ld16_sum(accA + lane_off + (uint32_t)(ch * NCOL), 384, v);
+            tmem_ld16(accA + lane_off + (uint32_t)(ch * NCOL), v);
             float* dr = a.dR + wrow0 * D + ch * NCOL;
             // G and dR = s_f G cnt through this warp's patch of B2 (free since S1's weight-gradient MMAs drained)
             warp_store_block(patch, v, a.G + wrow0 * D + ch * NCOL, rows_valid, lane,
@@ -431,8 +430,8 @@ tc_embed_backward_kernel(const EmbBwdArgs a) {
                 mbar_wait(bar_ready, ph_r); ph_r ^= 1;
                 tc_fence_after();
                 if (it == 0) mbar_wait(wbar, 0);
-                issue_dgrad(accA, B0, W0, 0, 320);
-                if (two) issue_dgrad(accA, B2, W1, 1, 320);
+                issue_dgrad(accA, B0, W0, 0);
+                if (two) issue_dgrad(accA, B2, W1, 1);
                 umma_commit(bar_d);
                 issue_wgrad<true>(acc_w0, B1, T16_BYTES, B0, wacc);
                 if (two) issue_wgrad<true>(acc_w1, B1, T16_BYTES, B2, wacc);
@@ -440,7 +439,7 @@ tc_embed_backward_kernel(const EmbBwdArgs a) {
                 // E1
                 mbar_wait(bar_ready, ph_r); ph_r ^= 1;
                 tc_fence_after();
-                issue_dgrad(accA, B0, W2, 0, 320);
+                issue_dgrad(accA, B0, W2, 0);
                 umma_commit(bar_d);
                 issue_wgrad<true>(acc_w2, B2, T16_BYTES, B0, wacc);
                 umma_commit(bar_w);
@@ -503,7 +502,7 @@ tc_embed_backward_kernel(const EmbBwdArgs a) {
         tc_fence_after();
         {
             float v[NCOL], xr[NCOL];
-            tmem_ld16_sum(accA + lane_off + (uint32_t)(ch * NCOL), 320, v);
+            tmem_ld16(accA + lane_off + (uint32_t)(ch * NCOL), v);
             mbar_wait(bar_w, ph_w); ph_w ^= 1;  // B0 (dP_0) and B2 (dP_1) are free: B2 hosts the transpose patches
             warp_gather_row(patch, dx, xr, lane);
 #pragma unroll
@@ -534,7 +533,7 @@ tc_embed_backward_kernel(const EmbBwdArgs a) {
         tc_fence_after();
         {
             float v[NCOL];
-            tmem_ld16_sum(accA + lane_off + (uint32_t)(ch * NCOL), 320, v);
+            tmem_ld16(accA + lane_off + (uint32_t)(ch * NCOL), v);
             mask_row(B2g, r_own, ch, v);
             bacc[1] += warp_colsum(v, lane);
             store_row(B1g, r_own, ch, v);

@@ -59,7 +59,7 @@ tc_conv_forward16_kernel(const ConvFwdArgs a) {
     const uint32_t wbar0 = smem_u32(&bars[2]), wbar1 = smem_u32(&bars[3]), wbar2 = smem_u32(&bars[4]);
     const bool has_next = a.img_n != nullptr;
 
-    if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), 128);  // accumulator + its odd-k companion (chain_common.cuh)
+    if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), 64);
     if (tid == 0) {
         for (int i = 0; i < 5; ++i) mbar_init(smem_u32(&bars[i]), 1);
     }
@@ -80,7 +80,7 @@ tc_conv_forward16_kernel(const ConvFwdArgs a) {
             mbar_wait(bar_ready, 0);
             tc_fence_after();
             mbar_wait(wbar0, 0);
-            issue_dgrad(acc, P, W0, 0, 64);
+            issue_dgrad(acc, P, W0, 0);
             umma_commit(bar_d);
             mbar_wait(bar_d, 0);  // slot 0 is free
             bulk_load(W0, a.img_o2, W16_BYTES, wbar0);
@@ -89,8 +89,8 @@ tc_conv_forward16_kernel(const ConvFwdArgs a) {
             tc_fence_after();
             mbar_wait(wbar1, 0);
             mbar_wait(wbar2, 0);
-            issue_dgrad(acc, P, W1, 0, 64);
-            issue_dgrad(acc, Q, W2, 1, 64);
+            issue_dgrad(acc, P, W1, 0);
+            issue_dgrad(acc, Q, W2, 1);
             umma_commit(bar_d);
             mbar_wait(bar_d, 1);  // slots 1 and 2 are free
             if (has_next) bulk_load(W1, a.img_n, W16_BYTES, wbar1);
@@ -98,13 +98,13 @@ tc_conv_forward16_kernel(const ConvFwdArgs a) {
             mbar_wait(bar_ready, 0);
             tc_fence_after();
             mbar_wait(wbar0, 1);
-            issue_dgrad(acc, P, W0, 0, 64);
+            issue_dgrad(acc, P, W0, 0);
             umma_commit(bar_d);
             if (has_next) {  // S3
                 mbar_wait(bar_ready, 1);
                 tc_fence_after();
                 mbar_wait(wbar1, 1);
-                issue_dgrad(acc, Q, W1, 0, 64);
+                issue_dgrad(acc, Q, W1, 0);
                 umma_commit(bar_d);
             }
         }
@@ -141,7 +141,7 @@ tc_conv_forward16_kernel(const ConvFwdArgs a) {
     // S0
     mbar_wait(bar_d, 0);
     tc_fence_after();
-    tmem_ld16_sum(acc + lane_off + (uint32_t)(ch * NCOL), 64, v);
+    tmem_ld16(acc + lane_off + (uint32_t)(ch * NCOL), v);
     bias_act<false>(v, bias_s[0], ch, deg);
     if (a.C) warp_store_block(patch, v, a.C + wrow0 * D + ch * NCOL, rows_valid, lane, StoreIdentity());
 #pragma unroll
@@ -151,7 +151,7 @@ tc_conv_forward16_kernel(const ConvFwdArgs a) {
     // S1
     mbar_wait(bar_d, 1);
     tc_fence_after();
-    tmem_ld16_sum(acc + lane_off + (uint32_t)(ch * NCOL), 64, v);
+    tmem_ld16(acc + lane_off + (uint32_t)(ch * NCOL), v);
     bias_act<true>(v, bias_s[1], ch, 1.f);
     if (a.U1) warp_store_block(patch, v, a.U1 + wrow0 * D + ch * NCOL, rows_valid, lane, StoreIdentity());
     store_row(Pg, r_own, ch, v);
@@ -159,7 +159,7 @@ tc_conv_forward16_kernel(const ConvFwdArgs a) {
     // S2
     mbar_wait(bar_d, 0);
     tc_fence_after();
-    tmem_ld16_sum(acc + lane_off + (uint32_t)(ch * NCOL), 64, v);
+    tmem_ld16(acc + lane_off + (uint32_t)(ch * NCOL), v);
     bias_act<true>(v, bias_s[2], ch, 1.f);
     warp_store_block(patch, v, a.Y + wrow0 * D + ch * NCOL, rows_valid, lane, StoreIdentity());
     if (has_next) {
@@ -168,14 +168,14 @@ tc_conv_forward16_kernel(const ConvFwdArgs a) {
         // S3
         mbar_wait(bar_d, 1);
         tc_fence_after();
-        tmem_ld16_sum(acc + lane_off + (uint32_t)(ch * NCOL), 64, v);
+        tmem_ld16(acc + lane_off + (uint32_t)(ch * NCOL), v);
         if (a.relu_n) bias_act<true>(v, bias_s[3], ch, 1.f);
         else bias_act<false>(v, bias_s[3], ch, 1.f);
         warp_store_block(patch, v, a.Pn + wrow0 * D + ch * NCOL, rows_valid, lane, StoreIdentity());
     }
     tc_fence_before();
     __syncthreads();  // every warp, the MMA warp included
-    if (warp == 0) tmem_dealloc(acc, 128);
+    if (warp == 0) tmem_dealloc(acc, 64);
 }
 
 __global__ void __launch_bounds__(BWD_THREADS, 1)
@@ -199,7 +199,7 @@ tc_embed_forward16_kernel(const EmbFwdArgs a) {
     const int K = a.K;
     const bool two = a.img_p[1] != nullptr;
 
-    if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), 256);  // two accumulators + their odd-k companions
+    if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), 128);
     if (tid == 0) {
         for (int i = 0; i < 3; ++i) mbar_init(smem_u32(&bars[i]), 1);
     }
@@ -224,13 +224,13 @@ tc_embed_forward16_kernel(const EmbFwdArgs a) {
             mbar_wait(bar_ready, 0);
             tc_fence_after();
             mbar_wait(wbar, 0);
-            issue_dgrad(acc0, P, W0, 0, 128);
+            issue_dgrad(acc0, P, W0, 0);
             umma_commit(bar_d);
             // F2: both projections read the same tile
             mbar_wait(bar_ready, 1);
             tc_fence_after();
-            issue_dgrad(acc0, Q, W1, 0, 128);
-            if (two) issue_dgrad(acc1, Q, W2, 0, 128);
+            issue_dgrad(acc0, Q, W1, 0);
+            if (two) issue_dgrad(acc1, Q, W2, 0);
             umma_commit(bar_d);
         }
         __syncwarp();
@@ -282,7 +282,7 @@ tc_embed_forward16_kernel(const EmbFwdArgs a) {
     // F1
     mbar_wait(bar_d, 0);
     tc_fence_after();
-    tmem_ld16_sum(acc0 + lane_off + (uint32_t)(ch * NCOL), 128, v);
+    tmem_ld16(acc0 + lane_off + (uint32_t)(ch * NCOL), v);
     bias_act<true>(v, bias_s[0], ch, 1.f);
     warp_store_block(patch, v, a.out + wrow0 * D + ch * NCOL, rows_valid, lane, StoreIdentity());
     store_row(Qg, r_own, ch, v);
@@ -290,17 +290,17 @@ tc_embed_forward16_kernel(const EmbFwdArgs a) {
     // F2
     mbar_wait(bar_d, 1);
     tc_fence_after();
-    tmem_ld16_sum(acc0 + lane_off + (uint32_t)(ch * NCOL), 128, v);
+    tmem_ld16(acc0 + lane_off + (uint32_t)(ch * NCOL), v);
     bias_act<false>(v, bias_s[1], ch, 1.f);
     warp_store_block(patch, v, a.P[0] + wrow0 * D + ch * NCOL, rows_valid, lane, StoreIdentity());
     if (two) {
-        tmem_ld16_sum(acc1 + lane_off + (uint32_t)(ch * NCOL), 128, v);
+        tmem_ld16(acc1 + lane_off + (uint32_t)(ch * NCOL), v);
         bias_act<false>(v, bias_s[2], ch, 1.f);
         warp_store_block(patch, v, a.P[1] + wrow0 * D + ch * NCOL, rows_valid, lane, StoreIdentity());
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(acc0, 256);
+    if (warp == 0) tmem_dealloc(acc0, 128);
 }
 
 static int set_fwd_smem(const void* kern) {

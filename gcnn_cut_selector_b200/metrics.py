@@ -39,3 +39,39 @@ def ranking_accuracy(predictions: torch.Tensor, improvements, n_cuts, fractions)
     dev = ranking_deviation(predictions, improvements, n_cuts).cpu().numpy().astype(np.float64)
     frac = dev / n_cuts
     return (frac[:, None] >= np.asarray(fractions, dtype=np.float64)[None, :]).sum(axis=0).astype(np.float64)
+
+
+def select_cuts(quality, parallelism, parallelism_forced=None, p_max: float = 0.1, p_max_ub: float = 0.5,
+                max_selected: int | None = None):
+    """The ranking + parallelism filter of the reference's SCIP plug-in on the device
+    (``CustomCutsel.cutselselect``, model_benchmarker.py:112-157): ``quality`` [n] are the predicted bound improvements,
+    ``parallelism`` [n, n] / ``parallelism_forced`` [n_forced, n] what ``getRowParallelism`` returns for every pair.
+    Returns ``(order, n_selected)``: ``order`` (int32 device tensor) is the cut index at each position of the reference's
+    ``sorted_cuts`` and ``n_selected`` (int32 device tensor [1]) its ``nselectedcuts``."""
+    lib = _lib.load()
+    q = quality if torch.is_tensor(quality) else torch.as_tensor(np.asarray(quality, dtype=np.float32))
+    if not q.is_cuda:
+        q = q.cuda()
+    dev = q.device
+    q = q.detach().to(torch.float32).contiguous()
+    n = q.numel()
+    as_dev = lambda x: torch.as_tensor(np.asarray(x, dtype=np.float32) if not torch.is_tensor(x) else x,
+                                       dtype=torch.float32, device=dev).contiguous()
+    par = as_dev(parallelism)
+    if par.numel() != n * n:
+        raise _lib.InvalidArgumentError("parallelism must be [n_cuts, n_cuts]")
+    n_forced, pf = 0, None
+    if parallelism_forced is not None and len(parallelism_forced) > 0:
+        pf = as_dev(parallelism_forced)
+        if pf.numel() % max(n, 1) != 0:
+            raise _lib.InvalidArgumentError("parallelism_forced must be [n_forced, n_cuts]")
+        n_forced = pf.numel() // max(n, 1)
+    order = torch.empty(n, dtype=torch.int32, device=dev)
+    n_sel = torch.empty(1, dtype=torch.int32, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    with torch.cuda.device(dev):
+        _lib.check(lib.gcnn_select_cuts(q.data_ptr(), pf.data_ptr() if pf is not None else None, par.data_ptr(), n,
+                                        n_forced, float(p_max), float(p_max_ub),
+                                        int(max_selected) if max_selected is not None else n, order.data_ptr(),
+                                        n_sel.data_ptr(), st))
+    return order, n_sel

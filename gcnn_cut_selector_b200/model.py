@@ -463,15 +463,17 @@ class GCNN:
                                               out.data_ptr(), self._stream()))
         return out.numpy()
 
-    def score_host(self, host_batch: "HostBatch") -> np.ndarray:
+    def score_host(self, host_batch: "HostBatch", graph: bool = False) -> np.ndarray:
         """Cut scoring from host buffers to a host array (the ``get_improvements(state, False).numpy()`` path of
-        model_benchmarker.py:106)."""
+        model_benchmarker.py:106).  ``graph=True``: the whole call replays as one CUDA graph once its shape has been seen
+        twice (the plug-in's one-graph-per-call loop; include/gcnn_b200.h ``gcnn_score_host_graph``)."""
         b = host_batch.batch
         self.reserve(b, False)
         out = host_batch.scores
+        fn = self._lib.gcnn_score_host_graph if graph else self._lib.gcnn_score_host
         with torch.cuda.device(self.device):
-            check(self._lib.gcnn_score_host(self._ws, self.flat_params.data_ptr(), self.flat_prenorm.data_ptr(),
-                                            C.byref(b), out.data_ptr(), self._stream()))
+            check(fn(self._ws, self.flat_params.data_ptr(), self.flat_prenorm.data_ptr(), C.byref(b), out.data_ptr(),
+                     self._stream()))
         return out.numpy()
 
     # ---- pre-norm pretraining (model.py:69-133) -------------------------------------------------------------------

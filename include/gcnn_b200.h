@@ -163,6 +163,19 @@ int gcnn_forward_backward(gcnn_workspace* ws, const float* params, const float* 
 int gcnn_ranking_deviation(const float* predictions, const float* improvements, const int32_t* cut_offsets,
                             int64_t n_samples, int max_cuts, int32_t* deviation_out, void* stream);
 
+/* Cut selection after scoring: the ranking and parallelism filter of CustomCutsel.cutselselect
+ * (model_benchmarker.py:108-157; identical in model_evaluator.py and model_evaluator_igc.py).  quality [n_cuts]: the
+ * predicted bound improvements (or the hybrid rule's scores); parallelism [n_cuts, n_cuts]: getRowParallelism(cut i, cut j);
+ * parallelism_forced [n_forced, n_cuts]: getRowParallelism(forced cut f, cut j) (NULL when n_forced == 0); all device
+ * pointers, original cut numbering.  Cuts are ranked by quality (descending, stable, like Python's sorted); then every
+ * forced cut and, in turn, every surviving cut i moves the cuts j behind it with parallelism > p_max to the back when
+ * quality[position j] < 0.9 * quality[position 0] or parallelism > p_max_ub ("quality" stays indexed by position, as in
+ * the reference).  order_out [n_cuts]: cut index at each final position; n_selected_out[0] = min(kept, max_selected).
+ * At most 8,192 cuts. */
+int gcnn_select_cuts(const float* quality, const float* parallelism_forced, const float* parallelism, int64_t n_cuts,
+                     int64_t n_forced, double p_max, double p_max_ub, int64_t max_selected, int32_t* order_out,
+                     int32_t* n_selected_out, void* stream);
+
 /* ---- pre-norm pretraining (PreNormLayer.update_params, model.py:394-423) ------------------------------------- */
 /* Runs the forward up to pre-norm layer `layer` (0..10 in the order BaseModel.pretrain_next_rec visits them,
  * model.py:100-117) and returns that layer's batch statistics on the HOST: mean[n_units], var[n_units] (population
@@ -174,6 +187,15 @@ int gcnn_prenorm_stats(gcnn_workspace* ws, const float* params, const float* pre
  *      numpy out).  All pointers in `host_batch` and targets/scores are HOST pointers (pinned for async copies). */
 int gcnn_score_host(gcnn_workspace* ws, const float* params, const float* prenorm, const gcnn_batch* host_batch,
                     float* scores_host, void* stream);
+/* gcnn_score_host replayed as ONE CUDA graph per input shape (the low-latency serving path behind
+ * CustomCutsel.cutselselect, model_benchmarker.py:91-106: one graph per call, host arrays in, host scores out).  The
+ * first call with a new shape runs eagerly, the second is captured, later ones cost a memcpy into a library-owned pinned
+ * mirror plus one cudaGraphLaunch.  Up to 8 shapes are cached (LRU) per workspace; `params` / `prenorm` pointers are part
+ * of the key.  Host pointers need not be pinned.  Falls back to the eager path when stream capture is unavailable.
+ * gcnn_serve_graph_count: graphs currently instantiated (tests / diagnostics). */
+int gcnn_score_host_graph(gcnn_workspace* ws, const float* params, const float* prenorm, const gcnn_batch* host_batch,
+                          float* scores_host, void* stream);
+int gcnn_serve_graph_count(const gcnn_workspace* ws);
 int gcnn_train_step_host(gcnn_workspace* ws, float* params, const float* prenorm, float* adam_m, float* adam_v,
                          const gcnn_batch* host_batch, const float* targets_host, float lr, int64_t step,
                          float* loss_host, void* stream);

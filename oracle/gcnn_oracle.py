@@ -404,3 +404,41 @@ def ranking_accuracy(predictions, improvements, n_cuts, fractions):
         deviations.append(deviation)
         acc += (deviation / len(pred) >= fractions)                                             # :300-301
     return acc, np.asarray(deviations, dtype=np.int32)
+
+
+def select_cuts(quality, parallelism, parallelism_forced=None, p_max=0.1, p_max_ub=0.5, max_selected=None):
+    """The ranking + parallelism filter of ``CustomCutsel.cutselselect`` (model_benchmarker.py:112-157), restated line by
+    line on index arrays: ``parallelism[i, j]`` stands for ``model.getRowParallelism(cuts[i], cuts[j])`` and
+    ``parallelism_forced[f, j]`` for ``getRowParallelism(forcedcuts[f], cuts[j])``.  Returns (order, n_selected) where
+    ``order[pos]`` is the index of the cut at position ``pos`` of the reference's ``sorted_cuts``."""
+    quality = np.asarray(quality)
+    n = len(quality)
+    parallelism = np.asarray(parallelism)
+    n_forced = 0 if parallelism_forced is None else len(parallelism_forced)
+    rankings = sorted(range(n), key=lambda x: quality[x], reverse=True)                      # :113
+    sorted_cuts = np.array(rankings, dtype=np.int64)                                          # :114 (indices for objects)
+    quality = -np.sort(-quality)                                                              # :117
+    n_selected = n                                                                            # :120
+
+    def remove(parallelism_row, n_selected, sorted_cuts):
+        marked = (parallelism_row > p_max)                                                    # :125 / :146
+        low_quality = np.logical_or(quality < 0.9 * quality[0], parallelism_row > p_max_ub)   # :128 / :149
+        to_remove = np.logical_and(marked, low_quality)                                       # :129 / :150
+        removed = sorted_cuts[to_remove]                                                      # :132 / :153
+        sorted_cuts = np.delete(sorted_cuts, to_remove)
+        sorted_cuts = np.concatenate((sorted_cuts, removed))
+        return sorted_cuts, n_selected - removed.size
+
+    for f in range(n_forced):                                                                 # :121
+        par = [parallelism_forced[f][sorted_cuts[j]] for j in range(n_selected)]              # :123
+        par = np.pad(par, (0, n - n_selected), constant_values=0)                             # :124
+        sorted_cuts, n_selected = remove(par, n_selected, sorted_cuts)
+    i = 0                                                                                     # :141
+    while i < n_selected - 1:
+        par = [parallelism[sorted_cuts[i]][sorted_cuts[j]] for j in range(i + 1, n_selected)]  # :144
+        par = np.pad(par, (i + 1, n - n_selected), constant_values=0)                         # :146
+        sorted_cuts, n_selected = remove(par, n_selected, sorted_cuts)
+        i += 1
+    if max_selected is not None:
+        n_selected = min(n_selected, max_selected)                                            # :157
+    return sorted_cuts.astype(np.int32), int(n_selected)

@@ -17,6 +17,8 @@ Outputs (all small):
   pretrain_tiny.npz    batches + pre-norm parameters after the reference's pretraining loop
   metric_process.npz   preset predictions / targets -> mean loss and ranking accuracy from the reference's own
                        ``model_trainer.process`` (evaluation branch)
+  selector.npz         preset qualities / parallelism matrices -> final cut order and nselectedcuts from the reference's own
+                       ``CustomCutsel.cutselselect`` (model_benchmarker.py:70-157)
   state_stream.pkl     the weights every fixture uses, written by the reference's own ``save_state`` (62 arrays)
 """
 import gzip
@@ -179,8 +181,71 @@ def metric_case():
     print("metric_process: mean_loss", mean_loss, "mean_acc", mean_acc)
 
 
+def selector_case():
+    """The reference's own ``CustomCutsel.cutselselect`` (model_benchmarker.py:70-157, hybrid branch: no GCNN, so the
+    quality comes from the stand-in SCIP model) on preset qualities and parallelism matrices: the final order of the cuts
+    and ``nselectedcuts``.  float32-representable values, so the device kernel sees exactly these numbers."""
+    import model_benchmarker as ref_bench
+    rng = np.random.default_rng(2024)
+    cases = {}
+
+    class Cut:
+        def __init__(self, i):
+            self.i = i
+
+        def getNNonz(self):
+            return 1
+
+    class FakeScip:
+        def __init__(self, q, par, par_forced):
+            self.q, self.par, self.par_forced = q, par, par_forced
+
+        def getCutEfficacy(self, cut):
+            return float(self.q[cut.i])
+
+        def getRowNumIntCols(self, cut):
+            return 0
+
+        def getRowObjParallelism(self, cut):
+            return 0.0
+
+        def getRowParallelism(self, a, b):
+            if a.i < 0:  # forced cuts carry negative ids
+                return float(self.par_forced[-a.i - 1][b.i])
+            return float(self.par[a.i][b.i])
+
+    specs = [("small", 12, 2, 5), ("ties", 40, 0, 40), ("forced", 64, 5, 30), ("dense", 150, 3, 150), ("one", 1, 1, 1),
+             ("none_removed", 30, 2, 10)]
+    for name, n, nf, max_sel in specs:
+        q = np.round(rng.uniform(0.0, 1.0, n), 2 if name == "ties" else 6).astype(np.float32)
+        hi = 0.05 if name == "none_removed" else 1.0
+        par = rng.uniform(0.0, hi, (n, n)).astype(np.float32)
+        par = np.maximum(par, par.T)
+        mask = rng.random((n, n)) < (0.6 if name != "dense" else 0.1)
+        par = np.where(np.maximum(mask, mask.T), np.float32(0.0), par)  # most pairs are orthogonal
+        par_forced = rng.uniform(0.0, hi, (nf, n)).astype(np.float32)
+        par_forced[rng.random((nf, n)) < 0.7] = 0.0
+        sel = ref_bench.CustomCutsel()
+        sel.model = FakeScip(q, par, par_forced)
+        cuts = [Cut(i) for i in range(n)]
+        forced = [Cut(-f - 1) for f in range(nf)]
+        res = sel.cutselselect(cuts, forced, True, max_sel)
+        cases[f"{name}_quality"] = q
+        cases[f"{name}_par"] = par
+        cases[f"{name}_par_forced"] = par_forced
+        cases[f"{name}_max_selected"] = np.int64(max_sel)
+        cases[f"{name}_order"] = np.array([c.i for c in res["cuts"]], dtype=np.int32)
+        cases[f"{name}_n_selected"] = np.int64(res["nselectedcuts"])
+        print(f"selector {name}: n={n} forced={nf} kept={res['nselectedcuts']}")
+    cases["names"] = np.array([s[0] for s in specs])
+    np.savez_compressed(os.path.join(GOLDEN, "selector.npz"), **cases)
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
+    if "--selector-only" in sys.argv:
+        selector_case()
+        return
     if "--metric-only" in sys.argv:
         metric_case()
         return
@@ -208,6 +273,7 @@ def main():
     fwd_case("isolated", iso, params)
     pretrain_case(params)
     metric_case()
+    selector_case()
 
 
 if __name__ == "__main__":

@@ -4,3 +4,7 @@ class Model:  # annotation targets only (utils.py:35)
 
 class Row:
     pass
+
+
+class Cutsel:  # base class of the reference's CustomCutsel (model_benchmarker.py:36, 41); SCIP sets ``model``
+    model = None

@@ -884,3 +884,60 @@ def test_ranking_deviation_bit_exact(golden_dir):
     want_acc, want_dev = orc.ranking_accuracy(pred, true, n_cuts, fr)
     got = ranking_deviation(torch.from_numpy(pred).cuda(), torch.from_numpy(true).cuda(), n_cuts)
     np.testing.assert_array_equal(got.cpu().numpy(), want_dev)
+
+
+# ---- cut selection after scoring (model_benchmarker.py:108-157) ---------------------------------------------------------
+def test_select_cuts_bit_exact(golden_dir):
+    """The device kernel against the reference's own ``CustomCutsel.cutselselect`` (golden fixture) and, on larger random
+    cases with ties, forced cuts and a 3,000-cut candidate set, against the oracle's line-by-line restatement."""
+    from gcnn_cut_selector_b200 import select_cuts
+    z = np.load(os.path.join(golden_dir, "selector.npz"))
+    for name in z["names"]:
+        pf = z[f"{name}_par_forced"]
+        order, n_sel = select_cuts(z[f"{name}_quality"], z[f"{name}_par"], pf if len(pf) else None,
+                                   max_selected=int(z[f"{name}_max_selected"]))
+        np.testing.assert_array_equal(order.cpu().numpy(), z[f"{name}_order"])
+        assert int(n_sel.item()) == int(z[f"{name}_n_selected"])
+    rng = np.random.default_rng(9)
+    for n, nf, sparsity in ((257, 3, 0.9), (1500, 0, 0.97), (3000, 2, 0.995)):
+        q = np.round(rng.uniform(0, 1, n), 3).astype(np.float32)
+        par = rng.uniform(0, 1, (n, n)).astype(np.float32)
+        par = np.maximum(par, par.T)
+        mask = rng.random((n, n)) < sparsity
+        par[np.maximum(mask, mask.T)] = 0.0
+        pf = rng.uniform(0, 1, (nf, n)).astype(np.float32)
+        pf[rng.random((nf, n)) < 0.9] = 0.0
+        want_order, want_n = orc.select_cuts(q, par, pf if nf else None, max_selected=n // 2)
+        order, n_sel = select_cuts(torch.from_numpy(q).cuda(), par, pf if nf else None, max_selected=n // 2)
+        np.testing.assert_array_equal(order.cpu().numpy(), want_order)
+        assert int(n_sel.item()) == want_n
+
+
+def test_graph_scoring_matches_eager_scoring(golden_dir):
+    """The serving path: host arrays in, host scores out, replayed as one CUDA graph per shape from the third call on
+    (first call eager, second captured).  Bit-identical to the eager host path; new shapes, changed inputs of a cached
+    shape and a workspace growth in between are handled."""
+    from gcnn_cut_selector_b200 import GCNN, HostBatch
+    m = GCNN(device="cuda:0", seed=0)
+    m.restore_state(os.path.join(golden_dir, "state_stream.pkl"))
+    batches = [batching.concat_samples(synth.make_samples(shape, 1, seed0=s)) for shape, s in
+               (("combauc", 1), ("combauc", 2), ("indset", 3), ("mini", 4))]
+    hbs = [HostBatch(b) for b in batches]
+    want = [m.score_host(h).copy() for h in hbs]
+    for rep in range(4):
+        for h, w in zip(hbs, want):
+            np.testing.assert_array_equal(m.score_host(h, graph=True), w)
+    assert m._lib.gcnn_serve_graph_count(m._ws) >= 1  # (0 would mean the capture fell back to eager launches)
+    big = HostBatch(batching.concat_samples(synth.make_samples("setcov", 2, seed0=5)))  # grows the workspace
+    w_big = m.score_host(big).copy()
+    for rep in range(3):
+        np.testing.assert_array_equal(m.score_host(big, graph=True), w_big)
+        np.testing.assert_array_equal(m.score_host(hbs[0], graph=True), want[0])
+    bad = list(batches[0])
+    ei = bad[5].copy()
+    ei[1, 0] = int(bad[8].sum())  # out-of-range variable index on a cached shape
+    bad[5] = ei
+    from gcnn_cut_selector_b200 import InvalidArgumentError
+    with pytest.raises(InvalidArgumentError):
+        m.score_host(HostBatch(tuple(bad)), graph=True)
+    np.testing.assert_array_equal(m.score_host(hbs[0], graph=True), want[0])

@@ -195,3 +195,15 @@ def test_ranking_accuracy_hand_cases():
     # two samples: the second deviates at position 2 of 4 -> frac 0.5
     acc, dev = orc.ranking_accuracy([5, 4, 4, 3, 2, 1], [1, 0, 9, 8, 6, 7], [2, 4], fr)
     assert dev.tolist() == [2, 2] and acc.tolist() == [2, 2, 1, 1]
+
+
+def test_select_cuts_matches_reference_cutsel(golden_dir):
+    """The oracle's restatement of the ranking + parallelism filter against the reference's own
+    ``CustomCutsel.cutselselect`` (tests/golden/selector.npz, generated by oracle/make_golden.py over the SCIP stand-in)."""
+    z = np.load(os.path.join(golden_dir, "selector.npz"))
+    for name in z["names"]:
+        pf = z[f"{name}_par_forced"]
+        order, n_sel = orc.select_cuts(z[f"{name}_quality"], z[f"{name}_par"], pf if len(pf) else None,
+                                       max_selected=int(z[f"{name}_max_selected"]))
+        np.testing.assert_array_equal(order, z[f"{name}_order"])
+        assert n_sel == int(z[f"{name}_n_selected"])
