@@ -471,9 +471,17 @@ def run_b200(args):
                    "value": r4["value"], "unit": UNIT, "ms_per_step": r4["ms_per_step"],
                    "edge_messages_per_s": r4["value"] * SETCOV_MSGS_PER_GRAPH, "e2e": r4["e2e"],
                    "e2e_records": r4["e2e_records"], "steps": max(5, K // 4)}
-    others = None
+    others, bf16 = None, None
     if world == 1 and not args.no_extra_configs:
         others = measure_other_configs(model, dev)
+        # the bf16 MLP path (BASELINE.json's 1e-2 accuracy class): same workload, separate labelled object, never the headline
+        model.set_option("precision", 1)
+        rb = measure_training(model, trainer, graphs, max(10, K // 2), 3, world, rank, dev, detail=False)
+        model.set_option("precision", 0)
+        bf16 = {"dtype": "bf16 MLP (dense layers: bf16 operands, fp32 accumulate; edge kernels, loss, Adam fp32)",
+                "accuracy_class": "1e-2 (tests/test_gpu_parity.py::test_bf16_mlp_mode_within_1e2)",
+                "workload": workload_name(graphs), "value": rb["value"], "unit": UNIT, "ms_per_step": rb["ms_per_step"],
+                "e2e": rb["e2e"]}
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
@@ -525,6 +533,8 @@ def run_b200(args):
             line["config4"] = config4
         if others:
             line["configs"] = others
+        if bf16:
+            line["bf16_mlp"] = bf16
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(model, main_res["_batch0"], graphs)
         emit(line)

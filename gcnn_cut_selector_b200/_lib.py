@@ -64,6 +64,11 @@ SIGNATURES = {
     "gcnn_mse_seed": (_I, [_P, _P, _I64, _F, _P, _P, _P]),
     "gcnn_adam_step": (_I, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I64, _P, _P]),
     "gcnn_ranking_deviation": (_I, [_P, _P, _P, _I64, _I, _P, _P]),
+    "gcnn_dp_create": (_I, [_P, _I, _I, _P]),
+    "gcnn_dp_connect": (_I, [_P, _P]),
+    "gcnn_dp_bucket": (_P, [_P, _I]),
+    "gcnn_dp_next_parity": (_I, [_P]),
+    "gcnn_dp_allreduce_adam": (_I, [_P, _P, _P, _P, _F, _F, _F, _F, _I64, _P, _P]),
     "gcnn_select_cuts": (_I, [_P, _P, _P, _I64, _I64, C.c_double, C.c_double, _I64, _P, _P, _P]),
     "gcnn_forward_backward": (_I, [_P, _P, _P, _BP, _P, _F, _P, _P, _P, _P]),
     "gcnn_prenorm_stats": (_I, [_P, _P, _P, _BP, _I, C.POINTER(C.c_double), C.POINTER(C.c_double),

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgcnn_b200.so")
-SOURCES = ["api.cu", "csr_build.cu", "edge.cu", "node.cu", "node_tc.cu", "node_bwd.cu", "node_fwd.cu", "edge_block.cu", "records.cu", "select.cu"]
+SOURCES = ["api.cu", "csr_build.cu", "edge.cu", "node.cu", "node_tc.cu", "node_bwd.cu", "node_fwd.cu", "edge_block.cu", "records.cu", "select.cu", "dp.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math=false",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
 

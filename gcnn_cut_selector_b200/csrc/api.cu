@@ -105,6 +105,7 @@ struct gcnn_workspace {
     uint2* edge_masks[3] = {nullptr, nullptr, nullptr};  // per-edge ReLU masks of each convolution (by original edge id)
     int masks_valid[3] = {0, 0, 0};
     int use_fused_bwd = 1;
+    int bf16_mlp = 0;  // option "precision" = 1: plain bf16 MMAs (one product) in the four chain kernels -- the 1e-2 class
     int use_bf16_fwd = 1;
     int use_edge_masks = 1;  // forward edge kernel records per-edge ReLU masks, the backward reads them  // forward chains on bf16x3 tiles (node_fwd.cu) instead of 3xTF32 (node_tc.cu)
     // set by gcnn_forward_backward around a fused step: head layer 2, the loss seed and its backward are ONE launch
@@ -153,6 +154,7 @@ struct gcnn_workspace {
     uint8_t* serve_pin = nullptr;              // pinned host mirror of one batch + its scores + the error word
     size_t serve_pin_bytes = 0;
     int serve_graphs_ok = 1;                   // cleared when a capture fails (then every call runs eagerly)
+    DpState* dp = nullptr;                     // data-parallel peer-memory exchange (gcnn_dp_*)
     int device = 0;                            // CUDA device the workspace lives on
     int64_t act_stamp = 0;                     // generation of the saved activations (gcnn_activation_stamp)
     float* h_result = nullptr;    // pinned host: per slot {loss sum, error flag word}
@@ -495,6 +497,7 @@ static int forward_convs_fused(gcnn_workspace* ws, const float* p, const float* 
         c.img_n = next_img[i]; c.bias_n = next_bias[i]; c.relu_n = next_relu[i];
         c.C = keep ? a.C : nullptr; c.U1 = keep ? a.U1 : nullptr; c.Y = a.Y; c.Pn = next_out[i];
         c.M = n_recv[i];
+        c.bf16_mlp = ws->bf16_mlp;
         GCNN_TRY(bf16 ? tc_conv_forward16(c, st) : tc_conv_forward(c, st));
         if (stop_layer == 6 + 2 * i) return wait_all_layouts();
     }
@@ -594,6 +597,7 @@ static int forward_impl(gcnn_workspace* ws, const float* p, const float* pn, con
                 f.img_p[0] = img_t(P.conv[0].Wr); f.P[0] = ws->conv[0].B;
                 f.img_p[1] = img_t(P.conv[1].Wr); f.P[1] = ws->conv[1].B;
             } else { f.img_p[0] = img_t(P.conv[2].Wl); f.bias_p[0] = p + P.conv[2].bl; f.P[0] = ws->conv[2].A; }
+            f.bf16_mlp = ws->bf16_mlp;
             GCNN_TRY(bf16 ? tc_embed_forward16(f, se) : tc_embed_forward(f, se));
             continue;
         }
@@ -868,6 +872,7 @@ static int backward_impl_fused(gcnn_workspace* ws, const float* p, const float* 
         }
         g.img_p0 = img16(w0); g.img_p1 = w1 >= 0 ? img16(w1) : nullptr; g.img_w2 = img16(eo->W2);
         g.partials = ws->emb_partials[e];
+        g.bf16_mlp = ws->bf16_mlp;
         int np = 0;
         GCNN_TRY(tc_embed_backward(g, &np, se));
         if (np > 0) {
@@ -893,6 +898,7 @@ static int backward_impl_fused(gcnn_workspace* ws, const float* p, const float* 
         c.img_n = img16(next_w[i]); c.img_o2 = img16(o.Wo2); c.img_o1a = img16(o.Wo1); c.img_o1b = img16(o.Wo1 + D * D);
         c.img_f = img16(o.Wf);
         c.dXt = d_recv_in[i]; c.G = ws->bG[i]; c.dR = ws->bdR[i]; c.partials = ws->chain_partials[i]; c.M = n_recv[i];
+        c.bf16_mlp = ws->bf16_mlp;
         GCNN_TRY(tc_conv_backward(c, &n_parts, st));
         if (n_parts > 0) {
             const float* cp = ws->chain_partials[i];
@@ -1039,6 +1045,7 @@ static int read_error_flag(gcnn_workspace* ws, cudaStream_t st) {
         if (flag & 8) set_error("edge index + sample offset does not fit int32 (utils.py:403-414)");
         else if (flag & 1) set_error("edge index out of range (InvalidArgument, cf. tf.gather in model.py:564)");
         else if (flag & 4) set_error("an edge leaves its sample's node range although per-sample counts were given");
+        else if (flag & 16) set_error("data-parallel exchange timed out waiting for a peer rank");
         else set_error("batch flags claim edges sorted by row 0 (utils.py:102-104 order) but they are not");
         return GCNN_INVALID;
     }
@@ -1192,6 +1199,7 @@ int gcnn_workspace_destroy(gcnn_workspace* ws) {
     if (!ws) return GCNN_OK;
     DeviceGuard guard(ws->device);
     cudaDeviceSynchronize();
+    if (ws->dp) { dp_destroy(ws->dp); ws->dp = nullptr; }
     serve_drop_graphs(ws);
     if (ws->serve_pin) cudaFreeHost(ws->serve_pin);
     if (ws->arena) cudaFree(ws->arena);
@@ -1278,6 +1286,16 @@ int gcnn_set_option(gcnn_workspace* ws, const char* name, int value) {
     else if (!strcmp(name, "streams")) ws->use_streams = value != 0;
     else if (!strcmp(name, "fused")) ws->use_fused = value != 0;
     else if (!strcmp(name, "blocks")) ws->use_blocks = value != 0;
+    else if (!strcmp(name, "precision")) {
+        // 0: fp32-accurate (bf16x3 operands, six products per MMA; <= 1e-5 class); 1: bf16 MLP path (one product: the
+        // dense layers see bf16 operands with fp32 accumulation; <= 1e-2 class, BASELINE.json north_star).  The edge
+        // kernels, the loss and Adam stay fp32 in both.
+        if (value && !(ws->use_tc && ws->use_fused && ws->use_fused_bwd && ws->use_bf16_fwd)) {
+            set_error("precision = 1 needs the fused bf16x3 chain kernels (tensor_cores, fused, fused_backward, bf16_forward)");
+            return GCNN_INVALID;
+        }
+        ws->bf16_mlp = value != 0;
+    }
     else if (!strcmp(name, "fused_backward")) ws->use_fused_bwd = value != 0;
     else if (!strcmp(name, "bf16_forward")) ws->use_bf16_fwd = value != 0;
     else if (!strcmp(name, "count_before_loss")) ws->count_before_loss = value != 0;
@@ -1433,6 +1451,35 @@ int gcnn_ranking_deviation(const float* predictions, const float* improvements, 
         return GCNN_INVALID;
     }
     return ranking_deviation(predictions, improvements, cut_offsets, n_samples, max_cuts, deviation_out, (cudaStream_t)stream);
+}
+
+// ---- data parallel: one-shot all-reduce over NVLink peer memory fused with Adam (csrc/dp.cu) --------------------------
+int gcnn_dp_create(gcnn_workspace* ws, int world, int rank, void* handle_out64) {
+    if (!ws || !handle_out64) { set_error("bad dp_create arguments"); return GCNN_INVALID; }
+    DeviceGuard guard(ws->device);
+    if (ws->dp) { dp_destroy(ws->dp); ws->dp = nullptr; }
+    GCNN_TRY(dp_create(&ws->dp, world, rank));
+    return dp_handle(ws->dp, handle_out64);
+}
+
+int gcnn_dp_connect(gcnn_workspace* ws, const void* handles) {
+    if (!ws || !ws->dp || !handles) { set_error("gcnn_dp_connect: call gcnn_dp_create first"); return GCNN_INVALID; }
+    DeviceGuard guard(ws->device);
+    return dp_connect(ws->dp, handles);
+}
+
+float* gcnn_dp_bucket(gcnn_workspace* ws, int parity) { return (ws && ws->dp) ? dp_bucket(ws->dp, parity) : nullptr; }
+int gcnn_dp_next_parity(const gcnn_workspace* ws) { return (ws && ws->dp) ? dp_next_parity(ws->dp) : 0; }
+
+int gcnn_dp_allreduce_adam(gcnn_workspace* ws, float* params, float* adam_m, float* adam_v, float lr, float beta1,
+                           float beta2, float eps, int64_t step, float* sums_out, void* stream) {
+    if (!ws || !ws->dp || !ws->arena) { set_error("gcnn_dp_allreduce_adam: no data-parallel state / workspace"); return GCNN_INVALID; }
+    if (step < 1) { set_error("adam step counts from 1"); return GCNN_INVALID; }
+    DeviceGuard guard(ws->device);
+    const double lr_t = (double)lr * std::sqrt(1.0 - std::pow((double)beta2, (double)step)) /
+                        (1.0 - std::pow((double)beta1, (double)step));
+    return dp_allreduce_adam(ws->dp, params, adam_m, adam_v, (float)lr_t, beta1, beta2, eps, sums_out, ws->flags + 1,
+                             (cudaStream_t)stream);
 }
 
 int gcnn_select_cuts(const float* quality, const float* parallelism_forced, const float* parallelism, int64_t n_cuts,

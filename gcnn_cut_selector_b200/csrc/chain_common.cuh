@@ -56,11 +56,13 @@ __device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) 
 // (Tried in round 2: even / odd k-steps into two accumulators that the epilogue adds with round-to-nearest, to halve the
 // tensor core's truncating accumulations.  Scores moved from 2.6e-6 to 1.6e-6 of the fp64 oracle, the worst gradient
 // tensor did not improve and the backward chains took 9 % longer -- not kept; profiles/r2_grad_errors.md.)
-__device__ __forceinline__ void issue_dgrad(uint32_t tmem_d, uint32_t a_tile, uint32_t w_img, uint32_t acc) {
+// `first`: index of the first product issued -- 0 for the fp32-accurate path (all six), 5 for the bf16 MLP mode (option
+// "precision" = 1): only the leading (0,0) product, i.e. plain bf16 operands with fp32 accumulation.
+__device__ __forceinline__ void issue_dgrad(uint32_t tmem_d, uint32_t a_tile, uint32_t w_img, uint32_t acc, int first) {
     asm volatile("" : "+r"(a_tile), "+r"(w_img));
     const uint64_t da0 = make_desc(a_tile), db0 = make_desc(w_img);
 #pragma unroll 1
-    for (int p = 0; p < 6; ++p) {
+    for (int p = first; p < 6; ++p) {
         const uint32_t pa = (0x001012u >> (4 * p)) & 3u, pb = (0x010210u >> (4 * p)) & 3u;  // (2,0) (1,1) (0,2) (1,0) (0,1) (0,0)
         const uint64_t da = da0 + (uint64_t)(pa * (T16_PIECE >> 4)), db = db0 + (uint64_t)(pb * (W16_PIECE >> 4));
 #pragma unroll
@@ -76,11 +78,11 @@ __device__ __forceinline__ void issue_dgrad(uint32_t tmem_d, uint32_t a_tile, ui
 // after the first (the right half of the concat, or don't-care data whose result rows 64..127 are never read).
 template <bool M64 = false>
 __device__ __forceinline__ void issue_wgrad(uint32_t tmem_d, uint32_t act_tile, uint32_t lbo, uint32_t g_tile,
-                                            uint32_t acc) {
+                                            uint32_t acc, int first) {
     asm volatile("" : "+r"(act_tile), "+r"(g_tile));
     const uint64_t da0 = make_desc_mn16(act_tile, lbo), db0 = make_desc_mn16(g_tile, T16_BYTES);
 #pragma unroll 1
-    for (int p = ACT_PIECES == 3 ? 0 : 1; p < 6; ++p) {  // two activation pieces: (1,1) (0,2) (1,0) (0,1) (0,0); three: + (2,0)
+    for (int p = max(first, ACT_PIECES == 3 ? 0 : 1); p < 6; ++p) {  // two activation pieces: (1,1) (0,2) (1,0) (0,1) (0,0); three: + (2,0)
         const uint32_t pa = (0x001012u >> (4 * p)) & 3u, pb = (0x010210u >> (4 * p)) & 3u;
         const uint64_t da = da0 + (uint64_t)(pa * (T16_PIECE >> 4)), db = db0 + (uint64_t)(pb * (T16_PIECE >> 4));
 #pragma unroll

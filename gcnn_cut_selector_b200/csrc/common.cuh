@@ -315,6 +315,7 @@ struct ConvFwdArgs {          // fused node chain of one convolution (tc_conv_fo
     int relu_n;
     float *C, *U1, *Y, *Pn;   // outputs; C and U1 may be nullptr (inference)
     int64_t M;
+    int bf16_mlp;             // option "precision" = 1: one bf16 product per MMA instead of six (bf16x3 chains only)
 };
 int tc_conv_forward(const ConvFwdArgs& a, cudaStream_t st);
 int tc_conv_forward16(const ConvFwdArgs& a, cudaStream_t st);  // bf16x3 variant (node_fwd.cu): img_* are bf16x3 T images
@@ -327,6 +328,7 @@ struct ConvBwdArgs {          // fused backward node chain of one convolution (t
     float *dXt, *G, *dR;      // outputs [M, 64]: gradient of the concat's right half, dC Wf^T, s_f G cnt
     float* partials;          // [n_parts, conv_backward_part_floats()]: Wn | bn | Wo2 | bo2 | Wo1 | bo1 | Wf | bf
     int64_t M;
+    int bf16_mlp;
 };
 int tc_conv_backward(const ConvBwdArgs& a, int* n_parts, cudaStream_t st);
 int conv_backward_part_floats();
@@ -341,6 +343,7 @@ struct EmbFwdArgs {           // fused forward chain of one embedding (tc_embed_
     const float* bias_p[2];   // their biases or nullptr
     float *h1, *out, *P[2];   // outputs, [M, 64] each
     int64_t M;
+    int bf16_mlp;
 };
 int tc_embed_forward(const EmbFwdArgs& a, cudaStream_t st);
 int tc_embed_forward16(const EmbFwdArgs& a, cudaStream_t st);  // bf16x3 variant (node_fwd.cu)
@@ -355,6 +358,7 @@ struct EmbBwdArgs {           // fused backward chain of one embedding (tc_embed
     const void *img_p0, *img_p1, *img_w2;  // bf16x3 N images of the projection kernels and of W2
     float* partials;          // [n_parts, embed_backward_part_floats()]: W_0 | b_0 | W_1 | b_1 | W2 | b2 | W1 (64 rows) | b1
     int64_t M;
+    int bf16_mlp;
 };
 int tc_embed_backward(const EmbBwdArgs& a, int* n_parts, cudaStream_t st);
 int embed_backward_part_floats();
@@ -405,6 +409,17 @@ int adam_step(float* params, const float* grads, float* m, float* v, int64_t n, 
 // first position at which the predicted and the true ranking of each sample's cuts differ (model_trainer.py:279-302)
 int ranking_deviation(const float* pred, const float* truth, const int32_t* offsets_dev, int64_t n_samples, int max_cuts,
                       int32_t* deviation, cudaStream_t st);
+
+// data-parallel gradient exchange over peer memory fused with Adam (dp.cu)
+struct DpState;
+int dp_create(DpState** out, int world, int rank);
+int dp_handle(DpState* s, void* handle64);
+int dp_connect(DpState* s, const void* handles);
+void dp_destroy(DpState* s);
+float* dp_bucket(DpState* s, int parity);
+int dp_next_parity(const DpState* s);
+int dp_allreduce_adam(DpState* s, float* params, float* m, float* v, float lr_t, float beta1, float beta2, float eps,
+                      float* sums_out, int32_t* err_flag, cudaStream_t st);
 
 // ranking + parallelism filter of the cut-selector plug-in (model_benchmarker.py:108-157), one CTA (select.cu)
 int select_cuts(const float* quality, const float* par_forced, const float* par, int64_t n, int64_t n_forced, double p_max,

@@ -79,6 +79,7 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
     if (warp >= CWARPS) {
         // ================= MMA / weight-copy warp =================
         regs_mma();
+        const int first_p = a.bf16_mlp ? 5 : 0;  // bf16 MLP mode: the leading product only
         if (warp == CWARPS && elect_one()) {
             bulk_load(W0, a.img_n, W16_BYTES, wbar0);
             bulk_load(W1, a.img_o2, W16_BYTES, wbar1);
@@ -92,9 +93,9 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
                 mbar_wait(bar_ready, ph_r); ph_r ^= 1;
                 tc_fence_after();
                 mbar_wait(wbar0, 0);
-                issue_dgrad(accA, B0, W0, 0);
+                issue_dgrad(accA, B0, W0, 0, first_p);
                 umma_commit(bar_d);
-                issue_wgrad<true>(acc_wn, B1, T16_BYTES, B0, wacc);
+                issue_wgrad<true>(acc_wn, B1, T16_BYTES, B0, wacc, first_p);
                 umma_commit(bar_w);
                 mbar_wait(bar_d, ph_dd); ph_dd ^= 1;  // slot 0 is free
                 bulk_load(W0, a.img_o1b, W16_BYTES, wbar0);
@@ -102,9 +103,9 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
                 mbar_wait(bar_ready, ph_r); ph_r ^= 1;
                 tc_fence_after();
                 mbar_wait(wbar1, 0);
-                issue_dgrad(accA, B2, W1, 0);
+                issue_dgrad(accA, B2, W1, 0, first_p);
                 umma_commit(bar_d);
-                issue_wgrad<true>(acc_wo2, B0, T16_BYTES, B2, wacc);
+                issue_wgrad<true>(acc_wo2, B0, T16_BYTES, B2, wacc, first_p);
                 umma_commit(bar_w);
                 mbar_wait(bar_d, ph_dd); ph_dd ^= 1;  // slot 1 is free
                 bulk_load(W1, a.img_f, W16_BYTES, wbar1);
@@ -113,10 +114,10 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
                 tc_fence_after();
                 mbar_wait(wbar2, (uint32_t)(it & 1));
                 mbar_wait(wbar0, 1);
-                issue_dgrad(accA, B1, W2, 0);
-                issue_dgrad(accB, B1, W0, 0);
+                issue_dgrad(accA, B1, W2, 0, first_p);
+                issue_dgrad(accB, B1, W0, 0, first_p);
                 umma_commit(bar_d);
-                issue_wgrad(acc_wo1, B0, 2 * T16_BYTES, B1, wacc);
+                issue_wgrad(acc_wo1, B0, 2 * T16_BYTES, B1, wacc, first_p);
                 umma_commit(bar_w);
                 mbar_wait(bar_d, ph_dd); ph_dd ^= 1;  // slots 0 and 2 are free
                 if (has_next) {
@@ -127,9 +128,9 @@ tc_conv_backward_kernel(const ConvBwdArgs a) {
                 mbar_wait(bar_ready, ph_r); ph_r ^= 1;
                 tc_fence_after();
                 mbar_wait(wbar1, 1);
-                issue_dgrad(accA, B1, W1, 0);
+                issue_dgrad(accA, B1, W1, 0, first_p);
                 umma_commit(bar_d);
-                issue_wgrad<true>(acc_wf, B0, T16_BYTES, B1, wacc);
+                issue_wgrad<true>(acc_wf, B0, T16_BYTES, B1, wacc, first_p);
                 umma_commit(bar_w);
                 mbar_wait(bar_d, ph_dd); ph_dd ^= 1;  // slot 1 is free
                 if (has_next) bulk_load(W1, a.img_o2, W16_BYTES, wbar1);
@@ -413,6 +414,7 @@ tc_embed_backward_kernel(const EmbBwdArgs a) {
     if (warp >= CWARPS) {
         // ================= MMA / weight-copy warp =================
         regs_mma();
+        const int first_p = a.bf16_mlp ? 5 : 0;  // bf16 MLP mode: the leading product only
         if (warp == CWARPS && elect_one()) {
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(wbar), "r"((two ? 3u : 2u) * W16_BYTES) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -430,23 +432,23 @@ tc_embed_backward_kernel(const EmbBwdArgs a) {
                 mbar_wait(bar_ready, ph_r); ph_r ^= 1;
                 tc_fence_after();
                 if (it == 0) mbar_wait(wbar, 0);
-                issue_dgrad(accA, B0, W0, 0);
-                if (two) issue_dgrad(accA, B2, W1, 1);
+                issue_dgrad(accA, B0, W0, 0, first_p);
+                if (two) issue_dgrad(accA, B2, W1, 1, first_p);
                 umma_commit(bar_d);
-                issue_wgrad<true>(acc_w0, B1, T16_BYTES, B0, wacc);
-                if (two) issue_wgrad<true>(acc_w1, B1, T16_BYTES, B2, wacc);
+                issue_wgrad<true>(acc_w0, B1, T16_BYTES, B0, wacc, first_p);
+                if (two) issue_wgrad<true>(acc_w1, B1, T16_BYTES, B2, wacc, first_p);
                 umma_commit(bar_w);
                 // E1
                 mbar_wait(bar_ready, ph_r); ph_r ^= 1;
                 tc_fence_after();
-                issue_dgrad(accA, B0, W2, 0);
+                issue_dgrad(accA, B0, W2, 0, first_p);
                 umma_commit(bar_d);
-                issue_wgrad<true>(acc_w2, B2, T16_BYTES, B0, wacc);
+                issue_wgrad<true>(acc_w2, B2, T16_BYTES, B0, wacc, first_p);
                 umma_commit(bar_w);
                 // E2
                 mbar_wait(bar_ready, ph_r); ph_r ^= 1;
                 tc_fence_after();
-                issue_wgrad<true>(acc_wx, B0, T16_BYTES, B1, wacc);
+                issue_wgrad<true>(acc_wx, B0, T16_BYTES, B1, wacc, first_p);
                 umma_commit(bar_w);
             }
         }

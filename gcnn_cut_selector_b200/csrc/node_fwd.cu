@@ -72,6 +72,7 @@ tc_conv_forward16_kernel(const ConvFwdArgs a) {
     if (warp >= CWARPS) {
         // ================= MMA / weight-copy warp =================
         regs_mma();
+        const int first_p = a.bf16_mlp ? 5 : 0;  // bf16 MLP mode: the leading product only
         if (warp == CWARPS && elect_one()) {
             bulk_load(W0, a.img_f, W16_BYTES, wbar0);
             bulk_load(W1, a.img_o1a, W16_BYTES, wbar1);
@@ -80,7 +81,7 @@ tc_conv_forward16_kernel(const ConvFwdArgs a) {
             mbar_wait(bar_ready, 0);
             tc_fence_after();
             mbar_wait(wbar0, 0);
-            issue_dgrad(acc, P, W0, 0);
+            issue_dgrad(acc, P, W0, 0, first_p);
             umma_commit(bar_d);
             mbar_wait(bar_d, 0);  // slot 0 is free
             bulk_load(W0, a.img_o2, W16_BYTES, wbar0);
@@ -89,8 +90,8 @@ tc_conv_forward16_kernel(const ConvFwdArgs a) {
             tc_fence_after();
             mbar_wait(wbar1, 0);
             mbar_wait(wbar2, 0);
-            issue_dgrad(acc, P, W1, 0);
-            issue_dgrad(acc, Q, W2, 1);
+            issue_dgrad(acc, P, W1, 0, first_p);
+            issue_dgrad(acc, Q, W2, 1, first_p);
             umma_commit(bar_d);
             mbar_wait(bar_d, 1);  // slots 1 and 2 are free
             if (has_next) bulk_load(W1, a.img_n, W16_BYTES, wbar1);
@@ -98,13 +99,13 @@ tc_conv_forward16_kernel(const ConvFwdArgs a) {
             mbar_wait(bar_ready, 0);
             tc_fence_after();
             mbar_wait(wbar0, 1);
-            issue_dgrad(acc, P, W0, 0);
+            issue_dgrad(acc, P, W0, 0, first_p);
             umma_commit(bar_d);
             if (has_next) {  // S3
                 mbar_wait(bar_ready, 1);
                 tc_fence_after();
                 mbar_wait(wbar1, 1);
-                issue_dgrad(acc, Q, W1, 0);
+                issue_dgrad(acc, Q, W1, 0, first_p);
                 umma_commit(bar_d);
             }
         }
@@ -211,6 +212,7 @@ tc_embed_forward16_kernel(const EmbFwdArgs a) {
 
     if (warp >= CWARPS) {
         regs_mma();
+        const int first_p = a.bf16_mlp ? 5 : 0;  // bf16 MLP mode: the leading product only
         if (warp == CWARPS && elect_one()) {
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(wbar), "r"((two ? 3u : 2u) * W16_BYTES) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -224,13 +226,13 @@ tc_embed_forward16_kernel(const EmbFwdArgs a) {
             mbar_wait(bar_ready, 0);
             tc_fence_after();
             mbar_wait(wbar, 0);
-            issue_dgrad(acc0, P, W0, 0);
+            issue_dgrad(acc0, P, W0, 0, first_p);
             umma_commit(bar_d);
             // F2: both projections read the same tile
             mbar_wait(bar_ready, 1);
             tc_fence_after();
-            issue_dgrad(acc0, Q, W1, 0);
-            if (two) issue_dgrad(acc1, Q, W2, 0);
+            issue_dgrad(acc0, Q, W1, 0, first_p);
+            if (two) issue_dgrad(acc1, Q, W2, 0, first_p);
             umma_commit(bar_d);
         }
         __syncwarp();

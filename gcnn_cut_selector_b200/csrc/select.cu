@@ -81,7 +81,9 @@ select_cuts_kernel(const float* __restrict__ quality, const float* __restrict__ 
         qs[r] = qi;  // quality = -np.sort(-quality) (model_benchmarker.py:117)
     }
     __syncthreads();
-    const double low_thr = n > 0 ? 0.9 * (double)qs[0] : 0.0;  // quality < 0.9 * quality[0] (:132, :149)
+    // quality < 0.9 * quality[0] (:128, :149) on the GCNN's float32 scores under the reference's numpy 1.22.3: the product
+    // is formed in double, rounded to float32 and compared in float32 (value-based casting of a scalar against an array)
+    const float low_thr = n > 0 ? (float)(0.9 * (double)qs[0]) : 0.f;
     int n_sel = n;
     bool rem[SEL_MAX_PER];
     // cuts parallel to a forced cut (model_benchmarker.py:121-139)
@@ -92,7 +94,7 @@ select_cuts_kernel(const float* __restrict__ quality, const float* __restrict__ 
             bool r = false;
             if (p < n_sel) {
                 const double pl = (double)row[order[p]];
-                r = pl > p_max && ((double)qs[p] < low_thr || pl > p_max_ub);
+                r = pl > p_max && (qs[p] < low_thr || pl > p_max_ub);
             }
             rem[u] = r;
         }
@@ -106,7 +108,7 @@ select_cuts_kernel(const float* __restrict__ quality, const float* __restrict__ 
             bool r = false;
             if (p > i && p < n_sel) {
                 const double pl = (double)row[order[p]];
-                r = pl > p_max && ((double)qs[p] < low_thr || pl > p_max_ub);
+                r = pl > p_max && (qs[p] < low_thr || pl > p_max_ub);
             }
             rem[u] = r;
         }

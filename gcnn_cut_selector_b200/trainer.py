@@ -5,7 +5,10 @@ Samples are independent (block-diagonal batches, utils.py:403-407), so each rank
 its own shard with an UN-normalised MSE seed 2 (p - y); one all-reduce (sum) over a flat bucket
 ``[93,121 gradients | local cut count | local squared-error sum]`` followed by a fused Adam that divides by the
 global cut count reproduces the single-process mean over all cuts exactly (a mean of per-rank means would not when
-ranks hold different numbers of cuts).  The message is 372 KB: latency-bound, one NCCL call over NVLink.
+ranks hold different numbers of cuts).  The message is 372 KB: latency-bound.  On the GPUs of one box the exchange and
+the optimiser are ONE kernel per rank over NVLink peer memory (``peer_exchange``: every rank reads the other ranks'
+buckets in rank order through CUDA-IPC mappings and applies Adam, csrc/dp.cu); the NCCL ``all_reduce`` + Adam launch pair
+is the fallback (gloo on CPU in the tests).
 """
 from __future__ import annotations
 
@@ -20,6 +23,23 @@ def reduce_bucket(bucket: torch.Tensor, group=None) -> torch.Tensor:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=group)
     return bucket
+
+
+def ordered_bucket_sum(buckets):
+    """CPU emulation of the peer-memory exchange's reduction: the ranks' buckets are added element-wise IN RANK ORDER,
+    in fp32 (csrc/dp.cu) -- every rank forms the same bits.  ``buckets``: list of 1-D float32 arrays / tensors."""
+    import numpy as np
+    acc = np.zeros_like(np.asarray(buckets[0], dtype=np.float32))
+    for b in buckets:
+        acc = (acc + np.asarray(b, dtype=np.float32)).astype(np.float32)
+    return acc
+
+
+class _DeviceArray:
+    """A library-owned device buffer as a ``__cuda_array_interface__`` object (torch.as_tensor maps it without a copy)."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
 
 
 def gather_prenorm_stats(mean, var, count, group=None):
@@ -50,7 +70,7 @@ class DataParallelTrainer:
 
     N = _lib.N_TRAINABLE
 
-    def __init__(self, model, lr: float = 1e-4, group=None):
+    def __init__(self, model, lr: float = 1e-4, group=None, peer_exchange: bool | None = None):
         self.model, self.lr, self.group = model, lr, group
         self.bucket = torch.zeros(self.N + 2, dtype=torch.float32, device=model.device)
         model.flat_grads = self.bucket[:self.N]
@@ -59,6 +79,51 @@ class DataParallelTrainer:
         self.tail_on_device = model.device.type == "cuda"
         if self.tail_on_device:
             model.set_option("count_before_loss", 1)
+        # peer-memory exchange fused with Adam: default on for NCCL groups (one box); GCNN_DP_PEER=0 keeps NCCL
+        self.peer = False
+        self._peer_buckets = None
+        self._sums = None
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        if peer_exchange is None:
+            import os
+            peer_exchange = (world > 1 and self.tail_on_device and dist.get_backend(group) == "nccl"
+                             and os.environ.get("GCNN_DP_PEER", "1") != "0")
+        if peer_exchange and world > 1:
+            self._connect_peers(world, dist.get_rank(group))
+
+    def _connect_peers(self, world: int, rank: int):
+        """Exchange the CUDA-IPC handles of the ranks' communication blocks and map them (all ranks on one box)."""
+        import ctypes as C
+        m, lib = self.model, self.model._lib
+        handle = (C.c_ubyte * 64)()
+        ok = torch.ones(1, dtype=torch.int32, device=m.device)
+        try:
+            with torch.cuda.device(m.device):
+                _lib.check(lib.gcnn_dp_create(m._ws, world, rank, handle))
+        except Exception:
+            ok.zero_()
+        mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=m.device)
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine, group=self.group)
+        if int(ok.item()):
+            blob = bytes(torch.cat(parts).cpu().numpy().tobytes())
+            try:
+                with torch.cuda.device(m.device):
+                    _lib.check(lib.gcnn_dp_connect(m._ws, blob))
+            except Exception:
+                ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)  # every rank or none
+        if not int(ok.item()):
+            return
+        self._peer_buckets = [torch.as_tensor(_DeviceArray(int(lib.gcnn_dp_bucket(m._ws, p)), self.N + 2), device=m.device)
+                              for p in (0, 1)]
+        self._sums = torch.zeros(2, dtype=torch.float32, device=m.device)
+        self.peer = True
+        self._use_bucket(int(lib.gcnn_dp_next_parity(m._ws)))
+
+    def _use_bucket(self, parity: int):
+        self.bucket = self._peer_buckets[parity]
+        self.model.flat_grads = self.bucket[:self.N]
 
     def broadcast_parameters(self, src: int = 0):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
@@ -91,8 +156,17 @@ class DataParallelTrainer:
         return passes
 
     def _finish(self, want_loss: bool):
+        m = self.model
+        if self.peer:  # one kernel: wait for the peers' buckets, sum in rank order, Adam (csrc/dp.cu)
+            with torch.cuda.device(m.device):
+                _lib.check(m._lib.gcnn_dp_allreduce_adam(m._ws, m.flat_params.data_ptr(), m.adam_m.data_ptr(),
+                                                         m.adam_v.data_ptr(), self.lr, 0.9, 0.999, 1e-7, m.adam_step + 1,
+                                                         self._sums.data_ptr(), m._stream()))
+            m.adam_step += 1
+            self._use_bucket(int(m._lib.gcnn_dp_next_parity(m._ws)))
+            return self._sums[1:2] / self._sums[0:1] if want_loss else None
         reduce_bucket(self.bucket, self.group)
-        self.model.apply_gradients(self.lr, grad_divisor=self.bucket[self.N:self.N + 1])
+        m.apply_gradients(self.lr, grad_divisor=self.bucket[self.N:self.N + 1])
         return self.bucket[self.N + 1:self.N + 2] / self.bucket[self.N:self.N + 1] if want_loss else None
 
     def step(self, inputs, targets, want_loss: bool = True):

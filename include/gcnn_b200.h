@@ -104,7 +104,10 @@ int64_t gcnn_workspace_bytes(const gcnn_workspace* ws);
 /* Options: "tensor_cores" (1 = tcgen05 dense layers [default], 0 = exact-fp32 SIMT dense layers; env GCNN_TC),
  * "streams" (1 = independent kernels on auxiliary streams [default], 0 = everything on the caller's stream; env
  * GCNN_STREAMS), "blocks" (1 = use the batch's per-sample counts: shared-memory block edge kernels and per-sample
- * transposed layouts [default], 0 = generic kernels; env GCNN_BLOCKS).  Takes effect from the next call. */
+ * transposed layouts [default], 0 = generic kernels; env GCNN_BLOCKS), "precision" (0 = fp32-accurate dense layers:
+ * bf16x3 operands, six tensor-core products per MMA, scores and gradients within 1e-5 of the reference [default]; 1 =
+ * bf16 MLP path: one product per MMA, the dense layers see bf16 operands with fp32 accumulation, within 1e-2 -- the two
+ * accuracy classes of BASELINE.json).  Takes effect from the next call. */
 int gcnn_set_option(gcnn_workspace* ws, const char* name, int value);
 /* Synchronise `stream` and report deferred errors (GCNN_INVALID if any edge index was out of range). */
 int gcnn_check(gcnn_workspace* ws, void* stream);
@@ -163,14 +166,35 @@ int gcnn_forward_backward(gcnn_workspace* ws, const float* params, const float* 
 int gcnn_ranking_deviation(const float* predictions, const float* improvements, const int32_t* cut_offsets,
                             int64_t n_samples, int max_cuts, int32_t* deviation_out, void* stream);
 
+/* ---- data-parallel training on the GPUs of one box (the reference trains in one process): the gradient
+ *      exchange as ONE kernel per rank over NVLink peer memory, fused with Adam.  Each rank's bucket [93,121 gradients |
+ *      local cut count | local squared error] lives in a library-owned block that the other ranks map through CUDA IPC:
+ *        gcnn_dp_create   allocates the block and returns its 64-byte IPC handle (exchange the handles of all ranks with
+ *                         any host-side all-gather, e.g. torch.distributed);
+ *        gcnn_dp_connect  maps the peers' blocks (handles: world x 64 bytes in rank order, own entry ignored);
+ *        gcnn_dp_bucket   the local bucket of step parity 0 / 1 -- pass it as grads_out (and bucket + 93,122 as
+ *                         loss_sum_out with option "count_before_loss") to gcnn_forward_backward with seed_scale 1;
+ *                         gcnn_dp_next_parity tells which one the next gcnn_dp_allreduce_adam will read;
+ *        gcnn_dp_allreduce_adam  waits for every rank's bucket of this step, sums them in rank order (bit-identical on all
+ *                         ranks), divides by the global cut count and applies Keras Adam (model_trainer.py:131, 273) to
+ *                         the local parameter replica; sums_out (optional, device, 2 floats): global cut count and squared
+ *                         error.  Every rank must call it once per step.  A peer that never arrives is reported as
+ *                         GCNN_INVALID at the next gcnn_check (10 s timeout) instead of hanging the device. */
+int gcnn_dp_create(gcnn_workspace* ws, int world, int rank, void* handle_out64);
+int gcnn_dp_connect(gcnn_workspace* ws, const void* handles);
+float* gcnn_dp_bucket(gcnn_workspace* ws, int parity);
+int gcnn_dp_next_parity(const gcnn_workspace* ws);
+int gcnn_dp_allreduce_adam(gcnn_workspace* ws, float* params, float* adam_m, float* adam_v, float lr, float beta1,
+                           float beta2, float eps, int64_t step, float* sums_out, void* stream);
+
 /* Cut selection after scoring: the ranking and parallelism filter of CustomCutsel.cutselselect
  * (model_benchmarker.py:108-157; identical in model_evaluator.py and model_evaluator_igc.py).  quality [n_cuts]: the
  * predicted bound improvements (or the hybrid rule's scores); parallelism [n_cuts, n_cuts]: getRowParallelism(cut i, cut j);
  * parallelism_forced [n_forced, n_cuts]: getRowParallelism(forced cut f, cut j) (NULL when n_forced == 0); all device
  * pointers, original cut numbering.  Cuts are ranked by quality (descending, stable, like Python's sorted); then every
  * forced cut and, in turn, every surviving cut i moves the cuts j behind it with parallelism > p_max to the back when
- * quality[position j] < 0.9 * quality[position 0] or parallelism > p_max_ub ("quality" stays indexed by position, as in
- * the reference).  order_out [n_cuts]: cut index at each final position; n_selected_out[0] = min(kept, max_selected).
+ * quality[position j] < float(0.9 * quality[position 0]) or parallelism > p_max_ub ("quality" stays indexed by position
+ * and the threshold is rounded to float32, as the reference's numpy does for the model's float32 scores).  order_out [n_cuts]: cut index at each final position; n_selected_out[0] = min(kept, max_selected).
  * At most 8,192 cuts. */
 int gcnn_select_cuts(const float* quality, const float* parallelism_forced, const float* parallelism, int64_t n_cuts,
                      int64_t n_forced, double p_max, double p_max_ub, int64_t max_selected, int32_t* order_out,

@@ -420,9 +420,18 @@ def select_cuts(quality, parallelism, parallelism_forced=None, p_max=0.1, p_max_
     quality = -np.sort(-quality)                                                              # :117
     n_selected = n                                                                            # :120
 
+    # `quality < 0.9 * quality[0]` (:128 / :149) under the reference's pinned numpy 1.22.3 (environment.yml:6): the product
+    # of a Python float and a numpy scalar is a float64 scalar, and comparing a float32 ARRAY (the GCNN's scores) with it
+    # uses value-based casting, i.e. the threshold is rounded to float32 and the comparison runs in float32; a float64
+    # array (the hybrid rule's scores) compares in float64.  Spelled out so that the result does not depend on the numpy
+    # installed here (numpy >= 2 would multiply in float32).
+    threshold = 0.9 * float(quality[0]) if n else 0.0
+    if quality.dtype == np.float32:
+        threshold = np.float32(threshold)
+
     def remove(parallelism_row, n_selected, sorted_cuts):
         marked = (parallelism_row > p_max)                                                    # :125 / :146
-        low_quality = np.logical_or(quality < 0.9 * quality[0], parallelism_row > p_max_ub)   # :128 / :149
+        low_quality = np.logical_or(quality < threshold, parallelism_row > p_max_ub)          # :128 / :149
         to_remove = np.logical_and(marked, low_quality)                                       # :129 / :150
         removed = sorted_cuts[to_remove]                                                      # :132 / :153
         sorted_cuts = np.delete(sorted_cuts, to_remove)

@@ -15,7 +15,7 @@ import torch.multiprocessing as mp
 
 import gcnn_oracle as orc
 from gcnn_cut_selector_b200 import batching, synth
-from gcnn_cut_selector_b200.trainer import gather_prenorm_stats, reduce_bucket
+from gcnn_cut_selector_b200.trainer import gather_prenorm_stats, ordered_bucket_sum, reduce_bucket
 
 N = orc.N_TRAINABLE
 
@@ -73,6 +73,42 @@ def test_dp_bucket_reduction_matches_single_process(tmp_path):
         per_rank.append(_flat(orc.loss_and_grads(model, batching.model_inputs(bt), bt[10])[2]).numpy())
     naive = 0.5 * (per_rank[0] + per_rank[1])
     assert np.abs(naive - want).max() > 1e-3 * np.abs(want).max()
+
+
+def _ordered_worker(rank, world, port, out_dir):
+    """What csrc/dp.cu does on the GPUs, emulated over gloo: every rank gathers all fp32 buckets and adds them in RANK
+    order (not in an order the collective library picks), then applies the same Adam update to its replica."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(40 + rank)
+    bucket = torch.from_numpy((rng.standard_normal(N + 2) * 10.0 ** rng.integers(-6, 3, N + 2)).astype(np.float32))
+    bucket[N] = 7 + rank
+    parts = [torch.empty_like(bucket) for _ in range(world)]
+    dist.all_gather(parts, bucket)
+    total = ordered_bucket_sum([p.numpy() for p in parts])
+    # Keras Adam on the replica (model_trainer.py:131, 273), step 1, from identical parameters
+    p0 = np.linspace(-1, 1, N).astype(np.float32)
+    g = (total[:N] / total[N]).astype(np.float32)
+    m, v = (g * np.float32(0.1)).astype(np.float32), (g * g * np.float32(0.001)).astype(np.float32)
+    lr_t = np.float32(1e-3 * np.sqrt(1 - 0.999) / (1 - 0.9))
+    p1 = (p0 - lr_t * m / (np.sqrt(v) + np.float32(1e-7))).astype(np.float32)
+    np.save(os.path.join(out_dir, f"ordered{rank}.npy"), np.concatenate([total, p1]))
+    np.save(os.path.join(out_dir, f"bucket{rank}.npy"), bucket.numpy())
+    dist.destroy_process_group()
+
+
+def test_fixed_order_reduction_is_bit_identical_on_all_ranks(tmp_path):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_ordered_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    o0, o1 = (np.load(tmp_path / f"ordered{r}.npy") for r in range(2))
+    np.testing.assert_array_equal(o0, o1)  # same sums, same updated parameters, bit for bit
+    b0, b1 = (np.load(tmp_path / f"bucket{r}.npy") for r in range(2))
+    np.testing.assert_array_equal(o0[:N + 2], (b0.astype(np.float32) + b1.astype(np.float32)).astype(np.float32))
+    # the order is part of the contract: fp32 addition does not associate
+    three = [b0, b1, (b0 * np.float32(-1.0000001)).astype(np.float32)]
+    assert np.any(ordered_bucket_sum(three) != ordered_bucket_sum(three[::-1]))
 
 
 def test_reduce_bucket_is_identity_without_process_group():

@@ -923,13 +923,17 @@ def test_graph_scoring_matches_eager_scoring(golden_dir):
     batches = [batching.concat_samples(synth.make_samples(shape, 1, seed0=s)) for shape, s in
                (("combauc", 1), ("combauc", 2), ("indset", 3), ("mini", 4))]
     hbs = [HostBatch(b) for b in batches]
-    want = [m.score_host(h).copy() for h in hbs]
+    eager = [m.score_host(h).copy() for h in hbs]
+    want = [m.score_host(h, graph=True).copy() for h in hbs]  # first call of a shape: the same launches, not yet captured
+    for w, e in zip(want, eager):  # (score_host uses the batch's per-sample counts -> block kernels: another summation order)
+        assert rel_err(w, e) <= 2e-6
     for rep in range(4):
         for h, w in zip(hbs, want):
             np.testing.assert_array_equal(m.score_host(h, graph=True), w)
     assert m._lib.gcnn_serve_graph_count(m._ws) >= 1  # (0 would mean the capture fell back to eager launches)
     big = HostBatch(batching.concat_samples(synth.make_samples("setcov", 2, seed0=5)))  # grows the workspace
-    w_big = m.score_host(big).copy()
+    w_big = m.score_host(big, graph=True).copy()
+    assert rel_err(w_big, m.score_host(big)) <= 2e-6
     for rep in range(3):
         np.testing.assert_array_equal(m.score_host(big, graph=True), w_big)
         np.testing.assert_array_equal(m.score_host(hbs[0], graph=True), want[0])
@@ -941,3 +945,47 @@ def test_graph_scoring_matches_eager_scoring(golden_dir):
     with pytest.raises(InvalidArgumentError):
         m.score_host(HostBatch(tuple(bad)), graph=True)
     np.testing.assert_array_equal(m.score_host(hbs[0], graph=True), want[0])
+
+
+# ---- bf16 MLP path: the 1e-2 accuracy class of BASELINE.json -------------------------------------------------------------
+BF16_TOL = 1e-2
+
+
+@pytest.mark.parametrize("counts", [False, True], ids=["totals", "per_sample_counts"])
+@pytest.mark.parametrize("shape,n", [("setcov", 3), ("combauc", 4), ("indset", 4), ("capfac", 1), ("setcov", 32)])
+def test_bf16_mlp_mode_within_1e2(golden_dir, oracle64, shape, n, counts):
+    """option "precision" = 1: the dense layers run as plain bf16 tensor-core products with fp32 accumulation (one product
+    per MMA instead of the six of the fp32-accurate path); edge kernels, loss and Adam stay fp32.  Scores, loss and every
+    parameter gradient within 1e-2 of the fp64 oracle (relative to the tensor's max-abs / L2) on all four problem classes
+    and at BASELINE config 2's size; the mode is off by default and switches back cleanly."""
+    from gcnn_cut_selector_b200 import GCNN
+    m = GCNN(device="cuda:0", seed=0)
+    m.restore_state(os.path.join(golden_dir, "state_stream.pkl"))
+    batch = batching.concat_samples(synth.make_samples(shape, n, seed0=1000 + n, n_structures=min(n, 8)))
+    inputs, targets = batching.model_inputs(batch, per_sample_counts=counts), batch[10]
+    if n == 32:
+        loss, pred, grads = _oracle_at_size(golden_dir, "bf16_c2", batching.model_inputs(batch), targets)
+    else:
+        l, p, grads = orc.loss_and_grads(oracle64, batching.model_inputs(batch), targets)
+        loss, pred = float(l), p.numpy()
+    _, s32 = m.loss_and_grads(inputs, targets)
+    g32 = m.flat_grads.clone()
+    m.set_option("precision", 1)
+    loss_sum, scores = m.loss_and_grads(inputs, targets)
+    torch.cuda.synchronize()
+    err = rel_err(scores.cpu().numpy(), pred)
+    assert err <= BF16_TOL
+    assert err >= 1e-5  # (it really is another numerics path, not the fp32-accurate one)
+    assert abs(float(loss_sum) / scores.numel() - loss) <= 2 * BF16_TOL * loss
+    assert_grads_close(m.flat_grads.cpu().numpy(), grads, tol=BF16_TOL)
+    m.set_option("precision", 0)
+    _, s_back = m.loss_and_grads(inputs, targets)
+    assert torch.equal(s_back, s32) and torch.equal(m.flat_grads, g32)
+
+
+def test_bf16_mlp_mode_needs_the_chain_kernels(golden_dir):
+    from gcnn_cut_selector_b200 import GCNN, InvalidArgumentError
+    m = GCNN(device="cuda:0", seed=0)
+    m.set_option("tensor_cores", 0)
+    with pytest.raises(InvalidArgumentError):
+        m.set_option("precision", 1)
