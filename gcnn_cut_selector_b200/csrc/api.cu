@@ -37,6 +37,21 @@ struct Profiler {
 };
 static Profiler g_prof;
 
+int ensure_dynamic_smem(const void* kern, int bytes, unsigned* done_mask) {
+    int dev = 0;
+    GCNN_CUDA_TRY(cudaGetDevice(&dev));
+    const unsigned bit = 1u << (dev & 31);
+    if (*done_mask & bit) return GCNN_OK;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cudaFuncSetAttribute(%d bytes of dynamic shared memory): %s", bytes, cudaGetErrorString(e));
+        return GCNN_CUDA_ERROR;
+    }
+    *done_mask |= bit;
+    return GCNN_OK;
+}
+
 bool pdl_enabled() {
     static const bool on = [] { const char* e = getenv("GCNN_PDL"); return !(e && e[0] == '0'); }();
     return on;

@@ -35,14 +35,24 @@ struct ProfScope {  // records a start/stop event pair around the launches issue
         }                                                                                   \
     } while (0)
 
+// (cudaGetLastError, not Peek: a failed launch must not poison the checks of later, unrelated calls)
 #define GCNN_LAUNCH_CHECK()                                                                 \
     do {                                                                                    \
         gcnn::count_launch();                                                               \
-        cudaError_t err__ = cudaPeekAtLastError();                                          \
+        cudaError_t err__ = cudaGetLastError();                                             \
         if (err__ != cudaSuccess) {                                                         \
             gcnn::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(err__), __FILE__, __LINE__); \
             return GCNN_CUDA_ERROR;                                                         \
         }                                                                                   \
+    } while (0)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per DEVICE: each call site keeps one bit per device ordinal, so a
+// workspace on cuda:1 in a process whose first model lived on cuda:0 still gets its kernels' limits raised.
+int ensure_dynamic_smem(const void* kern, int bytes, unsigned* done_mask);
+#define GCNN_ENSURE_SMEM(kern, bytes)                                                              \
+    do {                                                                                           \
+        static unsigned done__ = 0;                                                                \
+        GCNN_TRY(gcnn::ensure_dynamic_smem((const void*)(kern), (int)(bytes), &done__));            \
     } while (0)
 
 #define GCNN_TRY(expr)                  \

@@ -148,9 +148,9 @@ int dp_allreduce_adam(DpState* s, float* params, float* m, float* v, float lr_t,
     ++s->seq;
     const int64_t n = GCNN_N_TRAINABLE;
     ProfScope prof(PROF_ADAM, 4.0 * (double)n * (s->world + 6), st);
-    int clock_khz = 1965000;
-    cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, 0);
-    const long long timeout = 10LL * 1000LL * (long long)clock_khz;  // ~10 s
+    // ~10 s of SM clocks at the B200's 1.965 GHz boost (a fixed constant: querying the clock attribute costs a
+    // millisecond of host time per call)
+    const long long timeout = 10LL * 1965000000LL;
     GCNN_LAUNCH(dp_allreduce_adam_kernel, (unsigned)ceil_div(n, DP_THREADS), DP_THREADS, 0, st, s->peers,
                 (uint32_t*)((char*)s->block + sizeof(float) * 2 * DP_BUCKET_FLOATS), s->world, s->rank, s->seq, params, m, v,
                 n, lr_t, beta1, beta2, eps, sums_out, err_flag, timeout);

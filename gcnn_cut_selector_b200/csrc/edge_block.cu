@@ -495,11 +495,6 @@ bool edge_block_fits(int64_t max_send_rows, int64_t max_recv_rows, bool training
 }
 bool edge_block_backward_fits(int64_t max_recv_rows) { return plan_slice_width(max_recv_rows, 2) != 0; }
 
-template <typename Kern>
-static int set_max_smem(Kern kern) {
-    GCNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BLK_SMEM_BUDGET));
-    return GCNN_OK;
-}
 
 // One row per lane group when a CTA's rows fill (most of) its groups; the groups of a warp share one row otherwise (few
 // long rows: the 64 cut rows of a sample).  GCNN_BLOCK_SPLIT=0/1 forces one mapping (experiments).
@@ -524,8 +519,7 @@ int edge_block_forward(const EdgeLayout& by_recv, const int32_t* recv_off, const
     ProfScope prof(PROF_EDGE_FWD, prof_bytes, st);
 #define GCNN_BLK_FWD(FW_, TRAIN_, SPLIT_)                                                                                 \
     do {                                                                                                                   \
-        static int once = set_max_smem(edge_block_forward_kernel<FW_, TRAIN_, SPLIT_>);                                    \
-        GCNN_TRY(once);                                                                                                    \
+        GCNN_ENSURE_SMEM((edge_block_forward_kernel<FW_, TRAIN_, SPLIT_>), BLK_SMEM_BUDGET);                                        \
         GCNN_LAUNCH((edge_block_forward_kernel<FW_, TRAIN_, SPLIT_>), grid, BLK_THREADS, smem, st, by_recv.ptr,            \
                     by_recv.pair, recv_off, send_off, K, R, S, w_edge, sc.s_f, H, cnt, rows);                             \
     } while (0)
@@ -557,8 +551,7 @@ int edge_block_backward(const EdgeLayout& by_send, const int32_t* send_off, cons
     ProfScope prof(PROF_EDGE_BWD, prof_bytes, st);
 #define GCNN_BLK_BWD(FW_, SPLIT_)                                                                                          \
     do {                                                                                                                   \
-        static int once = set_max_smem(edge_block_backward_kernel<FW_, SPLIT_>);                                           \
-        GCNN_TRY(once);                                                                                                    \
+        GCNN_ENSURE_SMEM((edge_block_backward_kernel<FW_, SPLIT_>), BLK_SMEM_BUDGET);                                        \
         GCNN_LAUNCH((edge_block_backward_kernel<FW_, SPLIT_>), grid, BLK_THREADS, smem, st, by_send.ptr, by_send.pair,      \
                     send_off, recv_off, K, R, S, G, w_edge, sc.s_f, dS, dw_partials, rows);                                \
     } while (0)
@@ -778,8 +771,7 @@ int transpose_blocks(const int32_t* keys_var, const int32_t* keys_left, const fl
     ProfScope prof(PROF_CSR_SCATTER, 12.0 * (double)E + 20.0 * (double)E + 4.0 * (double)(n_var + 1), st);
 #define GCNN_TR(W_)                                                                                                        \
     do {                                                                                                                   \
-        static int once = set_max_smem(transpose_blocks_kernel<W_>);                                                       \
-        GCNN_TRY(once);                                                                                                    \
+        GCNN_ENSURE_SMEM((transpose_blocks_kernel<W_>), BLK_SMEM_BUDGET);                                        \
         GCNN_LAUNCH_ORDERED(transpose_blocks_kernel<W_>, grid, W_ * 32, smem, st, keys_var, keys_left, feats, E,            \
                             (int32_t)n_left, (int32_t)n_var, left_off, var_off, (int)n_blocks, cap, range_cap, out,       \
                             f_shift, f_scale, err_flag, unsorted_flag, unsorted_flag + LONG_FLAG_OFFSET,                  \

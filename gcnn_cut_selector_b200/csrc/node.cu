@@ -92,25 +92,17 @@ linear_forward_kernel(LinFwdArgs a) {
     }
 }
 
-template <typename Kern>
-static int set_smem(Kern kern, size_t bytes) {
-    GCNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    return GCNN_OK;
-}
-
 int linear_forward(const LinFwdArgs& a, cudaStream_t st) {
     if (a.M <= 0) return GCNN_OK;
     ProfScope prof(PROF_LIN_FWD, 4.0 * ((double)a.M * (a.K + D) + (double)a.K * D + D), st);
     const unsigned grid = (unsigned)ceil_div(a.M, LIN_ROWS);
     if (a.K == 64) {
         const size_t smem = sizeof(float) * (LIN_ROWS * 68 + 64 * D);
-        static int once = set_smem(linear_forward_kernel<64>, smem);
-        GCNN_TRY(once);
+        GCNN_ENSURE_SMEM(linear_forward_kernel<64>, smem);
         GCNN_LAUNCH(linear_forward_kernel<64>, grid, LIN_THREADS, smem, st, a);
     } else if (a.K == 128) {
         const size_t smem = sizeof(float) * (LIN_ROWS * 132 + 128 * D);
-        static int once = set_smem(linear_forward_kernel<128>, smem);
-        GCNN_TRY(once);
+        GCNN_ENSURE_SMEM(linear_forward_kernel<128>, smem);
         GCNN_LAUNCH(linear_forward_kernel<128>, grid, LIN_THREADS, smem, st, a);
     } else {
         set_error("linear_forward: K must be 64 or 128");
@@ -193,8 +185,7 @@ int linear_dgrad(const LinDgradArgs& a, cudaStream_t st) {
                               (a.K == 128 && a.accumulate2 ? 1.0 : 0.0) + (a.dR ? 2.0 : 0.0);
     ProfScope prof(PROF_LIN_DGRAD, 256.0 * (double)a.M * rows_moved + 4.0 * a.K * D, st);
     const size_t smem = sizeof(float) * (LIN_ROWS * 68 + D * D);
-    static int once = set_smem(linear_dgrad_kernel, smem);
-    GCNN_TRY(once);
+    GCNN_ENSURE_SMEM(linear_dgrad_kernel, smem);
     dim3 grid((unsigned)ceil_div(a.M, LIN_ROWS), a.K / 64);
     GCNN_LAUNCH(linear_dgrad_kernel, grid, LIN_THREADS, smem, st, a);
     GCNN_LAUNCH_CHECK();
@@ -668,12 +659,7 @@ int ranking_deviation(const float* pred, const float* truth, const int32_t* offs
     if (n_samples <= 0) return GCNN_OK;
     const size_t smem = 2 * sizeof(int32_t) * (size_t)(max_cuts > 0 ? max_cuts : 1);
     if (smem > 200 * 1024) { set_error("ranking_deviation: more than 25,600 cuts in one sample"); return GCNN_INVALID; }
-    if (smem > 48 * 1024) {
-        static int once = [] {
-            return cudaFuncSetAttribute(ranking_deviation_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess ? 0 : 1;
-        }();
-        if (once) { set_error("ranking_deviation: cannot raise the shared-memory limit"); return GCNN_CUDA_ERROR; }
-    }
+    if (smem > 48 * 1024) GCNN_ENSURE_SMEM(ranking_deviation_kernel, 200 * 1024);
     GCNN_LAUNCH(ranking_deviation_kernel, (unsigned)n_samples, RANK_THREADS, smem, st, pred, truth, offsets_dev, deviation, max_cuts);
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;

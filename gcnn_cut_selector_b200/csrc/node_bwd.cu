@@ -355,13 +355,7 @@ int tc_conv_backward(const ConvBwdArgs& a, int* n_parts, cudaStream_t st) {
     // algorithmic bytes: read dP, Y, U1, C, X_t, H, cnt; write dXt, G, dR (one 256-byte row each per node); five weight
     // images; one partial per CTA
     ProfScope prof(PROF_CONV_BWD, 256.0 * 10.0 * (double)a.M + 5.0 * W16_BYTES + 4.0 * CONV_BWD_PART * parts, st);
-    static int once = [] {
-        cudaError_t e = cudaFuncSetAttribute(tc_conv_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)CONV_BWD_SMEM);
-        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(tc_conv_backward_kernel): %s", cudaGetErrorString(e)); return (int)GCNN_CUDA_ERROR; }
-        return (int)GCNN_OK;
-    }();
-    GCNN_TRY(once);
+    GCNN_ENSURE_SMEM(tc_conv_backward_kernel, CONV_BWD_SMEM);
     GCNN_LAUNCH(tc_conv_backward_kernel, parts, BWD_THREADS, CONV_BWD_SMEM, st, a);
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
@@ -610,13 +604,7 @@ int tc_embed_backward(const EmbBwdArgs& a, int* n_parts, cudaStream_t st) {
     *n_parts = parts;
     const double rows_moved = (a.dP1 ? 5.0 : 4.0);  // dP_j, out, dXt, h1 (256 B per node each) + the raw features
     ProfScope prof(PROF_EMB_BWD, (256.0 * rows_moved + 4.0 * a.K) * (double)a.M + 3.0 * W16_BYTES + 4.0 * EMB_BWD_PART * parts, st);
-    static int once = [] {
-        cudaError_t e = cudaFuncSetAttribute(tc_embed_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)CONV_BWD_SMEM);
-        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(tc_embed_backward_kernel): %s", cudaGetErrorString(e)); return (int)GCNN_CUDA_ERROR; }
-        return (int)GCNN_OK;
-    }();
-    GCNN_TRY(once);
+    GCNN_ENSURE_SMEM(tc_embed_backward_kernel, CONV_BWD_SMEM);
     GCNN_LAUNCH(tc_embed_backward_kernel, parts, BWD_THREADS, CONV_BWD_SMEM, st, a);
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;

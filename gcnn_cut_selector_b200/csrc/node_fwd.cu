@@ -305,20 +305,13 @@ tc_embed_forward16_kernel(const EmbFwdArgs a) {
     if (warp == 0) tmem_dealloc(acc0, 128);
 }
 
-static int set_fwd_smem(const void* kern) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(forward chain): %s", cudaGetErrorString(e)); return GCNN_CUDA_ERROR; }
-    return GCNN_OK;
-}
-
 // `a.img_*` are bf16x3 T images (B[n][k] = W[k][n]) here
 int tc_conv_forward16(const ConvFwdArgs& a, cudaStream_t st) {
     if (a.M <= 0) return GCNN_OK;
     const int stages = a.img_n ? 4 : 3;
     const double rows = 2.0 + (a.C ? 1 : 0) + (a.U1 ? 1 : 0) + 1.0 + (stages == 4 ? 1 : 0);
     ProfScope prof(PROF_LIN_FWD, 256.0 * (double)a.M * rows + 4.0 * D * D * (stages + 1), st);
-    static int once = set_fwd_smem((const void*)tc_conv_forward16_kernel);
-    GCNN_TRY(once);
+    GCNN_ENSURE_SMEM(tc_conv_forward16_kernel, FWD_SMEM);
     GCNN_LAUNCH(tc_conv_forward16_kernel, (unsigned)ceil_div(a.M, TC_ROWS), BWD_THREADS, FWD_SMEM, st, a);
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
@@ -329,8 +322,7 @@ int tc_embed_forward16(const EmbFwdArgs& a, cudaStream_t st) {
     if (a.K > 14) { set_error("tc_embed_forward: at most 14 input features"); return GCNN_INVALID; }
     const int n_proj = a.img_p[1] ? 2 : 1;
     ProfScope prof(PROF_EMB1_FWD, (4.0 * a.K + 256.0 * (2 + n_proj)) * (double)a.M + 4.0 * (a.K * D + D * D * (1 + n_proj)), st);
-    static int once = set_fwd_smem((const void*)tc_embed_forward16_kernel);
-    GCNN_TRY(once);
+    GCNN_ENSURE_SMEM(tc_embed_forward16_kernel, FWD_SMEM);
     GCNN_LAUNCH(tc_embed_forward16_kernel, (unsigned)ceil_div(a.M, TC_ROWS), BWD_THREADS, FWD_SMEM, st, a);
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;

@@ -219,11 +219,6 @@ tc_linear_kernel(const TcArgs a) {
     if (warp == 0) tmem_dealloc(tmem_d, 64);
 }
 
-template <typename Kern>
-static int set_smem_tc(Kern kern, size_t bytes) {
-    GCNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    return GCNN_OK;
-}
 
 // ---- fused forward node chain of one convolution -----------------------------------------------------------------
 // PartialGraphConvolution after the segmented sum (model.py:563, 570-573) plus the next layer's projection, one CTA per
@@ -388,8 +383,7 @@ int tc_conv_forward(const ConvFwdArgs& a, cudaStream_t st) {
     const double rows = 2.0 + (a.C ? 1 : 0) + (a.U1 ? 1 : 0) + 1.0 + (stages == 4 ? 1 : 0);
     ProfScope prof(PROF_LIN_FWD, 256.0 * (double)a.M * rows + 4.0 * D * D * (stages + 1), st);
     const size_t smem = 2 * REG_BYTES + 3 * IMG_BYTES + 1024;
-    static int once = set_smem_tc(tc_conv_forward_kernel, smem);
-    GCNN_TRY(once);
+    GCNN_ENSURE_SMEM(tc_conv_forward_kernel, smem);
     GCNN_LAUNCH(tc_conv_forward_kernel, (unsigned)ceil_div(a.M, TC_ROWS), TC_THREADS, smem, st, a);
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
@@ -514,8 +508,7 @@ int tc_embed_forward(const EmbFwdArgs& a, cudaStream_t st) {
     // algorithmic bytes: read the raw features, write h1, out and the projections (256 B per node each), weights once
     ProfScope prof(PROF_EMB1_FWD, (4.0 * a.K + 256.0 * (2 + n_proj)) * (double)a.M + 4.0 * (a.K * D + D * D * (1 + n_proj)), st);
     const size_t smem = 2 * REG_BYTES + 3 * IMG_BYTES + 1024;
-    static int once = set_smem_tc(tc_embed_forward_kernel, smem);
-    GCNN_TRY(once);
+    GCNN_ENSURE_SMEM(tc_embed_forward_kernel, smem);
     GCNN_LAUNCH(tc_embed_forward_kernel, (unsigned)ceil_div(a.M, TC_ROWS), TC_THREADS, smem, st, a);
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
@@ -696,13 +689,11 @@ int tc_linear(const TcArgs& a, int prof_class, double prof_bytes, cudaStream_t s
     dim3 grid((unsigned)ceil_div(a.M, TC_ROWS), a.slabs);
     if (a.K == 64) {
         const size_t smem = 2 * 2 * A_BLOCK_BYTES + 2 * 2 * B_BLOCK_BYTES + 1024;
-        static int once = set_smem_tc(tc_linear_kernel<64>, smem);
-        GCNN_TRY(once);
+        GCNN_ENSURE_SMEM(tc_linear_kernel<64>, smem);
         GCNN_LAUNCH(tc_linear_kernel<64>, grid, TC_THREADS, smem, st, a);
     } else if (a.K == 128) {
         const size_t smem = 2 * 4 * A_BLOCK_BYTES + 2 * 4 * B_BLOCK_BYTES + 1024;
-        static int once = set_smem_tc(tc_linear_kernel<128>, smem);
-        GCNN_TRY(once);
+        GCNN_ENSURE_SMEM(tc_linear_kernel<128>, smem);
         GCNN_LAUNCH(tc_linear_kernel<128>, grid, TC_THREADS, smem, st, a);
     } else {
         set_error("tc_linear: K must be 64 or 128");
@@ -718,13 +709,11 @@ int tc_wgrad(const TcWgradArgs& a, cudaStream_t st) {
     ProfScope prof(PROF_LIN_WGRAD, 4.0 * ((double)a.M * (a.K + D + (a.mask_act ? D : 0)) + (double)a.K * D + D), st);
     if (a.K == 64) {
         const size_t smem = 8 * A_BLOCK_BYTES + 1024;
-        static int once = set_smem_tc(tc_wgrad_kernel<64>, smem);
-        GCNN_TRY(once);
+        GCNN_ENSURE_SMEM(tc_wgrad_kernel<64>, smem);
         GCNN_LAUNCH(tc_wgrad_kernel<64>, parts, TC_THREADS, smem, st, a);
     } else if (a.K == 128) {
         const size_t smem = 12 * A_BLOCK_BYTES + 1024;
-        static int once = set_smem_tc(tc_wgrad_kernel<128>, smem);
-        GCNN_TRY(once);
+        GCNN_ENSURE_SMEM(tc_wgrad_kernel<128>, smem);
         GCNN_LAUNCH(tc_wgrad_kernel<128>, parts, TC_THREADS, smem, st, a);
     } else {
         set_error("tc_wgrad: K must be 64 or 128");

@@ -125,12 +125,7 @@ int select_cuts(const float* quality, const float* par_forced, const float* par,
         return GCNN_INVALID;
     }
     const size_t smem = 12 * (size_t)(n > 0 ? n : 1);
-    if (smem > 48 * 1024) {
-        static int once = [] {
-            return cudaFuncSetAttribute(select_cuts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * SEL_THREADS * SEL_MAX_PER) == cudaSuccess ? 0 : 1;
-        }();
-        if (once) { set_error("select_cuts: cannot raise the shared-memory limit"); return GCNN_CUDA_ERROR; }
-    }
+    if (smem > 48 * 1024) GCNN_ENSURE_SMEM(select_cuts_kernel, 12 * SEL_THREADS * SEL_MAX_PER);
     const int ms = (int)(max_selected < 0 ? 0 : (max_selected > (int64_t)INT32_MAX ? INT32_MAX : max_selected));
     GCNN_LAUNCH(select_cuts_kernel, 1, SEL_THREADS, smem, st, quality, par_forced, par, (int)n, (int)n_forced, p_max,
                 p_max_ub, ms, order_out, n_selected_out);
