@@ -477,11 +477,17 @@ def run_b200(args):
         # the bf16 MLP path (BASELINE.json's 1e-2 accuracy class): same workload, separate labelled object, never the headline
         model.set_option("precision", 1)
         rb = measure_training(model, trainer, graphs, max(10, K // 2), 3, world, rank, dev, detail=False)
+        model.set_option("precision", 2)
+        rb1 = measure_training(model, trainer, graphs, max(10, K // 2), 3, world, rank, dev, detail=False)
         model.set_option("precision", 0)
-        bf16 = {"dtype": "bf16 MLP (dense layers: bf16 operands, fp32 accumulate; edge kernels, loss, Adam fp32)",
+        bf16 = {"dtype": "bf16 MLP (dense layers: three bf16 products per MMA -- hi*hi + hi*lo + lo*hi -- fp32 accumulate; "
+                         "edge kernels, loss, Adam fp32)",
                 "accuracy_class": "1e-2 (tests/test_gpu_parity.py::test_bf16_mlp_mode_within_1e2)",
                 "workload": workload_name(graphs), "value": rb["value"], "unit": UNIT, "ms_per_step": rb["ms_per_step"],
-                "e2e": rb["e2e"]}
+                "e2e": rb["e2e"],
+                "one_product": {"note": "operands rounded to bf16, one product per MMA: measured 1.2-1.3e-2 from the "
+                                        "oracle, outside the 1e-2 class; a measurement point, not an offered mode",
+                                "value": rb1["value"], "unit": UNIT, "ms_per_step": rb1["ms_per_step"]}}
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()

@@ -120,7 +120,7 @@ struct gcnn_workspace {
     uint2* edge_masks[3] = {nullptr, nullptr, nullptr};  // per-edge ReLU masks of each convolution (by original edge id)
     int masks_valid[3] = {0, 0, 0};
     int use_fused_bwd = 1;
-    int bf16_mlp = 0;  // option "precision" = 1: plain bf16 MMAs (one product) in the four chain kernels -- the 1e-2 class
+    int bf16_mlp = 0;  // option "precision": 1 = three bf16 products per MMA in the four chain kernels (1e-2 class), 2 = one
     int use_bf16_fwd = 1;
     int use_edge_masks = 1;  // forward edge kernel records per-edge ReLU masks, the backward reads them  // forward chains on bf16x3 tiles (node_fwd.cu) instead of 3xTF32 (node_tc.cu)
     // set by gcnn_forward_backward around a fused step: head layer 2, the loss seed and its backward are ONE launch
@@ -169,6 +169,8 @@ struct gcnn_workspace {
     uint8_t* serve_pin = nullptr;              // pinned host mirror of one batch + its scores + the error word
     size_t serve_pin_bytes = 0;
     int serve_graphs_ok = 1;                   // cleared when a capture fails (then every call runs eagerly)
+    cudaStream_t serve_stream = nullptr;       // the serving path's own stream: the caller's may be the legacy default
+    cudaEvent_t serve_ev = nullptr;            // stream, which cannot be captured; ordered after the caller's by this event
     DpState* dp = nullptr;                     // data-parallel peer-memory exchange (gcnn_dp_*)
     int device = 0;                            // CUDA device the workspace lives on
     int64_t act_stamp = 0;                     // generation of the saved activations (gcnn_activation_stamp)
@@ -1217,6 +1219,8 @@ int gcnn_workspace_destroy(gcnn_workspace* ws) {
     if (ws->dp) { dp_destroy(ws->dp); ws->dp = nullptr; }
     serve_drop_graphs(ws);
     if (ws->serve_pin) cudaFreeHost(ws->serve_pin);
+    if (ws->serve_stream) cudaStreamDestroy(ws->serve_stream);
+    if (ws->serve_ev) cudaEventDestroy(ws->serve_ev);
     if (ws->arena) cudaFree(ws->arena);
     if (ws->stage_arena) cudaFree(ws->stage_arena);
     for (int i = 0; i < 4; ++i) {
@@ -1302,14 +1306,17 @@ int gcnn_set_option(gcnn_workspace* ws, const char* name, int value) {
     else if (!strcmp(name, "fused")) ws->use_fused = value != 0;
     else if (!strcmp(name, "blocks")) ws->use_blocks = value != 0;
     else if (!strcmp(name, "precision")) {
-        // 0: fp32-accurate (bf16x3 operands, six products per MMA; <= 1e-5 class); 1: bf16 MLP path (one product: the
-        // dense layers see bf16 operands with fp32 accumulation; <= 1e-2 class, BASELINE.json north_star).  The edge
-        // kernels, the loss and Adam stay fp32 in both.
+        // 0: fp32-accurate (bf16x3 operands, six products per MMA; <= 1e-5 class).  1: bf16 MLP path, three products
+        // (hi*hi + hi*lo + lo*hi of the two-piece split: bf16 MMAs, fp32 accumulation, ~16 operand bits) -- the mode
+        // that meets BASELINE.json's 1e-2 class with margin.  2: one product (operands rounded to bf16): measured
+        // 1.2-1.3e-2 on scores and gradients through the 14-layer-deep path, i.e. OUTSIDE the 1e-2 class; kept as a
+        // measurement point only.  The edge kernels, the loss and Adam stay fp32 in all three.
+        if (value < 0 || value > 2) { set_error("precision must be 0, 1 or 2"); return GCNN_INVALID; }
         if (value && !(ws->use_tc && ws->use_fused && ws->use_fused_bwd && ws->use_bf16_fwd)) {
-            set_error("precision = 1 needs the fused bf16x3 chain kernels (tensor_cores, fused, fused_backward, bf16_forward)");
+            set_error("precision > 0 needs the fused bf16x3 chain kernels (tensor_cores, fused, fused_backward, bf16_forward)");
             return GCNN_INVALID;
         }
-        ws->bf16_mlp = value != 0;
+        ws->bf16_mlp = value;
     }
     else if (!strcmp(name, "fused_backward")) ws->use_fused_bwd = value != 0;
     else if (!strcmp(name, "bf16_forward")) ws->use_bf16_fwd = value != 0;
@@ -1793,18 +1800,19 @@ static ServeLayout serve_layout(const gcnn_batch* b) {
 
 static int serve_enqueue(gcnn_workspace* ws, const float* params, const float* prenorm, const gcnn_batch* hb,
                          const ServeLayout& L, cudaStream_t st) {
+    // ONE copy: the pinned mirror and staging slot 0's raw area share the layout L (16-byte aligned sections)
     gcnn_workspace::Stage& g = ws->stage[0];
     uint8_t* pin = ws->serve_pin;
-    GCNN_TRY(h2d(g.cons, pin + L.off[0], sizeof(float) * hb->n_cons * GCNN_CONS_FEATS, st));
-    GCNN_TRY(h2d(g.cei, pin + L.off[1], sizeof(int32_t) * 2 * hb->n_cons_edges, st));
-    GCNN_TRY(h2d(g.cef, pin + L.off[2], sizeof(float) * hb->n_cons_edges, st));
-    GCNN_TRY(h2d(g.var, pin + L.off[3], sizeof(float) * hb->n_vars * GCNN_VAR_FEATS, st));
-    GCNN_TRY(h2d(g.cut, pin + L.off[4], sizeof(float) * hb->n_cuts * GCNN_CUT_FEATS, st));
-    GCNN_TRY(h2d(g.kei, pin + L.off[5], sizeof(int32_t) * 2 * hb->n_cut_edges, st));
-    GCNN_TRY(h2d(g.kef, pin + L.off[6], sizeof(float) * hb->n_cut_edges, st));
+    if ((int64_t)L.off[7] > g.raw_cap) { set_error("serving batch larger than the staging area"); return GCNN_INVALID; }
+    GCNN_TRY(h2d(g.raw + L.off[0], pin + L.off[0], L.off[7] - L.off[0], st));
     gcnn_batch meta = *hb;
-    meta.cons_feats = g.cons; meta.cons_edge_inds = g.cei; meta.cons_edge_feats = g.cef;
-    meta.var_feats = g.var; meta.cut_feats = g.cut; meta.cut_edge_inds = g.kei; meta.cut_edge_feats = g.kef;
+    meta.cons_feats = (const float*)(g.raw + L.off[0]);
+    meta.cons_edge_inds = (const int32_t*)(g.raw + L.off[1]);
+    meta.cons_edge_feats = (const float*)(g.raw + L.off[2]);
+    meta.var_feats = (const float*)(g.raw + L.off[3]);
+    meta.cut_feats = (const float*)(g.raw + L.off[4]);
+    meta.cut_edge_inds = (const int32_t*)(g.raw + L.off[5]);
+    meta.cut_edge_feats = (const float*)(g.raw + L.off[6]);
     meta.sample_n_cons = meta.sample_n_vars = meta.sample_n_cuts = nullptr;  // one graph per call: no block structure
     meta.n_samples = 0;
     GCNN_TRY(forward_impl(ws, params, prenorm, &meta, ws->scores, -1, st));
@@ -1820,7 +1828,15 @@ int gcnn_score_host_graph(gcnn_workspace* ws, const float* params, const float* 
                           float* scores_host, void* stream) {
     GCNN_TRY(check_batch(ws, hb, 0));
     DeviceGuard guard(ws->device);
-    cudaStream_t st = (cudaStream_t)stream;
+    if (!ws->serve_stream) {
+        GCNN_CUDA_TRY(cudaStreamCreateWithFlags(&ws->serve_stream, cudaStreamNonBlocking));
+        GCNN_CUDA_TRY(cudaEventCreateWithFlags(&ws->serve_ev, cudaEventDisableTiming));
+    }
+    // everything below runs on the workspace's serving stream, after whatever the caller's stream holds (a parameter
+    // update, say); the call ends with a host synchronisation, which orders the caller's later work after it
+    GCNN_CUDA_TRY(cudaEventRecord(ws->serve_ev, (cudaStream_t)stream));
+    cudaStream_t st = ws->serve_stream;
+    GCNN_CUDA_TRY(cudaStreamWaitEvent(st, ws->serve_ev, 0));
     const ServeLayout L = serve_layout(hb);
     if (L.total > ws->serve_pin_bytes) {  // (re)allocate the pinned mirror; captured graphs point into the old one
         GCNN_CUDA_TRY(cudaStreamSynchronize(st));
@@ -1878,6 +1894,7 @@ int gcnn_score_host_graph(gcnn_workspace* ws, const float* params, const float* 
         if (graph) cudaGraphDestroy(graph);
         if (e != cudaSuccess || rc != GCNN_OK || !slot->exec) {  // capture is not available here: stay eager from now on
             cudaGetLastError();
+            set_error("graph capture of the scoring path failed (%s, status %d): scoring eagerly", cudaGetErrorString(e), rc);
             slot->exec = nullptr;
             ws->serve_graphs_ok = 0;
             GCNN_TRY(serve_enqueue(ws, params, prenorm, hb, L, st));

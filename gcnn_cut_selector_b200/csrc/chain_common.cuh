@@ -56,8 +56,9 @@ __device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) 
 // (Tried in round 2: even / odd k-steps into two accumulators that the epilogue adds with round-to-nearest, to halve the
 // tensor core's truncating accumulations.  Scores moved from 2.6e-6 to 1.6e-6 of the fp64 oracle, the worst gradient
 // tensor did not improve and the backward chains took 9 % longer -- not kept; profiles/r2_grad_errors.md.)
-// `first`: index of the first product issued -- 0 for the fp32-accurate path (all six), 5 for the bf16 MLP mode (option
-// "precision" = 1): only the leading (0,0) product, i.e. plain bf16 operands with fp32 accumulation.
+// `first`: index of the first product issued -- 0 for the fp32-accurate path (all six); 3 for the bf16 MLP mode (option
+// "precision" = 1): (1,0) (0,1) (0,0), i.e. two-piece operands without the lo*lo term; 5 for option "precision" = 2: only
+// the leading (0,0) product, plain bf16 operands with fp32 accumulation.
 __device__ __forceinline__ void issue_dgrad(uint32_t tmem_d, uint32_t a_tile, uint32_t w_img, uint32_t acc, int first) {
     asm volatile("" : "+r"(a_tile), "+r"(w_img));
     const uint64_t da0 = make_desc(a_tile), db0 = make_desc(w_img);

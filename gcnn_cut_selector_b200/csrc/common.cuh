@@ -325,7 +325,7 @@ struct ConvFwdArgs {          // fused node chain of one convolution (tc_conv_fo
     int relu_n;
     float *C, *U1, *Y, *Pn;   // outputs; C and U1 may be nullptr (inference)
     int64_t M;
-    int bf16_mlp;             // option "precision" = 1: one bf16 product per MMA instead of six (bf16x3 chains only)
+    int bf16_mlp;             // option "precision": 1 = three bf16 products per MMA instead of six, 2 = one (bf16x3 chains only)
 };
 int tc_conv_forward(const ConvFwdArgs& a, cudaStream_t st);
 int tc_conv_forward16(const ConvFwdArgs& a, cudaStream_t st);  // bf16x3 variant (node_fwd.cu): img_* are bf16x3 T images

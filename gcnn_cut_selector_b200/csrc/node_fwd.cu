@@ -72,7 +72,7 @@ tc_conv_forward16_kernel(const ConvFwdArgs a) {
     if (warp >= CWARPS) {
         // ================= MMA / weight-copy warp =================
         regs_mma();
-        const int first_p = a.bf16_mlp ? 5 : 0;  // bf16 MLP mode: the leading product only
+        const int first_p = a.bf16_mlp == 2 ? 5 : a.bf16_mlp == 1 ? 3 : 0;  // bf16 MLP modes: the three / one leading products
         if (warp == CWARPS && elect_one()) {
             bulk_load(W0, a.img_f, W16_BYTES, wbar0);
             bulk_load(W1, a.img_o1a, W16_BYTES, wbar1);
@@ -212,7 +212,7 @@ tc_embed_forward16_kernel(const EmbFwdArgs a) {
 
     if (warp >= CWARPS) {
         regs_mma();
-        const int first_p = a.bf16_mlp ? 5 : 0;  // bf16 MLP mode: the leading product only
+        const int first_p = a.bf16_mlp == 2 ? 5 : a.bf16_mlp == 1 ? 3 : 0;  // bf16 MLP modes: the three / one leading products
         if (warp == CWARPS && elect_one()) {
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(wbar), "r"((two ? 3u : 2u) * W16_BYTES) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

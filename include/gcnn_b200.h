@@ -106,8 +106,9 @@ int64_t gcnn_workspace_bytes(const gcnn_workspace* ws);
  * GCNN_STREAMS), "blocks" (1 = use the batch's per-sample counts: shared-memory block edge kernels and per-sample
  * transposed layouts [default], 0 = generic kernels; env GCNN_BLOCKS), "precision" (0 = fp32-accurate dense layers:
  * bf16x3 operands, six tensor-core products per MMA, scores and gradients within 1e-5 of the reference [default]; 1 =
- * bf16 MLP path: one product per MMA, the dense layers see bf16 operands with fp32 accumulation, within 1e-2 -- the two
- * accuracy classes of BASELINE.json).  Takes effect from the next call. */
+ * bf16 MLP path: the three leading products (hi*hi + hi*lo + lo*hi) with fp32 accumulation, within 1e-2 -- the two
+ * accuracy classes of BASELINE.json; 2 = one product per MMA, operands rounded to bf16: measured 1.2-1.3e-2, outside
+ * both classes, a measurement point only).  Takes effect from the next call. */
 int gcnn_set_option(gcnn_workspace* ws, const char* name, int value);
 /* Synchronise `stream` and report deferred errors (GCNN_INVALID if any edge index was out of range). */
 int gcnn_check(gcnn_workspace* ws, void* stream);

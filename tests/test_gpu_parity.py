@@ -930,7 +930,8 @@ def test_graph_scoring_matches_eager_scoring(golden_dir):
     for rep in range(4):
         for h, w in zip(hbs, want):
             np.testing.assert_array_equal(m.score_host(h, graph=True), w)
-    assert m._lib.gcnn_serve_graph_count(m._ws) >= 1  # (0 would mean the capture fell back to eager launches)
+    # (0 would mean the capture fell back to eager launches; the library leaves the reason in its error string)
+    assert m._lib.gcnn_serve_graph_count(m._ws) >= 1, m._lib.gcnn_last_error().decode()
     big = HostBatch(batching.concat_samples(synth.make_samples("setcov", 2, seed0=5)))  # grows the workspace
     w_big = m.score_host(big, graph=True).copy()
     assert rel_err(w_big, m.score_host(big)) <= 2e-6
@@ -951,13 +952,18 @@ def test_graph_scoring_matches_eager_scoring(golden_dir):
 BF16_TOL = 1e-2
 
 
+BF16_SINGLE_TOL = 3e-2  # one product per MMA: measured 1.2-1.3e-2 -- outside BASELINE's 1e-2 class, tested as what it is
+
+
 @pytest.mark.parametrize("counts", [False, True], ids=["totals", "per_sample_counts"])
 @pytest.mark.parametrize("shape,n", [("setcov", 3), ("combauc", 4), ("indset", 4), ("capfac", 1), ("setcov", 32)])
-def test_bf16_mlp_mode_within_1e2(golden_dir, oracle64, shape, n, counts):
-    """option "precision" = 1: the dense layers run as plain bf16 tensor-core products with fp32 accumulation (one product
-    per MMA instead of the six of the fp32-accurate path); edge kernels, loss and Adam stay fp32.  Scores, loss and every
-    parameter gradient within 1e-2 of the fp64 oracle (relative to the tensor's max-abs / L2) on all four problem classes
-    and at BASELINE config 2's size; the mode is off by default and switches back cleanly."""
+@pytest.mark.parametrize("precision,tol", [(1, BF16_TOL), (2, BF16_SINGLE_TOL)], ids=["three_products", "one_product"])
+def test_bf16_mlp_mode_within_1e2(golden_dir, oracle64, shape, n, counts, precision, tol):
+    """option "precision" = 1: the dense layers run as bf16 tensor-core products with fp32 accumulation, three products
+    per MMA (hi*hi + hi*lo + lo*hi) instead of the six of the fp32-accurate path; edge kernels, loss and Adam stay fp32.
+    Scores, loss and every parameter gradient within 1e-2 of the fp64 oracle (relative to the tensor's max-abs / L2) on
+    all four problem classes and at BASELINE config 2's size; the mode is off by default and switches back cleanly.
+    "precision" = 2 (one product, operands rounded to bf16) is held to 3e-2: it does NOT meet the 1e-2 class."""
     from gcnn_cut_selector_b200 import GCNN
     m = GCNN(device="cuda:0", seed=0)
     m.restore_state(os.path.join(golden_dir, "state_stream.pkl"))
@@ -970,14 +976,16 @@ def test_bf16_mlp_mode_within_1e2(golden_dir, oracle64, shape, n, counts):
         loss, pred = float(l), p.numpy()
     _, s32 = m.loss_and_grads(inputs, targets)
     g32 = m.flat_grads.clone()
-    m.set_option("precision", 1)
+    err32 = rel_err(s32.cpu().numpy(), pred)
+    m.set_option("precision", precision)
     loss_sum, scores = m.loss_and_grads(inputs, targets)
     torch.cuda.synchronize()
     err = rel_err(scores.cpu().numpy(), pred)
-    assert err <= BF16_TOL
-    assert err >= 1e-5  # (it really is another numerics path, not the fp32-accurate one)
-    assert abs(float(loss_sum) / scores.numel() - loss) <= 2 * BF16_TOL * loss
-    assert_grads_close(m.flat_grads.cpu().numpy(), grads, tol=BF16_TOL)
+    print(f"precision={precision} {shape} x{n}: score error {err:.3e} (fp32-accurate path {err32:.3e})")
+    assert err <= tol
+    assert not torch.equal(scores, s32)  # (it really is another numerics path, not the fp32-accurate one)
+    assert abs(float(loss_sum) / scores.numel() - loss) <= 2 * tol * loss
+    assert_grads_close(m.flat_grads.cpu().numpy(), grads, tol=tol)
     m.set_option("precision", 0)
     _, s_back = m.loss_and_grads(inputs, targets)
     assert torch.equal(s_back, s32) and torch.equal(m.flat_grads, g32)
