@@ -80,9 +80,11 @@ SIGNATURES = {
     "gcnn_stage_host_batch": (_I, [_P, _I, _BP, _P]),
     "gcnn_record_bytes": (_I64, [_I64, _I64, _I64, _I64, _I64, _I]),
     "gcnn_stage_records": (_I, [_P, _I, _P, _I64, C.POINTER(_I64)]),
+    "gcnn_stage_resident_records": (_I, [_P, _I, _P, _P, _P, _I64, C.POINTER(_I64)]),
     "gcnn_score_staged": (_I, [_P, _I, _P, _P, _P, _P]),
     "gcnn_train_step_staged": (_I, [_P, _I, _P, _P, _P, _P, _F, _I64, C.POINTER(_F), _P]),
     "gcnn_train_step_staged_async": (_I, [_P, _I, _P, _P, _P, _P, _F, _I64, _P]),
+    "gcnn_dp_train_step_staged_async": (_I, [_P, _I, _P, _P, _P, _P, _F, _I64, _P]),
     "gcnn_train_step_result": (_I, [_P, _I, C.POINTER(_F), _P]),
     "gcnn_staged_batch": (_I, [_P, _I, _BP, C.POINTER(_P), _P]),
     "gcnn_release_staged": (_I, [_P, _I, _P]),

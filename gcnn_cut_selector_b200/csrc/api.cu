@@ -145,6 +145,7 @@ struct gcnn_workspace {
         cudaEvent_t staged = nullptr, consumed = nullptr, result = nullptr;
         int valid = 0;
         int64_t result_cuts = -1;  // cut count of the step whose result is pending (-1: none)
+        int result_global = 0;     // that step was data parallel: divide by the global cut count it read back
     } stage[2];
     char* stage_arena = nullptr;   // the staging slots' own allocation (never freed while a slot is valid)
     size_t stage_bytes = 0;
@@ -174,7 +175,7 @@ struct gcnn_workspace {
     DpState* dp = nullptr;                     // data-parallel peer-memory exchange (gcnn_dp_*)
     int device = 0;                            // CUDA device the workspace lives on
     int64_t act_stamp = 0;                     // generation of the saved activations (gcnn_activation_stamp)
-    float* h_result = nullptr;    // pinned host: per slot {loss sum, error flag word}
+    float* h_result = nullptr;    // pinned host: per slot {loss sum, error flag word, global cut count (data parallel), -}
     cudaStream_t copy_st = nullptr;
     cudaStream_t result_st = nullptr;  // device-to-host copies of a step's loss / error word, off the compute stream
     // auxiliary streams: independent kernels (CSR build, the two projections of a convolution, weight gradients) run
@@ -1199,7 +1200,7 @@ int gcnn_workspace_create(gcnn_workspace** out) {
         GCNN_CUDA_TRY(cudaEventCreateWithFlags(&ws->stage[s].consumed, cudaEventDisableTiming));
         GCNN_CUDA_TRY(cudaEventCreateWithFlags(&ws->stage[s].result, cudaEventDisableTiming));
     }
-    GCNN_CUDA_TRY(cudaHostAlloc((void**)&ws->h_result, 4 * sizeof(float), cudaHostAllocDefault));
+    GCNN_CUDA_TRY(cudaHostAlloc((void**)&ws->h_result, 8 * sizeof(float), cudaHostAllocDefault));
     for (int s = 0; s < 2; ++s) {
         GCNN_CUDA_TRY(cudaHostAlloc((void**)&ws->stage[s].descs_host, sizeof(RecordDesc) * MAX_RECORDS, cudaHostAllocDefault));
         GCNN_CUDA_TRY(cudaHostAlloc((void**)&ws->stage[s].blocks_host, sizeof(int32_t) * 3 * (MAX_RECORDS + 1), cudaHostAllocDefault));
@@ -1646,8 +1647,8 @@ int64_t gcnn_record_bytes(int64_t n_cons, int64_t n_vars, int64_t n_cuts, int64_
     return record_layout(n_cons, n_vars, n_cuts, n_cons_edges, n_cut_edges, flags, nullptr);
 }
 
-int gcnn_stage_records(gcnn_workspace* ws, int slot, const void* const* records_host, int64_t n_records,
-                       int64_t* h2d_bytes_out) {
+static int stage_records_impl(gcnn_workspace* ws, int slot, const void* const* records_host, int64_t n_records,
+                              int64_t* h2d_bytes_out, const uint8_t* resident_dev, const uint8_t* resident_host) {
     if (!ws || !ws->arena || slot < 0 || slot > 1 || (!records_host && n_records > 0)) {
         set_error("gcnn_stage_records: bad arguments or workspace not reserved");
         return GCNN_INVALID;
@@ -1662,7 +1663,7 @@ int gcnn_stage_records(gcnn_workspace* ws, int slot, const void* const* records_
     gcnn_batch meta;
     GCNN_TRY(assemble_records(records_host, n_records, g.raw, g.raw_cap, g.descs, g.descs_host, MAX_RECORDS, out,
                               ws->cap.nc, ws->cap.nv, ws->cap.nk, ws->cap.ec, ws->cap.ek, &meta, h2d_bytes_out,
-                              ws->flags + 1, cs));
+                              ws->flags + 1, cs, resident_dev, resident_host));
     {   // the records' node counts are the batch's block structure
         std::vector<int32_t> cnt[3];
         for (int t = 0; t < 3; ++t) cnt[t].resize((size_t)n_records);
@@ -1679,6 +1680,18 @@ int gcnn_stage_records(gcnn_workspace* ws, int slot, const void* const* records_
     g.meta = meta;
     g.valid = 1;
     return GCNN_OK;
+}
+
+int gcnn_stage_records(gcnn_workspace* ws, int slot, const void* const* records_host, int64_t n_records,
+                       int64_t* h2d_bytes_out) {
+    return stage_records_impl(ws, slot, records_host, n_records, h2d_bytes_out, nullptr, nullptr);
+}
+
+int gcnn_stage_resident_records(gcnn_workspace* ws, int slot, const void* shard_device, const void* shard_host,
+                                const void* const* records_host, int64_t n_records, int64_t* h2d_bytes_out) {
+    if (!shard_device || !shard_host) { set_error("gcnn_stage_resident_records: null shard"); return GCNN_INVALID; }
+    return stage_records_impl(ws, slot, records_host, n_records, h2d_bytes_out, static_cast<const uint8_t*>(shard_device),
+                              static_cast<const uint8_t*>(shard_host));
 }
 
 int gcnn_score_staged(gcnn_workspace* ws, int slot, const float* params, const float* prenorm, float* scores_host,
@@ -1721,10 +1734,45 @@ int gcnn_train_step_staged_async(gcnn_workspace* ws, int slot, float* params, co
     // gcnn_train_step_result waits for them.
     GCNN_CUDA_TRY(cudaEventRecord(g.consumed, st));
     GCNN_CUDA_TRY(cudaStreamWaitEvent(ws->result_st, g.consumed, 0));
-    GCNN_CUDA_TRY(cudaMemcpyAsync(ws->h_result + 2 * slot, loss_dev, sizeof(float), cudaMemcpyDeviceToHost, ws->result_st));
-    GCNN_CUDA_TRY(cudaMemcpyAsync(ws->h_result + 2 * slot + 1, ws->flags + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, ws->result_st));
+    GCNN_CUDA_TRY(cudaMemcpyAsync(ws->h_result + 4 * slot, loss_dev, sizeof(float), cudaMemcpyDeviceToHost, ws->result_st));
+    GCNN_CUDA_TRY(cudaMemcpyAsync(ws->h_result + 4 * slot + 1, ws->flags + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, ws->result_st));
     GCNN_CUDA_TRY(cudaEventRecord(g.result, ws->result_st));
     g.result_cuts = nk;
+    return GCNN_OK;
+}
+
+// The data-parallel twin: forward + backward of the staged batch straight into this rank's communication bucket
+// (gradients | cut count | squared error), then ONE kernel that waits for the peers' buckets, sums them in rank order and
+// applies Adam (csrc/dp.cu).  Nothing but library launches between the backward's last kernel and the update; the global
+// {cut count, squared error} pair travels to pinned host memory on the side stream like the single-GPU loss.
+int gcnn_dp_train_step_staged_async(gcnn_workspace* ws, int slot, float* params, const float* prenorm, float* adam_m,
+                                    float* adam_v, float lr, int64_t step, void* stream) {
+    if (!ws || slot < 0 || slot > 1 || !ws->stage[slot].valid) { set_error("no batch staged in this slot"); return GCNN_INVALID; }
+    if (!ws->dp) { set_error("gcnn_dp_train_step_staged_async: no data-parallel state (gcnn_dp_create / gcnn_dp_connect)"); return GCNN_INVALID; }
+    if (step < 1) { set_error("adam step counts from 1"); return GCNN_INVALID; }
+    DeviceGuard guard(ws->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    gcnn_workspace::Stage& g = ws->stage[slot];
+    GCNN_TRY(check_batch(ws, &g.meta, 1));
+    GCNN_CUDA_TRY(cudaStreamWaitEvent(st, g.staged, 0));
+    float* bucket = dp_bucket(ws->dp, dp_next_parity(ws->dp));
+    float* sums_dev = ws->loss_sum + 8 + 8 * slot;  // {global cut count, global squared error} of this step
+    const int keep = ws->count_before_loss;
+    ws->count_before_loss = 1;  // the bucket's tail: [N] = local cut count, [N + 1] = local squared error
+    const int rc = gcnn_forward_backward(ws, params, prenorm, &g.meta, g.targets, 1.f, nullptr, bucket,
+                                         bucket + GCNN_N_TRAINABLE + 1, st);
+    ws->count_before_loss = keep;
+    GCNN_TRY(rc);
+    const double lr_t = (double)lr * std::sqrt(1.0 - std::pow(0.999, (double)step)) / (1.0 - std::pow(0.9, (double)step));
+    GCNN_TRY(dp_allreduce_adam(ws->dp, params, adam_m, adam_v, (float)lr_t, 0.9f, 0.999f, 1e-7f, sums_dev, ws->flags + 1, st));
+    GCNN_CUDA_TRY(cudaEventRecord(g.consumed, st));
+    GCNN_CUDA_TRY(cudaStreamWaitEvent(ws->result_st, g.consumed, 0));
+    GCNN_CUDA_TRY(cudaMemcpyAsync(ws->h_result + 4 * slot + 2, sums_dev, sizeof(float), cudaMemcpyDeviceToHost, ws->result_st));
+    GCNN_CUDA_TRY(cudaMemcpyAsync(ws->h_result + 4 * slot, sums_dev + 1, sizeof(float), cudaMemcpyDeviceToHost, ws->result_st));
+    GCNN_CUDA_TRY(cudaMemcpyAsync(ws->h_result + 4 * slot + 1, ws->flags + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, ws->result_st));
+    GCNN_CUDA_TRY(cudaEventRecord(g.result, ws->result_st));
+    g.result_cuts = 0;
+    g.result_global = 1;
     return GCNN_OK;
 }
 
@@ -1734,10 +1782,15 @@ int gcnn_train_step_result(gcnn_workspace* ws, int slot, float* loss_host, void*
     gcnn_workspace::Stage& g = ws->stage[slot];
     GCNN_CUDA_TRY(cudaEventSynchronize(g.result));
     const int64_t nk = g.result_cuts;
+    const int global = g.result_global;
     g.result_cuts = -1;
+    g.result_global = 0;
     int32_t flag;
-    memcpy(&flag, ws->h_result + 2 * slot + 1, sizeof(flag));
-    if (loss_host) *loss_host = nk > 0 ? ws->h_result[2 * slot] / (float)nk : 0.f;
+    memcpy(&flag, ws->h_result + 4 * slot + 1, sizeof(flag));
+    if (loss_host) {
+        const float denom = global ? ws->h_result[4 * slot + 2] : (float)nk;  // data parallel: the global cut count
+        *loss_host = denom > 0.f ? ws->h_result[4 * slot] / denom : 0.f;
+    }
     if (flag) return read_error_flag(ws, (cudaStream_t)stream);  // re-reads, clears and reports the device word
     return GCNN_OK;
 }

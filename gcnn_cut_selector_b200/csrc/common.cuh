@@ -201,7 +201,8 @@ int64_t record_layout(int64_t n_cons, int64_t n_vars, int64_t n_cuts, int64_t ec
 int assemble_records(const void* const* records_host, int64_t n_records, uint8_t* raw, int64_t raw_cap,
                      RecordDesc* descs_dev, RecordDesc* descs_host, int64_t max_records, const AssembleOut& out,
                      int64_t cap_nc, int64_t cap_nv, int64_t cap_nk, int64_t cap_ec, int64_t cap_ek, gcnn_batch* meta,
-                     int64_t* h2d_bytes, int32_t* err_flag, cudaStream_t cs);
+                     int64_t* h2d_bytes, int32_t* err_flag, cudaStream_t cs, const uint8_t* resident_dev = nullptr,
+                     const uint8_t* resident_host = nullptr);
 
 // ---- edge kernels -------------------------------------------------------------------------------------------------
 struct EdgeScalars {  // device pointers to the scalars so no host sync is needed when they change (pretraining)

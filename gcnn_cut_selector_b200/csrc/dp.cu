@@ -41,8 +41,19 @@ __device__ __forceinline__ float ld_peer(const float* p) {  // peer data: never 
     return v;
 }
 
+__device__ __forceinline__ float4 ld_peer4(const float* p) {
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
 constexpr int DP_THREADS = 256;
 
+// WMAX = the world size rounded up to a power of two: the peer loads of a thread (one float4 of gradients and the cut
+// count per rank) are issued back to back from a fully unrolled loop BEFORE the first one is consumed, so a thread pays
+// one NVLink round trip, not one per rank (the first version summed inside a runtime loop: 2 x 7 dependent round trips,
+// 0.522 ms per step against NCCL's 0.466 ms on 8 GPUs).
+template <int WMAX>
 __global__ void __launch_bounds__(DP_THREADS)
 dp_allreduce_adam_kernel(DpPeers peers, uint32_t* my_words, const int world, const int rank, const uint32_t seq,
                          float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const int64_t n,
@@ -60,24 +71,41 @@ dp_allreduce_adam_kernel(DpPeers peers, uint32_t* my_words, const int world, con
         const long long t0 = clock64();
         while (ld_acquire_sys(w) != seq) {
             if (clock64() - t0 > timeout_cycles) { atomicOr(err_flag, 16); break; }
-            __nanosleep(64);
+            __nanosleep(32);
         }
     }
     __syncthreads();
     const int64_t boff = (int64_t)par * DP_BUCKET_FLOATS;
-    // global cut count and squared error: the two words behind the gradients
+    const int64_t i = ((int64_t)blockIdx.x * DP_THREADS + threadIdx.x) * 4;  // the bucket is padded: float4 loads stay inside
+    float4 x[WMAX];
+    float c[WMAX];
+#pragma unroll
+    for (int r = 0; r < WMAX; ++r) {
+        if (r < world) {
+            x[r] = ld_peer4(peers.bucket[r] + boff + (i < n ? i : 0));
+            c[r] = ld_peer(peers.bucket[r] + boff + n);  // the cut count sits behind the gradients
+        }
+    }
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
     float count = 0.f;
-    for (int r = 0; r < world; ++r) count += ld_peer(peers.bucket[r] + boff + n);
-    const int64_t i = (int64_t)blockIdx.x * DP_THREADS + threadIdx.x;
-    if (i < n) {
-        float g = 0.f;
-        for (int r = 0; r < world; ++r) g += ld_peer(peers.bucket[r] + boff + i);  // rank order: identical on every rank
-        g = g / count;
-        const float mi = m[i] + (g - m[i]) * (1.f - b1);
-        const float vi = v[i] + (g * g - v[i]) * (1.f - b2);
-        m[i] = mi;
-        v[i] = vi;
-        p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+#pragma unroll
+    for (int r = 0; r < WMAX; ++r) {  // rank order: identical sums on every rank
+        if (r < world) {
+            g.x += x[r].x; g.y += x[r].y; g.z += x[r].z; g.w += x[r].w;
+            count += c[r];
+        }
+    }
+    const float gs[4] = {g.x / count, g.y / count, g.z / count, g.w / count};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (i + k < n) {
+            const float gk = gs[k];
+            const float mi = m[i + k] + (gk - m[i + k]) * (1.f - b1);
+            const float vi = v[i + k] + (gk * gk - v[i + k]) * (1.f - b2);
+            m[i + k] = mi;
+            v[i + k] = vi;
+            p[i + k] -= lr_t * mi / (sqrtf(vi) + eps);
+        }
     }
     if (sums_out && blockIdx.x == 0 && threadIdx.x == 0) {
         float se = 0.f;
@@ -151,9 +179,16 @@ int dp_allreduce_adam(DpState* s, float* params, float* m, float* v, float lr_t,
     // ~10 s of SM clocks at the B200's 1.965 GHz boost (a fixed constant: querying the clock attribute costs a
     // millisecond of host time per call)
     const long long timeout = 10LL * 1965000000LL;
-    GCNN_LAUNCH(dp_allreduce_adam_kernel, (unsigned)ceil_div(n, DP_THREADS), DP_THREADS, 0, st, s->peers,
-                (uint32_t*)((char*)s->block + sizeof(float) * 2 * DP_BUCKET_FLOATS), s->world, s->rank, s->seq, params, m, v,
-                n, lr_t, beta1, beta2, eps, sums_out, err_flag, timeout);
+    uint32_t* words = (uint32_t*)((char*)s->block + sizeof(float) * 2 * DP_BUCKET_FLOATS);
+    const unsigned grid = (unsigned)ceil_div(ceil_div(n, (int64_t)4), (int64_t)DP_THREADS);
+#define GCNN_DP_LAUNCH(W_)                                                                                                 \
+    GCNN_LAUNCH(dp_allreduce_adam_kernel<W_>, grid, DP_THREADS, 0, st, s->peers, words, s->world, s->rank, s->seq, params, \
+                m, v, n, lr_t, beta1, beta2, eps, sums_out, err_flag, timeout)
+    if (s->world <= 2) GCNN_DP_LAUNCH(2);
+    else if (s->world <= 4) GCNN_DP_LAUNCH(4);
+    else if (s->world <= 8) GCNN_DP_LAUNCH(8);
+    else GCNN_DP_LAUNCH(16);
+#undef GCNN_DP_LAUNCH
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
 }

@@ -124,12 +124,14 @@ int64_t record_layout(int64_t n_cons, int64_t n_vars, int64_t n_cuts, int64_t ec
 }
 
 // Reads k record headers (host memory), lays the batch out, copies records + descriptors and launches the kernel on
-// `cs`.  raw / descs_dev / descs_host are the slot's staging areas; totals come back through `meta` (device pointers are
+// `cs`.  With `resident_dev` (the device copy of the shard whose host copy starts at `resident_host`) the records are
+// not copied: the kernel assembles the batch straight from the shard in HBM and only the descriptors cross PCIe.  raw / descs_dev / descs_host are the slot's staging areas; totals come back through `meta` (device pointers are
 // filled in by the caller).
 int assemble_records(const void* const* records_host, int64_t n_records, uint8_t* raw, int64_t raw_cap,
                      RecordDesc* descs_dev, RecordDesc* descs_host, int64_t max_records, const AssembleOut& out_in,
                      int64_t cap_nc, int64_t cap_nv, int64_t cap_nk, int64_t cap_ec, int64_t cap_ek, gcnn_batch* meta,
-                     int64_t* h2d_bytes, int32_t* err_flag, cudaStream_t cs) {
+                     int64_t* h2d_bytes, int32_t* err_flag, cudaStream_t cs, const uint8_t* resident_dev,
+                     const uint8_t* resident_host) {
     if (n_records < 0 || n_records > max_records) { set_error("too many records for one batch (%lld > %lld)", (long long)n_records, (long long)max_records); return GCNN_INVALID; }
     int64_t nc = 0, nv = 0, nk = 0, ec = 0, ek = 0, raw_off = 0;
     int all_flags = GCNN_RECORD_CONS_ROWS_AS_PTR | GCNN_RECORD_CUT_ROWS_AS_PTR | GCNN_RECORD_CONS_ROWS_SORTED | GCNN_RECORD_CUT_ROWS_SORTED;
@@ -144,8 +146,11 @@ int assemble_records(const void* const* records_host, int64_t n_records, uint8_t
         int64_t declared;
         memcpy(&declared, h + 8, sizeof(declared));
         if (declared != bytes) { set_error("record %lld: header says %lld bytes, layout needs %lld", (long long)r, (long long)declared, (long long)bytes); return GCNN_INVALID; }
-        if (raw_off + bytes > raw_cap) { set_error("records do not fit the staging area: reserve a larger workspace"); return GCNN_INVALID; }
-        for (int s = 0; s < REC_SECTIONS; ++s) d.sec[s] = raw_off + sec[s];
+        // resident shard: the kernel reads the record where it lies in the shard's device copy; nothing but descriptors travels
+        const int64_t base = resident_dev ? static_cast<const uint8_t*>(records_host[r]) - resident_host : raw_off;
+        if (resident_dev && (base & 15)) { set_error("record %lld: not 16-byte aligned in the resident shard", (long long)r); return GCNN_INVALID; }
+        if (!resident_dev && raw_off + bytes > raw_cap) { set_error("records do not fit the staging area: reserve a larger workspace"); return GCNN_INVALID; }
+        for (int s = 0; s < REC_SECTIONS; ++s) d.sec[s] = base + sec[s];
         d.cons_off = nc; d.var_off = nv; d.cut_off = nk; d.ec_off = ec; d.ek_off = ek;
         nc += d.n_cons; nv += d.n_vars; nk += d.n_cuts; ec += d.ec; ek += d.ek;
         raw_off += bytes;
@@ -157,7 +162,7 @@ int assemble_records(const void* const* records_host, int64_t n_records, uint8_t
     }
     // host-to-device: records that are neighbours in host memory travel in one copy
     int64_t run_begin = 0;
-    for (int64_t r = 0; r < n_records; ++r) {
+    for (int64_t r = 0; r < n_records && !resident_dev; ++r) {
         const int64_t bytes = (r + 1 < n_records ? descs_host[r + 1].sec[0] : raw_off + GCNN_RECORD_HEADER_BYTES) - descs_host[r].sec[0];
         const bool last = r + 1 == n_records;
         const bool contiguous = !last && static_cast<const uint8_t*>(records_host[r + 1]) == static_cast<const uint8_t*>(records_host[r]) + bytes;
@@ -172,7 +177,8 @@ int assemble_records(const void* const* records_host, int64_t n_records, uint8_t
         GCNN_CUDA_TRY(cudaMemcpyAsync(descs_dev, descs_host, sizeof(RecordDesc) * (size_t)n_records, cudaMemcpyHostToDevice, cs));
         AssembleOut out = out_in;
         out.ec_total = ec; out.ek_total = ek;
-        GCNN_LAUNCH_ORDERED(assemble_records_kernel, dim3((unsigned)n_records, REC_SECTIONS, REC_SLICES), REC_THREADS, 0, cs, raw, descs_dev, out, err_flag);
+        GCNN_LAUNCH_ORDERED(assemble_records_kernel, dim3((unsigned)n_records, REC_SECTIONS, REC_SLICES), REC_THREADS, 0, cs,
+                            resident_dev ? resident_dev : raw, descs_dev, out, err_flag);
         GCNN_LAUNCH_CHECK();
     }
     *meta = gcnn_batch{};
@@ -182,7 +188,7 @@ int assemble_records(const void* const* records_host, int64_t n_records, uint8_t
         if (all_flags & GCNN_RECORD_CONS_ROWS_SORTED) meta->flags |= GCNN_BATCH_CONS_EDGES_SORTED;
         if (all_flags & GCNN_RECORD_CUT_ROWS_SORTED) meta->flags |= GCNN_BATCH_CUT_EDGES_SORTED;
     }
-    if (h2d_bytes) *h2d_bytes = raw_off + (int64_t)sizeof(RecordDesc) * n_records;
+    if (h2d_bytes) *h2d_bytes = (resident_dev ? 0 : raw_off) + (int64_t)sizeof(RecordDesc) * n_records;
     return GCNN_OK;
 }
 

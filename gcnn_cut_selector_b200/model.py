@@ -404,13 +404,19 @@ class GCNN:
     def stage_records(self, reader, ids, slot: int, training: bool = True) -> "StagedRecords":
         """Stage the batch made of records ``ids`` of a ``shards.ShardReader`` in slot 0/1: the packed records are copied
         to the device as they are and one kernel assembles the batch there (the device-side ``utils.load_batch``,
-        utils.py:339-426).  Returns immediately; use the slot like one filled by ``stage_host``."""
+        utils.py:339-426).  If the reader's shard is resident on this model's device (``ShardReader.to_device``) no
+        record bytes are copied at all.  Returns immediately; use the slot like one filled by ``stage_host``."""
         nc, nv, nk, ec, ek = reader.totals(ids)
         ptrs = reader.pointers(ids)
         h2d = C.c_int64()
+        resident = reader.device_buffer(self.device)  # set by ShardReader.to_device: the shard lives in HBM
         with torch.cuda.device(self.device):
             check(self._lib.gcnn_workspace_reserve(self._ws, nc, nv, nk, ec, ek, int(training)))
-            check(self._lib.gcnn_stage_records(self._ws, slot, ptrs.ctypes.data, ptrs.shape[0], C.byref(h2d)))
+            if resident is not None:
+                check(self._lib.gcnn_stage_resident_records(self._ws, slot, resident.data_ptr(), reader.host_base,
+                                                            ptrs.ctypes.data, ptrs.shape[0], C.byref(h2d)))
+            else:
+                check(self._lib.gcnn_stage_records(self._ws, slot, ptrs.ctypes.data, ptrs.shape[0], C.byref(h2d)))
         staged = StagedRecords(reader, nk, int(ptrs.shape[0]), int(h2d.value))
         self._staged[slot] = staged  # keeps the pinned shard alive until the slot is consumed
         return staged

@@ -25,6 +25,40 @@ def reduce_bucket(bucket: torch.Tensor, group=None) -> torch.Tensor:
     return bucket
 
 
+def bind_host_to_device(device) -> dict | None:
+    """Restrict this process to the CPUs of the NUMA node the GPU ``device`` is attached to, so that the pinned staging
+    buffers it allocates afterwards (first touch) and the threads that fill them sit next to the GPU's PCIe root port.
+    With eight ranks streaming ~28 GB/s each, buffers on the far socket turn the inter-socket link into the bottleneck.
+    Returns {"numa_node", "cpus"} or None when the topology is not exposed (containers without sysfs PCI entries)."""
+    import os
+    try:
+        p = torch.cuda.get_device_properties(device)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            cpus = parse_cpulist(fh.read())
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus)}
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return None
+
+
+def parse_cpulist(text: str) -> set:
+    """sysfs cpulist syntax ("0-3,8,10-11") -> set of CPU numbers."""
+    cpus = set()
+    for part in text.strip().split(","):
+        if part:
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
 def ordered_bucket_sum(buckets):
     """CPU emulation of the peer-memory exchange's reduction: the ranks' buckets are added element-wise IN RANK ORDER,
     in fp32 (csrc/dp.cu) -- every rank forms the same bits.  ``buckets``: list of 1-D float32 arrays / tensors."""
@@ -81,6 +115,7 @@ class DataParallelTrainer:
             model.set_option("count_before_loss", 1)
         # peer-memory exchange fused with Adam: default on for NCCL groups (one box); GCNN_DP_PEER=0 keeps NCCL
         self.peer = False
+        self._pending_loss = {}
         self._peer_buckets = None
         self._sums = None
         world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
@@ -180,6 +215,27 @@ class DataParallelTrainer:
             self.bucket[self.N] = float(scores.numel())
             self.bucket[self.N + 1:self.N + 2].copy_(loss_sum)
         return self._finish(want_loss)
+
+    def step_staged_async(self, slot: int):
+        """Enqueue one data-parallel step on the batch staged in ``slot`` with ONE library call (backward into the
+        communication bucket, peer all-reduce + Adam); the global mean loss is read later with ``step_result(slot)``.
+        Needs the peer exchange (NCCL ranks of one box); falls back to ``step_staged`` otherwise."""
+        m = self.model
+        if not self.peer:
+            self._pending_loss[slot] = self.step_staged(slot).clone()
+            return
+        with torch.cuda.device(m.device):
+            _lib.check(m._lib.gcnn_dp_train_step_staged_async(m._ws, slot, m.flat_params.data_ptr(),
+                                                              m.flat_prenorm.data_ptr(), m.adam_m.data_ptr(),
+                                                              m.adam_v.data_ptr(), self.lr, m.adam_step + 1, m._stream()))
+        m.adam_step += 1
+        self._use_bucket(int(m._lib.gcnn_dp_next_parity(m._ws)))
+
+    def step_result(self, slot: int) -> float:
+        """Global mean loss of the step enqueued on ``slot`` by ``step_staged_async`` (waits for that step only)."""
+        if not self.peer:
+            return float(self._pending_loss.pop(slot).item())
+        return self.model.train_step_result(slot)
 
     def step_staged(self, slot: int):
         """``step`` on the host batch staged in ``slot`` (GCNN.stage_host): its copy overlapped the previous step."""

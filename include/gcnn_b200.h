@@ -242,6 +242,12 @@ int gcnn_train_step_staged(gcnn_workspace* ws, int slot, float* params, const fl
 int gcnn_train_step_staged_async(gcnn_workspace* ws, int slot, float* params, const float* prenorm, float* adam_m,
                                  float* adam_v, float lr, int64_t step, void* stream);
 int gcnn_train_step_result(gcnn_workspace* ws, int slot, float* loss_host, void* stream);
+/* Data-parallel twin of gcnn_train_step_staged_async (needs gcnn_dp_create + gcnn_dp_connect): the backward writes this
+ * rank's gradients, cut count and squared error into its communication bucket and one kernel forms the rank-ordered sums
+ * over all ranks' buckets and applies Adam -- no host round trip and no foreign launch between them.
+ * gcnn_train_step_result then returns the GLOBAL mean loss (identical on every rank). */
+int gcnn_dp_train_step_staged_async(gcnn_workspace* ws, int slot, float* params, const float* prenorm, float* adam_m,
+                                    float* adam_v, float lr, int64_t step, void* stream);
 int gcnn_staged_batch(gcnn_workspace* ws, int slot, gcnn_batch* out, float** targets_dev, void* stream);
 int gcnn_release_staged(gcnn_workspace* ws, int slot, void* stream);
 
@@ -278,6 +284,12 @@ int64_t gcnn_record_bytes(int64_t n_cons, int64_t n_vars, int64_t n_cuts, int64_
  * workspace must have been reserved for the batch totals.  h2d_bytes_out (optional) receives the bytes copied. */
 int gcnn_stage_records(gcnn_workspace* ws, int slot, const void* const* records_host, int64_t n_records,
                        int64_t* h2d_bytes_out);
+/* The same for a shard that is RESIDENT in device memory (model_trainer.py:147-153 reads the sample files again every
+ * epoch; a rank's share of the training set fits in HBM many times over): shard_device is the device copy of the bytes
+ * that start at shard_host, records_host still points at the records' host copies (their headers are read there).  No
+ * record bytes cross PCIe -- the assembly kernel reads them where they lie; only the descriptors travel (h2d_bytes_out). */
+int gcnn_stage_resident_records(gcnn_workspace* ws, int slot, const void* shard_device, const void* shard_host,
+                                const void* const* records_host, int64_t n_records, int64_t* h2d_bytes_out);
 
 /* ---- per-op entry points (unit parity tests; same kernels the whole-model calls launch) ---------------------- */
 /* H[t] = sum_{e in seg(t)} relu(s_f * (R[t] + f_e * w + S[src_e])), cnt[t] = number of active terms per feature.

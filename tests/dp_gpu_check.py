@@ -6,7 +6,8 @@ Every rank trains three steps on its own shard (different numbers of graphs / cu
 peer-memory exchange (csrc/dp.cu) and once with NCCL all_reduce + Adam.  Checks: (1) all ranks hold bit-identical
 parameters after the peer path; (2) the peer path's parameters equal the fixed-rank-order emulation applied to the gathered
 buckets (bit-exact); (3) peer and NCCL paths agree to fp32 rounding; (4) the reported global mean loss is the mean over
-all cuts of all ranks.  Prints one JSON line on rank 0.  Test infrastructure (not collected by pytest: needs torchrun)."""
+all cuts of all ranks; (5) the one-call staged path (gcnn_dp_train_step_staged_async) reports the same losses
+to fp32 rounding.  Prints one JSON line on rank 0.  Test infrastructure (not collected by pytest: needs torchrun)."""
 import json
 import os
 import sys
@@ -40,8 +41,31 @@ def main():
         torch.cuda.synchronize()
         return m, t, losses
 
+    def run_staged():  # the one-call-per-step path: host batches staged in alternating slots, loss read one step later
+        from gcnn_cut_selector_b200 import HostBatch
+        m = GCNN(device=dev, seed=0)
+        m.restore_state(state)
+        t = DataParallelTrainer(m, lr=1e-3, peer_exchange=True)
+        hosts = [HostBatch(b) for b in steps]
+        losses = []
+        m.stage_host(hosts[0], 0)
+        for i in range(len(steps)):
+            if i + 1 < len(steps):
+                m.stage_host(hosts[i + 1], (i + 1) & 1)
+            t.step_staged_async(i & 1)
+            if i > 0:
+                losses.append(t.step_result((i - 1) & 1))
+        losses.append(t.step_result((len(steps) - 1) & 1))
+        torch.cuda.synchronize()
+        return m, t, losses
+
     m_peer, t_peer, loss_peer = run(True)
     m_nccl, t_nccl, loss_nccl = run(False)
+    m_stg, t_stg, loss_stg = run_staged()
+    # (the staged host batch carries its sortedness hints, so its layouts come from the per-block transpose instead of the
+    # radix sort: another summation order in the backward pass, losses equal to fp32 rounding rather than bit for bit)
+    staged_same = all(abs(a - c) <= 5e-5 * abs(c) for a, c in zip(loss_stg, loss_peer))
+    staged_param_diff = float((m_stg.flat_params.detach() - m_peer.flat_params.detach()).abs().mean())
     ok_peer = bool(t_peer.peer)
     p = m_peer.flat_params.detach().clone()
     gathered = [torch.empty_like(p) for _ in range(world)]
@@ -73,9 +97,10 @@ def main():
     emu_exact = bool(np.array_equal(got, want))
     if rank == 0:
         print(json.dumps({"world": world, "peer_exchange_active": ok_peer, "ranks_bit_identical": identical,
-                          "peer_vs_nccl_max_abs": diff, "loss_peer": loss_peer, "loss_nccl": loss_nccl,
+                          "peer_vs_nccl_max_abs": diff, "loss_peer": loss_peer, "loss_nccl": loss_nccl, "loss_staged_async": loss_stg,
+                          "staged_async_matches_step": staged_same, "staged_mean_abs_param_diff": staged_param_diff,
                           "emulation_bit_exact": emu_exact, "emulation_max_abs": emu_max}), flush=True)
-    assert ok_peer and identical and diff < 1e-6 and emu_max < 1e-7
+    assert ok_peer and identical and diff < 1e-6 and emu_max < 1e-7 and staged_same
     assert all(abs(a - c) <= 1e-5 * abs(c) for a, c in zip(loss_peer, loss_nccl))
     dist.destroy_process_group()
 

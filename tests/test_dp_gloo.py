@@ -155,3 +155,11 @@ def test_dp_prenorm_statistics_equal_the_single_process_merge(tmp_path):
     allx = np.concatenate([x for rank in range(2) for x in _rank_batches(rank)])
     assert np.abs(s0[:4] - allx.mean(0)).max() <= 1e-5 and np.abs(s0[4:8] - allx.var(0)).max() <= 1e-4
     assert s0[8] == allx.shape[0]
+
+
+def test_cpulist_parsing_and_binding_without_topology():
+    from gcnn_cut_selector_b200.trainer import bind_host_to_device, parse_cpulist
+    assert parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert parse_cpulist("") == set()
+    if not torch.cuda.is_available():
+        assert bind_host_to_device(0) is None  # no driver, no sysfs entry: the process is left alone

@@ -181,8 +181,12 @@ def test_device_assembly_matches_reference_load_batch(golden_dir, tmp_path):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("resident", [False, True], ids=["host_shard", "resident_shard"])
 @pytest.mark.parametrize("compress", [True, False])
-def test_device_assembly_ragged_shuffled_and_subsets(tmp_path, compress):
+def test_device_assembly_ragged_shuffled_and_subsets(tmp_path, compress, resident):
+    """Batches assembled on the device from packed records equal utils.load_batch's concatenation bit for bit; with the
+    shard resident in device memory (``to_device``) the same kernel reads the records in place and only descriptors
+    cross PCIe."""
     from gcnn_cut_selector_b200 import GCNN
     model = GCNN(device=torch.device("cuda:0"), seed=0)
     base = synth.make_samples("setcov", 3, seed0=21) + synth.make_samples("combauc", 2, seed0=4) + \
@@ -190,6 +194,8 @@ def test_device_assembly_ragged_shuffled_and_subsets(tmp_path, compress):
     base[1] = synth.shuffle_edges(base[1], 3)
     base[3] = _edgeless(base[3])
     reader = _write_shard(tmp_path, base, compress_rows=compress)
+    if resident:
+        reader.to_device("cuda:0")
     for slot, ids in ((0, [0, 1, 2, 3, 4, 5]), (1, [4, 0, 5]), (0, [2]), (1, [3, 3])):
         staged = model.stage_records(reader, ids, slot=slot)
         got, flags = _staged_tensors(model, slot)
@@ -200,7 +206,10 @@ def test_device_assembly_ragged_shuffled_and_subsets(tmp_path, compress):
             np.testing.assert_array_equal(got[i], host[i])
         np.testing.assert_array_equal(got[7], host[10])
         assert flags == (0 if 1 in ids else 3)
-        assert staged.h2d_bytes >= reader.record_bytes(ids)
+        if resident:
+            assert 0 < staged.h2d_bytes <= 256 * len(ids)  # descriptors only
+        else:
+            assert staged.h2d_bytes >= reader.record_bytes(ids)
     if compress:  # the row pointer takes a third off the edge bytes of sorted lists
         plain = _write_shard(tmp_path, base, name="plain.shard", compress_rows=False)
         assert reader.record_bytes([0]) < 0.75 * plain.record_bytes([0])
@@ -212,7 +221,9 @@ def test_steps_from_records_equal_steps_from_host_batches(tmp_path):
     samples = synth.make_samples("setcov", 4, seed0=77)
     reader = _write_shard(tmp_path, samples)
     losses = []
-    for use_records in (False, True):
+    for use_records in (False, True, "resident"):
+        if use_records == "resident":
+            reader.to_device("cuda:0")
         model = GCNN(device=torch.device("cuda:0"), seed=5)
         out = []
         for step, ids in enumerate(([0, 1], [2, 3], [1, 3])):
@@ -228,8 +239,9 @@ def test_steps_from_records_equal_steps_from_host_batches(tmp_path):
             model.stage_host(HostBatch(batching.concat_samples([samples[0], samples[2]])), 1, training=False)
         out.append(model.score_staged(1).copy())
         losses.append(out)
-    assert losses[0][:3] == losses[1][:3]  # same tensors in, same kernels: bit-identical losses
-    np.testing.assert_array_equal(losses[0][3], losses[1][3])
+    for other in losses[1:]:
+        assert losses[0][:3] == other[:3]  # same tensors in, same kernels: bit-identical losses
+        np.testing.assert_array_equal(losses[0][3], other[3])
 
 
 @pytest.mark.gpu
