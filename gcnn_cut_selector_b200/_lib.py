@@ -5,7 +5,11 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("GCNN_LIB") or os.path.join(HERE, "libgcnn_b200.so")  # GCNN_LIB: an instrumented build (scripts/)
+# GCNN_LIB: an instrumented build (scripts/); GCNN_LIB_VARIANT=alt: build/alt/libgcnn_b200.so, the -DGCNN_ALT_PATHS build
+# with the round-1 A/B alternates (python -m gcnn_cut_selector_b200.build -DGCNN_ALT_PATHS --variant=alt)
+_VARIANT = os.environ.get("GCNN_LIB_VARIANT")
+LIB_PATH = os.environ.get("GCNN_LIB") or (os.path.join(HERE, "build", _VARIANT, "libgcnn_b200.so") if _VARIANT else
+                                         os.path.join(HERE, "libgcnn_b200.so"))
 
 OK, INVALID, CUDA_ERROR, OOM = 0, 1, 2, 3
 N_TRAINABLE, N_PRENORM, N_ARRAYS, N_PRENORM_LAYERS = 93121, 58, 62, 11
@@ -91,6 +95,7 @@ SIGNATURES = {
     "gcnn_edge_forward": (_I, [_P, _P, _P, _I64, _P, _P, _P, _F, _F, _F, _P, _P, _P]),
     "gcnn_edge_backward": (_I, [_P, _P, _P, _P, _I64, _P, _P, _P, _P, _F, _F, _F, _P, _P, _P]),
     "gcnn_linear_forward": (_I, [_P, _P, _P, _I64, _I, _I, _P, _P]),
+    "gcnn_has_alt_paths": (_I, []),
 }
 
 _lib = None

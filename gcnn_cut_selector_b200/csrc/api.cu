@@ -433,6 +433,21 @@ static int edge_forward_dispatch(gcnn_workspace* ws, int conv, const EdgeLayout&
     return edge_forward(L, n_recv, R, S, w_edge, sc, H, cnt, st, prof_bytes, n_edges, masks);
 }
 
+// The product build carries ONE dense path: the fused tcgen05 chains on bf16x3 tiles (node_fwd.cu / node_bwd.cu).  The A/B
+// alternates of round 1 -- fp32 SIMT dense kernels, one-launch-per-layer 3xTF32 tensor-core kernels, 3xTF32 forward
+// chains -- are compiled only with -DGCNN_ALT_PATHS (python -m gcnn_cut_selector_b200.build -DGCNN_ALT_PATHS
+// --variant=alt; tests pick that library up with GCNN_LIB_VARIANT=alt).
+#ifdef GCNN_ALT_PATHS
+constexpr bool kAltPaths = true;
+#else
+constexpr bool kAltPaths = false;
+static int no_alt_paths() {
+    set_error("this build has only the fused bf16x3 chain path: rebuild with -DGCNN_ALT_PATHS for the A/B alternates");
+    return GCNN_INVALID;
+}
+#endif
+
+#ifdef GCNN_ALT_PATHS
 // ---- dense-layer dispatch: tcgen05 3xTF32 tensor-core kernel (default) or the fp32 SIMT kernel (GCNN_TC=0) ---------
 static int dense_forward(gcnn_workspace* ws, const float* params, const LinFwdArgs& a, cudaStream_t st) {
     if (!ws->use_tc) return linear_forward(a, st);
@@ -466,6 +481,8 @@ static int dense_wgrad(gcnn_workspace* ws, const LinWgradArgs& a, cudaStream_t s
     TcWgradArgs t{a.X, a.X2, a.x_scale, a.dY, a.act, a.deg_ptr, a.K, a.M, a.partials, a.n_parts};
     return tc_wgrad(t, st);
 }
+
+#endif  // GCNN_ALT_PATHS
 
 // ---- convolutions + head with the fused tensor-core node chain (tc_conv_forward) ------------------------------------
 // Launch plan: the projections that do not depend on a previous convolution (A0 on the main stream; B0, B1 and A2 on
@@ -619,14 +636,21 @@ static int forward_impl(gcnn_workspace* ws, const float* p, const float* pn, con
             GCNN_TRY(bf16 ? tc_embed_forward16(f, se) : tc_embed_forward(f, se));
             continue;
         }
+#ifdef GCNN_ALT_PATHS
         GCNN_TRY(embed1_forward(e.x, e.K, pn + e.shift, pn + e.scale, p + e.o->W1, p + e.o->b1, e.h1, e.n, se));
         LinFwdArgs a{e.h1, nullptr, nullptr, p + e.o->W2, p + e.o->b2, nullptr, e.out, e.n, 64, 1};
         GCNN_TRY(dense_forward(ws, p, a, se));
+#else
+        return no_alt_paths();
+#endif
     }
     GCNN_TRY(stream_edge(ws, s2, st));  // v0 ready
     if (s1 != st) GCNN_CUDA_TRY(cudaEventRecord(ws->ev_layout[3], s1));  // everything on s1, incl. cut by-var
 
     if (ws->use_tc && ws->use_fused) return forward_convs_fused(ws, p, pn, b, scores_out, stop_layer, st, s1, s2);
+#ifndef GCNN_ALT_PATHS
+    return no_alt_paths();
+#else
 
     // convolutions (model.py:294-296): {left feats, var feats, receiving side, graph, edge pre-norm}
     const float* left_in[3] = {ws->c0, ws->conv[0].Y, ws->k0};
@@ -676,6 +700,7 @@ static int forward_impl(gcnn_workspace* ws, const float* p, const float* pn, con
     GCNN_TRY(dense_forward(ws, p, h1, st));
     GCNN_TRY(head2_forward(ws->g1, p + P.Wh2, p + P.bh2, scores_out ? scores_out : ws->scores, nk, st));
     return GCNN_OK;
+#endif  // GCNN_ALT_PATHS
 }
 
 // ---- backward ----------------------------------------------------------------------------------------------------
@@ -685,6 +710,9 @@ static int backward_impl_fused(gcnn_workspace* ws, const float* p, const float* 
 static int backward_impl(gcnn_workspace* ws, const float* p, const float* pn, const gcnn_batch* b,
                          const float* d_scores, float* grads, cudaStream_t st) {
     if (ws->use_tc && ws->use_fused && ws->use_fused_bwd) return backward_impl_fused(ws, p, pn, b, d_scores, grads, st);
+#ifndef GCNN_ALT_PATHS
+    return no_alt_paths();
+#else
     const int64_t nc = b->n_cons, nv = b->n_vars, nk = b->n_cuts;
     std::vector<ReduceJob> jobs;
     int slot = 0;
@@ -827,6 +855,7 @@ static int backward_impl(gcnn_workspace* ws, const float* p, const float* pn, co
     }
     GCNN_TRY(stream_edge(ws, s2, st));
     return reduce_partials(jobs.data(), (int)jobs.size(), grads, st);
+#endif  // GCNN_ALT_PATHS
 }
 
 // ---- backward with one fused tensor-core chain per convolution (node_bwd.cu) ----------------------------------------
@@ -1175,21 +1204,23 @@ int gcnn_workspace_create(gcnn_workspace** out) {
     if (!out) { set_error("null out pointer"); return GCNN_INVALID; }
     gcnn_workspace* ws = new (std::nothrow) gcnn_workspace();
     if (!ws) { set_error("host allocation failed"); return GCNN_OOM; }
-    const char* tc = getenv("GCNN_TC");  // GCNN_TC=0 selects the exact-fp32 SIMT dense kernels
-    ws->use_tc = !(tc && tc[0] == '0');
+    if (kAltPaths) {
+        const char* tc = getenv("GCNN_TC");  // GCNN_TC=0 selects the exact-fp32 SIMT dense kernels
+        ws->use_tc = !(tc && tc[0] == '0');
+        const char* fu = getenv("GCNN_FUSED");  // GCNN_FUSED=0: one launch per dense layer
+        ws->use_fused = !(fu && fu[0] == '0');
+        const char* bf = getenv("GCNN_BF16_FWD");  // GCNN_BF16_FWD=0: 3xTF32 forward chains
+        ws->use_bf16_fwd = !(bf && bf[0] == '0');
+        const char* fb = getenv("GCNN_FUSED_BWD");  // GCNN_FUSED_BWD=0: stand-alone dgrad / wgrad launches in the backward
+        ws->use_fused_bwd = !(fb && fb[0] == '0');
+    }
     const char* ms = getenv("GCNN_STREAMS");  // GCNN_STREAMS=0 serialises everything on the caller's stream
     ws->use_streams = !(ms && ms[0] == '0');
     const char* bl = getenv("GCNN_BLOCKS");  // GCNN_BLOCKS=0: ignore per-sample counts (generic edge kernels, radix sort)
     ws->use_blocks = !(bl && bl[0] == '0');
     GCNN_CUDA_TRY(cudaGetDevice(&ws->device));
-    const char* fu = getenv("GCNN_FUSED");  // GCNN_FUSED=0: one launch per dense layer
-    ws->use_fused = !(fu && fu[0] == '0');
-    const char* bf = getenv("GCNN_BF16_FWD");  // GCNN_BF16_FWD=0: 3xTF32 forward chains
-    ws->use_bf16_fwd = !(bf && bf[0] == '0');
     const char* em = getenv("GCNN_EDGE_MASKS");  // GCNN_EDGE_MASKS=0: the edge backward re-evaluates the ReLU masks
     ws->use_edge_masks = !(em && em[0] == '0');
-    const char* fb = getenv("GCNN_FUSED_BWD");  // GCNN_FUSED_BWD=0: stand-alone dgrad / wgrad launches in the backward
-    ws->use_fused_bwd = !(fb && fb[0] == '0');
     for (int i = 0; i < 3; ++i) GCNN_CUDA_TRY(cudaStreamCreateWithFlags(&ws->aux[i], cudaStreamNonBlocking));
     for (int i = 0; i < 16; ++i) GCNN_CUDA_TRY(cudaEventCreateWithFlags(&ws->ev[i], cudaEventDisableTiming));
     for (int i = 0; i < 4; ++i) GCNN_CUDA_TRY(cudaEventCreateWithFlags(&ws->ev_layout[i], cudaEventDisableTiming));
@@ -1302,6 +1333,13 @@ int gcnn_workspace_reserve(gcnn_workspace* ws, int64_t nc, int64_t nv, int64_t n
 
 int gcnn_set_option(gcnn_workspace* ws, const char* name, int value) {
     if (!ws || !name) { set_error("null argument"); return GCNN_INVALID; }
+    const bool alt_option = !strcmp(name, "tensor_cores") || !strcmp(name, "fused") || !strcmp(name, "fused_backward") ||
+                            !strcmp(name, "bf16_forward");
+    if (alt_option && !kAltPaths) {  // the product build: these are fixed at 1
+        if (value != 0) return GCNN_OK;
+        set_error("option \"%s\" = 0 selects an A/B alternate that this build does not carry (-DGCNN_ALT_PATHS)", name);
+        return GCNN_INVALID;
+    }
     if (!strcmp(name, "tensor_cores")) ws->use_tc = value != 0;
     else if (!strcmp(name, "streams")) ws->use_streams = value != 0;
     else if (!strcmp(name, "fused")) ws->use_fused = value != 0;
@@ -2034,9 +2072,16 @@ int gcnn_edge_backward(gcnn_workspace* ws, const int32_t* ptr, const int32_t* ot
 
 int gcnn_linear_forward(const float* X, const float* W, const float* b, int64_t m, int k, int relu, float* Y,
                         void* stream) {
+#ifdef GCNN_ALT_PATHS
     if (k != 64) { set_error("gcnn_linear_forward: only k = 64 is exposed (k = 128 is the fused concat layer)"); return GCNN_INVALID; }
     LinFwdArgs a{X, nullptr, nullptr, W, b, nullptr, Y, m, k, relu};
     return linear_forward(a, (cudaStream_t)stream);
+#else
+    (void)X; (void)W; (void)b; (void)m; (void)k; (void)relu; (void)Y; (void)stream;
+    return no_alt_paths();  // the fp32 SIMT dense kernel is an A/B alternate
+#endif
 }
+
+int gcnn_has_alt_paths(void) { return kAltPaths ? 1 : 0; }
 
 }  // extern "C"

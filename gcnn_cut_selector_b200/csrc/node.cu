@@ -18,6 +18,12 @@ constexpr int LIN_ROWS = 128;
 __device__ __forceinline__ float4 ld4s(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4s(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
+constexpr int WG_MAX_PARTS = NUM_SMS;
+int wgrad_max_parts() { return WG_MAX_PARTS; }
+
+// The SIMT dense kernels and the stand-alone first embedding layer are A/B alternates of the fused tcgen05 chains
+// (node_fwd.cu / node_bwd.cu): compiled only with -DGCNN_ALT_PATHS.
+#ifdef GCNN_ALT_PATHS
 // acc[i][j] += sum_k Xs[row_i][k] * Ws[k][col_j]   (Xs row stride K+4 floats, Ws row stride 64)
 template <int K>
 __device__ __forceinline__ void tile_mma(const float* __restrict__ Xs, const float* __restrict__ Ws, int ty, int tx,
@@ -195,8 +201,6 @@ int linear_dgrad(const LinDgradArgs& a, cudaStream_t st) {
 // ---- wgrad: dW[k, c] = sum_m Xcat[m, k] * dYp[m, c],  db[c] = sum_m (deg_m) dYp[m, c] -----------------------------
 // Persistent CTAs stride over 32-row sub-tiles and keep the [K, 64] partial in registers.
 constexpr int WG_ROWS = 32;
-constexpr int WG_MAX_PARTS = NUM_SMS;
-int wgrad_max_parts() { return WG_MAX_PARTS; }
 
 template <int K>
 __global__ void __launch_bounds__(LIN_THREADS)
@@ -384,6 +388,8 @@ int embed1_wgrad(const float* x, int K, const float* shift, const float* scale, 
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
 }
+
+#endif  // GCNN_ALT_PATHS
 
 // ---- head layer 2: score = g . w + b (Dense(1), model.py:208) and its backward -----------------------------------
 __global__ void __launch_bounds__(256)

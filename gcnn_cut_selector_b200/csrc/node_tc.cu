@@ -68,6 +68,9 @@ int pack_weights(const float* params, const int* block_offsets_dev, int n_blocks
     return GCNN_OK;
 }
 
+// Everything below -- the one-launch-per-layer 3xTF32 kernels and the 3xTF32 forward chains -- is an A/B alternate of the
+// bf16x3 chains (node_fwd.cu / node_bwd.cu): compiled only with -DGCNN_ALT_PATHS.  pack_weights above is product code.
+#ifdef GCNN_ALT_PATHS
 // ---- the GEMM ------------------------------------------------------------------------------------------------------
 template <int K>
 __global__ void __launch_bounds__(TC_THREADS)
@@ -722,5 +725,14 @@ int tc_wgrad(const TcWgradArgs& a, cudaStream_t st) {
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
 }
+
+#else
+// product build: the call sites that could select these (option "bf16_forward" = 0 ...) are unreachable; keep the linker happy
+static int alt_missing() { set_error("built without -DGCNN_ALT_PATHS"); return GCNN_INVALID; }
+int tc_conv_forward(const ConvFwdArgs&, cudaStream_t) { return alt_missing(); }
+int tc_embed_forward(const EmbFwdArgs&, cudaStream_t) { return alt_missing(); }
+int tc_linear(const TcArgs&, int, double, cudaStream_t) { return alt_missing(); }
+int tc_wgrad(const TcWgradArgs&, cudaStream_t) { return alt_missing(); }
+#endif  // GCNN_ALT_PATHS
 
 }  // namespace gcnn

@@ -302,9 +302,13 @@ int gcnn_edge_forward(const int32_t* ptr, const int32_t* src, const float* val, 
 int gcnn_edge_backward(gcnn_workspace* ws, const int32_t* ptr, const int32_t* other, const float* val, int64_t n_send,
                        const float* R, const float* S, const float* G, const float* w_edge, float f_shift,
                        float f_scale, float s_f, float* dS, float* dw, void* stream);
-/* Y = act(X W + b): X [m, k] (k in {64, 128}), W [k, 64]; relu != 0 applies ReLU; b may be NULL. */
+/* Y = act(X W + b): X [m, 64], W [64, 64]; relu != 0 applies ReLU; b may be NULL.  The fp32 SIMT dense kernel: one of
+ * the A/B alternates, present only in -DGCNN_ALT_PATHS builds (GCNN_INVALID otherwise). */
 int gcnn_linear_forward(const float* X, const float* W, const float* b, int64_t m, int k, int relu, float* Y,
                         void* stream);
+/* 1 if the library was built with -DGCNN_ALT_PATHS (options "tensor_cores" / "fused" / "fused_backward" /
+ * "bf16_forward" = 0 select the round-1 A/B alternates), 0 for the product build, where those options are fixed at 1. */
+int gcnn_has_alt_paths(void);
 
 #ifdef __cplusplus
 }

@@ -1,6 +1,7 @@
-# run 12: 8 GPUs -- peer-memory all-reduce vs NCCL, host / record / resident end-to-end, then the full line with config 4
+# run 12 (8 GPUs) -- peer-memory all-reduce vs NCCL, host / record / resident end-to-end, then the full line with config 4
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533"
+timeout 300 $TR tests/dp_gpu_check.py > gpurun_out/r2l_dp_check_8gpu.log 2>&1; echo "dp check exit $?"; grep "^{" gpurun_out/r2l_dp_check_8gpu.log
 for peer in 1 0; do
   GCNN_DP_PEER=$peer timeout 300 $TR bench.py --gpus 8 --steps 40 --warmup 5 --no-extra-configs > gpurun_out/r2l_bench_8gpu_peer$peer.json 2> gpurun_out/r2l_bench_8gpu_peer$peer.err
   echo "peer=$peer exit $?"

@@ -57,12 +57,11 @@ def main():
     rows = []
     for pname, opts in paths.items():
         m = GCNN(device="cuda:0", seed=0)
+        if pname != "tc_chains" and not m._lib.gcnn_has_alt_paths():
+            continue  # the fp32 SIMT path is an A/B alternate: GCNN_LIB_VARIANT=alt (-DGCNN_ALT_PATHS build)
         m.restore_state(state)
         for k, v in opts.items():
-            try:
-                m.set_option(k, v)
-            except Exception:
-                pass
+            m.set_option(k, v)
         for shape, n in cases:
             batch = batching.concat_samples(synth.make_samples(shape, n, seed0=1000 + n))
             for counts in (False, True):

@@ -33,9 +33,13 @@ GRAD_TOL = {"tc_chains": 1e-5, "tc_tf32_fwd": 3e-5, "tc_unfused": 3e-5, "fp32": 
 def model(request, golden_dir):
     """tc_chains: the default path (fused tcgen05 chains on bf16x3 tiles, forward and backward); tc_tf32_fwd: the same
     with the 3xTF32 forward chains; tc_unfused: one tensor-core launch per dense layer and per gradient (3xTF32); fp32:
-    exact-fp32 SIMT dense layers."""
+    exact-fp32 SIMT dense layers.  The product library carries only tc_chains; the other three are compiled with
+    -DGCNN_ALT_PATHS (``python -m gcnn_cut_selector_b200.build -DGCNN_ALT_PATHS --variant=alt``) and run with
+    ``GCNN_LIB_VARIANT=alt python -m pytest tests -m gpu``."""
     from gcnn_cut_selector_b200 import GCNN
     m = GCNN(device="cuda:0", seed=0)
+    if request.param != "tc_chains" and not m._lib.gcnn_has_alt_paths():
+        pytest.skip("A/B alternate: needs the -DGCNN_ALT_PATHS build (GCNN_LIB_VARIANT=alt)")
     m.restore_state(os.path.join(golden_dir, "state_stream.pkl"))
     m.set_option("tensor_cores", 0 if request.param == "fp32" else 1)
     m.set_option("fused", 0 if request.param == "tc_unfused" else 1)
@@ -256,6 +260,8 @@ def test_edge_forward_backward_ops(model, n_recv, n_send, E, s_f):
 @pytest.mark.parametrize("m", [1, 127, 128, 129, 1000])
 def test_linear_forward_op(model, m):
     from gcnn_cut_selector_b200._lib import check
+    if not model._lib.gcnn_has_alt_paths():
+        pytest.skip("the fp32 SIMT dense kernel is an A/B alternate (-DGCNN_ALT_PATHS build)")
     rng = np.random.default_rng(m)
     X, W, b = rng.standard_normal((m, 64)), rng.standard_normal((64, 64)), rng.standard_normal(64)
     dev = model.device
@@ -994,6 +1000,13 @@ def test_bf16_mlp_mode_within_1e2(golden_dir, oracle64, shape, n, counts, precis
 def test_bf16_mlp_mode_needs_the_chain_kernels(golden_dir):
     from gcnn_cut_selector_b200 import GCNN, InvalidArgumentError
     m = GCNN(device="cuda:0", seed=0)
+    if not m._lib.gcnn_has_alt_paths():  # the product build: the alternates cannot even be selected
+        with pytest.raises(InvalidArgumentError):
+            m.set_option("tensor_cores", 0)
+        m.set_option("tensor_cores", 1)
+        m.set_option("precision", 1)
+        m.set_option("precision", 0)
+        return
     m.set_option("tensor_cores", 0)
     with pytest.raises(InvalidArgumentError):
         m.set_option("precision", 1)
