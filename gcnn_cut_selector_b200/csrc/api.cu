@@ -187,6 +187,7 @@ struct gcnn_workspace {
     cudaEvent_t ev_layout[4] = {};  // cons by-left, cons by-var, cut by-left, cut by-var are ready
     float* t_dh1b = nullptr;
     // tensor-core path: packed 3xTF32 weight images, one per 64 x 64 weight block
+    int long_row = default_long_row();  // option "long_row": rows longer than this are reduced by a whole CTA (edge.cu)
     int use_tc = 1;
     int use_fused = 1;  // one tcgen05 chain kernel per convolution instead of four dense launches
     float* tc_images = nullptr;
@@ -258,6 +259,7 @@ static size_t carve(gcnn_workspace* ws, char* base, const Caps& c) {
             ls[s]->perm = cv.take<int32_t>(E);
             ls[s]->pair_buf = cv.take<int2>(E + 64);  // (the block kernels copy whole 16-pair chunks: up to a chunk past the end)
             ls[s]->pair = nullptr;
+            ls[s]->long_row = ws->long_row;
         }
     }
     ws->sort.key_a = cv.take<int32_t>(emax);
@@ -1361,7 +1363,10 @@ int gcnn_set_option(gcnn_workspace* ws, const char* name, int value) {
     else if (!strcmp(name, "bf16_forward")) ws->use_bf16_fwd = value != 0;
     else if (!strcmp(name, "count_before_loss")) ws->count_before_loss = value != 0;
     else if (!strcmp(name, "edge_masks")) ws->use_edge_masks = value != 0;
-    else if (!strcmp(name, "long_row")) set_long_row_threshold(value);  // process-wide; layouts must be rebuilt after a change
+    else if (!strcmp(name, "long_row")) {  // this workspace's layouts, from their next build on
+        ws->long_row = value < 32 ? 32 : value;
+        for (auto& g : ws->graph) g.by_left.long_row = g.by_var.long_row = ws->long_row;
+    }
     else { set_error("unknown option %s", name); return GCNN_INVALID; }
     return GCNN_OK;
 }

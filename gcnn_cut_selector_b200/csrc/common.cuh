@@ -145,13 +145,16 @@ struct EdgeLayout {   // edges grouped by one endpoint ("owner"), stable in orig
     float* val;       // [E] raw edge feature
     int32_t* perm;    // [E] original edge id
     const int32_t* reordered;  // device word: 0 = the layout kept the input order (perm[p] == p); set by build_layout
-    const int32_t* long_rows;  // device word, set by build_layout: bit 0 = some owner has more than long_row_threshold()
+    const int32_t* long_rows;  // device word, set by build_layout: bit 0 = some owner has more than long_row
                                // edges, bit 1 = some owner has more than max(32, 4 x mean degree) edges
     // Block-diagonal batches (edge_block.cu): {other endpoint clamped into the owner's block, normalised coefficient
     // (val + shift) * scale as float bits} per position -- one 8-byte load per edge, no range checks in the kernels.
     // nullptr unless the layout was built with the batch's block structure; pair_buf is the workspace buffer behind it.
     const int2* pair;
     int2* pair_buf;
+    // rows longer than this are reduced by a whole CTA in the generic edge kernels (edge.cu); set by the owner of the
+    // layout BEFORE it is built (workspace option "long_row", env GCNN_LONG_ROW): the build's degree report uses it too
+    int long_row = 512;
 };
 // what a layout build needs to write EdgeLayout::pair: node offsets of the blocks on the owner and on the other side,
 // and the edge pre-norm parameters (device scalars, nullable)
@@ -162,9 +165,7 @@ struct LayoutBlocks {
     const float* f_shift = nullptr;
     const float* f_scale = nullptr;
 };
-// rows longer than this are reduced by a whole CTA in the edge kernels (csrc/edge.cu); GCNN_LONG_ROW overrides (experiments)
-int long_row_threshold();
-void set_long_row_threshold(int v);
+int default_long_row();  // 512, or GCNN_LONG_ROW from the environment (read once; the value lives in each workspace)
 constexpr int LONG_FLAG_OFFSET = 8;  // build_layout writes the long-row word at unsorted_flag + 8
 
 struct SortScratch {

@@ -249,10 +249,10 @@ __global__ void finalize_layout_kernel(const int32_t* __restrict__ keys, const i
     }
 }
 
-// process-wide (like the error string): option "long_row" of gcnn_set_option, or GCNN_LONG_ROW in the environment
-static int g_long_row = [] { const char* e = getenv("GCNN_LONG_ROW"); const int x = e ? atoi(e) : 512; return x < 32 ? 32 : x; }();
-int long_row_threshold() { return g_long_row; }
-void set_long_row_threshold(int v) { g_long_row = v < 32 ? 32 : v; }
+int default_long_row() {
+    static const int v = [] { const char* e = getenv("GCNN_LONG_ROW"); const int x = e ? atoi(e) : 512; return x < 32 ? 32 : x; }();
+    return v;
+}
 
 static int bit_length(int64_t x) {
     int b = 0;
@@ -346,7 +346,7 @@ int build_layout(const int32_t* keys, const int32_t* others, const float* feats,
         // a violated hint leaves unsorted_flag = 1 with no sorted pairs: fall back to the input order (the error is
         // reported through err_flag) by reading the always-zero word
         ((trivially_sorted || hint_sorted) ? zero_flag : unsorted_flag), sorted_keys, sorted_perm, out,
-        unsorted_flag + LONG_FLAG_OFFSET, long_row_threshold(), (int)max((int64_t)32, 4 * ceil_div(E, n_owner > 0 ? n_owner : 1)),
+        unsorted_flag + LONG_FLAG_OFFSET, out.long_row, (int)max((int64_t)32, 4 * ceil_div(E, n_owner > 0 ? n_owner : 1)),
         blk, err_flag);
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;

@@ -8,7 +8,7 @@
 // Mapping: one warp per segment (receiving node in the forward, sending node in the backward); a half-warp covers one
 // 64-float row with one float4 per lane, so a warp works on two edges at a time and each gathered row is one fully
 // coalesced 256-byte read.  Persistent CTAs own contiguous row ranges -- equal in rows for regular graphs, equal in
-// weight (edges + rows) when the CSR build reports heavy rows; rows beyond long_row_threshold() are reduced by a whole
+// weight (edges + rows) when the CSR build reports heavy rows; rows beyond EdgeLayout::long_row are reduced by a whole
 // CTA.  Reduction order is fixed by the layout and the launch shape -> bit-reproducible, no atomics.
 // Roofline: HBM for the algorithmic bytes (stated in DESIGN.md); what the kernels actually run against is the L2 / L1
 // gather rate and instruction issue (profiles/).
@@ -196,7 +196,7 @@ struct EdgeFwdSmem {
 
 // The forward row loop.  IDENT: the layout kept the input order (perm[p] == p, e.g. batches sorted by their left index,
 // utils.py:102-104), so the masks go to the layout position itself -- no permutation load or shuffle per edge.
-//   * Long rows (> long_row_threshold() edges, default 512; only when the layout reports any): the whole CTA reduces the row, every warp an equal
+//   * Long rows (> EdgeLayout::long_row edges, default 512; only when the layout reports any): the whole CTA reduces the row, every warp an equal
 //     share of its edges, partial sums combined in warp order through shared memory -- a 1,000-edge row is no longer one
 //     warp's 150 us serial walk.
 //   * All other rows: one warp per row, handed out through a shared counter (row lengths differ; which warp reduces a
@@ -372,7 +372,7 @@ int edge_forward(const EdgeLayout& L, int64_t n_recv, const float* R, const floa
     const unsigned grid = (unsigned)min((int64_t)NUM_SMS * per_sm, ceil_div(n_recv, threads / 32));
 #define GCNN_EDGE_FWD_LAUNCH(TRAIN_, T_, C_)                                                                             \
     GCNN_LAUNCH((edge_forward_kernel<TRAIN_, T_, C_>), grid, threads, 0, st, L.ptr, L.other, L.val, n_recv, R, S, w_edge, sc, \
-                H, cnt, L.perm, mk, L.reordered, L.long_rows, long_row_threshold(), dyn)
+                H, cnt, L.perm, mk, L.reordered, L.long_rows, L.long_row, dyn)
     if (cfg == 1) { if (cnt) GCNN_EDGE_FWD_LAUNCH(true, 256, 3); else GCNN_EDGE_FWD_LAUNCH(false, 256, 3); }
     else { if (cnt) GCNN_EDGE_FWD_LAUNCH(true, 512, 2); else GCNN_EDGE_FWD_LAUNCH(false, 512, 2); }
 #undef GCNN_EDGE_FWD_LAUNCH
@@ -617,7 +617,7 @@ int edge_backward_masked(const EdgeLayout& L, int64_t n_send, const float* G, co
     int ctas = (int)min((int64_t)EDGE_BWD_MAX_CTAS, ceil_div(n_send > 0 ? n_send : 1, EDGE_WARPS));
     *n_partials = ctas;
     GCNN_LAUNCH(edge_backward_masked_kernel, ctas, EDGE_THREADS, 0, st, L.ptr, L.other, L.val, L.perm, n_send, G,
-                static_cast<const uint2*>(masks), sc, dS, dw_partials, L.long_rows, long_row_threshold());
+                static_cast<const uint2*>(masks), sc, dS, dw_partials, L.long_rows, L.long_row);
     GCNN_LAUNCH_CHECK();
     return GCNN_OK;
 }

@@ -775,7 +775,7 @@ int transpose_blocks(const int32_t* keys_var, const int32_t* keys_left, const fl
         GCNN_LAUNCH_ORDERED(transpose_blocks_kernel<W_>, grid, W_ * 32, smem, st, keys_var, keys_left, feats, E,            \
                             (int32_t)n_left, (int32_t)n_var, left_off, var_off, (int)n_blocks, cap, range_cap, out,       \
                             f_shift, f_scale, err_flag, unsorted_flag, unsorted_flag + LONG_FLAG_OFFSET,                  \
-                            long_row_threshold(), heavy);                                                                  \
+                            out.long_row, heavy);                                                                  \
     } while (0)
     if (warps == 32) GCNN_TR(32); else if (warps == 16) GCNN_TR(16); else GCNN_TR(8);
 #undef GCNN_TR

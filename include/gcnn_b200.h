@@ -11,8 +11,12 @@
  *     of TF-CPU's InvalidArgumentError from tf.gather, model.py:564), GCNN_CUDA_ERROR (see gcnn_last_error()),
  *     GCNN_OOM (the analogue of tf.errors.ResourceExhaustedError, model_trainer.py:308 -- callers skip the batch);
  *   - hot calls never allocate and never synchronise; only gcnn_workspace_reserve(), the *_host entry points,
- *     gcnn_check() and gcnn_prenorm_stats() synchronise;
- *   - the caller owns every tensor; the library owns only the workspace.
+ *     gcnn_check() and gcnn_prenorm_stats() synchronise.  The per-op TEST entry points at the end of this header
+ *     (gcnn_edge_forward, gcnn_edge_backward, gcnn_linear_forward) are the exception: they cudaMalloc a scalar buffer
+ *     and synchronise on every call and must not be used on a hot path;
+ *   - the caller owns every tensor; the library owns only the workspace.  State is per workspace; the only
+ *     process-wide items are diagnostics (the last-error string, the launch counter behind gcnn_kernel_launches() and
+ *     the CUDA-event profiler behind gcnn_profile_begin/end) -- they never influence results.
  *
  * Parameter layout: trainable parameters live in ONE flat fp32 buffer of GCNN_N_TRAINABLE floats, in the reference's
  * `trainable_variables` order (model.py:174-208, 486-508); the 58 non-trainable pre-norm values (PreNormLayer
@@ -291,7 +295,8 @@ int gcnn_stage_records(gcnn_workspace* ws, int slot, const void* const* records_
 int gcnn_stage_resident_records(gcnn_workspace* ws, int slot, const void* shard_device, const void* shard_host,
                                 const void* const* records_host, int64_t n_records, int64_t* h2d_bytes_out);
 
-/* ---- per-op entry points (unit parity tests; same kernels the whole-model calls launch) ---------------------- */
+/* ---- per-op entry points (unit parity tests ONLY: each call allocates, uploads scalars and synchronises; same kernels
+ *      the whole-model calls launch) ------------------------------------------------------------------------------ */
 /* H[t] = sum_{e in seg(t)} relu(s_f * (R[t] + f_e * w + S[src_e])), cnt[t] = number of active terms per feature.
  * ptr/src/val describe segments grouped by the receiving node.  f_e = (val + f_shift) * f_scale. */
 int gcnn_edge_forward(const int32_t* ptr, const int32_t* src, const float* val, int64_t n_recv, const float* R,
