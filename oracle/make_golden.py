@@ -19,6 +19,10 @@ Outputs (all small):
                        ``model_trainer.process`` (evaluation branch)
   selector.npz         preset qualities / parallelism matrices -> final cut order and nselectedcuts from the reference's own
                        ``CustomCutsel.cutselselect`` (model_benchmarker.py:70-157)
+  driver_trace.pkl     the call sequence of the reference's own drivers -- ``model_trainer.pretrain``,
+                       ``model_trainer.process`` (training and evaluation branch), ``model_tester.process`` -- run
+                       unmodified over the reference's own GCNN (fp64): every call on the model, every tape.gradient /
+                       apply_gradients, and what each returned (``--drivers-only``; replayed by tests/driver_replay.py)
   state_stream.pkl     the weights every fixture uses, written by the reference's own ``save_state`` (62 arrays)
 """
 import gzip
@@ -241,8 +245,110 @@ def selector_case():
     np.savez_compressed(os.path.join(GOLDEN, "selector.npz"), **cases)
 
 
+def driver_case(params):
+    """The reference's OWN drivers -- model_trainer.pretrain (model_trainer.py:194-236), model_trainer.process in its
+    training and evaluation branches (:239-316) and model_tester.process (model_tester.py:173-237) -- run UNMODIFIED
+    over the reference's own GCNN (fp64, TF stand-in) behind a recording proxy.  The trace lists, in order, every call
+    the drivers make on the model (``pretrain_init`` / ``pretrain`` / ``pretrain_next`` / ``__call__`` and any other
+    attribute they touch), every ``tape.gradient`` and ``optimizer.apply_gradients`` in between, and what each returned.
+    tests/test_driver_trace.py replays exactly this call sequence against gcnn_cut_selector_b200.GCNN on the GPU (the
+    reference tree does not exist on the GPU box and this container has no GPU, so the drivers themselves cannot be
+    executed over the CUDA class anywhere; the recorded sequence is what travels)."""
+    import model_tester as ref_tester
+    import model_trainer as ref_trainer
+    tf.set_float_dtype(torch.float64)
+    raw = [run_reference_batch(synth.make_samples(shape, n, seed0=seed))
+           for shape, n, seed in (("tiny", 3, 900), ("mini", 2, 910), ("tiny", 4, 920))]
+    tf.set_float_dtype(torch.float64)
+    batches = [tuple(tf.convert_to_tensor(x) for x in b) for b in raw]
+    m, _ = reference_model(params, torch.float64)
+    events = []
+    index_of = {id(b[0]): i for i, b in enumerate(batches)}
+
+    class Traced:
+        def __call__(self, batched_states, training):
+            out = m(batched_states, training)
+            events.append({"op": "call", "batch": index_of[id(batched_states[0])], "training": builtins_bool(training),
+                           "totals": [int(x) for x in batched_states[7:10]], "out": out.detach().numpy().copy()})
+            return out
+
+        def pretrain_init(self):
+            events.append({"op": "pretrain_init"})
+            return m.pretrain_init()
+
+        def pretrain(self, batched_states, training):
+            ret = m.pretrain(batched_states, training)
+            events.append({"op": "pretrain", "batch": index_of[id(batched_states[0])], "training": builtins_bool(training),
+                           "ret": builtins_bool(ret)})
+            return ret
+
+        def pretrain_next(self):
+            res = m.pretrain_next()
+            events.append({"op": "pretrain_next", "ret": None if res is None else str(res[1])})
+            return res
+
+        @property
+        def trainable_variables(self):
+            events.append({"op": "trainable_variables"})
+            return m.trainable_variables
+
+        def __getattr__(self, name):  # anything else the drivers reach for shows up in the trace
+            events.append({"op": "getattr", "name": name})
+            return getattr(m, name)
+
+    traced = Traced()
+    fractions = np.array([0.25, 0.5, 0.75, 1])
+    lr = 1e-4  # model_trainer.py:53, the reference's default
+    tf.trace = events
+    torch.set_grad_enabled(False)  # TF eager tensors carry no tape outside tf.GradientTape
+    n_layers = ref_trainer.pretrain(traced, batches[:2])
+    events.append({"op": "phase", "name": "pretrain", "result": int(n_layers)})
+    optimizer = ref_trainer.Adam(learning_rate=lambda: lr)
+    loss, acc = ref_trainer.process(traced, batches, fractions, ref_trainer.MeanSquaredError(), optimizer)
+    events.append({"op": "phase", "name": "train", "result": (float(loss), np.asarray(acc, np.float64))})
+    loss, acc = ref_trainer.process(traced, batches[::-1], fractions, ref_trainer.MeanSquaredError())
+    events.append({"op": "phase", "name": "valid", "result": (float(loss), np.asarray(acc, np.float64))})
+    loss, acc = ref_tester.process(traced, batches)
+    events.append({"op": "phase", "name": "test", "result": (float(loss), float(acc))})
+    torch.set_grad_enabled(True)
+    tf.trace = None
+    assert n_layers == 11
+    # gradients: the whole flat vector of the first step, per-array L2 norms of the later ones (fixture size)
+    first = True
+    for e in events:
+        if e["op"] == "tape_gradient":
+            flat = np.concatenate([g.reshape(-1) for g in e.pop("grads")])
+            e["norms"] = np.array([np.linalg.norm(flat[o:o + k]) for o, k in _offsets()], np.float64)
+            if first:
+                e["flat"] = flat.astype(np.float32)
+                first = False
+    final = np.concatenate([v.numpy().reshape(-1) for v in m.variables if v.trainable]).astype(np.float32)
+    prenorm = np.concatenate([v.numpy().reshape(-1) for v in m.variables if not v.trainable])
+    with open(os.path.join(GOLDEN, "driver_trace.pkl"), "wb") as fh:
+        pickle.dump({"batches": raw, "events": events, "fractions": fractions, "lr": lr, "final_trainable": final,
+                     "final_prenorm": prenorm.astype(np.float64)}, fh)
+    ops = [e["op"] for e in events]
+    print("driver_trace:", len(events), "events;", {o: ops.count(o) for o in dict.fromkeys(ops)})
+    print("  phases:", [(e["name"], e["result"]) for e in events if e["op"] == "phase"])
+
+
+def builtins_bool(x):
+    return bool(x.item()) if torch.is_tensor(x) else bool(x)
+
+
+def _offsets():
+    off = 0
+    for _name, shape in orc.TRAINABLE:
+        k = int(np.prod(shape))
+        yield off, k
+        off += k
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
+    if "--drivers-only" in sys.argv:
+        driver_case(orc.restore_state(os.path.join(GOLDEN, "state_stream.pkl"), dtype=torch.float32))
+        return
     if "--selector-only" in sys.argv:
         selector_case()
         return
@@ -274,6 +380,7 @@ def main():
     pretrain_case(params)
     metric_case()
     selector_case()
+    driver_case(params)
 
 
 if __name__ == "__main__":

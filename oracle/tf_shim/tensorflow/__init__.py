@@ -49,6 +49,18 @@ def _np(self):
 
 torch.Tensor.numpy_tf = _np  # not used by the reference; kept for debugging
 
+# A TF eager tensor gives up its value with .numpy() whether or not a tape is watching (model_trainer.py:285-286, 303 do
+# that with predictions and the loss inside the training branch); a torch tensor that requires grad refuses.  In this
+# process -- the golden generator and the tests that import the shim -- numpy() detaches first.
+_torch_numpy = torch.Tensor.numpy
+
+
+def _eager_numpy(self, *args, **kwargs):
+    return _torch_numpy(self.detach().cpu(), *args, **kwargs)
+
+
+torch.Tensor.numpy = _eager_numpy
+
 
 def convert_to_tensor(value, dtype=None):
     if dtype is float32 or dtype is torch.float32 or dtype is torch.float64:
@@ -160,3 +172,35 @@ def split(value, num_or_size_splits, axis=0):
 
 def numpy_function(func, inp, Tout):
     return func(*inp)
+
+
+# ---- training (model_trainer.py:267-273) ----------------------------------------------------------------------------
+# `trace` (a list, or None) receives one record per tape.gradient / optimizer.apply_gradients call, so that
+# oracle/make_golden.py can record what the reference's own training loop does around the model.
+trace = None
+
+
+class GradientTape:
+    """``with tf.GradientTape() as tape: ...; tape.gradient(target, sources)`` over torch autograd (the shim's Variables
+    are torch leaves, so everything computed inside the context is already on torch's tape)."""
+
+    def __enter__(self):
+        self._prev = torch.is_grad_enabled()
+        torch.set_grad_enabled(True)
+        return self
+
+    def __exit__(self, *exc):
+        torch.set_grad_enabled(self._prev)
+        return False
+
+    def gradient(self, target, sources):
+        sources = list(sources)
+        hook = getattr(sources[0], "_shim_gradient", None) if sources else None
+        if hook is not None:  # a model that differentiates itself (the recorded-driver replay of tests/)
+            grads = hook(target, sources)
+        else:
+            grads = list(torch.autograd.grad(target, [_val(v) for v in sources], allow_unused=True))
+        if trace is not None:
+            trace.append({"op": "tape_gradient", "target": float(target.detach()), "n_sources": len(sources),
+                          "grads": [None if g is None else g.detach().cpu().numpy() for g in grads]})
+        return grads

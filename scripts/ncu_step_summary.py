@@ -8,7 +8,8 @@ import sys
 rows = list(csv.reader(open(sys.argv[1])))
 hdr, units = rows[0], rows[1]
 col = {k: i for i, k in enumerate(hdr)}
-CLASS = [("check_init_hist", "csr_check"), ("digit_scan", "csr_scan"), ("radix_scatter", "csr_scatter"),
+CLASS = [("edge_block_forward", "edge_forward"), ("edge_block_backward", "edge_backward"), ("transpose_blocks", "csr_scatter"),
+         ("assemble_records", "assemble_records"), ("dp_allreduce_adam", "adam"), ("check_init_hist", "csr_check"), ("digit_scan", "csr_scan"), ("radix_scatter", "csr_scatter"),
          ("finalize_layout", "csr_finalize"), ("tc_embed_forward", "embed_forward_chain"),
          ("tc_conv_forward", "conv_forward_chain"), ("head_loss", "head2"),
          ("edge_forward", "edge_forward"), ("head2", "head2"), ("edge_backward", "edge_backward"),
@@ -65,7 +66,7 @@ for r in window:
 total_us = sum(o["us"] for o in out)
 with open(sys.argv[2] + "_kernels.md", "w") as f:
     f.write("# One training step under `ncu --set full` (cold caches, serialised; compare shares, not absolutes)\n\n")
-    f.write("Workload: bench.py default (32 setcov graphs per step).  DRAM = dram__bytes_read.sum + dram__bytes_write.sum.\n\n")
+    f.write("Workload: bench.py default (32 setcov graphs per step, per-sample counts -> block edge kernels and per-block transposes).  DRAM = dram__bytes_read.sum + dram__bytes_write.sum.\n\n")
     f.write("| # | kernel | grid | block | us | share | DRAM MB | DRAM % | L2 hit % | tensor % | warps active % | issue active % | regs |\n")
     f.write("|---|---|---|---|---|---|---|---|---|---|---|---|---|\n")
     for i, o in enumerate(out):
