@@ -161,7 +161,7 @@ struct gcnn_workspace {
     int conv_blocked[3] = {0, 0, 0};           // the forward of convolution i ran on the block kernels
     // serving path (gcnn_score_host_graph): the whole host-in / host-out scoring call of one shape as a CUDA graph
     struct ServeGraph {
-        int64_t key[6] = {-1, -1, -1, -1, -1, -1};  // n_cons, n_vars, n_cuts, n_cons_edges, n_cut_edges, flags
+        int64_t key[10] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1};  // five sizes, flags, blocks, largest block per node type
         const float *params = nullptr, *prenorm = nullptr;
         cudaGraphExec_t exec = nullptr;
         int64_t hits = 0, last_use = 0;
@@ -1881,16 +1881,19 @@ static void serve_drop_graphs(gcnn_workspace* ws) {
     }
 }
 
-struct ServeLayout { size_t off[8]; size_t total; };  // cons, cei, cef, var, cut, kei, kef, scores (+ 16 bytes: error word)
-static ServeLayout serve_layout(const gcnn_batch* b) {
-    const size_t bytes[8] = {sizeof(float) * b->n_cons * GCNN_CONS_FEATS, sizeof(int32_t) * 2 * b->n_cons_edges,
+// sections of the pinned mirror: cons, cei, cef, var, cut, kei, kef, block offsets, scores (+ 16 bytes in front: error word)
+struct ServeLayout { size_t off[9]; size_t total; int64_t n_blocks; int64_t max_nodes[3]; };
+static ServeLayout serve_layout(const gcnn_batch* b, int64_t n_blocks) {
+    const size_t bytes[9] = {sizeof(float) * b->n_cons * GCNN_CONS_FEATS, sizeof(int32_t) * 2 * b->n_cons_edges,
                              sizeof(float) * b->n_cons_edges, sizeof(float) * b->n_vars * GCNN_VAR_FEATS,
                              sizeof(float) * b->n_cuts * GCNN_CUT_FEATS, sizeof(int32_t) * 2 * b->n_cut_edges,
-                             sizeof(float) * b->n_cut_edges, sizeof(float) * b->n_cuts};
+                             sizeof(float) * b->n_cut_edges, sizeof(int32_t) * 3 * (size_t)(n_blocks > 0 ? n_blocks + 1 : 0),
+                             sizeof(float) * b->n_cuts};
     ServeLayout L{};
     size_t o = 16;
-    for (int i = 0; i < 8; ++i) { L.off[i] = o; o += (bytes[i] + 15) & ~(size_t)15; }
+    for (int i = 0; i < 9; ++i) { L.off[i] = o; o += (bytes[i] + 15) & ~(size_t)15; }
     L.total = o;
+    L.n_blocks = n_blocks;
     return L;
 }
 
@@ -1899,8 +1902,8 @@ static int serve_enqueue(gcnn_workspace* ws, const float* params, const float* p
     // ONE copy: the pinned mirror and staging slot 0's raw area share the layout L (16-byte aligned sections)
     gcnn_workspace::Stage& g = ws->stage[0];
     uint8_t* pin = ws->serve_pin;
-    if ((int64_t)L.off[7] > g.raw_cap) { set_error("serving batch larger than the staging area"); return GCNN_INVALID; }
-    GCNN_TRY(h2d(g.raw + L.off[0], pin + L.off[0], L.off[7] - L.off[0], st));
+    if ((int64_t)L.off[8] > g.raw_cap) { set_error("serving batch larger than the staging area"); return GCNN_INVALID; }
+    GCNN_TRY(h2d(g.raw + L.off[0], pin + L.off[0], L.off[8] - L.off[0], st));
     gcnn_batch meta = *hb;
     meta.cons_feats = (const float*)(g.raw + L.off[0]);
     meta.cons_edge_inds = (const int32_t*)(g.raw + L.off[1]);
@@ -1909,11 +1912,19 @@ static int serve_enqueue(gcnn_workspace* ws, const float* params, const float* p
     meta.cut_feats = (const float*)(g.raw + L.off[4]);
     meta.cut_edge_inds = (const int32_t*)(g.raw + L.off[5]);
     meta.cut_edge_feats = (const float*)(g.raw + L.off[6]);
-    meta.sample_n_cons = meta.sample_n_vars = meta.sample_n_cuts = nullptr;  // one graph per call: no block structure
+    meta.sample_n_cons = meta.sample_n_vars = meta.sample_n_cuts = nullptr;  // the block offsets travel with the mirror
     meta.n_samples = 0;
-    GCNN_TRY(forward_impl(ws, params, prenorm, &meta, ws->scores, -1, st));
+    BlockInfo bi;  // (empty when the caller gave no per-sample counts: generic kernels)
+    if (L.n_blocks > 0) {
+        bi.n = L.n_blocks;
+        for (int t = 0; t < 3; ++t) {
+            bi.off[t] = (const int32_t*)(g.raw + L.off[7]) + t * (L.n_blocks + 1);
+            bi.max_nodes[t] = L.max_nodes[t];
+        }
+    }
+    GCNN_TRY(forward_impl(ws, params, prenorm, &meta, ws->scores, -1, st, &bi));
     if (hb->n_cuts > 0)
-        GCNN_CUDA_TRY(cudaMemcpyAsync(pin + L.off[7], ws->scores, sizeof(float) * hb->n_cuts, cudaMemcpyDeviceToHost, st));
+        GCNN_CUDA_TRY(cudaMemcpyAsync(pin + L.off[8], ws->scores, sizeof(float) * hb->n_cuts, cudaMemcpyDeviceToHost, st));
     GCNN_CUDA_TRY(cudaMemcpyAsync(pin, ws->flags + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     return GCNN_OK;
 }
@@ -1933,7 +1944,23 @@ int gcnn_score_host_graph(gcnn_workspace* ws, const float* params, const float* 
     GCNN_CUDA_TRY(cudaEventRecord(ws->serve_ev, (cudaStream_t)stream));
     cudaStream_t st = ws->serve_stream;
     GCNN_CUDA_TRY(cudaStreamWaitEvent(st, ws->serve_ev, 0));
-    const ServeLayout L = serve_layout(hb);
+    // block structure from the caller's per-sample counts (host vectors in a host batch); anything inconsistent -> none
+    int64_t n_blocks = (ws->use_blocks && hb->n_samples > 0 && hb->n_samples <= MAX_RECORDS && hb->sample_n_cons &&
+                        hb->sample_n_vars && hb->sample_n_cuts) ? hb->n_samples : 0;
+    const int32_t* counts[3] = {hb->sample_n_cons, hb->sample_n_vars, hb->sample_n_cuts};
+    const int64_t totals[3] = {hb->n_cons, hb->n_vars, hb->n_cuts};
+    int64_t max_nodes[3] = {0, 0, 0};
+    for (int t = 0; t < 3 && n_blocks > 0; ++t) {
+        int64_t run = 0;
+        for (int64_t i = 0; i < n_blocks; ++i) {
+            if (counts[t][i] < 0) { run = -1; break; }
+            run += counts[t][i];
+            if (counts[t][i] > max_nodes[t]) max_nodes[t] = counts[t][i];
+        }
+        if (run != totals[t]) n_blocks = 0;
+    }
+    ServeLayout L = serve_layout(hb, n_blocks);
+    for (int t = 0; t < 3; ++t) L.max_nodes[t] = n_blocks > 0 ? max_nodes[t] : 0;
     if (L.total > ws->serve_pin_bytes) {  // (re)allocate the pinned mirror; captured graphs point into the old one
         GCNN_CUDA_TRY(cudaStreamSynchronize(st));
         serve_drop_graphs(ws);
@@ -1956,8 +1983,17 @@ int gcnn_score_host_graph(gcnn_workspace* ws, const float* params, const float* 
         (void)bytes;
         if (exact[i]) memcpy(ws->serve_pin + L.off[i], src[i], exact[i]);
     }
-    // find / age the graph of this shape
-    const int64_t key[6] = {hb->n_cons, hb->n_vars, hb->n_cuts, hb->n_cons_edges, hb->n_cut_edges, hb->flags};
+    if (n_blocks > 0) {  // node offsets of the blocks, [3][n_blocks + 1]
+        int32_t* off = reinterpret_cast<int32_t*>(ws->serve_pin + L.off[7]);
+        for (int t = 0; t < 3; ++t) {
+            int32_t run = 0;
+            for (int64_t i = 0; i < n_blocks; ++i) { off[t * (n_blocks + 1) + i] = run; run += counts[t][i]; }
+            off[t * (n_blocks + 1) + n_blocks] = run;
+        }
+    }
+    // find / age the graph of this shape (the block kernels' launch shapes depend on the largest block)
+    const int64_t key[10] = {hb->n_cons, hb->n_vars, hb->n_cuts, hb->n_cons_edges, hb->n_cut_edges, hb->flags, n_blocks,
+                             L.max_nodes[0], L.max_nodes[1], L.max_nodes[2]};
     gcnn_workspace::ServeGraph* slot = nullptr;
     gcnn_workspace::ServeGraph* oldest = &ws->serve[0];
     for (auto& g : ws->serve) {
@@ -2001,7 +2037,7 @@ int gcnn_score_host_graph(gcnn_workspace* ws, const float* params, const float* 
         GCNN_TRY(serve_enqueue(ws, params, prenorm, hb, L, st));
     }
     GCNN_CUDA_TRY(cudaStreamSynchronize(st));
-    if (hb->n_cuts > 0) memcpy(scores_host, ws->serve_pin + L.off[7], sizeof(float) * hb->n_cuts);
+    if (hb->n_cuts > 0) memcpy(scores_host, ws->serve_pin + L.off[8], sizeof(float) * hb->n_cuts);
     int32_t flag;
     memcpy(&flag, ws->serve_pin, sizeof(flag));
     if (flag) return read_error_flag(ws, st);

@@ -32,6 +32,7 @@ pack_weights_kernel(const float* __restrict__ params, const int* __restrict__ bl
     float* img = images + (int64_t)blockIdx.x * TC_IMG_FLOATS;
     for (int i = threadIdx.x; i < 64 * 64; i += 256) Wb[i >> 6][i & 63] = W[i];
     __syncthreads();
+#ifdef GCNN_ALT_PATHS  // the 3xTF32 images are read by the A/B alternates only
     for (int i = threadIdx.x + 256 * blockIdx.y; i < 64 * 16; i += 256 * PACK_SPLIT) {
         const int n = i >> 4, k = (i & 15) * 4;
         const uint32_t off = swz_chunk_off(n, k, 64) >> 2;
@@ -45,6 +46,7 @@ pack_weights_kernel(const float* __restrict__ params, const int* __restrict__ bl
         *reinterpret_cast<float4*>(img + 2 * IMG_FLOATS + off) = hi;
         *reinterpret_cast<float4*>(img + 3 * IMG_FLOATS + off) = lo;
     }
+#endif
     // bf16x3 N image for the backward chains (node_bwd.cu): B[n][k] = Wb[n][k] as three bf16 pieces, 64 rows x 128 bytes
     // each in the K-major SWIZZLE_128B layout (16-byte chunks of 8 bf16)
     uint8_t* img16 = reinterpret_cast<uint8_t*>(img + TC_IMG_TF32_FLOATS);
