@@ -2,17 +2,28 @@
 """Benchmark of the GCNN hot path (BASELINE.json metric: GCNN train graphs/s and edge-messages/s; % of HBM roofline).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--graphs-per-gpu G]
+                    [--no-extra-configs] [--no-cpu-baseline]
 
-A "step" is one training step (CSR build + forward + MSE + backward + Adam; data-parallel all-reduce when N > 1) on
-one batch of G synthetic setcov-shape graphs per GPU (500 rows x 1000 columns, 25,000 non-zeros, 64 cuts of 100
-non-zeros; offset-concatenated exactly as utils.py:403-407).  G defaults to 32 = BASELINE config 2 per GPU (weak
-scaling); ``--graphs-per-gpu 128 --gpus 8`` is BASELINE config 4 (1,024 graphs/step).
+A "step" is one training step (layout build + forward + MSE + backward + Adam; the peer-memory gradient exchange fused
+with Adam when N > 1) on one batch of G synthetic setcov-shape graphs per GPU (500 rows x 1000 columns, 25,000 non-zeros,
+64 cuts of 100 non-zeros; offset-concatenated exactly as utils.py:403-407, passed WITH the loader's per-sample counts,
+utils.py:420-422).  G defaults to 32 = BASELINE config 2 per GPU (weak scaling).
 
-`value`  : graphs/s over all ranks with the batches already resident in HBM, CUDA-event time, max over ranks.
-`e2e`    : the same metric through the host-buffer entry point (pinned host -> device copies of every input each
-           step, loss read back each step).
-`roofline`: the kernel class with the largest share of the step, ALGORITHMIC bytes / CUDA-event time.
-`cpu_baseline` / ``--impl reference``: the TF-equivalent torch-CPU restatement (oracle/) on the host cores.
+`value`         graphs/s over all ranks with the batches already resident in HBM, CUDA-event time, max over ranks.
+`e2e`           the same metric through the host-buffer entry points: every step copies one full batch from pinned host
+                memory (one batch kept in flight, as the reference's prefetch(1)) and reads one loss back.
+`e2e_records`   the same loop fed from packed sample records, batch assembled on the device (shards.py, csrc/records.cu).
+`e2e_resident`  the same with the rank's shard resident in HBM: only record descriptors cross PCIe per step.
+`roofline`      the kernel class with the largest share of the step: ALGORITHMIC bytes / CUDA-event time of its launches
+                (separate pass, auxiliary streams off); `traffic` from the committed ncu capture (profiles/).
+`configs`       N = 1: BASELINE config 1 (one graph, train step), config 3 (inference on the other three problem classes,
+                batch 1 and 4: device forward, host-in / host-out latency eager, from pageable arrays, and graph-replayed),
+                config 5 (MIPLIB-scale forward with its own roofline).
+`config4`       N > 1: BASELINE config 4, 1,024 / N graphs per GPU (value, e2e, e2e_records, e2e_resident).
+`bf16_mlp`      N = 1: the same workload with option "precision" = 1 (three bf16 products per MMA), labelled, never the
+                headline; `one_product` inside it is the operands-rounded-to-bf16 measurement point.
+`cpu_baseline` / ``--impl reference``: the TF-equivalent torch-CPU restatement (oracle/) on the host cores ("kind": "port";
+                TensorFlow is not installable here), same config.workload string and warm-up as the CUDA arm.
 """
 from __future__ import annotations
 
@@ -428,11 +439,16 @@ def measure_other_configs(model, dev, reps: int = 30):
                 ms = time_device(lambda: model._forward(inp, save_activations=False), reps, flush)
             p50, p95 = host_latency(lambda: model.score_host(hb), reps)
             g50, g95 = host_latency(lambda: model.score_host(hb, graph=True), reps)  # one CUDA graph per shape
+            # the graph path copies the caller's arrays into its own pinned mirror on every call; the eager figure above
+            # starts from arrays that are already pinned -- this one includes making them so (what a plug-in that receives
+            # pageable arrays from the solver pays on the eager path)
+            n50, n95 = host_latency(lambda: model.score_host(HostBatch(batch)), max(10, reps // 3))
             c3.append({"shape": shape, "graphs": n, "n_cons": nc, "n_vars": nv, "n_cuts": nk, "edges": ec + ek,
                        "device_forward_ms": ms, "cuts_per_s": nk / (ms * 1e-3),
                        "edge_messages_per_s": (2 * ec + ek) / (ms * 1e-3),
                        "score_host_ms_p50": p50, "score_host_ms_p95": p95,
-                       "score_host_graph_ms_p50": g50, "score_host_graph_ms_p95": g95})
+                       "score_host_graph_ms_p50": g50, "score_host_graph_ms_p95": g95,
+                       "score_host_from_pageable_ms_p50": n50, "score_host_from_pageable_ms_p95": n95})
     out["config3"] = {"workload": "combauc / capfac / indset shapes, inference cut scoring, batch 1 and 4", "cases": c3}
 
     # config 5: one MIPLIB-scale graph, forward scoring; whole-model algorithmic bytes (686 MB) / time

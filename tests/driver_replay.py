@@ -121,7 +121,7 @@ class GcnnSubject:
         loss = ((self.pred - target) ** 2).mean()
         (flat,) = torch.autograd.grad(loss, self.m.flat_params)
         assert torch.equal(flat, self.m.flat_grads)  # the views `trainable_gradients` hands out
-        return float(loss), flat.cpu().numpy()
+        return float(loss.detach()), flat.cpu().numpy()
 
     def apply(self, lr, iteration):
         self.m.apply_gradients(lr)  # optimizer.apply_gradients(zip(grads, model.trainable_variables)) (:273)
