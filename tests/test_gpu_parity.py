@@ -26,6 +26,7 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-5
 
 
+LINF_FACTOR = 4
 GRAD_TOL = {"tc_chains": 1e-5, "tc_tf32_fwd": 3e-5, "tc_unfused": 3e-5, "fp32": 1e-5}
 
 
@@ -67,14 +68,16 @@ def golden_inputs(z, prefix=""):
 
 
 def assert_grads_close(flat_got, grads_ref: dict, tol=TOL, grads_f32=None):
-    """Per parameter tensor, against fp64 truth: relative L2 error <= tol and max-abs error <= 10 tol.
+    """Per parameter tensor, against fp64 truth: relative L2 error <= tol and max-abs error <= LINF_FACTOR x tol.
 
     Why two norms: a ReLU network's gradient is discontinuous where a pre-activation is ~0.  Among the ~10^7
     pre-activations of a batch a few always sit within fp32 rounding of zero, and ANY fp32 evaluation (this one, the
     reference's TF kernels, the torch restatement -- which deviates up to 1.6e-5 in max-abs on these batches) may put
     them on the other side of the kink than fp64 does.  One such flip moves single gradient elements by ~1e-5 of the
     tensor's max-abs but leaves the tensor's L2 error far below 1e-5, so the tight bound is on the L2 norm and the
-    max-abs bound catches real bugs (a wrong index or a dropped term shows up at 1e-2 .. 1)."""
+    max-abs bound catches real bugs (a wrong index or a dropped term shows up at 1e-2 .. 1).  LINF_FACTOR = 4: the worst
+    max-abs deviation measured over all shapes is 2.6e-5 on the product path and 1.6e-5 on the exact-fp32 path
+    (profiles/r2_grad_errors.md); round 1 allowed 10 x."""
     flat_got = np.asarray(flat_got, np.float64)
     gmax = max(float(g.abs().max()) for g in grads_ref.values())
     gl2 = max(float(g.norm()) for g in grads_ref.values())
@@ -87,7 +90,7 @@ def assert_grads_close(flat_got, grads_ref: dict, tol=TOL, grads_f32=None):
         l2 = np.linalg.norm(diff) / max(np.linalg.norm(ref), 1e-3 * gl2)
         linf = np.abs(diff).max() / max(np.abs(ref).max(), 1e-3 * gmax)
         assert l2 <= tol, f"{name}: relative L2 error {l2:.3e} > {tol:.1e}"
-        assert linf <= 10 * tol, f"{name}: max-abs error {linf:.3e} > {10 * tol:.1e}"
+        assert linf <= LINF_FACTOR * tol, f"{name}: max-abs error {linf:.3e} > {LINF_FACTOR * tol:.1e}"
         o += k
 
 
