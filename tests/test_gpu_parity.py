@@ -583,10 +583,10 @@ def test_pretrain_protocol_matches_golden(golden_dir):
         n += 1
     assert n == 11
     got = m.flat_prenorm.cpu().numpy().astype(np.float64)
-    assert rel_err(got, z["prenorm_f64"]) <= 2e-5
+    assert rel_err(got, z["prenorm_f64"]) <= 2e-6  # measured 1.6e-7 (the reference's own fp32 run: 5.8e-8)
     with torch.no_grad():
         out = m(batches[0], False)
-    assert rel_err(out.cpu().numpy(), z["scores_f64"]) <= 5e-5  # scales carry fp32 rounding of the statistics
+    assert rel_err(out.cpu().numpy(), z["scores_f64"]) <= TOL  # measured 8.4e-7
 
 
 def test_fused_pretraining_equals_the_eleven_pass_protocol(golden_dir):
