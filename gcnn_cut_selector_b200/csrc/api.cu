@@ -1346,6 +1346,10 @@ int gcnn_set_option(gcnn_workspace* ws, const char* name, int value) {
     else if (!strcmp(name, "streams")) ws->use_streams = value != 0;
     else if (!strcmp(name, "fused")) ws->use_fused = value != 0;
     else if (!strcmp(name, "blocks")) ws->use_blocks = value != 0;
+    else if (!strcmp(name, "dp_timeout_ms")) {
+        if (!ws->dp) { set_error("dp_timeout_ms: no data-parallel state (gcnn_dp_create first)"); return GCNN_INVALID; }
+        dp_set_timeout_ms(ws->dp, value);
+    }
     else if (!strcmp(name, "precision")) {
         // 0: fp32-accurate (bf16x3 operands, six products per MMA; <= 1e-5 class).  1: bf16 MLP path, three products
         // (hi*hi + hi*lo + lo*hi of the two-piece split: bf16 MMAs, fp32 accumulation, ~16 operand bits) -- the mode

@@ -430,6 +430,7 @@ int dp_connect(DpState* s, const void* handles);
 void dp_destroy(DpState* s);
 float* dp_bucket(DpState* s, int parity);
 int dp_next_parity(const DpState* s);
+void dp_set_timeout_ms(DpState* s, long long ms);
 int dp_allreduce_adam(DpState* s, float* params, float* m, float* v, float lr_t, float beta1, float beta2, float eps,
                       float* sums_out, int32_t* err_flag, cudaStream_t st);
 

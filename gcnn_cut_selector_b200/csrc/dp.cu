@@ -65,16 +65,21 @@ dp_allreduce_adam_kernel(DpPeers peers, uint32_t* my_words, const int world, con
         __threadfence_system();
         st_release_sys(my_words + par, seq);
     }
-    // every CTA waits for every peer's word of this step (one polling thread per peer, then a CTA barrier)
+    // every CTA waits for every peer's word of this step (one polling thread per peer, then a CTA barrier); a CTA that
+    // gives up reports error bit 16 and leaves parameters and moments untouched
+    __shared__ int s_gave_up;
+    if (threadIdx.x == 0) s_gave_up = 0;
+    __syncthreads();
     if (threadIdx.x < world && threadIdx.x != rank) {
         const uint32_t* w = peers.word[threadIdx.x] + par;
         const long long t0 = clock64();
         while (ld_acquire_sys(w) != seq) {
-            if (clock64() - t0 > timeout_cycles) { atomicOr(err_flag, 16); break; }
+            if (clock64() - t0 > timeout_cycles) { atomicOr(err_flag, 16); s_gave_up = 1; break; }
             __nanosleep(32);
         }
     }
     __syncthreads();
+    if (s_gave_up) return;
     const int64_t boff = (int64_t)par * DP_BUCKET_FLOATS;
     const int64_t i = ((int64_t)blockIdx.x * DP_THREADS + threadIdx.x) * 4;  // the bucket is padded: float4 loads stay inside
     float4 x[WMAX];
@@ -120,6 +125,7 @@ struct DpState {
     char* block = nullptr;                 // [2 buckets][DP_BUCKET_FLOATS] floats, then 2 step words
     void* mapped[DP_MAX_RANKS] = {};       // peers' blocks as mapped here (own entry = block)
     uint32_t seq = 0;
+    long long timeout_ms = 10000;          // how long a rank waits for its peers' buckets before it sets error bit 16
     DpPeers peers{};
 };
 
@@ -169,6 +175,7 @@ void dp_destroy(DpState* s) {
 
 float* dp_bucket(DpState* s, int parity) { return (float*)s->block + (int64_t)(parity & 1) * DP_BUCKET_FLOATS; }
 int dp_next_parity(const DpState* s) { return (int)((s->seq + 1) & 1u); }
+void dp_set_timeout_ms(DpState* s, long long ms) { s->timeout_ms = ms < 1 ? 1 : ms; }
 
 int dp_allreduce_adam(DpState* s, float* params, float* m, float* v, float lr_t, float beta1, float beta2, float eps,
                       float* sums_out, int32_t* err_flag, cudaStream_t st) {
@@ -176,9 +183,9 @@ int dp_allreduce_adam(DpState* s, float* params, float* m, float* v, float lr_t,
     ++s->seq;
     const int64_t n = GCNN_N_TRAINABLE;
     ProfScope prof(PROF_ADAM, 4.0 * (double)n * (s->world + 6), st);
-    // ~10 s of SM clocks at the B200's 1.965 GHz boost (a fixed constant: querying the clock attribute costs a
-    // millisecond of host time per call)
-    const long long timeout = 10LL * 1965000000LL;
+    // SM clocks at the B200's 1.965 GHz boost (a fixed constant: querying the clock attribute costs a millisecond of host
+    // time per call); 10 s by default, option "dp_timeout_ms"
+    const long long timeout = s->timeout_ms * 1965000LL;
     uint32_t* words = (uint32_t*)((char*)s->block + sizeof(float) * 2 * DP_BUCKET_FLOATS);
     const unsigned grid = (unsigned)ceil_div(ceil_div(n, (int64_t)4), (int64_t)DP_THREADS);
 #define GCNN_DP_LAUNCH(W_)                                                                                                 \

@@ -112,7 +112,8 @@ int64_t gcnn_workspace_bytes(const gcnn_workspace* ws);
  * bf16x3 operands, six tensor-core products per MMA, scores and gradients within 1e-5 of the reference [default]; 1 =
  * bf16 MLP path: the three leading products (hi*hi + hi*lo + lo*hi) with fp32 accumulation, within 1e-2 -- the two
  * accuracy classes of BASELINE.json; 2 = one product per MMA, operands rounded to bf16: measured 1.2-1.3e-2, outside
- * both classes, a measurement point only).  Takes effect from the next call. */
+ * both classes, a measurement point only), "dp_timeout_ms" (how long the data-parallel exchange kernel waits for a peer's
+ * bucket before it sets error bit 16; default 10000; needs gcnn_dp_create).  Takes effect from the next call. */
 int gcnn_set_option(gcnn_workspace* ws, const char* name, int value);
 /* Synchronise `stream` and report deferred errors (GCNN_INVALID if any edge index was out of range). */
 int gcnn_check(gcnn_workspace* ws, void* stream);

@@ -7,7 +7,7 @@ peer-memory exchange (csrc/dp.cu) and once with NCCL all_reduce + Adam.  Checks:
 parameters after the peer path; (2) the peer path's parameters equal the fixed-rank-order emulation applied to the gathered
 buckets (bit-exact); (3) peer and NCCL paths agree to fp32 rounding; (4) the reported global mean loss is the mean over
 all cuts of all ranks; (5) the one-call staged path (gcnn_dp_train_step_staged_async) reports the same losses
-to fp32 rounding.  Prints one JSON line on rank 0.  Test infrastructure (not collected by pytest: needs torchrun)."""
+to fp32 rounding; (6) a rank whose peers never arrive gets an error after the configured timeout, not a hung GPU.  Prints one JSON line on rank 0.  Test infrastructure (not collected by pytest: needs torchrun)."""
 import json
 import os
 import sys
@@ -102,6 +102,26 @@ def main():
                           "emulation_bit_exact": emu_exact, "emulation_max_abs": emu_max}), flush=True)
     assert ok_peer and identical and diff < 1e-6 and emu_max < 1e-7 and staged_same
     assert all(abs(a - c) <= 1e-5 * abs(c) for a, c in zip(loss_peer, loss_nccl))
+    # (6) a peer that never arrives: rank 0 alone enqueues one more exchange with a 300 ms timeout.  Its kernel must give
+    # up, leave the parameters untouched and report error bit 16 as InvalidArgumentError instead of hanging the GPU.
+    dist.barrier()
+    timed_out = None
+    if rank == 0:
+        from gcnn_cut_selector_b200 import InvalidArgumentError
+        m_peer.set_option("dp_timeout_ms", 300)
+        before_lone = m_peer.flat_params.detach().clone()
+        t_peer._finish(False)
+        torch.cuda.synchronize()
+        assert torch.equal(before_lone, m_peer.flat_params.detach())
+        try:
+            m_peer.check_indices = True
+            m_peer._check_indices()
+            timed_out = False
+        except InvalidArgumentError as exc:
+            timed_out = "peer" in str(exc) or "16" in str(exc)
+        print(json.dumps({"lone_rank_times_out_with_error": timed_out}), flush=True)
+        assert timed_out
+    dist.barrier()
     dist.destroy_process_group()
 
 

@@ -423,7 +423,7 @@ def test_per_sample_counts_select_block_kernels_same_results(model, shape, n):
     _, s_generic = model.loss_and_grads(totals, batch[10])
     g_generic = model.flat_grads.clone()
     assert rel_err(s_blocks.cpu().numpy(), s_generic.cpu().numpy()) <= 2e-6
-    assert rel_err(g_blocks.cpu().numpy(), g_generic.cpu().numpy()) <= 2e-5
+    assert rel_err(g_blocks.cpu().numpy(), g_generic.cpu().numpy()) <= 1e-5
     # bit-reproducible, and switching the option off takes the generic path for the same inputs
     model.loss_and_grads(vectors, batch[10])
     assert torch.equal(g_blocks, model.flat_grads)
@@ -941,6 +941,16 @@ def test_graph_scoring_matches_eager_scoring(golden_dir):
             np.testing.assert_array_equal(m.score_host(h, graph=True), w)
     # (0 would mean the capture fell back to eager launches; the library leaves the reason in its error string)
     assert m._lib.gcnn_serve_graph_count(m._ws) >= 1, m._lib.gcnn_last_error().decode()
+    # more shapes than graph slots (8): the least recently used graphs are evicted, results stay exact
+    many = [HostBatch(batching.concat_samples(synth.make_samples("tiny", k, seed0=50 + k))) for k in range(1, 12)]
+    first = [m.score_host(h, graph=True).copy() for h in many]  # (sizes grow: every call also grows the workspace)
+    for h, w in zip(many, first):  # three calls in a row per shape: eager (new slot), captured, replayed
+        for rep in range(3):
+            np.testing.assert_array_equal(m.score_host(h, graph=True), w)
+    assert m._lib.gcnn_serve_graph_count(m._ws) == 8  # eleven shapes went through eight slots
+    for h, w in zip(many[::-1], first[::-1]):  # the last eight are cached, the first three come back eagerly
+        np.testing.assert_array_equal(m.score_host(h, graph=True), w)
+        assert rel_err(w, m.score_host(h)) <= 2e-6
     big = HostBatch(batching.concat_samples(synth.make_samples("setcov", 2, seed0=5)))  # grows the workspace
     w_big = m.score_host(big, graph=True).copy()
     assert rel_err(w_big, m.score_host(big)) <= 2e-6
