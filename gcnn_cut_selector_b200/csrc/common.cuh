@@ -178,6 +178,7 @@ int build_layout(const int32_t* keys, const int32_t* others, const float* feats,
                  int64_t n_other, const SortScratch& sc, int32_t* err_flag, int32_t* unsorted_flag, bool hint_sorted,
                  EdgeLayout& out, cudaStream_t st, const LayoutBlocks* blocks = nullptr);
 int64_t sort_hist_entries(int64_t E);
+int expand_row_ptr(const int32_t* ptr_dev, int64_t n_rows, int64_t n_edges, int32_t* rows_dev, cudaStream_t st);  // records.cu
 
 // ---- packed sample records (records.cu) ------------------------------------------------------------------------------
 constexpr int REC_SECTIONS = 10;

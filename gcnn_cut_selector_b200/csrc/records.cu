@@ -194,4 +194,26 @@ int assemble_records(const void* const* records_host, int64_t n_records, uint8_t
 
 int64_t record_desc_bytes() { return (int64_t)sizeof(RecordDesc); }
 
+// rows[e] = the row r with ptr[r] <= e < ptr[r + 1]: the row index of an edge list sorted by row, from its row pointer
+// (host batches that carry gcnn_batch::cons_row_ptr / cut_row_ptr: the row indices do not cross PCIe)
+__global__ void __launch_bounds__(REC_THREADS)
+expand_row_ptr_kernel(const int32_t* __restrict__ ptr, const int n_rows, const int64_t n_edges, int32_t* __restrict__ rows) {
+    const int64_t e = (int64_t)blockIdx.x * REC_THREADS + threadIdx.x;
+    if (e >= n_edges) return;
+    int lo = 0, hi = n_rows - 1;  // largest r in [0, n_rows) with ptr[r] <= e
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if ((int64_t)ptr[mid] <= e) lo = mid; else hi = mid - 1;
+    }
+    rows[e] = lo;
+}
+
+int expand_row_ptr(const int32_t* ptr_dev, int64_t n_rows, int64_t n_edges, int32_t* rows_dev, cudaStream_t st) {
+    if (n_edges <= 0 || n_rows <= 0) return GCNN_OK;
+    GCNN_LAUNCH_ORDERED(expand_row_ptr_kernel, (unsigned)ceil_div(n_edges, REC_THREADS), REC_THREADS, 0, st, ptr_dev,
+                        (int)n_rows, n_edges, rows_dev);
+    GCNN_LAUNCH_CHECK();
+    return GCNN_OK;
+}
+
 }  // namespace gcnn

@@ -570,7 +570,7 @@ class StagedRecords:
 class HostBatch:
     """A batch in pinned host memory plus its ``gcnn_batch`` of HOST pointers, for the ``*_host`` entry points."""
 
-    def __init__(self, batch11):
+    def __init__(self, batch11, row_pointers: bool = True):
         (cons, cons_ei, cons_ef, var, cut, cut_ei, cut_ef, n_cons, n_vars, n_cuts, targets) = batch11
         pin = lambda a, dt: torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=dt))).pin_memory()
         self.tensors = [pin(cons, np.float32), pin(cons_ei, np.int32), pin(cons_ef, np.float32), pin(var, np.float32),
@@ -582,6 +582,16 @@ class HostBatch:
         self.batch = Batch(t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(), t[4].data_ptr(),
                            t[5].data_ptr(), t[6].data_ptr(), nc, nv, nk, t[1].shape[1], t[5].shape[1],
                            _sorted_flags(t[1], t[5]))
+        # sorted edge lists travel as row pointers: 4 of their 12 bytes per edge stay on the host (gcnn_batch::*_row_ptr)
+        self.row_ptrs = [None, None]
+        for i, (ei, n_rows, flag) in enumerate(((t[1], nc, _lib.BATCH_CONS_EDGES_SORTED), (t[5], nk, _lib.BATCH_CUT_EDGES_SORTED))):
+            if row_pointers and (self.batch.flags & flag) and n_rows > 0 and ei.shape[1] > 0:
+                rp = np.searchsorted(ei[0].numpy(), np.arange(n_rows + 1, dtype=np.int64), side="left").astype(np.int32)
+                self.row_ptrs[i] = torch.from_numpy(rp).pin_memory()
+        if self.row_ptrs[0] is not None:
+            self.batch.cons_row_ptr = self.row_ptrs[0].data_ptr()
+        if self.row_ptrs[1] is not None:
+            self.batch.cut_row_ptr = self.row_ptrs[1].data_ptr()
         self.counts = _sample_counts(n_cons, n_vars, n_cuts)
         if self.counts is not None:
             b = self.batch
@@ -589,3 +599,6 @@ class HostBatch:
             b.n_samples = self.counts[0].shape[0]
         self.n_graphs = int(np.size(n_cons))
         self.h2d_bytes = sum(x.numel() * x.element_size() for x in self.tensors) + self.targets.numel() * 4
+        for rp, ei in zip(self.row_ptrs, (t[1], t[5])):  # a list with a row pointer: pointer + columns instead of [2, E]
+            if rp is not None:
+                self.h2d_bytes += rp.numel() * 4 - ei.shape[1] * 4

@@ -74,6 +74,13 @@ typedef struct gcnn_batch {
     const int32_t* sample_n_vars;
     const int32_t* sample_n_cuts;
     int64_t n_samples;
+    /* HOST batches only (gcnn_stage_host_batch and the *_host entry points; ignored elsewhere), optional: row pointers
+     * of edge lists sorted by row 0 -- n_cons + 1 / n_cuts + 1 int32 with ptr[r] = index of the first edge of row r and
+     * ptr[n] = the number of edges.  Given together with the matching *_EDGES_SORTED flag, row 0 of that index tensor is
+     * not copied to the device (4 of the 12 bytes per edge stay on the host): the library copies the pointer and
+     * expands it there, bit-identical to copying the row indices.  NULL = copy row 0 as it is. */
+    const int32_t* cons_row_ptr;
+    const int32_t* cut_row_ptr;
 } gcnn_batch;
 
 #define GCNN_BATCH_CONS_EDGES_SORTED 1

@@ -683,6 +683,33 @@ def test_prefetching_host_path_matches_synchronous_path(golden_dir):
     np.testing.assert_array_equal(b.score_staged(0), a.score_host(ha[1]))
 
 
+def test_row_pointer_host_batches_are_bit_identical(golden_dir):
+    """A host batch whose sorted edge lists travel as row pointer + columns (gcnn_batch::cons_row_ptr / cut_row_ptr, 8 instead
+    of 12 bytes per edge over PCIe) gives the same scores, losses and parameters, bit for bit, as one that copies [2, E];
+    an unsorted list keeps the full copy; a pointer that does not span the list is refused."""
+    from gcnn_cut_selector_b200 import GCNN, HostBatch, InvalidArgumentError
+    path = os.path.join(golden_dir, "state_stream.pkl")
+    batches = [list(batching.concat_samples(synth.make_samples("setcov", 2 + i, seed0=30 + i))) for i in range(2)]
+    perm = np.random.default_rng(0).permutation(batches[1][5].shape[1])  # second batch: cut edges in random order
+    batches[1][5], batches[1][6] = batches[1][5][:, perm], batches[1][6][perm]
+    a, b = GCNN(device="cuda:0", seed=3), GCNN(device="cuda:0", seed=4)
+    a.restore_state(path); b.restore_state(path)
+    ha = [HostBatch(tuple(x), row_pointers=False) for x in batches]
+    hb = [HostBatch(tuple(x)) for x in batches]
+    assert hb[0].row_ptrs[0] is not None and hb[0].row_ptrs[1] is not None and ha[0].row_ptrs == [None, None]
+    assert hb[1].row_ptrs[0] is not None and hb[1].row_ptrs[1] is None
+    assert hb[0].h2d_bytes == ha[0].h2d_bytes - 4 * (batches[0][1].shape[1] + batches[0][5].shape[1]) + 4 * (
+        hb[0].batch.n_cons + 1 + hb[0].batch.n_cuts + 1)
+    for x, y in zip(ha, hb):
+        np.testing.assert_array_equal(a.score_host(x), b.score_host(y))
+        assert a.train_step_host(x, 1e-3) == b.train_step_host(y, 1e-3)
+    torch.testing.assert_close(a.flat_params.detach(), b.flat_params.detach(), rtol=0, atol=0)
+    bad = HostBatch(tuple(batches[0]))
+    bad.row_ptrs[0][-1] -= 1
+    with pytest.raises(InvalidArgumentError):
+        b.score_host(bad)
+
+
 # ---- full BASELINE sizes: size-independent properties -----------------------------------------------------------------
 @pytest.mark.parametrize("n_graphs", [32, 128])  # BASELINE config 2, and config 4's per-GPU share at 8 GPUs (3.2 M edges)
 def test_config2_properties(model, n_graphs):
