@@ -158,6 +158,7 @@ class GCNN:
         with torch.cuda.device(self.device):  # the workspace (streams, events, arena) lives on the model's device
             check(self._lib.gcnn_workspace_create(C.byref(ws)))
         self._ws = ws
+        self._params_seen, self._params_epoch = None, 0
         self._prenorm_layers = self._make_prenorm_layers()
         self.call = self._call  # re-assignable like ``model.call = tf.function(model.call, ...)`` (model_trainer.py:144)
 
@@ -285,7 +286,25 @@ class GCNN:
         check(self._lib.gcnn_set_option(self._ws, name.encode(), int(value)))
 
     def _stream(self):
+        self._announce_params()  # every library call that takes a stream also reads the parameters
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _announce_params(self):
+        """Option "params_epoch" (include/gcnn_b200.h): a new epoch whenever the parameter tensor was written through
+        torch (its version counter counts in-place writes, also through ``trainable_variables`` views: ``restore_state``,
+        ``v.assign``-style copies, an external optimiser) or replaced, so the library re-packs its weight images only
+        then -- scoring with frozen weights (model_benchmarker.py:91-106) skips the re-pack.  The library's own update
+        calls invalidate the images themselves; ``apply_gradients`` (gcnn_adam_step, no workspace) bumps the epoch here.
+        Writes that bypass torch (a raw pointer handed to another library) need ``params_changed()``."""
+        seen = (self.flat_params.data_ptr(), self.flat_params._version)
+        if seen != self._params_seen:
+            self._params_seen = seen
+            self._params_epoch = self._params_epoch % (2 ** 31 - 2) + 1
+            check(self._lib.gcnn_set_option(self._ws, b"params_epoch", self._params_epoch))
+
+    def params_changed(self):
+        """Tell the library that ``flat_params`` was written behind torch's back (see ``_announce_params``)."""
+        self._params_seen = None
 
     def _activation_stamp(self) -> int:
         return int(self._lib.gcnn_activation_stamp(self._ws))
@@ -371,6 +390,7 @@ class GCNN:
                                            self.adam_m.data_ptr(), self.adam_v.data_ptr(), _lib.N_TRAINABLE, lr, beta1,
                                            beta2, eps, self.adam_step + 1, div, self._stream()))
         self.adam_step += 1  # only a step that was enqueued counts (Adam's bias correction depends on it)
+        self._params_seen = None  # gcnn_adam_step wrote the parameters without the workspace knowing
 
     def train_step(self, inputs, targets, lr: float):
         """One optimisation step on device-resident or host inputs; returns the mean loss as a device tensor."""

@@ -120,7 +120,12 @@ int64_t gcnn_workspace_bytes(const gcnn_workspace* ws);
  * bf16 MLP path: the three leading products (hi*hi + hi*lo + lo*hi) with fp32 accumulation, within 1e-2 -- the two
  * accuracy classes of BASELINE.json; 2 = one product per MMA, operands rounded to bf16: measured 1.2-1.3e-2, outside
  * both classes, a measurement point only), "dp_timeout_ms" (how long the data-parallel exchange kernel waits for a peer's
- * bucket before it sets error bit 16; default 10000; needs gcnn_dp_create).  Takes effect from the next call. */
+ * bucket before it sets error bit 16; default 10000; needs gcnn_dp_create), "params_epoch" (e > 0: the caller's promise
+ * that the parameter block passed to later calls changes only when a NEW epoch is announced or through this workspace's
+ * own update calls, gcnn_train_step_* / gcnn_dp_* -- NOT gcnn_adam_step, which has no workspace; the pre-split weight
+ * images the chains read are then packed once per epoch instead of once per forward, ~10 us off every scoring call with
+ * frozen weights, model_benchmarker.py:91-106; 0, the default, withdraws the promise: every forward re-packs).
+ * Takes effect from the next call. */
 int gcnn_set_option(gcnn_workspace* ws, const char* name, int value);
 /* Synchronise `stream` and report deferred errors (GCNN_INVALID if any edge index was out of range). */
 int gcnn_check(gcnn_workspace* ws, void* stream);

@@ -710,6 +710,65 @@ def test_row_pointer_host_batches_are_bit_identical(golden_dir):
         b.score_host(bad)
 
 
+def test_params_epoch_reuses_and_refreshes_weight_images(golden_dir):
+    """Option "params_epoch": scoring with frozen weights packs the weight images once (one launch fewer per call); every
+    way the parameters can change -- a torch write, restore_state, the library's fused step, apply_gradients, a raw write
+    announced with params_changed() -- is followed by scores that equal, bit for bit, those of a fresh model holding the
+    same parameters (eager and graph-replayed scoring alike)."""
+    from gcnn_cut_selector_b200 import GCNN, HostBatch
+    path = os.path.join(golden_dir, "state_stream.pkl")
+    batch = batching.concat_samples(synth.make_samples("setcov", 2, seed0=41))
+    hb, hb2 = HostBatch(batch), HostBatch(batch)
+    m = GCNN(device="cuda:0", seed=3)
+    m.restore_state(path)
+
+    def fresh_scores():
+        f = GCNN(device="cuda:0", seed=9)
+        with torch.no_grad():
+            f.flat_params.copy_(m.flat_params)
+            f.flat_prenorm.copy_(m.flat_prenorm)
+        return f.score_host(hb2).copy()
+
+    def check_both():
+        want = fresh_scores()
+        np.testing.assert_array_equal(m.score_host(hb), want)
+        np.testing.assert_array_equal(m.score_host(hb, graph=True), want)
+
+    launches = []
+    for _ in range(3):
+        n0 = m._lib.gcnn_kernel_launches()
+        m.score_host(hb)
+        launches.append(m._lib.gcnn_kernel_launches() - n0)
+    assert launches[1] == launches[0] - 1 and launches[2] == launches[1]  # the pack ran once
+    for _ in range(3):
+        m.score_host(hb, graph=True)
+    assert m._lib.gcnn_serve_graph_count(m._ws) >= 1
+    check_both()
+    with torch.no_grad():
+        m.flat_params.mul_(1.01)  # a torch write (version counter)
+    check_both()
+    with torch.no_grad():
+        m.trainable_variables[3].add_(0.01)  # ... through a view
+    check_both()
+    m.train_step_host(hb, 1e-3)  # the library's own Adam
+    check_both()
+    m.train_step(batching.model_inputs(batch, per_sample_counts=True), batch[10], 1e-3)  # gcnn_adam_step via apply_gradients
+    check_both()
+    m.restore_state(path)
+    check_both()
+    n0 = m._lib.gcnn_kernel_launches()
+    m.score_host(hb)  # (frozen since check_both: no pack)
+    m.params_changed()
+    n1 = m._lib.gcnn_kernel_launches()
+    m.score_host(hb)
+    assert m._lib.gcnn_kernel_launches() - n1 == (n1 - n0) + 1  # announced raw write: packed again
+    m.set_option("params_epoch", 0)  # promise withdrawn: every call packs
+    m._announce_params = lambda: None
+    n2 = m._lib.gcnn_kernel_launches()
+    m.score_host(hb)
+    assert m._lib.gcnn_kernel_launches() - n2 == (n1 - n0) + 1
+
+
 # ---- full BASELINE sizes: size-independent properties -----------------------------------------------------------------
 @pytest.mark.parametrize("n_graphs", [32, 128])  # BASELINE config 2, and config 4's per-GPU share at 8 GPUs (3.2 M edges)
 def test_config2_properties(model, n_graphs):
