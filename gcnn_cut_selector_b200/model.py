@@ -590,7 +590,9 @@ class StagedRecords:
 class HostBatch:
     """A batch in pinned host memory plus its ``gcnn_batch`` of HOST pointers, for the ``*_host`` entry points."""
 
-    def __init__(self, batch11, row_pointers: bool = True):
+    ROW_POINTER_MIN_EDGES = 1 << 17  # below this the two extra copies + expansions cost more host time than the bytes save
+
+    def __init__(self, batch11, row_pointers: bool | None = None):
         (cons, cons_ei, cons_ef, var, cut, cut_ei, cut_ef, n_cons, n_vars, n_cuts, targets) = batch11
         pin = lambda a, dt: torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=dt))).pin_memory()
         self.tensors = [pin(cons, np.float32), pin(cons_ei, np.int32), pin(cons_ef, np.float32), pin(var, np.float32),
@@ -602,10 +604,13 @@ class HostBatch:
         self.batch = Batch(t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(), t[4].data_ptr(),
                            t[5].data_ptr(), t[6].data_ptr(), nc, nv, nk, t[1].shape[1], t[5].shape[1],
                            _sorted_flags(t[1], t[5]))
-        # sorted edge lists travel as row pointers: 4 of their 12 bytes per edge stay on the host (gcnn_batch::*_row_ptr)
+        # sorted edge lists travel as row pointers: 4 of their 12 bytes per edge stay on the host (gcnn_batch::*_row_ptr).
+        # row_pointers=None: only for large lists -- measured on one box (profiles/r2_ab_host_paths.json): a 32-graph
+        # set-cover step 0.436 -> 0.428 ms end to end, but +25-30 us on a single-graph scoring / training call
         self.row_ptrs = [None, None]
         for i, (ei, n_rows, flag) in enumerate(((t[1], nc, _lib.BATCH_CONS_EDGES_SORTED), (t[5], nk, _lib.BATCH_CUT_EDGES_SORTED))):
-            if row_pointers and (self.batch.flags & flag) and n_rows > 0 and ei.shape[1] > 0:
+            want = ei.shape[1] >= self.ROW_POINTER_MIN_EDGES if row_pointers is None else bool(row_pointers)
+            if want and (self.batch.flags & flag) and n_rows > 0 and ei.shape[1] > 0:
                 rp = np.searchsorted(ei[0].numpy(), np.arange(n_rows + 1, dtype=np.int64), side="left").astype(np.int32)
                 self.row_ptrs[i] = torch.from_numpy(rp).pin_memory()
         if self.row_ptrs[0] is not None:

@@ -695,7 +695,8 @@ def test_row_pointer_host_batches_are_bit_identical(golden_dir):
     a, b = GCNN(device="cuda:0", seed=3), GCNN(device="cuda:0", seed=4)
     a.restore_state(path); b.restore_state(path)
     ha = [HostBatch(tuple(x), row_pointers=False) for x in batches]
-    hb = [HostBatch(tuple(x)) for x in batches]
+    hb = [HostBatch(tuple(x), row_pointers=True) for x in batches]
+    assert HostBatch(tuple(batches[0])).row_ptrs == [None, None]  # default: only lists of >= 128 k edges
     assert hb[0].row_ptrs[0] is not None and hb[0].row_ptrs[1] is not None and ha[0].row_ptrs == [None, None]
     assert hb[1].row_ptrs[0] is not None and hb[1].row_ptrs[1] is None
     assert hb[0].h2d_bytes == ha[0].h2d_bytes - 4 * (batches[0][1].shape[1] + batches[0][5].shape[1]) + 4 * (
@@ -704,7 +705,7 @@ def test_row_pointer_host_batches_are_bit_identical(golden_dir):
         np.testing.assert_array_equal(a.score_host(x), b.score_host(y))
         assert a.train_step_host(x, 1e-3) == b.train_step_host(y, 1e-3)
     torch.testing.assert_close(a.flat_params.detach(), b.flat_params.detach(), rtol=0, atol=0)
-    bad = HostBatch(tuple(batches[0]))
+    bad = HostBatch(tuple(batches[0]), row_pointers=True)
     bad.row_ptrs[0][-1] -= 1
     with pytest.raises(InvalidArgumentError):
         b.score_host(bad)
