@@ -125,6 +125,10 @@ struct gcnn_workspace {
     int use_edge_masks = 1;  // forward edge kernel records per-edge ReLU masks, the backward reads them  // forward chains on bf16x3 tiles (node_fwd.cu) instead of 3xTF32 (node_tc.cu)
     // set by gcnn_forward_backward around a fused step: head layer 2, the loss seed and its backward are ONE launch
     int head_fused = 0, head_parts = 0;
+    int head_chain_ok = 1;                     // option "head_in_chain"
+    int head_in_chain = 0;                     // the last forward chain computed the scores (and, in training, the loss seed)
+    const float* head_targets = nullptr;       // set by gcnn_forward_backward around its forward: targets / seed scale for
+    float head_scale = 0.f;                    // the head fused into the last chain
     int count_before_loss = 0;  // also write the batch's cut count (as a float) just before the loss sum
     float* loss_out = nullptr;
     // stats
@@ -547,11 +551,22 @@ static int forward_convs_fused(gcnn_workspace* ws, const float* p, const float* 
         c.C = keep ? a.C : nullptr; c.U1 = keep ? a.U1 : nullptr; c.Y = a.Y; c.Pn = next_out[i];
         c.M = n_recv[i];
         c.bf16_mlp = ws->bf16_mlp;
+        if (i == 2 && bf16 && nk > 0 && stop_layer < 0 && ws->head_chain_ok) {
+            // the head's Dense(1) -- and in training the MSE seed and its backward -- ride in this chain's last epilogue
+            c.head_w = p + P.Wh2; c.head_b = p + P.bh2;
+            c.scores = scores_out ? scores_out : ws->scores;
+            if (ws->head_fused) {
+                c.targets = ws->head_targets; c.seed_scale = ws->head_scale;
+                c.dg_pre = ws->t_dg; c.head_partials = ws->partials[0];
+                ws->head_parts = (int)ceil_div(nk, CHAIN_TILE_ROWS);
+            }
+            ws->head_in_chain = 1;
+        }
         GCNN_TRY(bf16 ? tc_conv_forward16(c, st) : tc_conv_forward(c, st));
         if (stop_layer == 6 + 2 * i) return wait_all_layouts();
     }
     GCNN_TRY(wait_all_layouts());  // the backward needs the cut by-variable layout
-    if (!ws->head_fused)
+    if (!ws->head_fused && !ws->head_in_chain)
         GCNN_TRY(head2_forward(ws->g1, p + P.Wh2, p + P.bh2, scores_out ? scores_out : ws->scores, nk, st));
     return GCNN_OK;
 }
@@ -594,6 +609,7 @@ static int forward_impl(gcnn_workspace* ws, const float* p, const float* pn, con
     const int64_t nc = b->n_cons, nv = b->n_vars, nk = b->n_cuts, ec = b->n_cons_edges, ek = b->n_cut_edges;
     const bool images_ready = ws->images_ready != 0;  // the caller ran ensure_images itself (outside a stream capture)
     ws->images_ready = 0;
+    ws->head_in_chain = 0;
 
     cudaStream_t s1 = aux_stream(ws, 0, st), s2 = aux_stream(ws, 1, st);
     // block structure first: the offset arrays are read by kernels on every stream forked below
@@ -1427,6 +1443,7 @@ int gcnn_set_option(gcnn_workspace* ws, const char* name, int value) {
     else if (!strcmp(name, "fused_backward")) ws->use_fused_bwd = value != 0;
     else if (!strcmp(name, "bf16_forward")) ws->use_bf16_fwd = value != 0;
     else if (!strcmp(name, "count_before_loss")) ws->count_before_loss = value != 0;
+    else if (!strcmp(name, "head_in_chain")) ws->head_chain_ok = value != 0;  // A/B: 0 = head layer 2 / loss seed in their own launch
     else if (!strcmp(name, "params_epoch")) {  // see ensure_images; 0 withdraws the promise
         if (value < 0) { set_error("params_epoch must be >= 0"); return GCNN_INVALID; }
         ws->params_epoch = value;
@@ -1641,12 +1658,15 @@ int gcnn_forward_backward(gcnn_workspace* ws, const float* params, const float* 
     const bool fuse_head = ws->use_tc && ws->use_fused && ws->use_fused_bwd;
     ws->head_fused = fuse_head ? 1 : 0;
     ws->loss_out = loss_out;
+    ws->head_targets = targets;
+    ws->head_scale = seed_scale;
     int rc = forward_impl(ws, params, prenorm, batch, scores, -1, st, staged_blocks_for(ws, batch));
     ws->last = *batch;
     ws->have_activations = 1;
     ++ws->act_stamp;
     if (rc == GCNN_OK) {
-        if (fuse_head)
+        if (fuse_head && ws->head_in_chain) {}  // scores, t_dg and the partials came out of the last forward chain
+        else if (fuse_head)
             rc = head_loss(ws->g1, params + P.Wh2, params + P.bh2, targets, seed_scale, scores, ws->t_dg, ws->partials[0],
                            &ws->head_parts, batch->n_cuts, st);
         else
@@ -1658,6 +1678,7 @@ int gcnn_forward_backward(gcnn_workspace* ws, const float* params, const float* 
     }
     if (rc == GCNN_OK) rc = backward_impl(ws, params, prenorm, batch, ws->d_scores, grads_out, st);
     ws->head_fused = 0;
+    ws->head_targets = nullptr;
     return rc;
 }
 

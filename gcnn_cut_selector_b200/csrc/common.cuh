@@ -329,7 +329,18 @@ struct ConvFwdArgs {          // fused node chain of one convolution (tc_conv_fo
     float *C, *U1, *Y, *Pn;   // outputs; C and U1 may be nullptr (inference)
     int64_t M;
     int bf16_mlp;             // option "precision": 1 = three bf16 products per MMA instead of six, 2 = one (bf16x3 chains only)
+    // bf16x3 chain only, last convolution: the head's second layer (Dense(1), model.py:208) on the S3 result, and in
+    // training the MSE seed (model_trainer.py:271) and that layer's backward -- what head2_forward / head_loss do in a
+    // launch of their own.  head_w == nullptr: not fused.
+    const float *head_w, *head_b;  // [64], [1]
+    float* scores;                 // [M]
+    const float* targets;          // [M] or nullptr (inference: scores only)
+    float seed_scale;              // d_score = 2 (p - y) seed_scale
+    float* dg_pre;                 // [M, 64] gradient w.r.t. the pre-activation of head layer 1
+    float* head_partials;          // [CTAs][64 + 3]: dw | db | rows | squared error
 };
+constexpr int HEAD_PART_FLOATS = D + 3;
+constexpr int CHAIN_TILE_ROWS = 128;  // nodes per forward-chain CTA (= TC_ROWS, tc_common.cuh): one head partial each
 int tc_conv_forward(const ConvFwdArgs& a, cudaStream_t st);
 int tc_conv_forward16(const ConvFwdArgs& a, cudaStream_t st);  // bf16x3 variant (node_fwd.cu): img_* are bf16x3 T images
 struct ConvBwdArgs {          // fused backward node chain of one convolution (tc_conv_backward, node_bwd.cu)

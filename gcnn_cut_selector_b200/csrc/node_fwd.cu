@@ -21,6 +21,7 @@
 
 namespace gcnn {
 
+static_assert(CHAIN_TILE_ROWS == TC_ROWS, "one head partial per forward-chain CTA");
 constexpr uint32_t FWD_SMEM = 2 * T16_BYTES + 3 * W16_BYTES + CWARPS * PATCH + 1024;
 
 // y[i] = v[i] + scale * bias[16 ch + i] (+ ReLU): bias vector in shared memory, broadcast reads
@@ -46,6 +47,9 @@ tc_conv_forward16_kernel(const ConvFwdArgs a) {
     __shared__ __align__(8) uint64_t bars[5];  // 0: MMAs of the stage, 1: tiles ready, 2..4: weight slots
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(16) float bias_s[4][D];
+    __shared__ __align__(16) float head_w_s[D];
+    __shared__ float head_dot[4][TC_ROWS];      // per column chunk: a row's partial dot product with the head's weights
+    __shared__ float head_col[4][D + 4];        // per row quadrant: column sums of g * ds (+ ds, rows, d^2 in [D .. D+2])
     const int tid = threadIdx.x, warp = warp_index(), lane = tid & 31;
     const int64_t row0 = (int64_t)blockIdx.x * TC_ROWS;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -58,6 +62,7 @@ tc_conv_forward16_kernel(const ConvFwdArgs a) {
     const uint32_t bar_d = smem_u32(&bars[0]), bar_ready = smem_u32(&bars[1]);
     const uint32_t wbar0 = smem_u32(&bars[2]), wbar1 = smem_u32(&bars[3]), wbar2 = smem_u32(&bars[4]);
     const bool has_next = a.img_n != nullptr;
+    const bool head = has_next && a.head_w != nullptr;
 
     if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), 64);
     if (tid == 0) {
@@ -119,6 +124,7 @@ tc_conv_forward16_kernel(const ConvFwdArgs a) {
     {   // all four bias vectors up front
         const float* bsrc = tid < D ? a.bias_f : (tid < 2 * D ? a.bias_o1 : (tid < 3 * D ? a.bias_o2 : a.bias_n));
         if (tid < 4 * D) bias_s[tid >> 6][tid & 63] = bsrc ? bsrc[tid & 63] : 0.f;
+        if (head && tid >= 4 * D && tid < 5 * D) head_w_s[tid - 4 * D] = a.head_w[tid - 4 * D];
     }
     const int q = warp & 3, ch = warp >> 2;
     const int r_own = q * 32 + lane;
@@ -173,6 +179,48 @@ tc_conv_forward16_kernel(const ConvFwdArgs a) {
         if (a.relu_n) bias_act<true>(v, bias_s[3], ch, 1.f);
         else bias_act<false>(v, bias_s[3], ch, 1.f);
         warp_store_block(patch, v, a.Pn + wrow0 * D + ch * NCOL, rows_valid, lane, StoreIdentity());
+        if (head) {
+            // head layer 2 (model.py:208): score = g . w + b.  A thread holds 16 of its row's 64 activations: sequential
+            // partial dot product, the four column chunks of a row meet in shared memory and every thread of the row adds
+            // them in chunk order -- one fixed order for training and inference.
+            float dot = 0.f;
+#pragma unroll
+            for (int i = 0; i < NCOL; ++i) dot = fmaf(v[i], head_w_s[ch * NCOL + i], dot);
+            head_dot[ch][r_own] = dot;
+            compute_barrier();
+            const bool row_ok = m_own < a.M;
+            const float score = ((head_dot[0][r_own] + head_dot[1][r_own]) + (head_dot[2][r_own] + head_dot[3][r_own])) + a.head_b[0];
+            if (row_ok && ch == 0) a.scores[m_own] = score;
+            if (a.targets) {
+                // MeanSquaredError seed (model_trainer.py:271) and the backward of head layer 2: dg_pre = ds w 1[g > 0],
+                // per-CTA partials of dw = sum_rows g ds, db = sum ds, the row count and the squared error
+                const float d = row_ok ? score - a.targets[m_own] : 0.f;
+                const float ds = 2.f * d * a.seed_scale;
+                float t[NCOL];
+#pragma unroll
+                for (int i = 0; i < NCOL; ++i) {
+                    t[i] = v[i] * ds;                                      // (g = 0 on rows beyond M: their ds is 0 too)
+                    v[i] = v[i] > 0.f ? ds * head_w_s[ch * NCOL + i] : 0.f;
+                }
+                warp_store_block(patch, v, a.dg_pre + wrow0 * D + ch * NCOL, rows_valid, lane, StoreIdentity());
+                const float cs = warp_colsum(t, lane);  // lanes l, l ^ 1: sum over the warp's rows of column (l >> 1) & 15
+                if ((lane & 1) == 0) head_col[q][ch * NCOL + (lane >> 1)] = cs;
+                if (ch == 0) {  // one thread per row: ds, rows, d^2 over the warp's 32 rows (fixed shuffle tree)
+                    float s0 = ds, s1 = row_ok ? 1.f : 0.f, s2 = d * d;
+#pragma unroll
+                    for (int o = 16; o >= 1; o >>= 1) {
+                        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                    }
+                    if (lane == 0) { head_col[q][D] = s0; head_col[q][D + 1] = s1; head_col[q][D + 2] = s2; }
+                }
+                compute_barrier();
+                if (tid < HEAD_PART_FLOATS)
+                    a.head_partials[(int64_t)blockIdx.x * HEAD_PART_FLOATS + tid] =
+                        (head_col[0][tid] + head_col[1][tid]) + (head_col[2][tid] + head_col[3][tid]);
+            }
+        }
     }
     tc_fence_before();
     __syncthreads();  // every warp, the MMA warp included

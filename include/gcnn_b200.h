@@ -125,6 +125,8 @@ int64_t gcnn_workspace_bytes(const gcnn_workspace* ws);
  * own update calls, gcnn_train_step_* / gcnn_dp_* -- NOT gcnn_adam_step, which has no workspace; the pre-split weight
  * images the chains read are then packed once per epoch instead of once per forward, ~10 us off every scoring call with
  * frozen weights, model_benchmarker.py:91-106; 0, the default, withdraws the promise: every forward re-packs).
+ * "head_in_chain" (default 1: the head's Dense(1), and in training the MSE seed and that layer's backward, run in the
+ * last epilogue of the cut convolution's forward chain; 0: in a launch of their own -- an A/B switch).
  * Takes effect from the next call. */
 int gcnn_set_option(gcnn_workspace* ws, const char* name, int value);
 /* Synchronise `stream` and report deferred errors (GCNN_INVALID if any edge index was out of range). */
