@@ -35,10 +35,12 @@ class Batch(C.Structure):
                 ("cut_edge_feats", C.c_void_p), ("n_cons", C.c_int64), ("n_vars", C.c_int64), ("n_cuts", C.c_int64),
                 ("n_cons_edges", C.c_int64), ("n_cut_edges", C.c_int64), ("flags", C.c_int64),
                 ("sample_n_cons", C.c_void_p), ("sample_n_vars", C.c_void_p), ("sample_n_cuts", C.c_void_p),
-                ("n_samples", C.c_int64), ("cons_row_ptr", C.c_void_p), ("cut_row_ptr", C.c_void_p)]
+                ("n_samples", C.c_int64), ("cons_row_ptr", C.c_void_p), ("cut_row_ptr", C.c_void_p),
+                ("cons_col16", C.c_void_p), ("cut_col16", C.c_void_p)]
 
 
 BATCH_CONS_EDGES_SORTED, BATCH_CUT_EDGES_SORTED = 1, 2
+MAX_RECORDS = 4096  # samples per batch the staging slots keep block offsets for (csrc/common.cuh)
 
 _P, _I64, _I, _F = C.c_void_p, C.c_int64, C.c_int, C.c_float
 _BP = C.POINTER(Batch)

@@ -139,6 +139,7 @@ struct gcnn_workspace {
         float *cons = nullptr, *cef = nullptr, *var = nullptr, *cut = nullptr, *kef = nullptr, *targets = nullptr;
         int32_t *cei = nullptr, *kei = nullptr;
         int32_t *crp = nullptr, *krp = nullptr;  // row pointers of a host batch's sorted edge lists (gcnn_batch::*_row_ptr)
+        uint16_t *c16 = nullptr, *k16 = nullptr;  // ... and their sample-local column indices (gcnn_batch::*_col16)
         uint8_t* raw = nullptr;          // packed records as copied from the host (gcnn_stage_records)
         int64_t raw_cap = 0;
         RecordDesc* descs = nullptr;     // [MAX_RECORDS] device
@@ -338,6 +339,7 @@ struct StagePtrs {
     RecordDesc* descs;
     int32_t* blocks;  // [3][MAX_RECORDS + 1] node offsets of the batch's samples (constraints, variables, cuts)
     int32_t *crp, *krp;  // row pointers of a host batch's sorted edge lists (expanded into cei / kei on the device)
+    uint16_t *c16, *k16; // sample-local column indices of the same lists
 };
 static size_t carve_stage(StagePtrs out[2], char* base, const Caps& c) {
     Carver cv{base};
@@ -359,6 +361,8 @@ static size_t carve_stage(StagePtrs out[2], char* base, const Caps& c) {
         g.blocks = cv.take<int32_t>(3 * (MAX_RECORDS + 1));
         g.crp = cv.take<int32_t>(nc + 1);
         g.krp = cv.take<int32_t>(nk + 1);
+        g.c16 = cv.take<uint16_t>(c.ec);
+        g.k16 = cv.take<uint16_t>(c.ek);
     }
     return cv.off + 256;
 }
@@ -1092,12 +1096,22 @@ static int stage_batch(gcnn_workspace* ws, int slot, const gcnn_batch* hb, const
     cudaStream_t cs = ws->copy_st;
     if (g.valid) GCNN_CUDA_TRY(cudaStreamWaitEvent(cs, g.consumed, 0));
     if (g.valid) GCNN_CUDA_TRY(cudaEventSynchronize(g.staged));  // the previous copy out of blocks_host is done
-    // an index tensor [2, E] whose row 0 is sorted and comes with its row pointer travels as pointer + columns
+    // the block structure first: the local column indices below are resolved against it on the device
+    const int32_t* const counts[3] = {hb->sample_n_cons, hb->sample_n_vars, hb->sample_n_cuts};
+    const int64_t totals[3] = {hb->n_cons, hb->n_vars, hb->n_cuts};
+    GCNN_TRY(stage_blocks(ws, g, counts, hb->n_samples, totals, cs));
+    // an index tensor [2, E] whose row 0 is sorted and comes with its row pointer travels as pointer + columns, the
+    // columns as uint16 local to the sample when the caller provides them (left: 0 = constraints, 2 = cuts)
     auto edge_inds = [&](int32_t* dst, const int32_t* src, int64_t E, const int32_t* row_ptr, int32_t* ptr_dev, int64_t n_rows,
-                         bool sorted) -> int {
+                         bool sorted, const uint16_t* col16, uint16_t* col16_dev, int left) -> int {
         if (row_ptr && sorted && n_rows > 0 && E > 0) {
             if (row_ptr[0] != 0 || (int64_t)row_ptr[n_rows] != E) { set_error("row pointer does not span the edge list"); return GCNN_INVALID; }
             GCNN_TRY(h2d(ptr_dev, row_ptr, sizeof(int32_t) * (size_t)(n_rows + 1), cs));
+            if (col16) {
+                if (g.blk.n <= 0) { set_error("local column indices need valid per-sample counts"); return GCNN_INVALID; }
+                GCNN_TRY(h2d(col16_dev, col16, sizeof(uint16_t) * (size_t)E, cs));
+                return expand_row_ptr(ptr_dev, n_rows, E, dst, cs, col16_dev, g.blk.off[left], g.blk.off[1], g.blk.n, dst + E);
+            }
             GCNN_TRY(h2d(dst + E, src + E, sizeof(int32_t) * (size_t)E, cs));
             return expand_row_ptr(ptr_dev, n_rows, E, dst, cs);
         }
@@ -1105,17 +1119,14 @@ static int stage_batch(gcnn_workspace* ws, int slot, const gcnn_batch* hb, const
     };
     GCNN_TRY(h2d(g.cons, hb->cons_feats, sizeof(float) * hb->n_cons * GCNN_CONS_FEATS, cs));
     GCNN_TRY(edge_inds(g.cei, hb->cons_edge_inds, hb->n_cons_edges, hb->cons_row_ptr, g.crp, hb->n_cons,
-                       (hb->flags & GCNN_BATCH_CONS_EDGES_SORTED) != 0));
+                       (hb->flags & GCNN_BATCH_CONS_EDGES_SORTED) != 0, hb->cons_col16, g.c16, 0));
     GCNN_TRY(h2d(g.cef, hb->cons_edge_feats, sizeof(float) * hb->n_cons_edges, cs));
     GCNN_TRY(h2d(g.var, hb->var_feats, sizeof(float) * hb->n_vars * GCNN_VAR_FEATS, cs));
     GCNN_TRY(h2d(g.cut, hb->cut_feats, sizeof(float) * hb->n_cuts * GCNN_CUT_FEATS, cs));
     GCNN_TRY(edge_inds(g.kei, hb->cut_edge_inds, hb->n_cut_edges, hb->cut_row_ptr, g.krp, hb->n_cuts,
-                       (hb->flags & GCNN_BATCH_CUT_EDGES_SORTED) != 0));
+                       (hb->flags & GCNN_BATCH_CUT_EDGES_SORTED) != 0, hb->cut_col16, g.k16, 2));
     GCNN_TRY(h2d(g.kef, hb->cut_edge_feats, sizeof(float) * hb->n_cut_edges, cs));
     if (targets_host) GCNN_TRY(h2d(g.targets, targets_host, sizeof(float) * hb->n_cuts, cs));
-    const int32_t* const counts[3] = {hb->sample_n_cons, hb->sample_n_vars, hb->sample_n_cuts};
-    const int64_t totals[3] = {hb->n_cons, hb->n_vars, hb->n_cuts};
-    GCNN_TRY(stage_blocks(ws, g, counts, hb->n_samples, totals, cs));
     GCNN_CUDA_TRY(cudaEventRecord(g.staged, cs));
     g.meta = *hb;
     g.meta.cons_feats = g.cons; g.meta.cons_edge_inds = g.cei; g.meta.cons_edge_feats = g.cef;
@@ -1124,6 +1135,7 @@ static int stage_batch(gcnn_workspace* ws, int slot, const gcnn_batch* hb, const
     g.meta.sample_n_cons = g.meta.sample_n_vars = g.meta.sample_n_cuts = nullptr;
     g.meta.n_samples = 0;
     g.meta.cons_row_ptr = g.meta.cut_row_ptr = nullptr;
+    g.meta.cons_col16 = g.meta.cut_col16 = nullptr;
     g.valid = 1;
     return GCNN_OK;
 }
@@ -1150,7 +1162,7 @@ static int move_stage(gcnn_workspace::Stage& g, const StagePtrs& n) {
     }
     g.cons = n.cons; g.cei = n.cei; g.cef = n.cef; g.var = n.var; g.cut = n.cut; g.kei = n.kei; g.kef = n.kef;
     g.targets = n.targets; g.raw = n.raw; g.raw_cap = n.raw_cap; g.descs = n.descs; g.blocks = n.blocks;
-    g.crp = n.crp; g.krp = n.krp;
+    g.crp = n.crp; g.krp = n.krp; g.c16 = n.c16; g.k16 = n.k16;
     if (g.valid) {
         g.meta.cons_feats = g.cons; g.meta.cons_edge_inds = g.cei; g.meta.cons_edge_feats = g.cef;
         g.meta.var_feats = g.var; g.meta.cut_feats = g.cut; g.meta.cut_edge_inds = g.kei; g.meta.cut_edge_feats = g.kef;

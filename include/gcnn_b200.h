@@ -81,6 +81,13 @@ typedef struct gcnn_batch {
      * expands it there, bit-identical to copying the row indices.  NULL = copy row 0 as it is. */
     const int32_t* cons_row_ptr;
     const int32_t* cut_row_ptr;
+    /* HOST batches only, optional, each only together with the row pointer of the same list and valid per-sample counts
+     * (sample_n_*): the variable index of every edge as uint16 LOCAL to its sample (index - first variable of the sample
+     * that owns the edge's row; a sample has at most 65,536 variables).  Then row 1 of that index tensor is not copied
+     * either -- an edge costs 2 + 4 bytes (column + coefficient) over PCIe instead of 12; the library adds the sample's
+     * variable offset on the device, bit-identical to copying the indices.  NULL = copy row 1 as it is. */
+    const uint16_t* cons_col16;
+    const uint16_t* cut_col16;
 } gcnn_batch;
 
 #define GCNN_BATCH_CONS_EDGES_SORTED 1

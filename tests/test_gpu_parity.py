@@ -699,8 +699,14 @@ def test_row_pointer_host_batches_are_bit_identical(golden_dir):
     assert HostBatch(tuple(batches[0])).row_ptrs == [None, None]  # default: only lists of >= 128 k edges
     assert hb[0].row_ptrs[0] is not None and hb[0].row_ptrs[1] is not None and ha[0].row_ptrs == [None, None]
     assert hb[1].row_ptrs[0] is not None and hb[1].row_ptrs[1] is None
-    assert hb[0].h2d_bytes == ha[0].h2d_bytes - 4 * (batches[0][1].shape[1] + batches[0][5].shape[1]) + 4 * (
+    assert hb[0].col16[0] is not None and hb[0].col16[1] is not None and hb[1].col16[1] is None  # uint16 local columns
+    assert hb[0].h2d_bytes == ha[0].h2d_bytes - 6 * (batches[0][1].shape[1] + batches[0][5].shape[1]) + 4 * (
         hb[0].batch.n_cons + 1 + hb[0].batch.n_cuts + 1)
+    totals = list(batches[0])
+    totals[7:10] = [int(np.sum(x)) for x in totals[7:10]]  # no per-sample counts: row pointers, full column indices
+    ht = HostBatch(tuple(totals), row_pointers=True)
+    assert ht.row_ptrs[0] is not None and ht.col16 == [None, None]
+    np.testing.assert_array_equal(a.score_host(HostBatch(tuple(totals), row_pointers=False)), b.score_host(ht))
     for x, y in zip(ha, hb):
         np.testing.assert_array_equal(a.score_host(x), b.score_host(y))
         assert a.train_step_host(x, 1e-3) == b.train_step_host(y, 1e-3)
