@@ -36,7 +36,7 @@ class Batch(C.Structure):
                 ("n_cons_edges", C.c_int64), ("n_cut_edges", C.c_int64), ("flags", C.c_int64),
                 ("sample_n_cons", C.c_void_p), ("sample_n_vars", C.c_void_p), ("sample_n_cuts", C.c_void_p),
                 ("n_samples", C.c_int64), ("cons_row_ptr", C.c_void_p), ("cut_row_ptr", C.c_void_p),
-                ("cons_col16", C.c_void_p), ("cut_col16", C.c_void_p)]
+                ("cons_col16", C.c_void_p), ("cut_col16", C.c_void_p), ("packed", C.c_void_p), ("packed_bytes", C.c_int64)]
 
 
 BATCH_CONS_EDGES_SORTED, BATCH_CUT_EDGES_SORTED = 1, 2

@@ -137,6 +137,7 @@ struct gcnn_workspace {
     // step on batch i runs (the reference's loader prefetches one batch the same way, model_trainer.py:153)
     struct Stage {
         float *cons = nullptr, *cef = nullptr, *var = nullptr, *cut = nullptr, *kef = nullptr, *targets = nullptr;
+        float* targets_at = nullptr;     // where the staged batch's targets are (targets, or inside raw: gcnn_batch::packed)
         int32_t *cei = nullptr, *kei = nullptr;
         int32_t *crp = nullptr, *krp = nullptr;  // row pointers of a host batch's sorted edge lists (gcnn_batch::*_row_ptr)
         uint16_t *c16 = nullptr, *k16 = nullptr;  // ... and their sample-local column indices (gcnn_batch::*_col16)
@@ -1100,40 +1101,62 @@ static int stage_batch(gcnn_workspace* ws, int slot, const gcnn_batch* hb, const
     const int32_t* const counts[3] = {hb->sample_n_cons, hb->sample_n_vars, hb->sample_n_cuts};
     const int64_t totals[3] = {hb->n_cons, hb->n_vars, hb->n_cuts};
     GCNN_TRY(stage_blocks(ws, g, counts, hb->n_samples, totals, cs));
+    // gcnn_batch::packed: one transfer for every array that lives in the caller's packed buffer
+    const uint8_t* pk = (const uint8_t*)hb->packed;
+    const size_t pk_bytes = pk && hb->packed_bytes > 0 && hb->packed_bytes <= g.raw_cap ? (size_t)hb->packed_bytes : 0;
+    // (in pieces: one uninterrupted multi-megabyte transfer delays the launches of the step that runs next to it -- same
+    // box, 32-graph batch, end-to-end step 0.430 ms with 13 copies, 0.440 ms with one 8 MB copy)
+    static const size_t piece = [] { const char* e = getenv("GCNN_PACKED_PIECE_KB"); return (size_t)(e ? atoi(e) : 1024) << 10; }();
+    for (size_t o = 0; o < pk_bytes; o += piece)
+        GCNN_TRY(h2d(g.raw + o, pk + o, pk_bytes - o < piece ? pk_bytes - o : piece, cs));
+    // device address of a host array: inside the packed copy when the array lies in the packed buffer, else `dev` after a
+    // copy of its own
+    int rc_sec = GCNN_OK;
+    auto section = [&](void* dev, const void* host, size_t bytes) -> void* {
+        if (bytes == 0 || !host) return dev;
+        const uint8_t* h = (const uint8_t*)host;
+        if (pk_bytes && h >= pk && h + bytes <= pk + pk_bytes && ((size_t)(h - pk) & 15) == 0) return g.raw + (h - pk);
+        if (rc_sec == GCNN_OK) rc_sec = h2d(dev, host, bytes, cs);
+        return dev;
+    };
+    gcnn_batch m = *hb;
+    m.cons_feats = (const float*)section(g.cons, hb->cons_feats, sizeof(float) * hb->n_cons * GCNN_CONS_FEATS);
+    m.cons_edge_feats = (const float*)section(g.cef, hb->cons_edge_feats, sizeof(float) * hb->n_cons_edges);
+    m.var_feats = (const float*)section(g.var, hb->var_feats, sizeof(float) * hb->n_vars * GCNN_VAR_FEATS);
+    m.cut_feats = (const float*)section(g.cut, hb->cut_feats, sizeof(float) * hb->n_cuts * GCNN_CUT_FEATS);
+    m.cut_edge_feats = (const float*)section(g.kef, hb->cut_edge_feats, sizeof(float) * hb->n_cut_edges);
+    g.targets_at = targets_host ? (float*)section(g.targets, targets_host, sizeof(float) * hb->n_cuts) : g.targets;
     // an index tensor [2, E] whose row 0 is sorted and comes with its row pointer travels as pointer + columns, the
     // columns as uint16 local to the sample when the caller provides them (left: 0 = constraints, 2 = cuts)
     auto edge_inds = [&](int32_t* dst, const int32_t* src, int64_t E, const int32_t* row_ptr, int32_t* ptr_dev, int64_t n_rows,
-                         bool sorted, const uint16_t* col16, uint16_t* col16_dev, int left) -> int {
+                         bool sorted, const uint16_t* col16, uint16_t* col16_dev, int left, const int32_t*& out) -> int {
+        out = dst;
         if (row_ptr && sorted && n_rows > 0 && E > 0) {
             if (row_ptr[0] != 0 || (int64_t)row_ptr[n_rows] != E) { set_error("row pointer does not span the edge list"); return GCNN_INVALID; }
-            GCNN_TRY(h2d(ptr_dev, row_ptr, sizeof(int32_t) * (size_t)(n_rows + 1), cs));
+            const int32_t* ptr_at = (const int32_t*)section(ptr_dev, row_ptr, sizeof(int32_t) * (size_t)(n_rows + 1));
             if (col16) {
                 if (g.blk.n <= 0) { set_error("local column indices need valid per-sample counts"); return GCNN_INVALID; }
-                GCNN_TRY(h2d(col16_dev, col16, sizeof(uint16_t) * (size_t)E, cs));
-                return expand_row_ptr(ptr_dev, n_rows, E, dst, cs, col16_dev, g.blk.off[left], g.blk.off[1], g.blk.n, dst + E);
+                const uint16_t* c16_at = (const uint16_t*)section(col16_dev, col16, sizeof(uint16_t) * (size_t)E);
+                return expand_row_ptr(ptr_at, n_rows, E, dst, cs, c16_at, g.blk.off[left], g.blk.off[1], g.blk.n, dst + E);
             }
             GCNN_TRY(h2d(dst + E, src + E, sizeof(int32_t) * (size_t)E, cs));
-            return expand_row_ptr(ptr_dev, n_rows, E, dst, cs);
+            return expand_row_ptr(ptr_at, n_rows, E, dst, cs);
         }
-        return h2d(dst, src, sizeof(int32_t) * 2 * (size_t)E, cs);
+        out = (const int32_t*)section(dst, src, sizeof(int32_t) * 2 * (size_t)E);
+        return GCNN_OK;
     };
-    GCNN_TRY(h2d(g.cons, hb->cons_feats, sizeof(float) * hb->n_cons * GCNN_CONS_FEATS, cs));
     GCNN_TRY(edge_inds(g.cei, hb->cons_edge_inds, hb->n_cons_edges, hb->cons_row_ptr, g.crp, hb->n_cons,
-                       (hb->flags & GCNN_BATCH_CONS_EDGES_SORTED) != 0, hb->cons_col16, g.c16, 0));
-    GCNN_TRY(h2d(g.cef, hb->cons_edge_feats, sizeof(float) * hb->n_cons_edges, cs));
-    GCNN_TRY(h2d(g.var, hb->var_feats, sizeof(float) * hb->n_vars * GCNN_VAR_FEATS, cs));
-    GCNN_TRY(h2d(g.cut, hb->cut_feats, sizeof(float) * hb->n_cuts * GCNN_CUT_FEATS, cs));
+                       (hb->flags & GCNN_BATCH_CONS_EDGES_SORTED) != 0, hb->cons_col16, g.c16, 0, m.cons_edge_inds));
     GCNN_TRY(edge_inds(g.kei, hb->cut_edge_inds, hb->n_cut_edges, hb->cut_row_ptr, g.krp, hb->n_cuts,
-                       (hb->flags & GCNN_BATCH_CUT_EDGES_SORTED) != 0, hb->cut_col16, g.k16, 2));
-    GCNN_TRY(h2d(g.kef, hb->cut_edge_feats, sizeof(float) * hb->n_cut_edges, cs));
-    if (targets_host) GCNN_TRY(h2d(g.targets, targets_host, sizeof(float) * hb->n_cuts, cs));
+                       (hb->flags & GCNN_BATCH_CUT_EDGES_SORTED) != 0, hb->cut_col16, g.k16, 2, m.cut_edge_inds));
+    GCNN_TRY(rc_sec);
     GCNN_CUDA_TRY(cudaEventRecord(g.staged, cs));
-    g.meta = *hb;
-    g.meta.cons_feats = g.cons; g.meta.cons_edge_inds = g.cei; g.meta.cons_edge_feats = g.cef;
-    g.meta.var_feats = g.var; g.meta.cut_feats = g.cut; g.meta.cut_edge_inds = g.kei; g.meta.cut_edge_feats = g.kef;
+    g.meta = m;
     // the count vectors were consumed above; the staged batch carries its block structure in g.blk
     g.meta.sample_n_cons = g.meta.sample_n_vars = g.meta.sample_n_cuts = nullptr;
     g.meta.n_samples = 0;
+    g.meta.packed = nullptr;
+    g.meta.packed_bytes = 0;
     g.meta.cons_row_ptr = g.meta.cut_row_ptr = nullptr;
     g.meta.cons_col16 = g.meta.cut_col16 = nullptr;
     g.valid = 1;
@@ -1150,18 +1173,19 @@ static int move_stage(gcnn_workspace::Stage& g, const StagePtrs& n) {
             GCNN_CUDA_TRY(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice));
             return GCNN_OK;
         };
-        GCNN_TRY(d2d(n.cons, g.cons, sizeof(float) * m.n_cons * GCNN_CONS_FEATS));
-        GCNN_TRY(d2d(n.cei, g.cei, sizeof(int32_t) * 2 * m.n_cons_edges));
-        GCNN_TRY(d2d(n.cef, g.cef, sizeof(float) * m.n_cons_edges));
-        GCNN_TRY(d2d(n.var, g.var, sizeof(float) * m.n_vars * GCNN_VAR_FEATS));
-        GCNN_TRY(d2d(n.cut, g.cut, sizeof(float) * m.n_cuts * GCNN_CUT_FEATS));
-        GCNN_TRY(d2d(n.kei, g.kei, sizeof(int32_t) * 2 * m.n_cut_edges));
-        GCNN_TRY(d2d(n.kef, g.kef, sizeof(float) * m.n_cut_edges));
-        GCNN_TRY(d2d(n.targets, g.targets, sizeof(float) * m.n_cuts));
+        // (from wherever the batch's arrays are: the slot's own buffers, or its raw area for a packed host batch)
+        GCNN_TRY(d2d(n.cons, m.cons_feats, sizeof(float) * m.n_cons * GCNN_CONS_FEATS));
+        GCNN_TRY(d2d(n.cei, m.cons_edge_inds, sizeof(int32_t) * 2 * m.n_cons_edges));
+        GCNN_TRY(d2d(n.cef, m.cons_edge_feats, sizeof(float) * m.n_cons_edges));
+        GCNN_TRY(d2d(n.var, m.var_feats, sizeof(float) * m.n_vars * GCNN_VAR_FEATS));
+        GCNN_TRY(d2d(n.cut, m.cut_feats, sizeof(float) * m.n_cuts * GCNN_CUT_FEATS));
+        GCNN_TRY(d2d(n.kei, m.cut_edge_inds, sizeof(int32_t) * 2 * m.n_cut_edges));
+        GCNN_TRY(d2d(n.kef, m.cut_edge_feats, sizeof(float) * m.n_cut_edges));
+        GCNN_TRY(d2d(n.targets, g.targets_at ? g.targets_at : g.targets, sizeof(float) * m.n_cuts));
         GCNN_TRY(d2d(n.blocks, g.blocks, sizeof(int32_t) * 3 * (MAX_RECORDS + 1)));
     }
     g.cons = n.cons; g.cei = n.cei; g.cef = n.cef; g.var = n.var; g.cut = n.cut; g.kei = n.kei; g.kef = n.kef;
-    g.targets = n.targets; g.raw = n.raw; g.raw_cap = n.raw_cap; g.descs = n.descs; g.blocks = n.blocks;
+    g.targets = n.targets; g.targets_at = n.targets; g.raw = n.raw; g.raw_cap = n.raw_cap; g.descs = n.descs; g.blocks = n.blocks;
     g.crp = n.crp; g.krp = n.krp; g.c16 = n.c16; g.k16 = n.k16;
     if (g.valid) {
         g.meta.cons_feats = g.cons; g.meta.cons_edge_inds = g.cei; g.meta.cons_edge_feats = g.cef;
@@ -1191,8 +1215,8 @@ static int read_error_flag(gcnn_workspace* ws, cudaStream_t st) {
 // A batch descriptor handed out by gcnn_staged_batch points into a staging slot: its block structure lives there.
 static const BlockInfo* staged_blocks_for(const gcnn_workspace* ws, const gcnn_batch* b) {
     for (int s = 0; s < 2; ++s)
-        if (ws->stage[s].valid && ws->stage[s].blk.n > 0 && b->cons_feats == ws->stage[s].cons &&
-            b->var_feats == ws->stage[s].var)
+        if (ws->stage[s].valid && ws->stage[s].blk.n > 0 && b->cons_feats == ws->stage[s].meta.cons_feats &&
+            b->var_feats == ws->stage[s].meta.var_feats)  // (the slot's own buffers, or its raw area: gcnn_batch::packed)
             return &ws->stage[s].blk;
     return nullptr;
 }
@@ -1805,6 +1829,7 @@ static int stage_records_impl(gcnn_workspace* ws, int slot, const void* const* r
     // the slot's previous consumer must be done with the batch tensors, and the previous assembly with descs_host
     if (g.valid) GCNN_CUDA_TRY(cudaStreamWaitEvent(cs, g.consumed, 0));
     if (g.valid) GCNN_CUDA_TRY(cudaEventSynchronize(g.staged));
+    g.targets_at = g.targets;
     AssembleOut out{g.cons, g.var, g.cut, g.targets, g.cef, g.kef, g.cei, g.kei, 0, 0};
     gcnn_batch meta;
     GCNN_TRY(assemble_records(records_host, n_records, g.raw, g.raw_cap, g.descs, g.descs_host, MAX_RECORDS, out,
@@ -1870,7 +1895,7 @@ int gcnn_train_step_staged_async(gcnn_workspace* ws, int slot, float* params, co
     // each slot has its own loss word: the copy below runs on another stream and may still be pending when the next
     // step's loss kernel writes
     float* loss_dev = ws->loss_sum + 8 + 8 * slot;
-    GCNN_TRY(gcnn_forward_backward(ws, params, prenorm, &g.meta, g.targets, scale, nullptr, grads, loss_dev, st));
+    GCNN_TRY(gcnn_forward_backward(ws, params, prenorm, &g.meta, g.targets_at, scale, nullptr, grads, loss_dev, st));
     GCNN_TRY(gcnn_adam_step(params, grads, adam_m, adam_v, GCNN_N_TRAINABLE, lr, 0.9f, 0.999f, 1e-7f, step, nullptr,
                             st));
     images_stale(ws);
@@ -1906,7 +1931,7 @@ int gcnn_dp_train_step_staged_async(gcnn_workspace* ws, int slot, float* params,
     float* sums_dev = ws->loss_sum + 8 + 8 * slot;  // {global cut count, global squared error} of this step
     const int keep = ws->count_before_loss;
     ws->count_before_loss = 1;  // the bucket's tail: [N] = local cut count, [N + 1] = local squared error
-    const int rc = gcnn_forward_backward(ws, params, prenorm, &g.meta, g.targets, 1.f, nullptr, bucket,
+    const int rc = gcnn_forward_backward(ws, params, prenorm, &g.meta, g.targets_at, 1.f, nullptr, bucket,
                                          bucket + GCNN_N_TRAINABLE + 1, st);
     ws->count_before_loss = keep;
     GCNN_TRY(rc);
@@ -1954,7 +1979,7 @@ int gcnn_staged_batch(gcnn_workspace* ws, int slot, gcnn_batch* out, float** tar
     DeviceGuard guard(ws->device);
     GCNN_CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, ws->stage[slot].staged, 0));
     *out = ws->stage[slot].meta;
-    if (targets_dev) *targets_dev = ws->stage[slot].targets;
+    if (targets_dev) *targets_dev = ws->stage[slot].targets_at;
     return GCNN_OK;
 }
 

@@ -10,6 +10,7 @@ Same constructor, call signature and method surface the reference's drivers use 
 from __future__ import annotations
 
 import ctypes as C
+import os
 import pickle
 from dataclasses import dataclass
 
@@ -592,60 +593,87 @@ class HostBatch:
 
     ROW_POINTER_MIN_EDGES = 1 << 17  # below this the two extra copies + expansions cost more host time than the bytes save
 
-    def __init__(self, batch11, row_pointers: bool | None = None):
+    def __init__(self, batch11, row_pointers: bool | None = None, packed: bool = True):
         (cons, cons_ei, cons_ef, var, cut, cut_ei, cut_ef, n_cons, n_vars, n_cuts, targets) = batch11
-        pin = lambda a, dt: torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=dt))).pin_memory()
-        self.tensors = [pin(cons, np.float32), pin(cons_ei, np.int32), pin(cons_ef, np.float32), pin(var, np.float32),
-                        pin(cut, np.float32), pin(cut_ei, np.int32), pin(cut_ef, np.float32)]
-        self.targets = pin(targets, np.float32)
+        arr = lambda a, dt: np.ascontiguousarray(np.asarray(a, dtype=dt))
+        host = [arr(cons, np.float32), arr(cons_ei, np.int32), arr(cons_ef, np.float32), arr(var, np.float32),
+                arr(cut, np.float32), arr(cut_ei, np.int32), arr(cut_ef, np.float32)]
+        tgt = arr(targets, np.float32)
         nc, nv, nk = int(np.sum(n_cons)), int(np.sum(n_vars)), int(np.sum(n_cuts))
-        self.scores = torch.empty(nk, dtype=torch.float32).pin_memory()
-        t = self.tensors
-        self.batch = Batch(t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(), t[4].data_ptr(),
-                           t[5].data_ptr(), t[6].data_ptr(), nc, nv, nk, t[1].shape[1], t[5].shape[1],
-                           _sorted_flags(t[1], t[5]))
+        flags = _sorted_flags(torch.from_numpy(host[1]), torch.from_numpy(host[5]))
         # sorted edge lists travel as row pointers: 4 of their 12 bytes per edge stay on the host (gcnn_batch::*_row_ptr).
         # row_pointers=None: only for large lists -- measured on one box (profiles/r2_ab_host_paths.json): a 32-graph
         # set-cover step 0.436 -> 0.428 ms end to end, but +25-30 us on a single-graph scoring / training call
-        self.row_ptrs = [None, None]
-        for i, (ei, n_rows, flag) in enumerate(((t[1], nc, _lib.BATCH_CONS_EDGES_SORTED), (t[5], nk, _lib.BATCH_CUT_EDGES_SORTED))):
+        row_ptrs = [None, None]
+        for i, (ei, n_rows, flag) in enumerate(((host[1], nc, _lib.BATCH_CONS_EDGES_SORTED), (host[5], nk, _lib.BATCH_CUT_EDGES_SORTED))):
             want = ei.shape[1] >= self.ROW_POINTER_MIN_EDGES if row_pointers is None else bool(row_pointers)
-            if want and (self.batch.flags & flag) and n_rows > 0 and ei.shape[1] > 0:
-                rp = np.searchsorted(ei[0].numpy(), np.arange(n_rows + 1, dtype=np.int64), side="left").astype(np.int32)
-                self.row_ptrs[i] = torch.from_numpy(rp).pin_memory()
-        if self.row_ptrs[0] is not None:
-            self.batch.cons_row_ptr = self.row_ptrs[0].data_ptr()
-        if self.row_ptrs[1] is not None:
-            self.batch.cut_row_ptr = self.row_ptrs[1].data_ptr()
+            if row_pointers is None and os.environ.get("GCNN_HOST_ROW_POINTERS") in ("0", "1"):  # A/B switch
+                want = os.environ["GCNN_HOST_ROW_POINTERS"] == "1"
+            if want and (flags & flag) and n_rows > 0 and ei.shape[1] > 0:
+                row_ptrs[i] = np.searchsorted(ei[0], np.arange(n_rows + 1, dtype=np.int64), side="left").astype(np.int32)
+        # ... and the column (variable) indices of those lists as uint16 local to the sample that owns the edge's row
+        # (gcnn_batch::*_col16): 2 instead of 4 bytes per edge; skipped when a local index does not fit or the edge
+        # leaves its sample's block (the library's own checks then see the full indices)
         self.counts = _sample_counts(n_cons, n_vars, n_cuts)
-        self.col16 = [None, None]
+        col16 = [None, None]
+        if self.counts is not None and self.counts[0].shape[0] <= _lib.MAX_RECORDS:
+            var_off = np.concatenate(([0], np.cumsum(self.counts[1], dtype=np.int64)))
+            for i, (ei, left_counts) in enumerate(((host[1], self.counts[0]), (host[5], self.counts[2]))):
+                left_end = np.cumsum(left_counts, dtype=np.int64)
+                if row_ptrs[i] is None or left_end[-1] != (nc, nk)[i] or var_off[-1] != nv:
+                    continue
+                sidx = np.searchsorted(left_end, ei[0], side="right").clip(max=len(left_end) - 1)
+                local = ei[1] - var_off[sidx]
+                if local.size and local.min() >= 0 and local.max() < 65536 and bool(np.all(local < self.counts[1][sidx])):
+                    col16[i] = local.astype(np.uint16)
+        # one pinned buffer for everything that crosses PCIe whole (gcnn_batch::packed): a single transfer per batch
+        # instead of ~13; an index tensor that travels as a row pointer stays outside it (only its columns are copied, or
+        # nothing at all with local columns)
+        inside = [True, row_ptrs[0] is None, True, True, True, row_ptrs[1] is None, True]
+        sections = [(a, k) for k, a in enumerate(host) if inside[k]] + [(tgt, "t")]
+        sections += [(a, ("p", i)) for i, a in enumerate(row_ptrs) if a is not None]
+        sections += [(a, ("c", i)) for i, a in enumerate(col16) if a is not None]
+        pin = lambda a: torch.from_numpy(a).pin_memory()
+        placed = {}
+        if packed:
+            offs, total = [], 0
+            for a, _ in sections:
+                offs.append(total)
+                total += (a.nbytes + 255) & ~255  # (the device copy keeps the staging buffers' 256-byte alignment)
+            self.arena = torch.empty(max(total, 16), dtype=torch.uint8).pin_memory()
+            for (a, key), off in zip(sections, offs):
+                view = self.arena[off:off + a.nbytes].view(torch.from_numpy(a).dtype).view(a.shape)
+                view.copy_(torch.from_numpy(a))
+                placed[key] = view
+        else:
+            self.arena = None
+            for a, key in sections:
+                placed[key] = pin(a)
+        self.tensors = [placed[k] if inside[k] else pin(host[k]) for k in range(7)]
+        self.targets = placed["t"]
+        self.row_ptrs = [placed.get(("p", i)) for i in range(2)]
+        self.col16 = [placed.get(("c", i)) for i in range(2)]
+        self.scores = torch.empty(nk, dtype=torch.float32).pin_memory()
+        t = self.tensors
+        self.batch = b = Batch(t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(), t[4].data_ptr(),
+                               t[5].data_ptr(), t[6].data_ptr(), nc, nv, nk, t[1].shape[1], t[5].shape[1], flags)
+        if self.row_ptrs[0] is not None:
+            b.cons_row_ptr = self.row_ptrs[0].data_ptr()
+        if self.row_ptrs[1] is not None:
+            b.cut_row_ptr = self.row_ptrs[1].data_ptr()
+        if self.col16[0] is not None:
+            b.cons_col16 = self.col16[0].data_ptr()
+        if self.col16[1] is not None:
+            b.cut_col16 = self.col16[1].data_ptr()
         if self.counts is not None:
-            b = self.batch
             b.sample_n_cons, b.sample_n_vars, b.sample_n_cuts = (c.ctypes.data for c in self.counts)
             b.n_samples = self.counts[0].shape[0]
-            # ... and the column (variable) indices of those lists as uint16 local to the sample that owns the edge's row
-            # (gcnn_batch::*_col16): 2 instead of 4 bytes per edge; skipped when a local index does not fit or the edge
-            # leaves its sample's block (the library's own checks then see the full indices)
-            var_off = np.concatenate(([0], np.cumsum(self.counts[1], dtype=np.int64)))
-            for i, (ei, left_counts) in enumerate(((t[1], self.counts[0]), (t[5], self.counts[2]))):
-                if self.row_ptrs[i] is None or len(var_off) - 1 > _lib.MAX_RECORDS:
-                    continue
-                left_end = np.cumsum(left_counts, dtype=np.int64)
-                if left_end[-1] != (nc, nk)[i] or var_off[-1] != nv:
-                    continue
-                rows, cols = ei[0].numpy(), ei[1].numpy()
-                sidx = np.searchsorted(left_end, rows, side="right").clip(max=len(left_end) - 1)
-                local = cols - var_off[sidx]
-                if local.size and local.min() >= 0 and local.max() < 65536 and bool(np.all(local < self.counts[1][sidx])):
-                    self.col16[i] = torch.from_numpy(local.astype(np.uint16)).pin_memory()
-            if self.col16[0] is not None:
-                b.cons_col16 = self.col16[0].data_ptr()
-            if self.col16[1] is not None:
-                b.cut_col16 = self.col16[1].data_ptr()
+        if self.arena is not None:
+            b.packed, b.packed_bytes = self.arena.data_ptr(), total
         self.n_graphs = int(np.size(n_cons))
-        self.h2d_bytes = sum(x.numel() * x.element_size() for x in self.tensors) + self.targets.numel() * 4
-        for rp, c16, ei in zip(self.row_ptrs, self.col16, (t[1], t[5])):  # pointer + columns instead of [2, E]
-            if rp is not None:
-                self.h2d_bytes += rp.numel() * 4 - ei.shape[1] * 4
-            if c16 is not None:
-                self.h2d_bytes -= ei.shape[1] * 2
+        # bytes that cross PCIe per staging call: the packed sections (features, coefficients, targets, pointers, local
+        # columns, whole index tensors of unsorted lists) + the column row of a list with a pointer but no local columns
+        self.h2d_bytes = total if packed else sum(a.nbytes for a, _ in sections)
+        for i, k in enumerate((1, 5)):
+            if row_ptrs[i] is not None and col16[i] is None:
+                self.h2d_bytes += host[k].shape[1] * 4

@@ -88,6 +88,13 @@ typedef struct gcnn_batch {
      * variable offset on the device, bit-identical to copying the indices.  NULL = copy row 1 as it is. */
     const uint16_t* cons_col16;
     const uint16_t* cut_col16;
+    /* HOST batches only, optional: the caller keeps (some of) the arrays above in ONE host buffer
+     * [packed, packed + packed_bytes), each at a 16-byte aligned offset.  The library then copies that buffer with a single
+     * transfer and reads every array that lies inside it at the same offset on the device; arrays outside it are copied
+     * one by one as before (a batch is ~13 arrays: on a host that feeds eight GPUs the per-copy latency, not the bytes,
+     * bounds the staging).  targets_host of gcnn_stage_host_batch may lie inside it too.  NULL / 0 = no such buffer. */
+    const void* packed;
+    int64_t packed_bytes;
 } gcnn_batch;
 
 #define GCNN_BATCH_CONS_EDGES_SORTED 1

@@ -1,4 +1,5 @@
-"""Same-box A/B of the host-side paths: row-pointer host batches on / off, option "params_epoch" on / off.
+"""Same-box A/B of the host-side paths: host batches plain (13 copies) / packed (one copy) / row pointers + uint16 local
+columns / both; option "params_epoch" on / off.
 Prints one JSON line.  (python scripts/ab_host_paths.py [--e2e-graphs 32])"""
 import json
 import os
@@ -28,6 +29,7 @@ def lat(fn, n=200, warm=10):
     return round(1e3 * float(np.median(t)), 4)
 
 
+VARIANTS = {"plain": (False, False), "packed": (False, True), "rowptr": (True, False), "rowptr_packed": (True, True)}
 announce = GCNN._announce_params
 
 
@@ -42,30 +44,30 @@ def epoch(on: bool):
 
 for shape, n in (("combauc", 1), ("indset", 1), ("capfac", 1)):
     batch = batching.concat_samples(synth.make_samples(shape, n, seed0=300))
-    hb = {rp: HostBatch(batch, row_pointers=rp) for rp in (False, True)}
+    hb = {v: HostBatch(batch, row_pointers=v[0], packed=v[1]) for v in VARIANTS.values()}
     res = {}
     for rnd in range(2):
         for ep in (False, True):
             epoch(ep)
-            for rp in (False, True):
-                k = f"epoch{int(ep)}_rowptr{int(rp)}"
+            for name, rp in VARIANTS.items():
+                k = f"epoch{int(ep)}_{name}"
                 res.setdefault(k + "_eager", []).append(lat(lambda: model.score_host(hb[rp])))
                 res.setdefault(k + "_graph", []).append(lat(lambda: model.score_host(hb[rp], graph=True)))
     out[f"score_{shape}"] = {k: min(v) for k, v in res.items()}
 
 epoch(True)
 batch = batching.concat_samples(synth.make_samples("setcov", 1, seed0=77))
-hb = {rp: HostBatch(batch, row_pointers=rp) for rp in (False, True)}
+hb = {v: HostBatch(batch, row_pointers=v[0], packed=v[1]) for v in VARIANTS.values()}
 res = {}
 for rnd in range(2):
-    for rp in (False, True):
-        res.setdefault(f"rowptr{int(rp)}", []).append(lat(lambda: model.train_step_host(hb[rp], 1e-4), 100))
+    for name, rp in VARIANTS.items():
+        res.setdefault(name, []).append(lat(lambda: model.train_step_host(hb[rp], 1e-4), 100))
 out["config1_train_step_host"] = {k: min(v) for k, v in res.items()}
 
 graphs = int(sys.argv[sys.argv.index("--e2e-graphs") + 1]) if "--e2e-graphs" in sys.argv else 32
 batches = [batching.concat_samples(synth.make_samples("setcov", graphs, seed0=1000 * i)) for i in range(4)]
-hosts = {rp: [HostBatch(b, row_pointers=rp) for b in batches] for rp in (False, True)}
-for h in hosts[True]:
+hosts = {v: [HostBatch(b, row_pointers=v[0], packed=v[1]) for b in batches] for v in VARIANTS.values()}
+for h in hosts[(False, False)]:
     model.reserve(h.batch, True)
 
 
@@ -95,8 +97,8 @@ def e2e(host, K=60, W=5):
 
 res = {}
 for rnd in range(3):
-    for rp in (False, True):
-        res.setdefault(f"rowptr{int(rp)}", []).append(round(e2e(hosts[rp]), 4))
+    for name, rp in VARIANTS.items():
+        res.setdefault(name, []).append(round(e2e(hosts[rp]), 4))
 out[f"e2e_{graphs}_graphs_ms"] = res
-out["h2d_bytes"] = {f"rowptr{int(rp)}": hosts[rp][0].h2d_bytes for rp in (False, True)}
+out["h2d_bytes"] = {name: hosts[rp][0].h2d_bytes for name, rp in VARIANTS.items()}
 print(json.dumps(out))

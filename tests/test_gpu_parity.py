@@ -694,14 +694,18 @@ def test_row_pointer_host_batches_are_bit_identical(golden_dir):
     batches[1][5], batches[1][6] = batches[1][5][:, perm], batches[1][6][perm]
     a, b = GCNN(device="cuda:0", seed=3), GCNN(device="cuda:0", seed=4)
     a.restore_state(path); b.restore_state(path)
-    ha = [HostBatch(tuple(x), row_pointers=False) for x in batches]
-    hb = [HostBatch(tuple(x), row_pointers=True) for x in batches]
+    ha = [HostBatch(tuple(x), row_pointers=False, packed=False) for x in batches]  # thirteen plain copies
+    hb = [HostBatch(tuple(x), row_pointers=True) for x in batches]  # one packed buffer: features, pointers, local columns
     assert HostBatch(tuple(batches[0])).row_ptrs == [None, None]  # default: only lists of >= 128 k edges
     assert hb[0].row_ptrs[0] is not None and hb[0].row_ptrs[1] is not None and ha[0].row_ptrs == [None, None]
     assert hb[1].row_ptrs[0] is not None and hb[1].row_ptrs[1] is None
     assert hb[0].col16[0] is not None and hb[0].col16[1] is not None and hb[1].col16[1] is None  # uint16 local columns
-    assert hb[0].h2d_bytes == ha[0].h2d_bytes - 6 * (batches[0][1].shape[1] + batches[0][5].shape[1]) + 4 * (
-        hb[0].batch.n_cons + 1 + hb[0].batch.n_cuts + 1)
+    assert HostBatch(tuple(batches[0]), row_pointers=True, packed=False).h2d_bytes == ha[0].h2d_bytes - 6 * (
+        batches[0][1].shape[1] + batches[0][5].shape[1]) + 4 * (hb[0].batch.n_cons + 1 + hb[0].batch.n_cuts + 1)
+    assert hb[0].batch.packed_bytes == hb[0].h2d_bytes and hb[0].h2d_bytes < ha[0].h2d_bytes
+    hp = [HostBatch(tuple(x), row_pointers=False) for x in batches]  # packed, full index tensors
+    for x, y in zip(ha, hp):
+        np.testing.assert_array_equal(a.score_host(x), b.score_host(y))
     totals = list(batches[0])
     totals[7:10] = [int(np.sum(x)) for x in totals[7:10]]  # no per-sample counts: row pointers, full column indices
     ht = HostBatch(tuple(totals), row_pointers=True)
