@@ -401,7 +401,7 @@ head2_forward_kernel(const float* __restrict__ g, const float* __restrict__ w, c
     float s = 0.f;
     if (m < M) {
         const float4 a = ld4s(g + m * D + hl * 4), w4 = ld4s(w + hl * 4);
-        s = a.x * w4.x + a.y * w4.y + a.z * w4.z + a.w * w4.w;
+        s = fmaf(a.w, w4.w, fmaf(a.z, w4.z, fmaf(a.y, w4.y, a.x * w4.x)));  // (explicit: the same contraction as head_loss_kernel)
     }
 #pragma unroll
     for (int o = 8; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -436,7 +436,7 @@ head_loss_kernel(const float* __restrict__ g, const float* __restrict__ w, const
         const bool ok = m < M;  // uniform over the 16 lanes of a row
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ok) a = ld4s(g + m * D + hl * 4);
-        float s = a.x * w4.x + a.y * w4.y + a.z * w4.z + a.w * w4.w;
+        float s = fmaf(a.w, w4.w, fmaf(a.z, w4.z, fmaf(a.y, w4.y, a.x * w4.x)));
 #pragma unroll
         for (int o = 8; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (ok) {

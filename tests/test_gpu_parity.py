@@ -721,6 +721,40 @@ def test_row_pointer_host_batches_are_bit_identical(golden_dir):
         b.score_host(bad)
 
 
+def test_head_in_the_last_chain_equals_the_separate_head_kernels(golden_dir):
+    """Option "head_in_chain": the head's Dense(1), the MSE seed and that layer's backward computed in the epilogue of the
+    cut convolution's forward chain (default) against the launches of their own -- same scores, loss and gradients to
+    fp32 rounding (another summation order inside the 64-term dot product), a launch fewer; training and inference scores
+    bit-identical in either mode; a cut count that is not a multiple of the 128-node tile and more than one tile."""
+    from gcnn_cut_selector_b200 import GCNN
+    path = os.path.join(golden_dir, "state_stream.pkl")
+    m = GCNN(device="cuda:0", seed=3)
+    m.restore_state(path)
+    for shape, n in (("setcov", 3), ("combauc", 5), ("mini", 2)):
+        batch = batching.concat_samples(synth.make_samples(shape, n, seed0=70 + n))
+        inputs, targets = batching.model_inputs(batch, per_sample_counts=True), batch[10]
+        got = {}
+        m.loss_and_grads(inputs, targets)  # (packs the weight images of this parameter epoch: not counted below)
+        for mode in (1, 0):
+            m.set_option("head_in_chain", mode)
+            n0 = m._lib.gcnn_kernel_launches()
+            loss_sum, scores = m.loss_and_grads(inputs, targets)
+            launches = m._lib.gcnn_kernel_launches() - n0
+            with torch.no_grad():
+                inference = m(inputs, False)
+            if mode == 1:  # one code path computes the score in training and inference
+                torch.testing.assert_close(inference, scores, rtol=0, atol=0)
+            else:
+                assert rel_err(inference.cpu().numpy(), scores.cpu().numpy()) <= 1e-6
+            got[mode] = (float(loss_sum), scores.cpu().numpy().copy(), m.flat_grads.cpu().numpy().copy(), launches)
+        m.set_option("head_in_chain", 1)
+        assert got[0][3] == got[1][3] + 1, f"launches {got[0][3]} vs {got[1][3]}"
+        assert abs(got[0][0] - got[1][0]) <= 1e-5 * abs(got[0][0]), f"loss {got[0][0]} vs {got[1][0]}"
+        assert rel_err(got[1][1], got[0][1]) <= 1e-6, f"scores {rel_err(got[1][1], got[0][1])}"
+        g_err = np.linalg.norm(got[1][2] - got[0][2]) / np.linalg.norm(got[0][2])
+        assert g_err <= 1e-5, f"gradients {g_err}"
+
+
 def test_params_epoch_reuses_and_refreshes_weight_images(golden_dir):
     """Option "params_epoch": scoring with frozen weights packs the weight images once (one launch fewer per call); every
     way the parameters can change -- a torch write, restore_state, the library's fused step, apply_gradients, a raw write
