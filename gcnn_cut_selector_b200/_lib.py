@@ -48,6 +48,7 @@ _BP = C.POINTER(Batch)
 # name -> (restype, argtypes); every symbol include/gcnn_b200.h declares
 SIGNATURES = {
     "gcnn_version": (_I, []),
+    "gcnn_batch_bytes": (_I64, []),
     "gcnn_last_error": (C.c_char_p, []),
     "gcnn_kernel_launches": (_I, []),
     "gcnn_profile_begin": (_I, []),
@@ -115,6 +116,9 @@ def load():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError if the header and the library ever disagree
             fn.restype, fn.argtypes = res, args
+        if lib.gcnn_batch_bytes() != C.sizeof(Batch):
+            raise ImportError(f"{LIB_PATH}: gcnn_batch is {lib.gcnn_batch_bytes()} bytes in the library but "
+                              f"{C.sizeof(Batch)} in this binding (rebuild: python -m gcnn_cut_selector_b200.build)")
         _lib = lib
     return _lib
 

@@ -1229,6 +1229,7 @@ static void serve_drop_graphs(gcnn_workspace* ws);
 extern "C" {
 
 int gcnn_version(void) { return 100; }
+int64_t gcnn_batch_bytes(void) { return (int64_t)sizeof(gcnn_batch); }
 const char* gcnn_last_error(void) { return g_err; }
 int gcnn_kernel_launches(void) { return g_launches.load(); }
 

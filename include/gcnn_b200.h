@@ -102,6 +102,9 @@ typedef struct gcnn_batch {
 
 /* ---- library ------------------------------------------------------------------------------------------------ */
 int gcnn_version(void);
+/* sizeof(gcnn_batch) of this build: a binding checks its own struct declaration against it (the struct grows at its end:
+ * a caller built against an older header must zero-fill what it does not know). */
+int64_t gcnn_batch_bytes(void);
 const char* gcnn_last_error(void);
 int gcnn_kernel_launches(void); /* kernels launched by this library in this process so far */
 

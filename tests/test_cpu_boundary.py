@@ -111,3 +111,54 @@ def test_synth_shapes(shape, n_edges):
     pairs = ei[0].astype(np.int64) * n_vars + ei[1]
     assert np.unique(pairs).size == n_edges
     assert ke["indices"].shape == (2, n_cuts * nnz)
+
+
+def test_batch_struct_matches_the_library(lib):
+    """The binding's gcnn_batch (ctypes) and the library's agree in size; field order is the header's."""
+    import ctypes as C
+    assert lib.gcnn_batch_bytes() == C.sizeof(_lib.Batch)
+    hdr = open(os.path.join(ROOT, "include", "gcnn_b200.h")).read()
+    body = hdr[hdr.index("typedef struct gcnn_batch {"):hdr.index("} gcnn_batch;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = [n for stmt in body.split(";") for n in re.findall(r"[\*\s,](\w+)\s*(?=,|$)", stmt.strip())]
+    assert names == [f for f, _ in _lib.Batch._fields_]
+
+
+def test_host_batch_packing_and_local_columns(monkeypatch):
+    """HostBatch's host-side logic without a GPU (pin_memory stubbed): every packed section at a 256-byte offset inside
+    the one buffer and equal to its source array; row pointers index the sorted list; uint16 local columns + the sample's
+    first variable reproduce the column indices; an unsorted list and a batch without per-sample counts keep full indices;
+    the byte count is what the library would copy."""
+    import torch
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
+    from gcnn_cut_selector_b200 import HostBatch
+    batch = list(batching.concat_samples(synth.make_samples("setcov", 3, seed0=1)))
+    perm = np.random.default_rng(0).permutation(batch[5].shape[1])
+    shuffled = list(batch)
+    shuffled[5], shuffled[6] = batch[5][:, perm], batch[6][perm]
+    h = HostBatch(tuple(batch), row_pointers=True)
+    base, size = h.arena.data_ptr(), h.arena.numel()
+    inside = [x for x in h.tensors + [h.targets] + h.row_ptrs + h.col16 if base <= x.data_ptr() < base + size]
+    assert len(inside) == 10 and all((x.data_ptr() - base) % 256 == 0 for x in inside)
+    assert h.batch.packed == base and h.batch.packed_bytes == h.h2d_bytes <= size
+    for k in range(7):
+        np.testing.assert_array_equal(h.tensors[k].numpy().reshape(-1), np.asarray(batch[k]).reshape(-1))
+    np.testing.assert_array_equal(h.targets.numpy(), batch[10])
+    var_off = np.concatenate(([0], np.cumsum(batch[8])))
+    for i, (k, left_counts) in enumerate(((1, batch[7]), (5, batch[9]))):
+        rows, cols = batch[k][0], batch[k][1]
+        rp = h.row_ptrs[i].numpy()
+        assert rp[0] == 0 and rp[-1] == rows.size
+        np.testing.assert_array_equal(np.repeat(np.arange(rp.size - 1), np.diff(rp)), rows)
+        sample = np.searchsorted(np.cumsum(left_counts), rows, side="right")
+        np.testing.assert_array_equal(h.col16[i].numpy().astype(np.int64) + var_off[sample], cols)
+    plain = HostBatch(tuple(batch), row_pointers=False, packed=False)
+    assert plain.arena is None and plain.batch.packed is None and plain.row_ptrs == [None, None]
+    assert h.h2d_bytes < plain.h2d_bytes - 5 * (batch[1].shape[1] + batch[5].shape[1])
+    hs = HostBatch(tuple(shuffled), row_pointers=True)
+    assert hs.row_ptrs[0] is not None and hs.row_ptrs[1] is None and hs.col16[1] is None
+    totals = list(batch)
+    totals[7:10] = [int(np.sum(x)) for x in totals[7:10]]
+    ht = HostBatch(tuple(totals), row_pointers=True)
+    assert ht.row_ptrs[0] is not None and ht.col16 == [None, None] and ht.batch.n_samples == 0
+    assert HostBatch(tuple(batch)).row_ptrs == [None, None]  # default: only lists of >= 128 k edges
