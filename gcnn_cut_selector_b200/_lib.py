@@ -98,6 +98,12 @@ SIGNATURES = {
     "gcnn_edge_forward": (_I, [_P, _P, _P, _I64, _P, _P, _P, _F, _F, _F, _P, _P, _P]),
     "gcnn_edge_backward": (_I, [_P, _P, _P, _P, _I64, _P, _P, _P, _P, _F, _F, _F, _P, _P, _P]),
     "gcnn_linear_forward": (_I, [_P, _P, _P, _I64, _I, _I, _P, _P]),
+    "gcnn_conv_forward": (_I, [_P, _P, _P, _I, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P]),
+    "gcnn_conv_backward": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P]),
+    "gcnn_embed_forward": (_I, [_P, _P, _P, _I, _P, _I64, _P, _P, _P, _P, _P]),
+    "gcnn_embed_backward": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I64, _P, _P]),
+    "gcnn_head_forward": (_I, [_P, _P, _P, _I64, _P, _P]),
+    "gcnn_head_backward": (_I, [_P, _P, _P, _P, _I64, _P, _P, _P]),
     "gcnn_has_alt_paths": (_I, []),
 }
 

@@ -2258,6 +2258,177 @@ int gcnn_linear_forward(const float* X, const float* W, const float* b, int64_t 
 #endif
 }
 
+// ---- per-op entry points of the tensor-core node chains (unit parity tests; SURVEY 8b "minimum exports") ---------------
+// The same launches the whole-model calls make (bf16x3 chains, this workspace's weight images), on caller-provided device
+// arrays; each call re-packs or reuses the images (option "params_epoch"), runs the fixed-order reduction of the chain's
+// weight-gradient partials where there is one and synchronises the stream.
+static const float* chain_img_t(const gcnn_workspace* ws, int param_off) {  // forward (T) image of a 64 x 64 weight block
+    return ws->tc_images + (int64_t)tc_block_index(param_off) * TC_IMG_FLOATS + TC_IMG_TF32_FLOATS + TC_IMG_BF16_ONE;
+}
+static const void* chain_img_n(const gcnn_workspace* ws, int param_off) {   // backward (N) image
+    return ws->tc_images + (int64_t)tc_block_index(param_off) * TC_IMG_FLOATS + TC_IMG_TF32_FLOATS;
+}
+static int chain_op_ready(gcnn_workspace* ws, const float* params, int training, int64_t M, cudaStream_t st) {
+    if (!ws || !ws->arena || !params) { set_error("chain op: workspace not reserved / null parameters"); return GCNN_INVALID; }
+    if (training && !ws->cap.training) { set_error("chain op: reserve the workspace for training first"); return GCNN_INVALID; }
+    if (M < 0) { set_error("chain op: negative row count"); return GCNN_INVALID; }
+    return ensure_images(ws, params, st);
+}
+struct NextLayer { int w, b, relu; };  // the layer that consumes a convolution's output Y
+static NextLayer conv_next(int conv) {
+    if (conv == 0) return {P.conv[1].Wl, P.conv[1].bl, 0};
+    if (conv == 1) return {P.conv[2].Wr, -1, 0};
+    return {P.Wh1, P.bh1, 1};
+}
+
+int gcnn_conv_forward(gcnn_workspace* ws, const float* params, const float* prenorm, int conv, const float* H,
+                      const float* Xt, const int32_t* deg_ptr, int64_t M, float* C_out, float* U1_out, float* Y_out,
+                      float* Pn_out, float* scores_out, void* stream) {
+    if (conv < 0 || conv > 2 || !H || !Xt || !Y_out || !Pn_out || !prenorm) { set_error("gcnn_conv_forward: bad arguments"); return GCNN_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    GCNN_TRY(chain_op_ready(ws, params, 0, M, st));
+    DeviceGuard guard(ws->device);
+    const ConvOff& o = P.conv[conv];
+    const NextLayer nx = conv_next(conv);
+    ConvFwdArgs c{};
+    c.H = H; c.Xt = Xt; c.deg_ptr = deg_ptr; c.s_p = prenorm + PN.conv_sp[conv];
+    c.img_f = chain_img_t(ws, o.Wf); c.bias_f = params + o.bf;
+    c.img_o1a = chain_img_t(ws, o.Wo1); c.img_o1b = chain_img_t(ws, o.Wo1 + D * D); c.bias_o1 = params + o.bo1;
+    c.img_o2 = chain_img_t(ws, o.Wo2); c.bias_o2 = params + o.bo2;
+    c.img_n = chain_img_t(ws, nx.w); c.bias_n = nx.b >= 0 ? params + nx.b : nullptr; c.relu_n = nx.relu;
+    c.C = C_out; c.U1 = U1_out; c.Y = Y_out; c.Pn = Pn_out; c.M = M;
+    c.bf16_mlp = ws->bf16_mlp;
+    if (conv == 2 && scores_out) { c.head_w = params + P.Wh2; c.head_b = params + P.bh2; c.scores = scores_out; }
+    GCNN_TRY(tc_conv_forward16(c, st));
+    GCNN_CUDA_TRY(cudaStreamSynchronize(st));
+    return GCNN_OK;
+}
+
+int gcnn_conv_backward(gcnn_workspace* ws, const float* params, const float* prenorm, int conv, const float* dP,
+                       const float* Y, const float* U1, const float* C_in, const float* Xt, const float* H,
+                       const float* cnt, const int32_t* deg_ptr, int64_t M, float* dXt, float* G, float* dR,
+                       float* grads, void* stream) {
+    if (conv < 0 || conv > 2 || !dP || !Y || !U1 || !C_in || !Xt || !H || !cnt || !deg_ptr || !dXt || !G || !dR || !grads || !prenorm) {
+        set_error("gcnn_conv_backward: bad arguments");
+        return GCNN_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    GCNN_TRY(chain_op_ready(ws, params, 1, M, st));
+    DeviceGuard guard(ws->device);
+    const ConvOff& o = P.conv[conv];
+    const NextLayer nx = conv_next(conv);
+    ConvBwdArgs c{};
+    c.dP = dP; c.Y = Y; c.U1 = U1; c.C = C_in; c.Xt = Xt; c.H = H; c.cnt = cnt; c.deg_ptr = deg_ptr;
+    c.s_p = prenorm + PN.conv_sp[conv]; c.s_f = prenorm + PN.conv_sf[conv];
+    c.img_n = chain_img_n(ws, nx.w); c.img_o2 = chain_img_n(ws, o.Wo2); c.img_o1a = chain_img_n(ws, o.Wo1);
+    c.img_o1b = chain_img_n(ws, o.Wo1 + D * D); c.img_f = chain_img_n(ws, o.Wf);
+    c.dXt = dXt; c.G = G; c.dR = dR; c.partials = ws->chain_partials[conv]; c.M = M;
+    c.bf16_mlp = ws->bf16_mlp;
+    int n_parts = 0;
+    GCNN_TRY(tc_conv_backward(c, &n_parts, st));
+    if (n_parts > 0) {
+        const int PART = conv_backward_part_floats();
+        const float* cp = ws->chain_partials[conv];
+        const ReduceJob jobs[4] = {
+            {cp, n_parts, PART, D * D + (nx.b >= 0 ? D : 0), nx.w, nullptr, nullptr},
+            {cp + (D * D + D), n_parts, PART, D * D + D, o.Wo2, nullptr, nullptr},
+            {cp + 2 * (D * D + D), n_parts, PART, 2 * D * D + D, o.Wo1, nullptr, nullptr},
+            {cp + 2 * (D * D + D) + 2 * D * D + D, n_parts, PART, D * D + D, o.Wf, nullptr, nullptr}};
+        GCNN_TRY(reduce_partials(jobs, 4, grads, st));
+    }
+    GCNN_CUDA_TRY(cudaStreamSynchronize(st));
+    return GCNN_OK;
+}
+
+int gcnn_embed_forward(gcnn_workspace* ws, const float* params, const float* prenorm, int node_type, const float* x,
+                       int64_t M, float* h1_out, float* out, float* P0_out, float* P1_out, void* stream) {
+    if (node_type < 0 || node_type > 2 || !x || !out || !P0_out || !prenorm || (node_type == 1 && !P1_out)) {
+        set_error("gcnn_embed_forward: bad arguments");
+        return GCNN_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    GCNN_TRY(chain_op_ready(ws, params, 0, M, st));
+    DeviceGuard guard(ws->device);
+    const EmbOff* eo = node_type == 0 ? &P.cons : (node_type == 1 ? &P.var : &P.cut);
+    const int K = node_type == 0 ? GCNN_CONS_FEATS : (node_type == 1 ? GCNN_VAR_FEATS : GCNN_CUT_FEATS);
+    const int shift = node_type == 0 ? PN.cons_shift : (node_type == 1 ? PN.var_shift : PN.cut_shift);
+    const int scale = node_type == 0 ? PN.cons_scale : (node_type == 1 ? PN.var_scale : PN.cut_scale);
+    EmbFwdArgs f{};
+    f.x = x; f.K = K; f.shift = prenorm + shift; f.scale = prenorm + scale; f.W1 = params + eo->W1; f.b1 = params + eo->b1;
+    f.img_w2 = chain_img_t(ws, eo->W2); f.bias2 = params + eo->b2; f.h1 = h1_out; f.out = out; f.M = M;
+    if (node_type == 0) { f.img_p[0] = chain_img_t(ws, P.conv[0].Wl); f.bias_p[0] = params + P.conv[0].bl; }
+    else if (node_type == 1) { f.img_p[0] = chain_img_t(ws, P.conv[0].Wr); f.img_p[1] = chain_img_t(ws, P.conv[1].Wr); f.P[1] = P1_out; }
+    else { f.img_p[0] = chain_img_t(ws, P.conv[2].Wl); f.bias_p[0] = params + P.conv[2].bl; }
+    f.P[0] = P0_out;
+    f.bf16_mlp = ws->bf16_mlp;
+    GCNN_TRY(tc_embed_forward16(f, st));
+    GCNN_CUDA_TRY(cudaStreamSynchronize(st));
+    return GCNN_OK;
+}
+
+int gcnn_embed_backward(gcnn_workspace* ws, const float* params, const float* prenorm, int node_type, const float* dP0,
+                        const float* dP1, const float* dXt, const float* out, const float* h1, const float* x, int64_t M,
+                        float* grads, void* stream) {
+    if (node_type < 0 || node_type > 2 || !dP0 || !dXt || !out || !h1 || !x || !grads || !prenorm || (node_type == 1 && !dP1)) {
+        set_error("gcnn_embed_backward: bad arguments");
+        return GCNN_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    GCNN_TRY(chain_op_ready(ws, params, 1, M, st));
+    DeviceGuard guard(ws->device);
+    const EmbOff* eo = node_type == 0 ? &P.cons : (node_type == 1 ? &P.var : &P.cut);
+    EmbBwdArgs g{};
+    g.dP0 = dP0; g.dP1 = node_type == 1 ? dP1 : nullptr; g.dXt = dXt; g.out = out; g.h1 = h1; g.x = x; g.M = M;
+    g.K = node_type == 0 ? GCNN_CONS_FEATS : (node_type == 1 ? GCNN_VAR_FEATS : GCNN_CUT_FEATS);
+    g.shift = prenorm + (node_type == 0 ? PN.cons_shift : (node_type == 1 ? PN.var_shift : PN.cut_shift));
+    g.scale = prenorm + (node_type == 0 ? PN.cons_scale : (node_type == 1 ? PN.var_scale : PN.cut_scale));
+    const int w0 = node_type == 0 ? P.conv[0].Wl : (node_type == 1 ? P.conv[0].Wr : P.conv[2].Wl);
+    const int w1 = node_type == 1 ? P.conv[1].Wr : -1;
+    const int bias0 = node_type == 1 ? 0 : 1;
+    g.img_p0 = chain_img_n(ws, w0); g.img_p1 = w1 >= 0 ? chain_img_n(ws, w1) : nullptr; g.img_w2 = chain_img_n(ws, eo->W2);
+    g.partials = ws->emb_partials[node_type];
+    g.bf16_mlp = ws->bf16_mlp;
+    int np = 0;
+    GCNN_TRY(tc_embed_backward(g, &np, st));
+    if (np > 0) {
+        const int EP = embed_backward_part_floats();
+        const float* ep = ws->emb_partials[node_type];
+        ReduceJob jobs[5];
+        int n = 0;
+        jobs[n++] = ReduceJob{ep, np, EP, D * D + (bias0 ? D : 0), w0, nullptr, nullptr};
+        if (w1 >= 0) jobs[n++] = ReduceJob{ep + (D * D + D), np, EP, D * D, w1, nullptr, nullptr};
+        jobs[n++] = ReduceJob{ep + 2 * (D * D + D), np, EP, D * D + D, eo->W2, nullptr, nullptr};
+        jobs[n++] = ReduceJob{ep + 3 * (D * D + D), np, EP, g.K * D, eo->W1, nullptr, nullptr};
+        jobs[n++] = ReduceJob{ep + 3 * (D * D + D) + D * D, np, EP, D, eo->b1, nullptr, nullptr};
+        GCNN_TRY(reduce_partials(jobs, n, grads, st));
+    }
+    GCNN_CUDA_TRY(cudaStreamSynchronize(st));
+    return GCNN_OK;
+}
+
+int gcnn_head_forward(const float* g, const float* w, const float* b, int64_t M, float* scores, void* stream) {
+    if (!g || !w || !b || !scores) { set_error("gcnn_head_forward: null argument"); return GCNN_INVALID; }
+    GCNN_TRY(head2_forward(g, w, b, scores, M, (cudaStream_t)stream));
+    GCNN_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    return GCNN_OK;
+}
+
+int gcnn_head_backward(gcnn_workspace* ws, const float* g, const float* w, const float* d_scores, int64_t M, float* dg_pre,
+                       float* dw_db, void* stream) {
+    if (!ws || !ws->arena || !ws->cap.training || !g || !w || !d_scores || !dg_pre || !dw_db) {
+        set_error("gcnn_head_backward: bad arguments (workspace reserved for training?)");
+        return GCNN_INVALID;
+    }
+    DeviceGuard guard(ws->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int n_parts = 0;
+    GCNN_TRY(head2_backward(g, w, d_scores, dg_pre, ws->partials[0], &n_parts, M, st));
+    const ReduceJob job{ws->partials[0], n_parts, D + 1, D + 1, 0, nullptr, dw_db};
+    GCNN_TRY(reduce_partials(&job, 1, nullptr, st));
+    GCNN_CUDA_TRY(cudaStreamSynchronize(st));
+    return GCNN_OK;
+}
+
 int gcnn_has_alt_paths(void) { return kAltPaths ? 1 : 0; }
 
 }  // extern "C"

@@ -343,6 +343,40 @@ int gcnn_edge_backward(gcnn_workspace* ws, const int32_t* ptr, const int32_t* ot
  * the A/B alternates, present only in -DGCNN_ALT_PATHS builds (GCNN_INVALID otherwise). */
 int gcnn_linear_forward(const float* X, const float* W, const float* b, int64_t m, int k, int relu, float* Y,
                         void* stream);
+/* The tensor-core node chains one at a time (gcnn_embed_fwd/bwd, gcnn_conv_fwd/bwd, gcnn_head_fwd/bwd), on
+ * caller-provided DEVICE arrays of 64 floats per row unless stated, with the weights taken from the flat parameter block.
+ * The workspace must be reserved (for training, for the backward ops).
+ *   conv = 0 / 1 / 2: constraints / variables / cuts receive (model.py:294-296).  gcnn_conv_forward (model.py:563,
+ *   570-573 after the segmented sum): C = H Wf + deg bf with deg[t] = deg_ptr[t+1] - deg_ptr[t] (deg_ptr NULL: 1),
+ *   U1 = relu([s_p C, Xt] Wo1 + bo1), Y = relu(U1 Wo2 + bo2), Pn = act(Y Wn + bn) for the layer that consumes Y (conv 0:
+ *   the next left projection; conv 1: the cuts' right projection, no bias; conv 2: the head's first layer, ReLU);
+ *   C_out / U1_out may be NULL; scores_out (conv 2 only, may be NULL): the head's Dense(1) on Pn, model.py:208.
+ *   gcnn_conv_backward is its adjoint: dP = gradient w.r.t. the pre-activation of the consuming layer; outputs
+ *   dXt (concat's right half), G = dC Wf^T, dR = s_f G cnt, and into grads (a flat block laid out like the parameters;
+ *   only these arrays are written) the gradients of Wn (+ bn), Wo2, bo2, Wo1, bo1, Wf, bf (bf weighted by deg). */
+int gcnn_conv_forward(gcnn_workspace* ws, const float* params, const float* prenorm, int conv, const float* H,
+                      const float* Xt, const int32_t* deg_ptr, int64_t M, float* C_out, float* U1_out, float* Y_out,
+                      float* Pn_out, float* scores_out, void* stream);
+int gcnn_conv_backward(gcnn_workspace* ws, const float* params, const float* prenorm, int conv, const float* dP,
+                       const float* Y, const float* U1, const float* C_in, const float* Xt, const float* H,
+                       const float* cnt, const int32_t* deg_ptr, int64_t M, float* dXt, float* G, float* dR,
+                       float* grads, void* stream);
+/*   node_type = 0 / 1 / 2: constraints / variables / cuts (x: [M, 4 / 14 / 6] raw features).  gcnn_embed_forward
+ *   (model.py:174-195, 377-381, 564-565): h1 = relu(((x + shift) scale) W1 + b1) (h1_out may be NULL),
+ *   out = relu(h1 W2 + b2), P0 = out Wp0 (+ bp0), P1 = out Wp1 -- the projections that read the embedding: constraints
+ *   conv 0 left (bias); variables conv 0 right and conv 1 right; cuts conv 2 left (bias).  gcnn_embed_backward: dP0 / dP1
+ *   gradients of those projections, dXt the gradient arriving through the concat that reads the embedding directly;
+ *   writes the gradients of Wp0 (+ bp0), Wp1, W2, b2, W1, b1 into grads. */
+int gcnn_embed_forward(gcnn_workspace* ws, const float* params, const float* prenorm, int node_type, const float* x,
+                       int64_t M, float* h1_out, float* out, float* P0_out, float* P1_out, void* stream);
+int gcnn_embed_backward(gcnn_workspace* ws, const float* params, const float* prenorm, int node_type, const float* dP0,
+                        const float* dP1, const float* dXt, const float* out, const float* h1, const float* x, int64_t M,
+                        float* grads, void* stream);
+/*   The head's Dense(1) as a launch of its own (the A/B path of option "head_in_chain"): scores = g w + b; backward:
+ *   dg_pre = d_scores w 1[g > 0], dw_db[0..63] = sum_m g[m] d_scores[m], dw_db[64] = sum_m d_scores[m]. */
+int gcnn_head_forward(const float* g, const float* w, const float* b, int64_t M, float* scores, void* stream);
+int gcnn_head_backward(gcnn_workspace* ws, const float* g, const float* w, const float* d_scores, int64_t M,
+                       float* dg_pre, float* dw_db, void* stream);
 /* 1 if the library was built with -DGCNN_ALT_PATHS (options "tensor_cores" / "fused" / "fused_backward" /
  * "bf16_forward" = 0 select the round-1 A/B alternates), 0 for the product build, where those options are fixed at 1. */
 int gcnn_has_alt_paths(void);

@@ -20,6 +20,7 @@ import torch
 
 import gcnn_oracle as orc
 from gcnn_cut_selector_b200 import batching, synth
+from gcnn_cut_selector_b200._lib import check
 
 pytestmark = pytest.mark.gpu
 
@@ -277,6 +278,174 @@ def test_linear_forward_op(model, m):
     ref = np.maximum(X.astype(np.float32).astype(np.float64) @ W.astype(np.float32).astype(np.float64)
                      + b.astype(np.float32).astype(np.float64), 0)
     assert rel_err(Y.cpu().numpy(), ref) <= 2e-6
+
+
+# ---- the tensor-core node chains one at a time (gcnn_conv_forward / backward, gcnn_embed_forward / backward,
+#      gcnn_head_forward / backward) against numpy fp64 restatements of model.py:174-208, 563-573 and their adjoints -------
+CONV_NAMES = ("cons_conv", "var_conv", "cut_conv")
+NEXT_LAYER = (("var_conv_feat_left", True, False), ("cut_conv_feat_right", False, False), ("out_1", True, True))  # name, bias, relu
+
+
+class _ChainOps:
+    """A model with the golden weights, non-trivial pre-norm values and a workspace reserved for training."""
+
+    def __init__(self, golden_dir):
+        from gcnn_cut_selector_b200 import GCNN
+        self.m = m = GCNN(device="cuda:0", seed=3)
+        m.restore_state(os.path.join(golden_dir, "state_stream.pkl"))
+        rng = np.random.default_rng(5)
+        with torch.no_grad():
+            m.flat_prenorm.copy_(torch.from_numpy(rng.uniform(0.6, 1.4, m.flat_prenorm.numel()).astype(np.float32)))
+        check(m._lib.gcnn_workspace_reserve(m._ws, 512, 512, 512, 1024, 1024, 1))
+        self.p64 = m.flat_params.detach().cpu().numpy().astype(np.float64)
+        self.pn64 = m.flat_prenorm.cpu().numpy().astype(np.float64)
+        self.table = {name: (shape, trainable, off) for name, shape, trainable, off in m._table}
+
+    def get(self, name):
+        shape, trainable, off = self.table[name]
+        return (self.p64 if trainable else self.pn64)[off:off + int(np.prod(shape))].reshape(shape)
+
+    def grad(self, flat, name):
+        shape, _, off = self.table[name]
+        return flat[off:off + int(np.prod(shape))].reshape(shape)
+
+    def dev(self, a, dtype=torch.float32):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(device="cuda:0", dtype=dtype)
+
+    def call(self, fn, *args):
+        m = self.m
+        ptr = lambda x: None if x is None else (x.data_ptr() if torch.is_tensor(x) else x)
+        with torch.cuda.device(m.device):
+            check(getattr(m._lib, fn)(*[ptr(a) for a in args], m._stream()))
+
+
+@pytest.fixture(scope="module")
+def chain_ops(golden_dir):
+    return _ChainOps(golden_dir)
+
+
+def l2_err(got, want):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    return np.linalg.norm(got - want) / max(np.linalg.norm(want), 1e-30)
+
+
+@pytest.mark.parametrize("M", [300, 128, 1])
+@pytest.mark.parametrize("conv", [0, 1, 2])
+def test_conv_chain_ops_match_numpy(chain_ops, conv, M):
+    o, rng = chain_ops, np.random.default_rng(10 * conv + M)
+    m, name = o.m, CONV_NAMES[conv]
+    Wf, bf = o.get(f"{name}_feat_final/kernel"), o.get(f"{name}_feat_final/bias")
+    Wo1, bo1 = o.get(f"{name}_out_1/kernel"), o.get(f"{name}_out_1/bias")
+    Wo2, bo2 = o.get(f"{name}_out_2/kernel"), o.get(f"{name}_out_2/bias")
+    nname, nbias, nrelu = NEXT_LAYER[conv]
+    Wn, bn = o.get(f"{nname}/kernel"), (o.get(f"{nname}/bias") if nbias else np.zeros(64))
+    s_p, s_f = float(o.get(f"{name}_post/prenorm/scale")[0]), float(o.get(f"{name}_final/prenorm/scale")[0])
+    H, Xt = rng.normal(size=(M, 64)).astype(np.float32), rng.normal(size=(M, 64)).astype(np.float32)
+    deg = rng.integers(0, 9, M)
+    deg_ptr = np.concatenate(([0], np.cumsum(deg))).astype(np.int32)
+    # forward
+    H64, Xt64 = H.astype(np.float64), Xt.astype(np.float64)
+    C = H64 @ Wf + deg[:, None] * bf
+    U1 = np.maximum(np.concatenate([s_p * C, Xt64], 1) @ Wo1 + bo1, 0)
+    Y = np.maximum(U1 @ Wo2 + bo2, 0)
+    Pn = Y @ Wn + bn
+    if nrelu:
+        Pn = np.maximum(Pn, 0)
+    dH, dXt_in, dptr = o.dev(H), o.dev(Xt), o.dev(deg_ptr, torch.int32)
+    outs = [torch.full((M, 64), float("nan"), device="cuda:0") for _ in range(4)]
+    scores = torch.full((M,), float("nan"), device="cuda:0") if conv == 2 else None
+    o.call("gcnn_conv_forward", m._ws, m.flat_params, m.flat_prenorm, conv, dH, dXt_in, dptr, M, *outs, scores)
+    for got, want, what in zip(outs, (C, U1, Y, Pn), ("C", "U1", "Y", "Pn")):
+        assert l2_err(got.cpu().numpy(), want) <= TOL, what
+    if conv == 2:
+        want = Pn @ o.get("out_2/kernel")[:, 0] + o.get("out_2/bias")[0]
+        assert l2_err(scores.cpu().numpy(), want) <= TOL
+    # backward: saved activations as the forward kernel wrote them (the ReLU masks are read from them)
+    Cs, U1s, Ys = (x.cpu().numpy().astype(np.float64) for x in outs[:3])
+    dP = rng.normal(size=(M, 64)).astype(np.float32)
+    cnt = rng.integers(0, 9, (M, 64)).astype(np.float32)
+    dP64 = dP.astype(np.float64)
+    dU2 = (dP64 @ Wn.T) * (Ys > 0)
+    dU1 = (dU2 @ Wo2.T) * (U1s > 0)
+    dcat = dU1 @ Wo1.T
+    dC, dXt = s_p * dcat[:, :64], dcat[:, 64:]
+    G = dC @ Wf.T
+    dR = s_f * G * cnt
+    want_g = {f"{nname}/kernel": Ys.T @ dP64, f"{name}_out_2/kernel": U1s.T @ dU2, f"{name}_out_2/bias": dU2.sum(0),
+              f"{name}_out_1/kernel": np.concatenate([s_p * Cs, Xt64], 1).T @ dU1, f"{name}_out_1/bias": dU1.sum(0),
+              f"{name}_feat_final/kernel": H64.T @ dC, f"{name}_feat_final/bias": (deg[:, None] * dC).sum(0)}
+    if nbias:
+        want_g[f"{nname}/bias"] = dP64.sum(0)
+    bouts = [torch.full((M, 64), float("nan"), device="cuda:0") for _ in range(3)]
+    grads = torch.zeros_like(m.flat_grads)
+    o.call("gcnn_conv_backward", m._ws, m.flat_params, m.flat_prenorm, conv, o.dev(dP), outs[2], outs[1], outs[0], dXt_in, dH,
+           o.dev(cnt), dptr, M, *bouts, grads)
+    for got, want, what in zip(bouts, (dXt, G, dR), ("dXt", "G", "dR")):
+        assert l2_err(got.cpu().numpy(), want) <= TOL, what
+    flat = grads.cpu().numpy()
+    for k, want in want_g.items():
+        assert l2_err(o.grad(flat, k), want) <= TOL, k
+
+
+@pytest.mark.parametrize("M", [300, 128, 1])
+@pytest.mark.parametrize("node_type", [0, 1, 2])
+def test_embedding_chain_ops_match_numpy(chain_ops, node_type, M):
+    o, rng = chain_ops, np.random.default_rng(100 + 10 * node_type + M)
+    m, name = o.m, ("cons", "var", "cut")[node_type]
+    K = (4, 14, 6)[node_type]
+    shift, scale = o.get(f"{name}_emb/prenorm/shift"), o.get(f"{name}_emb/prenorm/scale")
+    W1, b1, W2, b2 = (o.get(f"{name}_emb_{i}/{w}") for i in (1, 2) for w in ("kernel", "bias"))
+    proj = ((("cons_conv_feat_left", True),), (("cons_conv_feat_right", False), ("var_conv_feat_right", False)),
+            (("cut_conv_feat_left", True),))[node_type]
+    x = rng.normal(size=(M, K)).astype(np.float32)
+    xn = (x.astype(np.float64) + shift) * scale
+    h1 = np.maximum(xn @ W1 + b1, 0)
+    out = np.maximum(h1 @ W2 + b2, 0)
+    Ps = [out @ o.get(f"{n}/kernel") + (o.get(f"{n}/bias") if bias else 0.0) for n, bias in proj]
+    dx = o.dev(x)
+    outs = [torch.full((M, 64), float("nan"), device="cuda:0") for _ in range(2 + len(Ps))]
+    o.call("gcnn_embed_forward", m._ws, m.flat_params, m.flat_prenorm, node_type, dx, M, outs[0], outs[1], outs[2],
+           outs[3] if len(Ps) == 2 else None)
+    for got, want, what in zip(outs, [h1, out] + Ps, ("h1", "out", "P0", "P1")):
+        assert l2_err(got.cpu().numpy(), want) <= TOL, what
+    h1s, outs64 = outs[0].cpu().numpy().astype(np.float64), outs[1].cpu().numpy().astype(np.float64)
+    dPs = [rng.normal(size=(M, 64)).astype(np.float32) for _ in Ps]
+    dXt = rng.normal(size=(M, 64)).astype(np.float32)
+    dout = sum(d.astype(np.float64) @ o.get(f"{n}/kernel").T for d, (n, _) in zip(dPs, proj)) + dXt
+    g0 = dout * (outs64 > 0)
+    dh1 = (g0 @ W2.T) * (h1s > 0)
+    want_g = {f"{name}_emb_2/kernel": h1s.T @ g0, f"{name}_emb_2/bias": g0.sum(0), f"{name}_emb_1/kernel": xn.T @ dh1,
+              f"{name}_emb_1/bias": dh1.sum(0)}
+    for d, (n, bias) in zip(dPs, proj):
+        want_g[f"{n}/kernel"] = outs64.T @ d.astype(np.float64)
+        if bias:
+            want_g[f"{n}/bias"] = d.astype(np.float64).sum(0)
+    grads = torch.zeros_like(m.flat_grads)
+    o.call("gcnn_embed_backward", m._ws, m.flat_params, m.flat_prenorm, node_type, o.dev(dPs[0]),
+           o.dev(dPs[1]) if len(dPs) == 2 else None, o.dev(dXt), outs[1], outs[0], dx, M, grads)
+    flat = grads.cpu().numpy()
+    for k, want in want_g.items():
+        assert l2_err(o.grad(flat, k), want) <= TOL, k
+
+
+@pytest.mark.parametrize("M", [300, 1])
+def test_head_ops_match_numpy(chain_ops, M):
+    o, rng = chain_ops, np.random.default_rng(200 + M)
+    m = o.m
+    w, b = o.get("out_2/kernel")[:, 0], o.get("out_2/bias")
+    g = np.maximum(rng.normal(size=(M, 64)), 0).astype(np.float32)
+    ds = rng.normal(size=M).astype(np.float32)
+    dw, db = m.flat_params.detach()[o.table["out_2/kernel"][2]:], m.flat_params.detach()[o.table["out_2/bias"][2]:]
+    scores = torch.full((M,), float("nan"), device="cuda:0")
+    dg = o.dev(g)
+    o.call("gcnn_head_forward", dg, dw, db, M, scores)
+    assert l2_err(scores.cpu().numpy(), g.astype(np.float64) @ w + b[0]) <= TOL
+    dg_pre = torch.full((M, 64), float("nan"), device="cuda:0")
+    dw_db = torch.full((65,), float("nan"), device="cuda:0")
+    o.call("gcnn_head_backward", m._ws, dg, dw, o.dev(ds), M, dg_pre, dw_db)
+    ds64 = ds.astype(np.float64)
+    assert l2_err(dg_pre.cpu().numpy(), ds64[:, None] * w[None, :] * (g > 0)) <= TOL
+    assert l2_err(dw_db.cpu().numpy(), np.concatenate([g.astype(np.float64).T @ ds64, [ds64.sum()]])) <= TOL
 
 
 # ---- whole model against the golden fixtures (reference source over the TF shim) ----------------------------------------
