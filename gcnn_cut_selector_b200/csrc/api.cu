@@ -1137,10 +1137,10 @@ static int stage_batch(gcnn_workspace* ws, int slot, const gcnn_batch* hb, const
             if (col16) {
                 if (g.blk.n <= 0) { set_error("local column indices need valid per-sample counts"); return GCNN_INVALID; }
                 const uint16_t* c16_at = (const uint16_t*)section(col16_dev, col16, sizeof(uint16_t) * (size_t)E);
-                return expand_row_ptr(ptr_at, n_rows, E, dst, cs, c16_at, g.blk.off[left], g.blk.off[1], g.blk.n, dst + E);
+                return expand_row_ptr(ptr_at, n_rows, E, dst, cs, ws->flags + 1, c16_at, g.blk.off[left], g.blk.off[1], g.blk.n, dst + E);
             }
             GCNN_TRY(h2d(dst + E, src + E, sizeof(int32_t) * (size_t)E, cs));
-            return expand_row_ptr(ptr_at, n_rows, E, dst, cs);
+            return expand_row_ptr(ptr_at, n_rows, E, dst, cs, ws->flags + 1);
         }
         out = (const int32_t*)section(dst, src, sizeof(int32_t) * 2 * (size_t)E);
         return GCNN_OK;

@@ -180,9 +180,10 @@ int build_layout(const int32_t* keys, const int32_t* others, const float* feats,
 int64_t sort_hist_entries(int64_t E);
 // records.cu: rows[e] from a row pointer; with col16 also cols[e] = col16[e] + var_off[sample of row e] (left_off / var_off:
 // n_blocks + 1 node offsets of the samples)
+// err_flag: sticky error word (bit 1) for a pointer that is not monotone inside [0, n_edges]
 int expand_row_ptr(const int32_t* ptr_dev, int64_t n_rows, int64_t n_edges, int32_t* rows_dev, cudaStream_t st,
-                   const uint16_t* col16_dev = nullptr, const int32_t* left_off = nullptr, const int32_t* var_off = nullptr,
-                   int64_t n_blocks = 0, int32_t* cols_dev = nullptr);
+                   int32_t* err_flag, const uint16_t* col16_dev = nullptr, const int32_t* left_off = nullptr,
+                   const int32_t* var_off = nullptr, int64_t n_blocks = 0, int32_t* cols_dev = nullptr);
 
 // ---- packed sample records (records.cu) ------------------------------------------------------------------------------
 constexpr int REC_SECTIONS = 10;

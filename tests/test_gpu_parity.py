@@ -888,6 +888,11 @@ def test_row_pointer_host_batches_are_bit_identical(golden_dir):
     bad.row_ptrs[0][-1] -= 1
     with pytest.raises(InvalidArgumentError):
         b.score_host(bad)
+    bad = HostBatch(tuple(batches[0]), row_pointers=True)  # ends fine, not monotone inside: found on the device
+    bad.row_ptrs[0][5], bad.row_ptrs[0][6] = int(bad.row_ptrs[0][6]) + 3, int(bad.row_ptrs[0][5])
+    with pytest.raises(InvalidArgumentError):
+        b.score_host(bad)
+    np.testing.assert_array_equal(a.score_host(ha[0]), b.score_host(hb[0]))  # (the sticky error word was cleared)
 
 
 def test_head_in_the_last_chain_equals_the_separate_head_kernels(golden_dir):
