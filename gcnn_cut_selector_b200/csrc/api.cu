@@ -138,6 +138,7 @@ struct gcnn_workspace {
     struct Stage {
         float *cons = nullptr, *cef = nullptr, *var = nullptr, *cut = nullptr, *kef = nullptr, *targets = nullptr;
         float* targets_at = nullptr;     // where the staged batch's targets are (targets, or inside raw: gcnn_batch::packed)
+        int touched = 0, incomplete = 0; // a staging call ever started on this slot / the last one failed half way
         int32_t *cei = nullptr, *kei = nullptr;
         int32_t *crp = nullptr, *krp = nullptr;  // row pointers of a host batch's sorted edge lists (gcnn_batch::*_row_ptr)
         uint16_t *c16 = nullptr, *k16 = nullptr;  // ... and their sample-local column indices (gcnn_batch::*_col16)
@@ -1095,8 +1096,11 @@ static int stage_blocks(gcnn_workspace* ws, gcnn_workspace::Stage& g, const int3
 static int stage_batch(gcnn_workspace* ws, int slot, const gcnn_batch* hb, const float* targets_host) {
     gcnn_workspace::Stage& g = ws->stage[slot];
     cudaStream_t cs = ws->copy_st;
-    if (g.valid) GCNN_CUDA_TRY(cudaStreamWaitEvent(cs, g.consumed, 0));
-    if (g.valid) GCNN_CUDA_TRY(cudaEventSynchronize(g.staged));  // the previous copy out of blocks_host is done
+    if (g.touched) GCNN_CUDA_TRY(cudaStreamWaitEvent(cs, g.consumed, 0));
+    if (g.touched) GCNN_CUDA_TRY(cudaEventSynchronize(g.staged));  // the previous copy out of blocks_host is done
+    if (g.incomplete) GCNN_CUDA_TRY(cudaStreamSynchronize(cs));    // ... also the copies of a call that failed half way
+    g.touched = g.incomplete = 1;
+    g.valid = 0;  // (a staging call that fails half way leaves no batch behind)
     // the block structure first: the local column indices below are resolved against it on the device
     const int32_t* const counts[3] = {hb->sample_n_cons, hb->sample_n_vars, hb->sample_n_cuts};
     const int64_t totals[3] = {hb->n_cons, hb->n_vars, hb->n_cuts};
@@ -1106,7 +1110,11 @@ static int stage_batch(gcnn_workspace* ws, int slot, const gcnn_batch* hb, const
     const size_t pk_bytes = pk && hb->packed_bytes > 0 && hb->packed_bytes <= g.raw_cap ? (size_t)hb->packed_bytes : 0;
     // (in pieces: one uninterrupted multi-megabyte transfer delays the launches of the step that runs next to it -- same
     // box, 32-graph batch, end-to-end step 0.430 ms with 13 copies, 0.440 ms with one 8 MB copy)
-    static const size_t piece = [] { const char* e = getenv("GCNN_PACKED_PIECE_KB"); return (size_t)(e ? atoi(e) : 1024) << 10; }();
+    static const size_t piece = [] {
+        const char* e = getenv("GCNN_PACKED_PIECE_KB");
+        const int kb = e ? atoi(e) : 1024;
+        return (size_t)(kb > 0 ? kb : 1024) << 10;
+    }();
     for (size_t o = 0; o < pk_bytes; o += piece)
         GCNN_TRY(h2d(g.raw + o, pk + o, pk_bytes - o < piece ? pk_bytes - o : piece, cs));
     // device address of a host array: inside the packed copy when the array lies in the packed buffer, else `dev` after a
@@ -1159,6 +1167,7 @@ static int stage_batch(gcnn_workspace* ws, int slot, const gcnn_batch* hb, const
     g.meta.packed_bytes = 0;
     g.meta.cons_row_ptr = g.meta.cut_row_ptr = nullptr;
     g.meta.cons_col16 = g.meta.cut_col16 = nullptr;
+    g.incomplete = 0;
     g.valid = 1;
     return GCNN_OK;
 }
@@ -1828,8 +1837,11 @@ static int stage_records_impl(gcnn_workspace* ws, int slot, const void* const* r
     gcnn_workspace::Stage& g = ws->stage[slot];
     cudaStream_t cs = ws->copy_st;
     // the slot's previous consumer must be done with the batch tensors, and the previous assembly with descs_host
-    if (g.valid) GCNN_CUDA_TRY(cudaStreamWaitEvent(cs, g.consumed, 0));
-    if (g.valid) GCNN_CUDA_TRY(cudaEventSynchronize(g.staged));
+    if (g.valid || g.touched) GCNN_CUDA_TRY(cudaStreamWaitEvent(cs, g.consumed, 0));
+    if (g.valid || g.touched) GCNN_CUDA_TRY(cudaEventSynchronize(g.staged));
+    if (g.incomplete) GCNN_CUDA_TRY(cudaStreamSynchronize(cs));  // a host staging call that failed half way (stage_batch)
+    g.touched = 1;
+    g.incomplete = 0;
     g.targets_at = g.targets;
     AssembleOut out{g.cons, g.var, g.cut, g.targets, g.cef, g.kef, g.cei, g.kei, 0, 0};
     gcnn_batch meta;
