@@ -527,14 +527,30 @@ reduce_partials_kernel(const __grid_constant__ ReduceJobs jobs, float* __restric
     float total = 0.f;
     if (i < job.count) {
         const float* src = job.partials + i;
-        float s[4] = {};
+        // sixteen loads in flight per lane, then four, then one: 148 partials are 37 per lane = 2 + 1 + 1 rounds of memory
+        // latency (the last reduction of a step sits on its critical path; four at a time were ten rounds)
+        float s[16] = {};
         int p = lane;
-        for (; p + 3 * RED_LANES < job.n_parts; p += 4 * RED_LANES) {
+        for (; p + 15 * RED_LANES < job.n_parts; p += 16 * RED_LANES) {
+            float v[16];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) s[u] += src[(int64_t)(p + u * RED_LANES) * job.stride];
+            for (int u = 0; u < 16; ++u) v[u] = src[(int64_t)(p + u * RED_LANES) * job.stride];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) s[u] += v[u];
+        }
+        for (; p + 3 * RED_LANES < job.n_parts; p += 4 * RED_LANES) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = src[(int64_t)(p + u * RED_LANES) * job.stride];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) s[u] += v[u];
         }
         for (; p < job.n_parts; p += RED_LANES) s[0] += src[(int64_t)p * job.stride];
-        total = (s[0] + s[1]) + (s[2] + s[3]);
+#pragma unroll
+        for (int w = 8; w >= 1; w >>= 1)
+#pragma unroll
+            for (int u = 0; u < w; ++u) s[u] += s[u + w];  // fixed pairwise order
+        total = s[0];
     }
     red[threadIdx.x] = total;
     __syncthreads();

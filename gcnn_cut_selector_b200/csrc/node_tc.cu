@@ -30,7 +30,17 @@ pack_weights_kernel(const float* __restrict__ params, const int* __restrict__ bl
     __shared__ float Wb[64][65];
     const float* W = params + block_offsets[blockIdx.x];
     float* img = images + (int64_t)blockIdx.x * TC_IMG_FLOATS;
-    for (int i = threadIdx.x; i < 64 * 64; i += 256) Wb[i >> 6][i & 63] = W[i];
+    {   // all sixteen loads of a thread in flight at once: the rolled loop (load, store, branch) paid one cold-memory
+        // latency per iteration, 16 in a row -- most of the kernel's 10 us at the head of the step
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __ldg(W + threadIdx.x + 256 * j);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int i = threadIdx.x + 256 * j;
+            Wb[i >> 6][i & 63] = v[j];
+        }
+    }
     __syncthreads();
 #ifdef GCNN_ALT_PATHS  // the 3xTF32 images are read by the A/B alternates only
     for (int i = threadIdx.x + 256 * blockIdx.y; i < 64 * 16; i += 256 * PACK_SPLIT) {
