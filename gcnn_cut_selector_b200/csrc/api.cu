@@ -412,7 +412,7 @@ static int upload_blocks(gcnn_workspace* ws, const gcnn_batch* b, cudaStream_t s
     int32_t* h = ws->blk_pin[slot];
     const int32_t* counts[3] = {b->sample_n_cons, b->sample_n_vars, b->sample_n_cuts};
     const int64_t totals[3] = {b->n_cons, b->n_vars, b->n_cuts};
-    const int64_t n = b->n_samples, stride = MAX_RECORDS + 1;
+    const int64_t n = b->n_samples, stride = n + 1;  // the three arrays back to back: ONE copy
     BlockInfo bi;
     for (int t = 0; t < 3; ++t) {
         int64_t run = 0;
@@ -428,9 +428,7 @@ static int upload_blocks(gcnn_workspace* ws, const gcnn_batch* b, cudaStream_t s
         bi.off[t] = ws->blk_dev + t * stride;
     }
     bi.n = n;
-    for (int t = 0; t < 3; ++t)
-        GCNN_CUDA_TRY(cudaMemcpyAsync(ws->blk_dev + t * stride, h + t * stride, sizeof(int32_t) * (size_t)(n + 1),
-                                      cudaMemcpyHostToDevice, st));
+    GCNN_CUDA_TRY(cudaMemcpyAsync(ws->blk_dev, h, sizeof(int32_t) * (size_t)(3 * stride), cudaMemcpyHostToDevice, st));
     GCNN_CUDA_TRY(cudaEventRecord(ws->blk_ev[slot], st));
     out = bi;
     return GCNN_OK;
@@ -618,14 +616,15 @@ static int forward_impl(gcnn_workspace* ws, const float* p, const float* pn, con
     ws->head_in_chain = 0;
 
     cudaStream_t s1 = aux_stream(ws, 0, st), s2 = aux_stream(ws, 1, st);
-    // block structure first: the offset arrays are read by kernels on every stream forked below
-    if (staged_blocks) ws->cur_blk = ws->use_blocks ? *staged_blocks : BlockInfo();
-    else GCNN_TRY(upload_blocks(ws, b, st, ws->cur_blk));
-    const BlockInfo& bi = ws->cur_blk;
-
     // F1: edge layouts on an auxiliary stream, concurrent with the embeddings.  conv 0 reduces by constraint, conv 1
     // by variable (both over constraint edges), conv 2 by cut; the opposite grouping serves the backward pass.
     GCNN_TRY(stream_edge(ws, st, s1));
+    // block structure first, on the layout stream: the offset arrays are read by the layout builds (this stream and the
+    // one forked from it below) and by the block edge kernels, which wait for a layout event -- not by the embeddings,
+    // so the upload (it used to be three small copies at the head of the main stream) no longer delays them
+    if (staged_blocks) ws->cur_blk = ws->use_blocks ? *staged_blocks : BlockInfo();
+    else GCNN_TRY(upload_blocks(ws, b, s1, ws->cur_blk));
+    const BlockInfo& bi = ws->cur_blk;
     GCNN_CUDA_TRY(cudaMemsetAsync(ws->flags + 2, 0, 12 * sizeof(int32_t), s1));  // per-layout "unsorted" [2..5] and "long rows" [10..13] words
     const bool cons_sorted = (b->flags & GCNN_BATCH_CONS_EDGES_SORTED) != 0;
     const bool cuts_sorted = (b->flags & GCNN_BATCH_CUT_EDGES_SORTED) != 0;
