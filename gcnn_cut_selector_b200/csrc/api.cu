@@ -1697,6 +1697,7 @@ int gcnn_forward_backward(gcnn_workspace* ws, const float* params, const float* 
     if (!ws) { set_error("null workspace"); return GCNN_INVALID; }
     DeviceGuard guard(ws->device);
     GCNN_TRY(check_batch(ws, batch, 1));
+    if ((!targets && batch->n_cuts > 0) || !grads_out) { set_error("gcnn_forward_backward: null targets / gradient buffer"); return GCNN_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
     float* scores = scores_out ? scores_out : ws->scores;
     float* loss_out = loss_sum_out ? loss_sum_out : ws->loss_sum;
@@ -2297,8 +2298,9 @@ int gcnn_conv_forward(gcnn_workspace* ws, const float* params, const float* pren
                       float* Pn_out, float* scores_out, void* stream) {
     if (conv < 0 || conv > 2 || !H || !Xt || !Y_out || !Pn_out || !prenorm) { set_error("gcnn_conv_forward: bad arguments"); return GCNN_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
-    GCNN_TRY(chain_op_ready(ws, params, 0, M, st));
+    if (!ws) { set_error("null workspace"); return GCNN_INVALID; }
     DeviceGuard guard(ws->device);
+    GCNN_TRY(chain_op_ready(ws, params, 0, M, st));
     const ConvOff& o = P.conv[conv];
     const NextLayer nx = conv_next(conv);
     ConvFwdArgs c{};
@@ -2324,8 +2326,9 @@ int gcnn_conv_backward(gcnn_workspace* ws, const float* params, const float* pre
         return GCNN_INVALID;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    GCNN_TRY(chain_op_ready(ws, params, 1, M, st));
+    if (!ws) { set_error("null workspace"); return GCNN_INVALID; }
     DeviceGuard guard(ws->device);
+    GCNN_TRY(chain_op_ready(ws, params, 1, M, st));
     const ConvOff& o = P.conv[conv];
     const NextLayer nx = conv_next(conv);
     ConvBwdArgs c{};
@@ -2358,8 +2361,9 @@ int gcnn_embed_forward(gcnn_workspace* ws, const float* params, const float* pre
         return GCNN_INVALID;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    GCNN_TRY(chain_op_ready(ws, params, 0, M, st));
+    if (!ws) { set_error("null workspace"); return GCNN_INVALID; }
     DeviceGuard guard(ws->device);
+    GCNN_TRY(chain_op_ready(ws, params, 0, M, st));
     const EmbOff* eo = node_type == 0 ? &P.cons : (node_type == 1 ? &P.var : &P.cut);
     const int K = node_type == 0 ? GCNN_CONS_FEATS : (node_type == 1 ? GCNN_VAR_FEATS : GCNN_CUT_FEATS);
     const int shift = node_type == 0 ? PN.cons_shift : (node_type == 1 ? PN.var_shift : PN.cut_shift);
@@ -2385,8 +2389,9 @@ int gcnn_embed_backward(gcnn_workspace* ws, const float* params, const float* pr
         return GCNN_INVALID;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    GCNN_TRY(chain_op_ready(ws, params, 1, M, st));
+    if (!ws) { set_error("null workspace"); return GCNN_INVALID; }
     DeviceGuard guard(ws->device);
+    GCNN_TRY(chain_op_ready(ws, params, 1, M, st));
     const EmbOff* eo = node_type == 0 ? &P.cons : (node_type == 1 ? &P.var : &P.cut);
     EmbBwdArgs g{};
     g.dP0 = dP0; g.dP1 = node_type == 1 ? dP1 : nullptr; g.dXt = dXt; g.out = out; g.h1 = h1; g.x = x; g.M = M;
