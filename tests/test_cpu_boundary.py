@@ -162,3 +162,11 @@ def test_host_batch_packing_and_local_columns(monkeypatch):
     ht = HostBatch(tuple(totals), row_pointers=True)
     assert ht.row_ptrs[0] is not None and ht.col16 == [None, None] and ht.batch.n_samples == 0
     assert HostBatch(tuple(batch)).row_ptrs == [None, None]  # default: only lists of >= 128 k edges
+
+
+def test_integration_stub_declares_the_same_batch_struct():
+    """INTEGRATION.md's ctypes stub (what a maintainer of the reference would paste) lists gcnn_batch's fields exactly as the
+    binding does -- a shorter struct would make the library read past the caller's memory."""
+    txt = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blk = txt[txt.index("class Batch(C.Structure):"):txt.index("lib.gcnn_batch_bytes.restype")]
+    assert re.findall(r'\("(\w+)", C\.', blk) == [f for f, _ in _lib.Batch._fields_]
