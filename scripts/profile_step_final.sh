@@ -13,7 +13,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ncu --set full --clock-control none --import-source on --launch-skip 130 --launch-count 100 -f -o /tmp/prof_r2 $BENCH > gpurun_out/r2f_ncu_full.log 2>&1
 ncu -i /tmp/prof_r2.ncu-rep --page raw --csv > gpurun_out/r2f_step_raw.csv 2>/dev/null
 python scripts/ncu_step_summary.py gpurun_out/r2f_step_raw.csv gpurun_out/r2f_step > /dev/null
-python scripts/ncu_kernel_table.py gpurun_out/r2f_step_raw.csv > gpurun_out/r2f_step_stalls.md 2>/dev/null
+python scripts/ncu_kernel_table.py gpurun_out/r2f_step_raw.csv gpurun_out/r2f_step_stalls.md "whole training step: pipes, shared memory, stall reasons"
 python scripts/launch_summary.py gpurun_out/r2f_step_launches.csv > gpurun_out/r2f_step_launches_summary.txt
 ls -la /tmp/prof_r2.ncu-rep gpurun_out/ | tail -20
 tail -3 gpurun_out/r2f_tests.log
